@@ -1,0 +1,307 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see glam_mini.hpp header). C ABI over the CPU restatement so that tests/
+// (ctypes), __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs can call it. Batched
+// entry points take the same SoA layout the GPU C-ABI (include/bam3d_gpu.h) takes and split the batch
+// statically over `nthreads` std::threads (the reference itself is single-threaded; threads only replicate it).
+#include <atomic>
+#include <cstring>
+#include <thread>
+#include <vector>
+#include "bam3d_oracle.hpp"
+#include "broad_oracle.hpp"
+
+using namespace orc;
+
+namespace {
+
+struct ShapeTable {
+    const uint8_t* kind; const float* params; const float* xform; const uint32_t* mesh_id;
+    const float* mesh_verts; const uint32_t* mesh_offsets;
+    Shape shape(uint32_t i) const {
+        Shape s; s.kind = kind[i]; s.p0 = params[4 * i]; s.p1 = params[4 * i + 1]; s.p2 = params[4 * i + 2];
+        if (s.kind == POLYHEDRON) {
+            uint32_t m = mesh_id[i];
+            s.verts = mesh_verts + 3 * (size_t)mesh_offsets[m];
+            s.nverts = mesh_offsets[m + 1] - mesh_offsets[m];
+        }
+        return s;
+    }
+    Mat4 mat(uint32_t i) const { return Mat4::from_cols_array(xform + 16 * (size_t)i); }
+};
+
+template <class F>
+void parallel_for(uint64_t n, int nthreads, F f) {
+    if (nthreads <= 1 || n < 64) { f(0, n, 0); return; }
+    std::vector<std::thread> th;
+    uint64_t chunk = (n + nthreads - 1) / nthreads;
+    for (int t = 0; t < nthreads; ++t) {
+        uint64_t b = t * chunk, e = std::min<uint64_t>(n, b + chunk);
+        if (b >= e) break;
+        th.emplace_back([=] { f(b, e, t); });
+    }
+    for (auto& x : th) x.join();
+}
+
+void put_contact(float* out, const Contact& c) {
+    out[0] = c.normal.x; out[1] = c.normal.y; out[2] = c.normal.z; out[3] = c.penetration_depth;
+    out[4] = c.contact_point.x; out[5] = c.contact_point.y; out[6] = c.contact_point.z; out[7] = c.time_of_impact;
+}
+
+template <class R> void sort_hits(std::vector<std::pair<uint32_t, R>>& h) {
+    std::stable_sort(h.begin(), h.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+}
+
+}  // namespace
+
+extern "C" {
+
+struct orc_settings { float distance_tolerance, continuous_tolerance, epa_tolerance; uint32_t max_iterations; };
+struct orc_counters { uint64_t support_calls, gjk_iterations, epa_iterations; uint32_t max_faces, max_verts, max_edges, pad; };
+
+static void merge(orc_counters* dst, const std::vector<Counters>& cs) {
+    if (!dst) return;
+    std::memset(dst, 0, sizeof(*dst));
+    for (auto& c : cs) {
+        dst->support_calls += c.support_calls; dst->gjk_iterations += c.gjk_iterations; dst->epa_iterations += c.epa_iterations;
+        if (c.max_faces > dst->max_faces) dst->max_faces = c.max_faces;
+        if (c.max_verts > dst->max_verts) dst->max_verts = c.max_verts;
+        if (c.max_edges > dst->max_edges) dst->max_edges = c.max_edges;
+    }
+}
+
+static GJK make_gjk(const orc_settings* s) {
+    return s ? GJK(s->distance_tolerance, s->continuous_tolerance, s->epa_tolerance, s->max_iterations) : GJK();
+}
+
+// GJK::intersect over a batch (gjk/mod.rs:74-113). out_hit[i] in {0,1}; out_status[i] = orc::Status.
+void orc_gjk_intersect_batch(const uint8_t* kind, const float* params, const float* xform, const uint32_t* mesh_id,
+                             const float* mesh_verts, const uint32_t* mesh_offsets, const uint32_t* pairs, uint64_t n,
+                             const orc_settings* settings, uint8_t* out_hit, uint8_t* out_status, int nthreads,
+                             orc_counters* counters) {
+    ShapeTable T{kind, params, xform, mesh_id, mesh_verts, mesh_offsets};
+    GJK gjk = make_gjk(settings);
+    std::vector<Counters> cs(nthreads > 0 ? nthreads : 1);
+    parallel_for(n, nthreads, [&](uint64_t b, uint64_t e, int t) {
+        for (uint64_t i = b; i < e; ++i) {
+            uint32_t l = pairs[2 * i], r = pairs[2 * i + 1];
+            Simplex s; Status st;
+            bool hit = gjk.intersect(T.shape(l), T.mat(l), T.shape(r), T.mat(r), s, &st, counters ? &cs[t] : nullptr);
+            out_hit[i] = hit ? 1 : 0;
+            if (out_status) out_status[i] = (uint8_t)st;
+        }
+    });
+    merge(counters, cs);
+}
+
+// GJK::intersection over a batch (gjk/mod.rs:317-341). strategy: 0 FullResolution, 1 CollisionOnly.
+// out_contact: 8 floats per pair {normal xyz, depth, point xyz, toi}; zero-filled on miss.
+void orc_gjk_contact_batch(const uint8_t* kind, const float* params, const float* xform, const uint32_t* mesh_id,
+                           const float* mesh_verts, const uint32_t* mesh_offsets, const uint32_t* pairs, uint64_t n,
+                           const orc_settings* settings, int strategy, float* out_contact, uint8_t* out_hit,
+                           uint8_t* out_status, int nthreads, orc_counters* counters) {
+    ShapeTable T{kind, params, xform, mesh_id, mesh_verts, mesh_offsets};
+    GJK gjk = make_gjk(settings);
+    std::vector<Counters> cs(nthreads > 0 ? nthreads : 1);
+    parallel_for(n, nthreads, [&](uint64_t b, uint64_t e, int t) {
+        for (uint64_t i = b; i < e; ++i) {
+            uint32_t l = pairs[2 * i], r = pairs[2 * i + 1];
+            Contact c; Status st;
+            bool hit = gjk.intersection((CollisionStrategy)strategy, T.shape(l), T.mat(l), T.shape(r), T.mat(r), c, &st,
+                                        counters ? &cs[t] : nullptr);
+            out_hit[i] = hit ? 1 : 0;
+            if (out_status) out_status[i] = (uint8_t)st;
+            if (hit) put_contact(out_contact + 8 * i, c); else std::memset(out_contact + 8 * i, 0, 32);
+        }
+    });
+    merge(counters, cs);
+}
+
+// GJK::distance over a batch (gjk/mod.rs:232-280). out_some[i]=1 for Some; out_ref = dp-d0 (what the reference
+// returns), out_geo = sqrt(d.d).
+void orc_gjk_distance_batch(const uint8_t* kind, const float* params, const float* xform, const uint32_t* mesh_id,
+                            const float* mesh_verts, const uint32_t* mesh_offsets, const uint32_t* pairs, uint64_t n,
+                            const orc_settings* settings, float* out_ref, float* out_geo, uint8_t* out_some,
+                            uint8_t* out_status, int nthreads, orc_counters* counters) {
+    ShapeTable T{kind, params, xform, mesh_id, mesh_verts, mesh_offsets};
+    GJK gjk = make_gjk(settings);
+    std::vector<Counters> cs(nthreads > 0 ? nthreads : 1);
+    parallel_for(n, nthreads, [&](uint64_t b, uint64_t e, int t) {
+        for (uint64_t i = b; i < e; ++i) {
+            uint32_t l = pairs[2 * i], r = pairs[2 * i + 1];
+            float rv = 0.f, geo = 0.f; Status st;
+            bool some = gjk.distance(T.shape(l), T.mat(l), T.shape(r), T.mat(r), rv, geo, st, counters ? &cs[t] : nullptr);
+            out_some[i] = some ? 1 : 0; out_ref[i] = some ? rv : 0.f; out_geo[i] = some ? geo : 0.f;
+            if (out_status) out_status[i] = (uint8_t)st;
+        }
+    });
+    merge(counters, cs);
+}
+
+// GJK::intersection_time_of_impact over a batch (gjk/mod.rs:130-217). xform0 = start transforms, xform1 = end.
+void orc_gjk_toi_batch(const uint8_t* kind, const float* params, const float* xform0, const float* xform1,
+                       const uint32_t* mesh_id, const float* mesh_verts, const uint32_t* mesh_offsets,
+                       const uint32_t* pairs, uint64_t n, const orc_settings* settings, uint32_t toi_cap,
+                       float* out_contact, uint8_t* out_hit, uint8_t* out_status, int nthreads, orc_counters* counters) {
+    ShapeTable T0{kind, params, xform0, mesh_id, mesh_verts, mesh_offsets};
+    ShapeTable T1{kind, params, xform1, mesh_id, mesh_verts, mesh_offsets};
+    GJK gjk = make_gjk(settings);
+    if (toi_cap) gjk.toi_iteration_cap = toi_cap;
+    std::vector<Counters> cs(nthreads > 0 ? nthreads : 1);
+    parallel_for(n, nthreads, [&](uint64_t b, uint64_t e, int t) {
+        for (uint64_t i = b; i < e; ++i) {
+            uint32_t l = pairs[2 * i], r = pairs[2 * i + 1];
+            Contact c; Status st;
+            bool hit = gjk.intersection_time_of_impact(T0.shape(l), T0.mat(l), T1.mat(l), T0.shape(r), T0.mat(r), T1.mat(r),
+                                                       c, st, counters ? &cs[t] : nullptr);
+            out_hit[i] = hit ? 1 : 0;
+            if (out_status) out_status[i] = (uint8_t)st;
+            if (hit) put_contact(out_contact + 8 * i, c); else std::memset(out_contact + 8 * i, 0, 32);
+        }
+    });
+    merge(counters, cs);
+}
+
+// ---- single-call helpers used by the parity / golden tests -------------------------------------------------
+void orc_support_point(uint8_t kind, const float* params4, const float* verts, uint32_t nverts, const float* dir3,
+                       const float* xform16, float* out3) {
+    Shape s; s.kind = kind; s.p0 = params4[0]; s.p1 = params4[1]; s.p2 = params4[2]; s.verts = verts; s.nverts = nverts;
+    Vec3 p = support_point(s, Vec3(dir3[0], dir3[1], dir3[2]), Mat4::from_cols_array(xform16));
+    out3[0] = p.x; out3[1] = p.y; out3[2] = p.z;
+}
+void orc_mat4_from_srt(const float* scale3, const float* quat4, const float* trans3, float* out16) {
+    Mat4::from_scale_rotation_translation(Vec3(scale3[0], scale3[1], scale3[2]), Quat(quat4[0], quat4[1], quat4[2], quat4[3]),
+                                          Vec3(trans3[0], trans3[1], trans3[2])).to_cols_array(out16);
+}
+void orc_mat4_inverse(const float* in16, float* out16) { Mat4::from_cols_array(in16).inverse().to_cols_array(out16); }
+void orc_quat_from_rotation_z(float angle, float* out4) { Quat q = Quat::from_rotation_z(angle); out4[0] = q.x; out4[1] = q.y; out4[2] = q.z; out4[3] = q.w; }
+void orc_translation_interpolate(const float* a16, const float* b16, float amount, float* out16) {
+    translation_interpolate(Mat4::from_cols_array(a16), Mat4::from_cols_array(b16), amount).to_cols_array(out16);
+}
+
+// ComputeBound<Aabb3> for each primitive (sphere.rs:27-34, cuboid.rs:66-73, cylinder.rs:64-71, capsule.rs:51-58,
+// quad.rs:62-69, polyhedron.rs:84-86 + :357-361, primitive3.rs:83-96) followed by Aabb::transform (aabb3.rs:89-96).
+void orc_world_aabb_batch(const uint8_t* kind, const float* params, const float* xform, const uint32_t* mesh_id,
+                          const float* mesh_verts, const uint32_t* mesh_offsets, uint64_t n, float* out6) {
+    ShapeTable T{kind, params, xform, mesh_id, mesh_verts, mesh_offsets};
+    for (uint64_t i = 0; i < n; ++i) {
+        Shape s = T.shape((uint32_t)i);
+        Aabb3 b;
+        switch (s.kind) {
+            case PARTICLE: b = Aabb3::zero(); break;
+            case QUAD: b = Aabb3(Vec3(-s.p0, -s.p1, 0.f), Vec3(s.p0, s.p1, 0.f)); break;
+            case SPHERE: b = Aabb3(Vec3::splat(-s.p0), Vec3::splat(s.p0)); break;
+            case CUBOID: b = Aabb3(-Vec3(s.p0, s.p1, s.p2), Vec3(s.p0, s.p1, s.p2)); break;
+            case CYLINDER: b = Aabb3(Vec3(-s.p1, -s.p0, -s.p1), Vec3(s.p1, s.p0, s.p1)); break;
+            case CAPSULE: b = Aabb3(Vec3(-s.p1, -s.p0 - s.p1, -s.p1), Vec3(s.p1, s.p0 + s.p1, s.p1)); break;
+            case POLYHEDRON:
+                b = Aabb3::zero();
+                for (uint32_t k = 0; k < s.nverts; ++k) b = b.grow(Vec3(s.verts[3 * k], s.verts[3 * k + 1], s.verts[3 * k + 2]));
+                break;
+        }
+        Aabb3 w = b.transform(T.mat((uint32_t)i));
+        float* o = out6 + 6 * i;
+        o[0] = w.min.x; o[1] = w.min.y; o[2] = w.min.z; o[3] = w.max.x; o[4] = w.max.y; o[5] = w.max.z;
+    }
+}
+
+// ---- broad phase ---------------------------------------------------------------------------------------------
+static Aabb3 box6(const float* a) { Aabb3 b; b.min = Vec3(a[0], a[1], a[2]); b.max = Vec3(a[3], a[4], a[5]); return b; }
+
+// SweepAndPrune3::find_collider_pairs (sweep_prune.rs:69-128). aabbs: n x {min xyz, max xyz}, NOT modified;
+// out_perm[k] = original index at sorted position k; pairs are (i, j) indices into the sorted order.
+// Returns the number of pairs found (may exceed pair_capacity; only the first pair_capacity are written).
+uint64_t orc_sap_find_pairs(const float* aabbs, uint64_t n, int32_t* inout_axis, uint32_t* out_perm, uint32_t* out_pairs,
+                            uint64_t pair_capacity) {
+    std::vector<Aabb3> b(n);
+    for (uint64_t i = 0; i < n; ++i) b[i] = box6(aabbs + 6 * i);
+    SweepAndPrune3 sap; sap.sweep_axis = *inout_axis;
+    std::vector<uint32_t> perm;
+    auto pairs = sap.find_collider_pairs(b, &perm);
+    *inout_axis = sap.sweep_axis;
+    if (out_perm) std::memcpy(out_perm, perm.data(), n * sizeof(uint32_t));
+    uint64_t w = std::min<uint64_t>(pairs.size(), pair_capacity);
+    for (uint64_t i = 0; i < w; ++i) { out_pairs[2 * i] = pairs[i].first; out_pairs[2 * i + 1] = pairs[i].second; }
+    return pairs.size();
+}
+
+// Variance3 alone (sweep_prune.rs:192-215) over boxes in the given order.
+int32_t orc_sap_variance_axis(const float* aabbs, uint64_t n) {
+    Variance3 v; v.clear();
+    for (uint64_t i = 0; i < n; ++i) v.add_bound(box6(aabbs + 6 * i));
+    return v.compute_axis((float)n);
+}
+
+struct orc_dbvt { Dbvt tree; };
+orc_dbvt* orc_dbvt_build(const float* aabbs, const float* fat_aabbs, uint64_t n) {
+    orc_dbvt* t = new orc_dbvt();
+    for (uint64_t i = 0; i < n; ++i) {
+        TreeValue v; v.bound = box6(aabbs + 6 * i); v.fat = box6((fat_aabbs ? fat_aabbs : aabbs) + 6 * i);
+        t->tree.insert(v);
+    }
+    t->tree.refit();
+    return t;
+}
+void orc_dbvt_free(orc_dbvt* t) { delete t; }
+int32_t orc_dbvt_stack_overflow(orc_dbvt* t) { return t->tree.stack_overflow ? 1 : 0; }
+
+
+// DiscreteVisitor query (visitor.rs:57-90). Results sorted by value index. Returns hit count.
+uint64_t orc_dbvt_query_aabb(orc_dbvt* t, const float* q6, uint32_t* out_values, uint64_t cap) {
+    DiscreteVisitor vis; vis.bound = box6(q6);
+    std::vector<std::pair<uint32_t, uint8_t>> h;
+    t->tree.query_for_indices<DiscreteVisitor, uint8_t>(vis, h);
+    sort_hits(h);
+    for (uint64_t i = 0; i < h.size() && i < cap; ++i) out_values[i] = h[i].first;
+    return h.size();
+}
+// ContinuousVisitor<Ray> query == query_ray (util.rs:114-129). out_points: 3 floats per hit.
+uint64_t orc_dbvt_query_ray(orc_dbvt* t, const float* ray6, uint32_t* out_values, float* out_points, uint64_t cap) {
+    ContinuousRayVisitor vis; vis.ray = Ray(Vec3(ray6[0], ray6[1], ray6[2]), Vec3(ray6[3], ray6[4], ray6[5]));
+    std::vector<std::pair<uint32_t, Vec3>> h;
+    t->tree.query_for_indices<ContinuousRayVisitor, Vec3>(vis, h);
+    sort_hits(h);
+    for (uint64_t i = 0; i < h.size() && i < cap; ++i) {
+        out_values[i] = h[i].first; out_points[3 * i] = h[i].second.x; out_points[3 * i + 1] = h[i].second.y; out_points[3 * i + 2] = h[i].second.z;
+    }
+    return h.size();
+}
+// query_ray_closest (util.rs:77-103). Returns 1 if a value was hit.
+int32_t orc_dbvt_query_ray_closest(orc_dbvt* t, const float* ray6, uint32_t* out_value, float* out_point3, float* out_t) {
+    uint32_t v = 0; Vec3 p; float tt = 0.f;
+    bool ok = query_ray_closest(t->tree, Ray(Vec3(ray6[0], ray6[1], ray6[2]), Vec3(ray6[3], ray6[4], ray6[5])), v, p, tt);
+    if (ok) { *out_value = v; out_point3[0] = p.x; out_point3[1] = p.y; out_point3[2] = p.z; *out_t = tt; }
+    return ok ? 1 : 0;
+}
+// Frustum::from_mat4 (frustum.rs:46-75): out 6 planes x {n xyz, d} in the order left,right,bottom,top,near,far.
+int32_t orc_frustum_from_mat4(const float* m16, float* out24) {
+    Frustum f;
+    if (!Frustum::from_mat4(Mat4::from_cols_array(m16), f)) return 0;
+    const Plane* ps[6] = {&f.left, &f.right, &f.bottom, &f.top, &f.near_, &f.far_};
+    for (int i = 0; i < 6; ++i) { out24[4 * i] = ps[i]->n.x; out24[4 * i + 1] = ps[i]->n.y; out24[4 * i + 2] = ps[i]->n.z; out24[4 * i + 3] = ps[i]->d; }
+    return 1;
+}
+void orc_perspective_rh_gl(float fov, float aspect, float zn, float zf, float* out16) { Mat4::perspective_rh_gl(fov, aspect, zn, zf).to_cols_array(out16); }
+// FrustumVisitor query (visitor.rs:99-134). planes24 in the order left,right,bottom,top,near,far.
+uint64_t orc_dbvt_query_frustum(orc_dbvt* t, const float* planes24, uint32_t* out_values, uint8_t* out_relation, uint64_t cap) {
+    FrustumVisitor vis;
+    Plane* ps[6] = {&vis.frustum.left, &vis.frustum.right, &vis.frustum.bottom, &vis.frustum.top, &vis.frustum.near_, &vis.frustum.far_};
+    for (int i = 0; i < 6; ++i) *ps[i] = Plane(Vec3(planes24[4 * i], planes24[4 * i + 1], planes24[4 * i + 2]), planes24[4 * i + 3]);
+    std::vector<std::pair<uint32_t, uint8_t>> h;
+    t->tree.query_for_indices<FrustumVisitor, uint8_t>(vis, h);
+    sort_hits(h);
+    for (uint64_t i = 0; i < h.size() && i < cap; ++i) { out_values[i] = h[i].first; out_relation[i] = h[i].second; }
+    return h.size();
+}
+// DbvtBroadPhase::find_collider_pairs (broad_phase/dbvt.rs:26-63).
+uint64_t orc_dbvt_find_collider_pairs(orc_dbvt* t, const uint8_t* dirty, uint32_t* out_pairs, uint64_t cap) {
+    auto pr = dbvt_find_collider_pairs(t->tree, dirty);
+    for (uint64_t i = 0; i < pr.size() && i < cap; ++i) { out_pairs[2 * i] = pr[i].first; out_pairs[2 * i + 1] = pr[i].second; }
+    return pr.size();
+}
+// Ray / frustum vs one Aabb3 (aabb3.rs:165-257, frustum.rs:78-95) for direct leaf-level parity checks.
+int32_t orc_ray_aabb(const float* ray6, const float* box, float* out_point3) {
+    Vec3 p; bool ok = ray_aabb_intersection(Ray(Vec3(ray6[0], ray6[1], ray6[2]), Vec3(ray6[3], ray6[4], ray6[5])), box6(box), p);
+    if (ok) { out_point3[0] = p.x; out_point3[1] = p.y; out_point3[2] = p.z; }
+    return ok ? 1 : 0;
+}
+
+}  // extern "C"
