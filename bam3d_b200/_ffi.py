@@ -1,0 +1,87 @@
+"""ctypes binding of the C ABI declared in include/bam3d_gpu.h (libbam3d_gpu.so, built by bam3d_b200/build.py).
+
+There is no CPU fallback: if the CUDA library is missing or no device is present, loading / context creation
+raises. Nothing under oracle/ is ever imported from here.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbam3d_gpu.so")
+
+OK = 0
+ERR_CUDA, ERR_ARG, ERR_NON_AFFINE, ERR_CAPACITY, ERR_OOM = -1, -2, -3, -4, -5
+
+KIND_PARTICLE, KIND_QUAD, KIND_SPHERE, KIND_CUBOID, KIND_CYLINDER, KIND_CAPSULE, KIND_POLYHEDRON = range(7)
+STATUS_OK, STATUS_MISS, STATUS_MAX_ITER, STATUS_REF_PANIC, STATUS_NAN, STATUS_CAPACITY = range(6)
+FULL_RESOLUTION, COLLISION_ONLY = 0, 1
+
+
+class GjkSettings(C.Structure):
+    _fields_ = [("distance_tolerance", C.c_float), ("continuous_tolerance", C.c_float), ("epa_tolerance", C.c_float),
+                ("max_iterations", C.c_uint32), ("toi_iteration_cap", C.c_uint32)]
+
+
+class Bam3dError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"bam3d error {code}: {msg}")
+        self.code = code
+
+
+_vp, _u64, _i32, _u32 = C.c_void_p, C.c_uint64, C.c_int32, C.c_uint32
+_PS = C.POINTER(GjkSettings)
+
+# name -> (restype, argtypes); every symbol include/bam3d_gpu.h declares
+SIGNATURES = {
+    "bam3d_ctx_create": (_i32, [_i32, C.POINTER(_vp)]),
+    "bam3d_ctx_destroy": (None, [_vp]),
+    "bam3d_last_error": (C.c_char_p, [_vp]),
+    "bam3d_ctx_synchronize": (_i32, [_vp]),
+    "bam3d_ctx_stream": (_vp, [_vp]),
+    "bam3d_default_settings": (None, [_PS]),
+    "bam3d_ctx_set_option": (_i32, [_vp, C.c_char_p, _i32]),
+    "bam3d_host_alloc": (_i32, [_vp, _u64, C.POINTER(_vp)]),
+    "bam3d_host_free": (None, [_vp, _vp]),
+    "bam3d_meshes_upload": (_i32, [_vp, _vp, _vp, _u32, C.POINTER(_vp)]),
+    "bam3d_meshes_free": (None, [_vp, _vp]),
+    "bam3d_shapes_upload": (_i32, [_vp, _vp, _vp, _vp, _vp, _u32, _vp, C.POINTER(_vp)]),
+    "bam3d_shapes_set_transforms": (_i32, [_vp, _vp, _vp]),
+    "bam3d_shapes_free": (None, [_vp, _vp]),
+    "bam3d_shapes_count": (_u32, [_vp]),
+    "bam3d_gjk_intersect": (_i32, [_vp, _vp, _vp, _u64, _PS, _vp]),
+    "bam3d_gjk_contact": (_i32, [_vp, _vp, _vp, _u64, _PS, _i32, _vp, _vp]),
+    "bam3d_gjk_distance": (_i32, [_vp, _vp, _vp, _u64, _PS, _vp, _vp, _vp]),
+    "bam3d_gjk_time_of_impact": (_i32, [_vp, _vp, _vp, _vp, _u64, _PS, _vp, _vp]),
+    "bam3d_gjk_intersect_dev": (_i32, [_vp, _vp, _vp, _u64, _PS, _vp]),
+    "bam3d_gjk_contact_dev": (_i32, [_vp, _vp, _vp, _u64, _PS, _i32, _vp, _vp]),
+    "bam3d_gjk_distance_dev": (_i32, [_vp, _vp, _vp, _u64, _PS, _vp, _vp, _vp]),
+    "bam3d_gjk_time_of_impact_dev": (_i32, [_vp, _vp, _vp, _vp, _u64, _PS, _vp, _vp]),
+    "bam3d_compact_contacts_dev": (_i32, [_vp, _vp, _vp, _u64, _u64, _vp, _u64, _vp]),
+    "bam3d_ctx_launch_count": (_u64, [_vp]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load libbam3d_gpu.so (once). Raises if it has not been built — the product path has no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: build it with `python bam3d_b200/build.py` "
+                              "(nvcc, sm_100a). bam3d_b200 has no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def register(signatures):
+    """Add more entry points (broad phase) to the table before the library is loaded."""
+    SIGNATURES.update(signatures)
+    if _lib is not None:
+        for name, (res, args) in signatures.items():
+            fn = getattr(_lib, name)
+            fn.restype, fn.argtypes = res, args

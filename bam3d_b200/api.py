@@ -1,0 +1,336 @@
+"""Host-side mirror of bam3d's narrow-phase API over the CUDA C ABI.
+
+Names, argument meaning and None/Some behaviour follow the reference crate:
+  primitives   src/primitive/{sphere,cuboid,cylinder,capsule,quad,particle,polyhedron}.rs (constructors)
+  Contact, CollisionStrategy   src/contact.rs:12-69
+  GJK          src/algorithm/minkowski/gjk/mod.rs:32-524 (new, new_with_settings, intersect, intersection,
+               distance, intersection_time_of_impact) — the scalar methods are batch-of-1 calls into the same
+               kernels (no CPU fallback), the *_batch methods are the additions that make the path data parallel.
+Transforms are glam Mat4 values given as 16 f32 in column-major order (Mat4::to_cols_array).
+"""
+import ctypes as C
+import enum
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import Bam3dError, GjkSettings
+
+
+def _ptr(a):
+    return C.c_void_p(a.ctypes.data) if a is not None else None
+
+
+class Context:
+    """One per host thread: owns the CUDA stream and device scratch (bam3d_ctx)."""
+
+    def __init__(self, device=0):
+        self._lib = _ffi.lib()
+        h = C.c_void_p()
+        rc = self._lib.bam3d_ctx_create(int(device), C.byref(h))
+        if rc != _ffi.OK:
+            raise Bam3dError(rc, "bam3d_ctx_create failed: no usable CUDA device (there is no CPU fallback)")
+        self.handle = h
+        self.device = int(device)
+
+    def check(self, rc):
+        if rc != _ffi.OK:
+            raise Bam3dError(rc, self._lib.bam3d_last_error(self.handle).decode())
+
+    def synchronize(self):
+        self.check(self._lib.bam3d_ctx_synchronize(self.handle))
+
+    @property
+    def stream(self):
+        return self._lib.bam3d_ctx_stream(self.handle)
+
+    @property
+    def launch_count(self):
+        return int(self._lib.bam3d_ctx_launch_count(self.handle))
+
+    def set_option(self, name, value):
+        self.check(self._lib.bam3d_ctx_set_option(self.handle, name.encode(), int(value)))
+
+    def close(self):
+        if self.handle:
+            self._lib.bam3d_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_default_ctx = None
+
+
+def default_context():
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(0)
+    return _default_ctx
+
+
+# ---------------------------------------------------------------------------------------------------------
+# primitives (constructors mirror the reference's `new`)
+# ---------------------------------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class Particle:  # primitive/particle.rs:19-30
+    kind = _ffi.KIND_PARTICLE
+
+    def params(self):
+        return (0.0, 0.0, 0.0, 0.0)
+
+
+@dataclass(frozen=True)
+class Sphere:  # primitive/sphere.rs:8-18
+    radius: float
+    kind = _ffi.KIND_SPHERE
+
+    def params(self):
+        return (self.radius, 0.0, 0.0, 0.0)
+
+
+class Cuboid:  # primitive/cuboid.rs:13-35: new(dim_x, dim_y, dim_z), half_dim = dim / 2
+    kind = _ffi.KIND_CUBOID
+
+    def __init__(self, dim_x, dim_y, dim_z):
+        self.dim = np.array([dim_x, dim_y, dim_z], dtype=np.float32)
+        self.half_dim = self.dim / np.float32(2.0)
+
+    def params(self):
+        return (self.half_dim[0], self.half_dim[1], self.half_dim[2], 0.0)
+
+
+class Cube(Cuboid):  # primitive/cuboid.rs:109-131
+    def __init__(self, dim):
+        super().__init__(dim, dim, dim)
+
+
+class Quad:  # primitive/quad.rs:13-35
+    kind = _ffi.KIND_QUAD
+
+    def __init__(self, dim_x, dim_y):
+        self.half_dim = np.array([dim_x, dim_y], dtype=np.float32) / np.float32(2.0)
+
+    def params(self):
+        return (self.half_dim[0], self.half_dim[1], 0.0, 0.0)
+
+
+@dataclass(frozen=True)
+class Cylinder:  # primitive/cylinder.rs:12-24 (Y-axis aligned)
+    half_height: float
+    radius: float
+    kind = _ffi.KIND_CYLINDER
+
+    def params(self):
+        return (self.half_height, self.radius, 0.0, 0.0)
+
+
+@dataclass(frozen=True)
+class Capsule:  # primitive/capsule.rs:15-27 (Y-axis aligned)
+    half_height: float
+    radius: float
+    kind = _ffi.KIND_CAPSULE
+
+    def params(self):
+        return (self.half_height, self.radius, 0.0, 0.0)
+
+
+class ConvexPolyhedron:  # primitive/polyhedron.rs:69-95 ConvexPolyhedron::new (VertexOnly mode)
+    kind = _ffi.KIND_POLYHEDRON
+
+    def __init__(self, vertices):
+        self.vertices = np.ascontiguousarray(vertices, dtype=np.float32).reshape(-1, 3)
+
+    def params(self):
+        return (0.0, 0.0, 0.0, 0.0)
+
+
+class CollisionStrategy(enum.IntEnum):  # contact.rs:12-18
+    FullResolution = _ffi.FULL_RESOLUTION
+    CollisionOnly = _ffi.COLLISION_ONLY
+
+
+@dataclass
+class Contact:  # contact.rs:22-38
+    strategy: CollisionStrategy
+    normal: np.ndarray
+    penetration_depth: float
+    contact_point: np.ndarray
+    time_of_impact: float = 0.0
+
+
+# ---------------------------------------------------------------------------------------------------------
+# device-resident packs
+# ---------------------------------------------------------------------------------------------------------
+class MeshLibrary:
+    """Vertex lists of ConvexPolyhedron values, resident on the device (bam3d_meshes)."""
+
+    def __init__(self, ctx, verts, offsets):
+        self.ctx = ctx
+        self.verts = np.ascontiguousarray(verts, dtype=np.float32).reshape(-1, 3)
+        self.offsets = np.ascontiguousarray(offsets, dtype=np.uint32)
+        h = C.c_void_p()
+        ctx.check(ctx._lib.bam3d_meshes_upload(ctx.handle, _ptr(self.verts), _ptr(self.offsets), len(self.offsets) - 1, C.byref(h)))
+        self.handle = h
+
+    def close(self):
+        if self.handle:
+            self.ctx._lib.bam3d_meshes_free(self.ctx.handle, self.handle)
+            self.handle = None
+
+
+class ShapeSet:
+    """Primitives + model-to-world Mat4, packed into device buffers (bam3d_shapes)."""
+
+    def __init__(self, ctx, kind, params, xform, mesh_id=None, meshes=None):
+        self.ctx = ctx
+        self.kind = np.ascontiguousarray(kind, dtype=np.uint8)
+        n = len(self.kind)
+        self.params = np.ascontiguousarray(params, dtype=np.float32).reshape(n, 4)
+        xform = np.ascontiguousarray(xform, dtype=np.float32).reshape(n, 16)
+        self.mesh_id = None if mesh_id is None else np.ascontiguousarray(mesh_id, dtype=np.uint32)
+        self.meshes = meshes
+        h = C.c_void_p()
+        ctx.check(ctx._lib.bam3d_shapes_upload(ctx.handle, _ptr(self.kind), _ptr(self.params), _ptr(xform), _ptr(self.mesh_id), n,
+                                               meshes.handle if meshes is not None else None, C.byref(h)))
+        self.handle = h
+        self.n = n
+
+    @classmethod
+    def from_primitives(cls, ctx, primitives, transforms):
+        """primitives: sequence of primitive objects; transforms: matching sequence of 16-float Mat4 arrays."""
+        kind = np.array([p.kind for p in primitives], dtype=np.uint8)
+        params = np.array([p.params() for p in primitives], dtype=np.float32).reshape(-1, 4)
+        mesh_id, meshes = None, None
+        polys = [p for p in primitives if p.kind == _ffi.KIND_POLYHEDRON]
+        if polys:
+            offs, verts, mesh_id = [0], [], np.zeros(len(primitives), dtype=np.uint32)
+            m = 0
+            for i, p in enumerate(primitives):
+                if p.kind == _ffi.KIND_POLYHEDRON:
+                    verts.append(p.vertices)
+                    offs.append(offs[-1] + len(p.vertices))
+                    mesh_id[i] = m
+                    m += 1
+            meshes = MeshLibrary(ctx, np.concatenate(verts, axis=0), np.array(offs, dtype=np.uint32))
+        return cls(ctx, kind, params, np.array(transforms, dtype=np.float32).reshape(-1, 16), mesh_id, meshes)
+
+    def set_transforms(self, xform):
+        xform = np.ascontiguousarray(xform, dtype=np.float32).reshape(self.n, 16)
+        self.ctx.check(self.ctx._lib.bam3d_shapes_set_transforms(self.ctx.handle, self.handle, _ptr(xform)))
+
+    def close(self):
+        if self.handle:
+            self.ctx._lib.bam3d_shapes_free(self.ctx.handle, self.handle)
+            self.handle = None
+
+
+# ---------------------------------------------------------------------------------------------------------
+# GJK
+# ---------------------------------------------------------------------------------------------------------
+class GJK:
+    """Gilbert-Johnson-Keerthi narrow phase (gjk/mod.rs:24-58) running on the GPU."""
+
+    def __init__(self, ctx=None, distance_tolerance=0.000001, continuous_tolerance=0.000001, epa_tolerance=0.00001,
+                 max_iterations=100, toi_iteration_cap=100):
+        self.ctx = ctx if ctx is not None else default_context()
+        self.settings = GjkSettings(distance_tolerance, continuous_tolerance, epa_tolerance, max_iterations, toi_iteration_cap)
+
+    @classmethod
+    def new(cls, ctx=None):  # gjk/mod.rs:34-42
+        return cls(ctx)
+
+    @classmethod
+    def new_with_settings(cls, distance_tolerance, continuous_tolerance, epa_tolerance, max_iterations, ctx=None):  # :45-58
+        return cls(ctx, distance_tolerance, continuous_tolerance, epa_tolerance, max_iterations)
+
+    # ---- batched entry points (host buffers) -------------------------------------------------------------
+    @staticmethod
+    def _pairs(pairs):
+        pairs = np.ascontiguousarray(pairs, dtype=np.uint32).reshape(-1, 2)
+        return pairs, len(pairs)
+
+    def intersect_batch(self, shapes, pairs):
+        """GJK::intersect per pair (gjk/mod.rs:74-113). Returns status[n] (0 == Some(simplex))."""
+        pairs, n = self._pairs(pairs)
+        status = np.empty(n, dtype=np.uint8)
+        self.ctx.check(self.ctx._lib.bam3d_gjk_intersect(self.ctx.handle, shapes.handle, _ptr(pairs), n, C.byref(self.settings), _ptr(status)))
+        return status
+
+    def intersection_batch(self, strategy, shapes, pairs):
+        """GJK::intersection per pair (gjk/mod.rs:317-341). Returns (contacts[n, 8], status[n]); contact rows are
+        normal xyz, penetration_depth, contact_point xyz, time_of_impact."""
+        pairs, n = self._pairs(pairs)
+        status = np.empty(n, dtype=np.uint8)
+        contacts = np.empty((n, 8), dtype=np.float32)
+        self.ctx.check(self.ctx._lib.bam3d_gjk_contact(self.ctx.handle, shapes.handle, _ptr(pairs), n, C.byref(self.settings), int(strategy),
+                                                       _ptr(contacts), _ptr(status)))
+        return contacts, status
+
+    def distance_batch(self, shapes, pairs):
+        """GJK::distance per pair (gjk/mod.rs:232-280). Returns (ref_value[n], distance[n], status[n])."""
+        pairs, n = self._pairs(pairs)
+        status = np.empty(n, dtype=np.uint8)
+        ref = np.empty(n, dtype=np.float32)
+        dist = np.empty(n, dtype=np.float32)
+        self.ctx.check(self.ctx._lib.bam3d_gjk_distance(self.ctx.handle, shapes.handle, _ptr(pairs), n, C.byref(self.settings), _ptr(ref), _ptr(dist),
+                                                        _ptr(status)))
+        return ref, dist, status
+
+    def intersection_time_of_impact_batch(self, shapes_start, shapes_end, pairs):
+        """GJK::intersection_time_of_impact per pair (gjk/mod.rs:130-217)."""
+        pairs, n = self._pairs(pairs)
+        status = np.empty(n, dtype=np.uint8)
+        contacts = np.empty((n, 8), dtype=np.float32)
+        self.ctx.check(self.ctx._lib.bam3d_gjk_time_of_impact(self.ctx.handle, shapes_start.handle, shapes_end.handle, _ptr(pairs), n,
+                                                              C.byref(self.settings), _ptr(contacts), _ptr(status)))
+        return contacts, status
+
+    # ---- the reference's scalar methods, as batch-of-1 -----------------------------------------------------
+    def _two(self, left, left_transform, right, right_transform):
+        return ShapeSet.from_primitives(self.ctx, [left, right], [left_transform, right_transform])
+
+    @staticmethod
+    def _contact(strategy, row):
+        return Contact(CollisionStrategy(strategy), row[0:3].copy(), float(row[3]), row[4:7].copy(), float(row[7]))
+
+    def intersect(self, left, left_transform, right, right_transform):
+        """-> bool (the reference returns Option<Simplex>; the simplex itself stays on the device)."""
+        s = self._two(left, left_transform, right, right_transform)
+        try:
+            return bool(self.intersect_batch(s, [[0, 1]])[0] == _ffi.STATUS_OK)
+        finally:
+            s.close()
+
+    def intersection(self, strategy, left, left_transform, right, right_transform):
+        s = self._two(left, left_transform, right, right_transform)
+        try:
+            c, st = self.intersection_batch(strategy, s, [[0, 1]])
+            return self._contact(strategy, c[0]) if st[0] == _ffi.STATUS_OK else None
+        finally:
+            s.close()
+
+    def distance(self, left, left_transform, right, right_transform):
+        """-> Option<f32> exactly as the reference computes it (the residual dp - d0, gjk/mod.rs:273-275)."""
+        s = self._two(left, left_transform, right, right_transform)
+        try:
+            ref, _, st = self.distance_batch(s, [[0, 1]])
+            return float(ref[0]) if st[0] == _ffi.STATUS_OK else None
+        finally:
+            s.close()
+
+    def intersection_time_of_impact(self, left, left_transform_range, right, right_transform_range):
+        """transform ranges are (start, end) pairs, the reference's Range<&Mat4>."""
+        s0 = self._two(left, left_transform_range[0], right, right_transform_range[0])
+        s1 = self._two(left, left_transform_range[1], right, right_transform_range[1])
+        try:
+            c, st = self.intersection_time_of_impact_batch(s0, s1, [[0, 1]])
+            return self._contact(CollisionStrategy.FullResolution, c[0]) if st[0] == _ffi.STATUS_OK else None
+        finally:
+            s0.close()
+            s1.close()

@@ -1,0 +1,426 @@
+// C ABI (include/bam3d_gpu.h) over the CUDA kernels: context, device-resident shape sets, and the narrow-phase
+// entry points. Host layer duties (north_star subsystem 1): take primitives + glam Mat4 in the caller's host
+// arrays, pack them into device buffers, run the kernels on the ctx stream, copy results back.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/bam3d_gpu.h"
+#include "vecmath.cuh"
+#include "narrow.h"
+#include "broad.h"
+#include "ctx.h"
+
+using namespace b3;
+
+// ------------------------------------------------------------------------------------------------------------
+// helpers
+// ------------------------------------------------------------------------------------------------------------
+int32_t b3_fail(bam3d_ctx* ctx, int32_t code, const char* what, cudaError_t e) {
+    if (ctx) {
+        char buf[512];
+        if (e != cudaSuccess) std::snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+        else std::snprintf(buf, sizeof buf, "%s", what);
+        ctx->err = buf;
+    }
+    return code;
+}
+
+int32_t DevBuf::reserve(bam3d_ctx* ctx, size_t need) {
+    if (need <= bytes) return BAM3D_OK;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr; bytes = 0;
+    size_t want = need + need / 4 + 256;
+    cudaError_t e = cudaMalloc(&ptr, want);
+    if (e != cudaSuccess) { ptr = nullptr; return b3_fail(ctx, BAM3D_ERR_OOM, "cudaMalloc(scratch)", e); }
+    bytes = want;
+    return BAM3D_OK;
+}
+void DevBuf::release() { if (ptr) cudaFree(ptr); ptr = nullptr; bytes = 0; }
+
+static SettingsDev to_dev(const bam3d_gjk_settings* s) {
+    bam3d_gjk_settings d;
+    bam3d_default_settings(&d);
+    if (s) d = *s;
+    SettingsDev r;
+    r.distance_tolerance = d.distance_tolerance; r.continuous_tolerance = d.continuous_tolerance;
+    r.epa_tolerance = d.epa_tolerance; r.max_iterations = d.max_iterations;
+    r.toi_iteration_cap = d.toi_iteration_cap ? d.toi_iteration_cap : 100u;
+    return r;
+}
+
+static ShapeSetDev view(const bam3d_shapes* s) {
+    ShapeSetDev v;
+    v.recs = s->recs; v.meta = s->meta; v.n = s->n;
+    v.mesh_verts = s->meshes ? s->meshes->verts : nullptr;
+    v.mesh_offsets = s->meshes ? s->meshes->offsets : nullptr;
+    return v;
+}
+
+// Decide execution shapes for a shape set: which kernels run and whether pairs are binned first.
+struct Plan { bool bin, run_thread, run_warp; };
+static Plan plan_for(const bam3d_ctx* ctx, const bam3d_shapes* s) {
+    int analytic_kinds = 0;
+    for (int k = 0; k < 6; ++k) analytic_kinds += s->kind_hist[k] ? 1 : 0;
+    bool has_poly = s->kind_hist[BAM3D_KIND_POLYHEDRON] != 0;
+    Plan p;
+    if (!has_poly) { p.run_thread = true; p.run_warp = false; p.bin = analytic_kinds > 1; }
+    else if (analytic_kinds == 0) { p.run_thread = false; p.run_warp = true; p.bin = false; }
+    else { p.run_thread = true; p.run_warp = true; p.bin = true; }
+    if (!ctx->opt_binning && !(p.run_thread && p.run_warp)) p.bin = false;
+    return p;
+}
+
+static int32_t prepare_bins(bam3d_ctx* ctx, const Plan& plan, const ShapeSetDev& S, const uint2* d_pairs, uint32_t n,
+                            BinScratch& B, const BinScratch** out) {
+    *out = nullptr;
+    if (!plan.bin) return BAM3D_OK;
+    int32_t rc;
+    if ((rc = ctx->keys.reserve(ctx, n)) || (rc = ctx->order.reserve(ctx, (size_t)n * 4)) || (rc = ctx->small.reserve(ctx, 1024))) return rc;
+    B.keys = (uint8_t*)ctx->keys.ptr; B.order = (uint32_t*)ctx->order.ptr;
+    uint32_t* sm = (uint32_t*)ctx->small.ptr;
+    B.hist = sm; B.start = sm + 64; B.cursor = sm + 128; B.ranges = sm + 192;
+    ctx->launches += launch_bin_pairs(ctx->stream, S, d_pairs, n, B);
+    *out = &B;
+    return BAM3D_OK;
+}
+
+#define CU_TRY(call, what)                                                         \
+    do {                                                                           \
+        cudaError_t e_ = (call);                                                   \
+        if (e_ != cudaSuccess) return b3_fail(ctx, BAM3D_ERR_CUDA, what, e_);      \
+    } while (0)
+
+static int32_t check_launch(bam3d_ctx* ctx, const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return b3_fail(ctx, BAM3D_ERR_CUDA, what, e);
+    return BAM3D_OK;
+}
+
+static int32_t check_n(bam3d_ctx* ctx, uint64_t n) {
+    if (n > 0xFFFFFF00ull) return b3_fail(ctx, BAM3D_ERR_ARG, "batch too large: n must be < 2^32 - 256 pairs per call", cudaSuccess);
+    return BAM3D_OK;
+}
+
+extern "C" {
+
+// ------------------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------------------
+void bam3d_default_settings(bam3d_gjk_settings* out) {
+    out->distance_tolerance = 0.000001f;
+    out->continuous_tolerance = 0.000001f;
+    out->epa_tolerance = 0.00001f;
+    out->max_iterations = 100;
+    out->toi_iteration_cap = 100;
+}
+
+int32_t bam3d_ctx_create(int32_t device_ordinal, bam3d_ctx** out_ctx) {
+    if (!out_ctx) return BAM3D_ERR_ARG;
+    *out_ctx = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0 || device_ordinal < 0 || device_ordinal >= count) return BAM3D_ERR_CUDA;  // no CPU fallback
+    if (cudaSetDevice(device_ordinal) != cudaSuccess) return BAM3D_ERR_CUDA;
+    bam3d_ctx* ctx = new (std::nothrow) bam3d_ctx();
+    if (!ctx) return BAM3D_ERR_OOM;
+    ctx->device = device_ordinal;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return BAM3D_ERR_CUDA; }
+    *out_ctx = ctx;
+    return BAM3D_OK;
+}
+
+void bam3d_ctx_destroy(bam3d_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->release_scratch();
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* bam3d_last_error(const bam3d_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context (CUDA device unavailable?)"; }
+int32_t bam3d_ctx_synchronize(bam3d_ctx* ctx) {
+    if (!ctx) return BAM3D_ERR_ARG;
+    CU_TRY(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize");
+    return BAM3D_OK;
+}
+void* bam3d_ctx_stream(bam3d_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+uint64_t bam3d_ctx_launch_count(const bam3d_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int32_t bam3d_ctx_set_option(bam3d_ctx* ctx, const char* name, int32_t value) {
+    if (!ctx || !name) return BAM3D_ERR_ARG;
+    if (!std::strcmp(name, "binning")) { ctx->opt_binning = value != 0; return BAM3D_OK; }
+    return b3_fail(ctx, BAM3D_ERR_ARG, "unknown option", cudaSuccess);
+}
+
+int32_t bam3d_host_alloc(bam3d_ctx* ctx, uint64_t bytes, void** out_ptr) {
+    if (!ctx || !out_ptr) return BAM3D_ERR_ARG;
+    CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
+    CU_TRY(cudaHostAlloc(out_ptr, bytes ? bytes : 1, cudaHostAllocDefault), "cudaHostAlloc");
+    return BAM3D_OK;
+}
+void bam3d_host_free(bam3d_ctx* ctx, void* ptr) { (void)ctx; if (ptr) cudaFreeHost(ptr); }
+
+// ------------------------------------------------------------------------------------------------------------
+// meshes / shapes
+// ------------------------------------------------------------------------------------------------------------
+int32_t bam3d_meshes_upload(bam3d_ctx* ctx, const float* verts_xyz, const uint32_t* offsets, uint32_t n_meshes, bam3d_meshes** out) {
+    if (!ctx || !out || !offsets || (n_meshes && !verts_xyz)) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_meshes_upload: null argument", cudaSuccess);
+    *out = nullptr;
+    CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
+    for (uint32_t m = 0; m < n_meshes; ++m)
+        if (offsets[m + 1] < offsets[m]) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_meshes_upload: offsets must be non-decreasing", cudaSuccess);
+    uint64_t nverts = offsets[n_meshes];
+    bam3d_meshes* M = new (std::nothrow) bam3d_meshes();
+    if (!M) return BAM3D_ERR_OOM;
+    M->n_meshes = n_meshes; M->nverts = nverts;
+    float* d_xyz = nullptr;
+    cudaError_t e;
+    if ((e = cudaMalloc(&M->verts, (nverts ? nverts : 1) * sizeof(float4))) != cudaSuccess ||
+        (e = cudaMalloc(&M->offsets, ((size_t)n_meshes + 1) * sizeof(uint32_t))) != cudaSuccess ||
+        (e = cudaMalloc(&d_xyz, (nverts ? nverts : 1) * 3 * sizeof(float))) != cudaSuccess) {
+        bam3d_meshes_free(ctx, M); if (d_xyz) cudaFree(d_xyz);
+        return b3_fail(ctx, BAM3D_ERR_OOM, "cudaMalloc(meshes)", e);
+    }
+    cudaMemcpyAsync(M->offsets, offsets, ((size_t)n_meshes + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (nverts) cudaMemcpyAsync(d_xyz, verts_xyz, nverts * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+    ctx->launches += launch_pack_meshes(ctx->stream, d_xyz, nverts, M->verts);
+    e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_xyz);
+    if (e != cudaSuccess) { bam3d_meshes_free(ctx, M); return b3_fail(ctx, BAM3D_ERR_CUDA, "bam3d_meshes_upload", e); }
+    *out = M;
+    return BAM3D_OK;
+}
+
+void bam3d_meshes_free(bam3d_ctx* ctx, bam3d_meshes* M) {
+    (void)ctx;
+    if (!M) return;
+    if (M->verts) cudaFree(M->verts);
+    if (M->offsets) cudaFree(M->offsets);
+    delete M;
+}
+
+static int32_t run_pack(bam3d_ctx* ctx, bam3d_shapes* S) {
+    int32_t rc = ctx->small.reserve(ctx, 1024);
+    if (rc) return rc;
+    uint32_t* d_err = (uint32_t*)ctx->small.ptr + 200;
+    cudaMemsetAsync(d_err, 0, sizeof(uint32_t), ctx->stream);
+    ctx->launches += launch_pack_shapes(ctx->stream, S->d_kind, S->d_params, S->d_xform, S->d_mesh_id, S->n,
+                                        S->meshes ? S->meshes->n_meshes : 0, S->recs, S->meta, d_err);
+    if ((rc = check_launch(ctx, "pack_shapes_kernel"))) return rc;
+    uint32_t h_err = 0;
+    CU_TRY(cudaMemcpyAsync(&h_err, d_err, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(err)");
+    CU_TRY(cudaStreamSynchronize(ctx->stream), "pack_shapes_kernel");
+    if (h_err & 1u) return b3_fail(ctx, BAM3D_ERR_NON_AFFINE, "a transform's 4th row is not (0,0,0,1)", cudaSuccess);
+    if (h_err & 2u) return b3_fail(ctx, BAM3D_ERR_ARG, "unknown primitive kind", cudaSuccess);
+    if (h_err & 4u) return b3_fail(ctx, BAM3D_ERR_ARG, "polyhedron mesh_id out of range (or no mesh library given)", cudaSuccess);
+    return BAM3D_OK;
+}
+
+int32_t bam3d_shapes_upload(bam3d_ctx* ctx, const uint8_t* kind, const float* params, const float* xform, const uint32_t* mesh_id,
+                            uint32_t n, const bam3d_meshes* meshes, bam3d_shapes** out) {
+    if (!ctx || !out || (n && (!kind || !params || !xform))) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_shapes_upload: null argument", cudaSuccess);
+    *out = nullptr;
+    CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
+    bam3d_shapes* S = new (std::nothrow) bam3d_shapes();
+    if (!S) return BAM3D_ERR_OOM;
+    S->n = n; S->meshes = meshes;
+    for (uint32_t i = 0; i < n; ++i) if (kind[i] < 7) S->kind_hist[kind[i]]++;
+    size_t nn = n ? n : 1;
+    cudaError_t e;
+    if ((e = cudaMalloc(&S->recs, nn * 96)) != cudaSuccess || (e = cudaMalloc(&S->meta, nn * 4)) != cudaSuccess ||
+        (e = cudaMalloc(&S->d_kind, nn)) != cudaSuccess || (e = cudaMalloc(&S->d_params, nn * 16)) != cudaSuccess ||
+        (e = cudaMalloc(&S->d_xform, nn * 64)) != cudaSuccess || (mesh_id && (e = cudaMalloc(&S->d_mesh_id, nn * 4)) != cudaSuccess)) {
+        bam3d_shapes_free(ctx, S);
+        return b3_fail(ctx, BAM3D_ERR_OOM, "cudaMalloc(shapes)", e);
+    }
+    if (n) {
+        cudaMemcpyAsync(S->d_kind, kind, n, cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(S->d_params, params, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(S->d_xform, xform, (size_t)n * 64, cudaMemcpyHostToDevice, ctx->stream);
+        if (mesh_id) cudaMemcpyAsync(S->d_mesh_id, mesh_id, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream);
+    }
+    int32_t rc = run_pack(ctx, S);
+    if (rc) { bam3d_shapes_free(ctx, S); return rc; }
+    *out = S;
+    return BAM3D_OK;
+}
+
+int32_t bam3d_shapes_set_transforms(bam3d_ctx* ctx, bam3d_shapes* S, const float* xform) {
+    if (!ctx || !S || !xform) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_shapes_set_transforms: null argument", cudaSuccess);
+    CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
+    if (S->n) CU_TRY(cudaMemcpyAsync(S->d_xform, xform, (size_t)S->n * 64, cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpyAsync(xform)");
+    return run_pack(ctx, S);
+}
+
+void bam3d_shapes_free(bam3d_ctx* ctx, bam3d_shapes* S) {
+    (void)ctx;
+    if (!S) return;
+    if (S->recs) cudaFree(S->recs);
+    if (S->meta) cudaFree(S->meta);
+    if (S->d_kind) cudaFree(S->d_kind);
+    if (S->d_params) cudaFree(S->d_params);
+    if (S->d_xform) cudaFree(S->d_xform);
+    if (S->d_mesh_id) cudaFree(S->d_mesh_id);
+    delete S;
+}
+uint32_t bam3d_shapes_count(const bam3d_shapes* S) { return S ? S->n : 0; }
+
+// ------------------------------------------------------------------------------------------------------------
+// narrow phase, device buffers
+// ------------------------------------------------------------------------------------------------------------
+int32_t bam3d_gjk_intersect_dev(bam3d_ctx* ctx, const bam3d_shapes* shapes, const uint32_t* d_pairs, uint64_t n,
+                                const bam3d_gjk_settings* settings, uint8_t* d_status) {
+    if (!ctx || !shapes || (n && (!d_pairs || !d_status))) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_gjk_intersect: null argument", cudaSuccess);
+    int32_t rc;
+    if ((rc = check_n(ctx, n))) return rc;
+    if (n == 0) return BAM3D_OK;
+    CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
+    ShapeSetDev S = view(shapes);
+    Plan plan = plan_for(ctx, shapes);
+    BinScratch B; const BinScratch* pb;
+    if ((rc = prepare_bins(ctx, plan, S, (const uint2*)d_pairs, (uint32_t)n, B, &pb))) return rc;
+    ctx->launches += launch_intersect(ctx->stream, S, (const uint2*)d_pairs, (uint32_t)n, pb, plan.run_thread, plan.run_warp, to_dev(settings), d_status);
+    return check_launch(ctx, "gjk_intersect_kernel");
+}
+
+int32_t bam3d_gjk_contact_dev(bam3d_ctx* ctx, const bam3d_shapes* shapes, const uint32_t* d_pairs, uint64_t n,
+                              const bam3d_gjk_settings* settings, int32_t strategy, bam3d_contact* d_contacts, uint8_t* d_status) {
+    if (!ctx || !shapes || (n && (!d_pairs || !d_status || !d_contacts))) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_gjk_contact: null argument", cudaSuccess);
+    if (strategy != BAM3D_FULL_RESOLUTION && strategy != BAM3D_COLLISION_ONLY) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_gjk_contact: unknown strategy", cudaSuccess);
+    SettingsDev cfg = to_dev(settings);
+    if (strategy == BAM3D_FULL_RESOLUTION && cfg.max_iterations > 100)
+        return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_gjk_contact: max_iterations > 100 exceeds the device EPA polytope capacity", cudaSuccess);
+    int32_t rc;
+    if ((rc = check_n(ctx, n))) return rc;
+    if (n == 0) return BAM3D_OK;
+    CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
+    ShapeSetDev S = view(shapes);
+    Plan plan = plan_for(ctx, shapes);
+    BinScratch B; const BinScratch* pb;
+    if ((rc = prepare_bins(ctx, plan, S, (const uint2*)d_pairs, (uint32_t)n, B, &pb))) return rc;
+    if (strategy == BAM3D_FULL_RESOLUTION && (rc = ctx->epa_overflow.reserve(ctx, contact_overflow_scratch_bytes()))) return rc;
+    ctx->launches += launch_contact(ctx->stream, S, (const uint2*)d_pairs, (uint32_t)n, pb, plan.run_thread, plan.run_warp, cfg, strategy,
+                                    ctx->epa_overflow.ptr, (float4*)d_contacts, d_status);
+    return check_launch(ctx, "gjk_contact_kernel");
+}
+
+int32_t bam3d_gjk_distance_dev(bam3d_ctx* ctx, const bam3d_shapes* shapes, const uint32_t* d_pairs, uint64_t n,
+                               const bam3d_gjk_settings* settings, float* d_ref_value, float* d_distance, uint8_t* d_status) {
+    if (!ctx || !shapes || (n && (!d_pairs || !d_status || !d_ref_value || !d_distance))) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_gjk_distance: null argument", cudaSuccess);
+    int32_t rc;
+    if ((rc = check_n(ctx, n))) return rc;
+    if (n == 0) return BAM3D_OK;
+    CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
+    ShapeSetDev S = view(shapes);
+    Plan plan = plan_for(ctx, shapes);
+    BinScratch B; const BinScratch* pb;
+    if ((rc = prepare_bins(ctx, plan, S, (const uint2*)d_pairs, (uint32_t)n, B, &pb))) return rc;
+    ctx->launches += launch_distance(ctx->stream, S, (const uint2*)d_pairs, (uint32_t)n, pb, plan.run_thread, plan.run_warp, to_dev(settings),
+                                     d_ref_value, d_distance, d_status);
+    return check_launch(ctx, "gjk_distance_kernel");
+}
+
+int32_t bam3d_gjk_time_of_impact_dev(bam3d_ctx* ctx, const bam3d_shapes* s0, const bam3d_shapes* s1, const uint32_t* d_pairs, uint64_t n,
+                                     const bam3d_gjk_settings* settings, bam3d_contact* d_contacts, uint8_t* d_status) {
+    if (!ctx || !s0 || !s1 || (n && (!d_pairs || !d_status || !d_contacts))) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_gjk_time_of_impact: null argument", cudaSuccess);
+    if (s0->n != s1->n) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_gjk_time_of_impact: start/end shape sets differ in size", cudaSuccess);
+    int32_t rc;
+    if ((rc = check_n(ctx, n))) return rc;
+    if (n == 0) return BAM3D_OK;
+    CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
+    ShapeSetDev S0 = view(s0), S1 = view(s1);
+    Plan plan = plan_for(ctx, s0);
+    BinScratch B; const BinScratch* pb;
+    if ((rc = prepare_bins(ctx, plan, S0, (const uint2*)d_pairs, (uint32_t)n, B, &pb))) return rc;
+    ctx->launches += launch_toi(ctx->stream, S0, S1, (const uint2*)d_pairs, (uint32_t)n, pb, plan.run_thread, plan.run_warp, to_dev(settings),
+                                (float4*)d_contacts, d_status);
+    return check_launch(ctx, "gjk_toi_kernel");
+}
+
+int32_t bam3d_compact_contacts_dev(bam3d_ctx* ctx, const bam3d_contact* d_contacts, const uint8_t* d_status, uint64_t n, uint64_t base,
+                                   bam3d_contact40* d_out, uint64_t capacity, uint64_t* d_count) {
+    if (!ctx || !d_count || (n && (!d_contacts || !d_status || !d_out))) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_compact_contacts: null argument", cudaSuccess);
+    CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
+    ctx->launches += launch_compact_contacts(ctx->stream, (const float4*)d_contacts, d_status, n, base, d_out, capacity,
+                                             (unsigned long long*)d_count);
+    return check_launch(ctx, "compact_contacts_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// narrow phase, host buffers: H2D pairs -> kernels -> D2H results, synchronous on return
+// ------------------------------------------------------------------------------------------------------------
+static int32_t stage_pairs(bam3d_ctx* ctx, const uint32_t* pairs, uint64_t n) {
+    int32_t rc = ctx->pairs.reserve(ctx, n * 8);
+    if (rc) return rc;
+    CU_TRY(cudaMemcpyAsync(ctx->pairs.ptr, pairs, n * 8, cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpyAsync(pairs)");
+    return BAM3D_OK;
+}
+
+int32_t bam3d_gjk_intersect(bam3d_ctx* ctx, const bam3d_shapes* shapes, const uint32_t* pairs, uint64_t n,
+                            const bam3d_gjk_settings* settings, uint8_t* out_status) {
+    if (!ctx || !shapes || (n && (!pairs || !out_status))) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_gjk_intersect: null argument", cudaSuccess);
+    int32_t rc;
+    if ((rc = check_n(ctx, n))) return rc;
+    if (n == 0) return BAM3D_OK;
+    CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
+    if ((rc = stage_pairs(ctx, pairs, n)) || (rc = ctx->status.reserve(ctx, n))) return rc;
+    if ((rc = bam3d_gjk_intersect_dev(ctx, shapes, (const uint32_t*)ctx->pairs.ptr, n, settings, (uint8_t*)ctx->status.ptr))) return rc;
+    CU_TRY(cudaMemcpyAsync(out_status, ctx->status.ptr, n, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(status)");
+    CU_TRY(cudaStreamSynchronize(ctx->stream), "bam3d_gjk_intersect");
+    return BAM3D_OK;
+}
+
+int32_t bam3d_gjk_contact(bam3d_ctx* ctx, const bam3d_shapes* shapes, const uint32_t* pairs, uint64_t n,
+                          const bam3d_gjk_settings* settings, int32_t strategy, bam3d_contact* out_contacts, uint8_t* out_status) {
+    if (!ctx || !shapes || (n && (!pairs || !out_status || !out_contacts))) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_gjk_contact: null argument", cudaSuccess);
+    int32_t rc;
+    if ((rc = check_n(ctx, n))) return rc;
+    if (n == 0) return BAM3D_OK;
+    CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
+    if ((rc = stage_pairs(ctx, pairs, n)) || (rc = ctx->status.reserve(ctx, n)) || (rc = ctx->contacts.reserve(ctx, n * 32))) return rc;
+    if ((rc = bam3d_gjk_contact_dev(ctx, shapes, (const uint32_t*)ctx->pairs.ptr, n, settings, strategy, (bam3d_contact*)ctx->contacts.ptr,
+                                    (uint8_t*)ctx->status.ptr))) return rc;
+    CU_TRY(cudaMemcpyAsync(out_contacts, ctx->contacts.ptr, n * 32, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(contacts)");
+    CU_TRY(cudaMemcpyAsync(out_status, ctx->status.ptr, n, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(status)");
+    CU_TRY(cudaStreamSynchronize(ctx->stream), "bam3d_gjk_contact");
+    return BAM3D_OK;
+}
+
+int32_t bam3d_gjk_distance(bam3d_ctx* ctx, const bam3d_shapes* shapes, const uint32_t* pairs, uint64_t n,
+                           const bam3d_gjk_settings* settings, float* out_ref_value, float* out_distance, uint8_t* out_status) {
+    if (!ctx || !shapes || (n && (!pairs || !out_status || !out_ref_value || !out_distance))) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_gjk_distance: null argument", cudaSuccess);
+    int32_t rc;
+    if ((rc = check_n(ctx, n))) return rc;
+    if (n == 0) return BAM3D_OK;
+    CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
+    if ((rc = stage_pairs(ctx, pairs, n)) || (rc = ctx->status.reserve(ctx, n)) || (rc = ctx->f0.reserve(ctx, n * 4)) || (rc = ctx->f1.reserve(ctx, n * 4))) return rc;
+    if ((rc = bam3d_gjk_distance_dev(ctx, shapes, (const uint32_t*)ctx->pairs.ptr, n, settings, (float*)ctx->f0.ptr, (float*)ctx->f1.ptr,
+                                     (uint8_t*)ctx->status.ptr))) return rc;
+    CU_TRY(cudaMemcpyAsync(out_ref_value, ctx->f0.ptr, n * 4, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(ref)");
+    CU_TRY(cudaMemcpyAsync(out_distance, ctx->f1.ptr, n * 4, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(dist)");
+    CU_TRY(cudaMemcpyAsync(out_status, ctx->status.ptr, n, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(status)");
+    CU_TRY(cudaStreamSynchronize(ctx->stream), "bam3d_gjk_distance");
+    return BAM3D_OK;
+}
+
+int32_t bam3d_gjk_time_of_impact(bam3d_ctx* ctx, const bam3d_shapes* s0, const bam3d_shapes* s1, const uint32_t* pairs, uint64_t n,
+                                 const bam3d_gjk_settings* settings, bam3d_contact* out_contacts, uint8_t* out_status) {
+    if (!ctx || !s0 || !s1 || (n && (!pairs || !out_status || !out_contacts))) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_gjk_time_of_impact: null argument", cudaSuccess);
+    int32_t rc;
+    if ((rc = check_n(ctx, n))) return rc;
+    if (n == 0) return BAM3D_OK;
+    CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
+    if ((rc = stage_pairs(ctx, pairs, n)) || (rc = ctx->status.reserve(ctx, n)) || (rc = ctx->contacts.reserve(ctx, n * 32))) return rc;
+    if ((rc = bam3d_gjk_time_of_impact_dev(ctx, s0, s1, (const uint32_t*)ctx->pairs.ptr, n, settings, (bam3d_contact*)ctx->contacts.ptr,
+                                           (uint8_t*)ctx->status.ptr))) return rc;
+    CU_TRY(cudaMemcpyAsync(out_contacts, ctx->contacts.ptr, n * 32, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(contacts)");
+    CU_TRY(cudaMemcpyAsync(out_status, ctx->status.ptr, n, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(status)");
+    CU_TRY(cudaStreamSynchronize(ctx->stream), "bam3d_gjk_time_of_impact");
+    return BAM3D_OK;
+}
+
+}  // extern "C"

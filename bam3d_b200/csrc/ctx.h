@@ -1,0 +1,54 @@
+// Internal definitions of the opaque C-ABI handles (include/bam3d_gpu.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <string>
+
+struct bam3d_ctx;
+
+namespace b3 { struct ShapeRec; }
+
+struct DevBuf {  // grow-only device scratch owned by a ctx
+    void* ptr = nullptr;
+    size_t bytes = 0;
+    int32_t reserve(bam3d_ctx* ctx, size_t need);
+    void release();
+};
+
+struct bam3d_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+    bool opt_binning = true;
+    // scratch for the host-buffer entry points and the binning pass
+    DevBuf pairs, status, contacts, f0, f1, keys, order, small, epa_overflow;
+    // broad-phase scratch
+    DevBuf bp0, bp1, bp2, bp3, bp4, bp5, cub_tmp;
+    void release_scratch() {
+        DevBuf* all[] = {&pairs, &status, &contacts, &f0, &f1, &keys, &order, &small, &epa_overflow, &bp0, &bp1, &bp2, &bp3, &bp4, &bp5, &cub_tmp};
+        for (DevBuf* b : all) b->release();
+    }
+};
+
+struct bam3d_meshes {
+    float4* verts = nullptr;      // xyz + unused w
+    uint32_t* offsets = nullptr;  // n_meshes + 1
+    uint32_t n_meshes = 0;
+    uint64_t nverts = 0;
+};
+
+struct bam3d_shapes {
+    b3::ShapeRec* recs = nullptr;
+    uint32_t* meta = nullptr;
+    // inputs kept on the device so that set_transforms can re-pack without a re-upload of kinds / params
+    uint8_t* d_kind = nullptr;
+    float* d_params = nullptr;
+    float* d_xform = nullptr;
+    uint32_t* d_mesh_id = nullptr;
+    uint32_t n = 0;
+    const bam3d_meshes* meshes = nullptr;
+    uint32_t kind_hist[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+
+int32_t b3_fail(bam3d_ctx* ctx, int32_t code, const char* what, cudaError_t e);

@@ -1,0 +1,152 @@
+// EPA3 on the device. Reference: epa/epa3d.rs:16-190 (EPA3::process, Polytope, Face, remove_or_add_edge) and
+// contact()/point() (:70-94).
+//
+// The reference's tie-breaks are order-dependent — `closest_face_to_origin` keeps the FIRST minimum, `add`
+// walks the face list while `swap_remove`-ing, and the horizon is an ordered edge list with order-preserving
+// removal — and they decide which of several coplanar faces supplies the contact point. The device polytope
+// therefore keeps the same three ordered lists (vertices, faces, horizon edges) and mutates them in the same
+// order. Storage is supplied by the caller: per-thread local arrays for the thread-per-pair kernels, a per-warp
+// shared-memory slice for the warp-cooperative polyhedron kernels (all lanes then execute this code
+// redundantly on identical data and store identical values).
+#pragma once
+#include "simplex.cuh"
+#include "support.cuh"
+
+namespace b3 {
+
+// Capacities. EPA's loop counter starts at 1 and stops at max_iterations (<= 100, enforced by the host layer), so
+// at most 99 vertices are added to the 4 of the GJK tetrahedron: VCAP >= 103 always suffices. A closed
+// triangulated polytope has F = 2V - 4 <= 202 faces, but near-degenerate input (curved shapes, NaN normals)
+// makes the reference build pinched polytopes with many more (868 faces seen in 30k mixed contacts, 0.013 % of
+// pairs above 202). Two tiers therefore: the fast tier (per-thread local memory / per-warp shared memory) holds
+// EPA_FCAP faces; a pair that outgrows it gets ST_CAPACITY and is redone by the overflow kernel against a
+// global-memory slab with the EPA_BIG_* capacities. Only a pair that outgrows those keeps ST_CAPACITY.
+constexpr int EPA_VCAP = 104;
+constexpr int EPA_FCAP = 256;
+constexpr int EPA_ECAP = 320;
+constexpr int EPA_BIG_FCAP = 4096;
+constexpr int EPA_BIG_ECAP = 6144;
+
+struct PolytopeStore {
+    float* vv;        // EPA_VCAP * 3 : SupportPoint.v
+    float* va;        // EPA_VCAP * 3 : SupportPoint.sup_a
+    float4* fn;       // EPA_FCAP     : face normal xyz + distance
+    uint32_t* fi;     // EPA_FCAP     : face vertex indices, 8 bits each (a | b<<8 | c<<16)
+    uint16_t* ed;     // EPA_ECAP     : horizon edges (a | b<<8)
+    int fcap, ecap;   // capacities of fn/fi and ed
+};
+
+struct ContactOut { V3 normal; float depth; V3 point; };
+
+B3_DEV V3 ld3(const float* p, int i) { return v3(p[3 * i], p[3 * i + 1], p[3 * i + 2]); }
+B3_DEV void st3(float* p, int i, V3 v) { p[3 * i] = v.x; p[3 * i + 1] = v.y; p[3 * i + 2] = v.z; }
+
+// Face::new_impl (epa3d.rs:160-170)
+B3_DEV void make_face(const PolytopeStore& P, int slot, uint32_t a, uint32_t b, uint32_t c) {
+    V3 va = ld3(P.vv, a);
+    V3 ab = ld3(P.vv, b) - va;
+    V3 ac = ld3(P.vv, c) - va;
+    V3 n = normalize(cross(ab, ac));
+    float dist = dot(n, va);
+    P.fn[slot] = make_float4(n.x, n.y, n.z, dist);
+    P.fi[slot] = a | (b << 8) | (c << 16);
+}
+
+// remove_or_add_edge (epa3d.rs:183-190): a reversed duplicate is removed (order preserving), else push.
+B3_DEV bool remove_or_add_edge(uint16_t* ed, int& ne, int ecap, uint32_t a, uint32_t b) {
+    const uint16_t rev = (uint16_t)(b | (a << 8));
+    for (int i = 0; i < ne; ++i) {
+        if (ed[i] == rev) {
+            for (int k = i; k + 1 < ne; ++k) ed[k] = ed[k + 1];
+            --ne;
+            return true;
+        }
+    }
+    if (ne >= ecap) return false;
+    ed[ne++] = (uint16_t)(a | (b << 8));
+    return true;
+}
+
+// EPA3::process (epa3d.rs:16-52). `s` is the 4-point GJK simplex (with sup_a). Returns a Status.
+template <bool WARP>
+B3_DEV uint8_t epa_process(const Shape& L, const Shape& R, const Simplex<true>& s, float tolerance, uint32_t max_iterations,
+                           const PolytopeStore& P, ContactOut& out) {
+    // Polytope::new (epa3d.rs:103-109) + Face::new (:172-179)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { st3(P.vv, k, s.v[k]); st3(P.va, k, s.a[k]); }
+    if (WARP) __syncwarp();
+    int nv = 4, nf = 4;
+    make_face(P, 0, 3, 2, 1);
+    make_face(P, 1, 3, 1, 0);
+    make_face(P, 2, 3, 0, 2);
+    make_face(P, 3, 2, 0, 1);
+    if (WARP) __syncwarp();
+
+    uint32_t i = 1;
+    for (;;) {
+        // closest_face_to_origin (epa3d.rs:111-119): strict <, first minimum wins
+        int best = 0;
+        float best_d = P.fn[0].w;
+        for (int k = 1; k < nf; ++k) {
+            float dk = P.fn[k].w;
+            if (dk < best_d) { best_d = dk; best = k; }
+        }
+        float4 bf = P.fn[best];
+        V3 normal = v3(bf.x, bf.y, bf.z);
+        V3 pv, pa;
+        minkowski_support<WARP>(L, R, normal, pv, pa);
+        float d = dot(pv, normal);
+        if (d - bf.w < tolerance || i >= max_iterations) {
+            // contact() / point() (epa3d.rs:70-94)
+            uint32_t idx = P.fi[best];
+            uint32_t i0 = idx & 0xFF, i1 = (idx >> 8) & 0xFF, i2 = (idx >> 16) & 0xFF;
+            float u, v, w;
+            barycentric_vector(normal * bf.w, ld3(P.vv, i0), ld3(P.vv, i1), ld3(P.vv, i2), u, v, w);
+            out.normal = normal;
+            out.depth = bf.w;
+            out.point = ld3(P.va, i0) * u + ld3(P.va, i1) * v + ld3(P.va, i2) * w;
+            return ST_OK;
+        }
+
+        // Polytope::add (epa3d.rs:121-149)
+        int ne = 0;
+        int k = 0;
+        bool ok = true;
+        while (k < nf) {
+            float4 f = P.fn[k];
+            uint32_t idx = P.fi[k];
+            V3 v0 = ld3(P.vv, idx & 0xFF);
+            float dt = dot(v3(f.x, f.y, f.z), pv - v0);
+            if (dt > 0.f) {
+                --nf;                         // swap_remove(k)
+                float4 lf = P.fn[nf];
+                uint32_t li = P.fi[nf];
+                if (WARP) __syncwarp();
+                P.fn[k] = lf;
+                P.fi[k] = li;
+                uint32_t i0 = idx & 0xFF, i1 = (idx >> 8) & 0xFF, i2 = (idx >> 16) & 0xFF;
+                ok = ok && remove_or_add_edge(P.ed, ne, P.ecap, i0, i1);
+                ok = ok && remove_or_add_edge(P.ed, ne, P.ecap, i1, i2);
+                ok = ok && remove_or_add_edge(P.ed, ne, P.ecap, i2, i0);
+                if (WARP) __syncwarp();
+            } else {
+                ++k;
+            }
+        }
+        if (!ok || nv >= EPA_VCAP || nf + ne > P.fcap) return ST_CAPACITY;
+        const int n = nv;
+        st3(P.vv, n, pv);
+        st3(P.va, n, pa);
+        ++nv;
+        if (WARP) __syncwarp();
+        for (int e = 0; e < ne; ++e) {
+            uint32_t ab = P.ed[e];
+            make_face(P, nf + e, (uint32_t)n, ab & 0xFF, (ab >> 8) & 0xFF);
+        }
+        nf += ne;
+        if (WARP) __syncwarp();
+        i += 1;
+    }
+}
+
+}  // namespace b3

@@ -1,0 +1,484 @@
+// Narrow-phase kernels for sm_100a: shape packing, pair binning, and batched GJK intersect / contact (GJK+EPA) /
+// distance / time of impact. Two execution shapes per query:
+//   * thread-per-pair  — analytic supports (sphere, cuboid, cylinder, capsule, quad, particle); simplex in
+//     registers; EPA polytope in per-thread local memory;
+//   * warp-per-pair    — any pair that involves a ConvexPolyhedron: the 32 lanes stride the vertex list and
+//     arg-max by shuffle (support.cuh); everything else runs redundantly on identical data in all lanes, with the
+//     EPA polytope in a per-warp shared-memory slice.
+// Pairs are first binned by (kindL, kindR) so that a warp of the thread-per-pair kernel runs one support code
+// path; polyhedron pairs form the last bin and are routed to the warp kernel.
+//
+// Plain FP32 SIMT: there is no dense contraction anywhere in this path, so tensor cores / TMEM are not used.
+// Compiled with -fmad=false (see vecmath.cuh).
+#include "narrow.h"
+#include "gjk.cuh"
+
+namespace b3 {
+
+constexpr int TPB = 128;            // threads per block, every kernel in this file
+constexpr int WARPS_PER_BLOCK = TPB / 32;
+constexpr int NUM_SMS = 148;        // B200
+constexpr uint32_t KEY_WARP = 49;   // bin of the pairs that involve a polyhedron (thread bins are 0..48)
+constexpr uint32_t ERR_NON_AFFINE = 1u, ERR_BAD_KIND = 2u, ERR_BAD_MESH = 4u;
+
+// ------------------------------------------------------------------------------------------------------------
+// pack_shapes: Mat4 (16 f32, column-major) + params -> 96-byte ShapeRec with the inverse's linear part.
+// The inverse is glam 0.8's scalar Mat4::inverse (GLM cofactor expansion) evaluated on all 16 inputs in glam's
+// order; only its upper-left 3x3 is kept because the reference only ever applies the inverse through
+// transform_vector3 (primitive/util.rs:11, sphere.rs:22, cylinder.rs:39, capsule.rs:43, polyhedron.rs:346-350).
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB) pack_shapes_kernel(const uint8_t* __restrict__ kind, const float4* __restrict__ params,
+                                                          const float4* __restrict__ xform, const uint32_t* __restrict__ mesh_id,
+                                                          uint32_t n, uint32_t n_meshes, ShapeRec* __restrict__ recs,
+                                                          uint32_t* __restrict__ meta, uint32_t* __restrict__ err) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 cx = xform[4 * (size_t)i + 0], cy = xform[4 * (size_t)i + 1], cz = xform[4 * (size_t)i + 2], cw = xform[4 * (size_t)i + 3];
+    float m00 = cx.x, m01 = cx.y, m02 = cx.z, m03 = cx.w;
+    float m10 = cy.x, m11 = cy.y, m12 = cy.z, m13 = cy.w;
+    float m20 = cz.x, m21 = cz.y, m22 = cz.z, m23 = cz.w;
+    float m30 = cw.x, m31 = cw.y, m32 = cw.z, m33 = cw.w;
+    uint32_t e = 0;
+    if (!(m03 == 0.f && m13 == 0.f && m23 == 0.f && m33 == 1.f)) e |= ERR_NON_AFFINE;
+
+    float coef00 = m22 * m33 - m32 * m23, coef02 = m12 * m33 - m32 * m13;
+    float coef04 = m21 * m33 - m31 * m23, coef06 = m11 * m33 - m31 * m13;
+    float coef08 = m21 * m32 - m31 * m22, coef10 = m11 * m32 - m31 * m12;
+    float coef12 = m20 * m33 - m30 * m23, coef14 = m10 * m33 - m30 * m13;
+    float coef16 = m20 * m32 - m30 * m22, coef18 = m10 * m32 - m30 * m12;
+    float coef20 = m20 * m31 - m30 * m21, coef22 = m10 * m31 - m30 * m11;
+    // (coef03/07/11/15/19/23 only feed the w row of the inverse, which is never applied)
+    // inv_k = vec * fac - vec * fac + vec * fac, per component (x, y, z of each column)
+    // fac0 = (c00,c00,c02,c03) fac1 = (c04,c04,c06,c07) fac2 = (c08,c08,c10,c11)
+    // fac3 = (c12,c12,c14,c15) fac4 = (c16,c16,c18,c19) fac5 = (c20,c20,c22,c23)
+    // vec0 = (m10,m00,m00,m00) vec1 = (m11,m01,m01,m01) vec2 = (m12,m02,m02,m02) vec3 = (m13,m03,m03,m03)
+    float inv0x = m11 * coef00 - m12 * coef04 + m13 * coef08;
+    float inv0y = m01 * coef00 - m02 * coef04 + m03 * coef08;
+    float inv0z = m01 * coef02 - m02 * coef06 + m03 * coef10;
+    float inv1x = m10 * coef00 - m12 * coef12 + m13 * coef16;
+    float inv1y = m00 * coef00 - m02 * coef12 + m03 * coef16;
+    float inv1z = m00 * coef02 - m02 * coef14 + m03 * coef18;
+    float inv2x = m10 * coef04 - m11 * coef12 + m13 * coef20;
+    float inv2y = m00 * coef04 - m01 * coef12 + m03 * coef20;
+    float inv2z = m00 * coef06 - m01 * coef14 + m03 * coef22;
+    float inv3x = m10 * coef08 - m11 * coef16 + m12 * coef20;
+    // signs: columns 0 and 2 use (+,-,+,-), columns 1 and 3 use (-,+,-,+)
+    float i0x = inv0x * 1.0f, i0y = inv0y * -1.0f, i0z = inv0z * 1.0f;
+    float i1x = inv1x * -1.0f, i1y = inv1y * 1.0f, i1z = inv1z * -1.0f;
+    float i2x = inv2x * 1.0f, i2y = inv2y * -1.0f, i2z = inv2z * 1.0f;
+    float i3x = inv3x * -1.0f;
+    // det = dot(x_axis, (inv0.x, inv1.x, inv2.x, inv3.x)), summed left to right
+    float dot1 = ((m00 * i0x + m01 * i1x) + m02 * i2x) + m03 * i3x;
+    float rcp = 1.0f / dot1;
+    i0x *= rcp; i0y *= rcp; i0z *= rcp;
+    i1x *= rcp; i1y *= rcp; i1z *= rcp;
+    i2x *= rcp; i2y *= rcp; i2z *= rcp;
+
+    float4 p = params[i];
+    uint32_t k = kind[i];
+    if (k >= K_COUNT) e |= ERR_BAD_KIND;
+    uint32_t mid = 0;
+    if (k == K_POLYHEDRON) {
+        mid = mesh_id ? mesh_id[i] : 0xFFFFFFFFu;
+        if (mid >= n_meshes || mid >= (1u << 24)) { e |= ERR_BAD_MESH; mid = 0; }
+    }
+    float4* q = reinterpret_cast<float4*>(recs + i);
+    q[0] = make_float4(m00, m01, m02, m10);
+    q[1] = make_float4(m11, m12, m20, m21);
+    q[2] = make_float4(m22, m30, m31, m32);
+    q[3] = make_float4(i0x, i0y, i0z, i1x);
+    q[4] = make_float4(i1y, i1z, i2x, i2y);
+    q[5] = make_float4(i2z, p.x, p.y, p.z);
+    meta[i] = k | (mid << 8);
+    if (e) atomicOr(err, e);
+}
+
+__global__ void __launch_bounds__(TPB) pack_meshes_kernel(const float* __restrict__ xyz, uint64_t nverts, float4* __restrict__ out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nverts) out[i] = make_float4(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], 0.f);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// pair binning: counting sort of pair indices on key = kindL * 7 + kindR (polyhedron pairs -> KEY_WARP)
+// ------------------------------------------------------------------------------------------------------------
+B3_DEV uint32_t pair_key(uint32_t ml, uint32_t mr) {
+    uint32_t kl = ml & 0xFF, kr = mr & 0xFF;
+    return (kl == K_POLYHEDRON || kr == K_POLYHEDRON) ? KEY_WARP : kl * 7 + kr;
+}
+
+__global__ void __launch_bounds__(TPB) bin_hist_kernel(const uint32_t* __restrict__ meta, const uint2* __restrict__ pairs, uint32_t n,
+                                                       uint8_t* __restrict__ keys, uint32_t* __restrict__ hist) {
+    __shared__ uint32_t sh[64];
+    if (threadIdx.x < 64) sh[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint2 pr = __ldg(pairs + i);
+        uint32_t key = pair_key(__ldg(meta + pr.x), __ldg(meta + pr.y));
+        keys[i] = (uint8_t)key;
+        atomicAdd(&sh[key], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < 64 && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
+}
+
+__global__ void bin_scan_kernel(const uint32_t* __restrict__ hist, uint32_t* __restrict__ start, uint32_t* __restrict__ cursor,
+                                uint32_t* __restrict__ ranges, uint32_t n) {
+    if (threadIdx.x == 0) {
+        uint32_t acc = 0;
+        for (int k = 0; k < 64; ++k) { start[k] = acc; cursor[k] = acc; acc += hist[k]; }
+        ranges[0] = 0; ranges[1] = start[KEY_WARP]; ranges[2] = start[KEY_WARP]; ranges[3] = n;
+    }
+}
+
+__global__ void __launch_bounds__(TPB) bin_scatter_kernel(const uint8_t* __restrict__ keys, uint32_t n, uint32_t* __restrict__ cursor,
+                                                          uint32_t* __restrict__ order) {
+    // one tile of TPB pairs per block iteration: count per bin in shared memory, reserve a global range per bin,
+    // then every thread writes its pair index at (range base + its rank inside the tile's bin)
+    __shared__ uint32_t cnt[64];
+    __shared__ uint32_t base[64];
+    for (uint32_t tile = blockIdx.x * TPB; tile < n; tile += gridDim.x * TPB) {
+        if (threadIdx.x < 64) cnt[threadIdx.x] = 0;
+        __syncthreads();
+        uint32_t i = tile + threadIdx.x;
+        uint32_t key = 0, rank = 0;
+        bool valid = i < n;
+        if (valid) {
+            key = keys[i];
+            // warp-aggregated shared atomic: one atomic per distinct key per warp
+            uint32_t peers = __match_any_sync(__activemask(), key);
+            uint32_t lane = threadIdx.x & 31u;
+            uint32_t leader = __ffs(peers) - 1;
+            uint32_t wbase = 0;
+            if (lane == leader) wbase = atomicAdd(&cnt[key], __popc(peers));
+            wbase = __shfl_sync(peers, wbase, leader);
+            rank = wbase + __popc(peers & ((1u << lane) - 1u));
+        }
+        __syncthreads();
+        if (threadIdx.x < 64 && cnt[threadIdx.x]) base[threadIdx.x] = atomicAdd(&cursor[threadIdx.x], cnt[threadIdx.x]);
+        __syncthreads();
+        if (valid) order[base[key] + rank] = i;
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// pair loading
+// ------------------------------------------------------------------------------------------------------------
+B3_DEV void load_pair_shape(Shape& s, const ShapeSetDev& S, uint32_t idx) {
+    load_shape(s, S.recs, idx);
+    uint32_t m = __ldg(S.meta + idx);
+    s.kind = m & 0xFF;
+    s.verts = nullptr;
+    s.nverts = 0;
+    if (s.kind == K_POLYHEDRON) {
+        uint32_t mid = m >> 8;
+        uint32_t b = __ldg(S.mesh_offsets + mid), e = __ldg(S.mesh_offsets + mid + 1);
+        s.verts = S.mesh_verts + b;
+        s.nverts = e - b;
+    }
+}
+
+// Work distribution. Thread kernels: item t of [begin, end) per thread, grid-stride. Warp kernels: one item per
+// warp, grid-stride over warps. `order` (nullable) maps a sorted slot to the pair index.
+template <bool WARP>
+B3_DEV void work_range(const uint32_t* ranges, uint32_t n, uint32_t& first, uint32_t& end, uint32_t& stride) {
+    uint32_t begin = 0;
+    end = n;
+    if (ranges) { begin = ranges[WARP ? 2 : 0]; end = ranges[WARP ? 3 : 1]; }
+    if (WARP) {
+        first = begin + (blockIdx.x * blockDim.x + threadIdx.x) / 32;
+        stride = gridDim.x * blockDim.x / 32;
+    } else {
+        first = begin + blockIdx.x * blockDim.x + threadIdx.x;
+        stride = gridDim.x * blockDim.x;
+    }
+}
+
+struct WarpPolytopeSmem {
+    float vv[EPA_VCAP * 3];
+    float va[EPA_VCAP * 3];
+    float4 fn[EPA_FCAP];
+    uint32_t fi[EPA_FCAP];
+    uint16_t ed[EPA_ECAP];
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// GJK::intersect
+// ------------------------------------------------------------------------------------------------------------
+template <bool WARP>
+__global__ void __launch_bounds__(TPB) gjk_intersect_kernel(ShapeSetDev S, const uint2* __restrict__ pairs, uint32_t n,
+                                                            const uint32_t* __restrict__ order, const uint32_t* __restrict__ ranges,
+                                                            SettingsDev cfg, uint8_t* __restrict__ status) {
+    uint32_t first, end, stride;
+    work_range<WARP>(ranges, n, first, end, stride);
+    for (uint32_t slot = first; slot < end; slot += stride) {
+        uint32_t p = order ? __ldg(order + slot) : slot;
+        uint2 pr = __ldg(pairs + p);
+        Shape L, R;
+        load_pair_shape(L, S, pr.x);
+        load_pair_shape(R, S, pr.y);
+        Simplex<false> s;
+        uint8_t st = gjk_intersect<WARP, false>(L, R, cfg.max_iterations, s);
+        if (!WARP || (threadIdx.x & 31) == 0) status[p] = st;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// GJK::intersection = intersect + EPA3::process (FullResolution) or Contact::new(CollisionOnly)
+// ------------------------------------------------------------------------------------------------------------
+template <bool WARP>
+__global__ void __launch_bounds__(TPB) gjk_contact_kernel(ShapeSetDev S, const uint2* __restrict__ pairs, uint32_t n,
+                                                          const uint32_t* __restrict__ order, const uint32_t* __restrict__ ranges,
+                                                          SettingsDev cfg, int strategy, float4* __restrict__ contacts,
+                                                          uint8_t* __restrict__ status) {
+    extern __shared__ __align__(16) unsigned char dyn_smem[];  // WARP: WARPS_PER_BLOCK polytope slices; else unused
+    // thread-per-pair polytope: per-thread local memory (L1/L2-backed), indexed identically by all lanes
+    float lvv[WARP ? 1 : EPA_VCAP * 3];
+    float lva[WARP ? 1 : EPA_VCAP * 3];
+    float4 lfn[WARP ? 1 : EPA_FCAP];
+    uint32_t lfi[WARP ? 1 : EPA_FCAP];
+    uint16_t led[WARP ? 1 : EPA_ECAP];
+    PolytopeStore P;
+    if (WARP) {
+        WarpPolytopeSmem& w = reinterpret_cast<WarpPolytopeSmem*>(dyn_smem)[threadIdx.x / 32];
+        P.vv = w.vv; P.va = w.va; P.fn = w.fn; P.fi = w.fi; P.ed = w.ed;
+    } else {
+        P.vv = lvv; P.va = lva; P.fn = lfn; P.fi = lfi; P.ed = led;
+    }
+    P.fcap = EPA_FCAP; P.ecap = EPA_ECAP;
+    uint32_t first, end, stride;
+    work_range<WARP>(ranges, n, first, end, stride);
+    for (uint32_t slot = first; slot < end; slot += stride) {
+        uint32_t p = order ? __ldg(order + slot) : slot;
+        uint2 pr = __ldg(pairs + p);
+        Shape L, R;
+        load_pair_shape(L, S, pr.x);
+        load_pair_shape(R, S, pr.y);
+        Simplex<true> s;
+        uint8_t st = gjk_intersect<WARP, true>(L, R, cfg.max_iterations, s);
+        ContactOut c;
+        c.normal = v3(0.f, 0.f, 0.f); c.depth = 0.f; c.point = v3(0.f, 0.f, 0.f);
+        if (st == ST_OK && strategy == 0) {
+            st = epa_process<WARP>(L, R, s, cfg.epa_tolerance, cfg.max_iterations, P, c);
+            if (st != ST_OK) { c.normal = v3(0.f, 0.f, 0.f); c.depth = 0.f; c.point = v3(0.f, 0.f, 0.f); }
+        }
+        if (!WARP || (threadIdx.x & 31) == 0) {
+            contacts[2 * (size_t)p] = make_float4(c.normal.x, c.normal.y, c.normal.z, c.depth);
+            contacts[2 * (size_t)p + 1] = make_float4(c.point.x, c.point.y, c.point.z, 0.f);
+            status[p] = st;
+        }
+        if (WARP) __syncwarp();
+    }
+}
+
+// Overflow tier of the contact kernels: redo every pair the fast tier left at ST_CAPACITY, one thread per pair,
+// against a per-thread global-memory slab with the EPA_BIG_* capacities. Rare (~1e-4 of contacts), so a small
+// fixed grid scans the status array. Polyhedron supports are scanned sequentially here.
+constexpr int OVF_BLOCKS = 8;
+constexpr size_t OVF_SLAB_BYTES = (size_t)EPA_VCAP * 3 * 4 * 2 + (size_t)EPA_BIG_FCAP * (16 + 4) + (size_t)EPA_BIG_ECAP * 2;
+
+__global__ void __launch_bounds__(TPB) gjk_contact_overflow_kernel(ShapeSetDev S, const uint2* __restrict__ pairs, uint32_t n, SettingsDev cfg,
+                                                                   unsigned char* __restrict__ slabs, float4* __restrict__ contacts,
+                                                                   uint8_t* __restrict__ status) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned char* slab = slabs + (size_t)tid * OVF_SLAB_BYTES;
+    PolytopeStore P;
+    P.fn = reinterpret_cast<float4*>(slab);                       slab += (size_t)EPA_BIG_FCAP * 16;
+    P.fi = reinterpret_cast<uint32_t*>(slab);                     slab += (size_t)EPA_BIG_FCAP * 4;
+    P.vv = reinterpret_cast<float*>(slab);                        slab += (size_t)EPA_VCAP * 12;
+    P.va = reinterpret_cast<float*>(slab);                        slab += (size_t)EPA_VCAP * 12;
+    P.ed = reinterpret_cast<uint16_t*>(slab);
+    P.fcap = EPA_BIG_FCAP; P.ecap = EPA_BIG_ECAP;
+    for (uint32_t p = tid; p < n; p += gridDim.x * blockDim.x) {
+        if (status[p] != ST_CAPACITY) continue;
+        uint2 pr = __ldg(pairs + p);
+        Shape L, R;
+        load_pair_shape(L, S, pr.x);
+        load_pair_shape(R, S, pr.y);
+        Simplex<true> s;
+        uint8_t st = gjk_intersect<false, true>(L, R, cfg.max_iterations, s);
+        ContactOut c;
+        c.normal = v3(0.f, 0.f, 0.f); c.depth = 0.f; c.point = v3(0.f, 0.f, 0.f);
+        if (st == ST_OK) {
+            st = epa_process<false>(L, R, s, cfg.epa_tolerance, cfg.max_iterations, P, c);
+            if (st != ST_OK) { c.normal = v3(0.f, 0.f, 0.f); c.depth = 0.f; c.point = v3(0.f, 0.f, 0.f); }
+        }
+        contacts[2 * (size_t)p] = make_float4(c.normal.x, c.normal.y, c.normal.z, c.depth);
+        contacts[2 * (size_t)p + 1] = make_float4(c.point.x, c.point.y, c.point.z, 0.f);
+        status[p] = st;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// GJK::distance
+// ------------------------------------------------------------------------------------------------------------
+template <bool WARP>
+__global__ void __launch_bounds__(TPB) gjk_distance_kernel(ShapeSetDev S, const uint2* __restrict__ pairs, uint32_t n,
+                                                           const uint32_t* __restrict__ order, const uint32_t* __restrict__ ranges,
+                                                           SettingsDev cfg, float* __restrict__ out_ref, float* __restrict__ out_geo,
+                                                           uint8_t* __restrict__ status) {
+    uint32_t first, end, stride;
+    work_range<WARP>(ranges, n, first, end, stride);
+    for (uint32_t slot = first; slot < end; slot += stride) {
+        uint32_t p = order ? __ldg(order + slot) : slot;
+        uint2 pr = __ldg(pairs + p);
+        Shape L, R;
+        load_pair_shape(L, S, pr.x);
+        load_pair_shape(R, S, pr.y);
+        float rv = 0.f, geo = 0.f;
+        uint8_t st = gjk_distance<WARP>(L, R, cfg.distance_tolerance, cfg.max_iterations, rv, geo);
+        if (st != ST_OK) { rv = 0.f; geo = 0.f; }
+        if (!WARP || (threadIdx.x & 31) == 0) { out_ref[p] = rv; out_geo[p] = geo; status[p] = st; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// GJK::intersection_time_of_impact
+// ------------------------------------------------------------------------------------------------------------
+template <bool WARP>
+__global__ void __launch_bounds__(TPB) gjk_toi_kernel(ShapeSetDev S0, ShapeSetDev S1, const uint2* __restrict__ pairs, uint32_t n,
+                                                      const uint32_t* __restrict__ order, const uint32_t* __restrict__ ranges,
+                                                      SettingsDev cfg, float4* __restrict__ contacts, uint8_t* __restrict__ status) {
+    uint32_t first, end, stride;
+    work_range<WARP>(ranges, n, first, end, stride);
+    for (uint32_t slot = first; slot < end; slot += stride) {
+        uint32_t p = order ? __ldg(order + slot) : slot;
+        uint2 pr = __ldg(pairs + p);
+        Shape L0, R0, L1, R1;
+        load_pair_shape(L0, S0, pr.x);
+        load_pair_shape(R0, S0, pr.y);
+        // only the end transforms' affine columns are read (translation deltas; the right end transform's
+        // rotation/scale for the contact point)
+        load_shape(L1, S1.recs, pr.x);
+        load_shape(R1, S1.recs, pr.y);
+        ContactOut c;
+        c.normal = v3(0.f, 0.f, 0.f); c.depth = 0.f; c.point = v3(0.f, 0.f, 0.f);
+        float toi = 0.f;
+        uint8_t st = gjk_time_of_impact<WARP>(L0, L1, R0, R1, cfg.continuous_tolerance, cfg.toi_iteration_cap, c, toi);
+        if (st != ST_OK) { c.normal = v3(0.f, 0.f, 0.f); c.depth = 0.f; c.point = v3(0.f, 0.f, 0.f); toi = 0.f; }
+        if (!WARP || (threadIdx.x & 31) == 0) {
+            contacts[2 * (size_t)p] = make_float4(c.normal.x, c.normal.y, c.normal.z, c.depth);
+            contacts[2 * (size_t)p + 1] = make_float4(c.point.x, c.point.y, c.point.z, toi);
+            status[p] = st;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// contact compaction (hits only, tagged with the global pair index) — feeds the multi-GPU gather
+// ------------------------------------------------------------------------------------------------------------
+struct Contact40 { uint32_t pair_index, status; float4 a, b; };
+
+__global__ void __launch_bounds__(TPB) compact_contacts_kernel(const float4* __restrict__ contacts, const uint8_t* __restrict__ status,
+                                                               uint64_t n, uint64_t base, uint32_t* __restrict__ out, uint64_t capacity,
+                                                               unsigned long long* __restrict__ count) {
+    const uint32_t lane = threadIdx.x & 31u;
+    for (uint64_t i0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~31ull; i0 < n; i0 += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t i = i0 + lane;
+        bool hit = (i < n) && status[i] == ST_OK;
+        uint32_t mask = __ballot_sync(0xFFFFFFFFu, hit);
+        if (mask == 0) continue;
+        unsigned long long wbase = 0;
+        if (lane == 0) wbase = atomicAdd(count, (unsigned long long)__popc(mask));
+        wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
+        if (hit) {
+            uint64_t slot = wbase + __popc(mask & ((1u << lane) - 1u));
+            if (slot < capacity) {
+                float4 a = contacts[2 * i], b = contacts[2 * i + 1];
+                uint32_t* o = out + slot * 10;  // 40-byte records
+                o[0] = (uint32_t)(base + i); o[1] = ST_OK;
+                o[2] = __float_as_uint(a.x); o[3] = __float_as_uint(a.y); o[4] = __float_as_uint(a.z); o[5] = __float_as_uint(a.w);
+                o[6] = __float_as_uint(b.x); o[7] = __float_as_uint(b.y); o[8] = __float_as_uint(b.z); o[9] = __float_as_uint(b.w);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------------------
+static inline int grid_for(uint64_t items, int per_block, int max_blocks) {
+    uint64_t g = (items + per_block - 1) / per_block;
+    if (g < 1) g = 1;
+    if (g > (uint64_t)max_blocks) g = max_blocks;
+    return (int)g;
+}
+
+int launch_pack_shapes(cudaStream_t st, const uint8_t* d_kind, const float* d_params, const float* d_xform,
+                       const uint32_t* d_mesh_id, uint32_t n, uint32_t n_meshes, ShapeRec* recs, uint32_t* meta, uint32_t* d_err) {
+    if (n == 0) return 0;
+    pack_shapes_kernel<<<(n + TPB - 1) / TPB, TPB, 0, st>>>(d_kind, reinterpret_cast<const float4*>(d_params),
+                                                            reinterpret_cast<const float4*>(d_xform), d_mesh_id, n, n_meshes, recs, meta, d_err);
+    return 1;
+}
+
+int launch_pack_meshes(cudaStream_t st, const float* d_xyz, uint64_t nverts, float4* out) {
+    if (nverts == 0) return 0;
+    pack_meshes_kernel<<<(unsigned)((nverts + TPB - 1) / TPB), TPB, 0, st>>>(d_xyz, nverts, out);
+    return 1;
+}
+
+int launch_bin_pairs(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs, uint32_t n, const BinScratch& B) {
+    cudaMemsetAsync(B.hist, 0, 64 * sizeof(uint32_t), st);
+    int g = grid_for(n, TPB, NUM_SMS * 8);
+    bin_hist_kernel<<<g, TPB, 0, st>>>(S.meta, d_pairs, n, B.keys, B.hist);
+    bin_scan_kernel<<<1, 32, 0, st>>>(B.hist, B.start, B.cursor, B.ranges, n);
+    bin_scatter_kernel<<<g, TPB, 0, st>>>(B.keys, n, B.cursor, B.order);
+    return 3;
+}
+
+// Thread kernels: grid-stride with enough blocks to fill the machine several times over (iteration counts vary
+// per pair, so small blocks and many of them balance better than one fat wave). Warp kernels: one pair per warp.
+static inline int thread_grid(uint32_t n) { return grid_for(n, TPB, NUM_SMS * 32); }
+static inline int warp_grid(uint32_t n) { return grid_for(n, WARPS_PER_BLOCK, NUM_SMS * 32); }
+
+// run_thread / run_warp select the execution shapes; with a BinScratch both read their ranges from device memory,
+// without one the selected kernel covers all n pairs (the thread kernel scans polyhedron vertices sequentially,
+// so "thread only" is always correct, just slow for polyhedra).
+#define B3_LAUNCH(KERNEL, SMEM_WARP, ...)                                                                       \
+    int launched = 0;                                                                                            \
+    const uint32_t* order = B ? B->order : nullptr;                                                              \
+    const uint32_t* ranges = B ? B->ranges : nullptr;                                                            \
+    if (n == 0) return 0;                                                                                        \
+    if (run_thread) { KERNEL<false><<<thread_grid(n), TPB, 0, st>>>(__VA_ARGS__); ++launched; }                  \
+    if (run_warp) { KERNEL<true><<<warp_grid(n), TPB, SMEM_WARP, st>>>(__VA_ARGS__); ++launched; }               \
+    return launched;
+
+int launch_intersect(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs, uint32_t n, const BinScratch* B, bool run_thread,
+                     bool run_warp, const SettingsDev& cfg, uint8_t* d_status) {
+    B3_LAUNCH(gjk_intersect_kernel, 0, S, d_pairs, n, order, ranges, cfg, d_status)
+}
+static int launch_contact_main(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs, uint32_t n, const BinScratch* B, bool run_thread,
+                               bool run_warp, const SettingsDev& cfg, int strategy, float4* d_contacts, uint8_t* d_status) {
+    B3_LAUNCH(gjk_contact_kernel, WARPS_PER_BLOCK * sizeof(WarpPolytopeSmem), S, d_pairs, n, order, ranges, cfg, strategy, d_contacts, d_status)
+}
+size_t contact_overflow_scratch_bytes() { return (size_t)OVF_BLOCKS * TPB * OVF_SLAB_BYTES; }
+int launch_contact(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs, uint32_t n, const BinScratch* B, bool run_thread,
+                   bool run_warp, const SettingsDev& cfg, int strategy, void* d_overflow_scratch, float4* d_contacts, uint8_t* d_status) {
+    int launched = launch_contact_main(st, S, d_pairs, n, B, run_thread, run_warp, cfg, strategy, d_contacts, d_status);
+    if (n && strategy == 0) {
+        gjk_contact_overflow_kernel<<<OVF_BLOCKS, TPB, 0, st>>>(S, d_pairs, n, cfg, reinterpret_cast<unsigned char*>(d_overflow_scratch),
+                                                               d_contacts, d_status);
+        ++launched;
+    }
+    return launched;
+}
+int launch_distance(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs, uint32_t n, const BinScratch* B, bool run_thread,
+                    bool run_warp, const SettingsDev& cfg, float* d_ref, float* d_geo, uint8_t* d_status) {
+    B3_LAUNCH(gjk_distance_kernel, 0, S, d_pairs, n, order, ranges, cfg, d_ref, d_geo, d_status)
+}
+int launch_toi(cudaStream_t st, const ShapeSetDev& S0, const ShapeSetDev& S1, const uint2* d_pairs, uint32_t n, const BinScratch* B,
+               bool run_thread, bool run_warp, const SettingsDev& cfg, float4* d_contacts, uint8_t* d_status) {
+    B3_LAUNCH(gjk_toi_kernel, 0, S0, S1, d_pairs, n, order, ranges, cfg, d_contacts, d_status)
+}
+
+int launch_compact_contacts(cudaStream_t st, const float4* d_contacts, const uint8_t* d_status, uint64_t n, uint64_t base, void* d_out,
+                            uint64_t capacity, unsigned long long* d_count) {
+    cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), st);
+    if (n == 0) return 0;
+    compact_contacts_kernel<<<grid_for(n, TPB, NUM_SMS * 16), TPB, 0, st>>>(d_contacts, d_status, n, base,
+                                                                              reinterpret_cast<uint32_t*>(d_out), capacity, d_count);
+    return 1;
+}
+
+}  // namespace b3

@@ -1,0 +1,56 @@
+// Host-callable launchers of the narrow-phase kernels (implemented in narrow.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace b3 {
+
+struct ShapeRec;
+
+// Device view of a packed shape set (bam3d_shapes) and its mesh library.
+struct ShapeSetDev {
+    const ShapeRec* recs;          // n x 96 B
+    const uint32_t* meta;          // n : kind | mesh_id << 8
+    const float4* mesh_verts;      // polyhedron vertices (xyz, w unused)
+    const uint32_t* mesh_offsets;  // n_meshes + 1
+    uint32_t n;
+};
+
+struct SettingsDev {
+    float distance_tolerance, continuous_tolerance, epa_tolerance;
+    uint32_t max_iterations, toi_iteration_cap;
+};
+
+// Scratch the binning pass needs (owned by the ctx, sized for n pairs).
+struct BinScratch {
+    uint8_t* keys;     // n
+    uint32_t* order;   // n : pair indices, thread-path pairs grouped by (kindL,kindR) first, polyhedron pairs last
+    uint32_t* hist;    // 64 : per-bin counts
+    uint32_t* start;   // 64 : per-bin start offsets
+    uint32_t* cursor;  // 64 : per-bin running cursors
+    uint32_t* ranges;  // 4  : [0]=thread begin, [1]=thread end, [2]=warp begin, [3]=warp end
+};
+
+// Each launcher returns the number of kernels it enqueued (for the launch counter); errors via cudaGetLastError.
+int launch_pack_shapes(cudaStream_t st, const uint8_t* d_kind, const float* d_params, const float* d_xform,
+                       const uint32_t* d_mesh_id, uint32_t n, uint32_t n_meshes, ShapeRec* recs, uint32_t* meta,
+                       uint32_t* d_err);
+int launch_pack_meshes(cudaStream_t st, const float* d_xyz, uint64_t nverts, float4* out);
+int launch_bin_pairs(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs, uint32_t n, const BinScratch& B);
+
+// B may be null (no binning: the selected kernel covers every pair). run_thread / run_warp pick the execution shapes.
+int launch_intersect(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs, uint32_t n, const BinScratch* B,
+                     bool run_thread, bool run_warp, const SettingsDev& cfg, uint8_t* d_status);
+// d_overflow_scratch: contact_overflow_scratch_bytes() of device memory for the EPA overflow tier (see epa.cuh).
+size_t contact_overflow_scratch_bytes();
+int launch_contact(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs, uint32_t n, const BinScratch* B,
+                   bool run_thread, bool run_warp, const SettingsDev& cfg, int strategy, void* d_overflow_scratch,
+                   float4* d_contacts, uint8_t* d_status);
+int launch_distance(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs, uint32_t n, const BinScratch* B,
+                    bool run_thread, bool run_warp, const SettingsDev& cfg, float* d_ref, float* d_geo, uint8_t* d_status);
+int launch_toi(cudaStream_t st, const ShapeSetDev& S0, const ShapeSetDev& S1, const uint2* d_pairs, uint32_t n,
+               const BinScratch* B, bool run_thread, bool run_warp, const SettingsDev& cfg, float4* d_contacts, uint8_t* d_status);
+int launch_compact_contacts(cudaStream_t st, const float4* d_contacts, const uint8_t* d_status, uint64_t n,
+                            uint64_t base, void* d_out, uint64_t capacity, unsigned long long* d_count);
+
+}  // namespace b3

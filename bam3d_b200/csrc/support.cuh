@@ -1,0 +1,150 @@
+// Minkowski support functions for the bam3d primitives, one device function per primitive.
+// Reference semantics: Primitive::support_point (traits.rs:78-100) as implemented in primitive/*.rs — the
+// world direction goes to local space with transform.inverse().transform_vector3, the local farthest point is
+// found, and transform.transform_point3 brings it back. The inverse is a pure function of the transform, so
+// it is computed once per shape (pack_shapes_kernel) instead of once per call; results are bit-identical.
+#pragma once
+#include "vecmath.cuh"
+
+namespace b3 {
+
+// Kind numbering follows `enum Primitive3` (primitive3.rs:16-33); Cube is a Cuboid (cuboid.rs:133-137).
+enum Kind : uint32_t { K_PARTICLE = 0, K_QUAD = 1, K_SPHERE = 2, K_CUBOID = 3, K_CYLINDER = 4, K_CAPSULE = 5, K_POLYHEDRON = 6, K_COUNT = 7 };
+
+// get_max_point over the 8 cached cuboid corners (cuboid.rs:46-64, primitive/util.rs:7-23): fold from
+// (zero, -inf) with strict `>`, so the FIRST maximum in the reference's corner order wins. The eight dot
+// products (cx*dx + cy*dy) + cz*dz share the three products a=hx*dx, b=hy*dy, c=hz*dz: negating a factor
+// negates the rounded product, and (-a)+(-b) == -(a+b), (-a)+b == -(a-b) in IEEE arithmetic (up to the sign
+// of an exact zero, which no comparison sees), so 2 adds + 8 adds reproduce all eight dots bit-for-bit.
+B3_DEV V3 cuboid_local_support(float hx, float hy, float hz, V3 d) {
+    float a = hx * d.x, b = hy * d.y, c = hz * d.z;
+    float s1 = a + b, s2 = a - b;
+    float best = -INFINITY;
+    int idx = 8;
+    float t;
+    t = s1 + c;  if (t > best) { best = t; idx = 0; }   // ( hx,  hy,  hz)
+    t = -s2 + c; if (t > best) { best = t; idx = 1; }   // (-hx,  hy,  hz)
+    t = -s1 + c; if (t > best) { best = t; idx = 2; }   // (-hx, -hy,  hz)
+    t = s2 + c;  if (t > best) { best = t; idx = 3; }   // ( hx, -hy,  hz)
+    t = s1 - c;  if (t > best) { best = t; idx = 4; }   // ( hx,  hy, -hz)
+    t = -s2 - c; if (t > best) { best = t; idx = 5; }   // (-hx,  hy, -hz)
+    t = -s1 - c; if (t > best) { best = t; idx = 6; }   // (-hx, -hy, -hz)
+    t = s2 - c;  if (t > best) { best = t; idx = 7; }   // ( hx, -hy, -hz)
+    if (idx == 8) return v3(0.f, 0.f, 0.f);             // every dot was NaN: the fold keeps Vec3::zero()
+    // sign masks over idx: x negative for {1,2,5,6}, y negative for {2,3,6,7}, z negative for {4..7}
+    float px = ((0x66 >> idx) & 1) ? -hx : hx;
+    float py = ((0xCC >> idx) & 1) ? -hy : hy;
+    float pz = ((0xF0 >> idx) & 1) ? -hz : hz;
+    return v3(px, py, pz);
+}
+
+// Quad corners (quad.rs:46-53): (hx,hy,0), (-hx,hy,0), (-hx,-hy,0), (hx,-hy,0); same fold.
+B3_DEV V3 quad_local_support(float hx, float hy, V3 d) {
+    float a = hx * d.x, b = hy * d.y, c = 0.f * d.z;
+    float s1 = a + b, s2 = a - b;
+    float best = -INFINITY;
+    int idx = 4;
+    float t;
+    t = s1 + c;  if (t > best) { best = t; idx = 0; }
+    t = -s2 + c; if (t > best) { best = t; idx = 1; }
+    t = -s1 + c; if (t > best) { best = t; idx = 2; }
+    t = s2 + c;  if (t > best) { best = t; idx = 3; }
+    if (idx == 4) return v3(0.f, 0.f, 0.f);
+    float px = ((0x6 >> idx) & 1) ? -hx : hx;
+    float py = ((0xC >> idx) & 1) ? -hy : hy;
+    return v3(px, py, 0.f);
+}
+
+// Brute-force vertex scan (polyhedron.rs:135-150, VertexOnly mode): strict `>`, first maximum wins.
+// WARP = true: the 32 lanes of the warp stride the vertex list, each keeping its own first maximum; the
+// shuffle reduction prefers the larger dot and, on equal dots, the lower vertex index — the same vertex the
+// sequential scan returns. All lanes must call this convergently with identical arguments.
+template <bool WARP>
+B3_DEV V3 polyhedron_local_support(const float4* __restrict__ verts, uint32_t n, V3 d) {
+    float best = -INFINITY;
+    uint32_t idx = 0xFFFFFFFFu;
+    if (WARP) {
+        const uint32_t lane = threadIdx.x & 31u;
+        for (uint32_t i = lane; i < n; i += 32) {
+            float4 p = __ldg(verts + i);
+            float t = dot(v3(p.x, p.y, p.z), d);
+            if (t > best) { best = t; idx = i; }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            float ob = __shfl_xor_sync(0xFFFFFFFFu, best, off);
+            uint32_t oi = __shfl_xor_sync(0xFFFFFFFFu, idx, off);
+            // a lane that saw no valid dot has idx = 0xFFFFFFFF and best = -inf and never wins over a valid one
+            if (ob > best || (ob == best && oi < idx)) { best = ob; idx = oi; }
+        }
+    } else {
+        for (uint32_t i = 0; i < n; ++i) {
+            float4 p = __ldg(verts + i);
+            float t = dot(v3(p.x, p.y, p.z), d);
+            if (t > best) { best = t; idx = i; }
+        }
+    }
+    if (idx == 0xFFFFFFFFu) return v3(0.f, 0.f, 0.f);
+    float4 p = __ldg(verts + idx);
+    return v3(p.x, p.y, p.z);
+}
+
+// World-space support point of shape `s` along world direction `dir`.
+template <bool WARP>
+B3_DEV V3 support_point(const Shape& s, V3 dir) {
+    if (s.kind == K_PARTICLE) {
+        // primitive3.rs:119: transform.transform_point3(Vec3::zero())
+        return transform_point3(s, v3(0.f, 0.f, 0.f));
+    }
+    V3 d = inv_transform_vector3(s, dir);
+    V3 p;
+    switch (s.kind) {
+        case K_SPHERE:  // sphere.rs:20-25
+            p = d * (s.p0 / sqrtf(dot(d, d)));
+            break;
+        case K_CUBOID:
+            p = cuboid_local_support(s.p0, s.p1, s.p2, d);
+            break;
+        case K_QUAD:
+            p = quad_local_support(s.p0, s.p1, d);
+            break;
+        case K_CYLINDER: {  // cylinder.rs:37-62; p0 = half_height, p1 = radius
+            bool negative = signbit(d.y);
+            V3 r = v3(d.x, 0.f, d.z);
+            if (fabsf(dot(r, r) - 0.f) < F32_EPSILON) {
+                r = v3(0.f, 0.f, 0.f);
+            } else {
+                r = normalize(r);
+                if (fabsf(r.y - 0.f) < F32_EPSILON && fabsf(r.x - 0.f) < F32_EPSILON && fabsf(r.z - 0.f) < F32_EPSILON) {
+                    r = v3(0.f, 0.f, 0.f);
+                } else {
+                    r = r * s.p1;
+                }
+            }
+            r.y = negative ? -s.p0 : s.p0;
+            p = r;
+            break;
+        }
+        case K_CAPSULE: {  // capsule.rs:40-49; p0 = half_height, p1 = radius
+            V3 r = v3(0.f, rsignum(d.y) * s.p0, 0.f);
+            p = r + d * (s.p1 / sqrtf(dot(d, d)));
+            break;
+        }
+        default:  // K_POLYHEDRON, polyhedron.rs:342-355
+            p = polyhedron_local_support<WARP>(s.verts, s.nverts, d);
+            break;
+    }
+    return transform_point3(s, p);
+}
+
+// SupportPoint::from_minkowski (minkowski/mod.rs:33-51): v = l - r, sup_a = l. sup_b is never read by the
+// reference and is not kept.
+template <bool WARP>
+B3_DEV void minkowski_support(const Shape& L, const Shape& R, V3 dir, V3& v, V3& sup_a) {
+    V3 l = support_point<WARP>(L, dir);
+    V3 r = support_point<WARP>(R, -dir);
+    v = l - r;
+    sup_a = l;
+}
+
+}  // namespace b3

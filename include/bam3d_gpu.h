@@ -1,0 +1,166 @@
+/* bam3d_gpu.h — C ABI of the B200-native batched collision pipeline that sits behind bam3d's public API.
+ *
+ * The reference crate (DallasC/bam3d) is a pure-Rust library with no FFI of its own; this ABI is what a
+ * `bam3d` build with a `gpu` feature would bind through `extern "C"` (INTEGRATION.md shows the Rust block and
+ * the build.rs that compiles the CUDA sources with nvcc for sm_100a). Each entry point names the reference
+ * interface it stands in for (paths relative to the reference's src/).
+ *
+ * Conventions
+ *  - every function returns int32_t: 0 = BAM3D_OK, negative = error (bam3d_last_error gives the text);
+ *  - the caller owns every host buffer; device memory is owned by the ctx / opaque handles;
+ *  - per-item outcomes (hit, miss, not converged, "the reference would have panicked") are returned in
+ *    `out_status[]`, never as a function error;  hit  <=>  status == BAM3D_STATUS_OK;
+ *  - one ctx per host thread (a ctx is not thread-safe); any number of ctxs may exist;
+ *  - host-buffer entry points are synchronous on return; `_dev` entry points take device pointers, enqueue on
+ *    the ctx stream (bam3d_ctx_stream) and return without synchronising;
+ *  - matrices are glam `Mat4` column-major arrays of 16 f32 and must be affine (4th row exactly 0,0,0,1);
+ *  - there is no CPU fallback: without a CUDA device every call fails with BAM3D_ERR_CUDA.
+ */
+#ifndef BAM3D_GPU_H
+#define BAM3D_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BAM3D_OK 0
+#define BAM3D_ERR_CUDA (-1)        /* a CUDA runtime call failed */
+#define BAM3D_ERR_ARG (-2)         /* bad argument (null pointer, index out of range, unsupported setting) */
+#define BAM3D_ERR_NON_AFFINE (-3)  /* a transform's 4th row is not (0,0,0,1) */
+#define BAM3D_ERR_CAPACITY (-4)    /* output capacity too small; the required count is reported */
+#define BAM3D_ERR_OOM (-5)
+
+/* primitive kinds, in the order of `enum Primitive3` (primitive/primitive3.rs:16-33); Cube == Cuboid */
+#define BAM3D_KIND_PARTICLE 0   /* primitive/particle.rs   params: -                                  */
+#define BAM3D_KIND_QUAD 1       /* primitive/quad.rs       params: half_dim.x, half_dim.y              */
+#define BAM3D_KIND_SPHERE 2     /* primitive/sphere.rs     params: radius                              */
+#define BAM3D_KIND_CUBOID 3     /* primitive/cuboid.rs     params: half_dim.x, half_dim.y, half_dim.z  */
+#define BAM3D_KIND_CYLINDER 4   /* primitive/cylinder.rs   params: half_height, radius                 */
+#define BAM3D_KIND_CAPSULE 5    /* primitive/capsule.rs    params: half_height, radius                 */
+#define BAM3D_KIND_POLYHEDRON 6 /* primitive/polyhedron.rs ConvexPolyhedron::new (VertexOnly); mesh_id  */
+
+/* per-item status */
+#define BAM3D_STATUS_OK 0         /* Some(..): hit / converged                                          */
+#define BAM3D_STATUS_MISS 1       /* None: no intersection (distance: the shapes collide)               */
+#define BAM3D_STATUS_MAX_ITER 2   /* None: max_iterations reached (TOI: the added iteration cap)        */
+#define BAM3D_STATUS_REF_PANIC 3  /* the reference would panic here (simplex3d.rs:134 unwrap, :138 assert!) */
+#define BAM3D_STATUS_NAN 4        /* None through a NaN comparison                                      */
+#define BAM3D_STATUS_CAPACITY 5   /* EPA polytope outgrew the device capacities (never seen on valid input) */
+
+/* CollisionStrategy (contact.rs:12-18) */
+#define BAM3D_FULL_RESOLUTION 0
+#define BAM3D_COLLISION_ONLY 1
+
+typedef struct bam3d_ctx bam3d_ctx;
+typedef struct bam3d_meshes bam3d_meshes; /* convex-polyhedron vertex library resident on the device */
+typedef struct bam3d_shapes bam3d_shapes; /* packed primitives + transforms resident on the device   */
+typedef struct bam3d_bvh bam3d_bvh;       /* static BVH answering the DBVT queries                     */
+
+/* GJK::new_with_settings (algorithm/minkowski/gjk/mod.rs:45-58). max_iterations is shared by GJK and EPA, as in
+ * the reference, and must be <= 100 for contact generation (device polytope capacity). toi_iteration_cap bounds
+ * the reference's uncapped time-of-impact loop (gjk/mod.rs:166); 0 = default (100). */
+typedef struct bam3d_gjk_settings {
+    float distance_tolerance;   /* GJK_DISTANCE_TOLERANCE   = 1e-6 (gjk/mod.rs:19) */
+    float continuous_tolerance; /* GJK_CONTINUOUS_TOLERANCE = 1e-6 (gjk/mod.rs:20) */
+    float epa_tolerance;        /* EPA_TOLERANCE            = 1e-5 (epa/mod.rs:12) */
+    uint32_t max_iterations;    /* MAX_ITERATIONS           = 100  (gjk/mod.rs:18, epa/mod.rs:13) */
+    uint32_t toi_iteration_cap;
+} bam3d_gjk_settings;
+
+/* Contact (contact.rs:22-38) without the strategy tag: 32 bytes, one per pair. Zero for non-hits. */
+typedef struct bam3d_contact {
+    float normal[3];
+    float penetration_depth;
+    float contact_point[3];
+    float time_of_impact;
+} bam3d_contact;
+
+/* Compacted contact for the multi-GPU gather: only hits, tagged with the pair's index in the batch. */
+typedef struct bam3d_contact40 {
+    uint32_t pair_index;
+    uint32_t status;
+    bam3d_contact contact;
+} bam3d_contact40;
+
+/* ---- context ------------------------------------------------------------------------------------------ */
+int32_t bam3d_ctx_create(int32_t device_ordinal, bam3d_ctx** out_ctx);
+void bam3d_ctx_destroy(bam3d_ctx* ctx);
+const char* bam3d_last_error(const bam3d_ctx* ctx);
+int32_t bam3d_ctx_synchronize(bam3d_ctx* ctx);
+void* bam3d_ctx_stream(bam3d_ctx* ctx); /* the ctx's cudaStream_t */
+void bam3d_default_settings(bam3d_gjk_settings* out); /* GJK::new() (gjk/mod.rs:34-42) */
+/* tuning switches; "binning" (default 1): sort pairs by (kindL, kindR) before the thread-per-pair kernels */
+int32_t bam3d_ctx_set_option(bam3d_ctx* ctx, const char* name, int32_t value);
+/* page-locked host memory so that the host-buffer entry points copy at full PCIe / C2C rate */
+int32_t bam3d_host_alloc(bam3d_ctx* ctx, uint64_t bytes, void** out_ptr);
+void bam3d_host_free(bam3d_ctx* ctx, void* ptr);
+
+/* ---- host layer: pack primitives + Mat4 into device buffers ------------------------------------------- */
+/* ConvexPolyhedron::new(vertices) for a library of meshes (primitive/polyhedron.rs:69-95). verts_xyz holds
+ * offsets[n_meshes] vertices (3 f32 each); mesh m owns vertices offsets[m] .. offsets[m+1]. */
+int32_t bam3d_meshes_upload(bam3d_ctx* ctx, const float* verts_xyz, const uint32_t* offsets, uint32_t n_meshes,
+                            bam3d_meshes** out);
+void bam3d_meshes_free(bam3d_ctx* ctx, bam3d_meshes* meshes);
+
+/* Primitive3 values and their model-to-world Mat4 (primitive/primitive3.rs, traits.rs:78-100). kind[n],
+ * params[n*4] (see BAM3D_KIND_*), xform[n*16] column-major; mesh_id[n] only read for polyhedra (may be NULL
+ * when there are none); meshes may be NULL likewise. Computes Mat4::inverse() once per shape on the device
+ * (the reference recomputes it inside every support_point call: primitive/util.rs:11, sphere.rs:22, ...). */
+int32_t bam3d_shapes_upload(bam3d_ctx* ctx, const uint8_t* kind, const float* params, const float* xform,
+                            const uint32_t* mesh_id, uint32_t n, const bam3d_meshes* meshes, bam3d_shapes** out);
+/* replace every transform (next frame) without re-sending kinds / params */
+int32_t bam3d_shapes_set_transforms(bam3d_ctx* ctx, bam3d_shapes* shapes, const float* xform);
+void bam3d_shapes_free(bam3d_ctx* ctx, bam3d_shapes* shapes);
+uint32_t bam3d_shapes_count(const bam3d_shapes* shapes);
+
+/* ---- narrow phase, host buffers ------------------------------------------------------------------------ */
+/* pairs: n x (left shape index, right shape index). */
+
+/* GJK::intersect (gjk/mod.rs:74-113) per pair: status OK <=> Some(simplex). */
+int32_t bam3d_gjk_intersect(bam3d_ctx* ctx, const bam3d_shapes* shapes, const uint32_t* pairs, uint64_t n,
+                            const bam3d_gjk_settings* settings, uint8_t* out_status);
+/* GJK::intersection (gjk/mod.rs:317-341) per pair = intersect + EPA3::process (epa/epa3d.rs:16-52) for
+ * FullResolution, or Contact::new(CollisionOnly) (all-zero payload). */
+int32_t bam3d_gjk_contact(bam3d_ctx* ctx, const bam3d_shapes* shapes, const uint32_t* pairs, uint64_t n,
+                          const bam3d_gjk_settings* settings, int32_t strategy, bam3d_contact* out_contacts,
+                          uint8_t* out_status);
+/* GJK::distance (gjk/mod.rs:232-280) per pair. out_ref_value = what the reference returns for Some (dp - d0, the
+ * convergence residual, :273-275); out_distance = sqrt(d.d), the geometric separation (:274, commented out in the
+ * reference). Both 0 unless status == OK. */
+int32_t bam3d_gjk_distance(bam3d_ctx* ctx, const bam3d_shapes* shapes, const uint32_t* pairs, uint64_t n,
+                           const bam3d_gjk_settings* settings, float* out_ref_value, float* out_distance,
+                           uint8_t* out_status);
+/* GJK::intersection_time_of_impact (gjk/mod.rs:130-217) per pair; shapes_start / shapes_end hold the same
+ * primitives with their transforms at the start / end of the step (Range<&Mat4>). */
+int32_t bam3d_gjk_time_of_impact(bam3d_ctx* ctx, const bam3d_shapes* shapes_start, const bam3d_shapes* shapes_end,
+                                 const uint32_t* pairs, uint64_t n, const bam3d_gjk_settings* settings,
+                                 bam3d_contact* out_contacts, uint8_t* out_status);
+
+/* ---- narrow phase, device buffers (asynchronous on the ctx stream) -------------------------------------- */
+int32_t bam3d_gjk_intersect_dev(bam3d_ctx* ctx, const bam3d_shapes* shapes, const uint32_t* d_pairs, uint64_t n,
+                                const bam3d_gjk_settings* settings, uint8_t* d_status);
+int32_t bam3d_gjk_contact_dev(bam3d_ctx* ctx, const bam3d_shapes* shapes, const uint32_t* d_pairs, uint64_t n,
+                              const bam3d_gjk_settings* settings, int32_t strategy, bam3d_contact* d_contacts,
+                              uint8_t* d_status);
+int32_t bam3d_gjk_distance_dev(bam3d_ctx* ctx, const bam3d_shapes* shapes, const uint32_t* d_pairs, uint64_t n,
+                               const bam3d_gjk_settings* settings, float* d_ref_value, float* d_distance,
+                               uint8_t* d_status);
+int32_t bam3d_gjk_time_of_impact_dev(bam3d_ctx* ctx, const bam3d_shapes* shapes_start,
+                                     const bam3d_shapes* shapes_end, const uint32_t* d_pairs, uint64_t n,
+                                     const bam3d_gjk_settings* settings, bam3d_contact* d_contacts,
+                                     uint8_t* d_status);
+/* Compact the hits of a contact batch into d_out (capacity records), pair_index = index + pair_index_base.
+ * *d_count (device u32/u64 pair: one uint64) receives the number of hits. Feeds the multi-GPU gather. */
+int32_t bam3d_compact_contacts_dev(bam3d_ctx* ctx, const bam3d_contact* d_contacts, const uint8_t* d_status,
+                                   uint64_t n, uint64_t pair_index_base, bam3d_contact40* d_out, uint64_t capacity,
+                                   uint64_t* d_count);
+
+/* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
+uint64_t bam3d_ctx_launch_count(const bam3d_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BAM3D_GPU_H */

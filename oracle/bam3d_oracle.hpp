@@ -316,10 +316,19 @@ inline void remove_or_add_edge(std::vector<std::pair<uint32_t, uint32_t>>& edges
     edges.push_back(edge);
 }
 
+// The reference's Vecs are unbounded, and on near-degenerate input (e.g. a Particle inside a Cylinder: the cap's
+// rim supports are coplanar, visibility becomes rounding noise) its face list grows multiplicatively per
+// iteration — the reference itself then effectively hangs / exhausts memory. The oracle therefore stops a pair
+// whose polytope would exceed these capacities and reports Status::Capacity; the GPU path uses the same numbers
+// (EPA_BIG_FCAP / EPA_BIG_ECAP in bam3d_b200/csrc/epa.cuh) for its overflow tier, so both report the same pairs.
+constexpr size_t EPA_FACE_LIMIT = 4096;
+constexpr size_t EPA_EDGE_LIMIT = 6144;
+
 struct Polytope {  // epa3d.rs:97-150
     std::vector<SupportPoint>& vertices;
     std::vector<Face> faces;
     uint32_t max_edges = 0;
+    bool overflow = false;
     explicit Polytope(std::vector<SupportPoint>& simplex) : vertices(simplex) {
         // Face::new, epa3d.rs:172-179
         faces.push_back(Face::new_impl(simplex, 3, 2, 1));
@@ -344,14 +353,16 @@ struct Polytope {  // epa3d.rs:97-150
                 Face face = faces[i];
                 faces[i] = faces.back();  // swap_remove
                 faces.pop_back();
-                remove_or_add_edge(edges, {face.vertices[0], face.vertices[1]});
-                remove_or_add_edge(edges, {face.vertices[1], face.vertices[2]});
-                remove_or_add_edge(edges, {face.vertices[2], face.vertices[0]});
+                for (int e = 0; e < 3; ++e) {
+                    remove_or_add_edge(edges, {face.vertices[e], face.vertices[(e + 1) % 3]});
+                    if (edges.size() > EPA_EDGE_LIMIT) { overflow = true; return; }
+                }
                 if (edges.size() > max_edges) max_edges = (uint32_t)edges.size();
             } else {
                 ++i;
             }
         }
+        if (faces.size() + edges.size() > EPA_FACE_LIMIT) { overflow = true; return; }
         uint32_t n = (uint32_t)vertices.size();
         vertices.push_back(sup);
         for (auto& e : edges) faces.push_back(Face::new_impl(vertices, n, e.first, e.second));
@@ -378,7 +389,7 @@ struct EPA3 {  // epa3d.rs:9-67; constants epa/mod.rs:12-13
     uint32_t max_iterations = 100;
     // epa3d.rs:16-52
     bool process(std::vector<SupportPoint>& simplex, const Shape& left, const Mat4& lt, const Shape& right,
-                 const Mat4& rt, Contact& out, Counters* cnt = nullptr) const {
+                 const Mat4& rt, Contact& out, Counters* cnt = nullptr, Status* st = nullptr) const {
         if (simplex.size() < 4) return false;
         Polytope polytope(simplex);
         uint32_t i = 1;
@@ -397,6 +408,7 @@ struct EPA3 {  // epa3d.rs:9-67; constants epa/mod.rs:12-13
                 return true;
             }
             polytope.add(p);
+            if (polytope.overflow) { if (st) *st = Status::Capacity; return false; }
             i += 1;
         }
     }
@@ -470,7 +482,7 @@ struct GJK {
             return true;
         }
         std::vector<SupportPoint> sv(simplex.p, simplex.p + simplex.n);  // simplex.into_vec()
-        return epa.process(sv, left, lt, right, rt, out, cnt);            // get_contact_manifold, :285-299
+        return epa.process(sv, left, lt, right, rt, out, cnt, st);        // get_contact_manifold, :285-299
     }
 
     // gjk/mod.rs:232-280. Returns Some/None; `ref_value` is what the reference returns (dp - d0, the

@@ -1,0 +1,225 @@
+"""ctypes wrapper over the CPU oracle (oracle/oracle_capi.cpp). TEST INFRASTRUCTURE: imported only from tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs — never from bam3d_b200/."""
+import ctypes as C
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(ROOT, "oracle", "_build", "libbam3d_oracle.so")
+KAT_PATH = os.path.join(ROOT, "oracle", "_build", "kat")
+
+
+class Settings(C.Structure):
+    _fields_ = [("distance_tolerance", C.c_float), ("continuous_tolerance", C.c_float), ("epa_tolerance", C.c_float),
+                ("max_iterations", C.c_uint32)]
+
+
+class Counters(C.Structure):
+    _fields_ = [("support_calls", C.c_uint64), ("gjk_iterations", C.c_uint64), ("epa_iterations", C.c_uint64),
+                ("max_faces", C.c_uint32), ("max_verts", C.c_uint32), ("max_edges", C.c_uint32), ("pad", C.c_uint32)]
+
+
+def _p(a):
+    return C.c_void_p(a.ctypes.data) if a is not None else None
+
+
+class Oracle:
+    def __init__(self):
+        self.lib = C.CDLL(LIB_PATH)
+        self.lib.orc_sap_find_pairs.restype = C.c_uint64
+        self.lib.orc_dbvt_build.restype = C.c_void_p
+        for f in ("orc_dbvt_query_aabb", "orc_dbvt_query_ray", "orc_dbvt_query_frustum", "orc_dbvt_find_collider_pairs"):
+            getattr(self.lib, f).restype = C.c_uint64
+
+    # ---- narrow phase ------------------------------------------------------------------------------------
+    @staticmethod
+    def _scene_args(scene):
+        kind = np.ascontiguousarray(scene["kind"], dtype=np.uint8)
+        params = np.ascontiguousarray(scene["params"], dtype=np.float32)
+        mesh_id = scene.get("mesh_id")
+        mv, mo = scene.get("mesh_verts"), scene.get("mesh_offsets")
+        keep = [kind, params,
+                None if mesh_id is None else np.ascontiguousarray(mesh_id, dtype=np.uint32),
+                None if mv is None else np.ascontiguousarray(mv, dtype=np.float32),
+                None if mo is None else np.ascontiguousarray(mo, dtype=np.uint32)]
+        return keep
+
+    @staticmethod
+    def _settings(settings):
+        if settings is None:
+            return None
+        s = Settings(settings.distance_tolerance, settings.continuous_tolerance, settings.epa_tolerance, settings.max_iterations)
+        return C.byref(s)
+
+    def intersect(self, scene, settings=None, nthreads=1, counters=None):
+        kind, params, mesh_id, mv, mo = self._scene_args(scene)
+        xform = np.ascontiguousarray(scene["xform"], dtype=np.float32)
+        pairs = np.ascontiguousarray(scene["pairs"], dtype=np.uint32)
+        n = len(pairs)
+        hit = np.empty(n, dtype=np.uint8)
+        status = np.empty(n, dtype=np.uint8)
+        self.lib.orc_gjk_intersect_batch(_p(kind), _p(params), _p(xform), _p(mesh_id), _p(mv), _p(mo), _p(pairs), C.c_uint64(n),
+                                         self._settings(settings), _p(hit), _p(status), C.c_int(nthreads),
+                                         C.byref(counters) if counters is not None else None)
+        return hit, status
+
+    def contact(self, scene, strategy=0, settings=None, nthreads=1, counters=None):
+        kind, params, mesh_id, mv, mo = self._scene_args(scene)
+        xform = np.ascontiguousarray(scene["xform"], dtype=np.float32)
+        pairs = np.ascontiguousarray(scene["pairs"], dtype=np.uint32)
+        n = len(pairs)
+        hit = np.empty(n, dtype=np.uint8)
+        status = np.empty(n, dtype=np.uint8)
+        contacts = np.empty((n, 8), dtype=np.float32)
+        self.lib.orc_gjk_contact_batch(_p(kind), _p(params), _p(xform), _p(mesh_id), _p(mv), _p(mo), _p(pairs), C.c_uint64(n),
+                                       self._settings(settings), C.c_int(int(strategy)), _p(contacts), _p(hit), _p(status),
+                                       C.c_int(nthreads), C.byref(counters) if counters is not None else None)
+        return contacts, hit, status
+
+    def distance(self, scene, settings=None, nthreads=1, counters=None):
+        kind, params, mesh_id, mv, mo = self._scene_args(scene)
+        xform = np.ascontiguousarray(scene["xform"], dtype=np.float32)
+        pairs = np.ascontiguousarray(scene["pairs"], dtype=np.uint32)
+        n = len(pairs)
+        some = np.empty(n, dtype=np.uint8)
+        status = np.empty(n, dtype=np.uint8)
+        ref = np.empty(n, dtype=np.float32)
+        geo = np.empty(n, dtype=np.float32)
+        self.lib.orc_gjk_distance_batch(_p(kind), _p(params), _p(xform), _p(mesh_id), _p(mv), _p(mo), _p(pairs), C.c_uint64(n),
+                                        self._settings(settings), _p(ref), _p(geo), _p(some), _p(status), C.c_int(nthreads),
+                                        C.byref(counters) if counters is not None else None)
+        return ref, geo, some, status
+
+    def toi(self, scene, xform_end, settings=None, toi_cap=100, nthreads=1, counters=None):
+        kind, params, mesh_id, mv, mo = self._scene_args(scene)
+        x0 = np.ascontiguousarray(scene["xform"], dtype=np.float32)
+        x1 = np.ascontiguousarray(xform_end, dtype=np.float32)
+        pairs = np.ascontiguousarray(scene["pairs"], dtype=np.uint32)
+        n = len(pairs)
+        hit = np.empty(n, dtype=np.uint8)
+        status = np.empty(n, dtype=np.uint8)
+        contacts = np.empty((n, 8), dtype=np.float32)
+        self.lib.orc_gjk_toi_batch(_p(kind), _p(params), _p(x0), _p(x1), _p(mesh_id), _p(mv), _p(mo), _p(pairs), C.c_uint64(n),
+                                   self._settings(settings), C.c_uint32(toi_cap), _p(contacts), _p(hit), _p(status), C.c_int(nthreads),
+                                   C.byref(counters) if counters is not None else None)
+        return contacts, hit, status
+
+    def support_point(self, kind, params4, direction, xform16, verts=None):
+        params4 = np.ascontiguousarray(params4, dtype=np.float32)
+        direction = np.ascontiguousarray(direction, dtype=np.float32)
+        xform16 = np.ascontiguousarray(xform16, dtype=np.float32)
+        verts = None if verts is None else np.ascontiguousarray(verts, dtype=np.float32)
+        out = np.empty(3, dtype=np.float32)
+        self.lib.orc_support_point(C.c_uint8(kind), _p(params4), _p(verts), C.c_uint32(0 if verts is None else len(verts)),
+                                   _p(direction), _p(xform16), _p(out))
+        return out
+
+    def mat4_from_srt(self, scale, quat, trans):
+        out = np.empty(16, dtype=np.float32)
+        sc, q, t = (np.ascontiguousarray(a, dtype=np.float32) for a in (scale, quat, trans))  # keep alive across the call
+        self.lib.orc_mat4_from_srt(_p(sc), _p(q), _p(t), _p(out))
+        return out
+
+    def quat_from_rotation_z(self, angle):
+        out = np.empty(4, dtype=np.float32)
+        self.lib.orc_quat_from_rotation_z(C.c_float(angle), _p(out))
+        return out
+
+    def transform_z(self, x, y, z, angle_deg):
+        """The reference tests' transform()/transform_3d(): rotation about z by angle_deg.to_radians()."""
+        rad = np.float32(angle_deg) * (np.float32(np.pi) / np.float32(180.0))
+        return self.mat4_from_srt([1, 1, 1], self.quat_from_rotation_z(float(rad)), [x, y, z])
+
+    def mat4_inverse(self, m):
+        out = np.empty(16, dtype=np.float32)
+        m = np.ascontiguousarray(m, dtype=np.float32)
+        self.lib.orc_mat4_inverse(_p(m), _p(out))
+        return out
+
+    def world_aabbs(self, scene):
+        kind, params, mesh_id, mv, mo = self._scene_args(scene)
+        xform = np.ascontiguousarray(scene["xform"], dtype=np.float32)
+        out = np.empty((len(kind), 6), dtype=np.float32)
+        self.lib.orc_world_aabb_batch(_p(kind), _p(params), _p(xform), _p(mesh_id), _p(mv), _p(mo), C.c_uint64(len(kind)), _p(out))
+        return out
+
+    # ---- broad phase -------------------------------------------------------------------------------------
+    def sap_find_pairs(self, aabbs, axis=0):
+        aabbs = np.ascontiguousarray(aabbs, dtype=np.float32).reshape(-1, 6)
+        n = len(aabbs)
+        ax = C.c_int32(axis)
+        perm = np.empty(n, dtype=np.uint32)
+        cap = max(1024, 16 * n)
+        while True:
+            pairs = np.empty((cap, 2), dtype=np.uint32)
+            ax = C.c_int32(axis)
+            cnt = self.lib.orc_sap_find_pairs(_p(aabbs), C.c_uint64(n), C.byref(ax), _p(perm), _p(pairs), C.c_uint64(cap))
+            if cnt <= cap:
+                return pairs[:cnt].copy(), perm, int(ax.value)
+            cap = int(cnt)
+
+    def dbvt_build(self, aabbs, fat=None):
+        aabbs = np.ascontiguousarray(aabbs, dtype=np.float32).reshape(-1, 6)
+        fat = None if fat is None else np.ascontiguousarray(fat, dtype=np.float32).reshape(-1, 6)
+        return OracleDbvt(self, self.lib.orc_dbvt_build(_p(aabbs), _p(fat), C.c_uint64(len(aabbs))), len(aabbs))
+
+    def frustum_from_mat4(self, m16):
+        out = np.empty(24, dtype=np.float32)
+        m16 = np.ascontiguousarray(m16, dtype=np.float32)
+        ok = self.lib.orc_frustum_from_mat4(_p(m16), _p(out))
+        return out if ok else None
+
+    def perspective_rh_gl(self, fov, aspect, zn, zf):
+        out = np.empty(16, dtype=np.float32)
+        self.lib.orc_perspective_rh_gl(C.c_float(fov), C.c_float(aspect), C.c_float(zn), C.c_float(zf), _p(out))
+        return out
+
+
+class OracleDbvt:
+    def __init__(self, orc, handle, n):
+        self.orc, self.h, self.n = orc, C.c_void_p(handle), n
+
+    def query_aabb(self, q6):
+        q6 = np.ascontiguousarray(q6, dtype=np.float32)
+        out = np.empty(self.n, dtype=np.uint32)
+        c = self.orc.lib.orc_dbvt_query_aabb(self.h, _p(q6), _p(out), C.c_uint64(self.n))
+        return out[:c].copy()
+
+    def query_ray(self, ray6):
+        ray6 = np.ascontiguousarray(ray6, dtype=np.float32)
+        vals = np.empty(self.n, dtype=np.uint32)
+        pts = np.empty((self.n, 3), dtype=np.float32)
+        c = self.orc.lib.orc_dbvt_query_ray(self.h, _p(ray6), _p(vals), _p(pts), C.c_uint64(self.n))
+        return vals[:c].copy(), pts[:c].copy()
+
+    def query_ray_closest(self, ray6):
+        ray6 = np.ascontiguousarray(ray6, dtype=np.float32)
+        v = C.c_uint32(0)
+        t = C.c_float(0)
+        pt = np.empty(3, dtype=np.float32)
+        ok = self.orc.lib.orc_dbvt_query_ray_closest(self.h, _p(ray6), C.byref(v), _p(pt), C.byref(t))
+        return (int(v.value), pt, float(t.value)) if ok else None
+
+    def query_frustum(self, planes24):
+        planes24 = np.ascontiguousarray(planes24, dtype=np.float32)
+        vals = np.empty(self.n, dtype=np.uint32)
+        rel = np.empty(self.n, dtype=np.uint8)
+        c = self.orc.lib.orc_dbvt_query_frustum(self.h, _p(planes24), _p(vals), _p(rel), C.c_uint64(self.n))
+        return vals[:c].copy(), rel[:c].copy()
+
+    def find_collider_pairs(self, dirty):
+        dirty = np.ascontiguousarray(dirty, dtype=np.uint8)
+        cap = 64 * self.n + 1024
+        out = np.empty((cap, 2), dtype=np.uint32)
+        c = self.orc.lib.orc_dbvt_find_collider_pairs(self.h, _p(dirty), _p(out), C.c_uint64(cap))
+        return out[:c].copy()
+
+    def stack_overflow(self):
+        return bool(self.orc.lib.orc_dbvt_stack_overflow(self.h))
+
+    def __del__(self):
+        try:
+            self.orc.lib.orc_dbvt_free(self.h)
+        except Exception:
+            pass

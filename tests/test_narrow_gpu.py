@@ -1,0 +1,316 @@
+"""GPU parity tests for the narrow phase: CUDA path (through the C ABI) vs the CPU oracle on the same seeded inputs,
+plus the reference's own known-answer tests run through the GPU API. Integer/boolean results (status, hit) must be
+bit-exact; f32 results are compared bit-exactly too (the kernels evaluate the reference's expressions in the
+reference's order without FMA), with the north-star tolerance (1e-4 relative) as the documented fallback bound.
+"""
+import numpy as np
+import pytest
+
+import bam3d_b200 as b3
+from bam3d_b200 import scenes
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-4  # BASELINE.json north_star: depth / normal / distance / TOI within 1e-4 relative
+
+
+def shapes_of(ctx, scene, xform=None):
+    meshes = None
+    if scene.get("mesh_verts") is not None:
+        meshes = b3.MeshLibrary(ctx, scene["mesh_verts"], scene["mesh_offsets"])
+    return b3.ShapeSet(ctx, scene["kind"], scene["params"], scene["xform"] if xform is None else xform, scene.get("mesh_id"), meshes)
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def assert_f32_equal(name, got, want, mask=None):
+    """Bit-exact f32 equality (treating -0 == +0 and NaN == NaN), with a useful report on failure."""
+    got = np.asarray(got, dtype=np.float32)
+    want = np.asarray(want, dtype=np.float32)
+    if mask is not None:
+        got, want = got[mask], want[mask]
+    same = (got == want) | (np.isnan(got) & np.isnan(want))
+    if not same.all():
+        bad = np.argwhere(~same)
+        rel = np.abs(got - want) / np.maximum(np.abs(want), 1e-30)
+        raise AssertionError(f"{name}: {len(bad)} of {same.size} values differ; first at {bad[0]}: got {got[tuple(bad[0])]!r} "
+                             f"want {want[tuple(bad[0])]!r}; max rel err {np.nanmax(rel[~same]):.3e}")
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the reference's known-answer tests, through the GPU API
+# ---------------------------------------------------------------------------------------------------------
+def test_kat_gjk_3d_hit(ctx, oracle):
+    """gjk/mod.rs:575-596 test_gjk_3d_hit + epa3d.rs:279-302 test_epa_3d"""
+    gjk = b3.GJK.new(ctx)
+    left, right = b3.Cuboid(10., 10., 10.), b3.Cuboid(10., 10., 10.)
+    lt, rt = oracle.transform_z(15., 0., 0., 0.), oracle.transform_z(7., 2., 0., 0.)
+    assert gjk.intersect(left, lt, right, rt)
+    c = gjk.intersection(b3.CollisionStrategy.FullResolution, left, lt, right, rt)
+    assert c is not None
+    assert c.normal.tolist() == [-1., 0., 0.]
+    assert c.penetration_depth == 2.
+    assert c.contact_point.tolist() == [np.float32(10.), np.float32(1.0000002), np.float32(4.999999)]
+    c2 = gjk.intersection(b3.CollisionStrategy.CollisionOnly, left, lt, right, rt)
+    assert c2 is not None and c2.penetration_depth == 0. and c2.normal.tolist() == [0., 0., 0.]
+
+
+def test_kat_gjk_exact_and_sphere(ctx, oracle):
+    """gjk/mod.rs:552-573 test_gjk_exact_3d, test_gjk_sphere"""
+    gjk = b3.GJK.new(ctx)
+    t = oracle.transform_z(0., 0., 0., 0.)
+    cube = b3.Cuboid(1., 1., 1.)
+    assert gjk.intersection(b3.CollisionStrategy.FullResolution, cube, t, cube, t) is not None
+    assert gjk.distance(cube, t, cube, t) is None
+    sph = b3.Sphere(1.)
+    assert gjk.intersection(b3.CollisionStrategy.FullResolution, sph, t, sph, t) is not None
+    d = gjk.distance(sph, t, sph, t)
+    assert d is not None  # the reference asserts == 0.; its code yields a ~8e-7 residual (documented discrepancy)
+    assert abs(d) < 1e-6
+
+
+def test_kat_distance_3d(ctx, oracle):
+    """gjk/mod.rs:598-615 test_gjk_distance_3d: None when overlapping; separated -> Some(residual), geometric 4."""
+    gjk = b3.GJK.new(ctx)
+    left, right = b3.Cuboid(10., 10., 10.), b3.Cuboid(10., 10., 10.)
+    lt = oracle.transform_z(15., 0., 0., 0.)
+    assert gjk.distance(left, lt, right, oracle.transform_z(7., 2., 0., 0.)) is None
+    s = b3.ShapeSet.from_primitives(ctx, [left, right], [lt, oracle.transform_z(1., 0., 0., 0.)])
+    ref, geo, st = gjk.distance_batch(s, [[0, 1]])
+    assert st[0] == b3.STATUS_OK and geo[0] == 4.0 and ref[0] == 0.0
+
+
+def test_kat_time_of_impact(ctx, oracle):
+    """gjk/mod.rs:617-644 test_gjk_time_of_impact_3d"""
+    gjk = b3.GJK.new(ctx)
+    left, right = b3.Cuboid(10., 11., 10.), b3.Cuboid(10., 15., 10.)
+    l0, l1 = oracle.transform_z(0., 0., 0., 0.), oracle.transform_z(30., 0., 0., 0.)
+    rt = oracle.transform_z(15., 0., 0., 0.)
+    c = gjk.intersection_time_of_impact(left, (l0, l1), right, (rt, rt))
+    assert c is not None
+    assert np.float32(c.time_of_impact) == np.float32(0.16666667)
+    assert c.normal.tolist() == [-1., 0., 0.]
+    assert c.penetration_depth == 0.
+    assert c.contact_point.tolist() == [10., 0., 0.]
+    assert gjk.intersection_time_of_impact(left, (l0, l0), right, (rt, rt)) is None
+
+
+def test_kat_quad_cuboid(ctx, oracle):
+    """quad.rs:113-124 test_plane_cuboid_intersect (rotation about x by 1 degree)"""
+    h = np.float32(np.float32(1.0) * (np.float32(np.pi) / np.float32(180.0))) * np.float32(0.5)
+    q = [float(np.sin(np.float32(h), dtype=np.float32)), 0., 0., float(np.cos(np.float32(h), dtype=np.float32))]
+    t1 = oracle.mat4_from_srt([1, 1, 1], q, [0., 0., 1.])
+    t2 = oracle.mat4_from_srt([1, 1, 1], q, [0., 0., 1.1])
+    assert b3.GJK.new(ctx).intersect(b3.Quad(2., 2.), t1, b3.Cuboid(1., 1., 1.), t2)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# differential tests on seeded scenes
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("s", [2.0, 1.2])
+def test_intersect_parity_cuboids(ctx, oracle, s):
+    """C1 at a size the oracle finishes in seconds: hit/miss and status bit-exact."""
+    scene = scenes.cuboid_pairs(200_000, s=s)
+    shapes = shapes_of(ctx, scene)
+    st = b3.GJK.new(ctx).intersect_batch(shapes, scene["pairs"])
+    hit, ost = oracle.intersect(scene, nthreads=8)
+    assert np.array_equal(st, ost), f"{int((st != ost).sum())} status mismatches"
+    assert np.array_equal(st == 0, hit == 1)
+    frac = hit.mean()
+    assert 0.2 < frac < 0.95
+
+
+def test_intersect_parity_all_kinds(ctx, oracle):
+    """Every analytic primitive (Particle, Quad, Sphere, Cuboid, Cylinder, Capsule) on both sides, binned."""
+    scene = scenes.all_kinds_pairs(150_000, s=1.5)
+    shapes = shapes_of(ctx, scene)
+    st = b3.GJK.new(ctx).intersect_batch(shapes, scene["pairs"])
+    hit, ost = oracle.intersect(scene, nthreads=8)
+    assert np.array_equal(st, ost), f"{int((st != ost).sum())} status mismatches"
+    # binning off must give the same answers
+    ctx.set_option("binning", 0)
+    try:
+        st2 = b3.GJK.new(ctx).intersect_batch(shapes, scene["pairs"])
+    finally:
+        ctx.set_option("binning", 1)
+    assert np.array_equal(st, st2)
+
+
+def test_contact_parity_mixed(ctx, oracle):
+    """C2 shape mix, FullResolution: status bit-exact; normal / depth / contact point compared bit-for-bit."""
+    scene = scenes.mixed_pairs(60_000, s=1.5)
+    shapes = shapes_of(ctx, scene)
+    contacts, st = b3.GJK.new(ctx).intersection_batch(b3.CollisionStrategy.FullResolution, shapes, scene["pairs"])
+    oc, ohit, ost = oracle.contact(scene, strategy=0, nthreads=8)
+    assert np.array_equal(st, ost), f"{int((st != ost).sum())} status mismatches"
+    hit = st == 0
+    assert hit.sum() > 1000
+    assert_f32_equal("normal+depth", contacts[:, 0:4], oc[:, 0:4], hit)
+    assert_f32_equal("contact_point", contacts[:, 4:7], oc[:, 4:7], hit)
+    assert not contacts[~hit].any()
+
+
+def test_contact_parity_all_kinds_and_collision_only(ctx, oracle):
+    scene = scenes.all_kinds_pairs(40_000, s=1.0)
+    shapes = shapes_of(ctx, scene)
+    gjk = b3.GJK.new(ctx)
+    contacts, st = gjk.intersection_batch(b3.CollisionStrategy.FullResolution, shapes, scene["pairs"])
+    oc, ohit, ost = oracle.contact(scene, strategy=0, nthreads=8)
+    assert np.array_equal(st, ost), f"{int((st != ost).sum())} status mismatches"
+    hit = st == 0
+    assert_f32_equal("contact", contacts[:, 0:7], oc[:, 0:7], hit)
+    # all of these involve a cylinder cap (coplanar rim supports): the reference's face list explodes there
+    assert (st == b3.STATUS_CAPACITY).sum() == (ost == b3.STATUS_CAPACITY).sum() > 0
+    c2, st2 = gjk.intersection_batch(b3.CollisionStrategy.CollisionOnly, shapes, scene["pairs"])
+    oc2, ohit2, ost2 = oracle.contact(scene, strategy=1, nthreads=8)
+    assert np.array_equal(st2, ost2)
+    assert not c2.any()
+
+
+def test_distance_parity(ctx, oracle):
+    scene = scenes.mixed_pairs(60_000, s=4.0, seed=0xB3D000D1)
+    shapes = shapes_of(ctx, scene)
+    ref, dist, st = b3.GJK.new(ctx).distance_batch(shapes, scene["pairs"])
+    oref, ogeo, osome, ost = oracle.distance(scene, nthreads=8)
+    assert np.array_equal(st, ost), f"{int((st != ost).sum())} status mismatches"
+    some = st == 0
+    assert some.sum() > 1000
+    assert_f32_equal("ref_value", ref, oref, some)
+    assert_f32_equal("distance", dist, ogeo, some)
+    # the statuses the reference cannot express except by panicking / giving up must be present and identical
+    for code in (b3.STATUS_MISS, b3.STATUS_MAX_ITER, b3.STATUS_REF_PANIC):
+        assert (st == code).sum() == (ost == code).sum()
+
+
+def test_toi_parity(ctx, oracle):
+    scene = scenes.mixed_pairs(60_000, s=4.0, seed=0xB3D000E1)
+    x1 = scenes.end_transforms(scene, span=3.0)
+    s0, s1 = shapes_of(ctx, scene), shapes_of(ctx, scene, x1)
+    contacts, st = b3.GJK.new(ctx).intersection_time_of_impact_batch(s0, s1, scene["pairs"])
+    oc, ohit, ost = oracle.toi(scene, x1, nthreads=8)
+    assert np.array_equal(st, ost), f"{int((st != ost).sum())} status mismatches"
+    hit = st == 0
+    assert hit.sum() > 1000
+    # normals are NaN when the shapes already overlap at t = 0 (normalize(0), gjk/mod.rs:208): NaN == NaN here
+    assert_f32_equal("toi", contacts[:, 7], oc[:, 7], hit)
+    assert_f32_equal("normal+depth", contacts[:, 0:4], oc[:, 0:4], hit)
+    # contact_point goes through decompose/recompose of the end transform: tolerance class
+    cp, ocp = contacts[hit][:, 4:7], oc[hit][:, 4:7]
+    ok = np.isclose(cp, ocp, rtol=REL_TOL, atol=1e-4) | (np.isnan(cp) & np.isnan(ocp))
+    assert ok.all()
+
+
+def test_polyhedron_parity(ctx, oracle):
+    """C3 at reduced size: warp-cooperative support (64..256 vertices) vs the sequential scan of the oracle."""
+    lib = scenes.mesh_library(256)
+    scene = scenes.polyhedron_pairs(20_000, library=lib)
+    shapes = shapes_of(ctx, scene)
+    gjk = b3.GJK.new(ctx)
+    st = gjk.intersect_batch(shapes, scene["pairs"])
+    hit, ost = oracle.intersect(scene, nthreads=8)
+    assert np.array_equal(st, ost), f"{int((st != ost).sum())} status mismatches"
+    contacts, st2 = gjk.intersection_batch(b3.CollisionStrategy.FullResolution, shapes, scene["pairs"])
+    oc, ohit, ost2 = oracle.contact(scene, strategy=0, nthreads=8)
+    assert np.array_equal(st2, ost2), f"{int((st2 != ost2).sum())} status mismatches"
+    h = st2 == 0
+    assert h.sum() > 1000
+    assert_f32_equal("contact", contacts[:, 0:7], oc[:, 0:7], h)
+
+
+def test_polyhedron_small_and_degenerate_meshes(ctx, oracle):
+    """Ragged mesh sizes: 1, 2, 3, 4 (tetrahedron), 33 vertices and duplicated vertices (ties: first maximum wins)."""
+    rng = np.random.default_rng(7)
+    sizes = [1, 2, 3, 4, 31, 32, 33, 64]
+    verts, offs = [], [0]
+    for k in sizes:
+        v = rng.normal(size=(k, 3)).astype(np.float32)
+        verts.append(v)
+        offs.append(offs[-1] + k)
+    dup = np.repeat(rng.normal(size=(8, 3)).astype(np.float32), 3, axis=0)  # every vertex three times
+    verts.append(dup)
+    offs.append(offs[-1] + len(dup))
+    lib = (np.concatenate(verts), np.array(offs, dtype=np.uint32))
+    scene = scenes.polyhedron_pairs(8_000, library=lib, s=1.0, seed=0xB3D000F1)
+    shapes = shapes_of(ctx, scene)
+    contacts, st = b3.GJK.new(ctx).intersection_batch(b3.CollisionStrategy.FullResolution, shapes, scene["pairs"])
+    oc, ohit, ost = oracle.contact(scene, strategy=0, nthreads=8)
+    assert np.array_equal(st, ost), f"{int((st != ost).sum())} status mismatches"
+    assert_f32_equal("contact", contacts[:, 0:7], oc[:, 0:7], st == 0)
+
+
+def test_mixed_polyhedron_and_analytic(ctx, oracle):
+    """Pairs mixing polyhedra with analytic shapes: binning routes them to the warp kernel, the rest to threads."""
+    lib = scenes.mesh_library(64, seed=0xB3D000F2)
+    n = 20_000
+    a = scenes.mixed_pairs(n, s=1.5, seed=0xB3D000F3)
+    p = scenes.polyhedron_pairs(n, library=lib, s=1.5, seed=0xB3D000F3)
+    rng = np.random.default_rng(11)
+    use_poly = rng.random(2 * n) < 0.4
+    scene = dict(a)
+    scene["kind"] = np.where(use_poly, p["kind"], a["kind"]).astype(np.uint8)
+    scene["mesh_id"] = p["mesh_id"]
+    scene["mesh_verts"], scene["mesh_offsets"] = lib
+    shapes = shapes_of(ctx, scene)
+    gjk = b3.GJK.new(ctx)
+    contacts, st = gjk.intersection_batch(b3.CollisionStrategy.FullResolution, shapes, scene["pairs"])
+    oc, ohit, ost = oracle.contact(scene, strategy=0, nthreads=8)
+    assert np.array_equal(st, ost), f"{int((st != ost).sum())} status mismatches"
+    assert_f32_equal("contact", contacts[:, 0:7], oc[:, 0:7], st == 0)
+    ref, dist, dst = gjk.distance_batch(shapes, scene["pairs"])
+    oref, ogeo, osome, odst = oracle.distance(scene, nthreads=8)
+    assert np.array_equal(dst, odst)
+    assert_f32_equal("distance", dist, ogeo, dst == 0)
+
+
+def test_shared_shapes_and_set_transforms(ctx, oracle):
+    """Pairs that share shapes (real broad-phase output) and the per-frame transform update."""
+    scene = scenes.mixed_pairs(5_000, s=1.5, seed=0xB3D000F4)
+    n_shapes = len(scene["kind"])
+    rng = np.random.default_rng(3)
+    pairs = rng.integers(0, n_shapes, size=(50_000, 2), dtype=np.uint32)
+    scene["pairs"] = pairs
+    shapes = shapes_of(ctx, scene)
+    gjk = b3.GJK.new(ctx)
+    st = gjk.intersect_batch(shapes, pairs)
+    hit, ost = oracle.intersect(scene, nthreads=8)
+    assert np.array_equal(st, ost)
+    x1 = scenes.end_transforms(scene, span=1.0)
+    shapes.set_transforms(x1)
+    scene2 = dict(scene)
+    scene2["xform"] = x1
+    st2 = gjk.intersect_batch(shapes, pairs)
+    hit2, ost2 = oracle.intersect(scene2, nthreads=8)
+    assert np.array_equal(st2, ost2)
+
+
+def test_edge_cases(ctx, oracle):
+    """Empty batch, one pair, coincident centres (d == 0 -> (1,1,1), gjk/mod.rs:87-90), custom settings, bad input."""
+    scene = scenes.mixed_pairs(64, s=1.5)
+    shapes = shapes_of(ctx, scene)
+    gjk = b3.GJK.new(ctx)
+    assert len(gjk.intersect_batch(shapes, np.zeros((0, 2), dtype=np.uint32))) == 0
+    assert len(gjk.intersect_batch(shapes, [[0, 1]])) == 1
+    # every shape against itself: coincident centres
+    self_pairs = np.stack([np.arange(128, dtype=np.uint32)] * 2, axis=1)
+    sc = dict(scene)
+    sc["pairs"] = self_pairs
+    c, st = gjk.intersection_batch(b3.CollisionStrategy.FullResolution, shapes, self_pairs)
+    oc, ohit, ost = oracle.contact(sc, nthreads=1)
+    assert np.array_equal(st, ost)
+    assert_f32_equal("self contact", c[:, 0:7], oc[:, 0:7], st == 0)
+    # tighter iteration budget, looser tolerances (GJK::new_with_settings, gjk/mod.rs:45-58)
+    g2 = b3.GJK.new_with_settings(1e-4, 1e-4, 1e-3, 12, ctx=ctx)
+    c2, st2 = g2.intersection_batch(b3.CollisionStrategy.FullResolution, shapes, scene["pairs"])
+    oc2, _, ost2 = oracle.contact(scene, settings=g2.settings, nthreads=1)
+    assert np.array_equal(st2, ost2)
+    assert_f32_equal("contact (settings)", c2[:, 0:7], oc2[:, 0:7], st2 == 0)
+    # non-affine transform is rejected, not silently accepted
+    bad = scene["xform"].copy()
+    bad[3, 15] = 2.0
+    with pytest.raises(b3.Bam3dError):
+        b3.ShapeSet(ctx, scene["kind"], scene["params"], bad)
+    g3 = b3.GJK.new_with_settings(1e-6, 1e-6, 1e-5, 500, ctx=ctx)
+    with pytest.raises(b3.Bam3dError):
+        g3.intersection_batch(b3.CollisionStrategy.FullResolution, shapes, scene["pairs"])
