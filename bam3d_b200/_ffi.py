@@ -40,6 +40,7 @@ SIGNATURES = {
     "bam3d_ctx_stream": (_vp, [_vp]),
     "bam3d_default_settings": (None, [_PS]),
     "bam3d_ctx_set_option": (_i32, [_vp, C.c_char_p, _i32]),
+    "bam3d_ctx_read_timing": (_i32, [_vp, C.POINTER(C.c_double), C.POINTER(_u64)]),
     "bam3d_host_alloc": (_i32, [_vp, _u64, C.POINTER(_vp)]),
     "bam3d_host_free": (None, [_vp, _vp]),
     "bam3d_meshes_upload": (_i32, [_vp, _vp, _vp, _u32, C.POINTER(_vp)]),

@@ -52,6 +52,12 @@ class Context:
     def set_option(self, name, value):
         self.check(self._lib.bam3d_ctx_set_option(self.handle, name.encode(), int(value)))
 
+    def read_timing(self):
+        """-> (total_ms, calls) of the bracketed main kernels since the last read (option "timing" = 1)."""
+        ms, cnt = C.c_double(0), C.c_uint64(0)
+        self.check(self._lib.bam3d_ctx_read_timing(self.handle, C.byref(ms), C.byref(cnt)))
+        return float(ms.value), int(cnt.value)
+
     def close(self):
         if self.handle:
             self._lib.bam3d_ctx_destroy(self.handle)
@@ -290,6 +296,25 @@ class GJK:
         self.ctx.check(self.ctx._lib.bam3d_gjk_time_of_impact(self.ctx.handle, shapes_start.handle, shapes_end.handle, _ptr(pairs), n,
                                                               C.byref(self.settings), _ptr(contacts), _ptr(status)))
         return contacts, status
+
+    # ---- device-resident entry points (pointers are raw device addresses; asynchronous on ctx.stream) ------
+    def intersect_dev(self, shapes, d_pairs, n, d_status):
+        self.ctx.check(self.ctx._lib.bam3d_gjk_intersect_dev(self.ctx.handle, shapes.handle, d_pairs, n, C.byref(self.settings), d_status))
+
+    def intersection_dev(self, strategy, shapes, d_pairs, n, d_contacts, d_status):
+        self.ctx.check(self.ctx._lib.bam3d_gjk_contact_dev(self.ctx.handle, shapes.handle, d_pairs, n, C.byref(self.settings), int(strategy),
+                                                           d_contacts, d_status))
+
+    def distance_dev(self, shapes, d_pairs, n, d_ref, d_dist, d_status):
+        self.ctx.check(self.ctx._lib.bam3d_gjk_distance_dev(self.ctx.handle, shapes.handle, d_pairs, n, C.byref(self.settings), d_ref, d_dist,
+                                                            d_status))
+
+    def intersection_time_of_impact_dev(self, shapes_start, shapes_end, d_pairs, n, d_contacts, d_status):
+        self.ctx.check(self.ctx._lib.bam3d_gjk_time_of_impact_dev(self.ctx.handle, shapes_start.handle, shapes_end.handle, d_pairs, n,
+                                                                  C.byref(self.settings), d_contacts, d_status))
+
+    def compact_contacts_dev(self, d_contacts, d_status, n, base, d_out, capacity, d_count):
+        self.ctx.check(self.ctx._lib.bam3d_compact_contacts_dev(self.ctx.handle, d_contacts, d_status, n, base, d_out, capacity, d_count))
 
     # ---- the reference's scalar methods, as batch-of-1 -----------------------------------------------------
     def _two(self, left, left_transform, right, right_transform):

@@ -100,6 +100,21 @@ static int32_t check_launch(bam3d_ctx* ctx, const char* what) {
     return BAM3D_OK;
 }
 
+// Bracket the dominant kernel(s) of a call with events when the "timing" option is on.
+struct KernelTimer {
+    bam3d_ctx* ctx; cudaEvent_t a = nullptr, b = nullptr;
+    explicit KernelTimer(bam3d_ctx* c) : ctx(c) {
+        if (!ctx->opt_timing) return;
+        cudaEventCreate(&a); cudaEventCreate(&b);
+        cudaEventRecord(a, ctx->stream);
+    }
+    ~KernelTimer() {
+        if (!a) return;
+        cudaEventRecord(b, ctx->stream);
+        ctx->timing_events.emplace_back(a, b);
+    }
+};
+
 static int32_t check_n(bam3d_ctx* ctx, uint64_t n) {
     if (n > 0xFFFFFF00ull) return b3_fail(ctx, BAM3D_ERR_ARG, "batch too large: n must be < 2^32 - 256 pairs per call", cudaSuccess);
     return BAM3D_OK;
@@ -153,7 +168,23 @@ uint64_t bam3d_ctx_launch_count(const bam3d_ctx* ctx) { return ctx ? ctx->launch
 int32_t bam3d_ctx_set_option(bam3d_ctx* ctx, const char* name, int32_t value) {
     if (!ctx || !name) return BAM3D_ERR_ARG;
     if (!std::strcmp(name, "binning")) { ctx->opt_binning = value != 0; return BAM3D_OK; }
+    if (!std::strcmp(name, "timing")) { ctx->opt_timing = value != 0; return BAM3D_OK; }
     return b3_fail(ctx, BAM3D_ERR_ARG, "unknown option", cudaSuccess);
+}
+
+int32_t bam3d_ctx_read_timing(bam3d_ctx* ctx, double* out_total_ms, uint64_t* out_count) {
+    if (!ctx || !out_total_ms || !out_count) return BAM3D_ERR_ARG;
+    CU_TRY(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize");
+    double total = 0.0;
+    for (auto& ev : ctx->timing_events) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev.first, ev.second);
+        total += ms;
+        cudaEventDestroy(ev.first); cudaEventDestroy(ev.second);
+    }
+    *out_total_ms = total; *out_count = ctx->timing_events.size();
+    ctx->timing_events.clear();
+    return BAM3D_OK;
 }
 
 int32_t bam3d_host_alloc(bam3d_ctx* ctx, uint64_t bytes, void** out_ptr) {
@@ -283,7 +314,8 @@ int32_t bam3d_gjk_intersect_dev(bam3d_ctx* ctx, const bam3d_shapes* shapes, cons
     Plan plan = plan_for(ctx, shapes);
     BinScratch B; const BinScratch* pb;
     if ((rc = prepare_bins(ctx, plan, S, (const uint2*)d_pairs, (uint32_t)n, B, &pb))) return rc;
-    ctx->launches += launch_intersect(ctx->stream, S, (const uint2*)d_pairs, (uint32_t)n, pb, plan.run_thread, plan.run_warp, to_dev(settings), d_status);
+    { KernelTimer kt(ctx);
+      ctx->launches += launch_intersect(ctx->stream, S, (const uint2*)d_pairs, (uint32_t)n, pb, plan.run_thread, plan.run_warp, to_dev(settings), d_status); }
     return check_launch(ctx, "gjk_intersect_kernel");
 }
 
@@ -302,9 +334,11 @@ int32_t bam3d_gjk_contact_dev(bam3d_ctx* ctx, const bam3d_shapes* shapes, const 
     Plan plan = plan_for(ctx, shapes);
     BinScratch B; const BinScratch* pb;
     if ((rc = prepare_bins(ctx, plan, S, (const uint2*)d_pairs, (uint32_t)n, B, &pb))) return rc;
-    if (strategy == BAM3D_FULL_RESOLUTION && (rc = ctx->epa_overflow.reserve(ctx, contact_overflow_scratch_bytes()))) return rc;
-    ctx->launches += launch_contact(ctx->stream, S, (const uint2*)d_pairs, (uint32_t)n, pb, plan.run_thread, plan.run_warp, cfg, strategy,
-                                    ctx->epa_overflow.ptr, (float4*)d_contacts, d_status);
+    if ((rc = ctx->epa_overflow.reserve(ctx, contact_overflow_scratch_bytes()))) return rc;
+    if (plan.run_thread && (rc = ctx->epa_queue.reserve(ctx, contact_queue_bytes(strategy == BAM3D_FULL_RESOLUTION ? (uint32_t)n : 0)))) return rc;
+    { KernelTimer kt(ctx);
+      ctx->launches += launch_contact(ctx->stream, S, (const uint2*)d_pairs, (uint32_t)n, pb, plan.run_thread, plan.run_warp, cfg, strategy,
+                                      ctx->epa_overflow.ptr, ctx->epa_queue.ptr, (float4*)d_contacts, d_status); }
     return check_launch(ctx, "gjk_contact_kernel");
 }
 
@@ -319,8 +353,9 @@ int32_t bam3d_gjk_distance_dev(bam3d_ctx* ctx, const bam3d_shapes* shapes, const
     Plan plan = plan_for(ctx, shapes);
     BinScratch B; const BinScratch* pb;
     if ((rc = prepare_bins(ctx, plan, S, (const uint2*)d_pairs, (uint32_t)n, B, &pb))) return rc;
-    ctx->launches += launch_distance(ctx->stream, S, (const uint2*)d_pairs, (uint32_t)n, pb, plan.run_thread, plan.run_warp, to_dev(settings),
-                                     d_ref_value, d_distance, d_status);
+    { KernelTimer kt(ctx);
+      ctx->launches += launch_distance(ctx->stream, S, (const uint2*)d_pairs, (uint32_t)n, pb, plan.run_thread, plan.run_warp, to_dev(settings),
+                                       d_ref_value, d_distance, d_status); }
     return check_launch(ctx, "gjk_distance_kernel");
 }
 
@@ -336,8 +371,9 @@ int32_t bam3d_gjk_time_of_impact_dev(bam3d_ctx* ctx, const bam3d_shapes* s0, con
     Plan plan = plan_for(ctx, s0);
     BinScratch B; const BinScratch* pb;
     if ((rc = prepare_bins(ctx, plan, S0, (const uint2*)d_pairs, (uint32_t)n, B, &pb))) return rc;
-    ctx->launches += launch_toi(ctx->stream, S0, S1, (const uint2*)d_pairs, (uint32_t)n, pb, plan.run_thread, plan.run_warp, to_dev(settings),
-                                (float4*)d_contacts, d_status);
+    { KernelTimer kt(ctx);
+      ctx->launches += launch_toi(ctx->stream, S0, S1, (const uint2*)d_pairs, (uint32_t)n, pb, plan.run_thread, plan.run_warp, to_dev(settings),
+                                  (float4*)d_contacts, d_status); }
     return check_launch(ctx, "gjk_toi_kernel");
 }
 

@@ -17,15 +17,14 @@ namespace b3 {
 // Capacities. EPA's loop counter starts at 1 and stops at max_iterations (<= 100, enforced by the host layer), so
 // at most 99 vertices are added to the 4 of the GJK tetrahedron: VCAP >= 103 always suffices. A closed
 // triangulated polytope has F = 2V - 4 <= 202 faces, but near-degenerate input (curved shapes, NaN normals)
-// makes the reference build pinched polytopes with many more (868 faces seen in 30k mixed contacts, 0.013 % of
-// pairs above 202). Two tiers therefore: the fast tier (per-thread local memory / per-warp shared memory) holds
-// EPA_FCAP faces; a pair that outgrows it gets ST_CAPACITY and is redone by the overflow kernel against a
-// global-memory slab with the EPA_BIG_* capacities. Only a pair that outgrows those keeps ST_CAPACITY.
+// makes the reference build pinched polytopes with many more (63 of 2^20 mixed pairs exceed 256 faces, 44 exceed
+// 1024, and those keep growing multiplicatively). Two tiers therefore: the fast tier (per-thread local memory /
+// per-warp shared memory) holds EPA_FCAP faces; a pair that outgrows it gets ST_CAPACITY and is redone by the
+// warp-per-pair overflow tier (epa_big.cuh) with EPA_BIG_FCAP faces. Only a pair that outgrows that keeps
+// ST_CAPACITY (the CPU oracle applies the same limit, oracle/bam3d_oracle.hpp EPA_FACE_LIMIT).
 constexpr int EPA_VCAP = 104;
 constexpr int EPA_FCAP = 256;
 constexpr int EPA_ECAP = 320;
-constexpr int EPA_BIG_FCAP = 4096;
-constexpr int EPA_BIG_ECAP = 6144;
 
 struct PolytopeStore {
     float* vv;        // EPA_VCAP * 3 : SupportPoint.v
@@ -67,85 +66,102 @@ B3_DEV bool remove_or_add_edge(uint16_t* ed, int& ne, int ecap, uint32_t a, uint
     return true;
 }
 
-// EPA3::process (epa3d.rs:16-52). `s` is the 4-point GJK simplex (with sup_a). Returns a Status.
+// Polytope::new (epa3d.rs:103-109) + Face::new (:172-179) from the 4-point GJK simplex (with sup_a).
 template <bool WARP>
-B3_DEV uint8_t epa_process(const Shape& L, const Shape& R, const Simplex<true>& s, float tolerance, uint32_t max_iterations,
-                           const PolytopeStore& P, ContactOut& out) {
-    // Polytope::new (epa3d.rs:103-109) + Face::new (:172-179)
+B3_DEV void epa_init(const Simplex<true>& s, const PolytopeStore& P, int& nv, int& nf, uint32_t& it) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) { st3(P.vv, k, s.v[k]); st3(P.va, k, s.a[k]); }
     if (WARP) __syncwarp();
-    int nv = 4, nf = 4;
     make_face(P, 0, 3, 2, 1);
     make_face(P, 1, 3, 1, 0);
     make_face(P, 2, 3, 0, 2);
     make_face(P, 3, 2, 0, 1);
     if (WARP) __syncwarp();
+    nv = 4; nf = 4; it = 1;
+}
 
-    uint32_t i = 1;
-    for (;;) {
-        // closest_face_to_origin (epa3d.rs:111-119): strict <, first minimum wins
-        int best = 0;
-        float best_d = P.fn[0].w;
-        for (int k = 1; k < nf; ++k) {
-            float dk = P.fn[k].w;
-            if (dk < best_d) { best_d = dk; best = k; }
-        }
-        float4 bf = P.fn[best];
-        V3 normal = v3(bf.x, bf.y, bf.z);
-        V3 pv, pa;
-        minkowski_support<WARP>(L, R, normal, pv, pa);
-        float d = dot(pv, normal);
-        if (d - bf.w < tolerance || i >= max_iterations) {
-            // contact() / point() (epa3d.rs:70-94)
-            uint32_t idx = P.fi[best];
+constexpr uint8_t EPA_CONTINUE = 0xFF;
+
+// One trip of EPA3::process's loop (epa3d.rs:33-51): closest face, support, convergence test, Polytope::add.
+// Returns EPA_CONTINUE, or a final Status (ST_OK with `out` filled, ST_CAPACITY).
+template <bool WARP>
+B3_DEV uint8_t epa_iterate(const Shape& L, const Shape& R, float tolerance, uint32_t max_iterations, const PolytopeStore& P,
+                           int& nv, int& nf, uint32_t& it, ContactOut& out) {
+    // closest_face_to_origin (epa3d.rs:111-119): strict <, first minimum wins
+    int best = 0;
+    float best_d = P.fn[0].w;
+    for (int k = 1; k < nf; ++k) {
+        float dk = P.fn[k].w;
+        if (dk < best_d) { best_d = dk; best = k; }
+    }
+    float4 bf = P.fn[best];
+    V3 normal = v3(bf.x, bf.y, bf.z);
+    V3 pv, pa;
+    minkowski_support<WARP>(L, R, normal, pv, pa);
+    float d = dot(pv, normal);
+    if (d - bf.w < tolerance || it >= max_iterations) {
+        // contact() / point() (epa3d.rs:70-94)
+        uint32_t idx = P.fi[best];
+        uint32_t i0 = idx & 0xFF, i1 = (idx >> 8) & 0xFF, i2 = (idx >> 16) & 0xFF;
+        float u, v, w;
+        barycentric_vector(normal * bf.w, ld3(P.vv, i0), ld3(P.vv, i1), ld3(P.vv, i2), u, v, w);
+        out.normal = normal;
+        out.depth = bf.w;
+        out.point = ld3(P.va, i0) * u + ld3(P.va, i1) * v + ld3(P.va, i2) * w;
+        return ST_OK;
+    }
+
+    // Polytope::add (epa3d.rs:121-149)
+    int ne = 0;
+    int k = 0;
+    bool ok = true;
+    while (k < nf) {
+        float4 f = P.fn[k];
+        uint32_t idx = P.fi[k];
+        V3 v0 = ld3(P.vv, idx & 0xFF);
+        float dt = dot(v3(f.x, f.y, f.z), pv - v0);
+        if (dt > 0.f) {
+            --nf;                         // swap_remove(k)
+            float4 lf = P.fn[nf];
+            uint32_t li = P.fi[nf];
+            if (WARP) __syncwarp();
+            P.fn[k] = lf;
+            P.fi[k] = li;
             uint32_t i0 = idx & 0xFF, i1 = (idx >> 8) & 0xFF, i2 = (idx >> 16) & 0xFF;
-            float u, v, w;
-            barycentric_vector(normal * bf.w, ld3(P.vv, i0), ld3(P.vv, i1), ld3(P.vv, i2), u, v, w);
-            out.normal = normal;
-            out.depth = bf.w;
-            out.point = ld3(P.va, i0) * u + ld3(P.va, i1) * v + ld3(P.va, i2) * w;
-            return ST_OK;
+            ok = ok && remove_or_add_edge(P.ed, ne, P.ecap, i0, i1);
+            ok = ok && remove_or_add_edge(P.ed, ne, P.ecap, i1, i2);
+            ok = ok && remove_or_add_edge(P.ed, ne, P.ecap, i2, i0);
+            if (WARP) __syncwarp();
+        } else {
+            ++k;
         }
+    }
+    if (!ok || nv >= EPA_VCAP || nf + ne > P.fcap) return ST_CAPACITY;
+    const int n = nv;
+    st3(P.vv, n, pv);
+    st3(P.va, n, pa);
+    ++nv;
+    if (WARP) __syncwarp();
+    for (int e = 0; e < ne; ++e) {
+        uint32_t ab = P.ed[e];
+        make_face(P, nf + e, (uint32_t)n, ab & 0xFF, (ab >> 8) & 0xFF);
+    }
+    nf += ne;
+    if (WARP) __syncwarp();
+    it += 1;
+    return EPA_CONTINUE;
+}
 
-        // Polytope::add (epa3d.rs:121-149)
-        int ne = 0;
-        int k = 0;
-        bool ok = true;
-        while (k < nf) {
-            float4 f = P.fn[k];
-            uint32_t idx = P.fi[k];
-            V3 v0 = ld3(P.vv, idx & 0xFF);
-            float dt = dot(v3(f.x, f.y, f.z), pv - v0);
-            if (dt > 0.f) {
-                --nf;                         // swap_remove(k)
-                float4 lf = P.fn[nf];
-                uint32_t li = P.fi[nf];
-                if (WARP) __syncwarp();
-                P.fn[k] = lf;
-                P.fi[k] = li;
-                uint32_t i0 = idx & 0xFF, i1 = (idx >> 8) & 0xFF, i2 = (idx >> 16) & 0xFF;
-                ok = ok && remove_or_add_edge(P.ed, ne, P.ecap, i0, i1);
-                ok = ok && remove_or_add_edge(P.ed, ne, P.ecap, i1, i2);
-                ok = ok && remove_or_add_edge(P.ed, ne, P.ecap, i2, i0);
-                if (WARP) __syncwarp();
-            } else {
-                ++k;
-            }
-        }
-        if (!ok || nv >= EPA_VCAP || nf + ne > P.fcap) return ST_CAPACITY;
-        const int n = nv;
-        st3(P.vv, n, pv);
-        st3(P.va, n, pa);
-        ++nv;
-        if (WARP) __syncwarp();
-        for (int e = 0; e < ne; ++e) {
-            uint32_t ab = P.ed[e];
-            make_face(P, nf + e, (uint32_t)n, ab & 0xFF, (ab >> 8) & 0xFF);
-        }
-        nf += ne;
-        if (WARP) __syncwarp();
-        i += 1;
+// EPA3::process (epa3d.rs:16-52). `s` is the 4-point GJK simplex (with sup_a). Returns a Status.
+template <bool WARP>
+B3_DEV uint8_t epa_process(const Shape& L, const Shape& R, const Simplex<true>& s, float tolerance, uint32_t max_iterations,
+                           const PolytopeStore& P, ContactOut& out) {
+    int nv, nf;
+    uint32_t it;
+    epa_init<WARP>(s, P, nv, nf, it);
+    for (;;) {
+        uint8_t st = epa_iterate<WARP>(L, R, tolerance, max_iterations, P, nv, nf, it, out);
+        if (st != EPA_CONTINUE) return st;
     }
 }
 

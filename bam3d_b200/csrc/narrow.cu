@@ -12,6 +12,7 @@
 // Compiled with -fmad=false (see vecmath.cuh).
 #include "narrow.h"
 #include "gjk.cuh"
+#include "epa_big.cuh"
 
 namespace b3 {
 
@@ -20,6 +21,7 @@ constexpr int WARPS_PER_BLOCK = TPB / 32;
 constexpr int NUM_SMS = 148;        // B200
 constexpr uint32_t KEY_WARP = 49;   // bin of the pairs that involve a polyhedron (thread bins are 0..48)
 constexpr uint32_t ERR_NON_AFFINE = 1u, ERR_BAD_KIND = 2u, ERR_BAD_MESH = 4u;
+constexpr uint32_t OVF_MAX = 65536;  // capacity of the EPA overflow list; pairs beyond it keep ST_CAPACITY
 
 // ------------------------------------------------------------------------------------------------------------
 // pack_shapes: Mat4 (16 f32, column-major) + params -> 96-byte ShapeRec with the inverse's linear part.
@@ -229,8 +231,8 @@ __global__ void __launch_bounds__(TPB) gjk_intersect_kernel(ShapeSetDev S, const
 template <bool WARP>
 __global__ void __launch_bounds__(TPB) gjk_contact_kernel(ShapeSetDev S, const uint2* __restrict__ pairs, uint32_t n,
                                                           const uint32_t* __restrict__ order, const uint32_t* __restrict__ ranges,
-                                                          SettingsDev cfg, int strategy, float4* __restrict__ contacts,
-                                                          uint8_t* __restrict__ status) {
+                                                          SettingsDev cfg, int strategy, unsigned char* __restrict__ ovf_scratch,
+                                                          float4* __restrict__ contacts, uint8_t* __restrict__ status) {
     extern __shared__ __align__(16) unsigned char dyn_smem[];  // WARP: WARPS_PER_BLOCK polytope slices; else unused
     // thread-per-pair polytope: per-thread local memory (L1/L2-backed), indexed identically by all lanes
     float lvv[WARP ? 1 : EPA_VCAP * 3];
@@ -266,46 +268,181 @@ __global__ void __launch_bounds__(TPB) gjk_contact_kernel(ShapeSetDev S, const u
             contacts[2 * (size_t)p] = make_float4(c.normal.x, c.normal.y, c.normal.z, c.depth);
             contacts[2 * (size_t)p + 1] = make_float4(c.point.x, c.point.y, c.point.z, 0.f);
             status[p] = st;
+            if (st == ST_CAPACITY) {  // hand the pair to the overflow tier
+                uint32_t slot = atomicAdd(reinterpret_cast<uint32_t*>(ovf_scratch), 1u);
+                if (slot < OVF_MAX) reinterpret_cast<uint32_t*>(ovf_scratch + 256)[slot] = p;
+            }
         }
         if (WARP) __syncwarp();
     }
 }
 
-// Overflow tier of the contact kernels: redo every pair the fast tier left at ST_CAPACITY, one thread per pair,
-// against a per-thread global-memory slab with the EPA_BIG_* capacities. Rare (~1e-4 of contacts), so a small
-// fixed grid scans the status array. Polyhedron supports are scanned sequentially here.
-constexpr int OVF_BLOCKS = 8;
-constexpr size_t OVF_SLAB_BYTES = (size_t)EPA_VCAP * 3 * 4 * 2 + (size_t)EPA_BIG_FCAP * (16 + 4) + (size_t)EPA_BIG_ECAP * 2;
+// ------------------------------------------------------------------------------------------------------------
+// Thread-per-pair contact path, split in two kernels so that lanes stay busy:
+//   gjk_phase_kernel   GJK::intersect per pair; misses are final (zero contact + status); every hit that needs
+//                      EPA is appended (warp-aggregated) to a device queue with its 4-point simplex (v, sup_a);
+//   epa_refill_kernel  persistent warps; each LANE owns one queued pair at a time and all 32 lanes advance by one
+//                      EPA iteration per trip; a lane whose pair finishes refills from the queue at once. Without
+//                      this, a warp ran as long as its slowest pair (iteration counts span 2..100) and ncu showed
+//                      4.4 of 32 lanes active on average.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int EPAQ_REC_F4 = 7;            // queue record: 4 x (v, sup_a) = 24 floats, pair index, 3 pad words
+constexpr size_t EPAQ_HEADER_BYTES = 256;  // [0] = number of records, [1] = consumer cursor
 
-__global__ void __launch_bounds__(TPB) gjk_contact_overflow_kernel(ShapeSetDev S, const uint2* __restrict__ pairs, uint32_t n, SettingsDev cfg,
-                                                                   unsigned char* __restrict__ slabs, float4* __restrict__ contacts,
-                                                                   uint8_t* __restrict__ status) {
-    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned char* slab = slabs + (size_t)tid * OVF_SLAB_BYTES;
+__global__ void __launch_bounds__(TPB) gjk_phase_kernel(ShapeSetDev S, const uint2* __restrict__ pairs, uint32_t n,
+                                                        const uint32_t* __restrict__ order, const uint32_t* __restrict__ ranges,
+                                                        SettingsDev cfg, int strategy, unsigned char* __restrict__ queue,
+                                                        float4* __restrict__ contacts, uint8_t* __restrict__ status) {
+    uint32_t first, end, stride;
+    work_range<false>(ranges, n, first, end, stride);
+    uint32_t* q_count = reinterpret_cast<uint32_t*>(queue);
+    float4* q_recs = reinterpret_cast<float4*>(queue + EPAQ_HEADER_BYTES);
+    const uint32_t lane = threadIdx.x & 31u;
+    // keep the warp convergent for the ballot below: iterate until every lane is past the end
+    for (uint32_t slot0 = first - lane; slot0 < end; slot0 += stride) {
+        const uint32_t slot = slot0 + lane;
+        const bool valid = slot < end;
+        uint32_t p = 0;
+        uint8_t st = ST_MISS;
+        Simplex<true> s;
+        if (valid) {
+            p = order ? __ldg(order + slot) : slot;
+            uint2 pr = __ldg(pairs + p);
+            Shape L, R;
+            load_pair_shape(L, S, pr.x);
+            load_pair_shape(R, S, pr.y);
+            st = gjk_intersect<false, true>(L, R, cfg.max_iterations, s);
+        }
+        const bool to_epa = valid && st == ST_OK && strategy == 0;
+        const uint32_t mask = __ballot_sync(0xFFFFFFFFu, to_epa);
+        if (mask) {
+            uint32_t base = 0;
+            const uint32_t leader = __ffs(mask) - 1;
+            if (lane == leader) base = atomicAdd(q_count, (uint32_t)__popc(mask));
+            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            if (to_epa) {
+                float4* r = q_recs + (size_t)(base + __popc(mask & ((1u << lane) - 1u))) * EPAQ_REC_F4;
+                r[0] = make_float4(s.v[0].x, s.v[0].y, s.v[0].z, s.a[0].x);
+                r[1] = make_float4(s.a[0].y, s.a[0].z, s.v[1].x, s.v[1].y);
+                r[2] = make_float4(s.v[1].z, s.a[1].x, s.a[1].y, s.a[1].z);
+                r[3] = make_float4(s.v[2].x, s.v[2].y, s.v[2].z, s.a[2].x);
+                r[4] = make_float4(s.a[2].y, s.a[2].z, s.v[3].x, s.v[3].y);
+                r[5] = make_float4(s.v[3].z, s.a[3].x, s.a[3].y, s.a[3].z);
+                r[6] = make_float4(__uint_as_float(p), 0.f, 0.f, 0.f);
+            }
+        }
+        if (valid && !to_epa) {
+            contacts[2 * (size_t)p] = make_float4(0.f, 0.f, 0.f, 0.f);
+            contacts[2 * (size_t)p + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            status[p] = st;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(TPB) epa_refill_kernel(ShapeSetDev S, const uint2* __restrict__ pairs, SettingsDev cfg,
+                                                         unsigned char* __restrict__ queue, unsigned char* __restrict__ ovf_scratch,
+                                                         float4* __restrict__ contacts, uint8_t* __restrict__ status) {
+    float lvv[EPA_VCAP * 3];
+    float lva[EPA_VCAP * 3];
+    float4 lfn[EPA_FCAP];
+    uint32_t lfi[EPA_FCAP];
+    uint16_t led[EPA_ECAP];
     PolytopeStore P;
-    P.fn = reinterpret_cast<float4*>(slab);                       slab += (size_t)EPA_BIG_FCAP * 16;
-    P.fi = reinterpret_cast<uint32_t*>(slab);                     slab += (size_t)EPA_BIG_FCAP * 4;
-    P.vv = reinterpret_cast<float*>(slab);                        slab += (size_t)EPA_VCAP * 12;
-    P.va = reinterpret_cast<float*>(slab);                        slab += (size_t)EPA_VCAP * 12;
-    P.ed = reinterpret_cast<uint16_t*>(slab);
-    P.fcap = EPA_BIG_FCAP; P.ecap = EPA_BIG_ECAP;
-    for (uint32_t p = tid; p < n; p += gridDim.x * blockDim.x) {
-        if (status[p] != ST_CAPACITY) continue;
+    P.vv = lvv; P.va = lva; P.fn = lfn; P.fi = lfi; P.ed = led;
+    P.fcap = EPA_FCAP; P.ecap = EPA_ECAP;
+    const uint32_t count = *reinterpret_cast<const uint32_t*>(queue);
+    uint32_t* q_cursor = reinterpret_cast<uint32_t*>(queue) + 1;
+    const float4* q_recs = reinterpret_cast<const float4*>(queue + EPAQ_HEADER_BYTES);
+    const uint32_t lane = threadIdx.x & 31u;
+    bool active = false, exhausted = false;
+    Shape L, R;
+    int nv = 0, nf = 0;
+    uint32_t it = 0, p = 0;
+    for (;;) {
+        // refill idle lanes from the queue (one atomic per warp per trip)
+        const uint32_t need = __ballot_sync(0xFFFFFFFFu, !active && !exhausted);
+        if (need) {
+            uint32_t base = 0;
+            const uint32_t leader = __ffs(need) - 1;
+            if (lane == leader) base = atomicAdd(q_cursor, (uint32_t)__popc(need));
+            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            if (!active && !exhausted) {
+                const uint32_t idx = base + __popc(need & ((1u << lane) - 1u));
+                if (idx < count) {
+                    const float4* r = q_recs + (size_t)idx * EPAQ_REC_F4;
+                    float4 a = __ldg(r), b = __ldg(r + 1), c = __ldg(r + 2), d = __ldg(r + 3), e = __ldg(r + 4), f = __ldg(r + 5), g = __ldg(r + 6);
+                    Simplex<true> s;
+                    s.n = 4;
+                    s.v[0] = v3(a.x, a.y, a.z); s.a[0] = v3(a.w, b.x, b.y);
+                    s.v[1] = v3(b.z, b.w, c.x); s.a[1] = v3(c.y, c.z, c.w);
+                    s.v[2] = v3(d.x, d.y, d.z); s.a[2] = v3(d.w, e.x, e.y);
+                    s.v[3] = v3(e.z, e.w, f.x); s.a[3] = v3(f.y, f.z, f.w);
+                    p = __float_as_uint(g.x);
+                    uint2 pr = __ldg(pairs + p);
+                    load_pair_shape(L, S, pr.x);
+                    load_pair_shape(R, S, pr.y);
+                    epa_init<false>(s, P, nv, nf, it);
+                    active = true;
+                } else {
+                    exhausted = true;
+                }
+            }
+        }
+        if (!__any_sync(0xFFFFFFFFu, active)) break;
+        if (active) {
+            ContactOut c;
+            uint8_t st = epa_iterate<false>(L, R, cfg.epa_tolerance, cfg.max_iterations, P, nv, nf, it, c);
+            if (st != EPA_CONTINUE) {
+                if (st != ST_OK) { c.normal = v3(0.f, 0.f, 0.f); c.depth = 0.f; c.point = v3(0.f, 0.f, 0.f); }
+                contacts[2 * (size_t)p] = make_float4(c.normal.x, c.normal.y, c.normal.z, c.depth);
+                contacts[2 * (size_t)p + 1] = make_float4(c.point.x, c.point.y, c.point.z, 0.f);
+                status[p] = st;
+                if (st == ST_CAPACITY) {  // hand the pair to the overflow tier
+                    uint32_t slot = atomicAdd(reinterpret_cast<uint32_t*>(ovf_scratch), 1u);
+                    if (slot < OVF_MAX) reinterpret_cast<uint32_t*>(ovf_scratch + 256)[slot] = p;
+                }
+                active = false;
+            }
+        }
+    }
+}
+
+// Overflow tier of the contact kernels (epa_big.cuh): the fast-tier kernels append every pair they leave at
+// ST_CAPACITY to a device list; one warp per listed pair redoes GJK + EPA against a per-warp global-memory slab.
+// Rare (~6e-5 of mixed pairs), but those pairs are the long tail of the reference's cost.
+constexpr int OVF_WARPS = NUM_SMS;        // one 32-thread block per SM
+constexpr size_t OVF_HEADER_BYTES = 256 + (size_t)OVF_MAX * 4;
+
+__global__ void __launch_bounds__(32) gjk_contact_overflow_kernel(ShapeSetDev S, const uint2* __restrict__ pairs, SettingsDev cfg,
+                                                                  unsigned char* __restrict__ scratch, float4* __restrict__ contacts,
+                                                                  uint8_t* __restrict__ status) {
+    const uint32_t count = min(*reinterpret_cast<const uint32_t*>(scratch), OVF_MAX);
+    const uint32_t* list = reinterpret_cast<const uint32_t*>(scratch + 256);
+    const uint32_t warp = blockIdx.x, lane = threadIdx.x;
+    if (warp >= count) return;
+    BigStore B = carve_big_store(scratch + OVF_HEADER_BYTES + (size_t)warp * EPA_BIG_SLAB_BYTES);
+    for (int k = lane; k < EPA_KEYS; k += 32) { B.head[k] = EPA_NIL; B.tail[k] = EPA_NIL; }
+    __syncwarp();
+    for (uint32_t i = warp; i < count; i += gridDim.x) {
+        uint32_t p = list[i];
         uint2 pr = __ldg(pairs + p);
         Shape L, R;
         load_pair_shape(L, S, pr.x);
         load_pair_shape(R, S, pr.y);
         Simplex<true> s;
-        uint8_t st = gjk_intersect<false, true>(L, R, cfg.max_iterations, s);
+        uint8_t st = gjk_intersect<true, true>(L, R, cfg.max_iterations, s);
         ContactOut c;
         c.normal = v3(0.f, 0.f, 0.f); c.depth = 0.f; c.point = v3(0.f, 0.f, 0.f);
         if (st == ST_OK) {
-            st = epa_process<false>(L, R, s, cfg.epa_tolerance, cfg.max_iterations, P, c);
+            st = epa_process_big(L, R, s, cfg.epa_tolerance, cfg.max_iterations, B, c);
             if (st != ST_OK) { c.normal = v3(0.f, 0.f, 0.f); c.depth = 0.f; c.point = v3(0.f, 0.f, 0.f); }
         }
-        contacts[2 * (size_t)p] = make_float4(c.normal.x, c.normal.y, c.normal.z, c.depth);
-        contacts[2 * (size_t)p + 1] = make_float4(c.point.x, c.point.y, c.point.z, 0.f);
-        status[p] = st;
+        if (lane == 0) {
+            contacts[2 * (size_t)p] = make_float4(c.normal.x, c.normal.y, c.normal.z, c.depth);
+            contacts[2 * (size_t)p + 1] = make_float4(c.point.x, c.point.y, c.point.z, 0.f);
+            status[p] = st;
+        }
+        __syncwarp();
     }
 }
 
@@ -448,17 +585,45 @@ int launch_intersect(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs
                      bool run_warp, const SettingsDev& cfg, uint8_t* d_status) {
     B3_LAUNCH(gjk_intersect_kernel, 0, S, d_pairs, n, order, ranges, cfg, d_status)
 }
-static int launch_contact_main(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs, uint32_t n, const BinScratch* B, bool run_thread,
-                               bool run_warp, const SettingsDev& cfg, int strategy, float4* d_contacts, uint8_t* d_status) {
-    B3_LAUNCH(gjk_contact_kernel, WARPS_PER_BLOCK * sizeof(WarpPolytopeSmem), S, d_pairs, n, order, ranges, cfg, strategy, d_contacts, d_status)
+size_t contact_overflow_scratch_bytes() { return OVF_HEADER_BYTES + (size_t)OVF_WARPS * EPA_BIG_SLAB_BYTES; }
+size_t contact_queue_bytes(uint32_t n) { return EPAQ_HEADER_BYTES + (size_t)n * EPAQ_REC_F4 * 16; }
+
+static int epa_refill_grid() {
+    static int blocks = 0;
+    if (!blocks) {
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, epa_refill_kernel, TPB, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
+        blocks = per_sm * NUM_SMS;
+    }
+    return blocks;
 }
-size_t contact_overflow_scratch_bytes() { return (size_t)OVF_BLOCKS * TPB * OVF_SLAB_BYTES; }
+
 int launch_contact(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs, uint32_t n, const BinScratch* B, bool run_thread,
-                   bool run_warp, const SettingsDev& cfg, int strategy, void* d_overflow_scratch, float4* d_contacts, uint8_t* d_status) {
-    int launched = launch_contact_main(st, S, d_pairs, n, B, run_thread, run_warp, cfg, strategy, d_contacts, d_status);
-    if (n && strategy == 0) {
-        gjk_contact_overflow_kernel<<<OVF_BLOCKS, TPB, 0, st>>>(S, d_pairs, n, cfg, reinterpret_cast<unsigned char*>(d_overflow_scratch),
-                                                               d_contacts, d_status);
+                   bool run_warp, const SettingsDev& cfg, int strategy, void* d_overflow_scratch, void* d_queue, float4* d_contacts,
+                   uint8_t* d_status) {
+    unsigned char* ovf = reinterpret_cast<unsigned char*>(d_overflow_scratch);
+    unsigned char* queue = reinterpret_cast<unsigned char*>(d_queue);
+    if (n == 0) return 0;
+    int launched = 0;
+    const uint32_t* order = B ? B->order : nullptr;
+    const uint32_t* ranges = B ? B->ranges : nullptr;
+    cudaMemsetAsync(ovf, 0, 4, st);
+    if (run_thread) {
+        cudaMemsetAsync(queue, 0, 8, st);
+        gjk_phase_kernel<<<thread_grid(n), TPB, 0, st>>>(S, d_pairs, n, order, ranges, cfg, strategy, queue, d_contacts, d_status);
+        ++launched;
+        if (strategy == 0) {
+            epa_refill_kernel<<<epa_refill_grid(), TPB, 0, st>>>(S, d_pairs, cfg, queue, ovf, d_contacts, d_status);
+            ++launched;
+        }
+    }
+    if (run_warp) {
+        gjk_contact_kernel<true><<<warp_grid(n), TPB, WARPS_PER_BLOCK * sizeof(WarpPolytopeSmem), st>>>(S, d_pairs, n, order, ranges, cfg,
+                                                                                                     strategy, ovf, d_contacts, d_status);
+        ++launched;
+    }
+    if (strategy == 0) {
+        gjk_contact_overflow_kernel<<<OVF_WARPS, 32, 0, st>>>(S, d_pairs, cfg, ovf, d_contacts, d_status);
         ++launched;
     }
     return launched;

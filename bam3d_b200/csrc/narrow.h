@@ -41,11 +41,13 @@ int launch_bin_pairs(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs
 // B may be null (no binning: the selected kernel covers every pair). run_thread / run_warp pick the execution shapes.
 int launch_intersect(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs, uint32_t n, const BinScratch* B,
                      bool run_thread, bool run_warp, const SettingsDev& cfg, uint8_t* d_status);
-// d_overflow_scratch: contact_overflow_scratch_bytes() of device memory for the EPA overflow tier (see epa.cuh).
+// d_overflow_scratch: contact_overflow_scratch_bytes() of device memory for the EPA overflow tier (epa_big.cuh);
+// d_queue: contact_queue_bytes(n) for the GJK -> EPA hit queue of the thread-per-pair path.
 size_t contact_overflow_scratch_bytes();
+size_t contact_queue_bytes(uint32_t n);
 int launch_contact(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs, uint32_t n, const BinScratch* B,
                    bool run_thread, bool run_warp, const SettingsDev& cfg, int strategy, void* d_overflow_scratch,
-                   float4* d_contacts, uint8_t* d_status);
+                   void* d_queue, float4* d_contacts, uint8_t* d_status);
 int launch_distance(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs, uint32_t n, const BinScratch* B,
                     bool run_thread, bool run_warp, const SettingsDev& cfg, float* d_ref, float* d_geo, uint8_t* d_status);
 int launch_toi(cudaStream_t st, const ShapeSetDev& S0, const ShapeSetDev& S1, const uint2* d_pairs, uint32_t n,

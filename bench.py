@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""bench.py — the hot path of bam3d on B200: batched GJK+EPA contact generation (pairs/s).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c1|c2|c3|toi]
+
+A step is one pass of the narrow phase over one batch of synthetic pairs:
+  c2 (default, BASELINE.json configs[1]): GJK3+EPA3 Contact (FullResolution) on 2^20 mixed Sphere/Cuboid/Cylinder
+     pairs per GPU; c1: GJK intersect on 2^20 Cuboid-Cuboid pairs; c3: GJK+EPA on 2^20 ConvexPolyhedron pairs
+     (64-256 vertices); toi: time of impact on 2^20 mixed pairs.
+`value`  = pairs/s over all ranks with everything resident in HBM (device-pointer C-ABI entry points, CUDA events
+           on the library's stream, max over ranks).
+`e2e`    = the same through the host-buffer C-ABI call a user of the crate would make each frame: pinned host
+           transforms + pair list in, contacts + status out, copies inside the timed region.
+`roofline` = algorithmic HBM bytes of the dominant kernel / its event-timed duration vs MEASURED_PEAKS.json.
+`cpu_baseline` = the CPU oracle (strict-f32 C++ restatement of the reference; the Rust crate cannot be built in this
+           image) on all host cores, same workload. `--impl reference` times only that.
+Multi-GPU (torchrun, one rank per GPU): pairs shard contiguously (weak scaling: 2^20 pairs per GPU); every rank
+compacts its hits and the compacted Contact40 records are all-gathered over NCCL each step.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALGO_BYTES = {  # algorithmic HBM bytes per pair
+    "c1": 129.0,   # 2 x (48 B affine + 16 B params) + 1 B status
+    "c2": 148.0,   # 128 B in + 40 B contact x ~0.5 hit rate
+    "c3": 124.0,   # 2 x 48 B + 2 x 4 B mesh id + 40 B x hit rate (vertex reads are L2 traffic)
+    "toi": 264.0,  # 4 x 48 + 2 x 16 + 40 B out
+}
+WORKLOAD_DESC = {
+    "c1": "C1: GJK intersect, 2^20 random Cuboid-Cuboid pairs per GPU (f32, random transforms, offset U[-2,2]^3)",
+    "c2": "C2: GJK+EPA Contact (FullResolution), 2^20 mixed Sphere/Cuboid/Cylinder pairs per GPU (offset U[-1.5,1.5]^3)",
+    "c3": "C3: GJK+EPA Contact, 2^20 ConvexPolyhedron pairs per GPU (4096-mesh library, 64-256 vertices, warp-cooperative support)",
+    "toi": "TOI: GJK time of impact, 2^20 mixed Sphere/Cuboid/Cylinder pairs per GPU (end = start + U[-3,3]^3)",
+}
+METRIC = {"c1": "gjk_intersect_pairs_per_sec", "c2": "gjk_epa_contact_pairs_per_sec", "c3": "gjk_epa_contact_pairs_per_sec",
+          "toi": "gjk_toi_pairs_per_sec"}
+
+
+def make_scene(workload, n, rank):
+    from bam3d_b200 import scenes
+    start = rank * n  # every rank generates exactly its own slice of the global scene
+    if workload == "c1":
+        return scenes.cuboid_pairs(n, s=2.0, start=start)
+    if workload in ("c2", "toi"):
+        sc = scenes.mixed_pairs(n, s=1.5 if workload == "c2" else 4.0, start=start)
+        if workload == "toi":
+            sc["xform_end"] = scenes.end_transforms(sc, start=2 * start)
+        return sc
+    if workload == "c3":
+        return scenes.polyhedron_pairs(n, n_meshes=4096, s=2.0, start=start)
+    raise SystemExit(f"unknown workload {workload}")
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle on all host cores (the reference crate itself cannot be built here: no cargo / rustc)
+# ---------------------------------------------------------------------------------------------------------
+def oracle_run(workload, scene, nthreads):
+    from tests.oracle_ffi import Oracle
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
+    orc = Oracle()
+
+    def once():
+        if workload == "c1":
+            orc.intersect(scene, nthreads=nthreads)
+        elif workload == "toi":
+            orc.toi(scene, scene["xform_end"], nthreads=nthreads)
+        else:
+            orc.contact(scene, strategy=0, nthreads=nthreads)
+    return once
+
+
+def cpu_sample(scene, workload, n_sample):
+    sc = dict(scene)
+    sc["pairs"] = scene["pairs"][:n_sample]
+    return sc
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    n = args.pairs
+    cores = os.cpu_count() or 1
+    scene = make_scene(args.workload, n, 0)
+    n_sample = min(n, args.cpu_pairs)
+    once = oracle_run(args.workload, cpu_sample(scene, args.workload, n_sample), cores)
+    for _ in range(args.warmup):
+        once()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        once()
+    dt = time.perf_counter() - t0
+    value = n_sample * args.steps / dt
+    unit = "pairs/s"
+    line = {
+        "impl": "reference", "metric": METRIC[args.workload], "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD_DESC[args.workload], "pairs_per_step": n_sample,
+                   "note": "reference crate (Rust) cannot be built in this image; this arm times the strict-f32 C++ restatement of it"},
+        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port",
+                         "sample": f"{n_sample} pairs of the workload per step, std::thread static partition over {cores} threads"},
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ---------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for k, nme in enumerate(names):
+                if f[2 + k].lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ---------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; bam3d_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    import bam3d_b200 as b3
+    from bam3d_b200 import build
+    build.build()
+
+    wl, n = args.workload, args.pairs
+    scene = make_scene(wl, n, rank)
+    ctx = b3.Context(local_rank)
+    gjk = b3.GJK.new(ctx)
+    ext = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    meshes = b3.MeshLibrary(ctx, scene["mesh_verts"], scene["mesh_offsets"]) if scene.get("mesh_verts") is not None else None
+    shapes = b3.ShapeSet(ctx, scene["kind"], scene["params"], scene["xform"], scene.get("mesh_id"), meshes)
+    shapes_end = b3.ShapeSet(ctx, scene["kind"], scene["params"], scene["xform_end"], scene.get("mesh_id"), meshes) if wl == "toi" else None
+
+    # resident buffers (torch owns the memory; the library gets raw device pointers)
+    d_pairs = torch.from_numpy(scene["pairs"].astype(np.int32).reshape(-1)).to(dev)
+    d_status = torch.empty(n, dtype=torch.uint8, device=dev)
+    d_contacts = torch.empty(n * 8, dtype=torch.float32, device=dev)
+    d_compact = torch.empty(n * 10, dtype=torch.int32, device=dev)  # Contact40 records
+    d_count = torch.zeros(1, dtype=torch.int64, device=dev)
+    gathered = torch.empty(world * n * 10, dtype=torch.int32, device=dev) if world > 1 else None
+    counts = torch.zeros(world, dtype=torch.int64, device=dev) if world > 1 else None
+    p = lambda t: C.c_void_p(t.data_ptr())
+
+    def step_resident():
+        if wl == "c1":
+            gjk.intersect_dev(shapes, p(d_pairs), n, p(d_status))
+            return
+        if wl == "toi":
+            gjk.intersection_time_of_impact_dev(shapes, shapes_end, p(d_pairs), n, p(d_contacts), p(d_status))
+        else:
+            gjk.intersection_dev(b3.CollisionStrategy.FullResolution, shapes, p(d_pairs), n, p(d_contacts), p(d_status))
+        if world > 1:
+            # compact hits, then all-gather the compacted Contact40 records over NCCL (variable length: counts first)
+            gjk.compact_contacts_dev(p(d_contacts), p(d_status), n, rank * n, p(d_compact), n, p(d_count))
+            with torch.cuda.stream(ext):
+                dist.all_gather_into_tensor(counts, d_count)
+                m = int(counts.max().item())
+                dist.all_gather_into_tensor(gathered[: world * m * 10], d_compact[: m * 10])
+
+    def sync_all():
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- resident throughput ------------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        step_resident()
+    sync_all()
+    ctx.set_option("timing", 1)
+    ctx.read_timing()
+    launches0 = ctx.launch_count
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(ext)
+    for _ in range(args.steps):
+        step_resident()
+    ev1.record(ext)
+    sync_all()
+    ms = ev0.elapsed_time(ev1)
+    kernel_ms, kernel_calls = ctx.read_timing()
+    ctx.set_option("timing", 0)
+    launches = ctx.launch_count - launches0
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * n * args.steps / (ms_max * 1e-3)
+
+    # ---- end to end through the host-buffer C ABI ----------------------------------------------------------
+    # per step: pinned host transforms (n_shapes x 64 B) + pair list (n x 8 B) in; status (+ contacts) out
+    n_shapes = len(scene["kind"])
+    h_xform = torch.from_numpy(scene["xform"]).pin_memory()
+    h_pairs = torch.from_numpy(scene["pairs"].astype(np.int32)).pin_memory()
+    h_status = torch.empty(n, dtype=torch.uint8).pin_memory()
+    h_contacts = torch.empty((n, 8), dtype=torch.float32).pin_memory()
+    h_f0 = torch.empty(n, dtype=torch.float32).pin_memory()
+    hp = lambda t: C.c_void_p(t.data_ptr())
+    lib, h = ctx._lib, ctx.handle
+
+    def step_e2e():
+        ctx.check(lib.bam3d_shapes_set_transforms(h, shapes.handle, hp(h_xform)))
+        if wl == "c1":
+            ctx.check(lib.bam3d_gjk_intersect(h, shapes.handle, hp(h_pairs), n, C.byref(gjk.settings), hp(h_status)))
+        elif wl == "toi":
+            ctx.check(lib.bam3d_gjk_time_of_impact(h, shapes.handle, shapes_end.handle, hp(h_pairs), n, C.byref(gjk.settings), hp(h_contacts), hp(h_status)))
+        else:
+            ctx.check(lib.bam3d_gjk_contact(h, shapes.handle, hp(h_pairs), n, C.byref(gjk.settings), 0, hp(h_contacts), hp(h_status)))
+
+    h2d = n_shapes * 64 + n * 8
+    d2h = n * 1 + (0 if wl == "c1" else n * 32)
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(3):
+        step_e2e()
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e()  # synchronous on return (results are in host memory)
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * n * e2e_steps / float(t.item())
+    hit_rate = float((h_status == 0).float().mean().item()) if wl != "c1" else float((h_status == 0).float().mean().item())
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        per_launch_ms = kernel_ms / max(1, kernel_calls)
+        achieved = ALGO_BYTES[wl] * n / (per_launch_ms * 1e-3) / 1e9
+        cores = os.cpu_count() or 1
+        n_sample = min(n, args.cpu_pairs)
+        once = oracle_run(wl, cpu_sample(scene, wl, n_sample), cores)
+        once()
+        best = 1e30
+        for _ in range(3):
+            t0 = time.perf_counter()
+            once()
+            best = min(best, time.perf_counter() - t0)
+        line = {
+            "metric": METRIC[wl], "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD_DESC[wl], "pairs_per_gpu": n, "shapes_per_gpu": n_shapes, "hit_rate": hit_rate,
+                       "l2": "inputs larger than L2 (shape records 96 B x 2 per pair + pairs + outputs > 126 MB); no flush",
+                       "multi_gpu": "contiguous pair slices, per-rank compaction, NCCL all-gather of Contact40 records each step" if world > 1 else "single GPU"},
+            "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                    "path": "bam3d_shapes_set_transforms + host-buffer bam3d_gjk_* call, pinned host memory"},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "kernel": {"c1": "gjk_intersect_kernel<false>", "c2": "gjk_contact_kernel<false>", "c3": "gjk_contact_kernel<true>",
+                                    "toi": "gjk_toi_kernel<false>"}[wl],
+                         "kernel_ms_per_launch": per_launch_ms, "algorithmic_bytes_per_pair": ALGO_BYTES[wl], "peak_source": peak_src,
+                         "note": "plain-FP32 SIMT, compute/latency bound: see profiles/ for FP32-pipe and branch efficiency"},
+            "cpu_baseline": {"value": n_sample / best, "unit": "pairs/s", "cores": cores, "kind": "port",
+                             "sample": f"first {n_sample} pairs of rank 0's batch, best of 3, std::thread static partition"},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(ALGO_BYTES))
+    ap.add_argument("--pairs", type=int, default=1 << 20, help="pairs per GPU per step")
+    ap.add_argument("--cpu-pairs", type=int, default=1 << 20, help="pairs in the CPU sample")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

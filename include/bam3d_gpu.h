@@ -91,8 +91,11 @@ const char* bam3d_last_error(const bam3d_ctx* ctx);
 int32_t bam3d_ctx_synchronize(bam3d_ctx* ctx);
 void* bam3d_ctx_stream(bam3d_ctx* ctx); /* the ctx's cudaStream_t */
 void bam3d_default_settings(bam3d_gjk_settings* out); /* GJK::new() (gjk/mod.rs:34-42) */
-/* tuning switches; "binning" (default 1): sort pairs by (kindL, kindR) before the thread-per-pair kernels */
+/* switches: "binning" (default 1) sorts pairs by (kindL, kindR) before the thread-per-pair kernels; "timing"
+ * (default 0) brackets the main kernel(s) of every narrow-phase / broad-phase call with CUDA events */
 int32_t bam3d_ctx_set_option(bam3d_ctx* ctx, const char* name, int32_t value);
+/* synchronise, then return and reset the summed device time (ms) and number of bracketed calls ("timing" = 1) */
+int32_t bam3d_ctx_read_timing(bam3d_ctx* ctx, double* out_total_ms, uint64_t* out_count);
 /* page-locked host memory so that the host-buffer entry points copy at full PCIe / C2C rate */
 int32_t bam3d_host_alloc(bam3d_ctx* ctx, uint64_t bytes, void** out_ptr);
 void bam3d_host_free(bam3d_ctx* ctx, void* ptr);

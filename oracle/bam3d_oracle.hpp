@@ -320,9 +320,9 @@ inline void remove_or_add_edge(std::vector<std::pair<uint32_t, uint32_t>>& edges
 // rim supports are coplanar, visibility becomes rounding noise) its face list grows multiplicatively per
 // iteration — the reference itself then effectively hangs / exhausts memory. The oracle therefore stops a pair
 // whose polytope would exceed these capacities and reports Status::Capacity; the GPU path uses the same numbers
-// (EPA_BIG_FCAP / EPA_BIG_ECAP in bam3d_b200/csrc/epa.cuh) for its overflow tier, so both report the same pairs.
-constexpr size_t EPA_FACE_LIMIT = 4096;
-constexpr size_t EPA_EDGE_LIMIT = 6144;
+// (EPA_BIG_FCAP in bam3d_b200/csrc/epa_big.cuh) for its overflow tier, so both report the same pairs.
+constexpr size_t EPA_FACE_LIMIT = 1024;                 // ~5x the 202 faces a valid 103-vertex polytope can have
+constexpr size_t EPA_EDGE_LIMIT = 3 * EPA_FACE_LIMIT;    // 3 edges per removed face: can never trigger first
 
 struct Polytope {  // epa3d.rs:97-150
     std::vector<SupportPoint>& vertices;
@@ -408,7 +408,12 @@ struct EPA3 {  // epa3d.rs:9-67; constants epa/mod.rs:12-13
                 return true;
             }
             polytope.add(p);
-            if (polytope.overflow) { if (st) *st = Status::Capacity; return false; }
+            if (polytope.overflow) {
+                if (st) *st = Status::Capacity;
+                if (cnt) cnt->max_faces = (uint32_t)EPA_FACE_LIMIT + 1;
+                return false;
+            }
+            if (cnt && polytope.faces.size() > cnt->max_faces) cnt->max_faces = (uint32_t)polytope.faces.size();
             i += 1;
         }
     }

@@ -115,6 +115,22 @@ void orc_gjk_contact_batch(const uint8_t* kind, const float* params, const float
     merge(counters, cs);
 }
 
+// Per-pair EPA statistics (polytope face high-water, EPA iterations) for sizing the device tiers; FullResolution.
+void orc_gjk_contact_stats_batch(const uint8_t* kind, const float* params, const float* xform, const uint32_t* mesh_id,
+                                 const float* mesh_verts, const uint32_t* mesh_offsets, const uint32_t* pairs, uint64_t n,
+                                 uint32_t* out_max_faces, uint32_t* out_epa_iterations, uint8_t* out_status, int nthreads) {
+    ShapeTable T{kind, params, xform, mesh_id, mesh_verts, mesh_offsets};
+    GJK gjk;
+    parallel_for(n, nthreads, [&](uint64_t b, uint64_t e, int) {
+        for (uint64_t i = b; i < e; ++i) {
+            uint32_t l = pairs[2 * i], r = pairs[2 * i + 1];
+            Contact c; Status st; Counters cnt;
+            gjk.intersection(CollisionStrategy::FullResolution, T.shape(l), T.mat(l), T.shape(r), T.mat(r), c, &st, &cnt);
+            out_max_faces[i] = cnt.max_faces; out_epa_iterations[i] = (uint32_t)cnt.epa_iterations; out_status[i] = (uint8_t)st;
+        }
+    });
+}
+
 // GJK::distance over a batch (gjk/mod.rs:232-280). out_some[i]=1 for Some; out_ref = dp-d0 (what the reference
 // returns), out_geo = sqrt(d.d).
 void orc_gjk_distance_batch(const uint8_t* kind, const float* params, const float* xform, const uint32_t* mesh_id,
