@@ -68,9 +68,13 @@ B3_DEV bool remove_or_add_edge(uint16_t* ed, int& ne, int ecap, uint32_t a, uint
 
 // Polytope::new (epa3d.rs:103-109) + Face::new (:172-179) from the 4-point GJK simplex (with sup_a).
 template <bool WARP>
-B3_DEV void epa_init(const Simplex<true>& s, const PolytopeStore& P, int& nv, int& nf, uint32_t& it) {
+B3_DEV void epa_init(const Simplex<true>& s, const PolytopeStore& P, int& nv, int& nf, uint32_t& it, V3& vmax) {
+    vmax = v3(0.f, 0.f, 0.f);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) { st3(P.vv, k, s.v[k]); st3(P.va, k, s.a[k]); }
+    for (int k = 0; k < 4; ++k) {
+        st3(P.vv, k, s.v[k]); st3(P.va, k, s.a[k]);
+        vmax = v3(fmaxf(vmax.x, fabsf(s.v[k].x)), fmaxf(vmax.y, fabsf(s.v[k].y)), fmaxf(vmax.z, fabsf(s.v[k].z)));
+    }
     if (WARP) __syncwarp();
     make_face(P, 0, 3, 2, 1);
     make_face(P, 1, 3, 1, 0);
@@ -86,10 +90,11 @@ constexpr uint8_t EPA_CONTINUE = 0xFF;
 // Returns EPA_CONTINUE, or a final Status (ST_OK with `out` filled, ST_CAPACITY).
 template <bool WARP>
 B3_DEV uint8_t epa_iterate(const Shape& L, const Shape& R, float tolerance, uint32_t max_iterations, const PolytopeStore& P,
-                           int& nv, int& nf, uint32_t& it, ContactOut& out) {
+                           int& nv, int& nf, uint32_t& it, V3& vmax, ContactOut& out) {
     // closest_face_to_origin (epa3d.rs:111-119): strict <, first minimum wins
     int best = 0;
     float best_d = P.fn[0].w;
+#pragma unroll 4
     for (int k = 1; k < nf; ++k) {
         float dk = P.fn[k].w;
         if (dk < best_d) { best_d = dk; best = k; }
@@ -111,35 +116,75 @@ B3_DEV uint8_t epa_iterate(const Shape& L, const Shape& R, float tolerance, uint
         return ST_OK;
     }
 
-    // Polytope::add (epa3d.rs:121-149)
+    // Polytope::add (epa3d.rs:121-149), in three passes so that the lanes of a thread-per-pair warp stay together:
+    //  A. visibility flag of every face (uniform loop body);
+    //  B. the order-dependent walk: visit the flagged faces exactly as the reference's `while i < len` loop with
+    //     swap_remove does (the face moved into slot k is examined next), feeding the horizon edge list;
+    //  C. the new faces.
+    // Pass A needs dot(n, p - v0) > 0 with v0 = the face's first vertex (a divergent gather). face.distance is
+    // fl(dot(n, v0)) (Face::new_impl), so a2 = fl(dot(n, p)) - distance equals the reference's value up to
+    // 8.02 u S, S = sum |n_i| (|p_i| + |v0_i|), u = 2^-24 (standard dot-product error bounds). Whenever
+    // |a2| > 2^-20 S (S bounded with the running max |vertex coordinate|) the sign is decided without the gather;
+    // otherwise — and for any NaN/inf — the reference's expression is evaluated as written. Exact either way.
+    // The flags live in a bitmask (32 faces per word, built in a register chunk by chunk) so that pass A is a pure
+    // load + arithmetic loop the compiler can software-pipeline, and pass B finds the next flagged face with ffs.
+    uint32_t vm[EPA_FCAP / 32];
+    const int nchunks = (nf + 31) >> 5;
+    for (int c = 0; c < nchunks; ++c) {
+        uint32_t m = 0;
+        const int k0 = c << 5;
+        const int k1 = min(nf, k0 + 32);
+#pragma unroll 4
+        for (int k = k0; k < k1; ++k) {
+            float4 f = P.fn[k];
+            V3 fnv = v3(f.x, f.y, f.z);
+            float a2 = dot(fnv, pv) - f.w;
+            float S = (fabsf(f.x) * (fabsf(pv.x) + vmax.x) + fabsf(f.y) * (fabsf(pv.y) + vmax.y)) + fabsf(f.z) * (fabsf(pv.z) + vmax.z);
+            bool vis;
+            if (fabsf(a2) > S * 9.5367431640625e-07f + 1e-30f) {
+                vis = a2 > 0.f;
+            } else {
+                V3 v0 = ld3(P.vv, P.fi[k] & 0xFF);
+                vis = dot(fnv, pv - v0) > 0.f;
+            }
+            m |= (vis ? 1u : 0u) << (k - k0);
+        }
+        vm[c] = m;
+    }
     int ne = 0;
-    int k = 0;
     bool ok = true;
-    while (k < nf) {
-        float4 f = P.fn[k];
-        uint32_t idx = P.fi[k];
-        V3 v0 = ld3(P.vv, idx & 0xFF);
-        float dt = dot(v3(f.x, f.y, f.z), pv - v0);
-        if (dt > 0.f) {
-            --nf;                         // swap_remove(k)
+    for (int k = 0;;) {
+        // next flagged slot >= k (bits at or beyond nf are always clear)
+        int c = k >> 5;
+        uint32_t w = (c < nchunks) ? (vm[c] >> (k & 31)) : 0u;
+        while (w == 0u && ++c < nchunks) { k = c << 5; w = vm[c]; }
+        if (w == 0u) break;
+        k += __ffs(w) - 1;
+        const uint32_t idx = P.fi[k];
+        --nf;                             // swap_remove(k): the last face (with its flag) moves into slot k
+        const uint32_t last_bit = (vm[nf >> 5] >> (nf & 31)) & 1u;
+        vm[nf >> 5] &= ~(1u << (nf & 31));
+        if (k != nf) {
             float4 lf = P.fn[nf];
             uint32_t li = P.fi[nf];
             if (WARP) __syncwarp();
             P.fn[k] = lf;
             P.fi[k] = li;
-            uint32_t i0 = idx & 0xFF, i1 = (idx >> 8) & 0xFF, i2 = (idx >> 16) & 0xFF;
-            ok = ok && remove_or_add_edge(P.ed, ne, P.ecap, i0, i1);
-            ok = ok && remove_or_add_edge(P.ed, ne, P.ecap, i1, i2);
-            ok = ok && remove_or_add_edge(P.ed, ne, P.ecap, i2, i0);
-            if (WARP) __syncwarp();
-        } else {
-            ++k;
+            vm[k >> 5] = (vm[k >> 5] & ~(1u << (k & 31))) | (last_bit << (k & 31));
         }
+        uint32_t i0 = idx & 0xFF, i1 = (idx >> 8) & 0xFF, i2 = (idx >> 16) & 0xFF;
+        ok = ok && remove_or_add_edge(P.ed, ne, P.ecap, i0, i1);
+        ok = ok && remove_or_add_edge(P.ed, ne, P.ecap, i1, i2);
+        ok = ok && remove_or_add_edge(P.ed, ne, P.ecap, i2, i0);
+        if (WARP) __syncwarp();
     }
     if (!ok || nv >= EPA_VCAP || nf + ne > P.fcap) return ST_CAPACITY;
     const int n = nv;
     st3(P.vv, n, pv);
     st3(P.va, n, pa);
+    // running max |coordinate| over the polytope's vertices; a NaN coordinate poisons it so the filter never fires
+    vmax = v3(pv.x != pv.x ? pv.x : fmaxf(vmax.x, fabsf(pv.x)), pv.y != pv.y ? pv.y : fmaxf(vmax.y, fabsf(pv.y)),
+              pv.z != pv.z ? pv.z : fmaxf(vmax.z, fabsf(pv.z)));
     ++nv;
     if (WARP) __syncwarp();
     for (int e = 0; e < ne; ++e) {
@@ -158,9 +203,10 @@ B3_DEV uint8_t epa_process(const Shape& L, const Shape& R, const Simplex<true>& 
                            const PolytopeStore& P, ContactOut& out) {
     int nv, nf;
     uint32_t it;
-    epa_init<WARP>(s, P, nv, nf, it);
+    V3 vmax;
+    epa_init<WARP>(s, P, nv, nf, it, vmax);
     for (;;) {
-        uint8_t st = epa_iterate<WARP>(L, R, tolerance, max_iterations, P, nv, nf, it, out);
+        uint8_t st = epa_iterate<WARP>(L, R, tolerance, max_iterations, P, nv, nf, it, vmax, out);
         if (st != EPA_CONTINUE) return st;
     }
 }

@@ -10,6 +10,7 @@
 //
 // Plain FP32 SIMT: there is no dense contraction anywhere in this path, so tensor cores / TMEM are not used.
 // Compiled with -fmad=false (see vecmath.cuh).
+#include <cstdlib>
 #include "narrow.h"
 #include "gjk.cuh"
 #include "epa_big.cuh"
@@ -358,6 +359,7 @@ __global__ void __launch_bounds__(TPB) epa_refill_kernel(ShapeSetDev S, const ui
     Shape L, R;
     int nv = 0, nf = 0;
     uint32_t it = 0, p = 0;
+    V3 vmax = v3(0.f, 0.f, 0.f);
     for (;;) {
         // refill idle lanes from the queue (one atomic per warp per trip)
         const uint32_t need = __ballot_sync(0xFFFFFFFFu, !active && !exhausted);
@@ -381,7 +383,7 @@ __global__ void __launch_bounds__(TPB) epa_refill_kernel(ShapeSetDev S, const ui
                     uint2 pr = __ldg(pairs + p);
                     load_pair_shape(L, S, pr.x);
                     load_pair_shape(R, S, pr.y);
-                    epa_init<false>(s, P, nv, nf, it);
+                    epa_init<false>(s, P, nv, nf, it, vmax);
                     active = true;
                 } else {
                     exhausted = true;
@@ -391,7 +393,7 @@ __global__ void __launch_bounds__(TPB) epa_refill_kernel(ShapeSetDev S, const ui
         if (!__any_sync(0xFFFFFFFFu, active)) break;
         if (active) {
             ContactOut c;
-            uint8_t st = epa_iterate<false>(L, R, cfg.epa_tolerance, cfg.max_iterations, P, nv, nf, it, c);
+            uint8_t st = epa_iterate<false>(L, R, cfg.epa_tolerance, cfg.max_iterations, P, nv, nf, it, vmax, c);
             if (st != EPA_CONTINUE) {
                 if (st != ST_OK) { c.normal = v3(0.f, 0.f, 0.f); c.depth = 0.f; c.point = v3(0.f, 0.f, 0.f); }
                 contacts[2 * (size_t)p] = make_float4(c.normal.x, c.normal.y, c.normal.z, c.depth);
@@ -593,6 +595,7 @@ static int epa_refill_grid() {
     if (!blocks) {
         int per_sm = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, epa_refill_kernel, TPB, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
+        if (const char* e = getenv("BAM3D_EPA_BLOCKS_PER_SM")) { int v = atoi(e); if (v >= 1 && v < per_sm) per_sm = v; }
         blocks = per_sm * NUM_SMS;
     }
     return blocks;
