@@ -59,6 +59,20 @@ SIGNATURES = {
     "bam3d_gjk_time_of_impact_dev": (_i32, [_vp, _vp, _vp, _vp, _u64, _PS, _vp, _vp]),
     "bam3d_compact_contacts_dev": (_i32, [_vp, _vp, _vp, _u64, _u64, _vp, _u64, _vp]),
     "bam3d_ctx_launch_count": (_u64, [_vp]),
+    "bam3d_sap_find_pairs": (_i32, [_vp, _vp, _u64, C.POINTER(_i32), _vp, _vp, _u64, C.POINTER(_u64)]),
+    "bam3d_sap_find_pairs_dev": (_i32, [_vp, _vp, _u64, C.POINTER(_i32), _vp, _vp, _u64, C.POINTER(_u64)]),
+    "bam3d_shapes_world_aabbs": (_i32, [_vp, _vp, _vp]),
+    "bam3d_shapes_world_aabbs_dev": (_i32, [_vp, _vp, _vp]),
+    "bam3d_bvh_build": (_i32, [_vp, _vp, _u64, C.POINTER(_vp)]),
+    "bam3d_bvh_build_dev": (_i32, [_vp, _vp, _u64, C.POINTER(_vp)]),
+    "bam3d_bvh_free": (None, [_vp, _vp]),
+    "bam3d_bvh_count": (_u32, [_vp]),
+    "bam3d_bvh_query_aabb": (_i32, [_vp, _vp, _vp, _u64, _vp, _vp, _u64, C.POINTER(_u64)]),
+    "bam3d_bvh_query_ray": (_i32, [_vp, _vp, _vp, _u64, _vp, _vp, _vp, _u64, C.POINTER(_u64)]),
+    "bam3d_bvh_query_frustum": (_i32, [_vp, _vp, _vp, _u64, _vp, _vp, _vp, _u64, C.POINTER(_u64)]),
+    "bam3d_bvh_query_ray_closest": (_i32, [_vp, _vp, _vp, _u64, _vp, _vp]),
+    "bam3d_bvh_find_collider_pairs": (_i32, [_vp, _vp, _vp, _vp, _u64, C.POINTER(_u64)]),
+    "bam3d_frustum_from_mat4": (_i32, [_vp, _vp]),
 }
 
 _lib = None

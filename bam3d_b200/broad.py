@@ -1,0 +1,220 @@
+"""Host-side mirror of bam3d's broad-phase API over the CUDA C ABI.
+
+  SweepAndPrune3            src/algorithm/broad_phase/sweep_prune.rs:27-128 (new, with_sweep_axis, get_sweep_axis,
+                            find_collider_pairs)
+  Aabb3, Ray, Frustum       src/volume/aabb/aabb3.rs, src/ray.rs, src/frustum.rs (plain value holders here)
+  DynamicBoundingVolumeTree src/dbvt/mod.rs:239-515 — the query side (query / query_for_indices with DiscreteVisitor,
+                            ContinuousVisitor, FrustumVisitor; query_ray, query_ray_closest of dbvt/util.rs) on a static
+                            device BVH; insert() only collects values, do_refit()/tick() (re)build the device tree.
+  DbvtBroadPhase            src/algorithm/broad_phase/dbvt.rs:14-63
+Aabb3 values are rows of 6 f32 (min.xyz, max.xyz).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _ffi
+from .api import _ptr, default_context
+
+
+def _retry_capacity(call, guess):
+    """Two-call pattern of the C ABI: on BAM3D_ERR_CAPACITY the required size is reported; allocate and call again."""
+    cap = max(int(guess), 1)
+    while True:
+        rc, need, result = call(cap)
+        if rc == _ffi.OK:
+            return result
+        if rc == _ffi.ERR_CAPACITY and need > cap:
+            cap = int(need)
+            continue
+        return rc
+
+
+class SweepAndPrune3:
+    """Sweep and prune broad phase (sweep_prune.rs:27-30); keeps `sweep_axis` across calls like the reference."""
+
+    def __init__(self, ctx=None, sweep_axis=0):
+        self.ctx = ctx if ctx is not None else default_context()
+        self.sweep_axis = int(sweep_axis)
+
+    @classmethod
+    def new(cls, ctx=None):  # sweep_prune.rs:37-39
+        return cls(ctx, 0)
+
+    @classmethod
+    def with_sweep_axis(cls, sweep_axis, ctx=None):  # sweep_prune.rs:42-47
+        return cls(ctx, sweep_axis)
+
+    def get_sweep_axis(self):  # sweep_prune.rs:50-52
+        return self.sweep_axis
+
+    def find_collider_pairs(self, aabbs, capacity=None):
+        """-> (pairs[m, 2], perm[n]). The reference re-sorts `shapes` in place and returns indices into the sorted
+        slice (sweep_prune.rs:65-69): pairs index the SORTED order; perm[k] is the original index of sorted slot k, so
+        `shapes[:] = shapes[perm]` reproduces the reference's side effect."""
+        aabbs = np.ascontiguousarray(aabbs, dtype=np.float32).reshape(-1, 6)
+        n = len(aabbs)
+        perm = np.empty(n, dtype=np.uint32)
+        ctx, lib = self.ctx, self.ctx._lib
+
+        def call(cap):
+            pairs = np.empty((cap, 2), dtype=np.uint32)
+            axis = C.c_int32(self.sweep_axis)
+            cnt = C.c_uint64(0)
+            rc = lib.bam3d_sap_find_pairs(ctx.handle, _ptr(aabbs), n, C.byref(axis), _ptr(perm), _ptr(pairs), cap, C.byref(cnt))
+            return rc, cnt.value, (pairs, int(cnt.value), int(axis.value))
+
+        res = _retry_capacity(call, capacity if capacity is not None else 8 * n + 1024)
+        if isinstance(res, int):
+            ctx.check(res)
+        pairs, cnt, axis = res
+        self.sweep_axis = axis
+        return pairs[:cnt], perm
+
+
+def frustum_from_mat4(mat4_cols):
+    """Frustum::from_mat4 (frustum.rs:46-75) -> 6 planes x (n.xyz, d): left, right, bottom, top, near, far; None if a
+    plane degenerates."""
+    m = np.ascontiguousarray(mat4_cols, dtype=np.float32).reshape(16)
+    out = np.empty(24, dtype=np.float32)
+    rc = _ffi.lib().bam3d_frustum_from_mat4(_ptr(m), _ptr(out))
+    return out.reshape(6, 4) if rc == _ffi.OK else None
+
+
+class Bvh:
+    """Device BVH over Aabb3 values (bam3d_bvh)."""
+
+    def __init__(self, ctx, aabbs):
+        self.ctx = ctx
+        self.aabbs = np.ascontiguousarray(aabbs, dtype=np.float32).reshape(-1, 6)
+        h = C.c_void_p()
+        ctx.check(ctx._lib.bam3d_bvh_build(ctx.handle, _ptr(self.aabbs), len(self.aabbs), C.byref(h)))
+        self.handle = h
+        self.n = len(self.aabbs)
+
+    def close(self):
+        if self.handle:
+            self.ctx._lib.bam3d_bvh_free(self.ctx.handle, self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _var_query(self, fn, queries, qwidth, payload):
+        ctx = self.ctx
+        q = np.ascontiguousarray(queries, dtype=np.float32).reshape(-1, qwidth)
+        nq = len(q)
+        offsets = np.zeros(nq + 1, dtype=np.uint64)
+
+        def call(cap):
+            values = np.empty(cap, dtype=np.uint32)
+            total = C.c_uint64(0)
+            if payload is None:
+                rc = fn(ctx.handle, self.handle, _ptr(q), nq, _ptr(offsets), _ptr(values), cap, C.byref(total))
+                pay = None
+            else:
+                pay = np.empty((cap,) + payload[0], dtype=payload[1])
+                rc = fn(ctx.handle, self.handle, _ptr(q), nq, _ptr(offsets), _ptr(values), _ptr(pay), cap, C.byref(total))
+            return rc, total.value, (values, pay, int(total.value))
+
+        res = _retry_capacity(call, 16 * nq + 1024)
+        if isinstance(res, int):
+            ctx.check(res)
+        values, pay, total = res
+        return offsets, values[:total], (None if pay is None else pay[:total])
+
+    def query_aabb(self, queries):
+        """DiscreteVisitor per query box -> (offsets[nq+1], values)."""
+        off, vals, _ = self._var_query(self.ctx._lib.bam3d_bvh_query_aabb, queries, 6, None)
+        return off, vals
+
+    def query_ray(self, rays):
+        """query_ray per ray (origin.xyz, direction.xyz) -> (offsets, values, points[total, 3])."""
+        return self._var_query(self.ctx._lib.bam3d_bvh_query_ray, rays, 6, ((3,), np.float32))
+
+    def query_frustum(self, planes):
+        """FrustumVisitor per frustum (6 planes x 4) -> (offsets, values, relation[total])."""
+        return self._var_query(self.ctx._lib.bam3d_bvh_query_frustum, planes, 24, ((), np.uint8))
+
+    def query_ray_closest(self, rays):
+        """query_ray_closest per ray -> (value[nq] (0xFFFFFFFF = None), point_t[nq, 4])."""
+        r = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 6)
+        val = np.empty(len(r), dtype=np.uint32)
+        pt = np.empty((len(r), 4), dtype=np.float32)
+        self.ctx.check(self.ctx._lib.bam3d_bvh_query_ray_closest(self.ctx.handle, self.handle, _ptr(r), len(r), _ptr(val), _ptr(pt)))
+        return val, pt
+
+    def find_collider_pairs(self, dirty):
+        """DbvtBroadPhase::find_collider_pairs -> sorted unique (low, high) pairs."""
+        dirty = np.ascontiguousarray(dirty, dtype=np.uint8)
+        assert len(dirty) == self.n
+        ctx = self.ctx
+
+        def call(cap):
+            pairs = np.empty((cap, 2), dtype=np.uint32)
+            cnt = C.c_uint64(0)
+            rc = ctx._lib.bam3d_bvh_find_collider_pairs(ctx.handle, self.handle, _ptr(dirty), _ptr(pairs), cap, C.byref(cnt))
+            return rc, cnt.value, (pairs, int(cnt.value))
+
+        res = _retry_capacity(call, 8 * self.n + 1024)
+        if isinstance(res, int):
+            ctx.check(res)
+        pairs, cnt = res
+        return pairs[:cnt]
+
+
+class DynamicBoundingVolumeTree:
+    """The query face of dbvt/mod.rs:239-515. insert() appends a value's (bound, fat bound); do_refit() / tick() build
+    the device tree; value indices are insertion order, as in the reference's `values` Vec."""
+
+    def __init__(self, ctx=None):
+        self.ctx = ctx if ctx is not None else default_context()
+        self._bounds = []
+        self._bvh = None
+
+    def insert(self, bound, fat_bound=None):  # dbvt/mod.rs:622 — returns the value index
+        self._bounds.append(np.asarray(bound, dtype=np.float32).reshape(6))
+        self._bvh = None
+        return len(self._bounds) - 1
+
+    def do_refit(self):  # dbvt/mod.rs:837-842
+        if self._bvh is not None:
+            self._bvh.close()
+        self._bvh = Bvh(self.ctx, np.array(self._bounds, dtype=np.float32).reshape(-1, 6))
+
+    tick = do_refit  # dbvt/mod.rs:595-599
+
+    def _tree(self):
+        if self._bvh is None:
+            self.do_refit()
+        return self._bvh
+
+    def query_aabb(self, bound):  # query(&mut DiscreteVisitor::new(&bound))
+        return self._tree().query_aabb([bound])[1]
+
+    def query_ray(self, origin, direction):  # dbvt/util.rs:114-129
+        _, v, p = self._tree().query_ray([list(origin) + list(direction)])
+        return v, p
+
+    def query_ray_closest(self, origin, direction):  # dbvt/util.rs:77-103
+        v, pt = self._tree().query_ray_closest([list(origin) + list(direction)])
+        return None if v[0] == 0xFFFFFFFF else (int(v[0]), pt[0, :3].copy())
+
+    def query_frustum(self, planes):  # query(&mut FrustumVisitor::new(&frustum))
+        _, v, r = self._tree().query_frustum([planes])
+        return v, r
+
+
+class DbvtBroadPhase:  # algorithm/broad_phase/dbvt.rs:14-63
+    def find_collider_pairs(self, tree, dirty):
+        return tree._tree().find_collider_pairs(dirty)
+
+
+def world_aabbs(shapes):
+    """ComputeBound<Aabb3> + Aabb::transform for every shape of a ShapeSet -> n x 6 f32."""
+    out = np.empty((shapes.n, 6), dtype=np.float32)
+    shapes.ctx.check(shapes.ctx._lib.bam3d_shapes_world_aabbs(shapes.ctx.handle, shapes.handle, _ptr(out)))
+    return out

@@ -1,2 +1,662 @@
-// Broad-phase kernels (sweep and prune, BVH queries) — see broad.h.
+// Broad-phase kernels for sm_100a.
+//  * SweepAndPrune3::find_collider_pairs (algorithm/broad_phase/sweep_prune.rs:69-128): 64-bit (min, max) keys on the
+//    sweep axis, stable radix sort, a shared-memory tiled forward sweep with warp-aggregated compaction of the
+//    overlapping pairs, a final sort of the pair list into the reference's emission order, and Variance3 (:166-216).
+//  * A static LBVH that answers the DynamicBoundingVolumeTree queries (dbvt/mod.rs:481-515 with the visitors of
+//    dbvt/visitor.rs and dbvt/util.rs). Query result SETS do not depend on the tree shape (every branch bound
+//    contains its descendants and every visitor is monotone in the bound), and the reference's own tree shape is
+//    randomised (rand::thread_rng, dbvt/mod.rs:901), so the device builds its own tree from the values' real bounds.
+//  * ComputeBound<Aabb3> + Aabb::transform for packed shapes (world AABBs feeding the broad phase).
+// HBM-bound integer/compare work: no tensor cores. Compiled with -fmad=false like the narrow phase.
+#include <cub/cub.cuh>
+
 #include "broad.h"
+#include "narrow.h"
+#include "support.cuh"
+
+namespace b3 {
+
+constexpr int BT = 128;  // threads per block
+constexpr int NSM = 148;
+
+B3_DEV float comp(float4 v, int a) { return a == 0 ? v.x : (a == 1 ? v.y : v.z); }
+
+// order-preserving f32 -> u32 (after canonicalising -0.0 to +0.0: partial_cmp treats them as Equal)
+B3_DEV uint32_t ord_key(float f) {
+    f = f + 0.0f;
+    uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// sweep and prune
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BT) sap_keys_kernel(const float* __restrict__ aabbs, uint32_t n, int axis,
+                                                      unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals) {
+    uint32_t i = blockIdx.x * BT + threadIdx.x;
+    if (i >= n) return;
+    float mn = aabbs[6 * (size_t)i + axis], mx = aabbs[6 * (size_t)i + 3 + axis];
+    // sort_by comparator (sweep_prune.rs:80-90): min on the sweep axis, then max; stable
+    keys[i] = ((unsigned long long)ord_key(mn) << 32) | ord_key(mx);
+    vals[i] = i;
+}
+
+__global__ void __launch_bounds__(BT) sap_gather_kernel(const float* __restrict__ aabbs, const uint32_t* __restrict__ perm, uint32_t n,
+                                                        float4* __restrict__ lo, float4* __restrict__ hi, uint32_t* __restrict__ out_perm) {
+    uint32_t k = blockIdx.x * BT + threadIdx.x;
+    if (k >= n) return;
+    uint32_t src = perm[k];
+    const float* b = aabbs + 6 * (size_t)src;
+    lo[k] = make_float4(b[0], b[1], b[2], 0.f);
+    hi[k] = make_float4(b[3], b[4], b[5], 0.f);
+    if (out_perm) out_perm[k] = src;
+}
+
+// Forward sweep. Block b owns sorted slots i in [128 b, 128 b + 128); it streams the following slots j through shared
+// memory one tile at a time (sweep-axis min, and the second axis' extent as a cheap filter) until the tile starts at
+// or beyond the largest sweep-axis max of the block: with mins sorted, no later box can overlap any of the block's
+// boxes on the sweep axis (Aabb3 overlap is strict: a.max > b.min, volume/aabb/aabb3.rs:237-244). The retain test of
+// the reference's active list (max_i >= min_j, sweep_prune.rs:102-105) is implied by that strict overlap, so the pair
+// set is exactly "all strictly overlapping (i < j)". Survivors of the filter run the full 3-axis test and are
+// appended through one atomic per warp.
+__global__ void __launch_bounds__(BT) sap_sweep_kernel(const float4* __restrict__ lo, const float4* __restrict__ hi, uint32_t n, int axis,
+                                                       int key_shift, unsigned long long* __restrict__ pair_keys, unsigned long long capacity,
+                                                       unsigned long long* __restrict__ count) {
+    __shared__ float s_alo[BT], s_blo[BT], s_bhi[BT];
+    __shared__ float s_red[BT / 32];
+    const int a = axis, b = (axis + 1) % 3;
+    const uint32_t i0 = blockIdx.x * BT, i = i0 + threadIdx.x;
+    const bool valid = i < n;
+    float4 li = make_float4(0, 0, 0, 0), hi_i = make_float4(0, 0, 0, 0);
+    if (valid) { li = __ldg(lo + i); hi_i = __ldg(hi + i); }
+    const float amax = valid ? comp(hi_i, a) : -INFINITY;
+    const float bmin = comp(li, b), bmax = comp(hi_i, b);
+    // block-wide max of amax
+    float m = amax;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, off));
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    float block_amax = s_red[0];
+#pragma unroll
+    for (int w = 1; w < BT / 32; ++w) block_amax = fmaxf(block_amax, s_red[w]);
+
+    for (uint32_t j0 = i0 + 1; j0 < n; j0 += BT) {
+        const uint32_t j = j0 + threadIdx.x;
+        if (j < n) {
+            float4 lj = __ldg(lo + j), hj = __ldg(hi + j);
+            s_alo[threadIdx.x] = comp(lj, a); s_blo[threadIdx.x] = comp(lj, b); s_bhi[threadIdx.x] = comp(hj, b);
+        } else {
+            s_alo[threadIdx.x] = INFINITY; s_blo[threadIdx.x] = INFINITY; s_bhi[threadIdx.x] = -INFINITY;
+        }
+        __syncthreads();
+        if (!(s_alo[0] < block_amax)) break;  // uniform: sorted mins, nothing further can overlap
+        if (valid) {
+#pragma unroll 8
+            for (int t = 0; t < BT; ++t) {
+                const uint32_t jj = j0 + t;
+                if (jj > i && s_alo[t] < amax && s_blo[t] < bmax && s_bhi[t] > bmin) {
+                    float4 lj = __ldg(lo + jj), hj = __ldg(hi + jj);
+                    // Discrete<Aabb3> for Aabb3 (aabb3.rs:237-244), self = box i, other = box j
+                    bool hit = hi_i.x > lj.x && li.x < hj.x && hi_i.y > lj.y && li.y < hj.y && hi_i.z > lj.z && li.z < hj.z;
+                    if (hit) {
+                        const uint32_t act = __activemask();
+                        const uint32_t lane = threadIdx.x & 31u;
+                        const uint32_t leader = __ffs(act) - 1;
+                        unsigned long long base = 0;
+                        if (lane == leader) base = atomicAdd(count, (unsigned long long)__popc(act));
+                        base = __shfl_sync(act, base, leader);
+                        const unsigned long long slot = base + __popc(act & ((1u << lane) - 1u));
+                        if (slot < capacity) pair_keys[slot] = ((unsigned long long)jj << key_shift) | i;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// Variance3 (sweep_prune.rs:166-216): c = (min + max) / 2; csum += c; csumsq += c * c, accumulated SEQUENTIALLY in
+// sorted order exactly as the reference's loop does (f32 addition is not associative, and the three axes of a
+// uniform scene are near-ties, so a tree reduction could pick a different axis). One warp: the lanes stage 1024
+// boxes at a time in shared memory, then every lane walks the tile in order (all lanes hold the same sums).
+// variance = csumsq * (csum * csum / n) — a product, not a difference, as in the reference (:203-204).
+__global__ void __launch_bounds__(32) sap_variance_kernel(const float4* __restrict__ lo, const float4* __restrict__ hi, uint32_t n,
+                                                          int* __restrict__ next_axis) {
+    constexpr int TILE = 1024;
+    __shared__ float cx[TILE], cy[TILE], cz[TILE];
+    float sx = 0.f, sy = 0.f, sz = 0.f, qx = 0.f, qy = 0.f, qz = 0.f;
+    for (uint32_t base = 0; base < n; base += TILE) {
+        const uint32_t cnt = min((uint32_t)TILE, n - base);
+        for (uint32_t t = threadIdx.x; t < cnt; t += 32) {
+            float4 l = __ldg(lo + base + t), h = __ldg(hi + base + t);
+            cx[t] = (l.x + h.x) / 2.0f; cy[t] = (l.y + h.y) / 2.0f; cz[t] = (l.z + h.z) / 2.0f;
+        }
+        __syncwarp();
+#pragma unroll 4
+        for (uint32_t t = 0; t < cnt; ++t) {
+            float x = cx[t], y = cy[t], z = cz[t];
+            sx = sx + x; sy = sy + y; sz = sz + z;
+            qx = qx + x * x; qy = qy + y * y; qz = qz + z * z;
+        }
+        __syncwarp();
+    }
+    if (threadIdx.x == 0) {
+        const float fn = (float)n;
+        float vx = qx * (sx * sx / fn), vy = qy * (sy * sy / fn), vz = qz * (sz * sz / fn);
+        int ax = 0; float best = vx;
+        if (vy > best) { ax = 1; best = vy; }
+        if (vz > best) { ax = 2; best = vz; }
+        *next_axis = ax;
+    }
+}
+
+__global__ void __launch_bounds__(BT) unpack_pairs_kernel(const unsigned long long* __restrict__ keys, unsigned long long n, int shift,
+                                                          uint2* __restrict__ pairs, int hi_first) {
+    unsigned long long k = (unsigned long long)blockIdx.x * BT + threadIdx.x;
+    if (k >= n) return;
+    unsigned long long key = keys[k];
+    uint32_t hi = (uint32_t)(key >> shift), lo = (uint32_t)(key & ((1ull << shift) - 1ull));
+    pairs[k] = hi_first ? make_uint2(hi, lo) : make_uint2(lo, hi);
+}
+
+static int bits_for(uint32_t n) { int b = 1; while (b < 32 && (1ull << b) < n) ++b; return b; }
+
+size_t sap_cub_tmp_bytes(uint32_t n, uint64_t pair_capacity) {
+    size_t a = 0, b = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, a, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)n);
+    cub::DeviceRadixSort::SortKeys(nullptr, b, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (long long)pair_capacity);
+    return (a > b ? a : b) + 256;
+}
+
+int launch_sap(cudaStream_t st, const float* d_aabbs, uint32_t n, int axis, const SapScratch& S, uint32_t* d_perm, uint2* d_pairs,
+               uint64_t capacity, unsigned long long* d_count, int* d_next_axis) {
+    (void)d_pairs;
+    cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), st);
+    if (n <= 1) return 0;  // sweep_prune.rs:76-78: no pairs, axis unchanged (the caller keeps its axis)
+    int launched = 0;
+    const int g = (n + BT - 1) / BT;
+    sap_keys_kernel<<<g, BT, 0, st>>>(d_aabbs, n, axis, S.keys_in, S.vals_in); ++launched;
+    size_t tmp = S.cub_tmp_bytes;
+    cub::DeviceRadixSort::SortPairs(S.cub_tmp, tmp, S.keys_in, S.keys_out, S.vals_in, S.vals_out, (int)n, 0, 64, st); launched += 8;
+    sap_gather_kernel<<<g, BT, 0, st>>>(d_aabbs, S.vals_out, n, S.lo, S.hi, d_perm); ++launched;
+    sap_sweep_kernel<<<g, BT, 0, st>>>(S.lo, S.hi, n, axis, bits_for(n), S.pair_keys, capacity, d_count); ++launched;
+    sap_variance_kernel<<<1, 32, 0, st>>>(S.lo, S.hi, n, d_next_axis); ++launched;
+    return launched;
+}
+
+int launch_sap_finish(cudaStream_t st, const SapScratch& S, uint64_t count, uint2* d_pairs, uint32_t n) {
+    if (count == 0) return 0;
+    const int shift = bits_for(n);
+    size_t tmp = S.cub_tmp_bytes;
+    // reference emission order: shape_index (j) ascending, then active index (i) ascending (sweep_prune.rs:98-113)
+    cub::DeviceRadixSort::SortKeys(S.cub_tmp, tmp, S.pair_keys, S.pair_keys_alt, (long long)count, 0, 2 * shift, st);
+    unpack_pairs_kernel<<<(unsigned)((count + BT - 1) / BT), BT, 0, st>>>(S.pair_keys_alt, count, shift, d_pairs, 0);
+    return 7;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// world AABBs: ComputeBound<Aabb3> per primitive, then Aabb::transform (aabb3.rs:89-96: 8 corners, grown in order)
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BT) world_aabb_kernel(ShapeSetDev S, float* __restrict__ out) {
+    uint32_t i = blockIdx.x * BT + threadIdx.x;
+    if (i >= S.n) return;
+    Shape s;
+    load_shape(s, S.recs, i);
+    uint32_t meta = S.meta[i];
+    uint32_t kind = meta & 0xFF;
+    V3 mn = v3(0.f, 0.f, 0.f), mx = v3(0.f, 0.f, 0.f);
+    switch (kind) {
+        case K_PARTICLE: break;                                                               // primitive3.rs:86 Aabb3::zero()
+        case K_QUAD: mn = v3(-s.p0, -s.p1, 0.f); mx = v3(s.p0, s.p1, 0.f); break;              // quad.rs:62-69
+        case K_SPHERE: mn = v3(-s.p0, -s.p0, -s.p0); mx = v3(s.p0, s.p0, s.p0); break;         // sphere.rs:27-34
+        case K_CUBOID: mn = v3(-s.p0, -s.p1, -s.p2); mx = v3(s.p0, s.p1, s.p2); break;         // cuboid.rs:66-73
+        case K_CYLINDER: mn = v3(-s.p1, -s.p0, -s.p1); mx = v3(s.p1, s.p0, s.p1); break;       // cylinder.rs:64-71
+        case K_CAPSULE: mn = v3(-s.p1, -s.p0 - s.p1, -s.p1); mx = v3(s.p1, s.p0 + s.p1, s.p1); break;  // capsule.rs:51-58
+        default: {  // polyhedron.rs:84-86: fold from Aabb3::zero() growing by every vertex
+            uint32_t mid = meta >> 8;
+            uint32_t b = S.mesh_offsets[mid], e = S.mesh_offsets[mid + 1];
+            for (uint32_t k = b; k < e; ++k) {
+                float4 p = S.mesh_verts[k];
+                mn = v3(rmin(mn.x, p.x), rmin(mn.y, p.y), rmin(mn.z, p.z));
+                mx = v3(rmax(mx.x, p.x), rmax(mx.y, p.y), rmax(mx.z, p.z));
+            }
+        }
+    }
+    // Aabb3::new sorts the two corner points component-wise (aabb3.rs:26-31)
+    V3 lo = v3(rmin(mn.x, mx.x), rmin(mn.y, mx.y), rmin(mn.z, mx.z)), hi = v3(rmax(mn.x, mx.x), rmax(mn.y, mx.y), rmax(mn.z, mx.z));
+    // to_corners order (aabb3.rs:35-46)
+    V3 c[8] = {lo, v3(hi.x, lo.y, lo.z), v3(lo.x, hi.y, lo.z), v3(hi.x, hi.y, lo.z), v3(lo.x, lo.y, hi.z), v3(hi.x, lo.y, hi.z),
+               v3(lo.x, hi.y, hi.z), hi};
+    V3 f = transform_point3(s, c[0]);
+    V3 wmin = f, wmax = f;
+#pragma unroll
+    for (int k = 1; k < 8; ++k) {
+        V3 p = transform_point3(s, c[k]);
+        // grow = Aabb::new(min(min, p), max(max, p)), and new() re-sorts min/max (no-op here)
+        wmin = v3(rmin(wmin.x, p.x), rmin(wmin.y, p.y), rmin(wmin.z, p.z));
+        wmax = v3(rmax(wmax.x, p.x), rmax(wmax.y, p.y), rmax(wmax.z, p.z));
+    }
+    float* o = out + 6 * (size_t)i;
+    o[0] = wmin.x; o[1] = wmin.y; o[2] = wmin.z; o[3] = wmax.x; o[4] = wmax.y; o[5] = wmax.z;
+}
+
+int launch_world_aabbs(cudaStream_t st, const ShapeSetDev& S, float* d_out6) {
+    if (S.n == 0) return 0;
+    world_aabb_kernel<<<(S.n + BT - 1) / BT, BT, 0, st>>>(S, d_out6);
+    return 1;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// LBVH build (Karras 2012): Morton codes of box centres, radix sort, radix-tree topology, bottom-up bounds
+// ------------------------------------------------------------------------------------------------------------
+B3_DEV uint32_t fkey(float f) { uint32_t b = __float_as_uint(f); return (b & 0x80000000u) ? ~b : (b | 0x80000000u); }
+B3_DEV float funkey(uint32_t k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k); }
+
+__global__ void bvh_scene_init_kernel(uint32_t* scene) {
+    if (threadIdx.x < 3) scene[threadIdx.x] = 0xFFFFFFFFu;
+    else if (threadIdx.x < 6) scene[threadIdx.x] = 0u;
+}
+
+__global__ void __launch_bounds__(BT) bvh_scene_kernel(const float* __restrict__ aabbs, uint32_t n, uint32_t* __restrict__ scene) {
+    uint32_t i = blockIdx.x * BT + threadIdx.x;
+    float c[3] = {0.f, 0.f, 0.f};
+    bool ok = i < n;
+    if (ok) {
+        const float* b = aabbs + 6 * (size_t)i;
+        c[0] = (b[0] + b[3]) * 0.5f; c[1] = (b[1] + b[4]) * 0.5f; c[2] = (b[2] + b[5]) * 0.5f;
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        uint32_t kmin = ok && c[a] == c[a] ? fkey(c[a]) : 0xFFFFFFFFu, kmax = ok && c[a] == c[a] ? fkey(c[a]) : 0u;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            kmin = min(kmin, __shfl_xor_sync(0xFFFFFFFFu, kmin, off));
+            kmax = max(kmax, __shfl_xor_sync(0xFFFFFFFFu, kmax, off));
+        }
+        if ((threadIdx.x & 31) == 0) { atomicMin(scene + a, kmin); atomicMax(scene + 3 + a, kmax); }
+    }
+}
+
+B3_DEV uint32_t expand10(uint32_t v) {
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+
+__global__ void __launch_bounds__(BT) bvh_morton_kernel(const float* __restrict__ aabbs, uint32_t n, const uint32_t* __restrict__ scene,
+                                                        uint32_t* __restrict__ morton, uint32_t* __restrict__ idx) {
+    uint32_t i = blockIdx.x * BT + threadIdx.x;
+    if (i >= n) return;
+    const float* b = aabbs + 6 * (size_t)i;
+    uint32_t q[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        float lo = funkey(scene[a]), hi = funkey(scene[3 + a]);
+        float c = (b[a] + b[3 + a]) * 0.5f;
+        float ext = hi - lo;
+        float t = ext > 0.f ? (c - lo) / ext : 0.f;
+        t = fminf(fmaxf(t * 1024.f, 0.f), 1023.f);  // NaN -> 0
+        q[a] = (uint32_t)t;
+    }
+    morton[i] = (expand10(q[0]) << 2) | (expand10(q[1]) << 1) | expand10(q[2]);
+    idx[i] = i;
+}
+
+B3_DEV int delta(const uint32_t* __restrict__ m, int n, int i, int j) {
+    if (j < 0 || j >= n) return -1;
+    uint32_t a = m[i], b = m[j];
+    if (a != b) return __clz(a ^ b);
+    return 32 + __clz((uint32_t)i ^ (uint32_t)j);
+}
+
+__global__ void __launch_bounds__(BT) bvh_topology_kernel(const uint32_t* __restrict__ morton, uint32_t n, int2* __restrict__ children,
+                                                          uint32_t* __restrict__ parent) {
+    int i = blockIdx.x * BT + threadIdx.x;
+    const int ni = (int)n;
+    if (i >= ni - 1) return;
+    int d = (delta(morton, ni, i, i + 1) - delta(morton, ni, i, i - 1)) >= 0 ? 1 : -1;
+    int dmin = delta(morton, ni, i, i - d);
+    int lmax = 2;
+    while (delta(morton, ni, i, i + lmax * d) > dmin) lmax <<= 1;
+    int l = 0;
+    for (int t = lmax >> 1; t >= 1; t >>= 1)
+        if (delta(morton, ni, i, i + (l + t) * d) > dmin) l += t;
+    int j = i + l * d;
+    int dnode = delta(morton, ni, i, j);
+    int s = 0;
+    int t = l;
+    do {
+        t = (t + 1) >> 1;
+        if (delta(morton, ni, i, i + (s + t) * d) > dnode) s += t;
+    } while (t > 1);
+    int gamma = i + s * d + min(d, 0);
+    int left = (min(i, j) == gamma) ? (ni - 1) + gamma : gamma;
+    int right = (max(i, j) == gamma + 1) ? (ni - 1) + gamma + 1 : gamma + 1;
+    children[i] = make_int2(left, right);
+    parent[left] = (uint32_t)i;
+    parent[right] = (uint32_t)i;
+    if (i == 0) parent[0] = 0xFFFFFFFFu;
+}
+
+__global__ void __launch_bounds__(BT) bvh_refit_kernel(const float* __restrict__ aabbs, const uint32_t* __restrict__ leaf_value, uint32_t n,
+                                                       const int2* __restrict__ children, const uint32_t* __restrict__ parent,
+                                                       uint32_t* __restrict__ flags, float4* __restrict__ lo, float4* __restrict__ hi) {
+    uint32_t k = blockIdx.x * BT + threadIdx.x;
+    if (k >= n) return;
+    const float* b = aabbs + 6 * (size_t)leaf_value[k];
+    uint32_t node = (n - 1) + k;
+    lo[node] = make_float4(b[0], b[1], b[2], 0.f);
+    hi[node] = make_float4(b[3], b[4], b[5], 0.f);
+    if (n == 1) return;
+    __threadfence();
+    uint32_t p = parent[node];
+    while (p != 0xFFFFFFFFu) {
+        if (atomicAdd(flags + p, 1u) == 0u) return;  // the second child to arrive computes the parent
+        __threadfence();
+        int2 ch = children[p];
+        float4 l0 = __ldcg(lo + ch.x), h0 = __ldcg(hi + ch.x), l1 = __ldcg(lo + ch.y), h1 = __ldcg(hi + ch.y);
+        // union = grow(min).grow(max) with Rust's NaN-ignoring min/max (aabb3.rs:146-152)
+        lo[p] = make_float4(rmin(l0.x, l1.x), rmin(l0.y, l1.y), rmin(l0.z, l1.z), 0.f);
+        hi[p] = make_float4(rmax(h0.x, h1.x), rmax(h0.y, h1.y), rmax(h0.z, h1.z), 0.f);
+        __threadfence();
+        p = parent[p];
+    }
+}
+
+size_t bvh_cub_tmp_bytes(uint32_t n) {
+    size_t a = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, a, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)n);
+    return a + 256;
+}
+
+int launch_bvh_build(cudaStream_t st, const float* d_aabbs, uint32_t n, const BvhBuildScratch& W, float4* lo, float4* hi, int2* children,
+                     uint32_t* leaf_value) {
+    if (n == 0) return 0;
+    int launched = 0;
+    const int g = (n + BT - 1) / BT;
+    uint32_t* scene = reinterpret_cast<uint32_t*>(W.scene);
+    bvh_scene_init_kernel<<<1, 32, 0, st>>>(scene); ++launched;
+    bvh_scene_kernel<<<g, BT, 0, st>>>(d_aabbs, n, scene); ++launched;
+    bvh_morton_kernel<<<g, BT, 0, st>>>(d_aabbs, n, scene, W.morton_in, W.idx_in); ++launched;
+    size_t tmp = W.cub_tmp_bytes;
+    cub::DeviceRadixSort::SortPairs(W.cub_tmp, tmp, W.morton_in, W.morton_out, W.idx_in, leaf_value, (int)n, 0, 30, st); launched += 4;
+    if (n > 1) {
+        cudaMemsetAsync(W.flags, 0, (size_t)(n - 1) * 4, st);
+        bvh_topology_kernel<<<(n - 1 + BT - 1) / BT, BT, 0, st>>>(W.morton_out, n, children, W.parent); ++launched;
+    }
+    bvh_refit_kernel<<<g, BT, 0, st>>>(d_aabbs, leaf_value, n, children, W.parent, W.flags, lo, hi); ++launched;
+    return launched;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// visitors (dbvt/visitor.rs, dbvt/util.rs) and the predicates they call
+// ------------------------------------------------------------------------------------------------------------
+// Continuous<Aabb3> for Ray (aabb3.rs:165-195)
+B3_DEV bool ray_aabb(V3 o, V3 d, float4 mn, float4 mx, V3& out, bool* entry = nullptr) {
+    float ix = 1.0f / d.x, iy = 1.0f / d.y, iz = 1.0f / d.z;
+    float t1 = (mn.x - o.x) * ix, t2 = (mx.x - o.x) * ix;
+    float tmin = rmin(t1, t2), tmax = rmax(t1, t2);
+    t1 = (mn.y - o.y) * iy; t2 = (mx.y - o.y) * iy;
+    tmin = rmax(tmin, rmin(t1, t2)); tmax = rmin(tmax, rmax(t1, t2));
+    t1 = (mn.z - o.z) * iz; t2 = (mx.z - o.z) * iz;
+    tmin = rmax(tmin, rmin(t1, t2)); tmax = rmin(tmax, rmax(t1, t2));
+    if ((tmin < 0.0f && tmax < 0.0f) || tmax < tmin) return false;
+    float t = (tmin >= 0.0f) ? tmin : tmax;
+    if (entry) *entry = tmin >= 0.0f;  // the returned point is where the ray ENTERS the box (origin outside)
+    out = o + d * t;
+    return true;
+}
+
+// PlaneBound for Vec3 (bound.rs:48-58): In = 0, Cross = 1, Out = 2
+B3_DEV int relate_point(V3 p, float4 pl) {
+    float dist = dot(p, v3(pl.x, pl.y, pl.z));
+    return dist > pl.w ? 0 : (dist < pl.w ? 2 : 1);
+}
+// PlaneBound for Aabb3 (aabb3.rs:246-257)
+B3_DEV int relate_box(float4 mn, float4 mx, float4 pl) {
+    int first = relate_point(v3(mn.x, mn.y, mn.z), pl);
+    if (relate_point(v3(mx.x, mn.y, mn.z), pl) != first) return 1;
+    if (relate_point(v3(mn.x, mx.y, mn.z), pl) != first) return 1;
+    if (relate_point(v3(mx.x, mx.y, mn.z), pl) != first) return 1;
+    if (relate_point(v3(mn.x, mn.y, mx.z), pl) != first) return 1;
+    if (relate_point(v3(mx.x, mn.y, mx.z), pl) != first) return 1;
+    if (relate_point(v3(mn.x, mx.y, mx.z), pl) != first) return 1;
+    if (relate_point(v3(mx.x, mx.y, mx.z), pl) != first) return 1;
+    return first;
+}
+// Frustum::contains (frustum.rs:78-95): fold max over [left, right, top, bottom, near, far]; planes are stored
+// left,right,bottom,top,near,far (the struct's field order) — max is order independent.
+B3_DEV int frustum_relation(float4 mn, float4 mx, const float4* pl) {
+    int cur = 0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) cur = max(cur, relate_box(mn, mx, pl[k]));
+    return cur;
+}
+
+struct Query {
+    float4 qlo, qhi;     // BQ_AABB
+    V3 o, d;             // BQ_RAY
+    float4 pl[6];        // BQ_FRUSTUM
+};
+
+template <int KIND>
+B3_DEV bool accept(const Query& q, float4 mn, float4 mx, V3& point, int& rel) {
+    if (KIND == BQ_AABB) {
+        // DiscreteVisitor: bound.intersects(query) with self = the tree bound (aabb3.rs:237-244)
+        return mx.x > q.qlo.x && mn.x < q.qhi.x && mx.y > q.qlo.y && mn.y < q.qhi.y && mx.z > q.qlo.z && mn.z < q.qhi.z;
+    } else if (KIND == BQ_RAY) {
+        return ray_aabb(q.o, q.d, mn, mx, point);
+    } else {
+        rel = frustum_relation(mn, mx, q.pl);
+        return rel != 2;
+    }
+}
+
+template <int KIND>
+B3_DEV void load_query(Query& q, const float* __restrict__ queries, uint32_t qi) {
+    if (KIND == BQ_AABB) {
+        const float* b = queries + 6 * (size_t)qi;
+        q.qlo = make_float4(b[0], b[1], b[2], 0.f); q.qhi = make_float4(b[3], b[4], b[5], 0.f);
+    } else if (KIND == BQ_RAY) {
+        const float* b = queries + 6 * (size_t)qi;
+        q.o = v3(b[0], b[1], b[2]); q.d = v3(b[3], b[4], b[5]);
+    } else {
+        const float4* b = reinterpret_cast<const float4*>(queries) + 6 * (size_t)qi;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) q.pl[k] = b[k];
+    }
+}
+
+// One thread per query, explicit stack. FILL = false counts hits; FILL = true writes them at offsets[qi].
+template <int KIND, bool FILL>
+__global__ void __launch_bounds__(BT) bvh_query_kernel(BvhDev T, const float* __restrict__ queries, uint32_t nq, uint32_t* __restrict__ counts,
+                                                       const unsigned long long* __restrict__ offsets, uint32_t* __restrict__ values,
+                                                       void* __restrict__ payload) {
+    uint32_t qi = blockIdx.x * BT + threadIdx.x;
+    if (qi >= nq) return;
+    Query q;
+    load_query<KIND>(q, queries, qi);
+    unsigned long long w = FILL ? offsets[qi] : 0ull;
+    uint32_t cnt = 0;
+    if (T.n > 0) {
+        uint32_t stack[64];
+        int sp = 0;
+        stack[sp++] = (T.n == 1) ? 0u + (T.n - 1) : 0u;
+        const uint32_t first_leaf = T.n - 1;
+        while (sp > 0) {
+            uint32_t node = stack[--sp];
+            float4 mn = __ldg(T.lo + node), mx = __ldg(T.hi + node);
+            V3 point; int rel = 0;
+            if (!accept<KIND>(q, mn, mx, point, rel)) continue;
+            if (node >= first_leaf) {
+                if (FILL) {
+                    values[w] = __ldg(T.leaf_value + (node - first_leaf));
+                    if (KIND == BQ_RAY) { float* p = reinterpret_cast<float*>(payload) + 3 * w; p[0] = point.x; p[1] = point.y; p[2] = point.z; }
+                    if (KIND == BQ_FRUSTUM) reinterpret_cast<uint8_t*>(payload)[w] = (uint8_t)rel;
+                    ++w;
+                }
+                ++cnt;
+            } else if (sp <= 62) {
+                int2 ch = __ldg(T.children + node);
+                stack[sp++] = (uint32_t)ch.y;
+                stack[sp++] = (uint32_t)ch.x;
+            }
+        }
+    }
+    if (!FILL) counts[qi] = cnt;
+}
+
+int launch_bvh_query(cudaStream_t st, const BvhDev& T, int kind, const float* d_queries, uint32_t nq, uint32_t* d_counts,
+                     const unsigned long long* d_offsets, uint32_t* d_values, void* d_payload) {
+    if (nq == 0) return 0;
+    const int g = (nq + BT - 1) / BT;
+    const bool fill = d_offsets != nullptr;
+#define B3_Q(KIND)                                                                                                        \
+    if (fill) bvh_query_kernel<KIND, true><<<g, BT, 0, st>>>(T, d_queries, nq, d_counts, d_offsets, d_values, d_payload); \
+    else bvh_query_kernel<KIND, false><<<g, BT, 0, st>>>(T, d_queries, nq, d_counts, d_offsets, d_values, d_payload);
+    if (kind == BQ_AABB) { B3_Q(BQ_AABB) }
+    else if (kind == BQ_RAY) { B3_Q(BQ_RAY) }
+    else { B3_Q(BQ_FRUSTUM) }
+#undef B3_Q
+    return 1;
+}
+
+// query_ray_closest (dbvt/util.rs:77-103): t = (point - origin) . direction over the leaves the ray hits; the smallest
+// t wins. Two properties of the reference make its answer depend on its (randomised) tree shape: it keeps the FIRST leaf
+// reaching the minimum in traversal order, and RayClosestVisitor (:46-62) prunes a branch when the branch bound's own t
+// is not below the current minimum — but for a bound that CONTAINS the ray origin the slab test returns the EXIT point
+// (aabb3.rs:190-193), so such a branch can be pruned although it holds closer leaves. The device returns the
+// shape-independent answer: the minimum of the reference's per-leaf t over every leaf the ray hits (what the
+// reference returns whenever its pruning does not misfire), exact-t ties resolved to the lowest value index. A branch
+// is pruned only on a true lower bound (its entry t when the origin is outside it).
+__global__ void __launch_bounds__(BT) bvh_ray_closest_kernel(BvhDev T, const float* __restrict__ rays, uint32_t nq, uint32_t* __restrict__ out_value,
+                                                             float* __restrict__ out_point_t) {
+    uint32_t qi = blockIdx.x * BT + threadIdx.x;
+    if (qi >= nq) return;
+    const float* b = rays + 6 * (size_t)qi;
+    V3 o = v3(b[0], b[1], b[2]), d = v3(b[3], b[4], b[5]);
+    float best_t = INFINITY;
+    uint32_t best_v = 0xFFFFFFFFu;
+    V3 best_p = v3(0.f, 0.f, 0.f);
+    if (T.n > 0) {
+        uint32_t stack[64];
+        int sp = 0;
+        stack[sp++] = (T.n == 1) ? (T.n - 1) : 0u;
+        const uint32_t first_leaf = T.n - 1;
+        while (sp > 0) {
+            uint32_t node = stack[--sp];
+            float4 mn = __ldg(T.lo + node), mx = __ldg(T.hi + node);
+            V3 p;
+            bool entered_from_outside;
+            if (!ray_aabb(o, d, mn, mx, p, &entered_from_outside)) continue;
+            float t = dot(p - o, d);
+            if (node >= first_leaf) {
+                uint32_t v = __ldg(T.leaf_value + (node - first_leaf));
+                if (t < best_t || (t == best_t && v < best_v)) { best_t = t; best_v = v; best_p = p; }
+            } else if (!(entered_from_outside && t > best_t) && sp <= 62) {
+                int2 ch = __ldg(T.children + node);
+                stack[sp++] = (uint32_t)ch.y;
+                stack[sp++] = (uint32_t)ch.x;
+            }
+        }
+    }
+    out_value[qi] = best_v;
+    float* op = out_point_t + 4 * (size_t)qi;
+    op[0] = best_p.x; op[1] = best_p.y; op[2] = best_p.z; op[3] = best_t;
+}
+
+int launch_bvh_ray_closest(cudaStream_t st, const BvhDev& T, const float* d_rays, uint32_t nq, uint32_t* d_value, float* d_point_t) {
+    if (nq == 0) return 0;
+    bvh_ray_closest_kernel<<<(nq + BT - 1) / BT, BT, 0, st>>>(T, d_rays, nq, d_value, d_point_t);
+    return 1;
+}
+
+// DbvtBroadPhase::find_collider_pairs (broad_phase/dbvt.rs:26-63): every dirty value queries the tree with its own
+// bound (DiscreteVisitor); pairs are ordered (low, high) and unique. A pair of two dirty values is found from both
+// sides — it is emitted from the lower index only; the caller sorts the keys, which gives the reference's sorted list.
+template <bool FILL>
+__global__ void __launch_bounds__(BT) bvh_collider_pairs_kernel(BvhDev T, const float* __restrict__ aabbs, const uint8_t* __restrict__ dirty,
+                                                                uint32_t* __restrict__ counts, const unsigned long long* __restrict__ offsets,
+                                                                unsigned long long* __restrict__ keys) {
+    uint32_t v = blockIdx.x * BT + threadIdx.x;
+    if (v >= T.n) return;
+    uint32_t cnt = 0;
+    if (dirty[v]) {
+        const float* b = aabbs + 6 * (size_t)v;
+        Query q;
+        q.qlo = make_float4(b[0], b[1], b[2], 0.f); q.qhi = make_float4(b[3], b[4], b[5], 0.f);
+        unsigned long long w = FILL ? offsets[v] : 0ull;
+        uint32_t stack[64];
+        int sp = 0;
+        stack[sp++] = (T.n == 1) ? (T.n - 1) : 0u;
+        const uint32_t first_leaf = T.n - 1;
+        while (sp > 0) {
+            uint32_t node = stack[--sp];
+            float4 mn = __ldg(T.lo + node), mx = __ldg(T.hi + node);
+            V3 pt; int rel;
+            if (!accept<BQ_AABB>(q, mn, mx, pt, rel)) continue;
+            if (node >= first_leaf) {
+                uint32_t h = __ldg(T.leaf_value + (node - first_leaf));
+                if (h != v && (!dirty[h] || v < h)) {
+                    if (FILL) keys[w++] = ((unsigned long long)min(v, h) << 32) | max(v, h);
+                    ++cnt;
+                }
+            } else if (sp <= 62) {
+                int2 ch = __ldg(T.children + node);
+                stack[sp++] = (uint32_t)ch.y;
+                stack[sp++] = (uint32_t)ch.x;
+            }
+        }
+    }
+    if (!FILL) counts[v] = cnt;
+}
+
+int launch_bvh_collider_pairs(cudaStream_t st, const BvhDev& T, const float* d_aabbs, const uint8_t* d_dirty, uint32_t* d_counts,
+                              const unsigned long long* d_offsets, unsigned long long* d_pair_keys) {
+    if (T.n == 0) return 0;
+    const int g = (T.n + BT - 1) / BT;
+    if (d_offsets) bvh_collider_pairs_kernel<true><<<g, BT, 0, st>>>(T, d_aabbs, d_dirty, d_counts, d_offsets, d_pair_keys);
+    else bvh_collider_pairs_kernel<false><<<g, BT, 0, st>>>(T, d_aabbs, d_dirty, d_counts, d_offsets, d_pair_keys);
+    return 1;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// small utilities over CUB
+// ------------------------------------------------------------------------------------------------------------
+struct U32ToU64 { __host__ __device__ unsigned long long operator()(uint32_t v) const { return v; } };
+
+size_t scan_tmp_bytes(uint32_t n) {
+    size_t a = 0;
+    cub::TransformInputIterator<unsigned long long, U32ToU64, const uint32_t*> it(nullptr, U32ToU64());
+    cub::DeviceScan::ExclusiveSum(nullptr, a, it, (unsigned long long*)nullptr, (int)(n + 1));
+    return a + 256;
+}
+// d_out gets n + 1 entries: exclusive prefix sums of d_in[0..n) and the total at d_out[n] (d_in must have n + 1 readable
+// entries with d_in[n] ignored: the caller zero-pads).
+int launch_exclusive_scan_u32_to_u64(cudaStream_t st, const uint32_t* d_in, unsigned long long* d_out, uint32_t n, void* tmp, size_t tmp_bytes) {
+    cub::TransformInputIterator<unsigned long long, U32ToU64, const uint32_t*> it(d_in, U32ToU64());
+    cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, it, d_out, (int)(n + 1), st);
+    return 2;
+}
+size_t sort_u64_tmp_bytes(uint64_t n) {
+    size_t a = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, a, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (long long)n);
+    return a + 256;
+}
+int launch_sort_u64(cudaStream_t st, unsigned long long* d_keys, unsigned long long* d_alt, uint64_t n, void* tmp, size_t tmp_bytes, bool* in_alt) {
+    *in_alt = false;
+    if (n == 0) return 0;
+    cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, d_keys, d_alt, (long long)n, 0, 64, st);
+    *in_alt = true;
+    return 8;
+}
+int launch_unpack_pairs(cudaStream_t st, const unsigned long long* d_keys, uint64_t n, uint2* d_pairs, bool hi_first) {
+    if (n == 0) return 0;
+    unpack_pairs_kernel<<<(unsigned)((n + BT - 1) / BT), BT, 0, st>>>(d_keys, n, 32, d_pairs, hi_first ? 1 : 0);
+    return 1;
+}
+
+}  // namespace b3

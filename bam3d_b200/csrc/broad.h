@@ -1,4 +1,70 @@
 // Host-callable launchers of the broad-phase kernels (implemented in broad.cu).
 #pragma once
 #include <cuda_runtime.h>
+#include <cstddef>
 #include <cstdint>
+
+namespace b3 {
+
+struct ShapeSetDev;
+
+// ---- sweep and prune ------------------------------------------------------------------------------------------
+struct SapScratch {
+    unsigned long long* keys_in;   // n
+    unsigned long long* keys_out;  // n
+    uint32_t* vals_in;             // n
+    uint32_t* vals_out;            // n  (== perm)
+    float4* lo;                    // n  sorted boxes: min xyz
+    float4* hi;                    // n  sorted boxes: max xyz
+    void* cub_tmp;
+    size_t cub_tmp_bytes;
+    unsigned long long* pair_keys; // capacity (j << 32 | i), unsorted then sorted in place via pair_keys_alt
+    unsigned long long* pair_keys_alt;
+};
+size_t sap_cub_tmp_bytes(uint32_t n, uint64_t pair_capacity);
+// d_count: device u64 (number of pairs found, may exceed capacity); d_next_axis: device i32.
+int launch_sap(cudaStream_t st, const float* d_aabbs, uint32_t n, int axis, const SapScratch& S, uint32_t* d_perm, uint2* d_pairs,
+               uint64_t capacity, unsigned long long* d_count, int* d_next_axis);
+// order the first `count` pair keys by (j, i) and unpack them into d_pairs
+int launch_sap_finish(cudaStream_t st, const SapScratch& S, uint64_t count, uint2* d_pairs, uint32_t n);
+
+// ---- world AABBs of packed shapes (ComputeBound<Aabb3> + Aabb::transform) ---------------------------------------
+int launch_world_aabbs(cudaStream_t st, const ShapeSetDev& S, float* d_out6);
+
+// ---- static BVH answering the DBVT queries ---------------------------------------------------------------------
+struct BvhDev {
+    // n leaves (values), n - 1 internal nodes. Node ids: internal 0..n-2 (root = 0), leaf k -> (n - 1) + k.
+    uint32_t n;
+    const float4* lo;        // 2n - 1 node bounds (min xyz)
+    const float4* hi;        // 2n - 1 node bounds (max xyz)
+    const int2* children;    // n - 1 : (left, right) node ids
+    const uint32_t* leaf_value;  // n : value index of leaf k (Morton order)
+};
+struct BvhBuildScratch {
+    uint32_t* morton_in; uint32_t* morton_out; uint32_t* idx_in; uint32_t* idx_out;
+    void* cub_tmp; size_t cub_tmp_bytes;
+    uint32_t* parent;   // 2n - 1
+    uint32_t* flags;    // n - 1
+    float* scene;       // 6 floats: scene bounds
+};
+size_t bvh_cub_tmp_bytes(uint32_t n);
+int launch_bvh_build(cudaStream_t st, const float* d_aabbs, uint32_t n, const BvhBuildScratch& W, float4* lo, float4* hi, int2* children,
+                     uint32_t* leaf_value);
+
+enum BvhQueryKind { BQ_AABB = 0, BQ_RAY = 1, BQ_FRUSTUM = 2 };
+// pass 1 (d_offsets == nullptr): per-query hit counts into d_counts. pass 2: fill d_values / d_payload at d_offsets.
+//   BQ_AABB: queries nq x 6 f32, no payload;  BQ_RAY: nq x 6 f32 (origin, direction), payload 3 f32 (hit point) per hit;
+//   BQ_FRUSTUM: nq x 24 f32 (6 planes n.xyz,d in the order left,right,bottom,top,near,far), payload 1 byte (Relation).
+int launch_bvh_query(cudaStream_t st, const BvhDev& T, int kind, const float* d_queries, uint32_t nq, uint32_t* d_counts,
+                     const unsigned long long* d_offsets, uint32_t* d_values, void* d_payload);
+int launch_bvh_ray_closest(cudaStream_t st, const BvhDev& T, const float* d_rays, uint32_t nq, uint32_t* d_value, float* d_point_t);
+// DbvtBroadPhase::find_collider_pairs: count / fill passes over the dirty values.
+int launch_bvh_collider_pairs(cudaStream_t st, const BvhDev& T, const float* d_aabbs, const uint8_t* d_dirty, uint32_t* d_counts,
+                              const unsigned long long* d_offsets, unsigned long long* d_pair_keys);
+int launch_exclusive_scan_u32_to_u64(cudaStream_t st, const uint32_t* d_in, unsigned long long* d_out, uint32_t n, void* tmp, size_t tmp_bytes);
+size_t scan_tmp_bytes(uint32_t n);
+int launch_sort_u64(cudaStream_t st, unsigned long long* d_keys, unsigned long long* d_alt, uint64_t n, void* tmp, size_t tmp_bytes, bool* in_alt);
+size_t sort_u64_tmp_bytes(uint64_t n);
+int launch_unpack_pairs(cudaStream_t st, const unsigned long long* d_keys, uint64_t n, uint2* d_pairs, bool hi_first);
+
+}  // namespace b3

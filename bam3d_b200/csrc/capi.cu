@@ -460,3 +460,309 @@ int32_t bam3d_gjk_time_of_impact(bam3d_ctx* ctx, const bam3d_shapes* s0, const b
 }
 
 }  // extern "C"
+
+// ============================================================================================================
+// broad phase
+// ============================================================================================================
+struct bam3d_bvh {
+    uint32_t n = 0;
+    float* d_aabbs = nullptr;      // n x 6 (kept for DbvtBroadPhase queries)
+    float4* lo = nullptr;          // 2n - 1
+    float4* hi = nullptr;
+    int2* children = nullptr;      // n - 1
+    uint32_t* leaf_value = nullptr;
+};
+
+static BvhDev bvh_view(const bam3d_bvh* t) {
+    BvhDev v; v.n = t->n; v.lo = t->lo; v.hi = t->hi; v.children = t->children; v.leaf_value = t->leaf_value;
+    return v;
+}
+
+extern "C" {
+
+// Frustum::from_mat4 (frustum.rs:46-75) on the host: rows of the matrix; NB near / far are built from the same rows as
+// left / right (w + x, w - x) exactly as the reference does. out24 = 6 x (n.xyz, d) in the order left, right, bottom,
+// top, near, far. Returns BAM3D_ERR_ARG when a plane normal is zero (the reference returns None).
+int32_t bam3d_frustum_from_mat4(const float* m, float* out24) {
+    if (!m || !out24) return BAM3D_ERR_ARG;
+    // transpose: row r = (m[r], m[4 + r], m[8 + r], m[12 + r])
+    auto row = [&](int r, float* v) { v[0] = m[r]; v[1] = m[4 + r]; v[2] = m[8 + r]; v[3] = m[12 + r]; };
+    float x[4], y[4], w[4];
+    row(0, x); row(1, y); row(3, w);
+    const float* src[6] = {x, x, y, y, x, x};
+    const float sgn[6] = {1.f, -1.f, 1.f, -1.f, 1.f, -1.f};
+    for (int k = 0; k < 6; ++k) {
+        float v[4];
+        for (int c = 0; c < 4; ++c) v[c] = sgn[k] > 0.f ? w[c] + src[k][c] : w[c] - src[k][c];
+        // Plane::from_vector4_alt: n = v.xyz, d = -v.w; Plane::normalize: * 1 / sqrt(n.n)
+        float nx = v[0], ny = v[1], nz = v[2], d = -v[3];
+        if (nx == 0.f && ny == 0.f && nz == 0.f) return BAM3D_ERR_ARG;
+        float denom = 1.0f / sqrtf((nx * nx + ny * ny) + nz * nz);
+        out24[4 * k] = nx * denom; out24[4 * k + 1] = ny * denom; out24[4 * k + 2] = nz * denom; out24[4 * k + 3] = d * denom;
+    }
+    return BAM3D_OK;
+}
+
+// ---- SweepAndPrune3 --------------------------------------------------------------------------------------------
+static int32_t sap_run(bam3d_ctx* ctx, const float* d_aabbs, uint64_t n64, int32_t* inout_axis, uint32_t* d_perm, uint32_t* d_pairs,
+                       uint64_t capacity, uint64_t* out_count) {
+    const uint32_t n = (uint32_t)n64;
+    int axis = *inout_axis;
+    if (axis < 0 || axis > 2) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_sap_find_pairs: sweep axis must be 0, 1 or 2", cudaSuccess);
+    *out_count = 0;
+    if (n <= 1) {
+        if (n == 1 && d_perm) cudaMemsetAsync(d_perm, 0, 4, ctx->stream);
+        return BAM3D_OK;
+    }
+    int32_t rc;
+    SapScratch S;
+    const size_t tmp_bytes = sap_cub_tmp_bytes(n, capacity ? capacity : 1);
+    if ((rc = ctx->bp0.reserve(ctx, (size_t)n * 8 * 2)) || (rc = ctx->bp1.reserve(ctx, (size_t)n * 4 * 2)) || (rc = ctx->bp2.reserve(ctx, (size_t)n * 16 * 2)) ||
+        (rc = ctx->bp3.reserve(ctx, (capacity ? capacity : 1) * 8 * 2)) || (rc = ctx->cub_tmp.reserve(ctx, tmp_bytes)) || (rc = ctx->small.reserve(ctx, 1024)))
+        return rc;
+    S.keys_in = (unsigned long long*)ctx->bp0.ptr; S.keys_out = S.keys_in + n;
+    S.vals_in = (uint32_t*)ctx->bp1.ptr; S.vals_out = S.vals_in + n;
+    S.lo = (float4*)ctx->bp2.ptr; S.hi = S.lo + n;
+    S.pair_keys = (unsigned long long*)ctx->bp3.ptr; S.pair_keys_alt = S.pair_keys + (capacity ? capacity : 1);
+    S.cub_tmp = ctx->cub_tmp.ptr; S.cub_tmp_bytes = tmp_bytes;
+    unsigned long long* d_count = (unsigned long long*)((char*)ctx->small.ptr + 832);
+    int* d_axis = (int*)((char*)ctx->small.ptr + 840);
+    { KernelTimer kt(ctx);
+      ctx->launches += launch_sap(ctx->stream, d_aabbs, n, axis, S, d_perm, (uint2*)d_pairs, capacity, d_count, d_axis); }
+    if ((rc = check_launch(ctx, "sap kernels"))) return rc;
+    unsigned long long h_count = 0; int h_axis = axis;
+    CU_TRY(cudaMemcpyAsync(&h_count, d_count, 8, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(count)");
+    CU_TRY(cudaMemcpyAsync(&h_axis, d_axis, 4, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(axis)");
+    CU_TRY(cudaStreamSynchronize(ctx->stream), "sap kernels");
+    *out_count = h_count;
+    if (h_count > capacity) {
+        char msg[160];
+        std::snprintf(msg, sizeof msg, "bam3d_sap_find_pairs: %llu pairs found, capacity %llu", h_count, (unsigned long long)capacity);
+        return b3_fail(ctx, BAM3D_ERR_CAPACITY, msg, cudaSuccess);
+    }
+    { KernelTimer kt(ctx);
+      ctx->launches += launch_sap_finish(ctx->stream, S, h_count, (uint2*)d_pairs, n); }
+    *inout_axis = h_axis;
+    return check_launch(ctx, "sap finish");
+}
+
+int32_t bam3d_sap_find_pairs_dev(bam3d_ctx* ctx, const float* d_aabbs, uint64_t n, int32_t* inout_sweep_axis, uint32_t* d_perm,
+                                 uint32_t* d_pairs, uint64_t capacity, uint64_t* out_count) {
+    if (!ctx || !inout_sweep_axis || !out_count || (n && !d_aabbs) || (capacity && !d_pairs)) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_sap_find_pairs: null argument", cudaSuccess);
+    int32_t rc;
+    if ((rc = check_n(ctx, n)) || (rc = check_n(ctx, capacity))) return rc;
+    CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
+    return sap_run(ctx, d_aabbs, n, inout_sweep_axis, d_perm, d_pairs, capacity, out_count);
+}
+
+int32_t bam3d_sap_find_pairs(bam3d_ctx* ctx, const float* aabbs, uint64_t n, int32_t* inout_sweep_axis, uint32_t* out_perm,
+                             uint32_t* out_pairs, uint64_t capacity, uint64_t* out_count) {
+    if (!ctx || !inout_sweep_axis || !out_count || (n && !aabbs) || (capacity && !out_pairs)) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_sap_find_pairs: null argument", cudaSuccess);
+    int32_t rc;
+    if ((rc = check_n(ctx, n)) || (rc = check_n(ctx, capacity))) return rc;
+    CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
+    if ((rc = ctx->bp4.reserve(ctx, (size_t)(n ? n : 1) * 24 + (size_t)(n ? n : 1) * 4)) || (rc = ctx->bp5.reserve(ctx, (capacity ? capacity : 1) * 8))) return rc;
+    float* d_aabbs = (float*)ctx->bp4.ptr;
+    uint32_t* d_perm = (uint32_t*)((char*)ctx->bp4.ptr + (size_t)(n ? n : 1) * 24);
+    uint32_t* d_pairs = (uint32_t*)ctx->bp5.ptr;
+    if (n) CU_TRY(cudaMemcpyAsync(d_aabbs, aabbs, n * 24, cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpyAsync(aabbs)");
+    rc = sap_run(ctx, d_aabbs, n, inout_sweep_axis, d_perm, d_pairs, capacity, out_count);
+    if (rc != BAM3D_OK) return rc;
+    if (out_perm && n) CU_TRY(cudaMemcpyAsync(out_perm, d_perm, n * 4, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(perm)");
+    if (*out_count) CU_TRY(cudaMemcpyAsync(out_pairs, d_pairs, *out_count * 8, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(pairs)");
+    CU_TRY(cudaStreamSynchronize(ctx->stream), "bam3d_sap_find_pairs");
+    return BAM3D_OK;
+}
+
+// ---- world AABBs -----------------------------------------------------------------------------------------------
+int32_t bam3d_shapes_world_aabbs_dev(bam3d_ctx* ctx, const bam3d_shapes* shapes, float* d_out6) {
+    if (!ctx || !shapes || (shapes->n && !d_out6)) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_shapes_world_aabbs: null argument", cudaSuccess);
+    CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
+    ctx->launches += launch_world_aabbs(ctx->stream, view(shapes), d_out6);
+    return check_launch(ctx, "world_aabb_kernel");
+}
+int32_t bam3d_shapes_world_aabbs(bam3d_ctx* ctx, const bam3d_shapes* shapes, float* out6) {
+    if (!ctx || !shapes || (shapes->n && !out6)) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_shapes_world_aabbs: null argument", cudaSuccess);
+    int32_t rc;
+    if ((rc = ctx->bp4.reserve(ctx, (size_t)(shapes->n ? shapes->n : 1) * 24))) return rc;
+    if ((rc = bam3d_shapes_world_aabbs_dev(ctx, shapes, (float*)ctx->bp4.ptr))) return rc;
+    if (shapes->n) CU_TRY(cudaMemcpyAsync(out6, ctx->bp4.ptr, (size_t)shapes->n * 24, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(aabbs)");
+    CU_TRY(cudaStreamSynchronize(ctx->stream), "bam3d_shapes_world_aabbs");
+    return BAM3D_OK;
+}
+
+// ---- BVH (DBVT queries) ----------------------------------------------------------------------------------------
+void bam3d_bvh_free(bam3d_ctx* ctx, bam3d_bvh* t) {
+    (void)ctx;
+    if (!t) return;
+    if (t->d_aabbs) cudaFree(t->d_aabbs);
+    if (t->lo) cudaFree(t->lo);
+    if (t->hi) cudaFree(t->hi);
+    if (t->children) cudaFree(t->children);
+    if (t->leaf_value) cudaFree(t->leaf_value);
+    delete t;
+}
+
+static int32_t bvh_build_impl(bam3d_ctx* ctx, const float* aabbs, bool on_device, uint64_t n64, bam3d_bvh** out) {
+    *out = nullptr;
+    int32_t rc;
+    if ((rc = check_n(ctx, n64))) return rc;
+    CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
+    const uint32_t n = (uint32_t)n64;
+    bam3d_bvh* t = new (std::nothrow) bam3d_bvh();
+    if (!t) return BAM3D_ERR_OOM;
+    t->n = n;
+    const size_t nn = n ? n : 1;
+    cudaError_t e;
+    if ((e = cudaMalloc(&t->d_aabbs, nn * 24)) != cudaSuccess || (e = cudaMalloc(&t->lo, (2 * nn) * 16)) != cudaSuccess ||
+        (e = cudaMalloc(&t->hi, (2 * nn) * 16)) != cudaSuccess || (e = cudaMalloc(&t->children, nn * 8)) != cudaSuccess ||
+        (e = cudaMalloc(&t->leaf_value, nn * 4)) != cudaSuccess) {
+        bam3d_bvh_free(ctx, t);
+        return b3_fail(ctx, BAM3D_ERR_OOM, "cudaMalloc(bvh)", e);
+    }
+    if (n) cudaMemcpyAsync(t->d_aabbs, aabbs, (size_t)n * 24, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream);
+    BvhBuildScratch W;
+    const size_t tmp_bytes = bvh_cub_tmp_bytes(n ? n : 1);
+    if ((rc = ctx->bp0.reserve(ctx, nn * 4 * 4)) || (rc = ctx->bp1.reserve(ctx, (2 * nn) * 4 + nn * 4)) || (rc = ctx->cub_tmp.reserve(ctx, tmp_bytes)) ||
+        (rc = ctx->small.reserve(ctx, 1024))) { bam3d_bvh_free(ctx, t); return rc; }
+    W.morton_in = (uint32_t*)ctx->bp0.ptr; W.morton_out = W.morton_in + nn; W.idx_in = W.morton_out + nn; W.idx_out = W.idx_in + nn;
+    W.parent = (uint32_t*)ctx->bp1.ptr; W.flags = W.parent + 2 * nn;
+    W.cub_tmp = ctx->cub_tmp.ptr; W.cub_tmp_bytes = tmp_bytes;
+    W.scene = (float*)((char*)ctx->small.ptr + 896);
+    { KernelTimer kt(ctx);
+      ctx->launches += launch_bvh_build(ctx->stream, t->d_aabbs, n, W, t->lo, t->hi, t->children, t->leaf_value); }
+    e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { bam3d_bvh_free(ctx, t); return b3_fail(ctx, BAM3D_ERR_CUDA, "bam3d_bvh_build", e); }
+    *out = t;
+    return BAM3D_OK;
+}
+
+int32_t bam3d_bvh_build(bam3d_ctx* ctx, const float* aabbs, uint64_t n, bam3d_bvh** out) {
+    if (!ctx || !out || (n && !aabbs)) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_bvh_build: null argument", cudaSuccess);
+    return bvh_build_impl(ctx, aabbs, false, n, out);
+}
+int32_t bam3d_bvh_build_dev(bam3d_ctx* ctx, const float* d_aabbs, uint64_t n, bam3d_bvh** out) {
+    if (!ctx || !out || (n && !d_aabbs)) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_bvh_build: null argument", cudaSuccess);
+    return bvh_build_impl(ctx, d_aabbs, true, n, out);
+}
+uint32_t bam3d_bvh_count(const bam3d_bvh* t) { return t ? t->n : 0; }
+
+// Shared implementation of the variable-length queries: count pass, exclusive scan, fill pass.
+static int32_t bvh_query_impl(bam3d_ctx* ctx, const bam3d_bvh* t, int kind, const float* queries, uint64_t nq64, uint64_t* out_offsets,
+                              uint32_t* out_values, void* out_payload, size_t payload_stride, uint64_t capacity, uint64_t* out_total) {
+    int32_t rc;
+    if ((rc = check_n(ctx, nq64))) return rc;
+    CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
+    const uint32_t nq = (uint32_t)nq64;
+    *out_total = 0;
+    if (nq == 0) { if (out_offsets) out_offsets[0] = 0; return BAM3D_OK; }
+    const size_t qfloats = kind == BQ_FRUSTUM ? 24 : 6;
+    const size_t scan_bytes = scan_tmp_bytes(nq);
+    if ((rc = ctx->bp0.reserve(ctx, nq * qfloats * 4)) || (rc = ctx->bp1.reserve(ctx, ((size_t)nq + 1) * 4)) ||
+        (rc = ctx->bp2.reserve(ctx, ((size_t)nq + 1) * 8)) || (rc = ctx->cub_tmp.reserve(ctx, scan_bytes))) return rc;
+    float* d_q = (float*)ctx->bp0.ptr;
+    uint32_t* d_counts = (uint32_t*)ctx->bp1.ptr;
+    unsigned long long* d_offsets = (unsigned long long*)ctx->bp2.ptr;
+    CU_TRY(cudaMemcpyAsync(d_q, queries, nq * qfloats * 4, cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpyAsync(queries)");
+    cudaMemsetAsync(d_counts + nq, 0, 4, ctx->stream);
+    BvhDev T = bvh_view(t);
+    { KernelTimer kt(ctx);
+      ctx->launches += launch_bvh_query(ctx->stream, T, kind, d_q, nq, d_counts, nullptr, nullptr, nullptr); }
+    ctx->launches += launch_exclusive_scan_u32_to_u64(ctx->stream, d_counts, d_offsets, nq, ctx->cub_tmp.ptr, scan_bytes);
+    if ((rc = check_launch(ctx, "bvh query (count)"))) return rc;
+    unsigned long long total = 0;
+    CU_TRY(cudaMemcpyAsync(&total, d_offsets + nq, 8, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(total)");
+    if (out_offsets) CU_TRY(cudaMemcpyAsync(out_offsets, d_offsets, ((size_t)nq + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(offsets)");
+    CU_TRY(cudaStreamSynchronize(ctx->stream), "bvh query (count)");
+    *out_total = total;
+    if (total > capacity) {
+        char msg[160];
+        std::snprintf(msg, sizeof msg, "bam3d_bvh_query: %llu hits, capacity %llu", total, (unsigned long long)capacity);
+        return b3_fail(ctx, BAM3D_ERR_CAPACITY, msg, cudaSuccess);
+    }
+    if (total == 0) return BAM3D_OK;
+    if ((rc = ctx->bp3.reserve(ctx, total * 4)) || (payload_stride && (rc = ctx->bp4.reserve(ctx, total * payload_stride)))) return rc;
+    { KernelTimer kt(ctx);
+      ctx->launches += launch_bvh_query(ctx->stream, T, kind, d_q, nq, d_counts, d_offsets, (uint32_t*)ctx->bp3.ptr, payload_stride ? ctx->bp4.ptr : nullptr); }
+    if ((rc = check_launch(ctx, "bvh query (fill)"))) return rc;
+    CU_TRY(cudaMemcpyAsync(out_values, ctx->bp3.ptr, total * 4, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(values)");
+    if (payload_stride) CU_TRY(cudaMemcpyAsync(out_payload, ctx->bp4.ptr, total * payload_stride, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(payload)");
+    CU_TRY(cudaStreamSynchronize(ctx->stream), "bvh query (fill)");
+    return BAM3D_OK;
+}
+
+int32_t bam3d_bvh_query_aabb(bam3d_ctx* ctx, const bam3d_bvh* t, const float* queries, uint64_t nq, uint64_t* out_offsets, uint32_t* out_values,
+                             uint64_t capacity, uint64_t* out_total) {
+    if (!ctx || !t || !out_total || (nq && !queries) || (capacity && !out_values)) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_bvh_query_aabb: null argument", cudaSuccess);
+    return bvh_query_impl(ctx, t, BQ_AABB, queries, nq, out_offsets, out_values, nullptr, 0, capacity, out_total);
+}
+int32_t bam3d_bvh_query_ray(bam3d_ctx* ctx, const bam3d_bvh* t, const float* rays, uint64_t nq, uint64_t* out_offsets, uint32_t* out_values,
+                            float* out_points, uint64_t capacity, uint64_t* out_total) {
+    if (!ctx || !t || !out_total || (nq && !rays) || (capacity && (!out_values || !out_points))) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_bvh_query_ray: null argument", cudaSuccess);
+    return bvh_query_impl(ctx, t, BQ_RAY, rays, nq, out_offsets, out_values, out_points, 12, capacity, out_total);
+}
+int32_t bam3d_bvh_query_frustum(bam3d_ctx* ctx, const bam3d_bvh* t, const float* planes, uint64_t nq, uint64_t* out_offsets, uint32_t* out_values,
+                                uint8_t* out_relation, uint64_t capacity, uint64_t* out_total) {
+    if (!ctx || !t || !out_total || (nq && !planes) || (capacity && (!out_values || !out_relation))) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_bvh_query_frustum: null argument", cudaSuccess);
+    return bvh_query_impl(ctx, t, BQ_FRUSTUM, planes, nq, out_offsets, out_values, out_relation, 1, capacity, out_total);
+}
+
+int32_t bam3d_bvh_query_ray_closest(bam3d_ctx* ctx, const bam3d_bvh* t, const float* rays, uint64_t nq64, uint32_t* out_value, float* out_point_t) {
+    if (!ctx || !t || (nq64 && (!rays || !out_value || !out_point_t))) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_bvh_query_ray_closest: null argument", cudaSuccess);
+    int32_t rc;
+    if ((rc = check_n(ctx, nq64))) return rc;
+    if (nq64 == 0) return BAM3D_OK;
+    CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
+    const uint32_t nq = (uint32_t)nq64;
+    if ((rc = ctx->bp0.reserve(ctx, (size_t)nq * 24)) || (rc = ctx->bp1.reserve(ctx, (size_t)nq * 4)) || (rc = ctx->bp2.reserve(ctx, (size_t)nq * 16))) return rc;
+    CU_TRY(cudaMemcpyAsync(ctx->bp0.ptr, rays, (size_t)nq * 24, cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpyAsync(rays)");
+    { KernelTimer kt(ctx);
+      ctx->launches += launch_bvh_ray_closest(ctx->stream, bvh_view(t), (const float*)ctx->bp0.ptr, nq, (uint32_t*)ctx->bp1.ptr, (float*)ctx->bp2.ptr); }
+    if ((rc = check_launch(ctx, "bvh_ray_closest_kernel"))) return rc;
+    CU_TRY(cudaMemcpyAsync(out_value, ctx->bp1.ptr, (size_t)nq * 4, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(value)");
+    CU_TRY(cudaMemcpyAsync(out_point_t, ctx->bp2.ptr, (size_t)nq * 16, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(point)");
+    CU_TRY(cudaStreamSynchronize(ctx->stream), "bam3d_bvh_query_ray_closest");
+    return BAM3D_OK;
+}
+
+int32_t bam3d_bvh_find_collider_pairs(bam3d_ctx* ctx, const bam3d_bvh* t, const uint8_t* dirty, uint32_t* out_pairs, uint64_t capacity, uint64_t* out_count) {
+    if (!ctx || !t || !out_count || (t->n && !dirty) || (capacity && !out_pairs)) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_bvh_find_collider_pairs: null argument", cudaSuccess);
+    CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
+    *out_count = 0;
+    const uint32_t n = t->n;
+    if (n == 0) return BAM3D_OK;
+    int32_t rc;
+    const size_t scan_bytes = scan_tmp_bytes(n);
+    if ((rc = ctx->bp0.reserve(ctx, n)) || (rc = ctx->bp1.reserve(ctx, ((size_t)n + 1) * 4)) || (rc = ctx->bp2.reserve(ctx, ((size_t)n + 1) * 8)) ||
+        (rc = ctx->cub_tmp.reserve(ctx, scan_bytes))) return rc;
+    uint8_t* d_dirty = (uint8_t*)ctx->bp0.ptr;
+    uint32_t* d_counts = (uint32_t*)ctx->bp1.ptr;
+    unsigned long long* d_offsets = (unsigned long long*)ctx->bp2.ptr;
+    CU_TRY(cudaMemcpyAsync(d_dirty, dirty, n, cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpyAsync(dirty)");
+    cudaMemsetAsync(d_counts + n, 0, 4, ctx->stream);
+    BvhDev T = bvh_view(t);
+    { KernelTimer kt(ctx);
+      ctx->launches += launch_bvh_collider_pairs(ctx->stream, T, t->d_aabbs, d_dirty, d_counts, nullptr, nullptr); }
+    ctx->launches += launch_exclusive_scan_u32_to_u64(ctx->stream, d_counts, d_offsets, n, ctx->cub_tmp.ptr, scan_bytes);
+    if ((rc = check_launch(ctx, "bvh collider pairs (count)"))) return rc;
+    unsigned long long total = 0;
+    CU_TRY(cudaMemcpyAsync(&total, d_offsets + n, 8, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(total)");
+    CU_TRY(cudaStreamSynchronize(ctx->stream), "bvh collider pairs (count)");
+    *out_count = total;
+    if (total > capacity) return b3_fail(ctx, BAM3D_ERR_CAPACITY, "bam3d_bvh_find_collider_pairs: output capacity too small", cudaSuccess);
+    if (total == 0) return BAM3D_OK;
+    const size_t sort_bytes = sort_u64_tmp_bytes(total);
+    if ((rc = ctx->bp3.reserve(ctx, total * 8 * 2)) || (rc = ctx->bp4.reserve(ctx, total * 8)) || (rc = ctx->cub_tmp.reserve(ctx, sort_bytes > scan_bytes ? sort_bytes : scan_bytes))) return rc;
+    unsigned long long* keys = (unsigned long long*)ctx->bp3.ptr;
+    { KernelTimer kt(ctx);
+      ctx->launches += launch_bvh_collider_pairs(ctx->stream, T, t->d_aabbs, d_dirty, d_counts, d_offsets, keys); }
+    bool in_alt = false;
+    ctx->launches += launch_sort_u64(ctx->stream, keys, keys + total, total, ctx->cub_tmp.ptr, sort_bytes, &in_alt);
+    ctx->launches += launch_unpack_pairs(ctx->stream, in_alt ? keys + total : keys, total, (uint2*)ctx->bp4.ptr, true);
+    if ((rc = check_launch(ctx, "bvh collider pairs (fill)"))) return rc;
+    CU_TRY(cudaMemcpyAsync(out_pairs, ctx->bp4.ptr, total * 8, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(pairs)");
+    CU_TRY(cudaStreamSynchronize(ctx->stream), "bam3d_bvh_find_collider_pairs");
+    return BAM3D_OK;
+}
+
+}  // extern "C"

@@ -173,3 +173,52 @@ def all_kinds_pairs(n, s=1.5, seed=0xB3D000AA, start=0):
     """Parity-test scene touching every analytic primitive kind, including Particle, Quad and Capsule."""
     kinds = (_ffi.KIND_PARTICLE, _ffi.KIND_QUAD, _ffi.KIND_SPHERE, _ffi.KIND_CUBOID, _ffi.KIND_CYLINDER, _ffi.KIND_CAPSULE)
     return mixed_pairs(n, s=s, seed=seed, start=start, kinds=kinds)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# broad phase (C4)
+# ---------------------------------------------------------------------------------------------------------
+def aabb_scene(n, seed=SEED_C4, start=0, density=4.0, extent=None):
+    """n Aabb3: centres U[0, L]^3, half-extents U[0.1, 0.5]^3. C4 uses L = 100 for n = 2^22 (density 4 boxes per unit
+    volume, ~7 overlaps per box); smaller n keep that density unless `extent` is given."""
+    L = float(extent) if extent is not None else (n / density) ** (1.0 / 3.0)
+    idx = np.arange(start, start + n, dtype=np.uint64)
+    c = np.stack([uniform(seed, 100 + k, idx, 0.0, L) for k in range(3)], axis=1)
+    h = np.stack([uniform(seed, 103 + k, idx, 0.1, 0.5) for k in range(3)], axis=1)
+    return np.concatenate([(c - h).astype(np.float32), (c + h).astype(np.float32)], axis=1), L
+
+
+def rays(nq, L, seed=SEED_C4, start=0):
+    """Rays with origin U in the volume and direction uniform on the sphere: nq x (origin.xyz, direction.xyz)."""
+    idx = np.arange(start, start + nq, dtype=np.uint64)
+    o = np.stack([uniform(seed, 110 + k, idx, 0.0, L) for k in range(3)], axis=1)
+    d = np.stack([gaussian(seed, 113 + k, idx) for k in range(3)], axis=1)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    return np.concatenate([o, d.astype(np.float32)], axis=1).astype(np.float32)
+
+
+def perspective_rh_gl(fov_y, aspect, z_near, z_far):
+    """glam Mat4::perspective_rh_gl as a column-major 16-float array (f32 arithmetic)."""
+    f32 = np.float32
+    inv_length = f32(1.0) / (f32(z_near) - f32(z_far))
+    f = f32(1.0) / np.tan(f32(0.5) * f32(fov_y), dtype=np.float32)
+    a = f / f32(aspect)
+    b = (f32(z_near) + f32(z_far)) * inv_length
+    c = (f32(2.0) * f32(z_near) * f32(z_far)) * inv_length
+    return np.array([a, 0, 0, 0, 0, f, 0, 0, 0, 0, b, -1, 0, 0, c, 0], dtype=np.float32)
+
+
+def view_projections(nq, L, seed=SEED_C4, start=0):
+    """nq projection * view matrices: perspective_rh_gl(60 deg, 16/9, 0.1, 50) times a random rigid view."""
+    idx = np.arange(start, start + nq, dtype=np.uint64)
+    q = random_quat(seed, 120, idx)
+    t = np.stack([uniform(seed, 125 + k, idx, 0.0, L) for k in range(3)], axis=1)
+    view = mat4_from_rotation_translation(q, -t).reshape(nq, 4, 4)  # column-major: [col][row]
+    proj = perspective_rh_gl(np.float32(np.pi / 3), 16.0 / 9.0, 0.1, 50.0).reshape(4, 4)
+    # column-major product P * V: result column j = P * V[:, j]
+    P = proj.T.astype(np.float32)  # row-major matrix
+    out = np.empty((nq, 16), dtype=np.float32)
+    for k in range(nq):
+        V = view[k].T
+        out[k] = (P @ V).T.reshape(16)
+    return out

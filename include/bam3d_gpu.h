@@ -160,6 +160,64 @@ int32_t bam3d_compact_contacts_dev(bam3d_ctx* ctx, const bam3d_contact* d_contac
                                    uint64_t n, uint64_t pair_index_base, bam3d_contact40* d_out, uint64_t capacity,
                                    uint64_t* d_count);
 
+
+/* ---- broad phase ---------------------------------------------------------------------------------------- */
+/* Aabb3 values are 6 f32: min.xyz, max.xyz (volume/aabb/aabb3.rs:15-21). NaN bounds are not supported (the
+ * reference's sort comparator treats NaN as Equal, which is not an ordering). */
+
+/* SweepAndPrune3::find_collider_pairs (algorithm/broad_phase/sweep_prune.rs:69-128). *inout_sweep_axis is the
+ * SweepAndPrune's sweep_axis state (:28,:42-52): read for this call, replaced by the axis Variance3 picks for the next
+ * one (:123-125). The reference re-sorts the caller's slice in place (stable, by (min, max) on the sweep axis) and
+ * returns indices into the SORTED slice; here out_perm[k] = index in `aabbs` of the box at sorted position k (may be
+ * NULL), and out_pairs holds (i, j), i < j, sorted positions, in the reference's emission order (j ascending, then i).
+ * The pair set is every strictly overlapping pair (aabb3.rs:237-244). If more than `capacity` pairs exist the call
+ * returns BAM3D_ERR_CAPACITY with *out_count = the number required (the axis is left unchanged). */
+int32_t bam3d_sap_find_pairs(bam3d_ctx* ctx, const float* aabbs, uint64_t n, int32_t* inout_sweep_axis, uint32_t* out_perm,
+                             uint32_t* out_pairs, uint64_t capacity, uint64_t* out_count);
+/* same with device buffers (d_perm may be NULL); synchronises once internally to size the final pair sort */
+int32_t bam3d_sap_find_pairs_dev(bam3d_ctx* ctx, const float* d_aabbs, uint64_t n, int32_t* inout_sweep_axis,
+                                 uint32_t* d_perm, uint32_t* d_pairs, uint64_t capacity, uint64_t* out_count);
+
+/* ComputeBound<Aabb3> of every packed primitive (sphere.rs:27-34, cuboid.rs:66-73, cylinder.rs:64-71,
+ * capsule.rs:51-58, quad.rs:62-69, polyhedron.rs:84-86, primitive3.rs:83-96) moved to world space with
+ * Aabb::transform (aabb3.rs:89-96): n x 6 f32. */
+int32_t bam3d_shapes_world_aabbs(bam3d_ctx* ctx, const bam3d_shapes* shapes, float* out_aabbs);
+int32_t bam3d_shapes_world_aabbs_dev(bam3d_ctx* ctx, const bam3d_shapes* shapes, float* d_out_aabbs);
+
+/* Static BVH over n values' bounds, answering DynamicBoundingVolumeTree::query_for_indices (dbvt/mod.rs:481-515).
+ * Value index k = position in `aabbs` (the tree's `values` order). The reference's insert / remove / rotate
+ * maintenance (dbvt/mod.rs:531-1235) is not reproduced: its tree shape is randomised (rand::thread_rng, :901) and
+ * query result SETS do not depend on the shape. Results of one query are returned in the device tree's traversal
+ * order (deterministic for given boxes); compare with the reference as sets. */
+int32_t bam3d_bvh_build(bam3d_ctx* ctx, const float* aabbs, uint64_t n, bam3d_bvh** out);
+int32_t bam3d_bvh_build_dev(bam3d_ctx* ctx, const float* d_aabbs, uint64_t n, bam3d_bvh** out);
+void bam3d_bvh_free(bam3d_ctx* ctx, bam3d_bvh* bvh);
+uint32_t bam3d_bvh_count(const bam3d_bvh* bvh);
+/* Variable-length results: hits of query q are out_values[out_offsets[q] .. out_offsets[q + 1]) (out_offsets has nq + 1
+ * entries, may be NULL). If the total exceeds `capacity` the call returns BAM3D_ERR_CAPACITY with *out_total (and
+ * out_offsets) filled, so the caller can size its buffers and call again. */
+/* DiscreteVisitor (dbvt/visitor.rs:57-90): values whose bound strictly overlaps the query Aabb3 (nq x 6 f32). */
+int32_t bam3d_bvh_query_aabb(bam3d_ctx* ctx, const bam3d_bvh* bvh, const float* queries, uint64_t nq, uint64_t* out_offsets,
+                             uint32_t* out_values, uint64_t capacity, uint64_t* out_total);
+/* ContinuousVisitor<Ray> == query_ray (dbvt/util.rs:114-129): rays are nq x (origin.xyz, direction.xyz); out_points holds
+ * the slab-test entry point per hit (aabb3.rs:165-195), 3 f32 each. */
+int32_t bam3d_bvh_query_ray(bam3d_ctx* ctx, const bam3d_bvh* bvh, const float* rays, uint64_t nq, uint64_t* out_offsets,
+                            uint32_t* out_values, float* out_points, uint64_t capacity, uint64_t* out_total);
+/* FrustumVisitor (dbvt/visitor.rs:99-134): planes are nq x 6 x (n.xyz, d) in the order left, right, bottom, top, near,
+ * far (bam3d_frustum_from_mat4); out_relation is Relation as u8: 0 In, 1 Cross (Out is never reported). */
+int32_t bam3d_bvh_query_frustum(bam3d_ctx* ctx, const bam3d_bvh* bvh, const float* planes, uint64_t nq, uint64_t* out_offsets,
+                                uint32_t* out_values, uint8_t* out_relation, uint64_t capacity, uint64_t* out_total);
+/* query_ray_closest (dbvt/util.rs:77-103): out_value[q] = value index or 0xFFFFFFFF (None); out_point_t[q] = point.xyz, t.
+ * Exact ties in t resolve to the lowest value index (the reference keeps the first in its randomised traversal order). */
+int32_t bam3d_bvh_query_ray_closest(bam3d_ctx* ctx, const bam3d_bvh* bvh, const float* rays, uint64_t nq, uint32_t* out_value,
+                                    float* out_point_t);
+/* DbvtBroadPhase::find_collider_pairs (algorithm/broad_phase/dbvt.rs:26-63): every value with dirty[k] != 0 is queried
+ * against the tree; out_pairs = sorted unique (low, high) value-index pairs. */
+int32_t bam3d_bvh_find_collider_pairs(bam3d_ctx* ctx, const bam3d_bvh* bvh, const uint8_t* dirty, uint32_t* out_pairs,
+                                      uint64_t capacity, uint64_t* out_count);
+/* Frustum::from_mat4 (frustum.rs:46-75) on the host; out_planes = 6 x (n.xyz, d). Returns BAM3D_ERR_ARG for None. */
+int32_t bam3d_frustum_from_mat4(const float* mat4_cols, float* out_planes);
+
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
 uint64_t bam3d_ctx_launch_count(const bam3d_ctx* ctx);
 
