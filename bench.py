@@ -136,7 +136,14 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
+
+    def window(self, t0, t1):
+        """Keep only the samples taken inside [t0, t1] (the timed region)."""
+        self.rows = [r for r in self.rows if t0 - 0.05 <= r[0] <= t1 + 0.05]
+
+    def count(self, t0, t1):
+        return sum(1 for r in self.rows if t0 - 0.05 <= r[0] <= t1 + 0.05)
 
     def stop(self):
         if not self.proc:
@@ -148,7 +155,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for _, r in self.rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 6:
                 continue
@@ -193,7 +200,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     import bam3d_b200 as b3
-    from bam3d_b200 import build
+    from bam3d_b200 import build, multi
     build.build()
 
     wl, n = args.workload, args.pairs
@@ -227,9 +234,7 @@ def run_ours(args):
             # compact hits, then all-gather the compacted Contact40 records over NCCL (variable length: counts first)
             gjk.compact_contacts_dev(p(d_contacts), p(d_status), n, rank * n, p(d_compact), n, p(d_count))
             with torch.cuda.stream(ext):
-                dist.all_gather_into_tensor(counts, d_count)
-                m = int(counts.max().item())
-                dist.all_gather_into_tensor(gathered[: world * m * 10], d_compact[: m * 10])
+                multi.gather_contacts(d_compact, d_count, counts_buf=counts, out=gathered)
 
     def sync_all():
         ctx.synchronize()
@@ -239,24 +244,42 @@ def run_ours(args):
             torch.cuda.synchronize()
 
     # ---- resident throughput ------------------------------------------------------------------------------
+    sampler = ClockSampler(local_rank) if rank == 0 else None  # nvidia-smi needs ~1 s to start: launch it before warm-up
     for _ in range(args.warmup):
         step_resident()
     sync_all()
     ctx.set_option("timing", 1)
     ctx.read_timing()
     launches0 = ctx.launch_count
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.time()
     ev0.record(ext)
     for _ in range(args.steps):
         step_resident()
     ev1.record(ext)
     sync_all()
+    w1 = time.time()
     ms = ev0.elapsed_time(ev1)
     kernel_ms, kernel_calls = ctx.read_timing()
     ctx.set_option("timing", 0)
     launches = ctx.launch_count - launches0
-    clocks = sampler.stop() if sampler else None
+    clocks = None
+    if sampler:
+        clock_note = "sampled during the timed region"
+        if sampler.count(w0, w1) < 3:
+            # the timed region is shorter than nvidia-smi's sampling period: keep the GPU under the same load for ~1.5 s
+            # (untimed) so that the clocks reported are clocks under this workload
+            clock_note = "timed region shorter than the sampling period: sampled during an untimed repeat of the same steps"
+            w0 = time.time()
+            while time.time() - w0 < 1.5:
+                step_resident()
+                ctx.synchronize()
+            w1 = time.time()
+        sampler.window(w0, w1)
+        clocks = sampler.stop()
+        clocks["note"] = clock_note
+    if world > 1:
+        dist.barrier()
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
