@@ -1,0 +1,213 @@
+// bam3d.hpp — header-only C++17 host layer over the C ABI (bam3d_gpu.h), mirroring the public interface of the
+// reference crate for the accelerated path: same type and method names, argument meaning and None/Some behaviour.
+//   primitives            reference src/primitive/*.rs          ->  bam3d::Primitive3 (Sphere, Cuboid, Cube, Cylinder, ...)
+//   Contact / strategy    reference src/contact.rs:12-69        ->  bam3d::Contact, bam3d::CollisionStrategy
+//   GJK                   reference src/algorithm/minkowski/gjk/mod.rs:32-524
+//   SweepAndPrune3        reference src/algorithm/broad_phase/sweep_prune.rs:27-128
+//   DBVT queries          reference src/dbvt/mod.rs:451-515, dbvt/visitor.rs, dbvt/util.rs
+// The reference is Rust; no Rust toolchain exists in this build image, so this C++ layer (the language the image does
+// have) is the compiled host side, and rust/ holds the source of the equivalent Rust shim.
+// There is no CPU fallback: every call runs on the GPU or throws bam3d::Error.
+#pragma once
+#include <array>
+#include <cstdint>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "bam3d_gpu.h"
+
+namespace bam3d {
+
+struct Error : std::runtime_error {
+    int32_t code;
+    Error(int32_t c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+using Vec3 = std::array<float, 3>;
+using Mat4 = std::array<float, 16>;  // glam Mat4::to_cols_array (column-major)
+
+inline Mat4 mat4_from_translation(float x, float y, float z) { return {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, x, y, z, 1}; }
+
+enum class CollisionStrategy : int32_t { FullResolution = BAM3D_FULL_RESOLUTION, CollisionOnly = BAM3D_COLLISION_ONLY };
+
+struct Contact {  // contact.rs:22-38
+    CollisionStrategy strategy;
+    Vec3 normal;
+    float penetration_depth;
+    Vec3 contact_point;
+    float time_of_impact;
+};
+
+// enum Primitive3 (primitive/primitive3.rs:16-33) as a tagged value; constructors follow the reference's `new`.
+struct Primitive3 {
+    uint8_t kind = BAM3D_KIND_PARTICLE;
+    std::array<float, 4> params{0, 0, 0, 0};
+    std::vector<float> vertices;  // ConvexPolyhedron only (xyz triples)
+    static Primitive3 Particle() { return {}; }
+    static Primitive3 Sphere(float radius) { Primitive3 p; p.kind = BAM3D_KIND_SPHERE; p.params = {radius, 0, 0, 0}; return p; }
+    static Primitive3 Cuboid(float dx, float dy, float dz) { Primitive3 p; p.kind = BAM3D_KIND_CUBOID; p.params = {dx / 2.f, dy / 2.f, dz / 2.f, 0}; return p; }
+    static Primitive3 Cube(float d) { return Cuboid(d, d, d); }
+    static Primitive3 Quad(float dx, float dy) { Primitive3 p; p.kind = BAM3D_KIND_QUAD; p.params = {dx / 2.f, dy / 2.f, 0, 0}; return p; }
+    static Primitive3 Cylinder(float half_height, float radius) { Primitive3 p; p.kind = BAM3D_KIND_CYLINDER; p.params = {half_height, radius, 0, 0}; return p; }
+    static Primitive3 Capsule(float half_height, float radius) { Primitive3 p; p.kind = BAM3D_KIND_CAPSULE; p.params = {half_height, radius, 0, 0}; return p; }
+    static Primitive3 ConvexPolyhedron(std::vector<float> xyz) { Primitive3 p; p.kind = BAM3D_KIND_POLYHEDRON; p.vertices = std::move(xyz); return p; }
+};
+
+class Context {
+public:
+    explicit Context(int device = 0) {
+        int32_t rc = bam3d_ctx_create(device, &h_);
+        if (rc != BAM3D_OK) throw Error(rc, "bam3d_ctx_create failed: no usable CUDA device (there is no CPU fallback)");
+    }
+    ~Context() { bam3d_ctx_destroy(h_); }
+    Context(const Context&) = delete;
+    Context& operator=(const Context&) = delete;
+    bam3d_ctx* handle() const { return h_; }
+    void check(int32_t rc) const { if (rc != BAM3D_OK) throw Error(rc, bam3d_last_error(h_)); }
+private:
+    bam3d_ctx* h_ = nullptr;
+};
+
+// Primitives + transforms packed into device buffers.
+class ShapeSet {
+public:
+    ShapeSet(const Context& ctx, const std::vector<Primitive3>& prims, const std::vector<Mat4>& xforms) : ctx_(ctx) {
+        const uint32_t n = (uint32_t)prims.size();
+        std::vector<uint8_t> kind(n);
+        std::vector<float> params(4 * (size_t)n), xf(16 * (size_t)n), verts;
+        std::vector<uint32_t> mesh_id(n, 0), offsets{0};
+        for (uint32_t i = 0; i < n; ++i) {
+            kind[i] = prims[i].kind;
+            for (int k = 0; k < 4; ++k) params[4 * i + k] = prims[i].params[k];
+            for (int k = 0; k < 16; ++k) xf[16 * i + k] = xforms[i][k];
+            if (prims[i].kind == BAM3D_KIND_POLYHEDRON) {
+                mesh_id[i] = (uint32_t)offsets.size() - 1;
+                verts.insert(verts.end(), prims[i].vertices.begin(), prims[i].vertices.end());
+                offsets.push_back((uint32_t)(verts.size() / 3));
+            }
+        }
+        if (offsets.size() > 1) ctx_.check(bam3d_meshes_upload(ctx_.handle(), verts.data(), offsets.data(), (uint32_t)offsets.size() - 1, &meshes_));
+        ctx_.check(bam3d_shapes_upload(ctx_.handle(), kind.data(), params.data(), xf.data(), mesh_id.data(), n, meshes_, &h_));
+    }
+    ~ShapeSet() { bam3d_shapes_free(ctx_.handle(), h_); bam3d_meshes_free(ctx_.handle(), meshes_); }
+    ShapeSet(const ShapeSet&) = delete;
+    ShapeSet& operator=(const ShapeSet&) = delete;
+    bam3d_shapes* handle() const { return h_; }
+    void set_transforms(const std::vector<Mat4>& xforms) { ctx_.check(bam3d_shapes_set_transforms(ctx_.handle(), h_, xforms.data()->data())); }
+private:
+    const Context& ctx_;
+    bam3d_shapes* h_ = nullptr;
+    bam3d_meshes* meshes_ = nullptr;
+};
+
+using Pair = std::pair<uint32_t, uint32_t>;
+
+// Gilbert-Johnson-Keerthi narrow phase (gjk/mod.rs:24-58).
+class GJK {
+public:
+    explicit GJK(const Context& ctx) : ctx_(ctx) { bam3d_default_settings(&s_); }                     // GJK::new()
+    GJK(const Context& ctx, float distance_tolerance, float continuous_tolerance, float epa_tolerance,  // new_with_settings
+        uint32_t max_iterations) : ctx_(ctx) {
+        bam3d_default_settings(&s_);
+        s_.distance_tolerance = distance_tolerance; s_.continuous_tolerance = continuous_tolerance;
+        s_.epa_tolerance = epa_tolerance; s_.max_iterations = max_iterations;
+    }
+
+    // ---- batched additions ----
+    std::vector<uint8_t> intersect_batch(const ShapeSet& shapes, const std::vector<Pair>& pairs) const {
+        std::vector<uint8_t> st(pairs.size());
+        ctx_.check(bam3d_gjk_intersect(ctx_.handle(), shapes.handle(), flat(pairs), pairs.size(), &s_, st.data()));
+        return st;
+    }
+    std::vector<std::optional<Contact>> intersection_batch(CollisionStrategy strategy, const ShapeSet& shapes, const std::vector<Pair>& pairs) const {
+        std::vector<uint8_t> st(pairs.size());
+        std::vector<bam3d_contact> c(pairs.size());
+        ctx_.check(bam3d_gjk_contact(ctx_.handle(), shapes.handle(), flat(pairs), pairs.size(), &s_, (int32_t)strategy, c.data(), st.data()));
+        return to_optional(strategy, c, st);
+    }
+    // Some(x): x.first = what the reference returns (the residual dp - d0), x.second = the geometric distance
+    std::vector<std::optional<std::pair<float, float>>> distance_batch(const ShapeSet& shapes, const std::vector<Pair>& pairs) const {
+        std::vector<uint8_t> st(pairs.size());
+        std::vector<float> ref(pairs.size()), dist(pairs.size());
+        ctx_.check(bam3d_gjk_distance(ctx_.handle(), shapes.handle(), flat(pairs), pairs.size(), &s_, ref.data(), dist.data(), st.data()));
+        std::vector<std::optional<std::pair<float, float>>> out(pairs.size());
+        for (size_t i = 0; i < pairs.size(); ++i) if (st[i] == BAM3D_STATUS_OK) out[i] = std::make_pair(ref[i], dist[i]);
+        return out;
+    }
+    std::vector<std::optional<Contact>> intersection_time_of_impact_batch(const ShapeSet& start, const ShapeSet& end, const std::vector<Pair>& pairs) const {
+        std::vector<uint8_t> st(pairs.size());
+        std::vector<bam3d_contact> c(pairs.size());
+        ctx_.check(bam3d_gjk_time_of_impact(ctx_.handle(), start.handle(), end.handle(), flat(pairs), pairs.size(), &s_, c.data(), st.data()));
+        return to_optional(CollisionStrategy::FullResolution, c, st);
+    }
+
+    // ---- the reference's scalar methods (batch of one) ----
+    bool intersect(const Primitive3& left, const Mat4& lt, const Primitive3& right, const Mat4& rt) const {  // gjk/mod.rs:74
+        ShapeSet s(ctx_, {left, right}, {lt, rt});
+        return intersect_batch(s, {{0, 1}})[0] == BAM3D_STATUS_OK;
+    }
+    std::optional<Contact> intersection(CollisionStrategy strategy, const Primitive3& left, const Mat4& lt, const Primitive3& right, const Mat4& rt) const {  // :317
+        ShapeSet s(ctx_, {left, right}, {lt, rt});
+        return intersection_batch(strategy, s, {{0, 1}})[0];
+    }
+    std::optional<float> distance(const Primitive3& left, const Mat4& lt, const Primitive3& right, const Mat4& rt) const {  // :232
+        ShapeSet s(ctx_, {left, right}, {lt, rt});
+        auto d = distance_batch(s, {{0, 1}})[0];
+        return d ? std::optional<float>(d->first) : std::nullopt;
+    }
+    std::optional<Contact> intersection_time_of_impact(const Primitive3& left, const Mat4& lt_start, const Mat4& lt_end, const Primitive3& right,
+                                                       const Mat4& rt_start, const Mat4& rt_end) const {  // :130
+        ShapeSet s0(ctx_, {left, right}, {lt_start, rt_start}), s1(ctx_, {left, right}, {lt_end, rt_end});
+        return intersection_time_of_impact_batch(s0, s1, {{0, 1}})[0];
+    }
+
+private:
+    static const uint32_t* flat(const std::vector<Pair>& p) { return reinterpret_cast<const uint32_t*>(p.data()); }
+    static std::vector<std::optional<Contact>> to_optional(CollisionStrategy strategy, const std::vector<bam3d_contact>& c, const std::vector<uint8_t>& st) {
+        std::vector<std::optional<Contact>> out(c.size());
+        for (size_t i = 0; i < c.size(); ++i)
+            if (st[i] == BAM3D_STATUS_OK)
+                out[i] = Contact{strategy, {c[i].normal[0], c[i].normal[1], c[i].normal[2]}, c[i].penetration_depth,
+                                 {c[i].contact_point[0], c[i].contact_point[1], c[i].contact_point[2]}, c[i].time_of_impact};
+        return out;
+    }
+    const Context& ctx_;
+    bam3d_gjk_settings s_;
+};
+
+struct Aabb3 { Vec3 min, max; };  // volume/aabb/aabb3.rs:15-21 (6 contiguous f32)
+
+// SweepAndPrune3 (sweep_prune.rs:27-128): keeps sweep_axis across calls; re-sorts the caller's slice like the reference.
+class SweepAndPrune3 {
+public:
+    explicit SweepAndPrune3(const Context& ctx, int sweep_axis = 0) : ctx_(ctx), axis_(sweep_axis) {}  // new / with_sweep_axis
+    int get_sweep_axis() const { return axis_; }
+    std::vector<std::pair<size_t, size_t>> find_collider_pairs(std::vector<Aabb3>& shapes) {
+        const uint64_t n = shapes.size();
+        std::vector<uint32_t> perm(n), pairs;
+        uint64_t cap = 8 * n + 1024, count = 0;
+        for (;;) {
+            pairs.resize(2 * cap);
+            int32_t axis = axis_;
+            int32_t rc = bam3d_sap_find_pairs(ctx_.handle(), reinterpret_cast<const float*>(shapes.data()), n, &axis, perm.data(), pairs.data(), cap, &count);
+            if (rc == BAM3D_ERR_CAPACITY && count > cap) { cap = count; continue; }
+            ctx_.check(rc);
+            axis_ = axis;
+            break;
+        }
+        std::vector<Aabb3> sorted(n);
+        for (uint64_t k = 0; k < n; ++k) sorted[k] = shapes[perm[k]];
+        shapes.swap(sorted);  // "The shapes list might have been resorted" (sweep_prune.rs:65-68)
+        std::vector<std::pair<size_t, size_t>> out(count);
+        for (uint64_t k = 0; k < count; ++k) out[k] = {pairs[2 * k], pairs[2 * k + 1]};
+        return out;
+    }
+private:
+    const Context& ctx_;
+    int axis_;
+};
+
+}  // namespace bam3d

@@ -1,0 +1,99 @@
+//! Rust shim over the C ABI of include/bam3d_gpu.h: packs bam3d primitives and glam `Mat4`s into the SoA host arrays
+//! the ABI takes and exposes batched `GJK` / `SweepAndPrune3` calls with the crate's own types.
+//! SOURCE ONLY: this repository's build image has no cargo / rustc, so this file is not compiled or tested here; the
+//! compiled host layer with the same shape is include/bam3d.hpp (C++), exercised by tests/cpp/kat_gpu.cpp.
+use bam3d::{Aabb3, CollisionStrategy, Contact, Primitive3};
+use glam::{Mat4, Vec3};
+use std::os::raw::{c_char, c_void};
+
+#[repr(C)]
+pub struct GjkSettings { pub distance_tolerance: f32, pub continuous_tolerance: f32, pub epa_tolerance: f32, pub max_iterations: u32, pub toi_iteration_cap: u32 }
+#[repr(C)] #[derive(Clone, Copy, Default)]
+pub struct RawContact { pub normal: [f32; 3], pub penetration_depth: f32, pub contact_point: [f32; 3], pub time_of_impact: f32 }
+
+#[allow(non_camel_case_types)] type ctx = c_void;
+extern "C" {
+    fn bam3d_ctx_create(device: i32, out: *mut *mut ctx) -> i32;
+    fn bam3d_ctx_destroy(c: *mut ctx);
+    fn bam3d_last_error(c: *const ctx) -> *const c_char;
+    fn bam3d_default_settings(out: *mut GjkSettings);
+    fn bam3d_meshes_upload(c: *mut ctx, verts: *const f32, offsets: *const u32, n: u32, out: *mut *mut c_void) -> i32;
+    fn bam3d_shapes_upload(c: *mut ctx, kind: *const u8, params: *const f32, xform: *const f32, mesh_id: *const u32, n: u32,
+                           meshes: *const c_void, out: *mut *mut c_void) -> i32;
+    fn bam3d_shapes_set_transforms(c: *mut ctx, s: *mut c_void, xform: *const f32) -> i32;
+    fn bam3d_shapes_free(c: *mut ctx, s: *mut c_void);
+    fn bam3d_gjk_intersect(c: *mut ctx, s: *const c_void, pairs: *const u32, n: u64, cfg: *const GjkSettings, status: *mut u8) -> i32;
+    fn bam3d_gjk_contact(c: *mut ctx, s: *const c_void, pairs: *const u32, n: u64, cfg: *const GjkSettings, strategy: i32,
+                         out: *mut RawContact, status: *mut u8) -> i32;
+    fn bam3d_gjk_distance(c: *mut ctx, s: *const c_void, pairs: *const u32, n: u64, cfg: *const GjkSettings, ref_value: *mut f32,
+                          distance: *mut f32, status: *mut u8) -> i32;
+    fn bam3d_gjk_time_of_impact(c: *mut ctx, s0: *const c_void, s1: *const c_void, pairs: *const u32, n: u64, cfg: *const GjkSettings,
+                                out: *mut RawContact, status: *mut u8) -> i32;
+    fn bam3d_sap_find_pairs(c: *mut ctx, aabbs: *const f32, n: u64, axis: *mut i32, perm: *mut u32, pairs: *mut u32, cap: u64, count: *mut u64) -> i32;
+}
+
+pub struct Context(*mut ctx);
+impl Context {
+    pub fn new(device: i32) -> Result<Self, i32> { let mut h = std::ptr::null_mut(); let rc = unsafe { bam3d_ctx_create(device, &mut h) }; if rc == 0 { Ok(Context(h)) } else { Err(rc) } }
+}
+impl Drop for Context { fn drop(&mut self) { unsafe { bam3d_ctx_destroy(self.0) } } }
+
+/// Primitive3 -> (kind, params) of the ABI (include/bam3d_gpu.h BAM3D_KIND_*).
+fn pack(p: &Primitive3) -> (u8, [f32; 4]) {
+    match p {
+        Primitive3::Particle(_) => (0, [0.; 4]),
+        Primitive3::Quad(q) => (1, [q.half_dim().x(), q.half_dim().y(), 0., 0.]),
+        Primitive3::Sphere(s) => (2, [s.radius, 0., 0., 0.]),
+        Primitive3::Cuboid(c) => (3, [c.half_dim().x(), c.half_dim().y(), c.half_dim().z(), 0.]),
+        Primitive3::Cube(c) => (3, [c.half_dim(), c.half_dim(), c.half_dim(), 0.]),
+        Primitive3::Cylinder(c) => (4, [c.height() / 2., c.radius(), 0., 0.]),
+        Primitive3::Capsule(c) => (5, [c.height() / 2., c.radius(), 0., 0.]),
+        Primitive3::ConvexPolyhedron(_) => (6, [0.; 4]), // vertices go through bam3d_meshes_upload
+    }
+}
+
+pub struct ShapeSet<'a> { ctx: &'a Context, h: *mut c_void }
+impl<'a> ShapeSet<'a> {
+    pub fn new(ctx: &'a Context, shapes: &[(Primitive3, Mat4)]) -> Result<Self, i32> {
+        let n = shapes.len();
+        let (mut kind, mut params, mut xf) = (Vec::with_capacity(n), Vec::with_capacity(4 * n), Vec::with_capacity(16 * n));
+        for (p, t) in shapes { let (k, q) = pack(p); kind.push(k); params.extend_from_slice(&q); xf.extend_from_slice(&t.to_cols_array()); }
+        let mut h = std::ptr::null_mut();
+        let rc = unsafe { bam3d_shapes_upload(ctx.0, kind.as_ptr(), params.as_ptr(), xf.as_ptr(), std::ptr::null(), n as u32, std::ptr::null(), &mut h) };
+        if rc == 0 { Ok(ShapeSet { ctx, h }) } else { Err(rc) }
+    }
+}
+impl<'a> Drop for ShapeSet<'a> { fn drop(&mut self) { unsafe { bam3d_shapes_free(self.ctx.0, self.h) } } }
+
+/// Batched counterpart of `GJK::intersection` (gjk/mod.rs:317-341): one `Option<Contact>` per pair.
+pub fn intersection_batch(ctx: &Context, strategy: &CollisionStrategy, shapes: &ShapeSet, pairs: &[(u32, u32)]) -> Result<Vec<Option<Contact>>, i32> {
+    let mut cfg = GjkSettings { distance_tolerance: 0., continuous_tolerance: 0., epa_tolerance: 0., max_iterations: 0, toi_iteration_cap: 0 };
+    unsafe { bam3d_default_settings(&mut cfg) };
+    let (mut raw, mut st) = (vec![RawContact::default(); pairs.len()], vec![0u8; pairs.len()]);
+    let s = match strategy { CollisionStrategy::FullResolution => 0, CollisionStrategy::CollisionOnly => 1 };
+    let rc = unsafe { bam3d_gjk_contact(ctx.0, shapes.h, pairs.as_ptr() as *const u32, pairs.len() as u64, &cfg, s, raw.as_mut_ptr(), st.as_mut_ptr()) };
+    if rc != 0 { return Err(rc); }
+    Ok(raw.iter().zip(&st).map(|(c, &s)| if s == 0 {
+        let mut k = Contact::new_with_point(strategy.clone(), Vec3::new(c.normal[0], c.normal[1], c.normal[2]), c.penetration_depth,
+                                            Vec3::new(c.contact_point[0], c.contact_point[1], c.contact_point[2]));
+        k.time_of_impact = c.time_of_impact; Some(k) } else { None }).collect())
+}
+
+/// `SweepAndPrune3::find_collider_pairs` on the device: re-sorts `shapes` like the reference and returns indices into it.
+pub fn sap_find_collider_pairs(ctx: &Context, sweep_axis: &mut usize, shapes: &mut [Aabb3]) -> Result<Vec<(usize, usize)>, i32> {
+    let n = shapes.len();
+    let flat: Vec<f32> = shapes.iter().flat_map(|b| vec![b.min.x(), b.min.y(), b.min.z(), b.max.x(), b.max.y(), b.max.z()]).collect();
+    let (mut perm, mut cap, mut count, mut axis) = (vec![0u32; n], (8 * n + 1024) as u64, 0u64, *sweep_axis as i32);
+    let mut pairs;
+    loop {
+        pairs = vec![0u32; 2 * cap as usize];
+        let rc = unsafe { bam3d_sap_find_pairs(ctx.0, flat.as_ptr(), n as u64, &mut axis, perm.as_mut_ptr(), pairs.as_mut_ptr(), cap, &mut count) };
+        if rc == -4 && count > cap { cap = count; continue; }
+        if rc != 0 { return Err(rc); }
+        break;
+    }
+    let sorted: Vec<Aabb3> = perm.iter().map(|&k| shapes[k as usize]).collect();
+    shapes.copy_from_slice(&sorted);
+    *sweep_axis = axis as usize;
+    Ok((0..count as usize).map(|k| (pairs[2 * k] as usize, pairs[2 * k + 1] as usize)).collect())
+}

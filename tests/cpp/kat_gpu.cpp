@@ -1,0 +1,69 @@
+// The reference's GJK / EPA / SweepAndPrune unit tests (gjk/mod.rs:552-644, quad.rs:113-124), rewritten against the C++
+// host layer (include/bam3d.hpp) so that they read like the crate's own tests. Needs a GPU. Exit code 0 = all passed.
+#include <cmath>
+#include <cstdio>
+#include "../../include/bam3d.hpp"
+
+using namespace bam3d;
+static int fails = 0;
+#define CHECK(c) do { if (!(c)) { ++fails; std::printf("FAIL line %d: %s\n", __LINE__, #c); } } while (0)
+
+static Mat4 transform_3d(float x, float y, float z) { return mat4_from_translation(x, y, z); }  // angle_z = 0 in every KAT used
+
+int main() {
+    Context ctx(0);
+    GJK gjk(ctx);
+    {   // test_gjk_exact_3d
+        auto shape = Primitive3::Cuboid(1, 1, 1);
+        auto t = transform_3d(0, 0, 0);
+        CHECK(gjk.intersection(CollisionStrategy::FullResolution, shape, t, shape, t).has_value());
+        CHECK(!gjk.distance(shape, t, shape, t).has_value());
+    }
+    {   // test_gjk_sphere
+        auto shape = Primitive3::Sphere(1);
+        auto t = transform_3d(0, 0, 0);
+        CHECK(gjk.intersection(CollisionStrategy::FullResolution, shape, t, shape, t).has_value());
+        CHECK(gjk.distance(shape, t, shape, t).has_value());
+    }
+    {   // test_gjk_3d_hit
+        auto left = Primitive3::Cuboid(10, 10, 10), right = Primitive3::Cuboid(10, 10, 10);
+        auto lt = transform_3d(15, 0, 0), rt = transform_3d(7, 2, 0);
+        CHECK(gjk.intersect(left, lt, right, rt));
+        auto c = gjk.intersection(CollisionStrategy::FullResolution, left, lt, right, rt);
+        CHECK(c.has_value());
+        if (c) {
+            CHECK(c->normal[0] == -1.f && c->normal[1] == 0.f && c->normal[2] == 0.f);
+            CHECK(c->penetration_depth == 2.f);
+            CHECK(c->contact_point[0] == 10.f && c->contact_point[1] == 1.0000002f && c->contact_point[2] == 4.999999f);
+        }
+    }
+    {   // test_gjk_distance_3d (the reference returns the convergence residual; the geometric distance is 4)
+        auto left = Primitive3::Cuboid(10, 10, 10), right = Primitive3::Cuboid(10, 10, 10);
+        CHECK(!gjk.distance(left, transform_3d(15, 0, 0), right, transform_3d(7, 2, 0)).has_value());
+        ShapeSet s(ctx, {left, right}, {transform_3d(15, 0, 0), transform_3d(1, 0, 0)});
+        auto d = gjk.distance_batch(s, {{0, 1}})[0];
+        CHECK(d.has_value() && d->second == 4.f);
+    }
+    {   // test_gjk_time_of_impact_3d
+        auto left = Primitive3::Cuboid(10, 11, 10), right = Primitive3::Cuboid(10, 15, 10);
+        auto c = gjk.intersection_time_of_impact(left, transform_3d(0, 0, 0), transform_3d(30, 0, 0), right, transform_3d(15, 0, 0), transform_3d(15, 0, 0));
+        CHECK(c.has_value());
+        if (c) {
+            CHECK(c->time_of_impact == 0.16666667f);
+            CHECK(c->normal[0] == -1.f && c->normal[1] == 0.f && c->normal[2] == 0.f);
+            CHECK(c->penetration_depth == 0.f);
+            CHECK(c->contact_point[0] == 10.f && c->contact_point[1] == 0.f && c->contact_point[2] == 0.f);
+        }
+        CHECK(!gjk.intersection_time_of_impact(left, transform_3d(0, 0, 0), transform_3d(0, 0, 0), right, transform_3d(15, 0, 0), transform_3d(15, 0, 0)).has_value());
+    }
+    {   // SweepAndPrune3: strict overlap only; the slice is re-sorted; indices refer to the sorted slice
+        std::vector<Aabb3> shapes = {{{5, 0, 0}, {6, 1, 1}}, {{0, 0, 0}, {1, 1, 1}}, {{0.5f, 0.5f, 0.5f}, {1.5f, 1.5f, 1.5f}}, {{1, 0, 0}, {2, 1, 1}}};
+        SweepAndPrune3 sap(ctx);
+        auto pairs = sap.find_collider_pairs(shapes);
+        CHECK(shapes[0].min[0] == 0.f && shapes[1].min[0] == 0.5f && shapes[2].min[0] == 1.f && shapes[3].min[0] == 5.f);
+        CHECK(pairs.size() == 2);
+        if (pairs.size() == 2) { CHECK(pairs[0].first == 0 && pairs[0].second == 1); CHECK(pairs[1].first == 1 && pairs[1].second == 2); }
+    }
+    std::printf("kat_gpu: %s\n", fails ? "FAILED" : "all passed");
+    return fails ? 1 : 0;
+}
