@@ -42,7 +42,8 @@ __global__ void __launch_bounds__(BT) sap_keys_kernel(const float* __restrict__ 
 }
 
 __global__ void __launch_bounds__(BT) sap_gather_kernel(const float* __restrict__ aabbs, const uint32_t* __restrict__ perm, uint32_t n,
-                                                        float4* __restrict__ lo, float4* __restrict__ hi, uint32_t* __restrict__ out_perm) {
+                                                        float4* __restrict__ lo, float4* __restrict__ hi, uint32_t* __restrict__ out_perm,
+                                                        float* __restrict__ sorted6) {
     uint32_t k = blockIdx.x * BT + threadIdx.x;
     if (k >= n) return;
     uint32_t src = perm[k];
@@ -50,6 +51,30 @@ __global__ void __launch_bounds__(BT) sap_gather_kernel(const float* __restrict_
     lo[k] = make_float4(b[0], b[1], b[2], 0.f);
     hi[k] = make_float4(b[3], b[4], b[5], 0.f);
     if (out_perm) out_perm[k] = src;
+    if (sorted6) {
+        float* o = sorted6 + 6 * (size_t)k;
+        o[0] = b[0]; o[1] = b[1]; o[2] = b[2]; o[3] = b[3]; o[4] = b[4]; o[5] = b[5];
+    }
+}
+
+// Number of (i, j) candidate tests the forward sweep would make: for every sorted slot i, the slots j > i whose
+// sweep-axis min is below i's max (binary search in the sorted mins). Decides sweep vs BVH strategy.
+__global__ void __launch_bounds__(BT) sap_candidates_kernel(const float4* __restrict__ lo, const float4* __restrict__ hi, uint32_t n, int axis,
+                                                            unsigned long long* __restrict__ total) {
+    uint32_t i = blockIdx.x * BT + threadIdx.x;
+    unsigned long long c = 0;
+    if (i < n) {
+        const float amax = comp(__ldg(hi + i), axis);
+        uint32_t a = i + 1, b = n;  // first j in (i, n) with min_j >= amax
+        while (a < b) {
+            uint32_t m = a + ((b - a) >> 1);
+            if (comp(__ldg(lo + m), axis) < amax) a = m + 1; else b = m;
+        }
+        c = a - (i + 1);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, off);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(total, c);
 }
 
 // Forward sweep. Block b owns sorted slots i in [128 b, 128 b + 128); it streams the following slots j through shared
@@ -118,32 +143,48 @@ __global__ void __launch_bounds__(BT) sap_sweep_kernel(const float4* __restrict_
 
 // Variance3 (sweep_prune.rs:166-216): c = (min + max) / 2; csum += c; csumsq += c * c, accumulated SEQUENTIALLY in
 // sorted order exactly as the reference's loop does (f32 addition is not associative, and the three axes of a
-// uniform scene are near-ties, so a tree reduction could pick a different axis). One warp: the lanes stage 1024
-// boxes at a time in shared memory, then every lane walks the tile in order (all lanes hold the same sums).
-// variance = csumsq * (csum * csum / n) — a product, not a difference, as in the reference (:203-204).
-__global__ void __launch_bounds__(32) sap_variance_kernel(const float4* __restrict__ lo, const float4* __restrict__ hi, uint32_t n,
-                                                          int* __restrict__ next_axis) {
-    constexpr int TILE = 1024;
-    __shared__ float cx[TILE], cy[TILE], cz[TILE];
-    float sx = 0.f, sy = 0.f, sz = 0.f, qx = 0.f, qy = 0.f, qz = 0.f;
-    for (uint32_t base = 0; base < n; base += TILE) {
+// uniform scene are near-ties, so a tree reduction could pick a different axis). The six running sums are six
+// independent dependency chains: block c of six walks the boxes in order for chain c (0..2 = csum.xyz, 3..5 =
+// csumsq.xyz); its 32 lanes stage 2048 centres at a time in shared memory, then every lane replays the chain.
+__global__ void __launch_bounds__(256) sap_variance_chain_kernel(const float4* __restrict__ lo, const float4* __restrict__ hi, uint32_t n,
+                                                                 float* __restrict__ sums) {
+    // Double buffered: warps 1..7 stage the next tile of centres (many loads in flight) while warp 0 replays the
+    // sequential chain over the current one — the chain (one dependent FADD per box) is the critical path.
+    constexpr int TILE = 2048;
+    __shared__ float cs[2][TILE];
+    const int chain = blockIdx.x, axis = chain % 3;
+    const bool squared = chain >= 3;
+    const int warp = threadIdx.x >> 5;
+    auto stage = [&](uint32_t base, float* dst, int first, int step) {
         const uint32_t cnt = min((uint32_t)TILE, n - base);
-        for (uint32_t t = threadIdx.x; t < cnt; t += 32) {
-            float4 l = __ldg(lo + base + t), h = __ldg(hi + base + t);
-            cx[t] = (l.x + h.x) / 2.0f; cy[t] = (l.y + h.y) / 2.0f; cz[t] = (l.z + h.z) / 2.0f;
+        for (uint32_t t = first; t < cnt; t += step) {
+            float c = (comp(__ldg(lo + base + t), axis) + comp(__ldg(hi + base + t), axis)) / 2.0f;
+            dst[t] = squared ? c * c : c;
         }
-        __syncwarp();
-#pragma unroll 4
-        for (uint32_t t = 0; t < cnt; ++t) {
-            float x = cx[t], y = cy[t], z = cz[t];
-            sx = sx + x; sy = sy + y; sz = sz + z;
-            qx = qx + x * x; qy = qy + y * y; qz = qz + z * z;
+    };
+    stage(0, cs[0], threadIdx.x, 256);
+    __syncthreads();
+    float acc = 0.f;
+    int cur = 0;
+    for (uint32_t base = 0; base < n; base += TILE, cur ^= 1) {
+        if (warp == 0) {
+            const uint32_t cnt = min((uint32_t)TILE, n - base);
+            const float* c = cs[cur];
+#pragma unroll 16
+            for (uint32_t t = 0; t < cnt; ++t) acc = acc + c[t];
+        } else if (base + TILE < n) {
+            stage(base + TILE, cs[cur ^ 1], threadIdx.x - 32, 224);
         }
-        __syncwarp();
+        __syncthreads();
     }
+    if (threadIdx.x == 0) sums[chain] = acc;
+}
+
+// variance = csumsq * (csum * csum / n) — a product, not a difference, as in the reference (:203-204); strict > from axis 0
+__global__ void sap_variance_axis_kernel(const float* __restrict__ sums, uint32_t n, int* __restrict__ next_axis) {
     if (threadIdx.x == 0) {
         const float fn = (float)n;
-        float vx = qx * (sx * sx / fn), vy = qy * (sy * sy / fn), vz = qz * (sz * sz / fn);
+        float vx = sums[3] * (sums[0] * sums[0] / fn), vy = sums[4] * (sums[1] * sums[1] / fn), vz = sums[5] * (sums[2] * sums[2] / fn);
         int ax = 0; float best = vx;
         if (vy > best) { ax = 1; best = vy; }
         if (vz > best) { ax = 2; best = vz; }
@@ -160,7 +201,7 @@ __global__ void __launch_bounds__(BT) unpack_pairs_kernel(const unsigned long lo
     pairs[k] = hi_first ? make_uint2(hi, lo) : make_uint2(lo, hi);
 }
 
-static int bits_for(uint32_t n) { int b = 1; while (b < 32 && (1ull << b) < n) ++b; return b; }
+int sap_bits_for(uint32_t n) { int b = 1; while (b < 32 && (1ull << b) < n) ++b; return b; }
 
 size_t sap_cub_tmp_bytes(uint32_t n, uint64_t pair_capacity) {
     size_t a = 0, b = 0;
@@ -169,30 +210,39 @@ size_t sap_cub_tmp_bytes(uint32_t n, uint64_t pair_capacity) {
     return (a > b ? a : b) + 256;
 }
 
-int launch_sap(cudaStream_t st, const float* d_aabbs, uint32_t n, int axis, const SapScratch& S, uint32_t* d_perm, uint2* d_pairs,
-               uint64_t capacity, unsigned long long* d_count, int* d_next_axis) {
-    (void)d_pairs;
-    cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), st);
-    if (n <= 1) return 0;  // sweep_prune.rs:76-78: no pairs, axis unchanged (the caller keeps its axis)
+int launch_sap_sort(cudaStream_t st, const float* d_aabbs, uint32_t n, int axis, const SapScratch& S, uint32_t* d_perm, float* d_sorted6,
+                    unsigned long long* d_candidates) {
     int launched = 0;
     const int g = (n + BT - 1) / BT;
     sap_keys_kernel<<<g, BT, 0, st>>>(d_aabbs, n, axis, S.keys_in, S.vals_in); ++launched;
     size_t tmp = S.cub_tmp_bytes;
-    cub::DeviceRadixSort::SortPairs(S.cub_tmp, tmp, S.keys_in, S.keys_out, S.vals_in, S.vals_out, (int)n, 0, 64, st); launched += 8;
-    sap_gather_kernel<<<g, BT, 0, st>>>(d_aabbs, S.vals_out, n, S.lo, S.hi, d_perm); ++launched;
-    sap_sweep_kernel<<<g, BT, 0, st>>>(S.lo, S.hi, n, axis, bits_for(n), S.pair_keys, capacity, d_count); ++launched;
-    sap_variance_kernel<<<1, 32, 0, st>>>(S.lo, S.hi, n, d_next_axis); ++launched;
+    cub::DeviceRadixSort::SortPairs(S.cub_tmp, tmp, S.keys_in, S.keys_out, S.vals_in, S.vals_out, (int)n, 0, 64, st); launched += 10;
+    sap_gather_kernel<<<g, BT, 0, st>>>(d_aabbs, S.vals_out, n, S.lo, S.hi, d_perm, d_sorted6); ++launched;
+    cudaMemsetAsync(d_candidates, 0, sizeof(unsigned long long), st);
+    sap_candidates_kernel<<<g, BT, 0, st>>>(S.lo, S.hi, n, axis, d_candidates); ++launched;
     return launched;
+}
+
+int launch_sap_variance(cudaStream_t st, const SapScratch& S, uint32_t n, float* d_sums, int* d_next_axis) {
+    sap_variance_chain_kernel<<<6, 256, 0, st>>>(S.lo, S.hi, n, d_sums);
+    sap_variance_axis_kernel<<<1, 32, 0, st>>>(d_sums, n, d_next_axis);
+    return 2;
+}
+
+int launch_sap_sweep(cudaStream_t st, uint32_t n, int axis, const SapScratch& S, uint64_t capacity, unsigned long long* d_count) {
+    cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), st);
+    sap_sweep_kernel<<<(n + BT - 1) / BT, BT, 0, st>>>(S.lo, S.hi, n, axis, sap_bits_for(n), S.pair_keys, capacity, d_count);
+    return 1;
 }
 
 int launch_sap_finish(cudaStream_t st, const SapScratch& S, uint64_t count, uint2* d_pairs, uint32_t n) {
     if (count == 0) return 0;
-    const int shift = bits_for(n);
+    const int shift = sap_bits_for(n);
     size_t tmp = S.cub_tmp_bytes;
     // reference emission order: shape_index (j) ascending, then active index (i) ascending (sweep_prune.rs:98-113)
     cub::DeviceRadixSort::SortKeys(S.cub_tmp, tmp, S.pair_keys, S.pair_keys_alt, (long long)count, 0, 2 * shift, st);
     unpack_pairs_kernel<<<(unsigned)((count + BT - 1) / BT), BT, 0, st>>>(S.pair_keys_alt, count, shift, d_pairs, 0);
-    return 7;
+    return 2 + (2 * shift + 7) / 8 + 1;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -577,14 +627,16 @@ int launch_bvh_ray_closest(cudaStream_t st, const BvhDev& T, const float* d_rays
 // DbvtBroadPhase::find_collider_pairs (broad_phase/dbvt.rs:26-63): every dirty value queries the tree with its own
 // bound (DiscreteVisitor); pairs are ordered (low, high) and unique. A pair of two dirty values is found from both
 // sides — it is emitted from the lower index only; the caller sorts the keys, which gives the reference's sorted list.
+// dirty == nullptr: every value is dirty (used by the BVH strategy of sweep-and-prune, where value index = sorted slot
+// and keys are packed (high << key_shift | low) to sort into the reference's (j, i) emission order).
 template <bool FILL>
 __global__ void __launch_bounds__(BT) bvh_collider_pairs_kernel(BvhDev T, const float* __restrict__ aabbs, const uint8_t* __restrict__ dirty,
                                                                 uint32_t* __restrict__ counts, const unsigned long long* __restrict__ offsets,
-                                                                unsigned long long* __restrict__ keys) {
+                                                                unsigned long long* __restrict__ keys, int key_shift) {
     uint32_t v = blockIdx.x * BT + threadIdx.x;
     if (v >= T.n) return;
     uint32_t cnt = 0;
-    if (dirty[v]) {
+    if (!dirty || dirty[v]) {
         const float* b = aabbs + 6 * (size_t)v;
         Query q;
         q.qlo = make_float4(b[0], b[1], b[2], 0.f); q.qhi = make_float4(b[3], b[4], b[5], 0.f);
@@ -600,8 +652,9 @@ __global__ void __launch_bounds__(BT) bvh_collider_pairs_kernel(BvhDev T, const 
             if (!accept<BQ_AABB>(q, mn, mx, pt, rel)) continue;
             if (node >= first_leaf) {
                 uint32_t h = __ldg(T.leaf_value + (node - first_leaf));
-                if (h != v && (!dirty[h] || v < h)) {
-                    if (FILL) keys[w++] = ((unsigned long long)min(v, h) << 32) | max(v, h);
+                if (h != v && ((dirty && !dirty[h]) || v < h)) {
+                    if (FILL) keys[w++] = key_shift ? (((unsigned long long)max(v, h) << key_shift) | min(v, h))
+                                                    : (((unsigned long long)min(v, h) << 32) | max(v, h));
                     ++cnt;
                 }
             } else if (sp <= 62) {
@@ -615,11 +668,11 @@ __global__ void __launch_bounds__(BT) bvh_collider_pairs_kernel(BvhDev T, const 
 }
 
 int launch_bvh_collider_pairs(cudaStream_t st, const BvhDev& T, const float* d_aabbs, const uint8_t* d_dirty, uint32_t* d_counts,
-                              const unsigned long long* d_offsets, unsigned long long* d_pair_keys) {
+                              const unsigned long long* d_offsets, unsigned long long* d_pair_keys, int key_shift) {
     if (T.n == 0) return 0;
     const int g = (T.n + BT - 1) / BT;
-    if (d_offsets) bvh_collider_pairs_kernel<true><<<g, BT, 0, st>>>(T, d_aabbs, d_dirty, d_counts, d_offsets, d_pair_keys);
-    else bvh_collider_pairs_kernel<false><<<g, BT, 0, st>>>(T, d_aabbs, d_dirty, d_counts, d_offsets, d_pair_keys);
+    if (d_offsets) bvh_collider_pairs_kernel<true><<<g, BT, 0, st>>>(T, d_aabbs, d_dirty, d_counts, d_offsets, d_pair_keys, key_shift);
+    else bvh_collider_pairs_kernel<false><<<g, BT, 0, st>>>(T, d_aabbs, d_dirty, d_counts, d_offsets, d_pair_keys, key_shift);
     return 1;
 }
 

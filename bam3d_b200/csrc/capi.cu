@@ -144,6 +144,9 @@ int32_t bam3d_ctx_create(int32_t device_ordinal, bam3d_ctx** out_ctx) {
     if (!ctx) return BAM3D_ERR_OOM;
     ctx->device = device_ordinal;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return BAM3D_ERR_CUDA; }
+    if (cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_a, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_b, cudaEventDisableTiming) != cudaSuccess) { bam3d_ctx_destroy(ctx); return BAM3D_ERR_CUDA; }
     *out_ctx = ctx;
     return BAM3D_OK;
 }
@@ -153,6 +156,9 @@ void bam3d_ctx_destroy(bam3d_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     ctx->release_scratch();
+    if (ctx->stream2) { cudaStreamSynchronize(ctx->stream2); cudaStreamDestroy(ctx->stream2); }
+    if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
+    if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -169,6 +175,7 @@ int32_t bam3d_ctx_set_option(bam3d_ctx* ctx, const char* name, int32_t value) {
     if (!ctx || !name) return BAM3D_ERR_ARG;
     if (!std::strcmp(name, "binning")) { ctx->opt_binning = value != 0; return BAM3D_OK; }
     if (!std::strcmp(name, "timing")) { ctx->opt_timing = value != 0; return BAM3D_OK; }
+    if (!std::strcmp(name, "sap_strategy")) { if (value < 0 || value > 2) return b3_fail(ctx, BAM3D_ERR_ARG, "sap_strategy must be 0 (auto), 1 (sweep) or 2 (bvh)", cudaSuccess); ctx->opt_sap_strategy = value; return BAM3D_OK; }
     return b3_fail(ctx, BAM3D_ERR_ARG, "unknown option", cudaSuccess);
 }
 
@@ -504,6 +511,10 @@ int32_t bam3d_frustum_from_mat4(const float* m, float* out24) {
 }
 
 // ---- SweepAndPrune3 --------------------------------------------------------------------------------------------
+// Pair search strategies (identical output): the tiled forward sweep does one test per (i, j) whose sweep-axis
+// intervals overlap — n x ~24k tests for the C4 scene (a 1-axis sweep prunes little in a 3-D uniform cloud) — while a
+// BVH overlap query over the SORTED boxes (value index = sorted slot) does O(log n + hits) per box. "auto" counts the
+// sweep's candidate tests exactly (binary search per slot) and takes the BVH when they exceed 64 per box.
 static int32_t sap_run(bam3d_ctx* ctx, const float* d_aabbs, uint64_t n64, int32_t* inout_axis, uint32_t* d_perm, uint32_t* d_pairs,
                        uint64_t capacity, uint64_t* out_count) {
     const uint32_t n = (uint32_t)n64;
@@ -516,32 +527,100 @@ static int32_t sap_run(bam3d_ctx* ctx, const float* d_aabbs, uint64_t n64, int32
     }
     int32_t rc;
     SapScratch S;
-    const size_t tmp_bytes = sap_cub_tmp_bytes(n, capacity ? capacity : 1);
+    const size_t cap1 = capacity ? capacity : 1;
+    size_t tmp_bytes = sap_cub_tmp_bytes(n, cap1);
+    const size_t bvh_tmp = bvh_cub_tmp_bytes(n), scan_tmp = scan_tmp_bytes(n);
+    if (bvh_tmp > tmp_bytes) tmp_bytes = bvh_tmp;
+    if (scan_tmp > tmp_bytes) tmp_bytes = scan_tmp;
     if ((rc = ctx->bp0.reserve(ctx, (size_t)n * 8 * 2)) || (rc = ctx->bp1.reserve(ctx, (size_t)n * 4 * 2)) || (rc = ctx->bp2.reserve(ctx, (size_t)n * 16 * 2)) ||
-        (rc = ctx->bp3.reserve(ctx, (capacity ? capacity : 1) * 8 * 2)) || (rc = ctx->cub_tmp.reserve(ctx, tmp_bytes)) || (rc = ctx->small.reserve(ctx, 1024)))
+        (rc = ctx->bp3.reserve(ctx, cap1 * 8 * 2)) || (rc = ctx->cub_tmp.reserve(ctx, tmp_bytes)) || (rc = ctx->small.reserve(ctx, 1024)))
         return rc;
     S.keys_in = (unsigned long long*)ctx->bp0.ptr; S.keys_out = S.keys_in + n;
     S.vals_in = (uint32_t*)ctx->bp1.ptr; S.vals_out = S.vals_in + n;
     S.lo = (float4*)ctx->bp2.ptr; S.hi = S.lo + n;
-    S.pair_keys = (unsigned long long*)ctx->bp3.ptr; S.pair_keys_alt = S.pair_keys + (capacity ? capacity : 1);
+    S.pair_keys = (unsigned long long*)ctx->bp3.ptr; S.pair_keys_alt = S.pair_keys + cap1;
     S.cub_tmp = ctx->cub_tmp.ptr; S.cub_tmp_bytes = tmp_bytes;
     unsigned long long* d_count = (unsigned long long*)((char*)ctx->small.ptr + 832);
     int* d_axis = (int*)((char*)ctx->small.ptr + 840);
+    unsigned long long* d_cand = (unsigned long long*)((char*)ctx->small.ptr + 848);
+    float* d_sums = (float*)((char*)ctx->small.ptr + 864);
+    const int strategy = ctx->opt_sap_strategy;
+    // BVH strategy scratch (one slab): sorted 6-float rows, node bounds, topology, per-slot counts / offsets
+    float* d_sorted6 = nullptr;
+    char* slab = nullptr;
+    const size_t nn = n;
+    if (strategy != 1) {
+        const size_t bytes = nn * 24 + 2 * nn * 16 * 2 + nn * 8 + nn * 4 + nn * 4 * 4 + 2 * nn * 4 + nn * 4 + (nn + 1) * 4 + (nn + 1) * 8 + 16 * 256;
+        if ((rc = ctx->bp6.reserve(ctx, bytes))) return rc;
+        slab = (char*)ctx->bp6.ptr;
+        d_sorted6 = (float*)slab;
+    }
     { KernelTimer kt(ctx);
-      ctx->launches += launch_sap(ctx->stream, d_aabbs, n, axis, S, d_perm, (uint2*)d_pairs, capacity, d_count, d_axis); }
-    if ((rc = check_launch(ctx, "sap kernels"))) return rc;
-    unsigned long long h_count = 0; int h_axis = axis;
-    CU_TRY(cudaMemcpyAsync(&h_count, d_count, 8, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(count)");
-    CU_TRY(cudaMemcpyAsync(&h_axis, d_axis, 4, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(axis)");
-    CU_TRY(cudaStreamSynchronize(ctx->stream), "sap kernels");
+      ctx->launches += launch_sap_sort(ctx->stream, d_aabbs, n, axis, S, d_perm, d_sorted6, d_cand); }
+    // Variance3 on the side stream, beside the pair search
+    cudaEventRecord(ctx->ev_a, ctx->stream);
+    cudaStreamWaitEvent(ctx->stream2, ctx->ev_a, 0);
+    ctx->launches += launch_sap_variance(ctx->stream2, S, n, d_sums, d_axis);
+    cudaEventRecord(ctx->ev_b, ctx->stream2);
+    if ((rc = check_launch(ctx, "sap sort"))) return rc;
+    bool use_bvh = strategy == 2;
+    if (strategy == 0) {
+        unsigned long long h_cand = 0;
+        CU_TRY(cudaMemcpyAsync(&h_cand, d_cand, 8, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(candidates)");
+        CU_TRY(cudaStreamSynchronize(ctx->stream), "sap sort");
+        use_bvh = h_cand > 64ull * n;
+    }
+    unsigned long long h_count = 0;
+    if (!use_bvh) {
+        { KernelTimer kt(ctx);
+          ctx->launches += launch_sap_sweep(ctx->stream, n, axis, S, capacity, d_count); }
+        CU_TRY(cudaMemcpyAsync(&h_count, d_count, 8, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(count)");
+        CU_TRY(cudaStreamSynchronize(ctx->stream), "sap sweep");
+    } else {
+        char* q = slab;
+        auto carve = [&](size_t bytes) { char* r = q; q += (bytes + 255) & ~(size_t)255; return r; };
+        carve(nn * 24);  // d_sorted6
+        float4* nlo = (float4*)carve(2 * nn * 16);
+        float4* nhi = (float4*)carve(2 * nn * 16);
+        int2* children = (int2*)carve(nn * 8);
+        uint32_t* leaf_value = (uint32_t*)carve(nn * 4);
+        BvhBuildScratch W;
+        W.morton_in = (uint32_t*)carve(nn * 4); W.morton_out = (uint32_t*)carve(nn * 4);
+        W.idx_in = (uint32_t*)carve(nn * 4); W.idx_out = (uint32_t*)carve(nn * 4);
+        W.parent = (uint32_t*)carve(2 * nn * 4);
+        W.flags = (uint32_t*)carve(nn * 4);
+        uint32_t* d_counts = (uint32_t*)carve((nn + 1) * 4);
+        unsigned long long* d_offsets = (unsigned long long*)carve((nn + 1) * 8);
+        W.cub_tmp = ctx->cub_tmp.ptr; W.cub_tmp_bytes = tmp_bytes;
+        W.scene = (float*)((char*)ctx->small.ptr + 896);
+        BvhDev T; T.n = n; T.lo = nlo; T.hi = nhi; T.children = children; T.leaf_value = leaf_value;
+        const int shift = sap_bits_for(n);
+        { KernelTimer kt(ctx);
+          ctx->launches += launch_bvh_build(ctx->stream, d_sorted6, n, W, nlo, nhi, children, leaf_value);
+          cudaMemsetAsync(d_counts + n, 0, 4, ctx->stream);
+          ctx->launches += launch_bvh_collider_pairs(ctx->stream, T, d_sorted6, nullptr, d_counts, nullptr, nullptr, shift);
+          ctx->launches += launch_exclusive_scan_u32_to_u64(ctx->stream, d_counts, d_offsets, n, ctx->cub_tmp.ptr, tmp_bytes); }
+        CU_TRY(cudaMemcpyAsync(&h_count, d_offsets + n, 8, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(count)");
+        CU_TRY(cudaStreamSynchronize(ctx->stream), "sap bvh count");
+        if (h_count <= capacity && h_count) {
+            KernelTimer kt(ctx);
+            ctx->launches += launch_bvh_collider_pairs(ctx->stream, T, d_sorted6, nullptr, d_counts, d_offsets, S.pair_keys, shift);
+        }
+    }
+    if ((rc = check_launch(ctx, "sap pair search"))) return rc;
     *out_count = h_count;
     if (h_count > capacity) {
+        cudaStreamWaitEvent(ctx->stream, ctx->ev_b, 0);  // keep the side stream ordered before the scratch is reused
         char msg[160];
         std::snprintf(msg, sizeof msg, "bam3d_sap_find_pairs: %llu pairs found, capacity %llu", h_count, (unsigned long long)capacity);
         return b3_fail(ctx, BAM3D_ERR_CAPACITY, msg, cudaSuccess);
     }
     { KernelTimer kt(ctx);
       ctx->launches += launch_sap_finish(ctx->stream, S, h_count, (uint2*)d_pairs, n); }
+    int h_axis = axis;
+    cudaStreamWaitEvent(ctx->stream, ctx->ev_b, 0);
+    CU_TRY(cudaMemcpyAsync(&h_axis, d_axis, 4, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(axis)");
+    CU_TRY(cudaStreamSynchronize(ctx->stream), "sap finish");
     *inout_axis = h_axis;
     return check_launch(ctx, "sap finish");
 }
@@ -742,7 +821,7 @@ int32_t bam3d_bvh_find_collider_pairs(bam3d_ctx* ctx, const bam3d_bvh* t, const 
     cudaMemsetAsync(d_counts + n, 0, 4, ctx->stream);
     BvhDev T = bvh_view(t);
     { KernelTimer kt(ctx);
-      ctx->launches += launch_bvh_collider_pairs(ctx->stream, T, t->d_aabbs, d_dirty, d_counts, nullptr, nullptr); }
+      ctx->launches += launch_bvh_collider_pairs(ctx->stream, T, t->d_aabbs, d_dirty, d_counts, nullptr, nullptr, 0); }
     ctx->launches += launch_exclusive_scan_u32_to_u64(ctx->stream, d_counts, d_offsets, n, ctx->cub_tmp.ptr, scan_bytes);
     if ((rc = check_launch(ctx, "bvh collider pairs (count)"))) return rc;
     unsigned long long total = 0;
@@ -755,7 +834,7 @@ int32_t bam3d_bvh_find_collider_pairs(bam3d_ctx* ctx, const bam3d_bvh* t, const 
     if ((rc = ctx->bp3.reserve(ctx, total * 8 * 2)) || (rc = ctx->bp4.reserve(ctx, total * 8)) || (rc = ctx->cub_tmp.reserve(ctx, sort_bytes > scan_bytes ? sort_bytes : scan_bytes))) return rc;
     unsigned long long* keys = (unsigned long long*)ctx->bp3.ptr;
     { KernelTimer kt(ctx);
-      ctx->launches += launch_bvh_collider_pairs(ctx->stream, T, t->d_aabbs, d_dirty, d_counts, d_offsets, keys); }
+      ctx->launches += launch_bvh_collider_pairs(ctx->stream, T, t->d_aabbs, d_dirty, d_counts, d_offsets, keys, 0); }
     bool in_alt = false;
     ctx->launches += launch_sort_u64(ctx->stream, keys, keys + total, total, ctx->cub_tmp.ptr, sort_bytes, &in_alt);
     ctx->launches += launch_unpack_pairs(ctx->stream, in_alt ? keys + total : keys, total, (uint2*)ctx->bp4.ptr, true);

@@ -23,15 +23,18 @@ struct bam3d_ctx {
     std::string err;
     uint64_t launches = 0;
     bool opt_binning = true;
+    int opt_sap_strategy = 0;  // 0 auto, 1 tiled sweep, 2 BVH overlap query
+    cudaStream_t stream2 = nullptr;  // side stream (Variance3 runs beside the pair search)
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     // opt-in timing of the dominant kernel of each narrow-phase call (CUDA events on the ctx stream)
     bool opt_timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_events;
     // scratch for the host-buffer entry points and the binning pass
     DevBuf pairs, status, contacts, f0, f1, keys, order, small, epa_overflow, epa_queue;
     // broad-phase scratch
-    DevBuf bp0, bp1, bp2, bp3, bp4, bp5, cub_tmp;
+    DevBuf bp0, bp1, bp2, bp3, bp4, bp5, bp6, cub_tmp;
     void release_scratch() {
-        DevBuf* all[] = {&pairs, &status, &contacts, &f0, &f1, &keys, &order, &small, &epa_overflow, &epa_queue, &bp0, &bp1, &bp2, &bp3, &bp4, &bp5, &cub_tmp};
+        DevBuf* all[] = {&pairs, &status, &contacts, &f0, &f1, &keys, &order, &small, &epa_overflow, &epa_queue, &bp0, &bp1, &bp2, &bp3, &bp4, &bp5, &bp6, &cub_tmp};
         for (DevBuf* b : all) b->release();
     }
 };

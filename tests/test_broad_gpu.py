@@ -10,7 +10,15 @@ from bam3d_b200 import broad, scenes
 pytestmark = pytest.mark.gpu
 
 
-def test_sap_parity_and_axis_sequence(ctx, oracle):
+@pytest.fixture(params=[0, 1, 2], ids=["auto", "sweep", "bvh"])
+def sap_strategy(request, ctx):
+    """Every sweep-and-prune test runs under all three pair-search strategies: the output must not depend on it."""
+    ctx.set_option("sap_strategy", request.param)
+    yield request.param
+    ctx.set_option("sap_strategy", 0)
+
+
+def test_sap_parity_and_axis_sequence(ctx, oracle, sap_strategy):
     """C4 density at a size the O(n * active) CPU sweep finishes in seconds; three consecutive calls so that the
     Variance3 axis hand-over (sweep_prune.rs:123-125) is exercised on every axis."""
     boxes, L = scenes.aabb_scene(60_000)
@@ -27,7 +35,7 @@ def test_sap_parity_and_axis_sequence(ctx, oracle):
 
 
 @pytest.mark.parametrize("scale", [(1.0, 1.0, 1.0), (1.0, 30.0, 1.0), (0.05, 1.0, 40.0)])
-def test_sap_anisotropic_axes(ctx, oracle, scale):
+def test_sap_anisotropic_axes(ctx, oracle, scale, sap_strategy):
     boxes, L = scenes.aabb_scene(20_000, seed=0xB3D0C401)
     s = np.array(scale * 2, dtype=np.float32)
     boxes = (boxes * s).astype(np.float32)
@@ -38,7 +46,7 @@ def test_sap_anisotropic_axes(ctx, oracle, scale):
         assert np.array_equal(perm, operm) and np.array_equal(pairs, opairs) and sap.get_sweep_axis() == oaxis
 
 
-def test_sap_edge_cases(ctx, oracle):
+def test_sap_edge_cases(ctx, oracle, sap_strategy):
     sap = broad.SweepAndPrune3.new(ctx)
     # empty and single: no pairs, axis untouched (sweep_prune.rs:76-78)
     p, perm = sap.find_collider_pairs(np.zeros((0, 6), dtype=np.float32))
