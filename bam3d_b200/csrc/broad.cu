@@ -574,6 +574,63 @@ int launch_bvh_query(cudaStream_t st, const BvhDev& T, int kind, const float* d_
     return 1;
 }
 
+// Few, large queries (a frustum returns ~10 % of all values) leave a thread-per-query traversal with no parallelism:
+// there the leaf predicate is simply evaluated for every (query, value) — exactly the set the tree query returns,
+// since the query result is "every value whose real bound the visitor accepts" — one block per (tile of 256 values,
+// query), results compacted in value-index order.
+template <int KIND, bool FILL>
+__global__ void __launch_bounds__(256) bvh_brute_kernel(const float* __restrict__ aabbs, uint32_t n, const float* __restrict__ queries,
+                                                        uint32_t ntiles, uint32_t* __restrict__ counts, const unsigned long long* __restrict__ offsets,
+                                                        uint32_t* __restrict__ values, void* __restrict__ payload) {
+    __shared__ uint32_t warp_cnt[8];
+    const uint32_t qi = blockIdx.y, tile = blockIdx.x, v = tile * 256 + threadIdx.x;
+    Query q;
+    load_query<KIND>(q, queries, qi);
+    bool hit = false;
+    V3 point = v3(0.f, 0.f, 0.f); int rel = 0;
+    if (v < n) {
+        const float* b = aabbs + 6 * (size_t)v;
+        hit = accept<KIND>(q, make_float4(b[0], b[1], b[2], 0.f), make_float4(b[3], b[4], b[5], 0.f), point, rel);
+    }
+    const uint32_t mask = __ballot_sync(0xFFFFFFFFu, hit);
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    if (lane == 0) warp_cnt[warp] = __popc(mask);
+    __syncthreads();
+    if (!FILL) {
+        if (threadIdx.x == 0) {
+            uint32_t c = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) c += warp_cnt[w];
+            counts[(size_t)qi * ntiles + tile] = c;
+        }
+        return;
+    }
+    if (hit) {
+        uint32_t before = 0;
+        for (uint32_t w = 0; w < warp; ++w) before += warp_cnt[w];
+        const unsigned long long slot = offsets[(size_t)qi * ntiles + tile] + before + __popc(mask & ((1u << lane) - 1u));
+        values[slot] = v;
+        if (KIND == BQ_RAY) { float* p = reinterpret_cast<float*>(payload) + 3 * slot; p[0] = point.x; p[1] = point.y; p[2] = point.z; }
+        if (KIND == BQ_FRUSTUM) reinterpret_cast<uint8_t*>(payload)[slot] = (uint8_t)rel;
+    }
+}
+
+int launch_bvh_brute(cudaStream_t st, const float* d_aabbs, uint32_t n, int kind, const float* d_queries, uint32_t nq, uint32_t* d_counts,
+                     const unsigned long long* d_offsets, uint32_t* d_values, void* d_payload) {
+    if (nq == 0 || n == 0) return 0;
+    const uint32_t ntiles = (n + 255) / 256;
+    dim3 g(ntiles, nq);
+    const bool fill = d_offsets != nullptr;
+#define B3_B(KIND)                                                                                                                  \
+    if (fill) bvh_brute_kernel<KIND, true><<<g, 256, 0, st>>>(d_aabbs, n, d_queries, ntiles, d_counts, d_offsets, d_values, d_payload); \
+    else bvh_brute_kernel<KIND, false><<<g, 256, 0, st>>>(d_aabbs, n, d_queries, ntiles, d_counts, d_offsets, d_values, d_payload);
+    if (kind == BQ_AABB) { B3_B(BQ_AABB) }
+    else if (kind == BQ_RAY) { B3_B(BQ_RAY) }
+    else { B3_B(BQ_FRUSTUM) }
+#undef B3_B
+    return 1;
+}
+
 // query_ray_closest (dbvt/util.rs:77-103): t = (point - origin) . direction over the leaves the ray hits; the smallest
 // t wins. Two properties of the reference make its answer depend on its (randomised) tree shape: it keeps the FIRST leaf
 // reaching the minimum in traversal order, and RayClosestVisitor (:46-62) prunes a branch when the branch bound's own t

@@ -62,6 +62,9 @@ enum BvhQueryKind { BQ_AABB = 0, BQ_RAY = 1, BQ_FRUSTUM = 2 };
 //   BQ_FRUSTUM: nq x 24 f32 (6 planes n.xyz,d in the order left,right,bottom,top,near,far), payload 1 byte (Relation).
 int launch_bvh_query(cudaStream_t st, const BvhDev& T, int kind, const float* d_queries, uint32_t nq, uint32_t* d_counts,
                      const unsigned long long* d_offsets, uint32_t* d_values, void* d_payload);
+// all (query, value) tests, for few large queries: d_counts / d_offsets are indexed [query * ntiles + tile], ntiles = ceil(n / 256)
+int launch_bvh_brute(cudaStream_t st, const float* d_aabbs, uint32_t n, int kind, const float* d_queries, uint32_t nq, uint32_t* d_counts,
+                     const unsigned long long* d_offsets, uint32_t* d_values, void* d_payload);
 int launch_bvh_ray_closest(cudaStream_t st, const BvhDev& T, const float* d_rays, uint32_t nq, uint32_t* d_value, float* d_point_t);
 // DbvtBroadPhase::find_collider_pairs: count / fill passes over the dirty values.
 int launch_bvh_collider_pairs(cudaStream_t st, const BvhDev& T, const float* d_aabbs, const uint8_t* d_dirty, uint32_t* d_counts,

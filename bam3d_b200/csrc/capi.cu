@@ -175,6 +175,7 @@ int32_t bam3d_ctx_set_option(bam3d_ctx* ctx, const char* name, int32_t value) {
     if (!ctx || !name) return BAM3D_ERR_ARG;
     if (!std::strcmp(name, "binning")) { ctx->opt_binning = value != 0; return BAM3D_OK; }
     if (!std::strcmp(name, "timing")) { ctx->opt_timing = value != 0; return BAM3D_OK; }
+    if (!std::strcmp(name, "bvh_strategy")) { if (value < 0 || value > 2) return b3_fail(ctx, BAM3D_ERR_ARG, "bvh_strategy must be 0 (auto), 1 (traversal) or 2 (all pairs)", cudaSuccess); ctx->opt_bvh_strategy = value; return BAM3D_OK; }
     if (!std::strcmp(name, "sap_strategy")) { if (value < 0 || value > 2) return b3_fail(ctx, BAM3D_ERR_ARG, "sap_strategy must be 0 (auto), 1 (sweep) or 2 (bvh)", cudaSuccess); ctx->opt_sap_strategy = value; return BAM3D_OK; }
     return b3_fail(ctx, BAM3D_ERR_ARG, "unknown option", cudaSuccess);
 }
@@ -736,22 +737,33 @@ static int32_t bvh_query_impl(bam3d_ctx* ctx, const bam3d_bvh* t, int kind, cons
     *out_total = 0;
     if (nq == 0) { if (out_offsets) out_offsets[0] = 0; return BAM3D_OK; }
     const size_t qfloats = kind == BQ_FRUSTUM ? 24 : 6;
-    const size_t scan_bytes = scan_tmp_bytes(nq);
-    if ((rc = ctx->bp0.reserve(ctx, nq * qfloats * 4)) || (rc = ctx->bp1.reserve(ctx, ((size_t)nq + 1) * 4)) ||
-        (rc = ctx->bp2.reserve(ctx, ((size_t)nq + 1) * 8)) || (rc = ctx->cub_tmp.reserve(ctx, scan_bytes))) return rc;
+    // few large queries -> evaluate the leaf predicate for every (query, value); many small ones -> tree traversal
+    const uint32_t ntiles = (t->n + 255) / 256;
+    bool brute = ctx->opt_bvh_strategy == 2 || (ctx->opt_bvh_strategy == 0 && nq < 2048 && (uint64_t)nq * t->n <= (1ull << 35));
+    if (nq > 65535 || t->n == 0) brute = false;
+    const size_t ncount = brute ? (size_t)nq * ntiles : (size_t)nq;
+    const size_t scan_bytes = scan_tmp_bytes((uint32_t)ncount);
+    if (ncount > 0xFFFFFF00ull) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_bvh_query: too many (query, tile) cells", cudaSuccess);
+    if ((rc = ctx->bp0.reserve(ctx, nq * qfloats * 4)) || (rc = ctx->bp1.reserve(ctx, (ncount + 1) * 4)) ||
+        (rc = ctx->bp2.reserve(ctx, (ncount + 1) * 8)) || (rc = ctx->cub_tmp.reserve(ctx, scan_bytes))) return rc;
     float* d_q = (float*)ctx->bp0.ptr;
     uint32_t* d_counts = (uint32_t*)ctx->bp1.ptr;
     unsigned long long* d_offsets = (unsigned long long*)ctx->bp2.ptr;
     CU_TRY(cudaMemcpyAsync(d_q, queries, nq * qfloats * 4, cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpyAsync(queries)");
-    cudaMemsetAsync(d_counts + nq, 0, 4, ctx->stream);
+    cudaMemsetAsync(d_counts + ncount, 0, 4, ctx->stream);
     BvhDev T = bvh_view(t);
     { KernelTimer kt(ctx);
-      ctx->launches += launch_bvh_query(ctx->stream, T, kind, d_q, nq, d_counts, nullptr, nullptr, nullptr); }
-    ctx->launches += launch_exclusive_scan_u32_to_u64(ctx->stream, d_counts, d_offsets, nq, ctx->cub_tmp.ptr, scan_bytes);
+      if (brute) ctx->launches += launch_bvh_brute(ctx->stream, t->d_aabbs, t->n, kind, d_q, nq, d_counts, nullptr, nullptr, nullptr);
+      else ctx->launches += launch_bvh_query(ctx->stream, T, kind, d_q, nq, d_counts, nullptr, nullptr, nullptr); }
+    ctx->launches += launch_exclusive_scan_u32_to_u64(ctx->stream, d_counts, d_offsets, (uint32_t)ncount, ctx->cub_tmp.ptr, scan_bytes);
     if ((rc = check_launch(ctx, "bvh query (count)"))) return rc;
     unsigned long long total = 0;
-    CU_TRY(cudaMemcpyAsync(&total, d_offsets + nq, 8, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(total)");
-    if (out_offsets) CU_TRY(cudaMemcpyAsync(out_offsets, d_offsets, ((size_t)nq + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(offsets)");
+    CU_TRY(cudaMemcpyAsync(&total, d_offsets + ncount, 8, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(total)");
+    if (out_offsets) {
+        // per-query offsets: every ntiles-th entry of the cell offsets when brute
+        const size_t stride = brute ? (size_t)ntiles * 8 : 8;
+        CU_TRY(cudaMemcpy2DAsync(out_offsets, 8, d_offsets, stride, 8, (size_t)nq + 1, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpy2DAsync(offsets)");
+    }
     CU_TRY(cudaStreamSynchronize(ctx->stream), "bvh query (count)");
     *out_total = total;
     if (total > capacity) {
@@ -762,7 +774,8 @@ static int32_t bvh_query_impl(bam3d_ctx* ctx, const bam3d_bvh* t, int kind, cons
     if (total == 0) return BAM3D_OK;
     if ((rc = ctx->bp3.reserve(ctx, total * 4)) || (payload_stride && (rc = ctx->bp4.reserve(ctx, total * payload_stride)))) return rc;
     { KernelTimer kt(ctx);
-      ctx->launches += launch_bvh_query(ctx->stream, T, kind, d_q, nq, d_counts, d_offsets, (uint32_t*)ctx->bp3.ptr, payload_stride ? ctx->bp4.ptr : nullptr); }
+      if (brute) ctx->launches += launch_bvh_brute(ctx->stream, t->d_aabbs, t->n, kind, d_q, nq, d_counts, d_offsets, (uint32_t*)ctx->bp3.ptr, payload_stride ? ctx->bp4.ptr : nullptr);
+      else ctx->launches += launch_bvh_query(ctx->stream, T, kind, d_q, nq, d_counts, d_offsets, (uint32_t*)ctx->bp3.ptr, payload_stride ? ctx->bp4.ptr : nullptr); }
     if ((rc = check_launch(ctx, "bvh query (fill)"))) return rc;
     CU_TRY(cudaMemcpyAsync(out_values, ctx->bp3.ptr, total * 4, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(values)");
     if (payload_stride) CU_TRY(cudaMemcpyAsync(out_payload, ctx->bp4.ptr, total * payload_stride, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(payload)");

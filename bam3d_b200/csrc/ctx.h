@@ -24,6 +24,7 @@ struct bam3d_ctx {
     uint64_t launches = 0;
     bool opt_binning = true;
     int opt_sap_strategy = 0;  // 0 auto, 1 tiled sweep, 2 BVH overlap query
+    int opt_bvh_strategy = 0;  // variable-length queries: 0 auto, 1 tree traversal, 2 all (query, value) tests
     cudaStream_t stream2 = nullptr;  // side stream (Variance3 runs beside the pair search)
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     // opt-in timing of the dominant kernel of each narrow-phase call (CUDA events on the ctx stream)

@@ -91,7 +91,14 @@ def _split(offsets, *arrays):
     return [tuple(a[int(offsets[q]):int(offsets[q + 1])] for a in arrays) for q in range(len(offsets) - 1)]
 
 
-def test_bvh_queries_parity(ctx, oracle):
+@pytest.fixture(params=[1, 2], ids=["traversal", "allpairs"])
+def bvh_strategy(request, ctx):
+    ctx.set_option("bvh_strategy", request.param)
+    yield request.param
+    ctx.set_option("bvh_strategy", 0)
+
+
+def test_bvh_queries_parity(ctx, oracle, bvh_strategy):
     boxes, L = scenes.aabb_scene(40_000, seed=0xB3D0C404)
     bvh = broad.Bvh(ctx, boxes)
     ot = oracle.dbvt_build(boxes)
