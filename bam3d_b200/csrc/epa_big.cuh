@@ -22,7 +22,7 @@ constexpr uint16_t EPA_NIL = 0xFFFFu;
 struct BigStore {
     float4* fn;      // EPA_BIG_FCAP
     uint32_t* fi;    // EPA_BIG_FCAP
-    uint8_t* vis;    // EPA_BIG_FCAP
+    uint32_t* vm;    // EPA_BIG_FCAP / 32 : visibility bitmask
     float* vv;       // EPA_VCAP * 3
     float* va;       // EPA_VCAP * 3
     uint16_t* ed;    // EPA_BIG_EAPP : appended edges (key), tombstoned via live[]
@@ -45,7 +45,7 @@ B3_DEV BigStore carve_big_store(unsigned char* slab) {
     B.nxt = reinterpret_cast<uint16_t*>(slab); slab += (size_t)EPA_BIG_EAPP * 2;
     B.head = reinterpret_cast<uint16_t*>(slab); slab += (size_t)EPA_KEYS * 2;
     B.tail = reinterpret_cast<uint16_t*>(slab); slab += (size_t)EPA_KEYS * 2;
-    B.vis = slab;                              slab += EPA_BIG_FCAP;
+    B.vm = reinterpret_cast<uint32_t*>(slab);   slab += EPA_BIG_FCAP;  // (only FCAP / 8 bytes used)
     B.live = slab;
     return B;
 }
@@ -137,29 +137,41 @@ B3_DEV uint8_t epa_process_big(const Shape& L, const Shape& R, const Simplex<tru
             out.point = ld3(B.va, i0) * u + ld3(B.va, i1) * v + ld3(B.va, i2) * w;
             return ST_OK;
         }
-        // visibility of every face w.r.t. the new point (epa3d.rs:126-129), strided over the lanes
-        for (int k = lane; k < nf; k += 32) {
-            float4 f = B.fn[k];
-            V3 v0 = ld3(B.vv, B.fi[k] & 0xFF);
-            B.vis[k] = dot(v3(f.x, f.y, f.z), pv - v0) > 0.f ? 1 : 0;
+        // visibility of every face w.r.t. the new point (epa3d.rs:126-129): 32 faces per step, one ballot word each
+        const int nwords = (nf + 31) >> 5;
+        for (int c = 0; c < nwords; ++c) {
+            const int k = (c << 5) + lane;
+            bool vis = false;
+            if (k < nf) {
+                float4 f = B.fn[k];
+                V3 v0 = ld3(B.vv, B.fi[k] & 0xFF);
+                vis = dot(v3(f.x, f.y, f.z), pv - v0) > 0.f;
+            }
+            const uint32_t w = __ballot_sync(0xFFFFFFFFu, vis);
+            if (lane == 0) B.vm[c] = w;
         }
         __syncwarp();
-        // lane 0: the order-dependent part — swap_remove walk + horizon edge list
+        // lane 0: the order-dependent part — swap_remove walk (driven by ffs over the mask) + horizon edge list
         int napp = 0, nlive = 0, ok = 1;
         if (lane == 0) {
-            int k = 0;
-            while (k < nf) {
-                if (B.vis[k]) {
-                    uint32_t idx = B.fi[k];
-                    --nf;
-                    B.fn[k] = B.fn[nf]; B.fi[k] = B.fi[nf]; B.vis[k] = B.vis[nf];
-                    uint32_t i0 = idx & 0xFF, i1 = (idx >> 8) & 0xFF, i2 = (idx >> 16) & 0xFF;
-                    ok = ok && big_edge_op(B, napp, i0, i1);
-                    ok = ok && big_edge_op(B, napp, i1, i2);
-                    ok = ok && big_edge_op(B, napp, i2, i0);
-                } else {
-                    ++k;
+            for (int k = 0;;) {
+                int c = k >> 5;
+                uint32_t w = (c < nwords) ? (B.vm[c] >> (k & 31)) : 0u;
+                while (w == 0u && ++c < nwords) { k = c << 5; w = B.vm[c]; }
+                if (w == 0u) break;
+                k += __ffs(w) - 1;
+                const uint32_t idx = B.fi[k];
+                --nf;  // swap_remove(k): the last face (with its flag) moves into slot k and is examined next
+                const uint32_t last_bit = (B.vm[nf >> 5] >> (nf & 31)) & 1u;
+                B.vm[nf >> 5] &= ~(1u << (nf & 31));
+                if (k != nf) {
+                    B.fn[k] = B.fn[nf]; B.fi[k] = B.fi[nf];
+                    B.vm[k >> 5] = (B.vm[k >> 5] & ~(1u << (k & 31))) | (last_bit << (k & 31));
                 }
+                uint32_t i0 = idx & 0xFF, i1 = (idx >> 8) & 0xFF, i2 = (idx >> 16) & 0xFF;
+                ok = ok && big_edge_op(B, napp, i0, i1);
+                ok = ok && big_edge_op(B, napp, i1, i2);
+                ok = ok && big_edge_op(B, napp, i2, i0);
             }
             // compact the surviving edges in list order; reset the queues of every key that was touched
             for (int pos = 0; pos < napp; ++pos) {

@@ -14,6 +14,7 @@
 #include "narrow.h"
 #include "gjk.cuh"
 #include "epa_big.cuh"
+#include "epa_warp.cuh"
 
 namespace b3 {
 
@@ -197,14 +198,6 @@ B3_DEV void work_range(const uint32_t* ranges, uint32_t n, uint32_t& first, uint
     }
 }
 
-struct WarpPolytopeSmem {
-    float vv[EPA_VCAP * 3];
-    float va[EPA_VCAP * 3];
-    float4 fn[EPA_FCAP];
-    uint32_t fi[EPA_FCAP];
-    uint16_t ed[EPA_ECAP];
-};
-
 // ------------------------------------------------------------------------------------------------------------
 // GJK::intersect
 // ------------------------------------------------------------------------------------------------------------
@@ -262,7 +255,8 @@ __global__ void __launch_bounds__(TPB) gjk_contact_kernel(ShapeSetDev S, const u
         ContactOut c;
         c.normal = v3(0.f, 0.f, 0.f); c.depth = 0.f; c.point = v3(0.f, 0.f, 0.f);
         if (st == ST_OK && strategy == 0) {
-            st = epa_process<WARP>(L, R, s, cfg.epa_tolerance, cfg.max_iterations, P, c);
+            if (WARP) st = epa_process_warp(L, R, s, cfg.epa_tolerance, cfg.max_iterations, reinterpret_cast<WarpPolytopeSmem*>(dyn_smem)[threadIdx.x / 32], c);
+            else st = epa_process<false>(L, R, s, cfg.epa_tolerance, cfg.max_iterations, P, c);
             if (st != ST_OK) { c.normal = v3(0.f, 0.f, 0.f); c.depth = 0.f; c.point = v3(0.f, 0.f, 0.f); }
         }
         if (!WARP || (threadIdx.x & 31) == 0) {
