@@ -94,10 +94,14 @@ B3_DEV uint8_t epa_iterate(const Shape& L, const Shape& R, float tolerance, uint
     // closest_face_to_origin (epa3d.rs:111-119): strict <, first minimum wins
     int best = 0;
     float best_d = P.fn[0].w;
-#pragma unroll 4
-    for (int k = 1; k < nf; ++k) {
-        float dk = P.fn[k].w;
-        if (dk < best_d) { best_d = dk; best = k; }
+    // loads batched 8 at a time ahead of the compares: the loop is bound by local-memory latency, not by arithmetic
+    for (int k = 1; k < nf; k += 8) {
+        float dk[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dk[j] = (k + j < nf) ? P.fn[k + j].w : INFINITY;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (dk[j] < best_d) { best_d = dk[j]; best = k + j; }
     }
     float4 bf = P.fn[best];
     V3 normal = v3(bf.x, bf.y, bf.z);
@@ -134,20 +138,28 @@ B3_DEV uint8_t epa_iterate(const Shape& L, const Shape& R, float tolerance, uint
         uint32_t m = 0;
         const int k0 = c << 5;
         const int k1 = min(nf, k0 + 32);
-#pragma unroll 4
-        for (int k = k0; k < k1; ++k) {
-            float4 f = P.fn[k];
-            V3 fnv = v3(f.x, f.y, f.z);
-            float a2 = dot(fnv, pv) - f.w;
-            float S = (fabsf(f.x) * (fabsf(pv.x) + vmax.x) + fabsf(f.y) * (fabsf(pv.y) + vmax.y)) + fabsf(f.z) * (fabsf(pv.z) + vmax.z);
-            bool vis;
-            if (fabsf(a2) > S * 9.5367431640625e-07f + 1e-30f) {
-                vis = a2 > 0.f;
-            } else {
-                V3 v0 = ld3(P.vv, P.fi[k] & 0xFF);
-                vis = dot(fnv, pv - v0) > 0.f;
+        for (int kb = k0; kb < k1; kb += 8) {
+            float4 fb[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) fb[j] = (kb + j < k1) ? P.fn[kb + j] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int k = kb + j;
+                if (k < k1) {
+                    const float4 f = fb[j];
+                    V3 fnv = v3(f.x, f.y, f.z);
+                    float a2 = dot(fnv, pv) - f.w;
+                    float S = (fabsf(f.x) * (fabsf(pv.x) + vmax.x) + fabsf(f.y) * (fabsf(pv.y) + vmax.y)) + fabsf(f.z) * (fabsf(pv.z) + vmax.z);
+                    bool vis;
+                    if (fabsf(a2) > S * 9.5367431640625e-07f + 1e-30f) {
+                        vis = a2 > 0.f;
+                    } else {
+                        V3 v0 = ld3(P.vv, P.fi[k] & 0xFF);
+                        vis = dot(fnv, pv - v0) > 0.f;
+                    }
+                    m |= (vis ? 1u : 0u) << (k - k0);
+                }
             }
-            m |= (vis ? 1u : 0u) << (k - k0);
         }
         vm[c] = m;
     }
