@@ -32,21 +32,24 @@ struct BigStore {
     uint16_t* tail;  // EPA_KEYS
 };
 
-constexpr size_t EPA_BIG_SLAB_BYTES = (size_t)EPA_BIG_FCAP * (16 + 4 + 1) + (size_t)EPA_VCAP * 3 * 4 * 2 +
-                                      (size_t)EPA_BIG_EAPP * (2 + 2 + 1) + (size_t)EPA_KEYS * 2 * 2 + 256;
+// Faces live in a per-warp global-memory slab; everything the serial part of add() chases pointers through (edge
+// queues, key tables, visibility words, vertices) lives in the block's shared memory (one warp per block).
+constexpr size_t EPA_BIG_SLAB_BYTES = (size_t)EPA_BIG_FCAP * (16 + 4);
+constexpr size_t EPA_BIG_SMEM_BYTES = (size_t)EPA_VCAP * 3 * 4 * 2 + (size_t)EPA_BIG_EAPP * (2 + 2 + 1) + (size_t)EPA_KEYS * 2 * 2 +
+                                      (size_t)EPA_BIG_FCAP / 8 + 64;
 
-B3_DEV BigStore carve_big_store(unsigned char* slab) {
+B3_DEV BigStore carve_big_store(unsigned char* slab, unsigned char* smem) {
     BigStore B;
     B.fn = reinterpret_cast<float4*>(slab);   slab += (size_t)EPA_BIG_FCAP * 16;
-    B.fi = reinterpret_cast<uint32_t*>(slab); slab += (size_t)EPA_BIG_FCAP * 4;
-    B.vv = reinterpret_cast<float*>(slab);    slab += (size_t)EPA_VCAP * 12;
-    B.va = reinterpret_cast<float*>(slab);    slab += (size_t)EPA_VCAP * 12;
-    B.ed = reinterpret_cast<uint16_t*>(slab); slab += (size_t)EPA_BIG_EAPP * 2;
-    B.nxt = reinterpret_cast<uint16_t*>(slab); slab += (size_t)EPA_BIG_EAPP * 2;
-    B.head = reinterpret_cast<uint16_t*>(slab); slab += (size_t)EPA_KEYS * 2;
-    B.tail = reinterpret_cast<uint16_t*>(slab); slab += (size_t)EPA_KEYS * 2;
-    B.vm = reinterpret_cast<uint32_t*>(slab);   slab += EPA_BIG_FCAP;  // (only FCAP / 8 bytes used)
-    B.live = slab;
+    B.fi = reinterpret_cast<uint32_t*>(slab);
+    B.vv = reinterpret_cast<float*>(smem);    smem += (size_t)EPA_VCAP * 12;
+    B.va = reinterpret_cast<float*>(smem);    smem += (size_t)EPA_VCAP * 12;
+    B.vm = reinterpret_cast<uint32_t*>(smem); smem += (size_t)EPA_BIG_FCAP / 8;
+    B.ed = reinterpret_cast<uint16_t*>(smem); smem += (size_t)EPA_BIG_EAPP * 2;
+    B.nxt = reinterpret_cast<uint16_t*>(smem); smem += (size_t)EPA_BIG_EAPP * 2;
+    B.head = reinterpret_cast<uint16_t*>(smem); smem += (size_t)EPA_KEYS * 2;
+    B.tail = reinterpret_cast<uint16_t*>(smem); smem += (size_t)EPA_KEYS * 2;
+    B.live = smem;
     return B;
 }
 

@@ -416,7 +416,8 @@ __global__ void __launch_bounds__(32) gjk_contact_overflow_kernel(ShapeSetDev S,
     const uint32_t* list = reinterpret_cast<const uint32_t*>(scratch + 256);
     const uint32_t warp = blockIdx.x, lane = threadIdx.x;
     if (warp >= count) return;
-    BigStore B = carve_big_store(scratch + OVF_HEADER_BYTES + (size_t)warp * EPA_BIG_SLAB_BYTES);
+    extern __shared__ __align__(16) unsigned char ovf_smem[];
+    BigStore B = carve_big_store(scratch + OVF_HEADER_BYTES + (size_t)warp * EPA_BIG_SLAB_BYTES, ovf_smem);
     for (int k = lane; k < EPA_KEYS; k += 32) { B.head[k] = EPA_NIL; B.tail[k] = EPA_NIL; }
     __syncwarp();
     for (uint32_t i = warp; i < count; i += gridDim.x) {
@@ -620,7 +621,12 @@ int launch_contact(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs, 
         ++launched;
     }
     if (strategy == 0) {
-        gjk_contact_overflow_kernel<<<OVF_WARPS, 32, 0, st>>>(S, d_pairs, cfg, ovf, d_contacts, d_status);
+        static bool smem_opt_in = false;
+        if (!smem_opt_in) {
+            cudaFuncSetAttribute(gjk_contact_overflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EPA_BIG_SMEM_BYTES);
+            smem_opt_in = true;
+        }
+        gjk_contact_overflow_kernel<<<OVF_WARPS, 32, EPA_BIG_SMEM_BYTES, st>>>(S, d_pairs, cfg, ovf, d_contacts, d_status);
         ++launched;
     }
     return launched;
