@@ -38,6 +38,10 @@ ALGO_BYTES = {  # algorithmic HBM bytes per pair
     "toi": 264.0,  # 4 x 48 + 2 x 16 + 40 B out
     "c4": 220.0,   # per box: 24 B read + 4 B perm + 8 radix passes x 2 x 12 B; plus 8 B per emitted pair (added below)
 }
+# DRAM traffic of the dominant kernel per launch (bytes), from the committed ncu captures (profiles/r1_*_ncu_full.txt);
+# for C2 it is far above the algorithmic bytes because the EPA polytopes live in per-thread local memory that
+# overflows L2 (the first thing to fix next round).
+NCU_DRAM_BYTES = {"c1": 223.0e6, "c2": 24.1e9, "c3": 262.0e6}
 WORKLOAD_DESC = {
     "c1": "C1: GJK intersect, 2^20 random Cuboid-Cuboid pairs per GPU (f32, random transforms, offset U[-2,2]^3)",
     "c2": "C2: GJK+EPA Contact (FullResolution), 2^20 mixed Sphere/Cuboid/Cylinder pairs per GPU (offset U[-1.5,1.5]^3)",
@@ -424,22 +428,26 @@ def run_ours(args):
     ctx.set_option("timing", 0)
     launches = ctx.launch_count - launches0
     clocks = None
+    # If the timed region was shorter than nvidia-smi's sampling period, keep every GPU under the same load for ~1.5 s
+    # (untimed) so that the clocks reported are clocks under this workload. The steps contain collectives when
+    # world > 1, so the decision and the repeat count come from rank 0 and EVERY rank runs the same number of steps.
+    repeat = torch.zeros(1, dtype=torch.int64, device=dev)
+    if sampler and sampler.count(w0, w1) < 3:
+        repeat[0] = max(1, int(1.5 / max(ms * 1e-3 / args.steps, 1e-5)))
+    if world > 1:
+        dist.broadcast(repeat, src=0)
+    reps = int(repeat.item())
+    if reps:
+        w0 = time.time()
+        for _ in range(reps):
+            step_resident()
+        sync_all()
+        w1 = time.time()
     if sampler:
-        clock_note = "sampled during the timed region"
-        if sampler.count(w0, w1) < 3:
-            # the timed region is shorter than nvidia-smi's sampling period: keep the GPU under the same load for ~1.5 s
-            # (untimed) so that the clocks reported are clocks under this workload
-            clock_note = "timed region shorter than the sampling period: sampled during an untimed repeat of the same steps"
-            w0 = time.time()
-            while time.time() - w0 < 1.5:
-                step_resident()
-                ctx.synchronize()
-            w1 = time.time()
         sampler.window(w0, w1)
         clocks = sampler.stop()
-        clocks["note"] = clock_note
-    if world > 1:
-        dist.barrier()
+        clocks["note"] = ("timed region shorter than the sampling period: sampled during an untimed repeat of the same steps"
+                          if reps else "sampled during the timed region")
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -506,9 +514,12 @@ def run_ours(args):
                     "path": "bam3d_shapes_set_transforms + host-buffer bam3d_gjk_* call, pinned host memory"},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "kernel": {"c1": "gjk_intersect_kernel<false>", "c2": "gjk_contact_kernel<false>", "c3": "gjk_contact_kernel<true>",
-                                    "toi": "gjk_toi_kernel<false>"}[wl],
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": NCU_DRAM_BYTES.get(wl),
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture in profiles/"
+                                           if NCU_DRAM_BYTES.get(wl) else None,
+                         "kernel": {"c1": "gjk_intersect_kernel<false>", "c2": "epa_refill_kernel (+ gjk_phase_kernel, gjk_contact_overflow_kernel)",
+                                    "c3": "gjk_contact_kernel<true>", "toi": "gjk_toi_kernel<false>"}[wl],
                          "kernel_ms_per_launch": per_launch_ms, "algorithmic_bytes_per_pair": ALGO_BYTES[wl], "peak_source": peak_src,
                          "note": "plain-FP32 SIMT, compute/latency bound: see profiles/ for FP32-pipe and branch efficiency"},
             "cpu_baseline": {"value": n_sample / best, "unit": "pairs/s", "cores": cores, "kind": "port",
