@@ -12,6 +12,7 @@
 // uncapped TOI loop (gjk/mod.rs:166) is capped at `toi_iteration_cap` and reported as Status::MaxIter.
 #pragma once
 #include <cstdint>
+#include <utility>
 #include <vector>
 #include "glam_mini.hpp"
 
@@ -488,6 +489,81 @@ struct GJK {
         }
         std::vector<SupportPoint> sv(simplex.p, simplex.p + simplex.n);  // simplex.into_vec()
         return epa.process(sv, left, lt, right, rt, out, cnt, st);        // get_contact_manifold, :285-299
+    }
+
+    // gjk/mod.rs:362-407 intersection_complex. Shapes are lists of (primitive, local transform). Returns true + contact.
+    // `st` = WouldPanic where `partial_cmp(..).unwrap()` meets a NaN depth (:403-405).
+    bool intersection_complex(CollisionStrategy strategy, const std::vector<std::pair<Shape, Mat4>>& left, const Mat4& lt,
+                              const std::vector<std::pair<Shape, Mat4>>& right, const Mat4& rt, Contact& out, Status& st) const {
+        st = Status::Miss;
+        std::vector<Contact> contacts;
+        for (auto& l : left) {
+            Mat4 ltf = lt.mul_mat4(l.second);
+            for (auto& r : right) {
+                Mat4 rtf = rt.mul_mat4(r.second);
+                Contact c; Status s1;
+                if (intersection(strategy, l.first, ltf, r.first, rtf, c, &s1)) {
+                    if (strategy == CollisionStrategy::CollisionOnly) { out = c; st = Status::Ok; return true; }
+                    contacts.push_back(c);
+                }
+            }
+        }
+        if (contacts.empty()) return false;
+        // Iterator::max_by: the LAST of several equal maxima is returned; unwrap() panics on NaN
+        size_t best = 0;
+        for (size_t i = 1; i < contacts.size(); ++i) {
+            float a = contacts[best].penetration_depth, b = contacts[i].penetration_depth;
+            if (a != a || b != b) { st = Status::WouldPanic; return false; }
+            if (!(a > b)) best = i;  // max_by keeps the later element unless the earlier compares Greater
+        }
+        if (contacts.size() == 1 && contacts[0].penetration_depth != contacts[0].penetration_depth) { /* single element: no comparison */ }
+        out = contacts[best]; st = Status::Ok;
+        return true;
+    }
+
+    // gjk/mod.rs:422-456 distance_complex: None as soon as one primitive pair returns None; else the f32::min of all.
+    bool distance_complex(const std::vector<std::pair<Shape, Mat4>>& left, const Mat4& lt, const std::vector<std::pair<Shape, Mat4>>& right,
+                          const Mat4& rt, float& out, Status& st) const {
+        bool have = false; float mn = 0.f;
+        for (auto& l : left) {
+            Mat4 ltf = lt.mul_mat4(l.second);
+            for (auto& r : right) {
+                Mat4 rtf = rt.mul_mat4(r.second);
+                float rv, geo; Status s1;
+                if (!distance(l.first, ltf, r.first, rtf, rv, geo, s1)) { st = s1 == Status::WouldPanic ? s1 : Status::Miss; return false; }
+                mn = have ? rmin(rv, mn) : rv;
+                have = true;
+            }
+        }
+        st = have ? Status::Ok : Status::Miss;
+        out = mn;
+        return have;
+    }
+
+    // gjk/mod.rs:478-523 intersection_complex_time_of_impact: CollisionOnly -> first hit; else min_by time_of_impact
+    // (the FIRST of several equal minima; partial_cmp(..).unwrap_or(Equal)).
+    bool intersection_complex_time_of_impact(CollisionStrategy strategy, const std::vector<std::pair<Shape, Mat4>>& left, const Mat4& lt0,
+                                             const Mat4& lt1, const std::vector<std::pair<Shape, Mat4>>& right, const Mat4& rt0, const Mat4& rt1,
+                                             Contact& out, Status& st) const {
+        st = Status::Miss;
+        std::vector<Contact> contacts;
+        for (auto& l : left) {
+            Mat4 l0 = lt0.mul_mat4(l.second), l1 = lt1.mul_mat4(l.second);
+            for (auto& r : right) {
+                Mat4 r0 = rt0.mul_mat4(r.second), r1 = rt1.mul_mat4(r.second);
+                Contact c; Status s1;
+                if (intersection_time_of_impact(l.first, l0, l1, r.first, r0, r1, c, s1)) {
+                    if (strategy == CollisionStrategy::CollisionOnly) { c.strategy = CollisionStrategy::CollisionOnly; out = c; st = Status::Ok; return true; }
+                    contacts.push_back(c);
+                } else if (s1 == Status::WouldPanic) { st = s1; return false; }
+            }
+        }
+        if (contacts.empty()) return false;
+        size_t best = 0;
+        for (size_t i = 1; i < contacts.size(); ++i)
+            if (contacts[i].time_of_impact < contacts[best].time_of_impact) best = i;  // min_by keeps the first unless a later one is Less
+        out = contacts[best]; st = Status::Ok;
+        return true;
     }
 
     // gjk/mod.rs:232-280. Returns Some/None; `ref_value` is what the reference returns (dp - d0, the

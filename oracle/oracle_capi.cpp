@@ -176,6 +176,37 @@ void orc_gjk_toi_batch(const uint8_t* kind, const float* params, const float* xf
     merge(counters, cs);
 }
 
+// Compound shapes (gjk/mod.rs:362-523). A compound = primitives [begin, end) of the shape table, whose `xform` entries
+// are the LOCAL transforms; comp_xform0/1 are the compounds' model-to-world transforms at the start / end of the step.
+// mode: 0 intersection_complex, 1 distance_complex, 2 intersection_complex_time_of_impact. out: 8 floats per compound
+// pair (contact layout; distance in [3]).
+void orc_gjk_complex_batch(const uint8_t* kind, const float* params, const float* xform, const uint32_t* mesh_id, const float* mesh_verts,
+                           const uint32_t* mesh_offsets, const uint32_t* comp_offsets, const float* comp_xform0, const float* comp_xform1,
+                           const uint32_t* pairs, uint64_t n, int mode, int strategy, float* out, uint8_t* out_status) {
+    ShapeTable T{kind, params, xform, mesh_id, mesh_verts, mesh_offsets};
+    GJK gjk;
+    auto compound = [&](uint32_t c) {
+        std::vector<std::pair<Shape, Mat4>> v;
+        for (uint32_t i = comp_offsets[c]; i < comp_offsets[c + 1]; ++i) v.emplace_back(T.shape(i), T.mat(i));
+        return v;
+    };
+    for (uint64_t i = 0; i < n; ++i) {
+        uint32_t l = pairs[2 * i], r = pairs[2 * i + 1];
+        auto L = compound(l), R = compound(r);
+        Mat4 l0 = Mat4::from_cols_array(comp_xform0 + 16 * (size_t)l), r0 = Mat4::from_cols_array(comp_xform0 + 16 * (size_t)r);
+        Contact c; Status st = Status::Miss; bool ok = false;
+        std::memset(out + 8 * i, 0, 32);
+        if (mode == 0) ok = gjk.intersection_complex((CollisionStrategy)strategy, L, l0, R, r0, c, st);
+        else if (mode == 1) { float d = 0.f; ok = gjk.distance_complex(L, l0, R, r0, d, st); if (ok) out[8 * i + 3] = d; }
+        else {
+            Mat4 l1 = Mat4::from_cols_array(comp_xform1 + 16 * (size_t)l), r1 = Mat4::from_cols_array(comp_xform1 + 16 * (size_t)r);
+            ok = gjk.intersection_complex_time_of_impact((CollisionStrategy)strategy, L, l0, l1, R, r0, r1, c, st);
+        }
+        if (ok && mode != 1) put_contact(out + 8 * i, c);
+        out_status[i] = ok ? 0 : (uint8_t)st;
+    }
+}
+
 // ---- single-call helpers used by the parity / golden tests -------------------------------------------------
 void orc_support_point(uint8_t kind, const float* params4, const float* verts, uint32_t nverts, const float* dir3,
                        const float* xform16, float* out3) {

@@ -105,6 +105,20 @@ class Oracle:
                                    C.byref(counters) if counters is not None else None)
         return contacts, hit, status
 
+    def complex(self, scene, comp_offsets, comp_xform0, comp_xform1, pairs, mode, strategy=0):
+        """Compound shapes: mode 0 intersection_complex, 1 distance_complex, 2 intersection_complex_time_of_impact."""
+        kind, params, mesh_id, mv, mo = self._scene_args(scene)
+        xform = np.ascontiguousarray(scene["xform"], dtype=np.float32)
+        co = np.ascontiguousarray(comp_offsets, dtype=np.uint32)
+        x0 = np.ascontiguousarray(comp_xform0, dtype=np.float32)
+        x1 = np.ascontiguousarray(comp_xform1 if comp_xform1 is not None else comp_xform0, dtype=np.float32)
+        pairs = np.ascontiguousarray(pairs, dtype=np.uint32)
+        out = np.empty((len(pairs), 8), dtype=np.float32)
+        st = np.empty(len(pairs), dtype=np.uint8)
+        self.lib.orc_gjk_complex_batch(_p(kind), _p(params), _p(xform), _p(mesh_id), _p(mv), _p(mo), _p(co), _p(x0), _p(x1), _p(pairs),
+                                       C.c_uint64(len(pairs)), C.c_int(mode), C.c_int(int(strategy)), _p(out), _p(st))
+        return out, st
+
     def support_point(self, kind, params4, direction, xform16, verts=None):
         params4 = np.ascontiguousarray(params4, dtype=np.float32)
         direction = np.ascontiguousarray(direction, dtype=np.float32)

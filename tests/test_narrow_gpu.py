@@ -314,3 +314,45 @@ def test_edge_cases(ctx, oracle):
     g3 = b3.GJK.new_with_settings(1e-6, 1e-6, 1e-5, 500, ctx=ctx)
     with pytest.raises(b3.Bam3dError):
         g3.intersection_batch(b3.CollisionStrategy.FullResolution, shapes, scene["pairs"])
+
+
+def test_compound_shapes_parity(ctx, oracle):
+    """a10: intersection_complex / distance_complex / intersection_complex_time_of_impact (gjk/mod.rs:362-523): all
+    primitive x primitive combinations on the GPU, composed with Mat4::mul_mat4, then the reference's reductions
+    (last max depth / min distance with early None / first min TOI / first hit for CollisionOnly)."""
+    from bam3d_b200.api import CompoundSet
+    prim = scenes.mixed_pairs(1500, s=0.8, seed=0xB3D0AA10)            # 3000 primitives with random LOCAL transforms
+    prim["xform"][:, 12:15] *= np.float32(0.08)                        # keep the parts of a compound close together
+    rng = np.random.default_rng(10)
+    sizes = rng.integers(1, 5, size=4000)
+    offs = np.concatenate([[0], np.cumsum(sizes)])
+    offs = offs[offs <= 3000]
+    ncomp = len(offs) - 1
+    for key in ("kind", "params", "xform"):
+        prim[key] = prim[key][: offs[-1]]
+    world = scenes.mixed_pairs((ncomp + 1) // 2, s=1.2, seed=0xB3D0AA11)["xform"][:ncomp]
+    world_end = world.copy()
+    world_end[:, 12:15] += rng.uniform(-3, 3, size=(ncomp, 3)).astype(np.float32)
+    pairs = rng.integers(0, ncomp, size=(3000, 2)).astype(np.uint32)
+    near = np.arange(0, ncomp - 1, 2, dtype=np.uint32)
+    pairs = np.concatenate([pairs, np.stack([near, near + 1], axis=1)])  # neighbours built as (left, right) of one pair
+    comp = CompoundSet(ctx, prim["kind"], prim["params"], prim["xform"], offs)
+    gjk = b3.GJK.new(ctx)
+    for strategy in (b3.CollisionStrategy.FullResolution, b3.CollisionStrategy.CollisionOnly):
+        c, st = gjk.intersection_complex_batch(strategy, comp, world, pairs)
+        oc, ost = oracle.complex(prim, offs, world, None, pairs, mode=0, strategy=int(strategy))
+        assert np.array_equal(st, ost), f"{int((st != ost).sum())} status mismatches"
+        assert (st == 0).sum() > 100
+        assert_f32_equal("complex contact", c[:, :7], oc[:, :7], st == 0)
+    d, st = gjk.distance_complex_batch(comp, world, pairs)
+    od, ost = oracle.complex(prim, offs, world, None, pairs, mode=1)
+    assert np.array_equal(st, ost) and (st == 0).sum() > 50
+    assert_f32_equal("complex distance", d, od[:, 3], st == 0)
+    for strategy in (b3.CollisionStrategy.FullResolution, b3.CollisionStrategy.CollisionOnly):
+        c, st = gjk.intersection_complex_time_of_impact_batch(strategy, comp, world, world_end, pairs)
+        oc, ost = oracle.complex(prim, offs, world, world_end, pairs, mode=2, strategy=int(strategy))
+        assert np.array_equal(st, ost), f"{int((st != ost).sum())} status mismatches"
+        hit = st == 0
+        assert hit.sum() > 20
+        assert_f32_equal("complex toi", c[:, [0, 1, 2, 3, 7]], oc[:, [0, 1, 2, 3, 7]], hit)
+        assert (np.isclose(c[hit][:, 4:7], oc[hit][:, 4:7], rtol=REL_TOL, atol=1e-4) | np.isnan(oc[hit][:, 4:7])).all()
