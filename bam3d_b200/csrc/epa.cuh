@@ -41,7 +41,7 @@ B3_DEV V3 ld3(const float* p, int i) { return v3(p[3 * i], p[3 * i + 1], p[3 * i
 B3_DEV void st3(float* p, int i, V3 v) { p[3 * i] = v.x; p[3 * i + 1] = v.y; p[3 * i + 2] = v.z; }
 
 // Face::new_impl (epa3d.rs:160-170)
-B3_DEV void make_face(const PolytopeStore& P, int slot, uint32_t a, uint32_t b, uint32_t c) {
+B3_DEV float make_face(const PolytopeStore& P, int slot, uint32_t a, uint32_t b, uint32_t c) {
     V3 va = ld3(P.vv, a);
     V3 ab = ld3(P.vv, b) - va;
     V3 ac = ld3(P.vv, c) - va;
@@ -49,7 +49,22 @@ B3_DEV void make_face(const PolytopeStore& P, int slot, uint32_t a, uint32_t b, 
     float dist = dot(n, va);
     P.fn[slot] = make_float4(n.x, n.y, n.z, dist);
     P.fi[slot] = a | (b << 8) | (c << 16);
+    return dist;
 }
+
+// closest_face_to_origin (epa3d.rs:111-119) is `best = 0; for k >= 1: if d[k] < d[best] best = k`: the FIRST index of
+// the minimum over non-NaN distances, except that a NaN d[0] is never displaced. The thread-per-pair tier does not
+// rescan the face list for it every iteration: the running (distance, index) is carried through Polytope::add —
+// survivors in pass A (strict <, increasing index), faces moved by swap_remove (an equal distance at a lower index
+// takes over), new faces in pass C — which yields exactly the index a fresh scan of the final list would.
+struct ClosestFace {
+    float d;
+    int idx;
+    B3_DEV void reset() { d = INFINITY; idx = -1; }
+    B3_DEV void offer(float fd, int k) { if (fd < d) { d = fd; idx = k; } }                       // in increasing k
+    B3_DEV void moved(float fd, int k) { if (fd == d && k < idx) idx = k; }                        // survivor moved to a lower slot
+    B3_DEV int finish(const PolytopeStore& P) const { float d0 = P.fn[0].w; return (d0 != d0 || idx < 0) ? 0 : idx; }
+};
 
 // remove_or_add_edge (epa3d.rs:183-190): a reversed duplicate is removed (order preserving), else push.
 B3_DEV bool remove_or_add_edge(uint16_t* ed, int& ne, int ecap, uint32_t a, uint32_t b) {
@@ -68,7 +83,7 @@ B3_DEV bool remove_or_add_edge(uint16_t* ed, int& ne, int ecap, uint32_t a, uint
 
 // Polytope::new (epa3d.rs:103-109) + Face::new (:172-179) from the 4-point GJK simplex (with sup_a).
 template <bool WARP>
-B3_DEV void epa_init(const Simplex<true>& s, const PolytopeStore& P, int& nv, int& nf, uint32_t& it, V3& vmax) {
+B3_DEV void epa_init(const Simplex<true>& s, const PolytopeStore& P, int& nv, int& nf, uint32_t& it, V3& vmax, int& best) {
     vmax = v3(0.f, 0.f, 0.f);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -76,11 +91,14 @@ B3_DEV void epa_init(const Simplex<true>& s, const PolytopeStore& P, int& nv, in
         vmax = v3(fmaxf(vmax.x, fabsf(s.v[k].x)), fmaxf(vmax.y, fabsf(s.v[k].y)), fmaxf(vmax.z, fabsf(s.v[k].z)));
     }
     if (WARP) __syncwarp();
-    make_face(P, 0, 3, 2, 1);
-    make_face(P, 1, 3, 1, 0);
-    make_face(P, 2, 3, 0, 2);
-    make_face(P, 3, 2, 0, 1);
+    ClosestFace cf;
+    cf.reset();
+    cf.offer(make_face(P, 0, 3, 2, 1), 0);
+    cf.offer(make_face(P, 1, 3, 1, 0), 1);
+    cf.offer(make_face(P, 2, 3, 0, 2), 2);
+    cf.offer(make_face(P, 3, 2, 0, 1), 3);
     if (WARP) __syncwarp();
+    best = cf.finish(P);
     nv = 4; nf = 4; it = 1;
 }
 
@@ -90,19 +108,7 @@ constexpr uint8_t EPA_CONTINUE = 0xFF;
 // Returns EPA_CONTINUE, or a final Status (ST_OK with `out` filled, ST_CAPACITY).
 template <bool WARP>
 B3_DEV uint8_t epa_iterate(const Shape& L, const Shape& R, float tolerance, uint32_t max_iterations, const PolytopeStore& P,
-                           int& nv, int& nf, uint32_t& it, V3& vmax, ContactOut& out) {
-    // closest_face_to_origin (epa3d.rs:111-119): strict <, first minimum wins
-    int best = 0;
-    float best_d = P.fn[0].w;
-    // loads batched 8 at a time ahead of the compares: the loop is bound by local-memory latency, not by arithmetic
-    for (int k = 1; k < nf; k += 8) {
-        float dk[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) dk[j] = (k + j < nf) ? P.fn[k + j].w : INFINITY;
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-            if (dk[j] < best_d) { best_d = dk[j]; best = k + j; }
-    }
+                           int& nv, int& nf, uint32_t& it, V3& vmax, int& best, ContactOut& out) {
     float4 bf = P.fn[best];
     V3 normal = v3(bf.x, bf.y, bf.z);
     V3 pv, pa;
@@ -133,6 +139,8 @@ B3_DEV uint8_t epa_iterate(const Shape& L, const Shape& R, float tolerance, uint
     // The flags live in a bitmask (32 faces per word, built in a register chunk by chunk) so that pass A is a pure
     // load + arithmetic loop the compiler can software-pipeline, and pass B finds the next flagged face with ffs.
     uint32_t vm[EPA_FCAP / 32];
+    ClosestFace cf;
+    cf.reset();
     const int nchunks = (nf + 31) >> 5;
     for (int c = 0; c < nchunks; ++c) {
         uint32_t m = 0;
@@ -158,6 +166,7 @@ B3_DEV uint8_t epa_iterate(const Shape& L, const Shape& R, float tolerance, uint
                         vis = dot(fnv, pv - v0) > 0.f;
                     }
                     m |= (vis ? 1u : 0u) << (k - k0);
+                    if (!vis) cf.offer(f.w, k);
                 }
             }
         }
@@ -183,6 +192,7 @@ B3_DEV uint8_t epa_iterate(const Shape& L, const Shape& R, float tolerance, uint
             P.fn[k] = lf;
             P.fi[k] = li;
             vm[k >> 5] = (vm[k >> 5] & ~(1u << (k & 31))) | (last_bit << (k & 31));
+            if (!last_bit) cf.moved(lf.w, k);
         }
         uint32_t i0 = idx & 0xFF, i1 = (idx >> 8) & 0xFF, i2 = (idx >> 16) & 0xFF;
         ok = ok && remove_or_add_edge(P.ed, ne, P.ecap, i0, i1);
@@ -201,10 +211,11 @@ B3_DEV uint8_t epa_iterate(const Shape& L, const Shape& R, float tolerance, uint
     if (WARP) __syncwarp();
     for (int e = 0; e < ne; ++e) {
         uint32_t ab = P.ed[e];
-        make_face(P, nf + e, (uint32_t)n, ab & 0xFF, (ab >> 8) & 0xFF);
+        cf.offer(make_face(P, nf + e, (uint32_t)n, ab & 0xFF, (ab >> 8) & 0xFF), nf + e);
     }
     nf += ne;
     if (WARP) __syncwarp();
+    best = cf.finish(P);
     it += 1;
     return EPA_CONTINUE;
 }
@@ -216,9 +227,10 @@ B3_DEV uint8_t epa_process(const Shape& L, const Shape& R, const Simplex<true>& 
     int nv, nf;
     uint32_t it;
     V3 vmax;
-    epa_init<WARP>(s, P, nv, nf, it, vmax);
+    int best;
+    epa_init<WARP>(s, P, nv, nf, it, vmax, best);
     for (;;) {
-        uint8_t st = epa_iterate<WARP>(L, R, tolerance, max_iterations, P, nv, nf, it, vmax, out);
+        uint8_t st = epa_iterate<WARP>(L, R, tolerance, max_iterations, P, nv, nf, it, vmax, best, out);
         if (st != EPA_CONTINUE) return st;
     }
 }

@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(TPB) gjk_phase_kernel(ShapeSetDev S, const uin
     }
 }
 
-__global__ void __launch_bounds__(TPB) epa_refill_kernel(ShapeSetDev S, const uint2* __restrict__ pairs, SettingsDev cfg,
+__global__ void __launch_bounds__(TPB, 4) epa_refill_kernel(ShapeSetDev S, const uint2* __restrict__ pairs, SettingsDev cfg,
                                                          unsigned char* __restrict__ queue, unsigned char* __restrict__ ovf_scratch,
                                                          float4* __restrict__ contacts, uint8_t* __restrict__ status) {
     float lvv[EPA_VCAP * 3];
@@ -354,6 +354,7 @@ __global__ void __launch_bounds__(TPB) epa_refill_kernel(ShapeSetDev S, const ui
     int nv = 0, nf = 0;
     uint32_t it = 0, p = 0;
     V3 vmax = v3(0.f, 0.f, 0.f);
+    int best = 0;
     for (;;) {
         // refill idle lanes from the queue (one atomic per warp per trip)
         const uint32_t need = __ballot_sync(0xFFFFFFFFu, !active && !exhausted);
@@ -377,7 +378,7 @@ __global__ void __launch_bounds__(TPB) epa_refill_kernel(ShapeSetDev S, const ui
                     uint2 pr = __ldg(pairs + p);
                     load_pair_shape(L, S, pr.x);
                     load_pair_shape(R, S, pr.y);
-                    epa_init<false>(s, P, nv, nf, it, vmax);
+                    epa_init<false>(s, P, nv, nf, it, vmax, best);
                     active = true;
                 } else {
                     exhausted = true;
@@ -387,7 +388,7 @@ __global__ void __launch_bounds__(TPB) epa_refill_kernel(ShapeSetDev S, const ui
         if (!__any_sync(0xFFFFFFFFu, active)) break;
         if (active) {
             ContactOut c;
-            uint8_t st = epa_iterate<false>(L, R, cfg.epa_tolerance, cfg.max_iterations, P, nv, nf, it, vmax, c);
+            uint8_t st = epa_iterate<false>(L, R, cfg.epa_tolerance, cfg.max_iterations, P, nv, nf, it, vmax, best, c);
             if (st != EPA_CONTINUE) {
                 if (st != ST_OK) { c.normal = v3(0.f, 0.f, 0.f); c.depth = 0.f; c.point = v3(0.f, 0.f, 0.f); }
                 contacts[2 * (size_t)p] = make_float4(c.normal.x, c.normal.y, c.normal.z, c.depth);
