@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbam3d_gpu.so")
+# BAM3D_LIB: development knob to load a differently-built copy of the same library (kernel A/B timing)
+LIB_PATH = os.environ.get("BAM3D_LIB") or os.path.join(_HERE, "libbam3d_gpu.so")
 
 OK = 0
 ERR_CUDA, ERR_ARG, ERR_NON_AFFINE, ERR_CAPACITY, ERR_OOM = -1, -2, -3, -4, -5

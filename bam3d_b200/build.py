@@ -40,5 +40,27 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def build_variant(name, extra_flags=(), csrc=CSRC):
+    """Development: build the same sources with extra nvcc flags (e.g. -DB3_...) into build/variants/lib_<name>.so,
+    for A/B timing with tools/ab_time.py. The product library is untouched."""
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    out_dir = os.path.join(HERE, "..", "build", "variants")
+    obj_dir = os.path.join(out_dir, "obj_" + name)
+    os.makedirs(obj_dir, exist_ok=True)
+    objs = []
+    procs = []
+    for src in SOURCES:
+        obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
+        procs.append(subprocess.Popen([nvcc] + NVCC_FLAGS + list(extra_flags) + ["-I", os.path.join(HERE, "..", "include"), "-c",
+                                                                                 os.path.join(csrc, src), "-o", obj]))
+        objs.append(obj)
+    for p in procs:
+        if p.wait() != 0:
+            raise RuntimeError("nvcc failed for variant " + name)
+    lib = os.path.abspath(os.path.join(out_dir, f"lib_{name}.so"))
+    subprocess.run([nvcc, "-shared", "-o", lib] + objs + ["-lcudart_static", "-lpthread", "-ldl", "-lrt"], check=True)
+    return lib
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -31,8 +31,9 @@ struct PolytopeStore {
     float* va;        // EPA_VCAP * 3 : SupportPoint.sup_a
     float4* fn;       // EPA_FCAP     : face normal xyz + distance
     uint32_t* fi;     // EPA_FCAP     : face vertex indices, 8 bits each (a | b<<8 | c<<16)
-    uint16_t* ed;     // EPA_ECAP     : horizon edges (a | b<<8)
+    uint16_t* ed;     // ecap entries, `estride` apart : horizon edges (a | b<<8)
     int fcap, ecap;   // capacities of fn/fi and ed
+    int estride;      // 1 = contiguous (local memory); blockDim.x = one shared-memory column per thread
 };
 
 struct ContactOut { V3 normal; float depth; V3 point; };
@@ -62,22 +63,24 @@ struct ClosestFace {
     int idx;
     B3_DEV void reset() { d = INFINITY; idx = -1; }
     B3_DEV void offer(float fd, int k) { if (fd < d) { d = fd; idx = k; } }                       // in increasing k
+    B3_DEV void offer_any(float fd, int k) { if (fd < d || (fd == d && k < idx)) { d = fd; idx = k; } }  // in any order
     B3_DEV void moved(float fd, int k) { if (fd == d && k < idx) idx = k; }                        // survivor moved to a lower slot
     B3_DEV int finish(const PolytopeStore& P) const { float d0 = P.fn[0].w; return (d0 != d0 || idx < 0) ? 0 : idx; }
 };
 
 // remove_or_add_edge (epa3d.rs:183-190): a reversed duplicate is removed (order preserving), else push.
-B3_DEV bool remove_or_add_edge(uint16_t* ed, int& ne, int ecap, uint32_t a, uint32_t b) {
+B3_DEV bool remove_or_add_edge(uint16_t* ed, int es, int& ne, int ecap, uint32_t a, uint32_t b) {
     const uint16_t rev = (uint16_t)(b | (a << 8));
     for (int i = 0; i < ne; ++i) {
-        if (ed[i] == rev) {
-            for (int k = i; k + 1 < ne; ++k) ed[k] = ed[k + 1];
+        if (ed[i * es] == rev) {
+            for (int k = i; k + 1 < ne; ++k) ed[k * es] = ed[(k + 1) * es];
             --ne;
             return true;
         }
     }
     if (ne >= ecap) return false;
-    ed[ne++] = (uint16_t)(a | (b << 8));
+    ed[ne * es] = (uint16_t)(a | (b << 8));
+    ++ne;
     return true;
 }
 
@@ -104,6 +107,29 @@ B3_DEV void epa_init(const Simplex<true>& s, const PolytopeStore& P, int& nv, in
 
 constexpr uint8_t EPA_CONTINUE = 0xFF;
 
+#ifndef B3_EPA_PREFETCH
+#define B3_EPA_PREFETCH 0  // 0 = off (measured: L1/L2 prefetch of the face list costs 0.8 ms on C2 — the caches are over capacity), 1 = prefetch.L1, 2 = prefetch.L2
+#endif
+
+// Thread-per-pair tier: pull the whole face list towards the SM while the support function computes, so that pass A
+// pays one memory round trip instead of one per 8-face batch. Per-thread local memory is interleaved by lane at word
+// granularity — word w of all 32 lanes shares one 128-byte line — so the active lanes split the lines between
+// them: the lane of rank r touches words r, r + count, ... of its own face array.
+B3_DEV void prefetch_faces(const PolytopeStore& P, int nf) {
+    const uint32_t act = __activemask();
+    const int cnt = __popc(act);
+    const int rank = __popc(act & ((1u << (threadIdx.x & 31u)) - 1u));
+    const int words = 4 * (int)__reduce_max_sync(act, (unsigned)nf);
+    const float* base = reinterpret_cast<const float*>(P.fn);
+    for (int w = rank; w < words; w += cnt) {
+#if B3_EPA_PREFETCH == 2
+        asm volatile("prefetch.L2 [%0];" ::"l"(base + w));
+#else
+        asm volatile("prefetch.L1 [%0];" ::"l"(base + w));
+#endif
+    }
+}
+
 // One trip of EPA3::process's loop (epa3d.rs:33-51): closest face, support, convergence test, Polytope::add.
 // Returns EPA_CONTINUE, or a final Status (ST_OK with `out` filled, ST_CAPACITY).
 template <bool WARP>
@@ -112,6 +138,9 @@ B3_DEV uint8_t epa_iterate(const Shape& L, const Shape& R, float tolerance, uint
     float4 bf = P.fn[best];
     V3 normal = v3(bf.x, bf.y, bf.z);
     V3 pv, pa;
+#if B3_EPA_PREFETCH
+    if (!WARP) prefetch_faces(P, nf);
+#endif
     minkowski_support<WARP>(L, R, normal, pv, pa);
     float d = dot(pv, normal);
     if (d - bf.w < tolerance || it >= max_iterations) {
@@ -143,7 +172,7 @@ B3_DEV uint8_t epa_iterate(const Shape& L, const Shape& R, float tolerance, uint
     cf.reset();
     const int nchunks = (nf + 31) >> 5;
     for (int c = 0; c < nchunks; ++c) {
-        uint32_t m = 0;
+        uint32_t m = 0, unsure = 0;
         const int k0 = c << 5;
         const int k1 = min(nf, k0 + 32);
         for (int kb = k0; kb < k1; kb += 8) {
@@ -155,20 +184,26 @@ B3_DEV uint8_t epa_iterate(const Shape& L, const Shape& R, float tolerance, uint
                 const int k = kb + j;
                 if (k < k1) {
                     const float4 f = fb[j];
-                    V3 fnv = v3(f.x, f.y, f.z);
-                    float a2 = dot(fnv, pv) - f.w;
+                    float a2 = dot(v3(f.x, f.y, f.z), pv) - f.w;
                     float S = (fabsf(f.x) * (fabsf(pv.x) + vmax.x) + fabsf(f.y) * (fabsf(pv.y) + vmax.y)) + fabsf(f.z) * (fabsf(pv.z) + vmax.z);
-                    bool vis;
-                    if (fabsf(a2) > S * 9.5367431640625e-07f + 1e-30f) {
-                        vis = a2 > 0.f;
-                    } else {
-                        V3 v0 = ld3(P.vv, P.fi[k] & 0xFF);
-                        vis = dot(fnv, pv - v0) > 0.f;
-                    }
-                    m |= (vis ? 1u : 0u) << (k - k0);
-                    if (!vis) cf.offer(f.w, k);
+                    const bool sure = fabsf(a2) > S * 9.5367431640625e-07f + 1e-30f;  // false for any NaN/inf too
+                    const bool vis = a2 > 0.f;
+                    m |= ((sure && vis) ? 1u : 0u) << (k - k0);
+                    unsure |= (sure ? 0u : 1u) << (k - k0);
+                    if (sure && !vis) cf.offer(f.w, k);
                 }
             }
+        }
+        // the few faces the filter could not decide: the reference's expression as written (kept out of the loop
+        // above so that its gather does not cost issue slots there)
+        while (unsure) {
+            const int b = __ffs(unsure) - 1;
+            unsure &= unsure - 1;
+            const int k = k0 + b;
+            const float4 f = P.fn[k];
+            V3 v0 = ld3(P.vv, P.fi[k] & 0xFF);
+            if (dot(v3(f.x, f.y, f.z), pv - v0) > 0.f) m |= 1u << b;
+            else cf.offer_any(f.w, k);
         }
         vm[c] = m;
     }
@@ -195,9 +230,9 @@ B3_DEV uint8_t epa_iterate(const Shape& L, const Shape& R, float tolerance, uint
             if (!last_bit) cf.moved(lf.w, k);
         }
         uint32_t i0 = idx & 0xFF, i1 = (idx >> 8) & 0xFF, i2 = (idx >> 16) & 0xFF;
-        ok = ok && remove_or_add_edge(P.ed, ne, P.ecap, i0, i1);
-        ok = ok && remove_or_add_edge(P.ed, ne, P.ecap, i1, i2);
-        ok = ok && remove_or_add_edge(P.ed, ne, P.ecap, i2, i0);
+        ok = ok && remove_or_add_edge(P.ed, P.estride, ne, P.ecap, i0, i1);
+        ok = ok && remove_or_add_edge(P.ed, P.estride, ne, P.ecap, i1, i2);
+        ok = ok && remove_or_add_edge(P.ed, P.estride, ne, P.ecap, i2, i0);
         if (WARP) __syncwarp();
     }
     if (!ok || nv >= EPA_VCAP || nf + ne > P.fcap) return ST_CAPACITY;
@@ -210,7 +245,7 @@ B3_DEV uint8_t epa_iterate(const Shape& L, const Shape& R, float tolerance, uint
     ++nv;
     if (WARP) __syncwarp();
     for (int e = 0; e < ne; ++e) {
-        uint32_t ab = P.ed[e];
+        uint32_t ab = P.ed[e * P.estride];
         cf.offer(make_face(P, nf + e, (uint32_t)n, ab & 0xFF, (ab >> 8) & 0xFF), nf + e);
     }
     nf += ne;

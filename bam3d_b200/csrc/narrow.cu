@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(TPB) gjk_contact_kernel(ShapeSetDev S, const u
     } else {
         P.vv = lvv; P.va = lva; P.fn = lfn; P.fi = lfi; P.ed = led;
     }
-    P.fcap = EPA_FCAP; P.ecap = EPA_ECAP;
+    P.fcap = EPA_FCAP; P.ecap = EPA_ECAP; P.estride = 1;
     uint32_t first, end, stride;
     work_range<WARP>(ranges, n, first, end, stride);
     for (uint32_t slot = first; slot < end; slot += stride) {
@@ -281,16 +281,26 @@ __global__ void __launch_bounds__(TPB) gjk_contact_kernel(ShapeSetDev S, const u
 //                      this, a warp ran as long as its slowest pair (iteration counts span 2..100) and ncu showed
 //                      4.4 of 32 lanes active on average.
 // ------------------------------------------------------------------------------------------------------------
-constexpr int EPAQ_REC_F4 = 7;            // queue record: 4 x (v, sup_a) = 24 floats, pair index, 3 pad words
-constexpr size_t EPAQ_HEADER_BYTES = 256;  // [0] = number of records, [1] = consumer cursor
+constexpr int EPAQ_REC_F4 = 7;             // queue record: 4 x (v, sup_a) = 24 floats, pair index, 3 pad words
+constexpr size_t EPAQ_HEADER_BYTES = 1024;  // u32 words: [1] = consumer cursor, [64 + b] = records queued for bin b
+constexpr int EPA_ECAP_SMEM = 24;            // horizon capacity of the thread-per-pair EPA tier (shared memory)
+constexpr int EPAQ_BINS = 49;               // thread-path bins (kindL * 7 + kindR)
+
+// The queue is segmented by pair bin: bin b's records live at [bin_start[b], bin_start[b] + count[b]) — the bin's
+// own slot range of the sorted pair order, so a segment can never overflow — and the EPA kernel consumes the
+// segments in `BinOrder` (heaviest expected EPA work first). Lanes of an EPA warp therefore hold pairs of the same
+// shape-kind combination (same support code, similar polytope sizes: their local-memory loads stay
+// sector-coalesced) except where one segment runs out. Without binning everything is bin 0 at base 0.
+struct BinOrder { uint8_t bin[64]; };
 
 __global__ void __launch_bounds__(TPB) gjk_phase_kernel(ShapeSetDev S, const uint2* __restrict__ pairs, uint32_t n,
                                                         const uint32_t* __restrict__ order, const uint32_t* __restrict__ ranges,
+                                                        const uint8_t* __restrict__ keys, const uint32_t* __restrict__ bin_start,
                                                         SettingsDev cfg, int strategy, unsigned char* __restrict__ queue,
                                                         float4* __restrict__ contacts, uint8_t* __restrict__ status) {
     uint32_t first, end, stride;
     work_range<false>(ranges, n, first, end, stride);
-    uint32_t* q_count = reinterpret_cast<uint32_t*>(queue);
+    uint32_t* q_count = reinterpret_cast<uint32_t*>(queue) + 64;
     float4* q_recs = reinterpret_cast<float4*>(queue + EPAQ_HEADER_BYTES);
     const uint32_t lane = threadIdx.x & 31u;
     // keep the warp convergent for the ballot below: iterate until every lane is past the end
@@ -311,12 +321,15 @@ __global__ void __launch_bounds__(TPB) gjk_phase_kernel(ShapeSetDev S, const uin
         const bool to_epa = valid && st == ST_OK && strategy == 0;
         const uint32_t mask = __ballot_sync(0xFFFFFFFFu, to_epa);
         if (mask) {
-            uint32_t base = 0;
-            const uint32_t leader = __ffs(mask) - 1;
-            if (lane == leader) base = atomicAdd(q_count, (uint32_t)__popc(mask));
-            base = __shfl_sync(0xFFFFFFFFu, base, leader);
             if (to_epa) {
-                float4* r = q_recs + (size_t)(base + __popc(mask & ((1u << lane) - 1u))) * EPAQ_REC_F4;
+                // one atomic per distinct bin per warp (a warp's slots are consecutive in bin order: usually one bin)
+                const uint32_t key = keys ? (uint32_t)keys[p] : 0u;
+                const uint32_t peers = __match_any_sync(mask, key);
+                const uint32_t leader = __ffs(peers) - 1;
+                uint32_t base = 0;
+                if (lane == leader) base = atomicAdd(q_count + key, (uint32_t)__popc(peers));
+                base = __shfl_sync(peers, base, leader) + (bin_start ? __ldg(bin_start + key) : 0u);
+                float4* r = q_recs + (size_t)(base + __popc(peers & ((1u << lane) - 1u))) * EPAQ_REC_F4;
                 r[0] = make_float4(s.v[0].x, s.v[0].y, s.v[0].z, s.a[0].x);
                 r[1] = make_float4(s.a[0].y, s.a[0].z, s.v[1].x, s.v[1].y);
                 r[2] = make_float4(s.v[1].z, s.a[1].x, s.a[1].y, s.a[1].z);
@@ -335,21 +348,49 @@ __global__ void __launch_bounds__(TPB) gjk_phase_kernel(ShapeSetDev S, const uin
 }
 
 __global__ void __launch_bounds__(TPB, 4) epa_refill_kernel(ShapeSetDev S, const uint2* __restrict__ pairs, SettingsDev cfg,
+                                                         const uint32_t* __restrict__ bin_start, BinOrder bo,
                                                          unsigned char* __restrict__ queue, unsigned char* __restrict__ ovf_scratch,
                                                          float4* __restrict__ contacts, uint8_t* __restrict__ status) {
+    // segment table in consumption order: s_pref[i] = records before segment i, s_base[i] = its first record
+    __shared__ uint32_t s_pref[EPAQ_BINS + 1];
+    __shared__ uint32_t s_base[EPAQ_BINS];
+    if (threadIdx.x == 0) {
+        const uint32_t* q_count = reinterpret_cast<const uint32_t*>(queue) + 64;
+        uint32_t acc = 0;
+        for (int i = 0; i < EPAQ_BINS; ++i) {
+            const uint32_t b = bo.bin[i];
+            s_pref[i] = acc;
+            s_base[i] = bin_start ? bin_start[b] : 0u;
+            acc += q_count[b];
+        }
+        s_pref[EPAQ_BINS] = acc;
+    }
+    __syncthreads();
     float lvv[EPA_VCAP * 3];
     float lva[EPA_VCAP * 3];
     float4 lfn[EPA_FCAP];
     uint32_t lfi[EPA_FCAP];
-    uint16_t led[EPA_ECAP];
     PolytopeStore P;
-    P.vv = lvv; P.va = lva; P.fn = lfn; P.fi = lfi; P.ed = led;
-    P.fcap = EPA_FCAP; P.ecap = EPA_ECAP;
-    const uint32_t count = *reinterpret_cast<const uint32_t*>(queue);
+    P.vv = lvv; P.va = lva; P.fn = lfn; P.fi = lfi;
+    P.fcap = EPA_FCAP;
+#ifdef B3_EPA_LOCAL_EDGES
+    uint16_t led[EPA_ECAP];
+    P.ed = led; P.ecap = EPA_ECAP; P.estride = 1;
+#else
+    // Horizon edge list: one shared-memory column per thread. Pass B indexes it data-dependently (every lane at its
+    // own position), which shared memory serves without the 32-lines-per-request cost of divergent local-memory
+    // addresses. The horizon of a well-formed polytope is short (<= 12 edges for 99.7 % of mixed pairs, <= 16 for
+    // all but ~1e-4); a pair that needs more than EPA_ECAP_SMEM goes to the overflow tier like one that outgrows
+    // the face list.
+    __shared__ uint16_t s_ed[EPA_ECAP_SMEM * TPB];
+    P.ed = s_ed + threadIdx.x; P.ecap = EPA_ECAP_SMEM; P.estride = TPB;
+#endif
+    const uint32_t count = s_pref[EPAQ_BINS];
     uint32_t* q_cursor = reinterpret_cast<uint32_t*>(queue) + 1;
     const float4* q_recs = reinterpret_cast<const float4*>(queue + EPAQ_HEADER_BYTES);
     const uint32_t lane = threadIdx.x & 31u;
     bool active = false, exhausted = false;
+    int seg = 0;  // the cursor only grows, so each lane walks the segment table forward
     Shape L, R;
     int nv = 0, nf = 0;
     uint32_t it = 0, p = 0;
@@ -366,7 +407,8 @@ __global__ void __launch_bounds__(TPB, 4) epa_refill_kernel(ShapeSetDev S, const
             if (!active && !exhausted) {
                 const uint32_t idx = base + __popc(need & ((1u << lane) - 1u));
                 if (idx < count) {
-                    const float4* r = q_recs + (size_t)idx * EPAQ_REC_F4;
+                    while (idx >= s_pref[seg + 1]) ++seg;
+                    const float4* r = q_recs + (size_t)(s_base[seg] + (idx - s_pref[seg])) * EPAQ_REC_F4;
                     float4 a = __ldg(r), b = __ldg(r + 1), c = __ldg(r + 2), d = __ldg(r + 3), e = __ldg(r + 4), f = __ldg(r + 5), g = __ldg(r + 6);
                     Simplex<true> s;
                     s.n = 4;
@@ -597,6 +639,29 @@ static int epa_refill_grid() {
     return blocks;
 }
 
+// Consumption order of the queue segments: expected EPA cost per pair, heaviest first, so that the long jobs
+// (sphere-like Minkowski sums: ~67 iterations and ~136 faces at the default tolerance) start early, the light
+// ones (box-box: ~6 iterations) fill the tail, and the pairs that end in the overflow tier are known early.
+static BinOrder epa_bin_order() {
+    static BinOrder bo;
+    static bool ready = false;
+    if (!ready) {
+        // roundness: how much of the shape's surface is smooth
+        const int round[7] = {/*particle*/ 0, /*quad*/ 1, /*sphere*/ 10, /*cuboid*/ 2, /*cylinder*/ 7, /*capsule*/ 10, /*polyhedron*/ 0};
+        int score[EPAQ_BINS];
+        for (int b = 0; b < EPAQ_BINS; ++b) {
+            const int kl = b / 7, kr = b % 7;
+            const bool ball_l = kl == K_SPHERE || kl == K_CAPSULE || kl == K_PARTICLE, ball_r = kr == K_SPHERE || kr == K_CAPSULE || kr == K_PARTICLE;
+            score[b] = round[kl] + round[kr] + ((ball_l && ball_r && round[kl] + round[kr] > 0) ? 100 : 0);
+            bo.bin[b] = (uint8_t)b;
+        }
+        for (int i = 1; i < EPAQ_BINS; ++i)  // stable insertion sort, descending score
+            for (int j = i; j > 0 && score[bo.bin[j]] > score[bo.bin[j - 1]]; --j) { uint8_t t = bo.bin[j]; bo.bin[j] = bo.bin[j - 1]; bo.bin[j - 1] = t; }
+        ready = true;
+    }
+    return bo;
+}
+
 int launch_contact(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs, uint32_t n, const BinScratch* B, bool run_thread,
                    bool run_warp, const SettingsDev& cfg, int strategy, void* d_overflow_scratch, void* d_queue, float4* d_contacts,
                    uint8_t* d_status) {
@@ -608,11 +673,15 @@ int launch_contact(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs, 
     const uint32_t* ranges = B ? B->ranges : nullptr;
     cudaMemsetAsync(ovf, 0, 4, st);
     if (run_thread) {
-        cudaMemsetAsync(queue, 0, 8, st);
-        gjk_phase_kernel<<<thread_grid(n), TPB, 0, st>>>(S, d_pairs, n, order, ranges, cfg, strategy, queue, d_contacts, d_status);
+        const uint8_t* keys = B ? B->keys : nullptr;
+        const uint32_t* bin_start = B ? B->start : nullptr;
+        cudaMemsetAsync(queue, 0, EPAQ_HEADER_BYTES, st);
+        gjk_phase_kernel<<<thread_grid(n), TPB, 0, st>>>(S, d_pairs, n, order, ranges, keys, bin_start, cfg, strategy, queue, d_contacts,
+                                                         d_status);
         ++launched;
         if (strategy == 0) {
-            epa_refill_kernel<<<epa_refill_grid(), TPB, 0, st>>>(S, d_pairs, cfg, queue, ovf, d_contacts, d_status);
+            epa_refill_kernel<<<epa_refill_grid(), TPB, 0, st>>>(S, d_pairs, cfg, bin_start, epa_bin_order(), queue, ovf, d_contacts,
+                                                                 d_status);
             ++launched;
         }
     }

@@ -118,7 +118,8 @@ void orc_gjk_contact_batch(const uint8_t* kind, const float* params, const float
 // Per-pair EPA statistics (polytope face high-water, EPA iterations) for sizing the device tiers; FullResolution.
 void orc_gjk_contact_stats_batch(const uint8_t* kind, const float* params, const float* xform, const uint32_t* mesh_id,
                                  const float* mesh_verts, const uint32_t* mesh_offsets, const uint32_t* pairs, uint64_t n,
-                                 uint32_t* out_max_faces, uint32_t* out_epa_iterations, uint8_t* out_status, int nthreads) {
+                                 uint32_t* out_max_faces, uint32_t* out_epa_iterations, uint8_t* out_status, int nthreads,
+                                 uint32_t* out_max_edges) {
     ShapeTable T{kind, params, xform, mesh_id, mesh_verts, mesh_offsets};
     GJK gjk;
     parallel_for(n, nthreads, [&](uint64_t b, uint64_t e, int) {
@@ -127,6 +128,7 @@ void orc_gjk_contact_stats_batch(const uint8_t* kind, const float* params, const
             Contact c; Status st; Counters cnt;
             gjk.intersection(CollisionStrategy::FullResolution, T.shape(l), T.mat(l), T.shape(r), T.mat(r), c, &st, &cnt);
             out_max_faces[i] = cnt.max_faces; out_epa_iterations[i] = (uint32_t)cnt.epa_iterations; out_status[i] = (uint8_t)st;
+            if (out_max_edges) out_max_edges[i] = cnt.max_edges;
         }
     });
 }
