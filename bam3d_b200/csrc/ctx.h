@@ -23,6 +23,8 @@ struct bam3d_ctx {
     std::string err;
     uint64_t launches = 0;
     bool opt_binning = true;
+    bool opt_epa_tiers = false;   // contact path: shared-memory EPA in size tiers (epa_tiers.cuh) instead of per-thread local-memory EPA
+    bool opt_epa_overlap = true;  // contact path: run the EPA overflow tier on the side stream next to the EPA kernel
     int opt_sap_strategy = 0;  // 0 auto, 1 tiled sweep, 2 BVH overlap query
     int opt_bvh_strategy = 0;  // variable-length queries: 0 auto, 1 tree traversal, 2 all (query, value) tests
     cudaStream_t stream2 = nullptr;  // side stream (Variance3 runs beside the pair search)

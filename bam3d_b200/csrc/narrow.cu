@@ -10,6 +10,7 @@
 //
 // Plain FP32 SIMT: there is no dense contraction anywhere in this path, so tensor cores / TMEM are not used.
 // Compiled with -fmad=false (see vecmath.cuh).
+#include <cstdio>
 #include <cstdlib>
 #include "narrow.h"
 #include "gjk.cuh"
@@ -24,6 +25,10 @@ constexpr int NUM_SMS = 148;        // B200
 constexpr uint32_t KEY_WARP = 49;   // bin of the pairs that involve a polyhedron (thread bins are 0..48)
 constexpr uint32_t ERR_NON_AFFINE = 1u, ERR_BAD_KIND = 2u, ERR_BAD_MESH = 4u;
 constexpr uint32_t OVF_MAX = 65536;  // capacity of the EPA overflow list; pairs beyond it keep ST_CAPACITY
+// Overflow list (head of the overflow scratch): u32 words [0] = entries appended, [1] = consumer cursor,
+// [2] = "every producer kernel has finished", [3] = producer blocks that have exited; entries (pair indices) from
+// byte 256, preset to 0xFFFFFFFF so that a consumer that reserved a position can wait for its value to land.
+constexpr int OVF_COUNT = 0, OVF_CURSOR = 1, OVF_DONE = 2, OVF_EXITED = 3;
 
 // ------------------------------------------------------------------------------------------------------------
 // pack_shapes: Mat4 (16 f32, column-major) + params -> 96-byte ShapeRec with the inverse's linear part.
@@ -165,6 +170,21 @@ __global__ void __launch_bounds__(TPB) bin_scatter_kernel(const uint8_t* __restr
     }
 }
 
+__device__ __forceinline__ void overflow_append(unsigned char* ovf_scratch, uint32_t p) {
+    __threadfence();  // the caller's ST_CAPACITY status / zero contact must land before the consumer can overwrite them
+    const uint32_t slot = atomicAdd(reinterpret_cast<uint32_t*>(ovf_scratch) + OVF_COUNT, 1u);
+    if (slot < OVF_MAX) { reinterpret_cast<uint32_t*>(ovf_scratch + 256)[slot] = p; __threadfence(); }
+}
+// Last thing a producer block does: the block that exits last raises the "producers finished" flag.
+__device__ __forceinline__ void overflow_producer_exit(unsigned char* ovf_scratch) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t* h = reinterpret_cast<uint32_t*>(ovf_scratch);
+        __threadfence();
+        if (atomicAdd(h + OVF_EXITED, 1u) == gridDim.x - 1) atomicExch(h + OVF_DONE, 1u);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // pair loading
 // ------------------------------------------------------------------------------------------------------------
@@ -264,8 +284,7 @@ __global__ void __launch_bounds__(TPB) gjk_contact_kernel(ShapeSetDev S, const u
             contacts[2 * (size_t)p + 1] = make_float4(c.point.x, c.point.y, c.point.z, 0.f);
             status[p] = st;
             if (st == ST_CAPACITY) {  // hand the pair to the overflow tier
-                uint32_t slot = atomicAdd(reinterpret_cast<uint32_t*>(ovf_scratch), 1u);
-                if (slot < OVF_MAX) reinterpret_cast<uint32_t*>(ovf_scratch + 256)[slot] = p;
+                overflow_append(ovf_scratch, p);
             }
         }
         if (WARP) __syncwarp();
@@ -291,16 +310,25 @@ constexpr int EPAQ_BINS = 49;               // thread-path bins (kindL * 7 + kin
 // segments in `BinOrder` (heaviest expected EPA work first). Lanes of an EPA warp therefore hold pairs of the same
 // shape-kind combination (same support code, similar polytope sizes: their local-memory loads stay
 // sector-coalesced) except where one segment runs out. Without binning everything is bin 0 at base 0.
-struct BinOrder { uint8_t bin[64]; };
+// bin[i] = the i-th bin to consume; tier[i] = the shared-memory EPA tier its pairs start in (epa_tiers.cuh).
+struct BinOrder { uint8_t bin[64]; uint8_t tier[64]; };
+// queue header words
+constexpr int QH_CURSOR = 1;        // epa_refill_kernel's cursor
+constexpr int QH_DONE = 4;          // pairs the EPA kernel has finished
+constexpr int QH_STAGE_CURSOR = 32; // + static stage (epa_tiers_kernel)
+constexpr int QH_PROMO_COUNT = 8;   // + tier (1..3)
+constexpr int QH_PROMO_CURSOR = 12; // + tier (1..3)
+constexpr int QH_BIN_COUNT = 64;    // + bin
 
 __global__ void __launch_bounds__(TPB) gjk_phase_kernel(ShapeSetDev S, const uint2* __restrict__ pairs, uint32_t n,
                                                         const uint32_t* __restrict__ order, const uint32_t* __restrict__ ranges,
-                                                        const uint8_t* __restrict__ keys, const uint32_t* __restrict__ bin_start,
-                                                        SettingsDev cfg, int strategy, unsigned char* __restrict__ queue,
+                                                        const uint8_t* __restrict__ keys, uint32_t default_key,
+                                                        const uint32_t* __restrict__ bin_start, SettingsDev cfg, int strategy,
+                                                        unsigned char* __restrict__ queue,
                                                         float4* __restrict__ contacts, uint8_t* __restrict__ status) {
     uint32_t first, end, stride;
     work_range<false>(ranges, n, first, end, stride);
-    uint32_t* q_count = reinterpret_cast<uint32_t*>(queue) + 64;
+    uint32_t* q_count = reinterpret_cast<uint32_t*>(queue) + QH_BIN_COUNT;
     float4* q_recs = reinterpret_cast<float4*>(queue + EPAQ_HEADER_BYTES);
     const uint32_t lane = threadIdx.x & 31u;
     // keep the warp convergent for the ballot below: iterate until every lane is past the end
@@ -323,7 +351,7 @@ __global__ void __launch_bounds__(TPB) gjk_phase_kernel(ShapeSetDev S, const uin
         if (mask) {
             if (to_epa) {
                 // one atomic per distinct bin per warp (a warp's slots are consecutive in bin order: usually one bin)
-                const uint32_t key = keys ? (uint32_t)keys[p] : 0u;
+                const uint32_t key = keys ? (uint32_t)keys[p] : default_key;
                 const uint32_t peers = __match_any_sync(mask, key);
                 const uint32_t leader = __ffs(peers) - 1;
                 uint32_t base = 0;
@@ -355,7 +383,7 @@ __global__ void __launch_bounds__(TPB, 4) epa_refill_kernel(ShapeSetDev S, const
     __shared__ uint32_t s_pref[EPAQ_BINS + 1];
     __shared__ uint32_t s_base[EPAQ_BINS];
     if (threadIdx.x == 0) {
-        const uint32_t* q_count = reinterpret_cast<const uint32_t*>(queue) + 64;
+        const uint32_t* q_count = reinterpret_cast<const uint32_t*>(queue) + QH_BIN_COUNT;
         uint32_t acc = 0;
         for (int i = 0; i < EPAQ_BINS; ++i) {
             const uint32_t b = bo.bin[i];
@@ -386,6 +414,9 @@ __global__ void __launch_bounds__(TPB, 4) epa_refill_kernel(ShapeSetDev S, const
     P.ed = s_ed + threadIdx.x; P.ecap = EPA_ECAP_SMEM; P.estride = TPB;
 #endif
     const uint32_t count = s_pref[EPAQ_BINS];
+#ifdef B3_TIER_TRACE
+    if (threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); atomicMin(reinterpret_cast<unsigned long long*>(queue) + 8, t_); }
+#endif
     uint32_t* q_cursor = reinterpret_cast<uint32_t*>(queue) + 1;
     const float4* q_recs = reinterpret_cast<const float4*>(queue + EPAQ_HEADER_BYTES);
     const uint32_t lane = threadIdx.x & 31u;
@@ -424,6 +455,9 @@ __global__ void __launch_bounds__(TPB, 4) epa_refill_kernel(ShapeSetDev S, const
                     active = true;
                 } else {
                     exhausted = true;
+#ifdef B3_TIER_TRACE
+                    { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); atomicMin(reinterpret_cast<unsigned long long*>(queue) + 9, t_); atomicMax(reinterpret_cast<unsigned long long*>(queue) + 10, t_); }
+#endif
                 }
             }
         }
@@ -437,13 +471,113 @@ __global__ void __launch_bounds__(TPB, 4) epa_refill_kernel(ShapeSetDev S, const
                 contacts[2 * (size_t)p + 1] = make_float4(c.point.x, c.point.y, c.point.z, 0.f);
                 status[p] = st;
                 if (st == ST_CAPACITY) {  // hand the pair to the overflow tier
-                    uint32_t slot = atomicAdd(reinterpret_cast<uint32_t*>(ovf_scratch), 1u);
-                    if (slot < OVF_MAX) reinterpret_cast<uint32_t*>(ovf_scratch + 256)[slot] = p;
+                    overflow_append(ovf_scratch, p);
                 }
                 active = false;
             }
         }
     }
+#ifdef B3_TIER_TRACE
+    if ((threadIdx.x & 31) == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); atomicMax(reinterpret_cast<unsigned long long*>(queue) + 11, t_); atomicMin(reinterpret_cast<unsigned long long*>(queue) + 13, t_); }
+#endif
+    overflow_producer_exit(ovf_scratch);
+}
+
+}  // namespace b3
+#include "epa_tiers.cuh"  // needs load_pair_shape
+namespace b3 {
+
+// Shared-memory EPA in size tiers (epa_tiers.cuh). One warp per block, TIER_WARPS_PER_SM blocks per SM, persistent:
+// every warp walks the static stages (the queue segments that start in tier 2, then tier 1, then tier 0), then
+// serves the promotion lists until every queued pair has a final status.
+constexpr size_t TIER_VA_BYTES = (size_t)NUM_SMS * TIER_WARPS_PER_SM * EPA_VCAP * 32 * sizeof(float4);
+B3_DEV size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+__global__ void __launch_bounds__(32, TIER_WARPS_PER_SM) epa_tiers_kernel(ShapeSetDev S, const uint2* __restrict__ pairs, SettingsDev cfg,
+                                                                         const uint32_t* __restrict__ bin_start, BinOrder bo,
+                                                                         unsigned char* __restrict__ queue, uint32_t n_cap,
+                                                                         unsigned char* __restrict__ ovf_scratch, float4* __restrict__ contacts,
+                                                                         uint8_t* __restrict__ status) {
+    extern __shared__ __align__(16) unsigned char tier_pool[];
+    __shared__ uint32_t s_pref[EPAQ_BINS + 1];
+    __shared__ uint32_t s_base[EPAQ_BINS];
+    uint32_t* qh = reinterpret_cast<uint32_t*>(queue);
+    if (threadIdx.x == 0) {
+        uint32_t acc = 0;
+        for (int i = 0; i < EPAQ_BINS; ++i) {
+            const uint32_t b = bo.bin[i];
+            s_pref[i] = acc;
+            s_base[i] = bin_start ? bin_start[b] : 0u;
+            acc += qh[QH_BIN_COUNT + b];
+        }
+        s_pref[EPAQ_BINS] = acc;
+    }
+    __syncwarp();
+    const uint32_t total = s_pref[EPAQ_BINS];
+    if (total == 0) { overflow_producer_exit(ovf_scratch); return; }
+
+    TierShared sh;
+    sh.S = &S;
+    sh.pairs = pairs;
+    sh.cfg = cfg;
+    sh.q_recs = reinterpret_cast<const float4*>(queue + EPAQ_HEADER_BYTES);
+    unsigned char* lists = queue + EPAQ_HEADER_BYTES + (size_t)n_cap * EPAQ_REC_F4 * 16;
+    sh.promo_count = qh + QH_PROMO_COUNT;
+    sh.promo_list[0] = nullptr;
+    for (int t = 1; t <= 3; ++t) sh.promo_list[t] = reinterpret_cast<uint32_t*>(lists) + (size_t)(t - 1) * n_cap;
+    sh.done = qh + QH_DONE;
+    sh.va = reinterpret_cast<float4*>(lists + align16((size_t)n_cap * 12)) + (size_t)blockIdx.x * EPA_VCAP * 32;
+    sh.ovf_scratch = ovf_scratch;
+    sh.contacts = contacts;
+    sh.status = status;
+    sh.pool = tier_pool;
+
+    TierSource src;
+    src.promo = false;
+    src.count = nullptr; src.list = nullptr;
+    src.s_pref = s_pref; src.s_base = s_base;
+#ifdef B3_TIER_TRACE
+    // development: [8..] u64 header words = earliest start, latest end of each static stage, latest exit (globaltimer ns)
+    unsigned long long* tr = reinterpret_cast<unsigned long long*>(queue) + 8;
+#define B3_TRACE(i, op) do { if (threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); op(tr + (i), t_); } } while (0)
+    B3_TRACE(0, atomicMin);
+#else
+#define B3_TRACE(i, op) do { } while (0)
+#endif
+    // static stages: maximal runs of consecutive queue segments that start in the same tier (at most 8 cursors)
+    int stage = 0;
+    for (int i = 0; i < EPAQ_BINS && stage < 8;) {
+        int j = i + 1;
+        while (j < EPAQ_BINS && bo.tier[j] == bo.tier[i]) ++j;
+        src.lo = s_pref[i]; src.hi = s_pref[j]; src.cursor = qh + QH_STAGE_CURSOR + stage;
+        if (src.hi > src.lo) {
+            if (bo.tier[i] == 2) tier_run<4>(src, sh);
+            else if (bo.tier[i] == 1) tier_run<2>(src, sh);
+            else tier_run<1>(src, sh);
+        }
+        ++stage;
+        i = j;
+    }
+    B3_TRACE(3, atomicMax);
+
+    src.promo = true;
+    src.lo = 0; src.hi = 0;
+    for (;;) {
+        bool any = false;
+        src.cursor = qh + QH_PROMO_CURSOR + 1; src.count = qh + QH_PROMO_COUNT + 1; src.list = sh.promo_list[1];
+        any |= tier_run<2>(src, sh);
+        src.cursor = qh + QH_PROMO_CURSOR + 2; src.count = qh + QH_PROMO_COUNT + 2; src.list = sh.promo_list[2];
+        any |= tier_run<4>(src, sh);
+        src.cursor = qh + QH_PROMO_CURSOR + 3; src.count = qh + QH_PROMO_COUNT + 3; src.list = sh.promo_list[3];
+        any |= tier_run<8>(src, sh);
+        uint32_t d = 0;
+        if (threadIdx.x == 0) d = ld_volatile_u32(sh.done);
+        d = __shfl_sync(FULL, d, 0);
+        if (d >= total) break;
+        if (!any) __nanosleep(1000);
+    }
+    B3_TRACE(4, atomicMax);
+    overflow_producer_exit(ovf_scratch);
 }
 
 // Overflow tier of the contact kernels (epa_big.cuh): the fast-tier kernels append every pair they leave at
@@ -453,18 +587,42 @@ constexpr int OVF_WARPS = NUM_SMS;        // one 32-thread block per SM
 constexpr size_t OVF_HEADER_BYTES = 256 + (size_t)OVF_MAX * 4;
 
 __global__ void __launch_bounds__(32) gjk_contact_overflow_kernel(ShapeSetDev S, const uint2* __restrict__ pairs, SettingsDev cfg,
-                                                                  unsigned char* __restrict__ scratch, float4* __restrict__ contacts,
-                                                                  uint8_t* __restrict__ status) {
-    const uint32_t count = min(*reinterpret_cast<const uint32_t*>(scratch), OVF_MAX);
+                                                                  unsigned char* __restrict__ scratch, int producers_running,
+                                                                  float4* __restrict__ contacts, uint8_t* __restrict__ status) {
+    // producers_running = 0: every producer kernel finished before this launch (stream order), the list is final.
+    // producers_running = 1: launched on a side stream next to the thread-per-pair EPA kernel; entries are taken as
+    // they appear, and the warp leaves once the producers have raised OVF_DONE and the list is drained. (The pairs
+    // that end here are the longest jobs of the whole call, so they should start as early as possible.)
+    uint32_t* hdr = reinterpret_cast<uint32_t*>(scratch);
     const uint32_t* list = reinterpret_cast<const uint32_t*>(scratch + 256);
     const uint32_t warp = blockIdx.x, lane = threadIdx.x;
-    if (warp >= count) return;
+    if (!producers_running && warp >= min(hdr[OVF_COUNT], OVF_MAX)) return;
     extern __shared__ __align__(16) unsigned char ovf_smem[];
     BigStore B = carve_big_store(scratch + OVF_HEADER_BYTES + (size_t)warp * EPA_BIG_SLAB_BYTES, ovf_smem);
     for (int k = lane; k < EPA_KEYS; k += 32) { B.head[k] = EPA_NIL; B.tail[k] = EPA_NIL; }
     __syncwarp();
-    for (uint32_t i = warp; i < count; i += gridDim.x) {
-        uint32_t p = list[i];
+    for (;;) {
+        uint32_t i = 0xFFFFFFFFu;
+        if (lane == 0) {
+            for (;;) {
+                // read the flag BEFORE the count: once the flag is up the count is final
+                const uint32_t done = producers_running ? ld_volatile_u32(hdr + OVF_DONE) : 1u;
+                const uint32_t cnt = min(ld_volatile_u32(hdr + OVF_COUNT), OVF_MAX);
+                const uint32_t cur = ld_volatile_u32(hdr + OVF_CURSOR);
+                if (cur < cnt) {
+                    if (atomicCAS(hdr + OVF_CURSOR, cur, cur + 1) == cur) { i = cur; break; }
+                } else if (done) {
+                    break;
+                } else {
+                    __nanosleep(2000);
+                }
+            }
+        }
+        i = __shfl_sync(0xFFFFFFFFu, i, 0);
+        if (i == 0xFFFFFFFFu) break;
+        uint32_t p = 0;
+        if (lane == 0) { while ((p = ld_volatile_u32(list + i)) == 0xFFFFFFFFu) __nanosleep(200); }
+        p = __shfl_sync(0xFFFFFFFFu, p, 0);
         uint2 pr = __ldg(pairs + p);
         Shape L, R;
         load_pair_shape(L, S, pr.x);
@@ -626,7 +784,11 @@ int launch_intersect(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs
     B3_LAUNCH(gjk_intersect_kernel, 0, S, d_pairs, n, order, ranges, cfg, d_status)
 }
 size_t contact_overflow_scratch_bytes() { return OVF_HEADER_BYTES + (size_t)OVF_WARPS * EPA_BIG_SLAB_BYTES; }
-size_t contact_queue_bytes(uint32_t n) { return EPAQ_HEADER_BYTES + (size_t)n * EPAQ_REC_F4 * 16; }
+// header | n GJK->EPA records | 3 promotion lists of n record indices | sup_a scratch of the shared-memory EPA warps
+static size_t queue_lists_bytes(uint32_t n) { return ((size_t)n * 12 + 15) & ~(size_t)15; }
+size_t contact_queue_bytes(uint32_t n) {
+    return EPAQ_HEADER_BYTES + (size_t)n * EPAQ_REC_F4 * 16 + (n ? queue_lists_bytes(n) + TIER_VA_BYTES : 0);
+}
 
 static int epa_refill_grid() {
     static int blocks = 0;
@@ -648,41 +810,97 @@ static BinOrder epa_bin_order() {
     if (!ready) {
         // roundness: how much of the shape's surface is smooth
         const int round[7] = {/*particle*/ 0, /*quad*/ 1, /*sphere*/ 10, /*cuboid*/ 2, /*cylinder*/ 7, /*capsule*/ 10, /*polyhedron*/ 0};
-        int score[EPAQ_BINS];
+        int tier[EPAQ_BINS], score[EPAQ_BINS];
+        int rim_boost = 150;  // measured on C2: 0 (after the curved bins) 8.4 ms, 150 (right after the ball bins) 7.8 ms, 250 (first) 9.3 ms
+        if (const char* e = getenv("BAM3D_RIM_BOOST")) rim_boost = atoi(e);  // development knob
         for (int b = 0; b < EPAQ_BINS; ++b) {
             const int kl = b / 7, kr = b % 7;
             const bool ball_l = kl == K_SPHERE || kl == K_CAPSULE || kl == K_PARTICLE, ball_r = kr == K_SPHERE || kr == K_CAPSULE || kr == K_PARTICLE;
-            score[b] = round[kl] + round[kr] + ((ball_l && ball_r && round[kl] + round[kr] > 0) ? 100 : 0);
+            const bool flat_l = kl == K_CUBOID || kl == K_QUAD, flat_r = kr == K_CUBOID || kr == K_QUAD;
+            const int sum = round[kl] + round[kr];
+            // starting tier of the shared-memory EPA: ball-like sums need ~71 vertices (tier 2), one curved side ~20-40
+            // (tier 1), box-like pairs < 22 (tier 0); a wrong guess only costs a promotion
+            tier[b] = (ball_l && ball_r && sum > 0) ? 2 : (sum >= 12 ? 1 : 0);
+            // Cylinder against a flat-faced shape early (right after the ball-like bins): cheap on average, but these
+            // bins hold the degenerate pairs (coplanar rim supports) that run to the iteration cap or end in the
+            // overflow tier, the longest jobs of the call: the sooner they are found, the sooner the overflow tier
+            // (running on the side stream) can start on them.
+            const bool rim_vs_flat = (kl == K_CYLINDER && flat_r) || (kr == K_CYLINDER && flat_l);
+            score[b] = sum + 100 * tier[b] + (rim_vs_flat ? rim_boost : 0);
             bo.bin[b] = (uint8_t)b;
         }
         for (int i = 1; i < EPAQ_BINS; ++i)  // stable insertion sort, descending score
             for (int j = i; j > 0 && score[bo.bin[j]] > score[bo.bin[j - 1]]; --j) { uint8_t t = bo.bin[j]; bo.bin[j] = bo.bin[j - 1]; bo.bin[j - 1] = t; }
+        for (int i = 0; i < EPAQ_BINS; ++i) bo.tier[i] = (uint8_t)tier[bo.bin[i]];
         ready = true;
     }
     return bo;
 }
 
 int launch_contact(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs, uint32_t n, const BinScratch* B, bool run_thread,
-                   bool run_warp, const SettingsDev& cfg, int strategy, void* d_overflow_scratch, void* d_queue, float4* d_contacts,
-                   uint8_t* d_status) {
+                   bool run_warp, const SettingsDev& cfg, int strategy, uint32_t default_key, int epa_mode, const ContactSide* side,
+                   void* d_overflow_scratch, void* d_queue, float4* d_contacts, uint8_t* d_status) {
     unsigned char* ovf = reinterpret_cast<unsigned char*>(d_overflow_scratch);
     unsigned char* queue = reinterpret_cast<unsigned char*>(d_queue);
     if (n == 0) return 0;
     int launched = 0;
     const uint32_t* order = B ? B->order : nullptr;
     const uint32_t* ranges = B ? B->ranges : nullptr;
-    cudaMemsetAsync(ovf, 0, 4, st);
+    static bool smem_opt_in = false;
+    if (!smem_opt_in) {
+        cudaFuncSetAttribute(gjk_contact_overflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EPA_BIG_SMEM_BYTES);
+        cudaFuncSetAttribute(epa_tiers_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(gjk_contact_overflow_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        smem_opt_in = true;
+    }
+    cudaMemsetAsync(ovf, 0, 256, st);
+    if (strategy == 0) cudaMemsetAsync(ovf + 256, 0xFF, (size_t)OVF_MAX * 4, st);
+    // The overflow tier runs next to the thread-per-pair EPA kernel (side stream) when that kernel is the only producer
+    // of its list: the pairs that end there are the longest jobs of the call, and the EPA kernel's tail leaves SMs idle.
+    // (Not next to epa_tiers_kernel: the overflow blocks would take the shared memory its blocks need to become resident.)
+    const bool overlap = strategy == 0 && run_thread && !run_warp && side != nullptr && epa_mode == 0;
     if (run_thread) {
         const uint8_t* keys = B ? B->keys : nullptr;
         const uint32_t* bin_start = B ? B->start : nullptr;
         cudaMemsetAsync(queue, 0, EPAQ_HEADER_BYTES, st);
-        gjk_phase_kernel<<<thread_grid(n), TPB, 0, st>>>(S, d_pairs, n, order, ranges, keys, bin_start, cfg, strategy, queue, d_contacts,
-                                                         d_status);
+#ifdef B3_TIER_TRACE
+        cudaMemsetAsync(queue + 64, 0xFF, 16, st);
+        cudaMemsetAsync(queue + 64 + 5 * 8, 0xFF, 8, st);
+#endif
+        gjk_phase_kernel<<<thread_grid(n), TPB, 0, st>>>(S, d_pairs, n, order, ranges, keys, default_key, bin_start, cfg, strategy, queue,
+                                                         d_contacts, d_status);
         ++launched;
-        if (strategy == 0) {
+        if (overlap) cudaEventRecord(side->fork, st);
+        if (strategy == 0 && epa_mode != 0) {
+            cudaMemsetAsync(queue + EPAQ_HEADER_BYTES + (size_t)n * EPAQ_REC_F4 * 16, 0xFF, queue_lists_bytes(n), st);
+            epa_tiers_kernel<<<NUM_SMS * TIER_WARPS_PER_SM, 32, TIER_POOL_BYTES, st>>>(S, d_pairs, cfg, bin_start, epa_bin_order(), queue, n, ovf,
+                                                                                       d_contacts, d_status);
+            ++launched;
+#ifdef B3_TIER_TRACE
+            {
+                unsigned long long h[16];
+                uint32_t w[32];
+                cudaMemcpyAsync(h, queue + 64, sizeof(h), cudaMemcpyDeviceToHost, st);
+                cudaMemcpyAsync(w, queue, sizeof(w), cudaMemcpyDeviceToHost, st);
+                cudaStreamSynchronize(st);
+                fprintf(stderr, "[tier trace] stage2 end %.3f ms, stage1 end %.3f, stage0 end %.3f, exit %.3f | promoted to t1 %u t2 %u t3 %u, done %u\n",
+                        (h[1] - h[0]) * 1e-6, (h[2] - h[0]) * 1e-6, (h[3] - h[0]) * 1e-6, (h[4] - h[0]) * 1e-6, w[QH_PROMO_COUNT + 1],
+                        w[QH_PROMO_COUNT + 2], w[QH_PROMO_COUNT + 3], w[QH_DONE]);
+            }
+#endif
+        } else if (strategy == 0) {
             epa_refill_kernel<<<epa_refill_grid(), TPB, 0, st>>>(S, d_pairs, cfg, bin_start, epa_bin_order(), queue, ovf, d_contacts,
                                                                  d_status);
             ++launched;
+#ifdef B3_TIER_TRACE
+            {
+                unsigned long long h[16];
+                cudaMemcpyAsync(h, queue + 64, sizeof(h), cudaMemcpyDeviceToHost, st);
+                cudaStreamSynchronize(st);
+                fprintf(stderr, "[refill trace] first lane out of work %.3f ms, last lane out of work %.3f ms, first warp exit %.3f, last warp exit %.3f ms\n",
+                        (h[1] - h[0]) * 1e-6, (h[2] - h[0]) * 1e-6, (h[5] - h[0]) * 1e-6, (h[3] - h[0]) * 1e-6);
+            }
+#endif
         }
     }
     if (run_warp) {
@@ -691,12 +909,15 @@ int launch_contact(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs, 
         ++launched;
     }
     if (strategy == 0) {
-        static bool smem_opt_in = false;
-        if (!smem_opt_in) {
-            cudaFuncSetAttribute(gjk_contact_overflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EPA_BIG_SMEM_BYTES);
-            smem_opt_in = true;
+        if (overlap) {
+            // launched AFTER the producer (a tool that serialises kernels then still runs them in a terminating order)
+            cudaStreamWaitEvent(side->stream, side->fork, 0);
+            gjk_contact_overflow_kernel<<<OVF_WARPS, 32, EPA_BIG_SMEM_BYTES, side->stream>>>(S, d_pairs, cfg, ovf, 1, d_contacts, d_status);
+            cudaEventRecord(side->join, side->stream);
+            cudaStreamWaitEvent(st, side->join, 0);
+        } else {
+            gjk_contact_overflow_kernel<<<OVF_WARPS, 32, EPA_BIG_SMEM_BYTES, st>>>(S, d_pairs, cfg, ovf, 0, d_contacts, d_status);
         }
-        gjk_contact_overflow_kernel<<<OVF_WARPS, 32, EPA_BIG_SMEM_BYTES, st>>>(S, d_pairs, cfg, ovf, d_contacts, d_status);
         ++launched;
     }
     return launched;

@@ -45,9 +45,14 @@ int launch_intersect(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs
 // d_queue: contact_queue_bytes(n) for the GJK -> EPA hit queue of the thread-per-pair path.
 size_t contact_overflow_scratch_bytes();
 size_t contact_queue_bytes(uint32_t n);
+// default_key: the (kindL * 7 + kindR) bin of every pair when B is null (a single-kind shape set), else ignored.
+// epa_mode: 1 = shared-memory EPA in size tiers (epa_tiers.cuh), 0 = per-thread local-memory EPA (epa.cuh).
+// side (nullable): a second stream and two events; when given, the EPA overflow tier runs on it concurrently with the
+// thread-per-pair EPA kernel and is joined back into `st` before the call returns.
+struct ContactSide { cudaStream_t stream; cudaEvent_t fork, join; };
 int launch_contact(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs, uint32_t n, const BinScratch* B,
-                   bool run_thread, bool run_warp, const SettingsDev& cfg, int strategy, void* d_overflow_scratch,
-                   void* d_queue, float4* d_contacts, uint8_t* d_status);
+                   bool run_thread, bool run_warp, const SettingsDev& cfg, int strategy, uint32_t default_key, int epa_mode,
+                   const ContactSide* side, void* d_overflow_scratch, void* d_queue, float4* d_contacts, uint8_t* d_status);
 int launch_distance(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs, uint32_t n, const BinScratch* B,
                     bool run_thread, bool run_warp, const SettingsDev& cfg, float* d_ref, float* d_geo, uint8_t* d_status);
 int launch_toi(cudaStream_t st, const ShapeSetDev& S0, const ShapeSetDev& S1, const uint2* d_pairs, uint32_t n,

@@ -152,6 +152,27 @@ def test_contact_parity_mixed(ctx, oracle):
     assert not contacts[~hit].any()
 
 
+@pytest.mark.parametrize("options", [{"epa_overlap": 0}, {"epa_tiers": 1}, {"binning": 0}])
+def test_contact_parity_execution_options(ctx, oracle, options):
+    """The contact path's execution switches change scheduling only: overflow tier in stream order instead of on the
+    side stream, shared-memory EPA tiers (promotion lists, restarts) instead of per-thread polytopes, no pair binning.
+    Same bits out; the scene includes sphere-sphere pairs (tier 2 -> 3 promotions) and overflow-tier pairs."""
+    scene = scenes.all_kinds_pairs(30_000, s=1.0)
+    shapes = shapes_of(ctx, scene)
+    oc, ohit, ost = oracle.contact(scene, strategy=0, nthreads=8)
+    try:
+        for k, v in options.items():
+            ctx.set_option(k, v)
+        contacts, st = b3.GJK.new(ctx).intersection_batch(b3.CollisionStrategy.FullResolution, shapes, scene["pairs"])
+    finally:
+        for k in options:
+            ctx.set_option(k, {"epa_overlap": 1, "epa_tiers": 0, "binning": 1}[k])
+    assert np.array_equal(st, ost), f"{int((st != ost).sum())} status mismatches"
+    hit = st == 0
+    assert_f32_equal("contact", contacts[:, 0:7], oc[:, 0:7], hit)
+    assert (st == b3.STATUS_CAPACITY).sum() == (ost == b3.STATUS_CAPACITY).sum()
+
+
 def test_contact_parity_all_kinds_and_collision_only(ctx, oracle):
     scene = scenes.all_kinds_pairs(40_000, s=1.0)
     shapes = shapes_of(ctx, scene)
