@@ -48,8 +48,10 @@ class SweepAndPrune3:
     def get_sweep_axis(self):  # sweep_prune.rs:50-52
         return self.sweep_axis
 
-    def find_collider_pairs(self, aabbs, capacity=None):
-        """-> (pairs[m, 2], perm[n]). The reference re-sorts `shapes` in place and returns indices into the sorted
+    def find_collider_pairs(self, aabbs, capacity=None, shard=0, n_shards=1):
+        """-> (pairs[m, 2], perm[n]). With n_shards > 1 only the pairs whose higher sorted index falls in this shard's
+        slice are returned (multi-GPU: the sort is replicated, the sweep is sharded; concatenating the shards' pairs
+        in shard order gives the unsharded list). The reference re-sorts `shapes` in place and returns indices into the sorted
         slice (sweep_prune.rs:65-69): pairs index the SORTED order; perm[k] is the original index of sorted slot k, so
         `shapes[:] = shapes[perm]` reproduces the reference's side effect."""
         aabbs = np.ascontiguousarray(aabbs, dtype=np.float32).reshape(-1, 6)
@@ -61,7 +63,8 @@ class SweepAndPrune3:
             pairs = np.empty((cap, 2), dtype=np.uint32)
             axis = C.c_int32(self.sweep_axis)
             cnt = C.c_uint64(0)
-            rc = lib.bam3d_sap_find_pairs(ctx.handle, _ptr(aabbs), n, C.byref(axis), _ptr(perm), _ptr(pairs), cap, C.byref(cnt))
+            rc = lib.bam3d_sap_find_pairs_shard(ctx.handle, _ptr(aabbs), n, C.byref(axis), _ptr(perm), _ptr(pairs), cap, C.byref(cnt),
+                                                int(shard), int(n_shards))
             return rc, cnt.value, (pairs, int(cnt.value), int(axis.value))
 
         res = _retry_capacity(call, capacity if capacity is not None else 8 * n + 1024)

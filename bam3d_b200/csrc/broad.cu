@@ -85,12 +85,14 @@ __global__ void __launch_bounds__(BT) sap_candidates_kernel(const float4* __rest
 // set is exactly "all strictly overlapping (i < j)". Survivors of the filter run the full 3-axis test and are
 // appended through one atomic per warp.
 __global__ void __launch_bounds__(BT) sap_sweep_kernel(const float4* __restrict__ lo, const float4* __restrict__ hi, uint32_t n, int axis,
-                                                       int key_shift, unsigned long long* __restrict__ pair_keys, unsigned long long capacity,
+                                                       uint32_t j_begin, uint32_t j_end, int key_shift,
+                                                       unsigned long long* __restrict__ pair_keys, unsigned long long capacity,
                                                        unsigned long long* __restrict__ count) {
     __shared__ float s_alo[BT], s_blo[BT], s_bhi[BT];
     __shared__ float s_red[BT / 32];
     const int a = axis, b = (axis + 1) % 3;
     const uint32_t i0 = blockIdx.x * BT, i = i0 + threadIdx.x;
+    if (i0 + 1 >= j_end) return;  // shard [j_begin, j_end) of the pairs' higher slot: nothing above this block is in it
     const bool valid = i < n;
     float4 li = make_float4(0, 0, 0, 0), hi_i = make_float4(0, 0, 0, 0);
     if (valid) { li = __ldg(lo + i); hi_i = __ldg(hi + i); }
@@ -106,9 +108,9 @@ __global__ void __launch_bounds__(BT) sap_sweep_kernel(const float4* __restrict_
 #pragma unroll
     for (int w = 1; w < BT / 32; ++w) block_amax = fmaxf(block_amax, s_red[w]);
 
-    for (uint32_t j0 = i0 + 1; j0 < n; j0 += BT) {
+    for (uint32_t j0 = max(i0 + 1, j_begin); j0 < j_end; j0 += BT) {
         const uint32_t j = j0 + threadIdx.x;
-        if (j < n) {
+        if (j < j_end) {
             float4 lj = __ldg(lo + j), hj = __ldg(hi + j);
             s_alo[threadIdx.x] = comp(lj, a); s_blo[threadIdx.x] = comp(lj, b); s_bhi[threadIdx.x] = comp(hj, b);
         } else {
@@ -229,9 +231,10 @@ int launch_sap_variance(cudaStream_t st, const SapScratch& S, uint32_t n, float*
     return 2;
 }
 
-int launch_sap_sweep(cudaStream_t st, uint32_t n, int axis, const SapScratch& S, uint64_t capacity, unsigned long long* d_count) {
+int launch_sap_sweep(cudaStream_t st, uint32_t n, int axis, uint32_t j_begin, uint32_t j_end, const SapScratch& S, uint64_t capacity,
+                     unsigned long long* d_count) {
     cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), st);
-    sap_sweep_kernel<<<(n + BT - 1) / BT, BT, 0, st>>>(S.lo, S.hi, n, axis, sap_bits_for(n), S.pair_keys, capacity, d_count);
+    sap_sweep_kernel<<<(n + BT - 1) / BT, BT, 0, st>>>(S.lo, S.hi, n, axis, j_begin, j_end, sap_bits_for(n), S.pair_keys, capacity, d_count);
     return 1;
 }
 
@@ -688,12 +691,15 @@ int launch_bvh_ray_closest(cudaStream_t st, const BvhDev& T, const float* d_rays
 // and keys are packed (high << key_shift | low) to sort into the reference's (j, i) emission order).
 template <bool FILL>
 __global__ void __launch_bounds__(BT) bvh_collider_pairs_kernel(BvhDev T, const float* __restrict__ aabbs, const uint8_t* __restrict__ dirty,
-                                                                uint32_t* __restrict__ counts, const unsigned long long* __restrict__ offsets,
+                                                                uint32_t v_begin, uint32_t v_end, uint32_t* __restrict__ counts,
+                                                                const unsigned long long* __restrict__ offsets,
                                                                 unsigned long long* __restrict__ keys, int key_shift) {
     uint32_t v = blockIdx.x * BT + threadIdx.x;
     if (v >= T.n) return;
     uint32_t cnt = 0;
-    if (!dirty || dirty[v]) {
+    // dirty == nullptr (sweep-and-prune): a pair is emitted from its HIGHER slot, and only the slots of the shard
+    // [v_begin, v_end) emit — shards then partition the (j, i)-ordered pair list into consecutive pieces.
+    if (dirty ? dirty[v] != 0 : (v >= v_begin && v < v_end)) {
         const float* b = aabbs + 6 * (size_t)v;
         Query q;
         q.qlo = make_float4(b[0], b[1], b[2], 0.f); q.qhi = make_float4(b[3], b[4], b[5], 0.f);
@@ -709,7 +715,7 @@ __global__ void __launch_bounds__(BT) bvh_collider_pairs_kernel(BvhDev T, const 
             if (!accept<BQ_AABB>(q, mn, mx, pt, rel)) continue;
             if (node >= first_leaf) {
                 uint32_t h = __ldg(T.leaf_value + (node - first_leaf));
-                if (h != v && ((dirty && !dirty[h]) || v < h)) {
+                if (h != v && (dirty ? (!dirty[h] || v < h) : h < v)) {
                     if (FILL) keys[w++] = key_shift ? (((unsigned long long)max(v, h) << key_shift) | min(v, h))
                                                     : (((unsigned long long)min(v, h) << 32) | max(v, h));
                     ++cnt;
@@ -724,12 +730,13 @@ __global__ void __launch_bounds__(BT) bvh_collider_pairs_kernel(BvhDev T, const 
     if (!FILL) counts[v] = cnt;
 }
 
-int launch_bvh_collider_pairs(cudaStream_t st, const BvhDev& T, const float* d_aabbs, const uint8_t* d_dirty, uint32_t* d_counts,
-                              const unsigned long long* d_offsets, unsigned long long* d_pair_keys, int key_shift) {
+int launch_bvh_collider_pairs(cudaStream_t st, const BvhDev& T, const float* d_aabbs, const uint8_t* d_dirty, uint32_t v_begin,
+                              uint32_t v_end, uint32_t* d_counts, const unsigned long long* d_offsets, unsigned long long* d_pair_keys,
+                              int key_shift) {
     if (T.n == 0) return 0;
     const int g = (T.n + BT - 1) / BT;
-    if (d_offsets) bvh_collider_pairs_kernel<true><<<g, BT, 0, st>>>(T, d_aabbs, d_dirty, d_counts, d_offsets, d_pair_keys, key_shift);
-    else bvh_collider_pairs_kernel<false><<<g, BT, 0, st>>>(T, d_aabbs, d_dirty, d_counts, d_offsets, d_pair_keys, key_shift);
+    if (d_offsets) bvh_collider_pairs_kernel<true><<<g, BT, 0, st>>>(T, d_aabbs, d_dirty, v_begin, v_end, d_counts, d_offsets, d_pair_keys, key_shift);
+    else bvh_collider_pairs_kernel<false><<<g, BT, 0, st>>>(T, d_aabbs, d_dirty, v_begin, v_end, d_counts, d_offsets, d_pair_keys, key_shift);
     return 1;
 }
 

@@ -29,7 +29,9 @@ int launch_sap_sort(cudaStream_t st, const float* d_aabbs, uint32_t n, int axis,
 // Variance3 in sorted order (six sequential chains); d_sums: 6 floats; d_next_axis: device i32
 int launch_sap_variance(cudaStream_t st, const SapScratch& S, uint32_t n, float* d_sums, int* d_next_axis);
 // phase 2a: tiled forward sweep; d_count: device u64 (pairs found, may exceed capacity)
-int launch_sap_sweep(cudaStream_t st, uint32_t n, int axis, const SapScratch& S, uint64_t capacity, unsigned long long* d_count);
+// Only pairs whose higher sorted slot j lies in [j_begin, j_end) are emitted (the multi-GPU shard of the sweep).
+int launch_sap_sweep(cudaStream_t st, uint32_t n, int axis, uint32_t j_begin, uint32_t j_end, const SapScratch& S, uint64_t capacity,
+                     unsigned long long* d_count);
 // order the first `count` pair keys by (j, i) and unpack them into d_pairs
 int launch_sap_finish(cudaStream_t st, const SapScratch& S, uint64_t count, uint2* d_pairs, uint32_t n);
 
@@ -67,8 +69,11 @@ int launch_bvh_brute(cudaStream_t st, const float* d_aabbs, uint32_t n, int kind
                      const unsigned long long* d_offsets, uint32_t* d_values, void* d_payload);
 int launch_bvh_ray_closest(cudaStream_t st, const BvhDev& T, const float* d_rays, uint32_t nq, uint32_t* d_value, float* d_point_t);
 // DbvtBroadPhase::find_collider_pairs: count / fill passes over the dirty values.
-int launch_bvh_collider_pairs(cudaStream_t st, const BvhDev& T, const float* d_aabbs, const uint8_t* d_dirty, uint32_t* d_counts,
-                              const unsigned long long* d_offsets, unsigned long long* d_pair_keys, int key_shift);
+// d_dirty == nullptr (sweep-and-prune over sorted slots): pairs are emitted from their higher slot, for the slots in
+// [v_begin, v_end) only.
+int launch_bvh_collider_pairs(cudaStream_t st, const BvhDev& T, const float* d_aabbs, const uint8_t* d_dirty, uint32_t v_begin,
+                              uint32_t v_end, uint32_t* d_counts, const unsigned long long* d_offsets, unsigned long long* d_pair_keys,
+                              int key_shift);
 int launch_exclusive_scan_u32_to_u64(cudaStream_t st, const uint32_t* d_in, unsigned long long* d_out, uint32_t n, void* tmp, size_t tmp_bytes);
 size_t scan_tmp_bytes(uint32_t n);
 int launch_sort_u64(cudaStream_t st, unsigned long long* d_keys, unsigned long long* d_alt, uint64_t n, void* tmp, size_t tmp_bytes, bool* in_alt);

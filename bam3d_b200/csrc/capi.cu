@@ -526,9 +526,14 @@ int32_t bam3d_frustum_from_mat4(const float* m, float* out24) {
 // intervals overlap — n x ~24k tests for the C4 scene (a 1-axis sweep prunes little in a 3-D uniform cloud) — while a
 // BVH overlap query over the SORTED boxes (value index = sorted slot) does O(log n + hits) per box. "auto" counts the
 // sweep's candidate tests exactly (binary search per slot) and takes the BVH when they exceed 64 per box.
+// shard / n_shards: only the pairs whose higher sorted slot j lies in [n * shard / n_shards, n * (shard + 1) / n_shards)
+// are searched and returned (the sort is replicated on every GPU, the sweep is sharded by sorted-index range;
+// the shards' outputs, concatenated in shard order, are the unsharded output).
 static int32_t sap_run(bam3d_ctx* ctx, const float* d_aabbs, uint64_t n64, int32_t* inout_axis, uint32_t* d_perm, uint32_t* d_pairs,
-                       uint64_t capacity, uint64_t* out_count) {
+                       uint64_t capacity, uint64_t* out_count, uint32_t shard = 0, uint32_t n_shards = 1) {
     const uint32_t n = (uint32_t)n64;
+    if (n_shards == 0 || shard >= n_shards) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_sap_find_pairs: shard index out of range", cudaSuccess);
+    const uint32_t j_begin = (uint32_t)(n64 * shard / n_shards), j_end = (uint32_t)(n64 * (shard + 1) / n_shards);
     int axis = *inout_axis;
     if (axis < 0 || axis > 2) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_sap_find_pairs: sweep axis must be 0, 1 or 2", cudaSuccess);
     *out_count = 0;
@@ -584,7 +589,7 @@ static int32_t sap_run(bam3d_ctx* ctx, const float* d_aabbs, uint64_t n64, int32
     unsigned long long h_count = 0;
     if (!use_bvh) {
         { KernelTimer kt(ctx);
-          ctx->launches += launch_sap_sweep(ctx->stream, n, axis, S, capacity, d_count); }
+          ctx->launches += launch_sap_sweep(ctx->stream, n, axis, j_begin, j_end, S, capacity, d_count); }
         CU_TRY(cudaMemcpyAsync(&h_count, d_count, 8, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(count)");
         CU_TRY(cudaStreamSynchronize(ctx->stream), "sap sweep");
     } else {
@@ -609,13 +614,13 @@ static int32_t sap_run(bam3d_ctx* ctx, const float* d_aabbs, uint64_t n64, int32
         { KernelTimer kt(ctx);
           ctx->launches += launch_bvh_build(ctx->stream, d_sorted6, n, W, nlo, nhi, children, leaf_value);
           cudaMemsetAsync(d_counts + n, 0, 4, ctx->stream);
-          ctx->launches += launch_bvh_collider_pairs(ctx->stream, T, d_sorted6, nullptr, d_counts, nullptr, nullptr, shift);
+          ctx->launches += launch_bvh_collider_pairs(ctx->stream, T, d_sorted6, nullptr, j_begin, j_end, d_counts, nullptr, nullptr, shift);
           ctx->launches += launch_exclusive_scan_u32_to_u64(ctx->stream, d_counts, d_offsets, n, ctx->cub_tmp.ptr, tmp_bytes); }
         CU_TRY(cudaMemcpyAsync(&h_count, d_offsets + n, 8, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(count)");
         CU_TRY(cudaStreamSynchronize(ctx->stream), "sap bvh count");
         if (h_count <= capacity && h_count) {
             KernelTimer kt(ctx);
-            ctx->launches += launch_bvh_collider_pairs(ctx->stream, T, d_sorted6, nullptr, d_counts, d_offsets, S.pair_keys, shift);
+            ctx->launches += launch_bvh_collider_pairs(ctx->stream, T, d_sorted6, nullptr, j_begin, j_end, d_counts, d_offsets, S.pair_keys, shift);
         }
     }
     if ((rc = check_launch(ctx, "sap pair search"))) return rc;
@@ -636,17 +641,25 @@ static int32_t sap_run(bam3d_ctx* ctx, const float* d_aabbs, uint64_t n64, int32
     return check_launch(ctx, "sap finish");
 }
 
-int32_t bam3d_sap_find_pairs_dev(bam3d_ctx* ctx, const float* d_aabbs, uint64_t n, int32_t* inout_sweep_axis, uint32_t* d_perm,
-                                 uint32_t* d_pairs, uint64_t capacity, uint64_t* out_count) {
+int32_t bam3d_sap_find_pairs_shard_dev(bam3d_ctx* ctx, const float* d_aabbs, uint64_t n, int32_t* inout_sweep_axis, uint32_t* d_perm,
+                                       uint32_t* d_pairs, uint64_t capacity, uint64_t* out_count, uint32_t shard, uint32_t n_shards) {
     if (!ctx || !inout_sweep_axis || !out_count || (n && !d_aabbs) || (capacity && !d_pairs)) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_sap_find_pairs: null argument", cudaSuccess);
     int32_t rc;
     if ((rc = check_n(ctx, n)) || (rc = check_n(ctx, capacity))) return rc;
     CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
-    return sap_run(ctx, d_aabbs, n, inout_sweep_axis, d_perm, d_pairs, capacity, out_count);
+    return sap_run(ctx, d_aabbs, n, inout_sweep_axis, d_perm, d_pairs, capacity, out_count, shard, n_shards);
+}
+int32_t bam3d_sap_find_pairs_dev(bam3d_ctx* ctx, const float* d_aabbs, uint64_t n, int32_t* inout_sweep_axis, uint32_t* d_perm,
+                                 uint32_t* d_pairs, uint64_t capacity, uint64_t* out_count) {
+    return bam3d_sap_find_pairs_shard_dev(ctx, d_aabbs, n, inout_sweep_axis, d_perm, d_pairs, capacity, out_count, 0, 1);
 }
 
 int32_t bam3d_sap_find_pairs(bam3d_ctx* ctx, const float* aabbs, uint64_t n, int32_t* inout_sweep_axis, uint32_t* out_perm,
                              uint32_t* out_pairs, uint64_t capacity, uint64_t* out_count) {
+    return bam3d_sap_find_pairs_shard(ctx, aabbs, n, inout_sweep_axis, out_perm, out_pairs, capacity, out_count, 0, 1);
+}
+int32_t bam3d_sap_find_pairs_shard(bam3d_ctx* ctx, const float* aabbs, uint64_t n, int32_t* inout_sweep_axis, uint32_t* out_perm,
+                                   uint32_t* out_pairs, uint64_t capacity, uint64_t* out_count, uint32_t shard, uint32_t n_shards) {
     if (!ctx || !inout_sweep_axis || !out_count || (n && !aabbs) || (capacity && !out_pairs)) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_sap_find_pairs: null argument", cudaSuccess);
     int32_t rc;
     if ((rc = check_n(ctx, n)) || (rc = check_n(ctx, capacity))) return rc;
@@ -656,7 +669,7 @@ int32_t bam3d_sap_find_pairs(bam3d_ctx* ctx, const float* aabbs, uint64_t n, int
     uint32_t* d_perm = (uint32_t*)((char*)ctx->bp4.ptr + (size_t)(n ? n : 1) * 24);
     uint32_t* d_pairs = (uint32_t*)ctx->bp5.ptr;
     if (n) CU_TRY(cudaMemcpyAsync(d_aabbs, aabbs, n * 24, cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpyAsync(aabbs)");
-    rc = sap_run(ctx, d_aabbs, n, inout_sweep_axis, d_perm, d_pairs, capacity, out_count);
+    rc = sap_run(ctx, d_aabbs, n, inout_sweep_axis, d_perm, d_pairs, capacity, out_count, shard, n_shards);
     if (rc != BAM3D_OK) return rc;
     if (out_perm && n) CU_TRY(cudaMemcpyAsync(out_perm, d_perm, n * 4, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(perm)");
     if (*out_count) CU_TRY(cudaMemcpyAsync(out_pairs, d_pairs, *out_count * 8, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(pairs)");
@@ -844,7 +857,7 @@ int32_t bam3d_bvh_find_collider_pairs(bam3d_ctx* ctx, const bam3d_bvh* t, const 
     cudaMemsetAsync(d_counts + n, 0, 4, ctx->stream);
     BvhDev T = bvh_view(t);
     { KernelTimer kt(ctx);
-      ctx->launches += launch_bvh_collider_pairs(ctx->stream, T, t->d_aabbs, d_dirty, d_counts, nullptr, nullptr, 0); }
+      ctx->launches += launch_bvh_collider_pairs(ctx->stream, T, t->d_aabbs, d_dirty, 0, 0, d_counts, nullptr, nullptr, 0); }
     ctx->launches += launch_exclusive_scan_u32_to_u64(ctx->stream, d_counts, d_offsets, n, ctx->cub_tmp.ptr, scan_bytes);
     if ((rc = check_launch(ctx, "bvh collider pairs (count)"))) return rc;
     unsigned long long total = 0;
@@ -857,7 +870,7 @@ int32_t bam3d_bvh_find_collider_pairs(bam3d_ctx* ctx, const bam3d_bvh* t, const 
     if ((rc = ctx->bp3.reserve(ctx, total * 8 * 2)) || (rc = ctx->bp4.reserve(ctx, total * 8)) || (rc = ctx->cub_tmp.reserve(ctx, sort_bytes > scan_bytes ? sort_bytes : scan_bytes))) return rc;
     unsigned long long* keys = (unsigned long long*)ctx->bp3.ptr;
     { KernelTimer kt(ctx);
-      ctx->launches += launch_bvh_collider_pairs(ctx->stream, T, t->d_aabbs, d_dirty, d_counts, d_offsets, keys, 0); }
+      ctx->launches += launch_bvh_collider_pairs(ctx->stream, T, t->d_aabbs, d_dirty, 0, 0, d_counts, d_offsets, keys, 0); }
     bool in_alt = false;
     ctx->launches += launch_sort_u64(ctx->stream, keys, keys + total, total, ctx->cub_tmp.ptr, sort_bytes, &in_alt);
     ctx->launches += launch_unpack_pairs(ctx->stream, in_alt ? keys + total : keys, total, (uint2*)ctx->bp4.ptr, true);

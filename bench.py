@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — the hot path of bam3d on B200: batched GJK+EPA contact generation (pairs/s).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c1|c2|c3|toi]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c1|c2|c3|toi|c4|c5]
 
 A step is one pass of the narrow phase over one batch of synthetic pairs:
   c2 (default, BASELINE.json configs[1]): GJK3+EPA3 Contact (FullResolution) on 2^20 mixed Sphere/Cuboid/Cylinder
@@ -37,6 +37,7 @@ ALGO_BYTES = {  # algorithmic HBM bytes per pair
     "c3": 124.0,   # 2 x 48 B + 2 x 4 B mesh id + 40 B x hit rate (vertex reads are L2 traffic)
     "toi": 264.0,  # 4 x 48 + 2 x 16 + 40 B out
     "c4": 220.0,   # per box: 24 B read + 4 B perm + 8 radix passes x 2 x 12 B; plus 8 B per emitted pair (added below)
+    "c5": 0.4 * 148.0 + 0.2 * 129.0 + 0.2 * 124.0 + 0.2 * 264.0,  # the C5 mix of the four rows above (162.6 B/pair)
 }
 # DRAM traffic of the dominant kernel per launch (bytes), from the committed ncu captures (profiles/r1_*_ncu_full.txt);
 # for C2 it is far above the algorithmic bytes because the EPA polytopes live in per-thread local memory that
@@ -47,11 +48,14 @@ WORKLOAD_DESC = {
     "c2": "C2: GJK+EPA Contact (FullResolution), 2^20 mixed Sphere/Cuboid/Cylinder pairs per GPU (offset U[-1.5,1.5]^3)",
     "c3": "C3: GJK+EPA Contact, 2^20 ConvexPolyhedron pairs per GPU (4096-mesh library, 64-256 vertices, warp-cooperative support)",
     "toi": "TOI: GJK time of impact, 2^20 mixed Sphere/Cuboid/Cylinder pairs per GPU (end = start + U[-3,3]^3)",
+    "c5": "C5: mixed convex pairs per GPU slice: 40 % analytic GJK+EPA contact (C2 mix), 20 % GJK intersect only, 20 % "
+          "ConvexPolyhedron GJK+EPA contact (C3 library), 20 % GJK time of impact; contacts compacted and all-gathered (NCCL) "
+          "every step; 2^23 pairs per GPU = 64M pairs on 8 GPUs",
     "c4": "C4: SweepAndPrune3 broad phase over 2^22 Aabb3 per GPU (centres U[0,100]^3, half-extents U[0.1,0.5]^3), "
           "plus BVH build and 2^16 ray / 64 frustum queries reported in `extra`",
 }
 METRIC = {"c1": "gjk_intersect_pairs_per_sec", "c2": "gjk_epa_contact_pairs_per_sec", "c3": "gjk_epa_contact_pairs_per_sec",
-          "toi": "gjk_toi_pairs_per_sec", "c4": "sap_candidate_pairs_per_sec"}
+          "toi": "gjk_toi_pairs_per_sec", "c4": "sap_candidate_pairs_per_sec", "c5": "mixed_narrow_phase_pairs_per_sec"}
 
 
 def make_scene(workload, n, rank):
@@ -99,6 +103,8 @@ def run_reference(args):
         return 0
     if args.workload == "c4":
         return run_reference_c4(args)
+    if args.workload == "c5":
+        return run_reference_c5(args)
     n = args.pairs
     cores = os.cpu_count() or 1
     scene = make_scene(args.workload, n, 0)
@@ -235,7 +241,9 @@ def run_ours_c4(args):
     from bam3d_b200 import broad, build, scenes
     build.build()
     n = args.boxes
-    boxes, L = scenes.aabb_scene(n, start=rank * n, extent=100.0 * (n / float(1 << 22)) ** (1.0 / 3.0))
+    # N > 1: every rank holds the SAME box set and sorts all of it (replicated sort); the pair search is
+    # sharded by the pairs' higher sorted slot, so the ranks' pair slices are disjoint and concatenate to the full list
+    boxes, L = scenes.aabb_scene(n, start=0, extent=100.0 * (n / float(1 << 22)) ** (1.0 / 3.0))
     ctx = b3.Context(local_rank)
     lib, h = ctx._lib, ctx.handle
     ext = torch.cuda.ExternalStream(ctx.stream, device=dev)
@@ -248,7 +256,7 @@ def run_ours_c4(args):
 
     def step_resident():
         axis = C.c_int32(0)
-        ctx.check(lib.bam3d_sap_find_pairs_dev(h, p(d_boxes), n, C.byref(axis), p(d_perm), p(d_pairs), cap, C.byref(cnt)))
+        ctx.check(lib.bam3d_sap_find_pairs_shard_dev(h, p(d_boxes), n, C.byref(axis), p(d_perm), p(d_pairs), cap, C.byref(cnt), rank, world))
 
     def sync_all():
         ctx.synchronize(); torch.cuda.synchronize()
@@ -277,7 +285,11 @@ def run_ours_c4(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
-    value = world * npairs * args.steps / (ms_max * 1e-3)
+    tot = torch.tensor([npairs], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    npairs_total = int(tot.item())  # pairs of the whole box set: the ranks' shards are disjoint
+    value = npairs_total * args.steps / (ms_max * 1e-3)
 
     # e2e: host boxes in, perm + pairs out through the host-buffer call
     h_boxes = torch.from_numpy(boxes).pin_memory()
@@ -287,7 +299,7 @@ def run_ours_c4(args):
 
     def step_e2e():
         axis = C.c_int32(0)
-        ctx.check(lib.bam3d_sap_find_pairs(h, hp(h_boxes), n, C.byref(axis), hp(h_perm), hp(h_pairs), cap, C.byref(cnt)))
+        ctx.check(lib.bam3d_sap_find_pairs_shard(h, hp(h_boxes), n, C.byref(axis), hp(h_perm), hp(h_pairs), cap, C.byref(cnt), rank, world))
     e2e_steps = max(3, min(args.steps, 5))
     step_e2e(); sync_all()
     t0 = time.perf_counter()
@@ -297,7 +309,7 @@ def run_ours_c4(args):
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * npairs * e2e_steps / float(t.item())
+    e2e_value = npairs_total * e2e_steps / float(t.item())
 
     extra = {}
     if rank == 0:
@@ -325,11 +337,11 @@ def run_ours_c4(args):
         sboxes, _ = scenes.aabb_scene(ns, extent=100.0 * (ns / float(1 << 22)) ** (1.0 / 3.0))
         t0 = time.perf_counter(); opairs, _, _ = orc.sap_find_pairs(sboxes, 0); cpu_dt = time.perf_counter() - t0
         line = {"metric": METRIC["c4"], "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic",
-                "config": {"workload": WORKLOAD_DESC["c4"], "boxes_per_gpu": n, "pairs_per_gpu": npairs,
+                "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": WORKLOAD_DESC["c4"], "boxes": n, "pairs_total": npairs_total, "pairs_rank0": npairs,
                            "l2": "inputs larger than L2 (96 MB boxes + 190 MB sort/sorted-box scratch + pair keys); no flush",
-                           "multi_gpu": "replicas (each rank sweeps its own box set)" if world > 1 else "single GPU"},
+                           "multi_gpu": "replicated sort, pair search sharded by the pairs' higher sorted slot (no collective)" if world > 1 else "single GPU"},
                 "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": n * 24, "d2h_bytes_per_step": n * 4 + npairs * 8,
                         "steps": e2e_steps, "path": "host-buffer bam3d_sap_find_pairs, pinned host memory"},
                 "gpu_launches": launches, "clocks": clocks,
@@ -346,11 +358,229 @@ def run_ours_c4(args):
     return 0
 
 
+
+# ---------------------------------------------------------------------------------------------------------
+# C5: the 64M mixed configuration, one contiguous slice per GPU
+# ---------------------------------------------------------------------------------------------------------
+C5_PARTS = (("contact", 0.4), ("intersect", 0.2), ("poly", 0.2), ("toi", 0.2))
+
+
+def c5_scenes(n, rank):
+    """The four sub-batches of one rank's C5 slice (seed ...0005). Sizes are multiples of 1024."""
+    from bam3d_b200 import scenes
+    sizes = {k: int(n * f) // 1024 * 1024 for k, f in C5_PARTS}
+    sizes["contact"] += n - sum(sizes.values())
+    seed = scenes.SEED_C5
+    out = {}
+    out["contact"] = scenes.mixed_pairs(sizes["contact"], s=1.5, seed=seed, start=rank * sizes["contact"])
+    out["intersect"] = scenes.mixed_pairs(sizes["intersect"], s=1.5, seed=seed + 1, start=rank * sizes["intersect"])
+    out["poly"] = scenes.polyhedron_pairs(sizes["poly"], n_meshes=4096, s=2.0, start=rank * sizes["poly"])
+    t = scenes.mixed_pairs(sizes["toi"], s=4.0, seed=seed + 2, start=rank * sizes["toi"])
+    t["xform_end"] = scenes.end_transforms(t, start=2 * rank * sizes["toi"])
+    out["toi"] = t
+    return out, sizes
+
+
+def c5_oracle_run(parts, nthreads):
+    from tests.oracle_ffi import Oracle
+    orc = Oracle()
+
+    def run():
+        orc.contact(parts["contact"], strategy=0, nthreads=nthreads)
+        orc.intersect(parts["intersect"], nthreads=nthreads)
+        orc.contact(parts["poly"], strategy=0, nthreads=nthreads)
+        orc.toi(parts["toi"], parts["toi"]["xform_end"], nthreads=nthreads)
+    return run
+
+
+def c5_sample(parts, n_sample):
+    """The same 40/20/20/20 mix on the first pairs of every sub-batch."""
+    out = {}
+    for k, f in C5_PARTS:
+        sub = dict(parts[k])
+        sub["pairs"] = parts[k]["pairs"][: max(1, int(n_sample * f))]
+        out[k] = sub
+    return out
+
+
+def run_reference_c5(args):
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
+    cores = os.cpu_count() or 1
+    n_sample = min(args.pairs, args.cpu_pairs)
+    parts, _ = c5_scenes(max(n_sample, 8192), 0)
+    sample = c5_sample(parts, n_sample)
+    n_done = sum(len(v["pairs"]) for v in sample.values())
+    once = c5_oracle_run(sample, cores)
+    for _ in range(args.warmup):
+        once()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        once()
+    dt = time.perf_counter() - t0
+    value = n_done * args.steps / dt
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC["c5"], "value": value, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD_DESC["c5"], "pairs_per_step": n_done,
+                   "note": "reference crate (Rust) cannot be built in this image; this arm times the strict-f32 C++ restatement of its code path"},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port",
+                         "sample": f"{n_done} pairs of the C5 mix per step, std::thread static partition over {cores} threads"},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+    return 0
+
+
+def run_ours_c5(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0")); local_rank = int(os.environ.get("LOCAL_RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; bam3d_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    import bam3d_b200 as b3
+    from bam3d_b200 import build, multi
+    build.build()
+    n = args.pairs
+    parts, sizes = c5_scenes(n, rank)
+    ctx = b3.Context(local_rank)
+    gjk = b3.GJK.new(ctx)
+    lib, h = ctx._lib, ctx.handle
+    ext = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    meshes = b3.MeshLibrary(ctx, parts["poly"]["mesh_verts"], parts["poly"]["mesh_offsets"])
+    shp = {k: b3.ShapeSet(ctx, v["kind"], v["params"], v["xform"], v.get("mesh_id"), meshes if k == "poly" else None) for k, v in parts.items()}
+    shp_end = b3.ShapeSet(ctx, parts["toi"]["kind"], parts["toi"]["params"], parts["toi"]["xform_end"])
+    d_pairs = {k: torch.from_numpy(v["pairs"].astype(np.int32).reshape(-1)).to(dev) for k, v in parts.items()}
+    # dense outputs of the three contact-producing sub-batches share one buffer so that one compaction feeds the gather
+    order = ("contact", "poly", "toi")
+    off = {}
+    acc = 0
+    for k in order:
+        off[k] = acc
+        acc += sizes[k]
+    n_dense = acc
+    d_status = torch.empty(n_dense, dtype=torch.uint8, device=dev)
+    d_contacts = torch.empty(n_dense * 8, dtype=torch.float32, device=dev)
+    d_status_i = torch.empty(sizes["intersect"], dtype=torch.uint8, device=dev)
+    d_compact = torch.empty(n_dense * 10, dtype=torch.int32, device=dev)
+    d_count = torch.zeros(1, dtype=torch.int64, device=dev)
+    gathered = torch.empty(world * n_dense * 10, dtype=torch.int32, device=dev) if world > 1 else None
+    counts = torch.zeros(world, dtype=torch.int64, device=dev) if world > 1 else None
+    pc = lambda t, o=0: C.c_void_p(t.data_ptr() + o)
+    FR = b3.CollisionStrategy.FullResolution
+
+    def step_resident():
+        gjk.intersection_dev(FR, shp["contact"], pc(d_pairs["contact"]), sizes["contact"], pc(d_contacts, 32 * off["contact"]), pc(d_status, off["contact"]))
+        gjk.intersect_dev(shp["intersect"], pc(d_pairs["intersect"]), sizes["intersect"], pc(d_status_i))
+        gjk.intersection_dev(FR, shp["poly"], pc(d_pairs["poly"]), sizes["poly"], pc(d_contacts, 32 * off["poly"]), pc(d_status, off["poly"]))
+        gjk.intersection_time_of_impact_dev(shp["toi"], shp_end, pc(d_pairs["toi"]), sizes["toi"], pc(d_contacts, 32 * off["toi"]), pc(d_status, off["toi"]))
+        gjk.compact_contacts_dev(pc(d_contacts), pc(d_status), n_dense, rank * n_dense, pc(d_compact), n_dense, pc(d_count))
+        if world > 1:
+            with torch.cuda.stream(ext):
+                multi.gather_contacts(d_compact, d_count, counts_buf=counts, out=gathered)
+
+    def sync_all():
+        ctx.synchronize(); torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(); torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    for _ in range(args.warmup):
+        step_resident()
+    sync_all()
+    ctx.set_option("timing", 1); ctx.read_timing()
+    launches0 = ctx.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.time(); ev0.record(ext)
+    for _ in range(args.steps):
+        step_resident()
+    ev1.record(ext); sync_all(); w1 = time.time()
+    ms = ev0.elapsed_time(ev1)
+    kernel_ms, kernel_calls = ctx.read_timing(); ctx.set_option("timing", 0)
+    launches = ctx.launch_count - launches0
+    clocks = None
+    if sampler:
+        sampler.window(w0, w1); clocks = sampler.stop(); clocks["note"] = "sampled during the timed region"
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * n * args.steps / (ms_max * 1e-3)
+    n_hits = int(d_count.item())
+
+    # e2e: host transforms + pairs in, status (+ contacts) out, through the host-buffer C ABI, per sub-batch
+    hx = {k: torch.from_numpy(v["xform"]).pin_memory() for k, v in parts.items()}
+    hx_end = torch.from_numpy(parts["toi"]["xform_end"]).pin_memory()
+    hpairs = {k: torch.from_numpy(v["pairs"].astype(np.int32)).pin_memory() for k, v in parts.items()}
+    hst = {k: torch.empty(sizes[k], dtype=torch.uint8).pin_memory() for k in sizes}
+    hct = {k: torch.empty((sizes[k], 8), dtype=torch.float32).pin_memory() for k in order}
+    hp = lambda t: C.c_void_p(t.data_ptr())
+    S = C.byref(gjk.settings)
+
+    def step_e2e():
+        for k in sizes:
+            ctx.check(lib.bam3d_shapes_set_transforms(h, shp[k].handle, hp(hx[k])))
+        ctx.check(lib.bam3d_shapes_set_transforms(h, shp_end.handle, hp(hx_end)))
+        ctx.check(lib.bam3d_gjk_contact(h, shp["contact"].handle, hp(hpairs["contact"]), sizes["contact"], S, 0, hp(hct["contact"]), hp(hst["contact"])))
+        ctx.check(lib.bam3d_gjk_intersect(h, shp["intersect"].handle, hp(hpairs["intersect"]), sizes["intersect"], S, hp(hst["intersect"])))
+        ctx.check(lib.bam3d_gjk_contact(h, shp["poly"].handle, hp(hpairs["poly"]), sizes["poly"], S, 0, hp(hct["poly"]), hp(hst["poly"])))
+        ctx.check(lib.bam3d_gjk_time_of_impact(h, shp["toi"].handle, shp_end.handle, hp(hpairs["toi"]), sizes["toi"], S, hp(hct["toi"]), hp(hst["toi"])))
+    h2d = sum(len(v["kind"]) * 64 + len(v["pairs"]) * 8 for v in parts.values()) + len(parts["toi"]["kind"]) * 64
+    d2h = n + n_dense * 32
+    e2e_steps = max(3, min(args.steps, 5))
+    step_e2e(); sync_all()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * n * e2e_steps / float(t.item())
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        step_kernel_ms = kernel_ms / max(1, args.steps)
+        achieved = ALGO_BYTES["c5"] * n / (step_kernel_ms * 1e-3) / 1e9
+        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
+        cores = os.cpu_count() or 1
+        sample = c5_sample(parts, min(n, args.cpu_pairs))
+        n_sample = sum(len(v["pairs"]) for v in sample.values())
+        once = c5_oracle_run(sample, cores)
+        once()
+        best = 1e30
+        for _ in range(2):
+            t0 = time.perf_counter(); once(); best = min(best, time.perf_counter() - t0)
+        print(json.dumps({
+            "metric": METRIC["c5"], "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD_DESC["c5"], "pairs_per_gpu": n, "sub_batches": sizes, "contacts_per_gpu_rank0": n_hits,
+                       "l2": "inputs larger than L2 (shape records 96 B x 2 per pair); no flush",
+                       "multi_gpu": "contiguous pair slices, per-rank compaction, NCCL all-gather of Contact40 records each step" if world > 1 else "single GPU"},
+            "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                    "path": "bam3d_shapes_set_transforms + host-buffer bam3d_gjk_* calls per sub-batch, pinned host memory"},
+            "gpu_launches": launches, "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "kernel": "epa_refill_kernel and gjk_contact_kernel<true> dominate (see the c2 / c3 lines and profiles/)",
+                         "kernel_ms_per_step": step_kernel_ms, "algorithmic_bytes_per_pair": ALGO_BYTES["c5"], "peak_source": peak_src,
+                         "note": "plain-FP32 SIMT, compute/latency bound"},
+            "cpu_baseline": {"value": n_sample / best, "unit": "pairs/s", "cores": cores, "kind": "port",
+                             "sample": f"{n_sample} pairs with the same 40/20/20/20 mix, best of 2, std::thread static partition"}}), flush=True)
+    if world > 1:
+        dist.barrier(); dist.destroy_process_group()
+    return 0
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
     if args.workload == "c4":
         return run_ours_c4(args)
+    if args.workload == "c5":
+        return run_ours_c5(args)
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -539,11 +769,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(ALGO_BYTES))
-    ap.add_argument("--pairs", type=int, default=1 << 20, help="pairs per GPU per step")
+    ap.add_argument("--pairs", type=int, default=None, help="pairs per GPU per step (default 2^20; c5: 2^23)")
     ap.add_argument("--cpu-pairs", type=int, default=1 << 20, help="pairs in the CPU sample")
     ap.add_argument("--boxes", type=int, default=1 << 22, help="c4: boxes per GPU")
     ap.add_argument("--cpu-boxes", type=int, default=1 << 17, help="c4: boxes in the CPU sample (the CPU sweep is O(n^(5/3)))")
     args = ap.parse_args()
+    if args.pairs is None:
+        args.pairs = (1 << 23) if (args.workload == "c5" and args.impl == "ours") else (1 << 20)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         return run_reference(args)

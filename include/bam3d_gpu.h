@@ -182,6 +182,16 @@ int32_t bam3d_sap_find_pairs(bam3d_ctx* ctx, const float* aabbs, uint64_t n, int
 int32_t bam3d_sap_find_pairs_dev(bam3d_ctx* ctx, const float* d_aabbs, uint64_t n, int32_t* inout_sweep_axis,
                                  uint32_t* d_perm, uint32_t* d_pairs, uint64_t capacity, uint64_t* out_count);
 
+/* Multi-GPU form: every GPU sorts the full box set (identical perm and next axis everywhere) and searches
+ * only the pairs whose higher sorted position j lies in [n * shard / n_shards, n * (shard + 1) / n_shards). The shards'
+ * outputs concatenated in shard order are exactly the output of bam3d_sap_find_pairs, so each GPU can feed its slice
+ * straight into its narrow phase with no pair exchange. capacity / *out_count refer to this shard's pairs. */
+int32_t bam3d_sap_find_pairs_shard(bam3d_ctx* ctx, const float* aabbs, uint64_t n, int32_t* inout_sweep_axis, uint32_t* out_perm,
+                                   uint32_t* out_pairs, uint64_t capacity, uint64_t* out_count, uint32_t shard, uint32_t n_shards);
+int32_t bam3d_sap_find_pairs_shard_dev(bam3d_ctx* ctx, const float* d_aabbs, uint64_t n, int32_t* inout_sweep_axis,
+                                       uint32_t* d_perm, uint32_t* d_pairs, uint64_t capacity, uint64_t* out_count,
+                                       uint32_t shard, uint32_t n_shards);
+
 /* ComputeBound<Aabb3> of every packed primitive (sphere.rs:27-34, cuboid.rs:66-73, cylinder.rs:64-71,
  * capsule.rs:51-58, quad.rs:62-69, polyhedron.rs:84-86, primitive3.rs:83-96) moved to world space with
  * Aabb::transform (aabb3.rs:89-96): n x 6 f32. */

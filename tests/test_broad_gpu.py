@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 import bam3d_b200 as b3
-from bam3d_b200 import broad, scenes
+from bam3d_b200 import broad, multi, scenes
 
 pytestmark = pytest.mark.gpu
 
@@ -32,6 +32,23 @@ def test_sap_parity_and_axis_sequence(ctx, oracle, sap_strategy):
         assert np.array_equal(pairs, opairs)          # same pairs in the same (j asc, i asc) order
         assert sap.get_sweep_axis() == oaxis
         axis = oaxis
+
+
+@pytest.mark.parametrize("n_shards", [2, 3, 8])
+def test_sap_shards_concatenate_to_the_full_list(ctx, oracle, sap_strategy, n_shards):
+    """Multi-GPU form of the sweep: every shard sorts everything (same perm, same next axis) and searches
+    the pairs whose higher sorted slot lies in its slice; concatenated in shard order they are the oracle's list."""
+    boxes, L = scenes.aabb_scene(40_000)
+    opairs, operm, oaxis = oracle.sap_find_pairs(boxes, 0)
+    got = []
+    for shard in range(n_shards):
+        sap = broad.SweepAndPrune3.new(ctx)
+        pairs, perm = sap.find_collider_pairs(boxes, shard=shard, n_shards=n_shards)
+        lo, hi = multi.sap_shard_range(len(boxes), shard, n_shards)
+        assert np.array_equal(perm, operm) and sap.get_sweep_axis() == oaxis
+        assert len(pairs) == 0 or (pairs[:, 1].min() >= lo and pairs[:, 1].max() < hi)
+        got.append(pairs)
+    assert np.array_equal(np.concatenate(got), opairs)
 
 
 @pytest.mark.parametrize("scale", [(1.0, 1.0, 1.0), (1.0, 30.0, 1.0), (0.05, 1.0, 40.0)])

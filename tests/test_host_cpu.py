@@ -139,3 +139,42 @@ def test_contact_gather_over_gloo_world_size_2():
     for rank, counts, allrec in res:
         assert counts == [5, 8]
         assert [v for rec in allrec for v in rec] == want
+
+
+def _sap_shard_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    from bam3d_b200 import multi, scenes
+    from tests.oracle_ffi import Oracle
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    boxes, _ = scenes.aabb_scene(3000)
+    # stand-in for the device call on this rank: the replicated sort + the sweep restricted to this rank's j-range
+    pairs, perm, axis = Oracle().sap_find_pairs(boxes, 0)
+    lo, hi = multi.sap_shard_range(len(boxes), rank, world)
+    mine = pairs[(pairs[:, 1] >= lo) & (pairs[:, 1] < hi)].astype(np.int32)
+    # like the device buffers, the send buffer has room for the largest slice (the payload all-gather is padded to it)
+    buf = torch.from_numpy(np.concatenate([mine.reshape(-1), np.full(2 * len(pairs), -1, dtype=np.int32)]))
+    gathered, counts = multi.gather_pairs(buf, torch.tensor([len(mine)], dtype=torch.int64))
+    allp = multi.unpack_gathered(gathered, counts, words=2).numpy()
+    q.put((rank, counts.tolist(), bool(np.array_equal(allp, pairs.astype(np.int32))), len(pairs)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sap_shards_gather_over_gloo_world_size_2(oracle):
+    """SURVEY 8e for the broad phase: the sort is replicated, the sweep is sharded by the pairs' higher sorted slot; the
+    per-rank slices, gathered in rank order, are the unsharded (j asc, i asc) pair list. CPU tensors, world_size 2."""
+    import torch.multiprocessing as mp
+    ctxm = mp.get_context("spawn")
+    q = ctxm.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctxm.Process(target=_sap_shard_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, counts, same, total in res:
+        assert same and sum(counts) == total > 1000 and min(counts) > 0
