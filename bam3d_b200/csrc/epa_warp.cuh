@@ -85,12 +85,12 @@ B3_DEV uint8_t epa_process_warp(const Shape& L, const Shape& R, const Simplex<tr
                 float dk = W.fn[k].w;
                 if (dk < lb) { lb = dk; li = k; }
             }
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-                float ob = __shfl_xor_sync(0xFFFFFFFFu, lb, off);
-                int oi = __shfl_xor_sync(0xFFFFFFFFu, li, off);
-                if (ob < lb || (ob == lb && oi < li)) { lb = ob; li = oi; }
-            }
+            // minimum by (distance, index) in two integer warp reductions: an order-preserving map of f32 onto u32
+            // (-0 folded onto +0, as == would; lb is never NaN), then the lowest index among the lanes that hold it
+            const uint32_t bits = __float_as_uint(lb + 0.0f);
+            const uint32_t key = bits ^ ((bits >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+            const uint32_t kmin = __reduce_min_sync(0xFFFFFFFFu, key);
+            li = (int)__reduce_min_sync(0xFFFFFFFFu, key == kmin ? (uint32_t)li : 0x7FFFFFFFu);
             if (li != 0x7FFFFFFF) best = li;
         }
         const float4 bf = W.fn[best];
@@ -122,9 +122,14 @@ B3_DEV uint8_t epa_process_warp(const Shape& L, const Shape& R, const Simplex<tr
             if (lane == 0) W.vm[c] = wmask;
         }
         __syncwarp();
-        // Pass B: the reference's `while i < len` walk with swap_remove, all lanes in step.
+        // Pass B: the reference's `while i < len` walk with swap_remove, all lanes in step. The horizon edge list lives
+        // in registers while it is short — lane i holds entry i: the search for a reversed duplicate is one ballot,
+        // Vec::remove one shuffle-down, push one predicated move — and moves to the shared-memory list (warp_edge_op)
+        // the moment it would need a 33rd entry.
         int ne = 0;
         bool ok = true;
+        bool spilled = false;
+        uint32_t my_edge = 0;
         for (int k = 0;;) {
             int c = k >> 5;
             uint32_t w = (c < nwords) ? (W.vm[c] >> (k & 31)) : 0u;
@@ -151,10 +156,29 @@ B3_DEV uint8_t epa_process_warp(const Shape& L, const Shape& R, const Simplex<tr
                 if (k != nf) { W.fn[k] = lf; W.fi[k] = li; }
             }
             __syncwarp();
-            const uint32_t i0 = idx & 0xFF, i1 = (idx >> 8) & 0xFF, i2 = (idx >> 16) & 0xFF;
-            ok = ok && warp_edge_op(W.ed, ne, i0, i1, lane);
-            ok = ok && warp_edge_op(W.ed, ne, i1, i2, lane);
-            ok = ok && warp_edge_op(W.ed, ne, i2, i0, lane);
+            const uint32_t vi[4] = {idx & 0xFF, (idx >> 8) & 0xFF, (idx >> 16) & 0xFF, idx & 0xFF};
+#pragma unroll
+            for (int e = 0; e < 3; ++e) {
+                const uint32_t a = vi[e], b = vi[e + 1];
+                if (!spilled) {
+                    const uint32_t rev = b | (a << 8);
+                    const uint32_t m = __ballot_sync(0xFFFFFFFFu, (int)lane < ne && my_edge == rev);
+                    if (m) {
+                        const uint32_t found = __ffs(m) - 1;
+                        const uint32_t nxt = __shfl_down_sync(0xFFFFFFFFu, my_edge, 1);
+                        if (lane >= found) my_edge = nxt;
+                        --ne;
+                    } else if (ne < 32) {
+                        if ((int)lane == ne) my_edge = a | (b << 8);
+                        ++ne;
+                    } else {
+                        W.ed[lane] = (uint16_t)my_edge;
+                        __syncwarp();
+                        spilled = true;
+                    }
+                }
+                if (spilled) ok = ok && warp_edge_op(W.ed, ne, a, b, lane);
+            }
         }
         if (!ok || nv >= EPA_VCAP || nf + ne > EPA_FCAP) return ST_CAPACITY;
         const int n = nv;
@@ -162,9 +186,13 @@ B3_DEV uint8_t epa_process_warp(const Shape& L, const Shape& R, const Simplex<tr
         ++nv;
         __syncwarp();
         // Pass C: the new faces, one per lane
-        for (int e = lane; e < ne; e += 32) {
-            const uint32_t ab = W.ed[e];
-            warp_make_face(W, nf + e, (uint32_t)n, ab & 0xFF, (ab >> 8) & 0xFF);
+        if (!spilled) {
+            if ((int)lane < ne) warp_make_face(W, nf + lane, (uint32_t)n, my_edge & 0xFF, (my_edge >> 8) & 0xFF);
+        } else {
+            for (int e = lane; e < ne; e += 32) {
+                const uint32_t ab = W.ed[e];
+                warp_make_face(W, nf + e, (uint32_t)n, ab & 0xFF, (ab >> 8) & 0xFF);
+            }
         }
         nf += ne;
         __syncwarp();

@@ -242,8 +242,11 @@ __global__ void __launch_bounds__(TPB) gjk_intersect_kernel(ShapeSetDev S, const
 // ------------------------------------------------------------------------------------------------------------
 // GJK::intersection = intersect + EPA3::process (FullResolution) or Contact::new(CollisionOnly)
 // ------------------------------------------------------------------------------------------------------------
+#ifndef B3_WARP_MIN_BLOCKS
+#define B3_WARP_MIN_BLOCKS 1
+#endif
 template <bool WARP>
-__global__ void __launch_bounds__(TPB) gjk_contact_kernel(ShapeSetDev S, const uint2* __restrict__ pairs, uint32_t n,
+__global__ void __launch_bounds__(TPB, B3_WARP_MIN_BLOCKS) gjk_contact_kernel(ShapeSetDev S, const uint2* __restrict__ pairs, uint32_t n,
                                                           const uint32_t* __restrict__ order, const uint32_t* __restrict__ ranges,
                                                           SettingsDev cfg, int strategy, unsigned char* __restrict__ ovf_scratch,
                                                           float4* __restrict__ contacts, uint8_t* __restrict__ status) {

@@ -65,11 +65,22 @@ B3_DEV V3 polyhedron_local_support(const float4* __restrict__ verts, uint32_t n,
     uint32_t idx = 0xFFFFFFFFu;
     if (WARP) {
         const uint32_t lane = threadIdx.x & 31u;
-        for (uint32_t i = lane; i < n; i += 32) {
-            float4 p = __ldg(verts + i);
-            float t = dot(v3(p.x, p.y, p.z), d);
-            if (t > best) { best = t; idx = i; }
+#ifndef B3_SUPPORT_BATCH
+#define B3_SUPPORT_BATCH 4
+#endif
+        // B3_SUPPORT_BATCH vertices per lane per step, loads first: one L1/L2 round trip per 32 x BATCH vertices
+        for (uint32_t i0 = lane; i0 < n; i0 += 32 * B3_SUPPORT_BATCH) {
+            float4 p[B3_SUPPORT_BATCH];
+#pragma unroll
+            for (int j = 0; j < B3_SUPPORT_BATCH; ++j) p[j] = (i0 + 32 * j < n) ? __ldg(verts + i0 + 32 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < B3_SUPPORT_BATCH; ++j) {
+                const uint32_t i = i0 + 32 * j;
+                const float t = dot(v3(p[j].x, p[j].y, p[j].z), d);
+                if (i < n && t > best) { best = t; idx = i; }
+            }
         }
+#ifdef B3_SUPPORT_SHUFFLE_REDUCE
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
             float ob = __shfl_xor_sync(0xFFFFFFFFu, best, off);
@@ -77,6 +88,16 @@ B3_DEV V3 polyhedron_local_support(const float4* __restrict__ verts, uint32_t n,
             // a lane that saw no valid dot has idx = 0xFFFFFFFF and best = -inf and never wins over a valid one
             if (ob > best || (ob == best && oi < idx)) { best = ob; idx = oi; }
         }
+#else
+        // Two warp-wide integer reductions (redux.sync) instead of five shuffle rounds: the largest dot through an
+        // order-preserving map of f32 onto u32 (-0 folded onto +0 first, as == would; a lane's `best` is never NaN),
+        // then the lowest vertex index among the lanes that hold it. A lane that saw no valid dot keeps
+        // (-inf, 0xFFFFFFFF) and can only win when every lane did.
+        const uint32_t bits = __float_as_uint(best + 0.0f);
+        const uint32_t key = bits ^ ((bits >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+        const uint32_t kmax = __reduce_max_sync(0xFFFFFFFFu, key);
+        idx = __reduce_min_sync(0xFFFFFFFFu, key == kmax ? idx : 0xFFFFFFFFu);
+#endif
     } else {
         for (uint32_t i = 0; i < n; ++i) {
             float4 p = __ldg(verts + i);
