@@ -146,6 +146,7 @@ int32_t bam3d_ctx_create(int32_t device_ordinal, bam3d_ctx** out_ctx) {
     ctx->device = device_ordinal;
     if (const char* e = std::getenv("BAM3D_EPA_TIERS")) ctx->opt_epa_tiers = std::atoi(e) != 0;      // development A/B switches
     if (const char* e = std::getenv("BAM3D_EPA_OVERLAP")) ctx->opt_epa_overlap = std::atoi(e) != 0;
+    if (const char* e = std::getenv("BAM3D_INTERSECT_SPLIT")) ctx->opt_intersect_split = std::atoi(e) != 0;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return BAM3D_ERR_CUDA; }
     if (cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_a, cudaEventDisableTiming) != cudaSuccess ||
@@ -180,6 +181,7 @@ int32_t bam3d_ctx_set_option(bam3d_ctx* ctx, const char* name, int32_t value) {
     if (!std::strcmp(name, "timing")) { ctx->opt_timing = value != 0; return BAM3D_OK; }
     if (!std::strcmp(name, "epa_tiers")) { ctx->opt_epa_tiers = value != 0; return BAM3D_OK; }
     if (!std::strcmp(name, "epa_overlap")) { ctx->opt_epa_overlap = value != 0; return BAM3D_OK; }
+    if (!std::strcmp(name, "intersect_split")) { ctx->opt_intersect_split = value != 0; return BAM3D_OK; }
     if (!std::strcmp(name, "bvh_strategy")) { if (value < 0 || value > 2) return b3_fail(ctx, BAM3D_ERR_ARG, "bvh_strategy must be 0 (auto), 1 (traversal) or 2 (all pairs)", cudaSuccess); ctx->opt_bvh_strategy = value; return BAM3D_OK; }
     if (!std::strcmp(name, "sap_strategy")) { if (value < 0 || value > 2) return b3_fail(ctx, BAM3D_ERR_ARG, "sap_strategy must be 0 (auto), 1 (sweep) or 2 (bvh)", cudaSuccess); ctx->opt_sap_strategy = value; return BAM3D_OK; }
     return b3_fail(ctx, BAM3D_ERR_ARG, "unknown option", cudaSuccess);
@@ -327,8 +329,14 @@ int32_t bam3d_gjk_intersect_dev(bam3d_ctx* ctx, const bam3d_shapes* shapes, cons
     Plan plan = plan_for(ctx, shapes);
     BinScratch B; const BinScratch* pb;
     if ((rc = prepare_bins(ctx, plan, S, (const uint2*)d_pairs, (uint32_t)n, B, &pb))) return rc;
+    void* split_scratch = nullptr;
+    if (plan.run_thread && ctx->opt_intersect_split) {
+        if ((rc = ctx->epa_queue.reserve(ctx, intersect_scratch_bytes((uint32_t)n)))) return rc;
+        split_scratch = ctx->epa_queue.ptr;
+    }
     { KernelTimer kt(ctx);
-      ctx->launches += launch_intersect(ctx->stream, S, (const uint2*)d_pairs, (uint32_t)n, pb, plan.run_thread, plan.run_warp, to_dev(settings), d_status); }
+      ctx->launches += launch_intersect(ctx->stream, S, (const uint2*)d_pairs, (uint32_t)n, pb, plan.run_thread, plan.run_warp, to_dev(settings),
+                                        split_scratch, d_status); }
     return check_launch(ctx, "gjk_intersect_kernel");
 }
 

@@ -24,6 +24,7 @@ struct bam3d_ctx {
     uint64_t launches = 0;
     bool opt_binning = true;
     bool opt_epa_tiers = false;   // contact path: shared-memory EPA in size tiers (epa_tiers.cuh) instead of per-thread local-memory EPA
+    bool opt_intersect_split = false;  // intersect, thread path: first-support test and the GJK loop as two launches (measured slower on C1: 0.176 vs 0.167 ms)
     bool opt_epa_overlap = true;  // contact path: run the EPA overflow tier on the side stream next to the EPA kernel
     int opt_sap_strategy = 0;  // 0 auto, 1 tiled sweep, 2 BVH overlap query
     int opt_bvh_strategy = 0;  // variable-length queries: 0 auto, 1 tree traversal, 2 all (query, value) tests

@@ -39,8 +39,11 @@ int launch_pack_meshes(cudaStream_t st, const float* d_xyz, uint64_t nverts, flo
 int launch_bin_pairs(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs, uint32_t n, const BinScratch& B);
 
 // B may be null (no binning: the selected kernel covers every pair). run_thread / run_warp pick the execution shapes.
+// d_scratch: intersect_scratch_bytes(n) of device memory for the survivor list of the two-launch thread path, or null to
+// run the single-kernel thread path.
+size_t intersect_scratch_bytes(uint32_t n);
 int launch_intersect(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs, uint32_t n, const BinScratch* B,
-                     bool run_thread, bool run_warp, const SettingsDev& cfg, uint8_t* d_status);
+                     bool run_thread, bool run_warp, const SettingsDev& cfg, void* d_scratch, uint8_t* d_status);
 // d_overflow_scratch: contact_overflow_scratch_bytes() of device memory for the EPA overflow tier (epa_big.cuh);
 // d_queue: contact_queue_bytes(n) for the GJK -> EPA hit queue of the thread-per-pair path.
 size_t contact_overflow_scratch_bytes();

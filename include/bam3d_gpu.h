@@ -96,7 +96,9 @@ void bam3d_default_settings(bam3d_gjk_settings* out); /* GJK::new() (gjk/mod.rs:
  * picks how sweep-and-prune finds its pairs — 0 auto, 1 tiled forward sweep, 2 BVH overlap query (same output);
  * "bvh_strategy" picks how the variable-length BVH queries run — 0 auto, 1 tree traversal (thread per query), 2 every
  * (query, value) test (for few large queries; results then come back in value-index order); "epa_tiers" (default 1)
- * runs EPA with the polytopes in shared memory in size tiers, 0 = per-thread local-memory polytopes (same results) */
+ * runs EPA with the polytopes in shared memory in size tiers, 0 = per-thread local-memory polytopes (same results);
+ * "epa_overlap" (default 1) runs the EPA overflow tier on a side stream next to the EPA kernel; "intersect_split"
+ * (default 0) runs bam3d_gjk_intersect's thread path as two launches (first-support test, then GJK on the survivors) */
 int32_t bam3d_ctx_set_option(bam3d_ctx* ctx, const char* name, int32_t value);
 /* synchronise, then return and reset the summed device time (ms) and number of bracketed calls ("timing" = 1) */
 int32_t bam3d_ctx_read_timing(bam3d_ctx* ctx, double* out_total_ms, uint64_t* out_count);

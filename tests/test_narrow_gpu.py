@@ -129,13 +129,14 @@ def test_intersect_parity_all_kinds(ctx, oracle):
     st = b3.GJK.new(ctx).intersect_batch(shapes, scene["pairs"])
     hit, ost = oracle.intersect(scene, nthreads=8)
     assert np.array_equal(st, ost), f"{int((st != ost).sum())} status mismatches"
-    # binning off must give the same answers
-    ctx.set_option("binning", 0)
-    try:
-        st2 = b3.GJK.new(ctx).intersect_batch(shapes, scene["pairs"])
-    finally:
-        ctx.set_option("binning", 1)
-    assert np.array_equal(st, st2)
+    # binning off / the two-launch thread path must give the same answers
+    for opt, off, on in (("binning", 0, 1), ("intersect_split", 1, 0)):
+        ctx.set_option(opt, off)
+        try:
+            st2 = b3.GJK.new(ctx).intersect_batch(shapes, scene["pairs"])
+        finally:
+            ctx.set_option(opt, on)
+        assert np.array_equal(st, st2), opt
 
 
 def test_contact_parity_mixed(ctx, oracle):
