@@ -14,7 +14,8 @@ OK = 0
 ERR_CUDA, ERR_ARG, ERR_NON_AFFINE, ERR_CAPACITY, ERR_OOM = -1, -2, -3, -4, -5
 
 KIND_PARTICLE, KIND_QUAD, KIND_SPHERE, KIND_CUBOID, KIND_CYLINDER, KIND_CAPSULE, KIND_POLYHEDRON = range(7)
-STATUS_OK, STATUS_MISS, STATUS_MAX_ITER, STATUS_REF_PANIC, STATUS_NAN, STATUS_CAPACITY = range(6)
+STATUS_OK, STATUS_MISS, STATUS_MAX_ITER, STATUS_REF_PANIC, STATUS_NAN, STATUS_CAPACITY, STATUS_UNSUPPORTED = range(7)
+RAY_INTERSECTS, RAY_INTERSECTION, PARTICLE_SWEEP = 0, 1, 2
 FULL_RESOLUTION, COLLISION_ONLY = 0, 1
 
 
@@ -58,6 +59,8 @@ SIGNATURES = {
     "bam3d_gjk_contact_dev": (_i32, [_vp, _vp, _vp, _u64, _PS, _i32, _vp, _vp]),
     "bam3d_gjk_distance_dev": (_i32, [_vp, _vp, _vp, _u64, _PS, _vp, _vp, _vp]),
     "bam3d_gjk_time_of_impact_dev": (_i32, [_vp, _vp, _vp, _vp, _u64, _PS, _vp, _vp]),
+    "bam3d_ray_cast": (_i32, [_vp, _vp, _vp, _u64, _vp, _u64, _i32, _vp, _vp]),
+    "bam3d_ray_cast_dev": (_i32, [_vp, _vp, _vp, _u64, _vp, _u64, _i32, _vp, _vp]),
     "bam3d_compact_contacts_dev": (_i32, [_vp, _vp, _vp, _u64, _u64, _vp, _u64, _vp]),
     "bam3d_ctx_launch_count": (_u64, [_vp]),
     "bam3d_sap_find_pairs": (_i32, [_vp, _vp, _u64, C.POINTER(_i32), _vp, _vp, _u64, C.POINTER(_u64)]),

@@ -11,6 +11,7 @@ Transforms are glam Mat4 values given as 16 f32 in column-major order (Mat4::to_
 import ctypes as C
 import enum
 from dataclasses import dataclass
+from typing import Sequence
 
 import numpy as np
 
@@ -491,3 +492,59 @@ def _complex_methods():
 
 
 _complex_methods()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# ray casts against primitives
+# ---------------------------------------------------------------------------------------------------------
+@dataclass
+class Ray:  # ray.rs:7-24: origin + direction as given (not normalised by the constructor)
+    origin: Sequence[float]
+    direction: Sequence[float]
+
+    def row(self):
+        return np.concatenate([np.asarray(self.origin, dtype=np.float32), np.asarray(self.direction, dtype=np.float32)])
+
+
+def ray_cast_batch(shapes, rays, casts, query=_ffi.RAY_INTERSECTION):
+    """Batched Discrete/ContinuousTransformed<Ray> for Primitive3 (ray.rs:58-78, primitive3.rs:133-166) and the swept
+    particle (particle.rs:39-128). rays: [m, 6] (origin, direction; PARTICLE_SWEEP: start, end); casts: [n, 2] =
+    (ray index, shape index). -> (points[n, 3], status[n]); status 0 = true / Some(point), 1 = false / None,
+    STATUS_UNSUPPORTED for a ConvexPolyhedron."""
+    ctx = shapes.ctx
+    rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 6)
+    casts = np.ascontiguousarray(casts, dtype=np.uint32).reshape(-1, 2)
+    n = len(casts)
+    points = np.zeros((n, 3), dtype=np.float32)
+    status = np.ones(n, dtype=np.uint8)
+    ctx.check(ctx._lib.bam3d_ray_cast(ctx.handle, shapes.handle, _ptr(rays), len(rays), _ptr(casts), n, int(query), _ptr(points), _ptr(status)))
+    return points, status
+
+
+def intersects_transformed(primitive, ray, transform, ctx=None):
+    """DiscreteTransformed<Ray>::intersects_transformed (ray.rs:58-66) as a batch of one."""
+    ctx = ctx if ctx is not None else default_context()
+    s = ShapeSet.from_primitives(ctx, [primitive], [transform])
+    _, st = ray_cast_batch(s, [ray.row()], [[0, 0]], _ffi.RAY_INTERSECTS)
+    if st[0] == _ffi.STATUS_UNSUPPORTED:
+        raise NotImplementedError("ray casts against ConvexPolyhedron are not built (polyhedron.rs:373-522)")
+    return bool(st[0] == _ffi.STATUS_OK)
+
+
+def intersection_transformed(primitive, ray, transform, ctx=None):
+    """ContinuousTransformed<Ray>::intersection_transformed (ray.rs:68-78) as a batch of one: hit point or None."""
+    ctx = ctx if ctx is not None else default_context()
+    s = ShapeSet.from_primitives(ctx, [primitive], [transform])
+    pts, st = ray_cast_batch(s, [ray.row()], [[0, 0]], _ffi.RAY_INTERSECTION)
+    if st[0] == _ffi.STATUS_UNSUPPORTED:
+        raise NotImplementedError("ray casts against ConvexPolyhedron are not built (polyhedron.rs:373-522)")
+    return pts[0] if st[0] == _ffi.STATUS_OK else None
+
+
+def particle_intersection_transformed(primitive, start, end, transform, ctx=None):
+    """ContinuousTransformed<(Particle, Range<Vec3>)> (particle.rs:108-128): where the particle moving start -> end hits."""
+    ctx = ctx if ctx is not None else default_context()
+    s = ShapeSet.from_primitives(ctx, [primitive], [transform])
+    seg = np.concatenate([np.asarray(start, dtype=np.float32), np.asarray(end, dtype=np.float32)])
+    pts, st = ray_cast_batch(s, [seg], [[0, 0]], _ffi.PARTICLE_SWEEP)
+    return pts[0] if st[0] == _ffi.STATUS_OK else None

@@ -469,6 +469,40 @@ int32_t bam3d_gjk_distance(bam3d_ctx* ctx, const bam3d_shapes* shapes, const uin
     return BAM3D_OK;
 }
 
+// ---- ray casts against primitives ---------------------------------------------------------------
+int32_t bam3d_ray_cast_dev(bam3d_ctx* ctx, const bam3d_shapes* shapes, const float* d_rays, uint64_t n_rays, const uint32_t* d_casts,
+                           uint64_t n, int32_t query, float* d_points, uint8_t* d_status) {
+    if (!ctx || !shapes || (n && (!d_rays || !d_casts || !d_points || !d_status))) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_ray_cast: null argument", cudaSuccess);
+    if (query < 0 || query > 2) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_ray_cast: query must be 0 (intersects), 1 (intersection) or 2 (swept particle)", cudaSuccess);
+    (void)n_rays;
+    int32_t rc;
+    if ((rc = check_n(ctx, n))) return rc;
+    if (n == 0) return BAM3D_OK;
+    CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
+    { KernelTimer kt(ctx);
+      ctx->launches += launch_ray_cast(ctx->stream, view(shapes), d_rays, (const uint2*)d_casts, n, query, d_points, d_status); }
+    return check_launch(ctx, "ray_cast_kernel");
+}
+
+int32_t bam3d_ray_cast(bam3d_ctx* ctx, const bam3d_shapes* shapes, const float* rays, uint64_t n_rays, const uint32_t* casts, uint64_t n,
+                       int32_t query, float* out_points, uint8_t* out_status) {
+    if (!ctx || !shapes || (n && (!rays || !casts || !out_points || !out_status))) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_ray_cast: null argument", cudaSuccess);
+    int32_t rc;
+    if ((rc = check_n(ctx, n)) || (rc = check_n(ctx, n_rays))) return rc;
+    if (n == 0) return BAM3D_OK;
+    for (uint64_t i = 0; i < n; ++i)
+        if (casts[2 * i] >= n_rays || casts[2 * i + 1] >= shapes->n) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_ray_cast: cast index out of range", cudaSuccess);
+    CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
+    if ((rc = stage_pairs(ctx, casts, n)) || (rc = ctx->status.reserve(ctx, n)) || (rc = ctx->f0.reserve(ctx, n * 12)) || (rc = ctx->f1.reserve(ctx, n_rays * 24))) return rc;
+    CU_TRY(cudaMemcpyAsync(ctx->f1.ptr, rays, n_rays * 24, cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpyAsync(rays)");
+    if ((rc = bam3d_ray_cast_dev(ctx, shapes, (const float*)ctx->f1.ptr, n_rays, (const uint32_t*)ctx->pairs.ptr, n, query, (float*)ctx->f0.ptr,
+                                 (uint8_t*)ctx->status.ptr))) return rc;
+    CU_TRY(cudaMemcpyAsync(out_points, ctx->f0.ptr, n * 12, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(points)");
+    CU_TRY(cudaMemcpyAsync(out_status, ctx->status.ptr, n, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(status)");
+    CU_TRY(cudaStreamSynchronize(ctx->stream), "bam3d_ray_cast");
+    return BAM3D_OK;
+}
+
 int32_t bam3d_gjk_time_of_impact(bam3d_ctx* ctx, const bam3d_shapes* s0, const bam3d_shapes* s1, const uint32_t* pairs, uint64_t n,
                                  const bam3d_gjk_settings* settings, bam3d_contact* out_contacts, uint8_t* out_status) {
     if (!ctx || !s0 || !s1 || (n && (!pairs || !out_status || !out_contacts))) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_gjk_time_of_impact: null argument", cudaSuccess);

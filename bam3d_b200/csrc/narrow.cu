@@ -16,6 +16,7 @@
 #include "gjk.cuh"
 #include "epa_big.cuh"
 #include "epa_warp.cuh"
+#include "raycast.cuh"
 
 namespace b3 {
 
@@ -1024,6 +1025,30 @@ int launch_distance(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs,
 int launch_toi(cudaStream_t st, const ShapeSetDev& S0, const ShapeSetDev& S1, const uint2* d_pairs, uint32_t n, const BinScratch* B,
                bool run_thread, bool run_warp, const SettingsDev& cfg, float4* d_contacts, uint8_t* d_status) {
     B3_LAUNCH(gjk_toi_kernel, 0, S0, S1, d_pairs, n, order, ranges, cfg, d_contacts, d_status)
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Ray casts against primitives (raycast.cuh): one thread per (ray, shape) cast
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB) ray_cast_kernel(ShapeSetDev S, const float* __restrict__ rays, const uint2* __restrict__ casts,
+                                                       uint64_t n, int query, float* __restrict__ points, uint8_t* __restrict__ status) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint2 c = __ldg(casts + i);
+        const float* r = rays + 6 * (size_t)c.x;
+        Shape s;
+        load_pair_shape(s, S, c.y);
+        V3 p;
+        const uint8_t st = ray_cast_one(s, v3(__ldg(r), __ldg(r + 1), __ldg(r + 2)), v3(__ldg(r + 3), __ldg(r + 4), __ldg(r + 5)), query, p);
+        status[i] = st;
+        points[3 * i] = p.x; points[3 * i + 1] = p.y; points[3 * i + 2] = p.z;
+    }
+}
+
+int launch_ray_cast(cudaStream_t st, const ShapeSetDev& S, const float* d_rays, const uint2* d_casts, uint64_t n, int query, float* d_points,
+                    uint8_t* d_status) {
+    if (n == 0) return 0;
+    ray_cast_kernel<<<grid_for(n, TPB, NUM_SMS * 32), TPB, 0, st>>>(S, d_rays, d_casts, n, query, d_points, d_status);
+    return 1;
 }
 
 int launch_compact_contacts(cudaStream_t st, const float4* d_contacts, const uint8_t* d_status, uint64_t n, uint64_t base, void* d_out,

@@ -60,6 +60,10 @@ int launch_distance(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs,
                     bool run_thread, bool run_warp, const SettingsDev& cfg, float* d_ref, float* d_geo, uint8_t* d_status);
 int launch_toi(cudaStream_t st, const ShapeSetDev& S0, const ShapeSetDev& S1, const uint2* d_pairs, uint32_t n,
                const BinScratch* B, bool run_thread, bool run_warp, const SettingsDev& cfg, float4* d_contacts, uint8_t* d_status);
+// Ray casts against primitives: d_rays = n_rays x 6 f32 (origin, direction; query 2: segment start, end), d_casts = n x
+// (ray index, shape index); query 0 = intersects_transformed, 1 = intersection_transformed, 2 = swept particle.
+int launch_ray_cast(cudaStream_t st, const ShapeSetDev& S, const float* d_rays, const uint2* d_casts, uint64_t n, int query, float* d_points,
+                    uint8_t* d_status);
 int launch_compact_contacts(cudaStream_t st, const float4* d_contacts, const uint8_t* d_status, uint64_t n,
                             uint64_t base, void* d_out, uint64_t capacity, unsigned long long* d_count);
 

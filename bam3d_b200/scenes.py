@@ -222,3 +222,40 @@ def view_projections(nq, L, seed=SEED_C4, start=0):
         V = view[k].T
         out[k] = (P @ V).T.reshape(16)
     return out
+
+
+def primitive_rays(scene, n_rays, seed=0xB3D000F1, start=0):
+    """Rays / particle segments aimed at the shapes of `scene` for the ray-cast parity tests: cast i pairs ray i with
+    shape (i mod n_shapes). Origins sit U[-3, 3]^3 around the shape's position; a third of the directions point at the
+    shape (plus noise), a third are random unit vectors, the rest are axis-parallel (exact zeros: the inf/NaN slab
+    arithmetic and the cylinder's vertical-ray branch) or not normalised. -> (rays[n, 6], segments[n, 6], casts[n, 2])."""
+    n_shapes = len(scene["kind"])
+    idx = np.arange(start, start + n_rays, dtype=np.uint64)
+    shape = (idx % np.uint64(n_shapes)).astype(np.uint32)
+    centre = scene["xform"][shape, 12:15]
+    off = np.stack([uniform(seed, 1 + k, idx, -3.0, 3.0) for k in range(3)], axis=1)
+    origin = (centre + off).astype(np.float32)
+    noise = np.stack([uniform(seed, 4 + k, idx, -0.6, 0.6) for k in range(3)], axis=1)
+    aimed = (centre - origin + noise).astype(np.float32)
+    rnd = np.stack([gaussian(seed, 7 + k, idx) for k in range(3)], axis=1).astype(np.float32)
+    mode = randint(seed, 10, idx, 6)
+    d = np.where((mode < 2)[:, None], aimed, rnd)
+    ln = np.linalg.norm(d.astype(np.float64), axis=1, keepdims=True)
+    d = (d / np.maximum(ln, 1e-30)).astype(np.float32)
+    axis = randint(seed, 11, idx, 3)
+    sign = np.where(randint(seed, 12, idx, 2) == 0, np.float32(1.0), np.float32(-1.0))
+    axial = np.zeros((n_rays, 3), dtype=np.float32)
+    axial[np.arange(n_rays), axis] = sign
+    # axis-parallel rays start on the shape's axis line half of the time so that they actually hit
+    on_axis = origin.copy()
+    keep = np.arange(n_rays), axis
+    on_axis[:] = centre
+    on_axis[keep] = origin[keep]
+    d = np.where((mode == 4)[:, None], axial, d)
+    origin = np.where(((mode == 4) & (randint(seed, 13, idx, 2) == 0))[:, None], on_axis, origin).astype(np.float32)
+    d = np.where((mode == 5)[:, None], aimed, d).astype(np.float32)  # not normalised
+    rays = np.concatenate([origin, d], axis=1).astype(np.float32)
+    reach = uniform(seed, 14, idx, 0.5, 6.0)[:, None]
+    segments = np.concatenate([origin, (origin + d * reach).astype(np.float32)], axis=1).astype(np.float32)
+    casts = np.stack([np.arange(n_rays, dtype=np.uint32), shape], axis=1)
+    return rays, segments, casts

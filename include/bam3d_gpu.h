@@ -48,6 +48,7 @@ extern "C" {
 #define BAM3D_STATUS_REF_PANIC 3  /* the reference would panic here (simplex3d.rs:134 unwrap, :138 assert!) */
 #define BAM3D_STATUS_NAN 4        /* None through a NaN comparison                                      */
 #define BAM3D_STATUS_CAPACITY 5   /* EPA polytope outgrew the device capacities (never seen on valid input) */
+#define BAM3D_STATUS_UNSUPPORTED 6 /* ray cast against a ConvexPolyhedron (needs half-edge faces): not computed    */
 
 /* CollisionStrategy (contact.rs:12-18) */
 #define BAM3D_FULL_RESOLUTION 0
@@ -160,6 +161,20 @@ int32_t bam3d_gjk_time_of_impact_dev(bam3d_ctx* ctx, const bam3d_shapes* shapes_
                                      const bam3d_shapes* shapes_end, const uint32_t* d_pairs, uint64_t n,
                                      const bam3d_gjk_settings* settings, bam3d_contact* d_contacts,
                                      uint8_t* d_status);
+/* Ray casts against primitives: Discrete/ContinuousTransformed<Ray> for Primitive3 (primitive3.rs:133-166, ray.rs:58-78;
+ * per primitive: ray.rs:35-57 Vec3, sphere.rs:45-76, cuboid.rs:85-103 and quad.rs:80-96 through aabb3.rs:165-235,
+ * cylinder.rs:82-204, capsule.rs:69-178, particle.rs:53-69) and the swept particle (Particle, Range<Vec3>)
+ * (particle.rs:39-128). rays: n_rays x 6 f32 = origin.xyz, direction.xyz as given (the reference does not normalise) —
+ * for query 2 the 6 floats are the particle's start and end point. casts: n x (ray index, shape index).
+ * query 0 = intersects_transformed (bool), 1 = intersection_transformed (Option<Vec3>), 2 = swept particle (both the
+ * Discrete and the Continuous form: the hit, kept only within the travelled distance).
+ * out_status: BAM3D_STATUS_OK = true / Some, BAM3D_STATUS_MISS = false / None, BAM3D_STATUS_UNSUPPORTED for a
+ * ConvexPolyhedron; out_points: n x 3 f32 world-space hit points (zero when there is none, and for query 0). */
+int32_t bam3d_ray_cast(bam3d_ctx* ctx, const bam3d_shapes* shapes, const float* rays, uint64_t n_rays, const uint32_t* casts,
+                       uint64_t n, int32_t query, float* out_points, uint8_t* out_status);
+int32_t bam3d_ray_cast_dev(bam3d_ctx* ctx, const bam3d_shapes* shapes, const float* d_rays, uint64_t n_rays,
+                           const uint32_t* d_casts, uint64_t n, int32_t query, float* d_points, uint8_t* d_status);
+
 /* Compact the hits of a contact batch into d_out (capacity records), pair_index = index + pair_index_base.
  * *d_count (device u32/u64 pair: one uint64) receives the number of hits. Feeds the multi-GPU gather. */
 int32_t bam3d_compact_contacts_dev(bam3d_ctx* ctx, const bam3d_contact* d_contacts, const uint8_t* d_status,

@@ -9,6 +9,7 @@
 #include <vector>
 #include "bam3d_oracle.hpp"
 #include "broad_oracle.hpp"
+#include "ray_oracle.hpp"
 
 using namespace orc;
 
@@ -323,6 +324,76 @@ static void bound_tests() {
     CHECK_V3(-5.f, -5.f, -5.f, b.min); CHECK_V3(5.f, 5.f, 5.f, b.max);
 }
 
+// Ray casts against primitives: every ray test of primitive/{sphere,cuboid,cylinder,capsule}.rs.
+static void ray_tests() {
+    Vec3 p;
+    const Mat4 I = transform_z(0, 0, 0, 0);
+    {   Shape sph = Shape::sphere(10.f);
+        TEST("sphere.rs:134 test_ray_discrete");
+        CHECK(ray_intersects_local(sph, Ray(Vec3(20, 0, 0), Vec3(-1, 0, 0))));
+        CHECK(!ray_intersects_local(sph, Ray(Vec3(20, 0, 0), Vec3(1, 0, 0))));
+        CHECK(!ray_intersects_local(sph, Ray(Vec3(20, -15, 0), Vec3(-1, 0, 0))));
+        TEST("sphere.rs:146 test_ray_discrete_transformed");
+        CHECK(ray_intersects_transformed(sph, Ray(Vec3(20, 0, 0), Vec3(-1, 0, 0)), I));
+        CHECK(!ray_intersects_transformed(sph, Ray(Vec3(20, 0, 0), Vec3(1, 0, 0)), I));
+        CHECK(!ray_intersects_transformed(sph, Ray(Vec3(20, 0, 0), Vec3(-1, 0, 0)), transform_z(0, 15, 0, 0)));
+        TEST("sphere.rs:159 test_ray_continuous");
+        CHECK(ray_intersection_local(sph, Ray(Vec3(20, 0, 0), Vec3(-1, 0, 0)), p)); CHECK_V3(10.f, 0.f, 0.f, p);
+        CHECK(!ray_intersection_local(sph, Ray(Vec3(20, 0, 0), Vec3(1, 0, 0)), p));
+        CHECK(!ray_intersection_local(sph, Ray(Vec3(20, -15, 0), Vec3(-1, 0, 0)), p));
+        TEST("sphere.rs:170 test_ray_continuous_transformed");
+        CHECK(ray_intersection_transformed(sph, Ray(Vec3(20, 0, 0), Vec3(-1, 0, 0)), I, p)); CHECK_V3(10.f, 0.f, 0.f, p);
+        CHECK(!ray_intersection_transformed(sph, Ray(Vec3(20, 0, 0), Vec3(1, 0, 0)), I, p));
+        CHECK(!ray_intersection_transformed(sph, Ray(Vec3(20, 0, 0), Vec3(-1, 0, 0)), transform_z(0, 15, 0, 0), p)); }
+    {   Shape cub = Shape::cuboid(10, 10, 10);
+        TEST("cuboid.rs test_ray_discrete");
+        CHECK(ray_intersects_local(cub, Ray(Vec3(10, 0, 0), Vec3(-1, 0, 0))));
+        CHECK(!ray_intersects_local(cub, Ray(Vec3(10, 0, 0), Vec3(1, 0, 0))));
+        TEST("cuboid.rs test_ray_discrete_transformed");
+        CHECK(ray_intersects_transformed(cub, Ray(Vec3(10, 0, 0), Vec3(-1, 0, 0)), transform_z(0, 1, 0, 0)));
+        CHECK(!ray_intersects_transformed(cub, Ray(Vec3(10, 0, 0), Vec3(1, 0, 0)), transform_z(0, 1, 0, 0)));
+        CHECK(ray_intersects_transformed(cub, Ray(Vec3(10, 0, 0), Vec3(-1, 0, 0)), transform_z(0, 1, 0, 0.3f)));
+        TEST("cuboid.rs test_ray_continuous");
+        CHECK(ray_intersection_local(cub, Ray(Vec3(10, 0, 0), Vec3(-1, 0, 0)), p)); CHECK_V3(5.f, 0.f, 0.f, p);
+        CHECK(!ray_intersection_local(cub, Ray(Vec3(10, 0, 0), Vec3(1, 0, 0)), p));
+        TEST("cuboid.rs test_ray_continuous_transformed");
+        CHECK(ray_intersection_transformed(cub, Ray(Vec3(10, 0, 0), Vec3(-1, 0, 0)), transform_z(0, 1, 0, 0), p)); CHECK_V3(5.f, 0.f, 0.f, p);
+        CHECK(!ray_intersection_transformed(cub, Ray(Vec3(10, 0, 0), Vec3(1, 0, 0)), transform_z(0, 1, 0, 0), p));
+        // rotated by 0.3 degrees: the reference asserts |p - (5.000068, 0, 0)| < f32::EPSILON per component
+        CHECK(ray_intersection_transformed(cub, Ray(Vec3(10, 0, 0), Vec3(-1, 0, 0)), transform_z(0, 0, 0, 0.3f), p));
+        CHECK(std::fabs(p.x - 5.000068f) < F32_EPSILON); CHECK(std::fabs(p.y - 0.f) < F32_EPSILON); CHECK(std::fabs(p.z - 0.f) < F32_EPSILON); }
+    {   Shape cyl = Shape::cylinder(2.f, 1.f);
+        TEST("cylinder.rs test_discrete_1..4");
+        CHECK(ray_intersects_local(cyl, Ray(Vec3(-3, 0, 0), Vec3(1, 0, 0))));
+        CHECK(!ray_intersects_local(cyl, Ray(Vec3(-3, 0, 0), Vec3(-1, 0, 0))));
+        CHECK(ray_intersects_local(cyl, Ray(Vec3(0, 3, 0), normalize(Vec3(0.1f, -1.f, 0.1f)))));
+        CHECK(!ray_intersects_local(cyl, Ray(Vec3(0, 3, 0), normalize(Vec3(0.1f, 1.f, 0.1f)))));
+        TEST("cylinder.rs test_continuous_1..5");
+        CHECK(ray_intersection_local(cyl, Ray(Vec3(-3, 0, 0), Vec3(1, 0, 0)), p)); CHECK_V3(-1.f, 0.f, 0.f, p);
+        CHECK(!ray_intersection_local(cyl, Ray(Vec3(-3, 0, 0), Vec3(-1, 0, 0)), p));
+        CHECK(ray_intersection_local(cyl, Ray(Vec3(0, 3, 0), normalize(Vec3(0.1f, -1.f, 0.1f))), p)); CHECK_V3(0.1f, 2.f, 0.1f, p);
+        CHECK(!ray_intersection_local(cyl, Ray(Vec3(0, 3, 0), normalize(Vec3(0.1f, 1.f, 0.1f))), p));
+        CHECK(ray_intersection_local(cyl, Ray(Vec3(0, 3, 0), normalize(Vec3(0.f, -1.f, 0.f))), p)); CHECK_V3(0.f, 2.f, 0.f, p); }
+    {   Shape cap = Shape::capsule(2.f, 1.f);
+        TEST("capsule.rs test_discrete_1..5");
+        CHECK(ray_intersects_local(cap, Ray(Vec3(-3, 0, 0), Vec3(1, 0, 0))));
+        CHECK(!ray_intersects_local(cap, Ray(Vec3(-3, 0, 0), Vec3(-1, 0, 0))));
+        CHECK(ray_intersects_local(cap, Ray(Vec3(0, 3, 0), normalize(Vec3(0.1f, -1.f, 0.1f)))));
+        CHECK(!ray_intersects_local(cap, Ray(Vec3(0, 3, 0), normalize(Vec3(0.1f, 1.f, 0.1f)))));
+        CHECK(ray_intersects_local(cap, Ray(Vec3(0, 3, 0), normalize(Vec3(0.f, -1.f, 0.f)))));
+        TEST("capsule.rs test_continuous_1..5");
+        CHECK(ray_intersection_local(cap, Ray(Vec3(-3, 0, 0), Vec3(1, 0, 0)), p)); CHECK_V3(-1.f, 0.f, 0.f, p);
+        CHECK(!ray_intersection_local(cap, Ray(Vec3(-3, 0, 0), Vec3(-1, 0, 0)), p));
+        CHECK(ray_intersection_local(cap, Ray(Vec3(0, 4, 0), normalize(Vec3(0.1f, -1.f, 0.1f))), p)); CHECK_V3(0.10102587f, 2.9897413f, 0.10102587f, p);
+        CHECK(!ray_intersection_local(cap, Ray(Vec3(0, 3, 0), normalize(Vec3(0.1f, 1.f, 0.1f))), p));
+        CHECK(ray_intersection_local(cap, Ray(Vec3(0, 4, 0), normalize(Vec3(0.f, -1.f, 0.f))), p)); CHECK_V3(0.f, 3.f, 0.f, p); }
+    {   TEST("tests/point.rs:19 test_ray_intersect");
+        Vec3 point(1.f, 2.f, 3.f);
+        CHECK(point_ray_intersects(point, Ray(Vec3(1, 2, 0), Vec3(0, 0, 1))));
+        CHECK(!point_ray_intersects(point, Ray(Vec3(1, 2, 0), Vec3(0, 0, -1))));
+        CHECK(!point_ray_intersects(point, Ray(Vec3(1, 0, 0), Vec3(0, 0, 1)))); }
+}
+
 int main() {
     simplex_tests();
     epa_tests();
@@ -332,6 +403,7 @@ int main() {
     plane_point_tests();
     dbvt_tests();
     bound_tests();
+    ray_tests();
     std::printf("KAT summary: %d checks passed, %d failed\n", g_pass, g_fail);
     return g_fail == 0 ? 0 : 1;
 }

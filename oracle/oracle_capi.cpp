@@ -8,6 +8,7 @@
 #include <vector>
 #include "bam3d_oracle.hpp"
 #include "broad_oracle.hpp"
+#include "ray_oracle.hpp"
 
 using namespace orc;
 
@@ -210,6 +211,37 @@ void orc_gjk_complex_batch(const uint8_t* kind, const float* params, const float
 }
 
 // ---- single-call helpers used by the parity / golden tests -------------------------------------------------
+// Ray casts against primitives (ray_oracle.hpp). rays: n_rays x 6 f32 (origin, direction) — or, for query 2, segments
+// (start, end) of a swept Particle; casts: n x (ray index, shape index). query: 0 = intersects_transformed,
+// 1 = intersection_transformed, 2 = (Particle, Range<Vec3>). out_status: 0 hit, 1 miss, 6 unsupported (ConvexPolyhedron);
+// out_points: n x 3 f32, the world-space hit point for queries 1 and 2 (zero otherwise).
+void orc_ray_cast_batch(const uint8_t* kind, const float* params, const float* xform, const float* rays, const uint32_t* casts,
+                        uint64_t n, int32_t query, float* out_points, uint8_t* out_status, int nthreads) {
+    ShapeTable T{kind, params, xform, nullptr, nullptr, nullptr};
+    parallel_for(n, nthreads, [&](uint64_t b, uint64_t e, int) {
+        for (uint64_t i = b; i < e; ++i) {
+            const float* r = rays + 6 * (size_t)casts[2 * i];
+            const uint32_t si = casts[2 * i + 1];
+            Vec3 p = Vec3::zero();
+            uint8_t st = 1;
+            if (kind[si] == POLYHEDRON) {
+                st = 6;
+            } else {
+                Shape s = T.shape(si);
+                Mat4 m = T.mat(si);
+                bool hit;
+                if (query == 0) hit = ray_intersects_transformed(s, Ray(Vec3(r[0], r[1], r[2]), Vec3(r[3], r[4], r[5])), m);
+                else if (query == 1) hit = ray_intersection_transformed(s, Ray(Vec3(r[0], r[1], r[2]), Vec3(r[3], r[4], r[5])), m, p);
+                else hit = particle_sweep_transformed(s, Vec3(r[0], r[1], r[2]), Vec3(r[3], r[4], r[5]), m, p);
+                st = hit ? 0 : 1;
+                if (!hit) p = Vec3::zero();
+            }
+            out_status[i] = st;
+            out_points[3 * i] = p.x; out_points[3 * i + 1] = p.y; out_points[3 * i + 2] = p.z;
+        }
+    });
+}
+
 void orc_support_point(uint8_t kind, const float* params4, const float* verts, uint32_t nverts, const float* dir3,
                        const float* xform16, float* out3) {
     Shape s; s.kind = kind; s.p0 = params4[0]; s.p1 = params4[1]; s.p2 = params4[2]; s.verts = verts; s.nverts = nverts;

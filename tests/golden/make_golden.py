@@ -55,7 +55,21 @@ def generate(oracle):
                                frustum_planes=np.array(planes, dtype=np.float32), frustum_values=np.concatenate(fv),
                                frustum_relation=np.concatenate(fr), frustum_offsets=np.array(foff, dtype=np.uint64),
                                collider_pairs=tree.find_collider_pairs(dirty))
+    prim = scenes_for_rays()
+    rays, segments, casts = prim[1:]
+    rg = {}
+    for name, q, r in (("intersects", 0, rays), ("intersection", 1, rays), ("sweep", 2, segments)):
+        pts, st = oracle.ray_cast(prim[0], r, casts, q)
+        rg[name + "_points"], rg[name + "_status"] = pts, st
+    out["rays_golden"] = rg
     return out
+
+
+def scenes_for_rays():
+    from bam3d_b200 import scenes
+    sc = scenes.all_kinds_pairs(600, s=1.2, seed=0xB3D060D6)
+    rays, segments, casts = scenes.primitive_rays(sc, 3000, seed=0xB3D060D7)
+    return sc, rays, segments, casts
 
 
 if __name__ == "__main__":

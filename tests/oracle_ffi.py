@@ -119,6 +119,19 @@ class Oracle:
                                        C.c_uint64(len(pairs)), C.c_int(mode), C.c_int(int(strategy)), _p(out), _p(st))
         return out, st
 
+    def ray_cast(self, scene, rays, casts, query, nthreads=1):
+        """-> (points[n, 3], status[n]); query 0 = intersects_transformed, 1 = intersection_transformed, 2 = swept particle."""
+        kind, params, mesh_id, mv, mo = self._scene_args(scene)
+        xform = np.ascontiguousarray(scene["xform"], dtype=np.float32)
+        rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 6)
+        casts = np.ascontiguousarray(casts, dtype=np.uint32).reshape(-1, 2)
+        n = len(casts)
+        pts = np.zeros((n, 3), dtype=np.float32)
+        st = np.zeros(n, dtype=np.uint8)
+        self.lib.orc_ray_cast_batch(_p(kind), _p(params), _p(xform), _p(rays), _p(casts), C.c_uint64(n), C.c_int32(int(query)), _p(pts),
+                                    _p(st), C.c_int(nthreads))
+        return pts, st
+
     def support_point(self, kind, params4, direction, xform16, verts=None):
         params4 = np.ascontiguousarray(params4, dtype=np.float32)
         direction = np.ascontiguousarray(direction, dtype=np.float32)
