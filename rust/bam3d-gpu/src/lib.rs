@@ -2,7 +2,7 @@
 //! the ABI takes and exposes batched `GJK` / `SweepAndPrune3` calls with the crate's own types.
 //! SOURCE ONLY: this repository's build image has no cargo / rustc, so this file is not compiled or tested here; the
 //! compiled host layer with the same shape is include/bam3d.hpp (C++), exercised by tests/cpp/kat_gpu.cpp.
-use bam3d::{Aabb3, CollisionStrategy, Contact, Primitive3};
+use bam3d::{Aabb3, CollisionStrategy, Contact, Primitive3, Ray};
 use glam::{Mat4, Vec3};
 use std::os::raw::{c_char, c_void};
 
@@ -30,6 +30,23 @@ extern "C" {
     fn bam3d_gjk_time_of_impact(c: *mut ctx, s0: *const c_void, s1: *const c_void, pairs: *const u32, n: u64, cfg: *const GjkSettings,
                                 out: *mut RawContact, status: *mut u8) -> i32;
     fn bam3d_sap_find_pairs(c: *mut ctx, aabbs: *const f32, n: u64, axis: *mut i32, perm: *mut u32, pairs: *mut u32, cap: u64, count: *mut u64) -> i32;
+    fn bam3d_sap_find_pairs_shard(c: *mut ctx, aabbs: *const f32, n: u64, axis: *mut i32, perm: *mut u32, pairs: *mut u32, cap: u64,
+                                  count: *mut u64, shard: u32, n_shards: u32) -> i32;
+    fn bam3d_ray_cast(c: *mut ctx, s: *const c_void, rays: *const f32, n_rays: u64, casts: *const u32, n: u64, query: i32,
+                      points: *mut f32, status: *mut u8) -> i32;
+}
+
+/// Batched `ContinuousTransformed<Ray> for Primitive3` (ray.rs:68-78): `casts[i] = (ray index, shape index)`.
+/// `None` where the reference returns `None`; a ConvexPolyhedron (status 6) is not computed on the device and should be
+/// routed to the crate's own `polyhedron.rs` implementation.
+pub fn ray_intersection_batch(ctx: &Context, shapes: &ShapeSet, rays: &[Ray], casts: &[(u32, u32)]) -> Result<Vec<Option<Vec3>>, i32> {
+    let flat: Vec<f32> = rays.iter().flat_map(|r| [r.origin.x(), r.origin.y(), r.origin.z(), r.direction.x(), r.direction.y(), r.direction.z()]).collect();
+    let idx: Vec<u32> = casts.iter().flat_map(|&(r, s)| [r, s]).collect();
+    let mut pts = vec![0f32; 3 * casts.len()];
+    let mut st = vec![0u8; casts.len()];
+    let rc = unsafe { bam3d_ray_cast(ctx.0, shapes.h, flat.as_ptr(), rays.len() as u64, idx.as_ptr(), casts.len() as u64, 1, pts.as_mut_ptr(), st.as_mut_ptr()) };
+    if rc != 0 { return Err(rc); }
+    Ok(st.iter().enumerate().map(|(i, &s)| if s == 0 { Some(Vec3::new(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2])) } else { None }).collect())
 }
 
 pub struct Context(*mut ctx);
