@@ -67,6 +67,7 @@ SIGNATURES = {
     "bam3d_sap_find_pairs_dev": (_i32, [_vp, _vp, _u64, C.POINTER(_i32), _vp, _vp, _u64, C.POINTER(_u64)]),
     "bam3d_sap_find_pairs_shard": (_i32, [_vp, _vp, _u64, C.POINTER(_i32), _vp, _vp, _u64, C.POINTER(_u64), _u32, _u32]),
     "bam3d_sap_find_pairs_shard_dev": (_i32, [_vp, _vp, _u64, C.POINTER(_i32), _vp, _vp, _u64, C.POINTER(_u64), _u32, _u32]),
+    "bam3d_sap_variance": (_i32, [_vp, _vp, _u64, _vp, C.POINTER(_i32)]),
     "bam3d_shapes_world_aabbs": (_i32, [_vp, _vp, _vp]),
     "bam3d_shapes_world_aabbs_dev": (_i32, [_vp, _vp, _vp]),
     "bam3d_bvh_build": (_i32, [_vp, _vp, _u64, C.POINTER(_vp)]),

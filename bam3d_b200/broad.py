@@ -75,6 +75,15 @@ class SweepAndPrune3:
         return pairs[:cnt], perm
 
 
+def variance3(ctx, aabbs):
+    """Variance3 (sweep_prune.rs:166-216) over `aabbs` in the given order -> (sums[6] = csum.xyz, csumsq.xyz, next axis)."""
+    aabbs = np.ascontiguousarray(aabbs, dtype=np.float32).reshape(-1, 6)
+    sums = np.zeros(6, dtype=np.float32)
+    axis = C.c_int32(0)
+    ctx.check(ctx._lib.bam3d_sap_variance(ctx.handle, _ptr(aabbs), len(aabbs), _ptr(sums), C.byref(axis)))
+    return sums, int(axis.value)
+
+
 def frustum_from_mat4(mat4_cols):
     """Frustum::from_mat4 (frustum.rs:46-75) -> 6 planes x (n.xyz, d): left, right, bottom, top, near, far; None if a
     plane degenerates."""

@@ -146,40 +146,116 @@ __global__ void __launch_bounds__(BT) sap_sweep_kernel(const float4* __restrict_
 // Variance3 (sweep_prune.rs:166-216): c = (min + max) / 2; csum += c; csumsq += c * c, accumulated SEQUENTIALLY in
 // sorted order exactly as the reference's loop does (f32 addition is not associative, and the three axes of a
 // uniform scene are near-ties, so a tree reduction could pick a different axis). The six running sums are six
-// independent dependency chains: block c of six walks the boxes in order for chain c (0..2 = csum.xyz, 3..5 =
-// csumsq.xyz); its 32 lanes stage 2048 centres at a time in shared memory, then every lane replays the chain.
-__global__ void __launch_bounds__(256) sap_variance_chain_kernel(const float4* __restrict__ lo, const float4* __restrict__ hi, uint32_t n,
-                                                                 float* __restrict__ sums) {
-    // Double buffered: warps 1..7 stage the next tile of centres (many loads in flight) while warp 0 replays the
-    // sequential chain over the current one — the chain (one dependent FADD per box) is the critical path.
-    constexpr int TILE = 2048;
-    __shared__ float cs[2][TILE];
+// independent chains: block c of six walks the boxes in order for chain c (0..2 = csum.xyz, 3..5 = csumsq.xyz).
+//
+// A chain of n dependent FADDs is latency bound (4 cycles each: 14 ms for 4M boxes). The same bits come out of integer
+// arithmetic, which IS associative: while the running sum `acc` stays inside one binade [2^e, 2^(e+1)) its ulp u is
+// constant, acc = A * u with A an integer in [2^23, 2^24), and fl(acc + c) = (A + r) * u where r = c / u rounded to the
+// nearest integer — unless c / u is exactly half-way (then the tie goes to the even RESULT, which depends on A) or the
+// sum leaves the binade. So a tile of values is handled in parallel: every thread rounds its values to r_i with exact
+// integer shifts (mantissa and exponent of c), the block adds up S = sum r_i and B = sum |r_i|, and if no value was a tie
+// and A - B >= 2^23 + 1 and A + B <= 2^24 - 1 (every prefix stays inside the binade, with the half-ulp of slack that
+// keeps the un-rounded prefix inside too) the new sum is (A + S) * u exactly. Any other tile — the first few, the ~25
+// binade crossings, an exact tie (probability ~2^-22 per value), non-positive / non-finite sums — is replayed
+// sequentially by one thread, as before.
+constexpr int VAR_TILE = 4096;
+constexpr int VAR_THREADS = 256;
+constexpr int VAR_PER_THREAD = VAR_TILE / VAR_THREADS;
+
+// c / 2^k rounded to the nearest integer (round-half flagged as `tie`, not resolved). false: not representable here.
+B3_DEV bool round_scaled(float c, int k, int& r, bool& tie) {
+    const uint32_t b = __float_as_uint(c);
+    const uint32_t ex = (b >> 23) & 0xFFu;
+    uint32_t mant = b & 0x7FFFFFu;
+    tie = false;
+    r = 0;
+    if (ex == 0xFFu) return false;  // inf / NaN
+    int E;
+    if (ex == 0) E = -149; else { mant |= 0x800000u; E = (int)ex - 150; }  // |c| = mant * 2^E
+    if (mant == 0) return true;
+    const int sh = E - k;
+    uint32_t q;
+    if (sh >= 0) {
+        if (sh > 6) return false;  // |c| >= 2^30 ulps: certainly leaves the binade
+        q = mant << sh;
+    } else {
+        const int s = -sh;
+        if (s > 25) q = 0;
+        else {
+            q = mant >> s;
+            const uint32_t rem = mant & ((1u << s) - 1u), half = 1u << (s - 1);
+            if (rem > half) ++q;
+            else if (rem == half) tie = true;
+        }
+    }
+    r = (b >> 31) ? -(int)q : (int)q;
+    return true;
+}
+
+__global__ void __launch_bounds__(VAR_THREADS) sap_variance_chain_kernel(const float4* __restrict__ lo, const float4* __restrict__ hi, uint32_t n,
+                                                                         float* __restrict__ sums) {
+    __shared__ float cs[VAR_TILE];
+    __shared__ int s_S[VAR_THREADS / 32], s_B[VAR_THREADS / 32], s_bad[VAR_THREADS / 32];
+    __shared__ float s_acc;
     const int chain = blockIdx.x, axis = chain % 3;
     const bool squared = chain >= 3;
-    const int warp = threadIdx.x >> 5;
-    auto stage = [&](uint32_t base, float* dst, int first, int step) {
-        const uint32_t cnt = min((uint32_t)TILE, n - base);
-        for (uint32_t t = first; t < cnt; t += step) {
-            float c = (comp(__ldg(lo + base + t), axis) + comp(__ldg(hi + base + t), axis)) / 2.0f;
-            dst[t] = squared ? c * c : c;
-        }
-    };
-    stage(0, cs[0], threadIdx.x, 256);
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_acc = 0.f;
     __syncthreads();
-    float acc = 0.f;
-    int cur = 0;
-    for (uint32_t base = 0; base < n; base += TILE, cur ^= 1) {
-        if (warp == 0) {
-            const uint32_t cnt = min((uint32_t)TILE, n - base);
-            const float* c = cs[cur];
+    for (uint32_t base = 0; base < n; base += VAR_TILE) {
+        const uint32_t cnt = min((uint32_t)VAR_TILE, n - base);
+        // stage this tile's values (all loads of a thread in flight at once); element t of the tile -> cs[t]
+        float v[VAR_PER_THREAD];
+#pragma unroll
+        for (int j = 0; j < VAR_PER_THREAD; ++j) {
+            const uint32_t t = threadIdx.x + j * VAR_THREADS;
+            float c = 0.f;
+            if (t < cnt) {
+                c = (comp(__ldg(lo + base + t), axis) + comp(__ldg(hi + base + t), axis)) / 2.0f;
+                if (squared) c = c * c;
+            }
+            v[j] = c;
+        }
+        const float acc = s_acc;
+        const uint32_t ab = __float_as_uint(acc);
+        const uint32_t aex = (ab >> 23) & 0xFFu;
+        const bool acc_ok = (ab >> 31) == 0 && aex != 0 && aex != 0xFFu;  // positive, normal
+        const int k = (int)aex - 150;                                      // ulp of acc = 2^k
+        const int A = (int)((ab & 0x7FFFFFu) | 0x800000u);
+        int S = 0, B = 0, bad = acc_ok ? 0 : 1;
+#pragma unroll
+        for (int j = 0; j < VAR_PER_THREAD; ++j) {
+            const uint32_t t = threadIdx.x + j * VAR_THREADS;
+            cs[t] = v[j];
+            if (t < cnt && !bad) {
+                int r; bool tie;
+                if (!round_scaled(v[j], k, r, tie) || tie) bad = 1;
+                else { S += r; B += abs(r); if (B >= (1 << 24)) bad = 1; }
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            S += __shfl_xor_sync(0xFFFFFFFFu, S, off);
+            B += __shfl_xor_sync(0xFFFFFFFFu, min(B, 1 << 24), off);
+            bad |= __shfl_xor_sync(0xFFFFFFFFu, bad, off);
+        }
+        if (lane == 0) { s_S[warp] = S; s_B[warp] = min(B, 1 << 25); s_bad[warp] = bad; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            long long St = 0, Bt = 0; int badt = 0;
+            for (int w = 0; w < VAR_THREADS / 32; ++w) { St += s_S[w]; Bt += s_B[w]; badt |= s_bad[w]; }
+            float a = acc;
+            if (!badt && (long long)A - Bt >= (1ll << 23) + 1 && (long long)A + Bt <= (1ll << 24) - 1) {
+                a = __uint_as_float((aex << 23) | ((uint32_t)(A + (int)St) & 0x7FFFFFu));
+            } else {
 #pragma unroll 16
-            for (uint32_t t = 0; t < cnt; ++t) acc = acc + c[t];
-        } else if (base + TILE < n) {
-            stage(base + TILE, cs[cur ^ 1], threadIdx.x - 32, 224);
+                for (uint32_t t = 0; t < cnt; ++t) a = a + cs[t];
+            }
+            s_acc = a;
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) sums[chain] = acc;
+    if (threadIdx.x == 0) sums[chain] = s_acc;
 }
 
 // variance = csumsq * (csum * csum / n) — a product, not a difference, as in the reference (:203-204); strict > from axis 0
@@ -225,8 +301,21 @@ int launch_sap_sort(cudaStream_t st, const float* d_aabbs, uint32_t n, int axis,
     return launched;
 }
 
+__global__ void __launch_bounds__(BT) boxes_to_lohi_kernel(const float* __restrict__ aabbs, uint32_t n, float4* __restrict__ lo, float4* __restrict__ hi) {
+    uint32_t k = blockIdx.x * BT + threadIdx.x;
+    if (k >= n) return;
+    const float* b = aabbs + 6 * (size_t)k;
+    lo[k] = make_float4(b[0], b[1], b[2], 0.f);
+    hi[k] = make_float4(b[3], b[4], b[5], 0.f);
+}
+int launch_boxes_to_lohi(cudaStream_t st, const float* d_aabbs, uint32_t n, float4* lo, float4* hi) {
+    if (n == 0) return 0;
+    boxes_to_lohi_kernel<<<(n + BT - 1) / BT, BT, 0, st>>>(d_aabbs, n, lo, hi);
+    return 1;
+}
+
 int launch_sap_variance(cudaStream_t st, const SapScratch& S, uint32_t n, float* d_sums, int* d_next_axis) {
-    sap_variance_chain_kernel<<<6, 256, 0, st>>>(S.lo, S.hi, n, d_sums);
+    sap_variance_chain_kernel<<<6, VAR_THREADS, 0, st>>>(S.lo, S.hi, n, d_sums);
     sap_variance_axis_kernel<<<1, 32, 0, st>>>(d_sums, n, d_next_axis);
     return 2;
 }

@@ -26,7 +26,9 @@ int sap_bits_for(uint32_t n);
 // phase 1: keys, stable radix sort, gather of the sorted boxes (+ optional 6-float rows), candidate-test count
 int launch_sap_sort(cudaStream_t st, const float* d_aabbs, uint32_t n, int axis, const SapScratch& S, uint32_t* d_perm, float* d_sorted6,
                     unsigned long long* d_candidates);
-// Variance3 in sorted order (six sequential chains); d_sums: 6 floats; d_next_axis: device i32
+// 6-float rows -> the (lo, hi) float4 arrays the variance kernels read, order unchanged
+int launch_boxes_to_lohi(cudaStream_t st, const float* d_aabbs, uint32_t n, float4* lo, float4* hi);
+// Variance3 in the order of S.lo / S.hi (six chains; bit-identical to the sequential loop); d_sums: 6 floats; d_next_axis: device i32
 int launch_sap_variance(cudaStream_t st, const SapScratch& S, uint32_t n, float* d_sums, int* d_next_axis);
 // phase 2a: tiled forward sweep; d_count: device u64 (pairs found, may exceed capacity)
 // Only pairs whose higher sorted slot j lies in [j_begin, j_end) are emitted (the multi-GPU shard of the sweep).

@@ -719,6 +719,30 @@ int32_t bam3d_sap_find_pairs_shard(bam3d_ctx* ctx, const float* aabbs, uint64_t 
     return BAM3D_OK;
 }
 
+// Variance3 (sweep_prune.rs:166-216) over the boxes in the order given: add_bound for each, then compute_axis.
+int32_t bam3d_sap_variance(bam3d_ctx* ctx, const float* aabbs, uint64_t n64, float* out_sums6, int32_t* out_axis) {
+    if (!ctx || !out_sums6 || !out_axis || (n64 && !aabbs)) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_sap_variance: null argument", cudaSuccess);
+    int32_t rc;
+    if ((rc = check_n(ctx, n64))) return rc;
+    const uint32_t n = (uint32_t)n64;
+    CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
+    const size_t nn = n ? n : 1;
+    if ((rc = ctx->bp4.reserve(ctx, nn * 24)) || (rc = ctx->bp2.reserve(ctx, nn * 16 * 2)) || (rc = ctx->small.reserve(ctx, 1024))) return rc;
+    SapScratch S{};
+    S.lo = (float4*)ctx->bp2.ptr; S.hi = S.lo + nn;
+    float* d_sums = (float*)((char*)ctx->small.ptr + 864);
+    int* d_axis = (int*)((char*)ctx->small.ptr + 840);
+    if (n) CU_TRY(cudaMemcpyAsync(ctx->bp4.ptr, aabbs, (size_t)n * 24, cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpyAsync(aabbs)");
+    ctx->launches += launch_boxes_to_lohi(ctx->stream, (const float*)ctx->bp4.ptr, n, S.lo, S.hi);
+    { KernelTimer kt(ctx);
+      ctx->launches += launch_sap_variance(ctx->stream, S, n, d_sums, d_axis); }
+    if ((rc = check_launch(ctx, "sap_variance_chain_kernel"))) return rc;
+    CU_TRY(cudaMemcpyAsync(out_sums6, d_sums, 24, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(sums)");
+    CU_TRY(cudaMemcpyAsync(out_axis, d_axis, 4, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(axis)");
+    CU_TRY(cudaStreamSynchronize(ctx->stream), "bam3d_sap_variance");
+    return BAM3D_OK;
+}
+
 // ---- world AABBs -----------------------------------------------------------------------------------------------
 int32_t bam3d_shapes_world_aabbs_dev(bam3d_ctx* ctx, const bam3d_shapes* shapes, float* d_out6) {
     if (!ctx || !shapes || (shapes->n && !d_out6)) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_shapes_world_aabbs: null argument", cudaSuccess);

@@ -199,6 +199,10 @@ int32_t bam3d_sap_find_pairs(bam3d_ctx* ctx, const float* aabbs, uint64_t n, int
 int32_t bam3d_sap_find_pairs_dev(bam3d_ctx* ctx, const float* d_aabbs, uint64_t n, int32_t* inout_sweep_axis,
                                  uint32_t* d_perm, uint32_t* d_pairs, uint64_t capacity, uint64_t* out_count);
 
+/* Variance3 (sweep_prune.rs:166-216) on its own: add_bound for every box in the order given, then compute_axis(n).
+ * out_sums6 = csum.xyz, csumsq.xyz — the same bits as the reference's sequential f32 accumulation. */
+int32_t bam3d_sap_variance(bam3d_ctx* ctx, const float* aabbs, uint64_t n, float* out_sums6, int32_t* out_axis);
+
 /* Multi-GPU form: every GPU sorts the full box set (identical perm and next axis everywhere) and searches
  * only the pairs whose higher sorted position j lies in [n * shard / n_shards, n * (shard + 1) / n_shards). The shards'
  * outputs concatenated in shard order are exactly the output of bam3d_sap_find_pairs, so each GPU can feed its slice

@@ -311,6 +311,14 @@ int32_t orc_sap_variance_axis(const float* aabbs, uint64_t n) {
     return v.compute_axis((float)n);
 }
 
+// Variance3 over the boxes in the given order: out6 = csum.xyz, csumsq.xyz; returns compute_axis(n).
+int32_t orc_sap_variance_sums(const float* aabbs, uint64_t n, float* out6) {
+    Variance3 v; v.clear();
+    for (uint64_t i = 0; i < n; ++i) v.add_bound(box6(aabbs + 6 * i));
+    out6[0] = v.csum.x; out6[1] = v.csum.y; out6[2] = v.csum.z; out6[3] = v.csumsq.x; out6[4] = v.csumsq.y; out6[5] = v.csumsq.z;
+    return v.compute_axis((float)n);
+}
+
 struct orc_dbvt { Dbvt tree; };
 orc_dbvt* orc_dbvt_build(const float* aabbs, const float* fat_aabbs, uint64_t n) {
     orc_dbvt* t = new orc_dbvt();

@@ -186,6 +186,13 @@ class Oracle:
                 return pairs[:cnt].copy(), perm, int(ax.value)
             cap = int(cnt)
 
+    def variance3(self, aabbs):
+        """Variance3 (sweep_prune.rs:166-216) over the boxes in the given order -> (sums[6] = csum.xyz, csumsq.xyz, axis)."""
+        aabbs = np.ascontiguousarray(aabbs, dtype=np.float32).reshape(-1, 6)
+        out = np.zeros(6, dtype=np.float32)
+        axis = self.lib.orc_sap_variance_sums(_p(aabbs), C.c_uint64(len(aabbs)), _p(out))
+        return out, int(axis)
+
     def dbvt_build(self, aabbs, fat=None):
         aabbs = np.ascontiguousarray(aabbs, dtype=np.float32).reshape(-1, 6)
         fat = None if fat is None else np.ascontiguousarray(fat, dtype=np.float32).reshape(-1, 6)

@@ -34,6 +34,30 @@ def test_sap_parity_and_axis_sequence(ctx, oracle, sap_strategy):
         axis = oaxis
 
 
+def test_variance3_sums_bit_exact(ctx, oracle):
+    """The running sums of Variance3 are f32 accumulated sequentially in the reference; the device computes the same
+    bits with per-tile integer arithmetic inside a binade and falls back to the sequential chain at binade crossings
+    and exact round-half ties. Scenes: C4-like (sums cross ~25 binades), negative and mixed-sign coordinates,
+    half-integer coordinates (every addition beyond 2^24 is an exact tie), huge / tiny magnitudes, short inputs."""
+    rng = np.random.default_rng(11)
+    cases = {}
+    cases["c4"] = scenes.aabb_scene(1 << 20)[0]
+    cases["negative"] = -scenes.aabb_scene(300_000, seed=0xB3D0C402)[0][:, [3, 4, 5, 0, 1, 2]]
+    mixed = scenes.aabb_scene(300_000, seed=0xB3D0C403)[0] - np.float32(50.0)
+    cases["mixed_sign"] = mixed.astype(np.float32)
+    half = rng.integers(0, 64, size=(400_000, 3)).astype(np.float32)
+    cases["half_integers"] = np.concatenate([half, half + np.float32(1.0)], axis=1)          # centres k + 0.5
+    cases["huge_and_tiny"] = (rng.random((200_000, 6)) * np.where(rng.random((200_000, 1)) < 0.5, 1e-12, 1e12)).astype(np.float32)
+    cases["short"] = scenes.aabb_scene(5000)[0][:37]
+    cases["one_tile_boundary"] = scenes.aabb_scene(8192)[0][:4097]
+    for name, boxes in cases.items():
+        boxes = np.ascontiguousarray(boxes, dtype=np.float32)
+        sums, axis = broad.variance3(ctx, boxes)
+        osums, oaxis = oracle.variance3(boxes)
+        assert sums.tobytes() == osums.tobytes(), (name, sums, osums)
+        assert axis == oaxis, name
+
+
 @pytest.mark.parametrize("n_shards", [2, 3, 8])
 def test_sap_shards_concatenate_to_the_full_list(ctx, oracle, sap_strategy, n_shards):
     """Multi-GPU form of the sweep: every shard sorts everything (same perm, same next axis) and searches
