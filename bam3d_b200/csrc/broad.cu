@@ -819,6 +819,55 @@ __global__ void __launch_bounds__(BT) bvh_collider_pairs_kernel(BvhDev T, const 
     if (!FILL) counts[v] = cnt;
 }
 
+// Sweep-and-prune over the sorted slots, BVH strategy, in ONE pass: the slots of the shard [v_begin, v_end) query the tree
+// over the sorted boxes and append every overlapping pair (h < v) to the key list through a warp-aggregated atomic. The
+// keys are radix-sorted into the reference's (j, i) order afterwards anyway, so their emission order is free — which is
+// what lets this skip the count + scan + fill structure the DBVT queries need. *count keeps counting past `capacity`.
+__global__ void __launch_bounds__(BT) bvh_overlap_append_kernel(BvhDev T, const float* __restrict__ aabbs, uint32_t v_begin, uint32_t v_end,
+                                                                int key_shift, unsigned long long* __restrict__ keys,
+                                                                unsigned long long capacity, unsigned long long* __restrict__ count) {
+    const uint32_t v = v_begin + blockIdx.x * BT + threadIdx.x;
+    if (v >= v_end) return;
+    const float* b = aabbs + 6 * (size_t)v;
+    Query q;
+    q.qlo = make_float4(b[0], b[1], b[2], 0.f); q.qhi = make_float4(b[3], b[4], b[5], 0.f);
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t stack[64];
+    int sp = 0;
+    stack[sp++] = (T.n == 1) ? (T.n - 1) : 0u;
+    const uint32_t first_leaf = T.n - 1;
+    while (sp > 0) {
+        const uint32_t node = stack[--sp];
+        const float4 mn = __ldg(T.lo + node), mx = __ldg(T.hi + node);
+        V3 pt; int rel;
+        if (!accept<BQ_AABB>(q, mn, mx, pt, rel)) continue;
+        if (node >= first_leaf) {
+            const uint32_t h = __ldg(T.leaf_value + (node - first_leaf));
+            if (h < v) {
+                const uint32_t act = __activemask();
+                const uint32_t leader = __ffs(act) - 1;
+                unsigned long long base = 0;
+                if (lane == leader) base = atomicAdd(count, (unsigned long long)__popc(act));
+                base = __shfl_sync(act, base, leader);
+                const unsigned long long slot = base + __popc(act & ((1u << lane) - 1u));
+                if (slot < capacity) keys[slot] = ((unsigned long long)v << key_shift) | h;
+            }
+        } else if (sp <= 62) {
+            const int2 ch = __ldg(T.children + node);
+            stack[sp++] = (uint32_t)ch.y;
+            stack[sp++] = (uint32_t)ch.x;
+        }
+    }
+}
+
+int launch_bvh_overlap_append(cudaStream_t st, const BvhDev& T, const float* d_aabbs, uint32_t v_begin, uint32_t v_end, int key_shift,
+                              unsigned long long* d_pair_keys, uint64_t capacity, unsigned long long* d_count) {
+    cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), st);
+    if (T.n == 0 || v_end <= v_begin) return 0;
+    bvh_overlap_append_kernel<<<(v_end - v_begin + BT - 1) / BT, BT, 0, st>>>(T, d_aabbs, v_begin, v_end, key_shift, d_pair_keys, capacity, d_count);
+    return 1;
+}
+
 int launch_bvh_collider_pairs(cudaStream_t st, const BvhDev& T, const float* d_aabbs, const uint8_t* d_dirty, uint32_t v_begin,
                               uint32_t v_end, uint32_t* d_counts, const unsigned long long* d_offsets, unsigned long long* d_pair_keys,
                               int key_shift) {

@@ -76,6 +76,10 @@ int launch_bvh_ray_closest(cudaStream_t st, const BvhDev& T, const float* d_rays
 int launch_bvh_collider_pairs(cudaStream_t st, const BvhDev& T, const float* d_aabbs, const uint8_t* d_dirty, uint32_t v_begin,
                               uint32_t v_end, uint32_t* d_counts, const unsigned long long* d_offsets, unsigned long long* d_pair_keys,
                               int key_shift);
+// sweep-and-prune, BVH strategy: one pass, pairs (h < v) of the slots v in [v_begin, v_end) appended to d_pair_keys as
+// (v << key_shift | h) in arbitrary order; *d_count (device u64) = pairs found (may exceed capacity)
+int launch_bvh_overlap_append(cudaStream_t st, const BvhDev& T, const float* d_aabbs, uint32_t v_begin, uint32_t v_end, int key_shift,
+                              unsigned long long* d_pair_keys, uint64_t capacity, unsigned long long* d_count);
 int launch_exclusive_scan_u32_to_u64(cudaStream_t st, const uint32_t* d_in, unsigned long long* d_out, uint32_t n, void* tmp, size_t tmp_bytes);
 size_t scan_tmp_bytes(uint32_t n);
 int launch_sort_u64(cudaStream_t st, unsigned long long* d_keys, unsigned long long* d_alt, uint64_t n, void* tmp, size_t tmp_bytes, bool* in_alt);

@@ -655,15 +655,10 @@ static int32_t sap_run(bam3d_ctx* ctx, const float* d_aabbs, uint64_t n64, int32
         const int shift = sap_bits_for(n);
         { KernelTimer kt(ctx);
           ctx->launches += launch_bvh_build(ctx->stream, d_sorted6, n, W, nlo, nhi, children, leaf_value);
-          cudaMemsetAsync(d_counts + n, 0, 4, ctx->stream);
-          ctx->launches += launch_bvh_collider_pairs(ctx->stream, T, d_sorted6, nullptr, j_begin, j_end, d_counts, nullptr, nullptr, shift);
-          ctx->launches += launch_exclusive_scan_u32_to_u64(ctx->stream, d_counts, d_offsets, n, ctx->cub_tmp.ptr, tmp_bytes); }
-        CU_TRY(cudaMemcpyAsync(&h_count, d_offsets + n, 8, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(count)");
-        CU_TRY(cudaStreamSynchronize(ctx->stream), "sap bvh count");
-        if (h_count <= capacity && h_count) {
-            KernelTimer kt(ctx);
-            ctx->launches += launch_bvh_collider_pairs(ctx->stream, T, d_sorted6, nullptr, j_begin, j_end, d_counts, d_offsets, S.pair_keys, shift);
-        }
+          ctx->launches += launch_bvh_overlap_append(ctx->stream, T, d_sorted6, j_begin, j_end, shift, S.pair_keys, capacity, d_count); }
+        CU_TRY(cudaMemcpyAsync(&h_count, d_count, 8, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(count)");
+        CU_TRY(cudaStreamSynchronize(ctx->stream), "sap bvh pair search");
+        (void)d_counts; (void)d_offsets;
     }
     if ((rc = check_launch(ctx, "sap pair search"))) return rc;
     *out_count = h_count;
