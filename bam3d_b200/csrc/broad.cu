@@ -159,8 +159,7 @@ __global__ void __launch_bounds__(BT) sap_sweep_kernel(const float4* __restrict_
 // binade crossings, an exact tie (probability ~2^-22 per value), non-positive / non-finite sums — is replayed
 // sequentially by one thread, as before.
 constexpr int VAR_TILE = 4096;
-constexpr int VAR_THREADS = 256;
-constexpr int VAR_PER_THREAD = VAR_TILE / VAR_THREADS;
+constexpr int VAR_THREADS = 1024;  // 4 values per thread per tile: one LDG.128
 
 // c / 2^k rounded to the nearest integer (round-half flagged as `tie`, not resolved). false: not representable here.
 B3_DEV bool round_scaled(float c, int k, int& r, bool& tie) {
@@ -192,30 +191,45 @@ B3_DEV bool round_scaled(float c, int k, int& r, bool& tie) {
     return true;
 }
 
-__global__ void __launch_bounds__(VAR_THREADS) sap_variance_chain_kernel(const float4* __restrict__ lo, const float4* __restrict__ hi, uint32_t n,
+// The six value streams of Variance3, planar: vals[chain * stride + i] = c (chains 0..2) or c * c (chains 3..5) of box i.
+__global__ void __launch_bounds__(BT) sap_centres_kernel(const float4* __restrict__ lo, const float4* __restrict__ hi, uint32_t n, size_t stride,
+                                                         float* __restrict__ vals) {
+    const uint32_t i = blockIdx.x * BT + threadIdx.x;
+    if (i >= n) return;
+    const float4 a = __ldg(lo + i), b = __ldg(hi + i);
+    const float cx = (a.x + b.x) / 2.0f, cy = (a.y + b.y) / 2.0f, cz = (a.z + b.z) / 2.0f;
+    vals[i] = cx; vals[stride + i] = cy; vals[2 * stride + i] = cz;
+    vals[3 * stride + i] = cx * cx; vals[4 * stride + i] = cy * cy; vals[5 * stride + i] = cz * cz;
+}
+
+__global__ void __launch_bounds__(VAR_THREADS) sap_variance_chain_kernel(const float* __restrict__ vals, uint32_t n, size_t stride,
                                                                          float* __restrict__ sums) {
-    __shared__ float cs[VAR_TILE];
+    __shared__ __align__(16) float cs[VAR_TILE];
     __shared__ int s_S[VAR_THREADS / 32], s_B[VAR_THREADS / 32], s_bad[VAR_THREADS / 32];
     __shared__ float s_acc;
-    const int chain = blockIdx.x, axis = chain % 3;
-    const bool squared = chain >= 3;
+    const int chain = blockIdx.x;
+    const float* __restrict__ src = vals + (size_t)chain * stride;  // stride is a multiple of 4 floats: float4 loads stay aligned
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) s_acc = 0.f;
+    auto load_tile = [&](uint32_t base) {
+        // values past n read as 0 (a no-op for the sum)
+        const uint32_t t = base + 4 * threadIdx.x;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t + 3 < n) v = __ldg(reinterpret_cast<const float4*>(src + t));
+        else {
+            if (t < n) v.x = __ldg(src + t);
+            if (t + 1 < n) v.y = __ldg(src + t + 1);
+            if (t + 2 < n) v.z = __ldg(src + t + 2);
+        }
+        return v;
+    };
+    float4 nxt = load_tile(0);
     __syncthreads();
     for (uint32_t base = 0; base < n; base += VAR_TILE) {
         const uint32_t cnt = min((uint32_t)VAR_TILE, n - base);
-        // stage this tile's values (all loads of a thread in flight at once); element t of the tile -> cs[t]
-        float v[VAR_PER_THREAD];
-#pragma unroll
-        for (int j = 0; j < VAR_PER_THREAD; ++j) {
-            const uint32_t t = threadIdx.x + j * VAR_THREADS;
-            float c = 0.f;
-            if (t < cnt) {
-                c = (comp(__ldg(lo + base + t), axis) + comp(__ldg(hi + base + t), axis)) / 2.0f;
-                if (squared) c = c * c;
-            }
-            v[j] = c;
-        }
+        const float4 v = nxt;
+        if (base + VAR_TILE < n) nxt = load_tile(base + VAR_TILE);  // in flight while this tile is processed
+        reinterpret_cast<float4*>(cs)[threadIdx.x] = v;
         const float acc = s_acc;
         const uint32_t ab = __float_as_uint(acc);
         const uint32_t aex = (ab >> 23) & 0xFFu;
@@ -223,35 +237,44 @@ __global__ void __launch_bounds__(VAR_THREADS) sap_variance_chain_kernel(const f
         const int k = (int)aex - 150;                                      // ulp of acc = 2^k
         const int A = (int)((ab & 0x7FFFFFu) | 0x800000u);
         int S = 0, B = 0, bad = acc_ok ? 0 : 1;
+        const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int j = 0; j < VAR_PER_THREAD; ++j) {
-            const uint32_t t = threadIdx.x + j * VAR_THREADS;
-            cs[t] = v[j];
-            if (t < cnt && !bad) {
-                int r; bool tie;
-                if (!round_scaled(v[j], k, r, tie) || tie) bad = 1;
-                else { S += r; B += abs(r); if (B >= (1 << 24)) bad = 1; }
-            }
+        for (int j = 0; j < 4; ++j) {
+            int r; bool tie;
+            if (!round_scaled(vv[j], k, r, tie) || tie) bad = 1;
+            else { S += r; B += min(abs(r), 1 << 24); }
         }
+        if (B >= (1 << 24)) bad = 1;
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
             S += __shfl_xor_sync(0xFFFFFFFFu, S, off);
-            B += __shfl_xor_sync(0xFFFFFFFFu, min(B, 1 << 24), off);
+            B += __shfl_xor_sync(0xFFFFFFFFu, B, off);
             bad |= __shfl_xor_sync(0xFFFFFFFFu, bad, off);
         }
-        if (lane == 0) { s_S[warp] = S; s_B[warp] = min(B, 1 << 25); s_bad[warp] = bad; }
+        if (lane == 0) { s_S[warp] = S; s_B[warp] = B; s_bad[warp] = bad; }
         __syncthreads();
-        if (threadIdx.x == 0) {
-            long long St = 0, Bt = 0; int badt = 0;
-            for (int w = 0; w < VAR_THREADS / 32; ++w) { St += s_S[w]; Bt += s_B[w]; badt |= s_bad[w]; }
-            float a = acc;
-            if (!badt && (long long)A - Bt >= (1ll << 23) + 1 && (long long)A + Bt <= (1ll << 24) - 1) {
-                a = __uint_as_float((aex << 23) | ((uint32_t)(A + (int)St) & 0x7FFFFFu));
-            } else {
-#pragma unroll 16
-                for (uint32_t t = 0; t < cnt; ++t) a = a + cs[t];
+        if (warp == 0) {
+            long long St = s_S[lane], Bt = s_B[lane];
+            int badt = s_bad[lane];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                St += __shfl_xor_sync(0xFFFFFFFFu, St, off);
+                Bt += __shfl_xor_sync(0xFFFFFFFFu, Bt, off);
+                badt |= __shfl_xor_sync(0xFFFFFFFFu, badt, off);
             }
-            s_acc = a;
+            if (lane == 0) {
+                float a = acc;
+                if (!badt && (long long)A - Bt >= (1ll << 23) + 1 && (long long)A + Bt <= (1ll << 24) - 1) {
+                    a = __uint_as_float((aex << 23) | ((uint32_t)(A + (int)St) & 0x7FFFFFu));
+                } else {
+#pragma unroll 16
+                    for (uint32_t t = 0; t < cnt; ++t) a = a + cs[t];
+#ifdef B3_VAR_TRACE
+                    atomicAdd(reinterpret_cast<int*>(sums) + 16 + chain, 1);
+#endif
+                }
+                s_acc = a;
+            }
         }
         __syncthreads();
     }
@@ -314,10 +337,15 @@ int launch_boxes_to_lohi(cudaStream_t st, const float* d_aabbs, uint32_t n, floa
     return 1;
 }
 
-int launch_sap_variance(cudaStream_t st, const SapScratch& S, uint32_t n, float* d_sums, int* d_next_axis) {
-    sap_variance_chain_kernel<<<6, VAR_THREADS, 0, st>>>(S.lo, S.hi, n, d_sums);
+size_t sap_variance_scratch_bytes(uint32_t n) { return 6 * (((size_t)n + 3) & ~(size_t)3) * sizeof(float); }
+
+int launch_sap_variance(cudaStream_t st, const SapScratch& S, uint32_t n, void* d_scratch, float* d_sums, int* d_next_axis) {
+    const size_t stride = ((size_t)n + 3) & ~(size_t)3;
+    float* vals = reinterpret_cast<float*>(d_scratch);
+    if (n) sap_centres_kernel<<<(n + BT - 1) / BT, BT, 0, st>>>(S.lo, S.hi, n, stride, vals);
+    sap_variance_chain_kernel<<<6, VAR_THREADS, 0, st>>>(vals, n, stride, d_sums);
     sap_variance_axis_kernel<<<1, 32, 0, st>>>(d_sums, n, d_next_axis);
-    return 2;
+    return 3;
 }
 
 int launch_sap_sweep(cudaStream_t st, uint32_t n, int axis, uint32_t j_begin, uint32_t j_end, const SapScratch& S, uint64_t capacity,

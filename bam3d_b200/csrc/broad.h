@@ -29,7 +29,9 @@ int launch_sap_sort(cudaStream_t st, const float* d_aabbs, uint32_t n, int axis,
 // 6-float rows -> the (lo, hi) float4 arrays the variance kernels read, order unchanged
 int launch_boxes_to_lohi(cudaStream_t st, const float* d_aabbs, uint32_t n, float4* lo, float4* hi);
 // Variance3 in the order of S.lo / S.hi (six chains; bit-identical to the sequential loop); d_sums: 6 floats; d_next_axis: device i32
-int launch_sap_variance(cudaStream_t st, const SapScratch& S, uint32_t n, float* d_sums, int* d_next_axis);
+// d_scratch: sap_variance_scratch_bytes(n) (the six planar value streams)
+size_t sap_variance_scratch_bytes(uint32_t n);
+int launch_sap_variance(cudaStream_t st, const SapScratch& S, uint32_t n, void* d_scratch, float* d_sums, int* d_next_axis);
 // phase 2a: tiled forward sweep; d_count: device u64 (pairs found, may exceed capacity)
 // Only pairs whose higher sorted slot j lies in [j_begin, j_end) are emitted (the multi-GPU shard of the sweep).
 int launch_sap_sweep(cudaStream_t st, uint32_t n, int axis, uint32_t j_begin, uint32_t j_end, const SapScratch& S, uint64_t capacity,

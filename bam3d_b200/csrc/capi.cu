@@ -591,7 +591,8 @@ static int32_t sap_run(bam3d_ctx* ctx, const float* d_aabbs, uint64_t n64, int32
     if (bvh_tmp > tmp_bytes) tmp_bytes = bvh_tmp;
     if (scan_tmp > tmp_bytes) tmp_bytes = scan_tmp;
     if ((rc = ctx->bp0.reserve(ctx, (size_t)n * 8 * 2)) || (rc = ctx->bp1.reserve(ctx, (size_t)n * 4 * 2)) || (rc = ctx->bp2.reserve(ctx, (size_t)n * 16 * 2)) ||
-        (rc = ctx->bp3.reserve(ctx, cap1 * 8 * 2)) || (rc = ctx->cub_tmp.reserve(ctx, tmp_bytes)) || (rc = ctx->small.reserve(ctx, 1024)))
+        (rc = ctx->bp3.reserve(ctx, cap1 * 8 * 2)) || (rc = ctx->cub_tmp.reserve(ctx, tmp_bytes)) || (rc = ctx->small.reserve(ctx, 1024)) ||
+        (rc = ctx->bp7.reserve(ctx, sap_variance_scratch_bytes(n))))
         return rc;
     S.keys_in = (unsigned long long*)ctx->bp0.ptr; S.keys_out = S.keys_in + n;
     S.vals_in = (uint32_t*)ctx->bp1.ptr; S.vals_out = S.vals_in + n;
@@ -618,7 +619,7 @@ static int32_t sap_run(bam3d_ctx* ctx, const float* d_aabbs, uint64_t n64, int32
     // Variance3 on the side stream, beside the pair search
     cudaEventRecord(ctx->ev_a, ctx->stream);
     cudaStreamWaitEvent(ctx->stream2, ctx->ev_a, 0);
-    ctx->launches += launch_sap_variance(ctx->stream2, S, n, d_sums, d_axis);
+    ctx->launches += launch_sap_variance(ctx->stream2, S, n, ctx->bp7.ptr, d_sums, d_axis);
     cudaEventRecord(ctx->ev_b, ctx->stream2);
     if ((rc = check_launch(ctx, "sap sort"))) return rc;
     bool use_bvh = strategy == 2;
@@ -722,7 +723,8 @@ int32_t bam3d_sap_variance(bam3d_ctx* ctx, const float* aabbs, uint64_t n64, flo
     const uint32_t n = (uint32_t)n64;
     CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
     const size_t nn = n ? n : 1;
-    if ((rc = ctx->bp4.reserve(ctx, nn * 24)) || (rc = ctx->bp2.reserve(ctx, nn * 16 * 2)) || (rc = ctx->small.reserve(ctx, 1024))) return rc;
+    if ((rc = ctx->bp4.reserve(ctx, nn * 24)) || (rc = ctx->bp2.reserve(ctx, nn * 16 * 2)) || (rc = ctx->small.reserve(ctx, 1024)) ||
+        (rc = ctx->bp7.reserve(ctx, sap_variance_scratch_bytes(n) + 64))) return rc;
     SapScratch S{};
     S.lo = (float4*)ctx->bp2.ptr; S.hi = S.lo + nn;
     float* d_sums = (float*)((char*)ctx->small.ptr + 864);
@@ -730,8 +732,13 @@ int32_t bam3d_sap_variance(bam3d_ctx* ctx, const float* aabbs, uint64_t n64, flo
     if (n) CU_TRY(cudaMemcpyAsync(ctx->bp4.ptr, aabbs, (size_t)n * 24, cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpyAsync(aabbs)");
     ctx->launches += launch_boxes_to_lohi(ctx->stream, (const float*)ctx->bp4.ptr, n, S.lo, S.hi);
     { KernelTimer kt(ctx);
-      ctx->launches += launch_sap_variance(ctx->stream, S, n, d_sums, d_axis); }
+      ctx->launches += launch_sap_variance(ctx->stream, S, n, ctx->bp7.ptr, d_sums, d_axis); }
     if ((rc = check_launch(ctx, "sap_variance_chain_kernel"))) return rc;
+#ifdef B3_VAR_TRACE
+    { int h[6]; cudaMemcpyAsync(h, d_sums + 16, 24, cudaMemcpyDeviceToHost, ctx->stream); cudaStreamSynchronize(ctx->stream);
+      fprintf(stderr, "[variance trace] sequential tiles per chain: %d %d %d %d %d %d of %u\n", h[0], h[1], h[2], h[3], h[4], h[5], (n + 4095) / 4096);
+      cudaMemsetAsync(d_sums + 16, 0, 24, ctx->stream); }
+#endif
     CU_TRY(cudaMemcpyAsync(out_sums6, d_sums, 24, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(sums)");
     CU_TRY(cudaMemcpyAsync(out_axis, d_axis, 4, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(axis)");
     CU_TRY(cudaStreamSynchronize(ctx->stream), "bam3d_sap_variance");
