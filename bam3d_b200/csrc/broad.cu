@@ -854,8 +854,12 @@ __global__ void __launch_bounds__(BT) bvh_collider_pairs_kernel(BvhDev T, const 
 __global__ void __launch_bounds__(BT) bvh_overlap_append_kernel(BvhDev T, const float* __restrict__ aabbs, uint32_t v_begin, uint32_t v_end,
                                                                 int key_shift, unsigned long long* __restrict__ keys,
                                                                 unsigned long long capacity, unsigned long long* __restrict__ count) {
-    const uint32_t v = v_begin + blockIdx.x * BT + threadIdx.x;
-    if (v >= v_end) return;
+    // threads walk the values in the tree's leaf (Morton) order, so that the queries of a warp are neighbours in space
+    // and descend through the same nodes
+    const uint32_t slot = blockIdx.x * BT + threadIdx.x;
+    if (slot >= T.n) return;
+    const uint32_t v = __ldg(T.leaf_value + slot);
+    if (v < v_begin || v >= v_end) return;
     const float* b = aabbs + 6 * (size_t)v;
     Query q;
     q.qlo = make_float4(b[0], b[1], b[2], 0.f); q.qhi = make_float4(b[3], b[4], b[5], 0.f);
@@ -892,7 +896,7 @@ int launch_bvh_overlap_append(cudaStream_t st, const BvhDev& T, const float* d_a
                               unsigned long long* d_pair_keys, uint64_t capacity, unsigned long long* d_count) {
     cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), st);
     if (T.n == 0 || v_end <= v_begin) return 0;
-    bvh_overlap_append_kernel<<<(v_end - v_begin + BT - 1) / BT, BT, 0, st>>>(T, d_aabbs, v_begin, v_end, key_shift, d_pair_keys, capacity, d_count);
+    bvh_overlap_append_kernel<<<(T.n + BT - 1) / BT, BT, 0, st>>>(T, d_aabbs, v_begin, v_end, key_shift, d_pair_keys, capacity, d_count);
     return 1;
 }
 
