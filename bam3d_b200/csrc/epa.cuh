@@ -163,13 +163,16 @@ B3_DEV uint8_t epa_iterate(const Shape& L, const Shape& R, float tolerance, uint
     // Pass A needs dot(n, p - v0) > 0 with v0 = the face's first vertex (a divergent gather). face.distance is
     // fl(dot(n, v0)) (Face::new_impl), so a2 = fl(dot(n, p)) - distance equals the reference's value up to
     // 8.02 u S, S = sum |n_i| (|p_i| + |v0_i|), u = 2^-24 (standard dot-product error bounds). Whenever
-    // |a2| > 2^-20 S (S bounded with the running max |vertex coordinate|) the sign is decided without the gather;
+    // |a2| > 2^-20 S (S bounded with the running max |vertex coordinate| and |n_i| <= 1) the sign is decided without the gather;
     // otherwise — and for any NaN/inf — the reference's expression is evaluated as written. Exact either way.
     // The flags live in a bitmask (32 faces per word, built in a register chunk by chunk) so that pass A is a pure
     // load + arithmetic loop the compiler can software-pipeline, and pass B finds the next flagged face with ffs.
     uint32_t vm[EPA_FCAP / 32];
     ClosestFace cf;
     cf.reset();
+    // |n_i| <= 1 (+ an ulp) for a normalised face normal, so S <= sum_i (|p_i| + max|v_i|): one face-independent bound per
+    // iteration instead of six more operations per face (a NaN / inf normal makes a2 NaN and lands in the exact path)
+    const float sure_bound = ((fabsf(pv.x) + vmax.x) + (fabsf(pv.y) + vmax.y) + (fabsf(pv.z) + vmax.z)) * 9.5367431640625e-07f + 1e-30f;
     const int nchunks = (nf + 31) >> 5;
     for (int c = 0; c < nchunks; ++c) {
         uint32_t m = 0, unsure = 0;
@@ -185,8 +188,7 @@ B3_DEV uint8_t epa_iterate(const Shape& L, const Shape& R, float tolerance, uint
                 if (k < k1) {
                     const float4 f = fb[j];
                     float a2 = dot(v3(f.x, f.y, f.z), pv) - f.w;
-                    float S = (fabsf(f.x) * (fabsf(pv.x) + vmax.x) + fabsf(f.y) * (fabsf(pv.y) + vmax.y)) + fabsf(f.z) * (fabsf(pv.z) + vmax.z);
-                    const bool sure = fabsf(a2) > S * 9.5367431640625e-07f + 1e-30f;  // false for any NaN/inf too
+                    const bool sure = fabsf(a2) > sure_bound;  // false for any NaN/inf too
                     const bool vis = a2 > 0.f;
                     m |= ((sure && vis) ? 1u : 0u) << (k - k0);
                     unsure |= (sure ? 0u : 1u) << (k - k0);

@@ -892,7 +892,8 @@ static BinOrder epa_bin_order() {
     static bool ready = false;
     if (!ready) {
         // roundness: how much of the shape's surface is smooth
-        const int round[7] = {/*particle*/ 0, /*quad*/ 1, /*sphere*/ 10, /*cuboid*/ 2, /*cylinder*/ 7, /*capsule*/ 10, /*polyhedron*/ 0};
+        // (cylinder below sphere + cuboid: sphere-cuboid pairs hit the iteration cap ten times as often as cylinder-cylinder ones)
+        const int round[7] = {/*particle*/ 0, /*quad*/ 1, /*sphere*/ 10, /*cuboid*/ 2, /*cylinder*/ 5, /*capsule*/ 10, /*polyhedron*/ 0};
         int tier[EPAQ_BINS], score[EPAQ_BINS];
         int rim_boost = 150;  // measured on C2: 0 (after the curved bins) 8.4 ms, 150 (right after the ball bins) 7.8 ms, 250 (first) 9.3 ms
         if (const char* e = getenv("BAM3D_RIM_BOOST")) rim_boost = atoi(e);  // development knob
@@ -1005,7 +1006,9 @@ int launch_contact(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs, 
         ++launched;
     }
     if (strategy == 0) {
-        if (overlap) {
+        // a polling consumer must never be launched behind a producer that failed to launch: it would wait forever
+        const bool producer_ok = cudaPeekAtLastError() == cudaSuccess;
+        if (overlap && producer_ok) {
             // launched AFTER the producer (a tool that serialises kernels then still runs them in a terminating order)
             cudaStreamWaitEvent(side->stream, side->fork, 0);
             gjk_contact_overflow_kernel<<<OVF_WARPS, 32, EPA_BIG_SMEM_BYTES, side->stream>>>(S, d_pairs, cfg, ovf, 1, d_contacts, d_status);
