@@ -72,6 +72,8 @@ SIGNATURES = {
     "bam3d_shapes_world_aabbs_dev": (_i32, [_vp, _vp, _vp]),
     "bam3d_bvh_build": (_i32, [_vp, _vp, _u64, C.POINTER(_vp)]),
     "bam3d_bvh_build_dev": (_i32, [_vp, _vp, _u64, C.POINTER(_vp)]),
+    "bam3d_bvh_refit": (_i32, [_vp, _vp, _vp]),
+    "bam3d_bvh_refit_dev": (_i32, [_vp, _vp, _vp]),
     "bam3d_bvh_free": (None, [_vp, _vp]),
     "bam3d_bvh_count": (_u32, [_vp]),
     "bam3d_bvh_query_aabb": (_i32, [_vp, _vp, _vp, _u64, _vp, _vp, _u64, C.POINTER(_u64)]),

@@ -104,6 +104,14 @@ class Bvh:
         self.handle = h
         self.n = len(self.aabbs)
 
+    def refit(self, aabbs):
+        """New bounds for the same values, topology unchanged (update_node + do_refit for every value, dbvt/mod.rs:561-589)."""
+        aabbs = np.ascontiguousarray(aabbs, dtype=np.float32).reshape(-1, 6)
+        if len(aabbs) != self.n:
+            raise ValueError("refit needs one box per value of the tree")
+        self.ctx.check(self.ctx._lib.bam3d_bvh_refit(self.ctx.handle, self.handle, _ptr(aabbs)))
+        self.aabbs = aabbs
+
     def close(self):
         if self.handle:
             self.ctx._lib.bam3d_bvh_free(self.ctx.handle, self.handle)

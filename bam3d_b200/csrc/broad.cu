@@ -536,6 +536,32 @@ __global__ void __launch_bounds__(BT) bvh_refit_kernel(const float* __restrict__
     }
 }
 
+// Refit without rebuilding (the device counterpart of update_node + do_refit, dbvt/mod.rs:561-589): the topology stays,
+// leaf bounds are re-read from the new values and the internal bounds recomputed bottom-up. Query results depend only on
+// "every branch bound contains its descendants", which holds again afterwards; only the tree's quality degrades as the
+// values move away from the Morton order they were built in.
+__global__ void __launch_bounds__(BT) bvh_parents_kernel(const int2* __restrict__ children, uint32_t n, uint32_t* __restrict__ parent) {
+    uint32_t i = blockIdx.x * BT + threadIdx.x;
+    if (i + 1 >= n) return;
+    const int2 ch = children[i];
+    parent[ch.x] = i;
+    parent[ch.y] = i;
+    if (i == 0) parent[0] = 0xFFFFFFFFu;
+}
+
+int launch_bvh_refit(cudaStream_t st, const float* d_aabbs, uint32_t n, const int2* children, const uint32_t* leaf_value, uint32_t* parent,
+                     uint32_t* flags, float4* lo, float4* hi) {
+    if (n == 0) return 0;
+    int launched = 1;
+    if (n > 1) {
+        cudaMemsetAsync(flags, 0, (size_t)(n - 1) * 4, st);
+        bvh_parents_kernel<<<(n + BT - 1) / BT, BT, 0, st>>>(children, n, parent);
+        ++launched;
+    }
+    bvh_refit_kernel<<<(n + BT - 1) / BT, BT, 0, st>>>(d_aabbs, leaf_value, n, children, parent, flags, lo, hi);
+    return launched;
+}
+
 size_t bvh_cub_tmp_bytes(uint32_t n) {
     size_t a = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, a, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)n);

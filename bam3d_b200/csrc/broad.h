@@ -62,6 +62,10 @@ size_t bvh_cub_tmp_bytes(uint32_t n);
 int launch_bvh_build(cudaStream_t st, const float* d_aabbs, uint32_t n, const BvhBuildScratch& W, float4* lo, float4* hi, int2* children,
                      uint32_t* leaf_value);
 
+// bounds of an existing tree recomputed from new values (same topology); parent: 2n - 1 words, flags: n - 1 words of scratch
+int launch_bvh_refit(cudaStream_t st, const float* d_aabbs, uint32_t n, const int2* children, const uint32_t* leaf_value, uint32_t* parent,
+                     uint32_t* flags, float4* lo, float4* hi);
+
 enum BvhQueryKind { BQ_AABB = 0, BQ_RAY = 1, BQ_FRUSTUM = 2 };
 // pass 1 (d_offsets == nullptr): per-query hit counts into d_counts. pass 2: fill d_values / d_payload at d_offsets.
 //   BQ_AABB: queries nq x 6 f32, no payload;  BQ_RAY: nq x 6 f32 (origin, direction), payload 3 f32 (hit point) per hit;

@@ -808,6 +808,26 @@ static int32_t bvh_build_impl(bam3d_ctx* ctx, const float* aabbs, bool on_device
     return BAM3D_OK;
 }
 
+static int32_t bvh_refit_impl(bam3d_ctx* ctx, bam3d_bvh* t, const float* aabbs, bool on_device) {
+    if (!ctx || !t || (t->n && !aabbs)) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_bvh_refit: null argument", cudaSuccess);
+    CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
+    const uint32_t n = t->n;
+    if (n == 0) return BAM3D_OK;
+    int32_t rc;
+    const size_t nn = n;
+    if ((rc = ctx->bp1.reserve(ctx, (2 * nn) * 4 + nn * 4))) return rc;
+    uint32_t* parent = (uint32_t*)ctx->bp1.ptr;
+    uint32_t* flags = parent + 2 * nn;
+    CU_TRY(cudaMemcpyAsync(t->d_aabbs, aabbs, nn * 24, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpyAsync(aabbs)");
+    { KernelTimer kt(ctx);
+      ctx->launches += launch_bvh_refit(ctx->stream, t->d_aabbs, n, t->children, t->leaf_value, parent, flags, t->lo, t->hi); }
+    if ((rc = check_launch(ctx, "bvh_refit_kernel"))) return rc;
+    if (!on_device) CU_TRY(cudaStreamSynchronize(ctx->stream), "bam3d_bvh_refit");
+    return BAM3D_OK;
+}
+int32_t bam3d_bvh_refit(bam3d_ctx* ctx, bam3d_bvh* tree, const float* aabbs) { return bvh_refit_impl(ctx, tree, aabbs, false); }
+int32_t bam3d_bvh_refit_dev(bam3d_ctx* ctx, bam3d_bvh* tree, const float* d_aabbs) { return bvh_refit_impl(ctx, tree, d_aabbs, true); }
+
 int32_t bam3d_bvh_build(bam3d_ctx* ctx, const float* aabbs, uint64_t n, bam3d_bvh** out) {
     if (!ctx || !out || (n && !aabbs)) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_bvh_build: null argument", cudaSuccess);
     return bvh_build_impl(ctx, aabbs, false, n, out);

@@ -226,6 +226,12 @@ int32_t bam3d_shapes_world_aabbs_dev(bam3d_ctx* ctx, const bam3d_shapes* shapes,
  * order (deterministic for given boxes); compare with the reference as sets. */
 int32_t bam3d_bvh_build(bam3d_ctx* ctx, const float* aabbs, uint64_t n, bam3d_bvh** out);
 int32_t bam3d_bvh_build_dev(bam3d_ctx* ctx, const float* d_aabbs, uint64_t n, bam3d_bvh** out);
+/* New bounds for the values of an existing tree, topology unchanged: the device form of update_node + do_refit
+ * (dbvt/mod.rs:561-589) for every value at once. `aabbs` holds bam3d_bvh_count(tree) boxes in value order. Query results
+ * are those of a tree built over the new boxes (result sets do not depend on the tree's shape); rebuild when the values
+ * have moved far from where they were at build time. */
+int32_t bam3d_bvh_refit(bam3d_ctx* ctx, bam3d_bvh* tree, const float* aabbs);
+int32_t bam3d_bvh_refit_dev(bam3d_ctx* ctx, bam3d_bvh* tree, const float* d_aabbs);
 void bam3d_bvh_free(bam3d_ctx* ctx, bam3d_bvh* bvh);
 uint32_t bam3d_bvh_count(const bam3d_bvh* bvh);
 /* Variable-length results: hits of query q are out_values[out_offsets[q] .. out_offsets[q + 1]) (out_offsets has nq + 1

@@ -234,3 +234,36 @@ def test_kat_dbvt_frustum_and_ray(ctx, oracle):
         v, pts = t.query_ray(o, d)
         assert v.tolist() == [0] and pts[0].tolist() == p
         assert t.query_ray_closest(o, d)[0] == 0
+
+
+def test_bvh_refit_matches_a_tree_built_over_the_moved_boxes(ctx, oracle):
+    """update_node + do_refit for every value (dbvt/mod.rs:561-589) as one device refit: after the values move — most a
+    little, some across the whole scene — ray, frustum, AABB and dirty-pair queries return what the oracle's tree built over
+    the new boxes returns."""
+    boxes, L = scenes.aabb_scene(30_000)
+    bvh = broad.Bvh(ctx, boxes)
+    rng = np.random.default_rng(3)
+    moved = boxes.copy()
+    shift = rng.normal(0.0, 0.4, size=(len(boxes), 3)).astype(np.float32)
+    far = rng.random(len(boxes)) < 0.05
+    shift[far] = rng.uniform(-L, L, size=(int(far.sum()), 3)).astype(np.float32)
+    moved[:, 0:3] += shift
+    moved[:, 3:6] += shift
+    for step in range(2):  # two refits in a row: the second starts from an already stale topology
+        if step == 1:
+            moved[:, [0, 3]] += np.float32(1.5)
+        bvh.refit(moved)
+        ot = oracle.dbvt_build(moved)
+        rays = scenes.rays(200, L, seed=0xB3D0C410 + step)
+        off, vals, pts = bvh.query_ray(rays)
+        for q in range(len(rays)):
+            a, b = int(off[q]), int(off[q + 1])
+            ov, op = ot.query_ray(rays[q])
+            o = np.argsort(vals[a:b], kind="stable")
+            assert np.array_equal(vals[a:b][o], ov) and pts[a:b][o].tobytes() == op.tobytes()
+        qb = moved[rng.integers(0, len(moved), size=100)]
+        off, vals = bvh.query_aabb(qb)
+        for q in range(len(qb)):
+            assert np.array_equal(np.sort(vals[int(off[q]):int(off[q + 1])]), ot.query_aabb(qb[q]))
+        dirty = (rng.random(len(moved)) < 0.2).astype(np.uint8)
+        assert np.array_equal(bvh.find_collider_pairs(dirty), ot.find_collider_pairs(dirty))
