@@ -46,6 +46,7 @@ SIGNATURES = {
     "bam3d_host_alloc": (_i32, [_vp, _u64, C.POINTER(_vp)]),
     "bam3d_host_free": (None, [_vp, _vp]),
     "bam3d_meshes_upload": (_i32, [_vp, _vp, _vp, _u32, C.POINTER(_vp)]),
+    "bam3d_meshes_upload_faces": (_i32, [_vp, _vp, _vp, _u32, _vp, _vp, C.POINTER(_vp)]),
     "bam3d_meshes_free": (None, [_vp, _vp]),
     "bam3d_shapes_upload": (_i32, [_vp, _vp, _vp, _vp, _vp, _u32, _vp, C.POINTER(_vp)]),
     "bam3d_shapes_set_transforms": (_i32, [_vp, _vp, _vp]),

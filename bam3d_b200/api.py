@@ -147,11 +147,20 @@ class Capsule:  # primitive/capsule.rs:15-27 (Y-axis aligned)
         return (self.half_height, self.radius, 0.0, 0.0)
 
 
-class ConvexPolyhedron:  # primitive/polyhedron.rs:69-95 ConvexPolyhedron::new (VertexOnly mode)
+class ConvexPolyhedron:  # primitive/polyhedron.rs:69-115: new (VertexOnly mode) / new_with_faces (HalfEdge mode)
     kind = _ffi.KIND_POLYHEDRON
 
-    def __init__(self, vertices):
+    def __init__(self, vertices, faces=None):
         self.vertices = np.ascontiguousarray(vertices, dtype=np.float32).reshape(-1, 3)
+        self.faces = None if faces is None else np.ascontiguousarray(faces, dtype=np.uint32).reshape(-1, 3)
+
+    @classmethod
+    def new(cls, vertices):  # polyhedron.rs:69-95
+        return cls(vertices)
+
+    @classmethod
+    def new_with_faces(cls, vertices, faces):  # polyhedron.rs:98-115: hill-climbing support, ray casts
+        return cls(vertices, faces)
 
     def params(self):
         return (0.0, 0.0, 0.0, 0.0)
@@ -177,12 +186,21 @@ class Contact:  # contact.rs:22-38
 class MeshLibrary:
     """Vertex lists of ConvexPolyhedron values, resident on the device (bam3d_meshes)."""
 
-    def __init__(self, ctx, verts, offsets):
+    def __init__(self, ctx, verts, offsets, faces=None, face_offsets=None):
+        """faces / face_offsets (optional): triangles (vertex indices local to their mesh) of the meshes built with
+        ConvexPolyhedron::new_with_faces; mesh m owns faces face_offsets[m] .. face_offsets[m + 1] (none = VertexOnly)."""
         self.ctx = ctx
         self.verts = np.ascontiguousarray(verts, dtype=np.float32).reshape(-1, 3)
         self.offsets = np.ascontiguousarray(offsets, dtype=np.uint32)
         h = C.c_void_p()
-        ctx.check(ctx._lib.bam3d_meshes_upload(ctx.handle, _ptr(self.verts), _ptr(self.offsets), len(self.offsets) - 1, C.byref(h)))
+        if faces is None:
+            self.faces = self.face_offsets = None
+            ctx.check(ctx._lib.bam3d_meshes_upload(ctx.handle, _ptr(self.verts), _ptr(self.offsets), len(self.offsets) - 1, C.byref(h)))
+        else:
+            self.faces = np.ascontiguousarray(faces, dtype=np.uint32).reshape(-1, 3)
+            self.face_offsets = np.ascontiguousarray(face_offsets, dtype=np.uint32)
+            ctx.check(ctx._lib.bam3d_meshes_upload_faces(ctx.handle, _ptr(self.verts), _ptr(self.offsets), len(self.offsets) - 1,
+                                                         _ptr(self.faces), _ptr(self.face_offsets), C.byref(h)))
         self.handle = h
 
     def close(self):
@@ -217,14 +235,22 @@ class ShapeSet:
         polys = [p for p in primitives if p.kind == _ffi.KIND_POLYHEDRON]
         if polys:
             offs, verts, mesh_id = [0], [], np.zeros(len(primitives), dtype=np.uint32)
+            foffs, faces = [0], []
             m = 0
             for i, p in enumerate(primitives):
                 if p.kind == _ffi.KIND_POLYHEDRON:
                     verts.append(p.vertices)
                     offs.append(offs[-1] + len(p.vertices))
+                    if p.faces is not None:
+                        faces.append(p.faces)
+                    foffs.append(foffs[-1] + (len(p.faces) if p.faces is not None else 0))
                     mesh_id[i] = m
                     m += 1
-            meshes = MeshLibrary(ctx, np.concatenate(verts, axis=0), np.array(offs, dtype=np.uint32))
+            if faces:
+                meshes = MeshLibrary(ctx, np.concatenate(verts, axis=0), np.array(offs, dtype=np.uint32), np.concatenate(faces, axis=0),
+                                     np.array(foffs, dtype=np.uint32))
+            else:
+                meshes = MeshLibrary(ctx, np.concatenate(verts, axis=0), np.array(offs, dtype=np.uint32))
         return cls(ctx, kind, params, np.array(transforms, dtype=np.float32).reshape(-1, 16), mesh_id, meshes)
 
     def set_transforms(self, xform):

@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(BT) world_aabb_kernel(ShapeSetDev S, float* __
         case K_CAPSULE: mn = v3(-s.p1, -s.p0 - s.p1, -s.p1); mx = v3(s.p1, s.p0 + s.p1, s.p1); break;  // capsule.rs:51-58
         default: {  // polyhedron.rs:84-86: fold from Aabb3::zero() growing by every vertex
             uint32_t mid = meta >> 8;
-            uint32_t b = S.mesh_offsets[mid], e = S.mesh_offsets[mid + 1];
+            uint32_t b = S.mesh_offsets[mid] + MESH_HEADER_SLOTS, e = S.mesh_offsets[mid + 1];  // skip the mesh header slots
             for (uint32_t k = b; k < e; ++k) {
                 float4 p = S.mesh_verts[k];
                 mn = v3(rmin(mn.x, p.x), rmin(mn.y, p.y), rmin(mn.z, p.z));

@@ -5,12 +5,14 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <new>
 #include <string>
 #include <vector>
 
 #include "../../include/bam3d_gpu.h"
 #include "vecmath.cuh"
+#include "support.cuh"
 #include "narrow.h"
 #include "broad.h"
 #include "ctx.h"
@@ -213,30 +215,136 @@ void bam3d_host_free(bam3d_ctx* ctx, void* ptr) { (void)ctx; if (ptr) cudaFreeHo
 // ------------------------------------------------------------------------------------------------------------
 // meshes / shapes
 // ------------------------------------------------------------------------------------------------------------
+// build_half_edges (primitive/polyhedron.rs:246-340) for one mesh, in the reference's order: faces one by one, a pair of
+// twin half-edges created the first time either direction is seen, and first-writer-wins for vertex.edge, edge.left_face
+// and face.edge — hill_climb_support_point and the ray walk follow exactly these links. Indices are local to the mesh.
+struct HostHalfEdges {
+    std::vector<uint32_t> vert_edge;                       // per vertex
+    std::vector<uint32_t> target, twin, next, prev, left;  // per half-edge
+    std::vector<uint32_t> fv, fedge;                       // per face: 3 vertices, first edge
+};
+static bool build_half_edges_host(uint32_t nverts, const uint32_t* faces, uint32_t nfaces, HostHalfEdges& H) {
+    H.vert_edge.assign(nverts, 0);
+    std::vector<uint8_t> vert_ready(nverts, 0), edge_ready;
+    std::map<std::pair<uint32_t, uint32_t>, uint32_t> edge_map;
+    for (uint32_t f = 0; f < nfaces; ++f) {
+        const uint32_t v[3] = {faces[3 * f], faces[3 * f + 1], faces[3 * f + 2]};
+        if (v[0] >= nverts || v[1] >= nverts || v[2] >= nverts) return false;
+        uint32_t fe[3] = {0, 0, 0};
+        bool face_ready = false;
+        uint32_t first_edge = 0;
+        for (int j = 0; j < 3; ++j) {
+            const int i = (j == 0) ? 2 : j - 1;
+            const uint32_t v0 = v[i], v1 = v[j];
+            uint32_t e01, e10;
+            auto it = edge_map.find({v0, v1});
+            if (it != edge_map.end()) { e01 = it->second; e10 = H.twin[e01]; }
+            else {
+                e01 = (uint32_t)H.target.size(); e10 = e01 + 1;
+                H.target.push_back(v1); H.twin.push_back(e10); H.next.push_back(0); H.prev.push_back(0); H.left.push_back(0); edge_ready.push_back(0);
+                H.target.push_back(v0); H.twin.push_back(e01); H.next.push_back(0); H.prev.push_back(0); H.left.push_back(0); edge_ready.push_back(0);
+            }
+            edge_map[{v0, v1}] = e01;
+            edge_map[{v1, v0}] = e10;
+            if (!edge_ready[e01]) { H.left[e01] = f; edge_ready[e01] = 1; }
+            if (!vert_ready[v0]) { H.vert_edge[v0] = e01; vert_ready[v0] = 1; }
+            if (!face_ready) { first_edge = e01; face_ready = true; }
+            fe[i] = e01;
+        }
+        H.fv.push_back(v[0]); H.fv.push_back(v[1]); H.fv.push_back(v[2]); H.fedge.push_back(first_edge);
+        for (int j = 0; j < 3; ++j) {
+            const int i = (j == 0) ? 2 : j - 1;
+            H.next[fe[i]] = fe[j];
+            H.prev[fe[j]] = fe[i];
+        }
+    }
+    return true;
+}
+
 int32_t bam3d_meshes_upload(bam3d_ctx* ctx, const float* verts_xyz, const uint32_t* offsets, uint32_t n_meshes, bam3d_meshes** out) {
-    if (!ctx || !out || !offsets || (n_meshes && !verts_xyz)) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_meshes_upload: null argument", cudaSuccess);
+    return bam3d_meshes_upload_faces(ctx, verts_xyz, offsets, n_meshes, nullptr, nullptr, out);
+}
+
+int32_t bam3d_meshes_upload_faces(bam3d_ctx* ctx, const float* verts_xyz, const uint32_t* offsets, uint32_t n_meshes, const uint32_t* faces,
+                                  const uint32_t* face_offsets, bam3d_meshes** out) {
+    if (!ctx || !out || !offsets || (n_meshes && !verts_xyz) || ((faces == nullptr) != (face_offsets == nullptr)))
+        return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_meshes_upload: null argument", cudaSuccess);
     *out = nullptr;
     CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
     for (uint32_t m = 0; m < n_meshes; ++m)
-        if (offsets[m + 1] < offsets[m]) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_meshes_upload: offsets must be non-decreasing", cudaSuccess);
-    uint64_t nverts = offsets[n_meshes];
+        if (offsets[m + 1] < offsets[m] || (face_offsets && face_offsets[m + 1] < face_offsets[m]))
+            return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_meshes_upload: offsets must be non-decreasing", cudaSuccess);
+    const uint64_t nverts = offsets[n_meshes];
+    // host-side half-edge structures, concatenated over the meshes that have faces
+    std::vector<uint32_t> h_vert_edge(nverts ? nverts : 1, 0);
+    std::vector<uint4> h_edges, h_faces;
+    std::vector<uint64_t> edge_base(n_meshes + 1, 0), face_base(n_meshes + 1, 0);
+    for (uint32_t m = 0; m < n_meshes; ++m) {
+        edge_base[m] = h_edges.size() / 2; face_base[m] = h_faces.size() / 2;
+        const uint32_t nf = face_offsets ? face_offsets[m + 1] - face_offsets[m] : 0;
+        if (nf == 0) continue;
+        HostHalfEdges H;
+        const uint32_t nv = offsets[m + 1] - offsets[m];
+        if (!build_half_edges_host(nv, faces + 3 * (size_t)face_offsets[m], nf, H))
+            return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_meshes_upload_faces: face vertex index out of range", cudaSuccess);
+        for (uint32_t v = 0; v < nv; ++v) h_vert_edge[offsets[m] + v] = H.vert_edge[v];
+        for (size_t e = 0; e < H.target.size(); ++e) {
+            h_edges.push_back(make_uint4(H.target[e], H.twin[e], H.next[e], H.prev[e]));
+            h_edges.push_back(make_uint4(H.left[e], 0, 0, 0));
+        }
+        for (uint32_t f = 0; f < nf; ++f) {
+            h_faces.push_back(make_uint4(H.fv[3 * f], H.fv[3 * f + 1], H.fv[3 * f + 2], H.fedge[f]));
+            h_faces.push_back(make_uint4(offsets[m] + MESH_HEADER_SLOTS * (m + 1), 0, 0, 0));  // vertex slot base: replaced by the plane on the device
+        }
+    }
+    edge_base[n_meshes] = h_edges.size() / 2; face_base[n_meshes] = h_faces.size() / 2;
     bam3d_meshes* M = new (std::nothrow) bam3d_meshes();
     if (!M) return BAM3D_ERR_OOM;
-    M->n_meshes = n_meshes; M->nverts = nverts;
-    float* d_xyz = nullptr;
+    M->n_meshes = n_meshes; M->nverts = nverts; M->n_edges = edge_base[n_meshes]; M->n_faces = face_base[n_meshes];
+    const size_t slots = nverts + (size_t)MESH_HEADER_SLOTS * n_meshes;
     cudaError_t e;
-    if ((e = cudaMalloc(&M->verts, (nverts ? nverts : 1) * sizeof(float4))) != cudaSuccess ||
+    uint32_t* d_err = nullptr;
+    if ((e = cudaMalloc(&M->verts, (slots ? slots : 1) * sizeof(float4))) != cudaSuccess ||
         (e = cudaMalloc(&M->offsets, ((size_t)n_meshes + 1) * sizeof(uint32_t))) != cudaSuccess ||
-        (e = cudaMalloc(&d_xyz, (nverts ? nverts : 1) * 3 * sizeof(float))) != cudaSuccess) {
-        bam3d_meshes_free(ctx, M); if (d_xyz) cudaFree(d_xyz);
+        (e = cudaMalloc(&M->vert_edge, h_vert_edge.size() * sizeof(uint32_t))) != cudaSuccess ||
+        (e = cudaMalloc(&M->edges, (h_edges.size() ? h_edges.size() : 1) * sizeof(uint4))) != cudaSuccess ||
+        (e = cudaMalloc(&M->faces, (h_faces.size() ? h_faces.size() : 1) * sizeof(uint4))) != cudaSuccess ||
+        (e = cudaMalloc(&d_err, sizeof(uint32_t))) != cudaSuccess) {
+        bam3d_meshes_free(ctx, M); if (d_err) cudaFree(d_err);
         return b3_fail(ctx, BAM3D_ERR_OOM, "cudaMalloc(meshes)", e);
     }
-    cudaMemcpyAsync(M->offsets, offsets, ((size_t)n_meshes + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
-    if (nverts) cudaMemcpyAsync(d_xyz, verts_xyz, nverts * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
-    ctx->launches += launch_pack_meshes(ctx->stream, d_xyz, nverts, M->verts);
-    e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_xyz);
+    // vertex slots with a header in front of every mesh; device offsets count the header slots
+    std::vector<float4> h_verts(slots ? slots : 1, make_float4(0.f, 0.f, 0.f, 0.f));
+    std::vector<uint32_t> h_off(n_meshes + 1);
+    for (uint32_t m = 0; m <= n_meshes; ++m) h_off[m] = offsets[m] + MESH_HEADER_SLOTS * m;
+    for (uint32_t m = 0; m < n_meshes; ++m) {
+        MeshHeader hd;
+        hd.vert_edge = M->vert_edge + offsets[m];
+        hd.edges = M->edges + 2 * edge_base[m];
+        hd.faces = M->faces + 2 * face_base[m];
+        hd.n_faces = (uint32_t)(face_base[m + 1] - face_base[m]);
+        hd.n_edges = (uint32_t)(edge_base[m + 1] - edge_base[m]);
+        std::memcpy(&h_verts[h_off[m]], &hd, sizeof(hd));
+        for (uint32_t v = offsets[m]; v < offsets[m + 1]; ++v)
+            h_verts[h_off[m] + MESH_HEADER_SLOTS + (v - offsets[m])] = make_float4(verts_xyz[3 * (size_t)v], verts_xyz[3 * (size_t)v + 1], verts_xyz[3 * (size_t)v + 2], 0.f);
+    }
+    cudaMemcpyAsync(M->verts, h_verts.data(), h_verts.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(M->offsets, h_off.data(), h_off.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(M->vert_edge, h_vert_edge.data(), h_vert_edge.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (!h_edges.empty()) cudaMemcpyAsync(M->edges, h_edges.data(), h_edges.size() * sizeof(uint4), cudaMemcpyHostToDevice, ctx->stream);
+    if (!h_faces.empty()) cudaMemcpyAsync(M->faces, h_faces.data(), h_faces.size() * sizeof(uint4), cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemsetAsync(d_err, 0, sizeof(uint32_t), ctx->stream);
+    // face planes (Plane::from_points, plane.rs:69-86) on the device: same unfused f32 arithmetic as everything else
+    ctx->launches += launch_mesh_face_planes(ctx->stream, M->verts, M->faces, M->n_faces, d_err);
+    uint32_t h_err = 0;
+    cudaMemcpyAsync(&h_err, d_err, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
+    e = cudaStreamSynchronize(ctx->stream);  // also keeps the host vectors alive until the copies are done
+    cudaFree(d_err);
     if (e != cudaSuccess) { bam3d_meshes_free(ctx, M); return b3_fail(ctx, BAM3D_ERR_CUDA, "bam3d_meshes_upload", e); }
+    if (h_err) {
+        bam3d_meshes_free(ctx, M);
+        return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_meshes_upload_faces: degenerate face (the reference panics in Plane::from_points(..).unwrap())", cudaSuccess);
+    }
     *out = M;
     return BAM3D_OK;
 }
@@ -246,6 +354,9 @@ void bam3d_meshes_free(bam3d_ctx* ctx, bam3d_meshes* M) {
     if (!M) return;
     if (M->verts) cudaFree(M->verts);
     if (M->offsets) cudaFree(M->offsets);
+    if (M->vert_edge) cudaFree(M->vert_edge);
+    if (M->edges) cudaFree(M->edges);
+    if (M->faces) cudaFree(M->faces);
     delete M;
 }
 

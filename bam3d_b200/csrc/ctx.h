@@ -44,10 +44,15 @@ struct bam3d_ctx {
 };
 
 struct bam3d_meshes {
-    float4* verts = nullptr;      // xyz + unused w
-    uint32_t* offsets = nullptr;  // n_meshes + 1
+    float4* verts = nullptr;      // per mesh: MESH_HEADER_SLOTS header slots (support.cuh: MeshHeader), then xyz + unused w per vertex
+    uint32_t* offsets = nullptr;  // n_meshes + 1, in float4 slots of `verts` (headers included)
     uint32_t n_meshes = 0;
     uint64_t nverts = 0;
+    // half-edge structures of the meshes uploaded with faces (ConvexPolyhedron::new_with_faces); null when there are none
+    uint32_t* vert_edge = nullptr;
+    uint4* edges = nullptr;
+    uint4* faces = nullptr;
+    uint64_t n_edges = 0, n_faces = 0;
 };
 
 struct bam3d_shapes {

@@ -118,6 +118,11 @@ constexpr uint8_t EPA_CONTINUE = 0xFF;
 B3_DEV void prefetch_faces(const PolytopeStore& P, int nf) {
     const uint32_t act = __activemask();
     const int cnt = __popc(act);
+#ifdef B3_EPA_PREFETCH_MAX_LANES
+    // only when the warp is nearly empty (the kernel's tail: the queue has run dry and a few long pairs are left): then
+    // L1 is not under pressure and a trip's cost is its chain of dependent memory round trips
+    if (cnt > B3_EPA_PREFETCH_MAX_LANES) return;
+#endif
     const int rank = __popc(act & ((1u << (threadIdx.x & 31u)) - 1u));
     const int words = 4 * (int)__reduce_max_sync(act, (unsigned)nf);
     const float* base = reinterpret_cast<const float*>(P.fn);

@@ -103,9 +103,21 @@ __global__ void __launch_bounds__(TPB) pack_shapes_kernel(const uint8_t* __restr
     if (e) atomicOr(err, e);
 }
 
-__global__ void __launch_bounds__(TPB) pack_meshes_kernel(const float* __restrict__ xyz, uint64_t nverts, float4* __restrict__ out) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nverts) out[i] = make_float4(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], 0.f);
+// Face planes of the half-edge meshes: Plane::from_points (plane.rs:69-86) with n = normalize(cross(p2 - p1, p3 - p1)),
+// d = -p1.dot(n). On entry the second uint4 of a face holds the slot of its mesh's vertex 0 in `verts`.
+__global__ void __launch_bounds__(TPB) mesh_face_planes_kernel(const float4* __restrict__ verts, uint4* __restrict__ faces, uint64_t nfaces,
+                                                               uint32_t* __restrict__ err) {
+    uint64_t f = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nfaces) return;
+    const uint4 fv = faces[2 * f];
+    const uint32_t base = faces[2 * f + 1].x;
+    const float4 a = verts[base + fv.x], b = verts[base + fv.y], c = verts[base + fv.z];
+    const V3 p1 = v3(a.x, a.y, a.z);
+    const V3 normal = cross(v3(b.x, b.y, b.z) - p1, v3(c.x, c.y, c.z) - p1);
+    if (is_zero(normal)) { atomicOr(err, 1u); return; }
+    const V3 n = normalize(normal);
+    const float d = -dot(p1, n);
+    reinterpret_cast<float4*>(faces)[2 * f + 1] = make_float4(n.x, n.y, n.z, d);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -197,9 +209,11 @@ B3_DEV void load_pair_shape(Shape& s, const ShapeSetDev& S, uint32_t idx) {
     s.nverts = 0;
     if (s.kind == K_POLYHEDRON) {
         uint32_t mid = m >> 8;
+        // device offsets count the header slots in front of every mesh's vertices (support.cuh: MeshHeader)
         uint32_t b = __ldg(S.mesh_offsets + mid), e = __ldg(S.mesh_offsets + mid + 1);
-        s.verts = S.mesh_verts + b;
-        s.nverts = e - b;
+        s.verts = S.mesh_verts + b + MESH_HEADER_SLOTS;
+        s.nverts = e - b - MESH_HEADER_SLOTS;
+        if (mesh_header(s.verts)->n_faces) s.nverts |= MESH_HALF_EDGE;
     }
 }
 
@@ -810,9 +824,9 @@ int launch_pack_shapes(cudaStream_t st, const uint8_t* d_kind, const float* d_pa
     return 1;
 }
 
-int launch_pack_meshes(cudaStream_t st, const float* d_xyz, uint64_t nverts, float4* out) {
-    if (nverts == 0) return 0;
-    pack_meshes_kernel<<<(unsigned)((nverts + TPB - 1) / TPB), TPB, 0, st>>>(d_xyz, nverts, out);
+int launch_mesh_face_planes(cudaStream_t st, const float4* d_verts, uint4* d_faces, uint64_t nfaces, uint32_t* d_err) {
+    if (nfaces == 0) return 0;
+    mesh_face_planes_kernel<<<(unsigned)((nfaces + TPB - 1) / TPB), TPB, 0, st>>>(d_verts, d_faces, nfaces, d_err);
     return 1;
 }
 

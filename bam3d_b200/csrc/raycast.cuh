@@ -6,8 +6,11 @@
 //   (particle.rs:53-69), cylinder_ray_quadratic_solve (primitive/util.rs:95-109), Primitive3's dispatch
 //   (primitive3.rs:133-166) and the swept particle (Particle, Range<Vec3>) (particle.rs:39-128).
 // Every expression is evaluated in the reference's (glam 0.8 scalar) order, unfused: results are bit-identical.
-// ConvexPolyhedron's ray walk (polyhedron.rs:373-522) needs half-edge face lists and is reported as unsupported.
+// ConvexPolyhedron (polyhedron.rs:373-522): the face walk over the half-edge structure, for meshes uploaded with faces
+// (up to POLY_RAY_MAX_FACES of them); a VertexOnly polyhedron has no faces to walk (the reference indexes an empty list and
+// panics) and is reported as unsupported.
 #pragma once
+#include "simplex.cuh"
 #include "support.cuh"
 
 namespace b3 {
@@ -109,6 +112,72 @@ B3_DEV float cylinder_cap_t(const RayD& r, float h0, float sy) {
     return -(h0 + dot(r.o, n)) / dot(r.d, n);
 }
 
+constexpr int POLY_RAY_MAX_FACES = 4096;  // `checked` BitSet of the walk: 128 words of local memory per thread
+
+// barycentric_point (primitive/util.rs:63-79): the same expressions as barycentric_vector (simplex.cuh)
+// find_intersecting_face (polyhedron.rs:401-425) + intersect_ray_face (:497-521) + next_face_classify (:433-494).
+// Returns the face index or -1; (u, v, w) = barycentric coordinates of the hit.
+B3_DEV int poly_find_intersecting_face(const Shape& s, const RayD& ray, float& u, float& v, float& w) {
+    const MeshHeader* h = mesh_header(s.verts);
+    const uint32_t nfaces = h->n_faces;
+    const uint4* __restrict__ faces = h->faces;
+    const uint4* __restrict__ edges = h->edges;
+    uint32_t checked[POLY_RAY_MAX_FACES / 32];
+    for (uint32_t i = 0; i < (nfaces + 31) / 32; ++i) checked[i] = 0u;
+    int face = 0;
+    while (face >= 0) {
+        const uint32_t fi = (uint32_t)face;
+        checked[fi >> 5] |= 1u << (fi & 31);
+        const uint4 fv = __ldg(faces + 2 * fi);
+        const float4 pl = __ldg(reinterpret_cast<const float4*>(faces + 2 * fi + 1));
+        const V3 n = v3(pl.x, pl.y, pl.z);
+        bool have = false;
+        if (dot(n, ray.d) < 0.f) {
+            const float t = -(pl.w + dot(ray.o, n)) / dot(ray.d, n);  // Continuous<Ray> for Plane (plane.rs:117-129)
+            if (!(t < 0.f)) {
+                const V3 p = ray.o + ray.d * t;
+                const float4 a = __ldg(s.verts + fv.x), b = __ldg(s.verts + fv.y), c = __ldg(s.verts + fv.z);
+                barycentric_vector(p, v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), v3(c.x, c.y, c.z), u, v, w);
+                have = true;
+                if (u >= 0.f && u <= 1.f && v >= 0.f && v <= 1.f && w >= 0.f && w <= 1.f) return face;
+            }
+        }
+        int next = -1;
+        if (nfaces < 10) {
+            next = (fi == nfaces - 1) ? -1 : (int)fi + 1;
+        } else if (!have) {
+            uint32_t nx = fi + 1;
+            while (nx < nfaces && ((checked[nx >> 5] >> (nx & 31)) & 1u)) ++nx;
+            next = (nx == nfaces) ? -1 : (int)nx;
+        } else {
+            const uint32_t target = (u < 0.f) ? fv.z : ((v < 0.f) ? fv.x : fv.y);
+            const uint4 fe = __ldg(edges + 2 * fv.w);  // (target_vertex, twin, next, previous)
+            uint32_t e3[3];
+            if (fe.x == target) { e3[0] = fv.w; e3[1] = fe.z; e3[2] = fe.w; }
+            else if (__ldg(edges + 2 * fe.w).x == target) { e3[0] = fe.w; e3[1] = fv.w; e3[2] = fe.z; }
+            else { e3[0] = fe.z; e3[1] = fe.w; e3[2] = fv.w; }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                if (next < 0) {
+                    const uint32_t twin = __ldg(edges + 2 * e3[k]).y;
+                    const uint32_t lf = __ldg(edges + 2 * twin + 1).x;
+                    if (!((checked[lf >> 5] >> (lf & 31)) & 1u)) next = (int)lf;
+                }
+            }
+            if (next < 0) {
+                for (uint32_t i = 0; i < (nfaces + 31) / 32 && next < 0; ++i) {
+                    uint32_t freebits = ~checked[i];
+                    if (i == nfaces / 32 && (nfaces & 31)) freebits &= (1u << (nfaces & 31)) - 1u;
+                    if (i * 32 >= nfaces) freebits = 0u;
+                    if (freebits) next = (int)(i * 32 + __ffs(freebits) - 1);
+                }
+            }
+        }
+        face = next;
+    }
+    return -1;
+}
+
 // Discrete<Ray> in object space
 B3_DEV bool ray_intersects_local(const Shape& s, const RayD& r) {
     V3 unused;
@@ -156,6 +225,10 @@ B3_DEV bool ray_intersects_local(const Shape& s, const RayD& r) {
             const V3 pc = r.o + r.d * t;
             if (pc.y <= hh && pc.y >= -hh) return true;
             return capsule_cap_discrete(r, hh, radius) || capsule_cap_discrete(r, -hh, radius);
+        }
+        case K_POLYHEDRON: {  // polyhedron.rs:373-378
+            float u, v, w;
+            return poly_find_intersecting_face(s, r, u, v, w) >= 0;
         }
         default: return false;
     }
@@ -223,6 +296,15 @@ B3_DEV bool ray_intersection_local(const Shape& s, const RayD& r, V3& out) {
             out = pc;
             return true;
         }
+        case K_POLYHEDRON: {  // polyhedron.rs:380-394
+            float u, v, w;
+            const int fi = poly_find_intersecting_face(s, r, u, v, w);
+            if (fi < 0) return false;
+            const uint4 fv = __ldg(mesh_header(s.verts)->faces + 2 * fi);
+            const float4 a = __ldg(s.verts + fv.x), b = __ldg(s.verts + fv.y), c = __ldg(s.verts + fv.z);
+            out = (v3(a.x, a.y, a.z) * u) + (v3(b.x, b.y, b.z) * v) + (v3(c.x, c.y, c.z) * w);
+            return true;
+        }
         default: return false;
     }
 }
@@ -230,7 +312,10 @@ B3_DEV bool ray_intersection_local(const Shape& s, const RayD& r, V3& out) {
 // query: 0 = intersects_transformed, 1 = intersection_transformed, 2 = swept particle (a = start, b = end)
 B3_DEV uint8_t ray_cast_one(const Shape& s, V3 a, V3 b, int query, V3& out) {
     out = v3(0.f, 0.f, 0.f);
-    if (s.kind == K_POLYHEDRON) return ST_UNSUPPORTED;
+    if (s.kind == K_POLYHEDRON) {
+        const uint32_t nfaces = (s.nverts & MESH_HALF_EDGE) ? mesh_header(s.verts)->n_faces : 0u;
+        if (nfaces == 0 || nfaces > (uint32_t)POLY_RAY_MAX_FACES) return ST_UNSUPPORTED;
+    }
     RayD world;
     V3 travel = v3(0.f, 0.f, 0.f);
     if (query == 2) { travel = b - a; world.o = a; world.d = normalize(travel); }

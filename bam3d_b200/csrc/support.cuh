@@ -110,6 +110,48 @@ B3_DEV V3 polyhedron_local_support(const float4* __restrict__ verts, uint32_t n,
     return v3(p.x, p.y, p.z);
 }
 
+// ConvexPolyhedron::new_with_faces (HalfEdge mode). The two float4 slots in front of a mesh's vertices hold this header
+// (written by the host layer, capi.cu); n_faces = 0 for a VertexOnly mesh. Shape::nverts carries MESH_HALF_EDGE then.
+constexpr uint32_t MESH_HALF_EDGE = 0x80000000u;
+constexpr int MESH_HEADER_SLOTS = 2;
+struct MeshHeader {
+    const uint32_t* vert_edge;  // per vertex: an outgoing half-edge
+    const uint4* edges;         // 2 x uint4 per half-edge: (target_vertex, twin_edge, next_edge, previous_edge), (left_face, 0, 0, 0)
+    const uint4* faces;         // 2 x 16 B per face: (v0, v1, v2, edge), then the plane (n.xyz, d) as float4
+    uint32_t n_faces, n_edges;
+};
+static_assert(sizeof(MeshHeader) == MESH_HEADER_SLOTS * 16, "mesh header must fill its float4 slots");
+B3_DEV const MeshHeader* mesh_header(const float4* verts) { return reinterpret_cast<const MeshHeader*>(verts - MESH_HEADER_SLOTS); }
+
+// hill_climb_support_point (polyhedron.rs:153-183): from vertex 0, walk the ring of neighbours of the best vertex, move
+// to the best of them, stop when a pass improves the dot product by less than f32::EPSILON. Serial by nature (in the warp
+// kernels every lane runs it on identical data). The caps only bound malformed input the reference would hang on (a ring
+// that does not close, NaN directions).
+B3_DEV V3 polyhedron_hill_climb(const float4* __restrict__ verts, uint32_t nverts, V3 d) {
+    const MeshHeader* h = mesh_header(verts);
+    const uint32_t* __restrict__ ve = h->vert_edge;
+    const uint4* __restrict__ ed = h->edges;
+    uint32_t best = 0;
+    float4 p = __ldg(verts);
+    float best_dot = dot(v3(p.x, p.y, p.z), d);
+    for (uint32_t pass = 0; pass <= nverts; ++pass) {
+        const float previous = best_dot;
+        uint32_t e = __ldg(ve + best);
+        const uint32_t start = e;
+        for (uint32_t step = 0; step <= h->n_edges; ++step) {
+            const uint4 E = __ldg(ed + 2 * e);
+            const float4 q = __ldg(verts + E.x);
+            const float t = dot(v3(q.x, q.y, q.z), d);
+            if (t > best_dot) { best = E.x; best_dot = t; }
+            e = __ldg(ed + 2 * E.y).z;
+            if (e == start) break;
+        }
+        if (fabsf(best_dot - previous) < F32_EPSILON) break;
+    }
+    p = __ldg(verts + best);
+    return v3(p.x, p.y, p.z);
+}
+
 // World-space support point of shape `s` along world direction `dir`.
 template <bool WARP>
 B3_DEV V3 support_point(const Shape& s, V3 dir) {
@@ -152,7 +194,8 @@ B3_DEV V3 support_point(const Shape& s, V3 dir) {
             break;
         }
         default:  // K_POLYHEDRON, polyhedron.rs:342-355
-            p = polyhedron_local_support<WARP>(s.verts, s.nverts, d);
+            if (s.nverts & MESH_HALF_EDGE) p = polyhedron_hill_climb(s.verts, s.nverts & ~MESH_HALF_EDGE, d);
+            else p = polyhedron_local_support<WARP>(s.verts, s.nverts, d);
             break;
     }
     return transform_point3(s, p);

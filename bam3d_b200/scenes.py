@@ -259,3 +259,21 @@ def primitive_rays(scene, n_rays, seed=0xB3D000F1, start=0):
     segments = np.concatenate([origin, (origin + d * reach).astype(np.float32)], axis=1).astype(np.float32)
     casts = np.stack([np.arange(n_rays, dtype=np.uint32), shape], axis=1)
     return rays, segments, casts
+
+
+def mesh_faces(verts, offsets):
+    """Triangulated convex hulls of the meshes of a library (scipy), counter-clockwise seen from outside, as
+    (faces[total, 3] with vertex indices local to each mesh, face_offsets[n_meshes + 1]) — what
+    ConvexPolyhedron::new_with_faces takes. Every vertex of a mesh_library() mesh lies on its hull."""
+    from scipy.spatial import ConvexHull
+    faces, foffs = [], [0]
+    for m in range(len(offsets) - 1):
+        v = np.asarray(verts[offsets[m]:offsets[m + 1]], dtype=np.float64)
+        hull = ConvexHull(v)
+        tri = hull.simplices.astype(np.int64).copy()
+        n = np.cross(v[tri[:, 1]] - v[tri[:, 0]], v[tri[:, 2]] - v[tri[:, 0]])
+        flip = np.einsum("ij,ij->i", n, hull.equations[:, :3]) < 0
+        tri[flip] = tri[flip][:, [0, 2, 1]]
+        faces.append(tri.astype(np.uint32))
+        foffs.append(foffs[-1] + len(tri))
+    return np.concatenate(faces, axis=0), np.array(foffs, dtype=np.uint32)

@@ -48,7 +48,7 @@ extern "C" {
 #define BAM3D_STATUS_REF_PANIC 3  /* the reference would panic here (simplex3d.rs:134 unwrap, :138 assert!) */
 #define BAM3D_STATUS_NAN 4        /* None through a NaN comparison                                      */
 #define BAM3D_STATUS_CAPACITY 5   /* EPA polytope outgrew the device capacities (never seen on valid input) */
-#define BAM3D_STATUS_UNSUPPORTED 6 /* ray cast against a ConvexPolyhedron (needs half-edge faces): not computed    */
+#define BAM3D_STATUS_UNSUPPORTED 6 /* ray cast against a ConvexPolyhedron uploaded without faces (or > 4096 faces)   */
 
 /* CollisionStrategy (contact.rs:12-18) */
 #define BAM3D_FULL_RESOLUTION 0
@@ -112,6 +112,14 @@ void bam3d_host_free(bam3d_ctx* ctx, void* ptr);
  * offsets[n_meshes] vertices (3 f32 each); mesh m owns vertices offsets[m] .. offsets[m+1]. */
 int32_t bam3d_meshes_upload(bam3d_ctx* ctx, const float* verts_xyz, const uint32_t* offsets, uint32_t n_meshes,
                             bam3d_meshes** out);
+/* ConvexPolyhedron::new_with_faces (primitive/polyhedron.rs:98-115, build_half_edges :246-340): the same library, where
+ * mesh m additionally has the triangles faces[3 * face_offsets[m]] .. faces[3 * face_offsets[m + 1]) (vertex indices local
+ * to the mesh, counter-clockwise seen from outside). A mesh with faces is in HalfEdge mode: its support point is the
+ * reference's hill climb over the half-edge structure (:153-183) and ray casts walk its faces (:373-522); a mesh without
+ * faces stays VertexOnly (brute-force support, no ray casts). A degenerate face (the reference panics) or an index out of
+ * range fails the call with BAM3D_ERR_ARG. */
+int32_t bam3d_meshes_upload_faces(bam3d_ctx* ctx, const float* verts_xyz, const uint32_t* offsets, uint32_t n_meshes,
+                                  const uint32_t* faces, const uint32_t* face_offsets, bam3d_meshes** out);
 void bam3d_meshes_free(bam3d_ctx* ctx, bam3d_meshes* meshes);
 
 /* Primitive3 values and their model-to-world Mat4 (primitive/primitive3.rs, traits.rs:78-100). kind[n],
@@ -169,7 +177,7 @@ int32_t bam3d_gjk_time_of_impact_dev(bam3d_ctx* ctx, const bam3d_shapes* shapes_
  * query 0 = intersects_transformed (bool), 1 = intersection_transformed (Option<Vec3>), 2 = swept particle (both the
  * Discrete and the Continuous form: the hit, kept only within the travelled distance).
  * out_status: BAM3D_STATUS_OK = true / Some, BAM3D_STATUS_MISS = false / None, BAM3D_STATUS_UNSUPPORTED for a
- * ConvexPolyhedron; out_points: n x 3 f32 world-space hit points (zero when there is none, and for query 0). */
+ * ConvexPolyhedron without faces (VertexOnly: the reference's walk panics on it) or with more than 4096; out_points: n x 3 f32 world-space hit points (zero when there is none, and for query 0). */
 int32_t bam3d_ray_cast(bam3d_ctx* ctx, const bam3d_shapes* shapes, const float* rays, uint64_t n_rays, const uint32_t* casts,
                        uint64_t n, int32_t query, float* out_points, uint8_t* out_status);
 int32_t bam3d_ray_cast_dev(bam3d_ctx* ctx, const bam3d_shapes* shapes, const float* d_rays, uint64_t n_rays,

@@ -13,6 +13,7 @@
 #pragma once
 #include <cstdint>
 #include <utility>
+#include <map>
 #include <vector>
 #include "glam_mini.hpp"
 
@@ -24,6 +25,64 @@ namespace orc {
 // ---------------------------------------------------------------------------------------------------------
 enum Kind : uint8_t { PARTICLE = 0, QUAD = 1, SPHERE = 2, CUBOID = 3, CYLINDER = 4, CAPSULE = 5, POLYHEDRON = 6 };
 
+// ConvexPolyhedron::new_with_faces: the half-edge structure of build_half_edges (primitive/polyhedron.rs:246-340), built
+// in the same order (face by face, edge pairs created on first sight, first-writer-wins for vertex.edge / edge.left_face /
+// face.edge) because hill_climb_support_point and the ray walk depend on those links.
+struct HalfEdgeMesh {
+    struct Edge { uint32_t target_vertex, left_face, next_edge, previous_edge, twin_edge; bool ready; };
+    struct Face { uint32_t edge; uint32_t v[3]; Vec3 n; float d; bool ready; };
+    std::vector<uint32_t> vertex_edge;
+    std::vector<Edge> edges;
+    std::vector<Face> faces;
+    // false if a face is degenerate (Plane::from_points(..).unwrap() would panic, polyhedron.rs:270-274)
+    bool build(const float* verts, uint32_t nverts, const uint32_t* in_faces, uint32_t nfaces) {
+        vertex_edge.assign(nverts, 0);
+        std::vector<bool> vertex_ready(nverts, false);
+        edges.clear(); faces.clear();
+        std::map<std::pair<uint32_t, uint32_t>, uint32_t> edge_map;
+        auto pos = [&](uint32_t i) { return Vec3(verts[3 * i], verts[3 * i + 1], verts[3 * i + 2]); };
+        for (uint32_t f = 0; f < nfaces; ++f) {
+            const uint32_t fv[3] = {in_faces[3 * f], in_faces[3 * f + 1], in_faces[3 * f + 2]};
+            if (fv[0] >= nverts || fv[1] >= nverts || fv[2] >= nverts) return false;
+            Face face; face.edge = 0; face.v[0] = fv[0]; face.v[1] = fv[1]; face.v[2] = fv[2]; face.ready = false;
+            {   // Plane::from_points (plane.rs:69-86)
+                Vec3 p1 = pos(fv[0]), v0 = pos(fv[1]) - p1, v1 = pos(fv[2]) - p1;
+                Vec3 normal = cross(v0, v1);
+                if (all_eq(normal, Vec3::zero())) return false;
+                face.n = normalize(normal);
+                face.d = -dot(p1, face.n);
+            }
+            const uint32_t face_index = (uint32_t)faces.size();
+            uint32_t face_edge_indices[3] = {0, 0, 0};
+            for (int j = 0; j < 3; ++j) {
+                const int i = (j == 0) ? 2 : j - 1;
+                const uint32_t v0 = fv[i], v1 = fv[j];
+                uint32_t e01, e10;
+                auto it = edge_map.find({v0, v1});
+                if (it != edge_map.end()) { e01 = it->second; e10 = edges[e01].twin_edge; }
+                else {
+                    e01 = (uint32_t)edges.size(); e10 = e01 + 1;
+                    edges.push_back(Edge{v1, 0, 0, 0, e10, false});
+                    edges.push_back(Edge{v0, 0, 0, 0, e01, false});
+                }
+                edge_map[{v0, v1}] = e01;
+                edge_map[{v1, v0}] = e10;
+                if (!edges[e01].ready) { edges[e01].left_face = face_index; edges[e01].ready = true; }
+                if (!vertex_ready[v0]) { vertex_edge[v0] = e01; vertex_ready[v0] = true; }
+                if (!face.ready) { face.edge = e01; face.ready = true; }
+                face_edge_indices[i] = e01;
+            }
+            faces.push_back(face);
+            for (int j = 0; j < 3; ++j) {
+                const int i = (j == 0) ? 2 : j - 1;
+                edges[face_edge_indices[i]].next_edge = face_edge_indices[j];
+                edges[face_edge_indices[j]].previous_edge = face_edge_indices[i];
+            }
+        }
+        return true;
+    }
+};
+
 struct Shape {
     uint8_t kind = PARTICLE;
     // SPHERE: p0 = radius. CUBOID: (p0,p1,p2) = half_dim. QUAD: (p0,p1) = half_dim.
@@ -31,6 +90,7 @@ struct Shape {
     float p0 = 0.f, p1 = 0.f, p2 = 0.f;
     const float* verts = nullptr;  // POLYHEDRON: nverts x 3 floats (ConvexPolyhedron::new = VertexOnly mode)
     uint32_t nverts = 0;
+    const HalfEdgeMesh* he = nullptr;  // POLYHEDRON built with new_with_faces (HalfEdge mode), else null
 
     static Shape sphere(float r) { Shape s; s.kind = SPHERE; s.p0 = r; return s; }
     // Cuboid::new(dim) -> half_dim = dim / 2 (cuboid.rs:27-34)
@@ -108,8 +168,27 @@ inline Vec3 support_point(const Shape& s, Vec3 direction, const Mat4& transform)
             result.y = rsignum(d.y) * s.p0;
             return transform.transform_point3(result + d * (s.p1 / std::sqrt(dot(d, d))));
         }
-        case POLYHEDRON: {  // polyhedron.rs:135-150 (VertexOnly) + :342-355
+        case POLYHEDRON: {  // polyhedron.rs:135-150 (VertexOnly) / :153-183 (HalfEdge) + :342-355
             Vec3 d = transform.inverse().transform_vector3(direction);
+            if (s.he) {  // hill_climb_support_point
+                auto pos = [&](uint32_t i) { return Vec3(s.verts[3 * i], s.verts[3 * i + 1], s.verts[3 * i + 2]); };
+                uint32_t best_index = 0;
+                float best_dot = dot(pos(best_index), d);
+                for (;;) {
+                    const float previous_best_dot = best_dot;
+                    uint32_t edge_index = s.he->vertex_edge[best_index];
+                    const uint32_t start_edge_index = edge_index;
+                    for (;;) {
+                        const uint32_t vertex_index = s.he->edges[edge_index].target_vertex;
+                        const float dt = dot(pos(vertex_index), d);
+                        if (dt > best_dot) { best_index = vertex_index; best_dot = dt; }
+                        edge_index = s.he->edges[s.he->edges[edge_index].twin_edge].next_edge;
+                        if (start_edge_index == edge_index) break;
+                    }
+                    if (std::fabs(best_dot - previous_best_dot) < F32_EPSILON) break;
+                }
+                return transform.transform_point3(pos(best_index));
+            }
             Vec3 max_p = Vec3::zero();
             float max_dot = -std::numeric_limits<float>::infinity();
             for (uint32_t i = 0; i < s.nverts; ++i) {

@@ -387,6 +387,35 @@ static void ray_tests() {
         CHECK(ray_intersection_local(cap, Ray(Vec3(0, 4, 0), normalize(Vec3(0.1f, -1.f, 0.1f))), p)); CHECK_V3(0.10102587f, 2.9897413f, 0.10102587f, p);
         CHECK(!ray_intersection_local(cap, Ray(Vec3(0, 3, 0), normalize(Vec3(0.1f, 1.f, 0.1f))), p));
         CHECK(ray_intersection_local(cap, Ray(Vec3(0, 4, 0), normalize(Vec3(0.f, -1.f, 0.f))), p)); CHECK_V3(0.f, 3.f, 0.f, p); }
+    {   // polyhedron.rs tests: the unit tetrahedron built with new_with_faces
+        const float verts[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};
+        const uint32_t faces[12] = {1, 3, 2, 3, 1, 0, 2, 0, 1, 0, 2, 3};
+        HalfEdgeMesh he; CHECK(he.build(verts, 4, faces, 4));
+        Shape hp = Shape::polyhedron(verts, 4); hp.he = &he;
+        Shape vp = Shape::polyhedron(verts, 4);
+        TEST("polyhedron.rs:533 test_polytope_half_edge");
+        CHECK_V3(1.f, 0.f, 0.f, support_point(vp, Vec3(1, 0, 0), I)); CHECK_V3(1.f, 0.f, 0.f, support_point(hp, Vec3(1, 0, 0), I));
+        CHECK_V3(0.f, 1.f, 0.f, support_point(vp, Vec3(0, 1, 0), I)); CHECK_V3(0.f, 1.f, 0.f, support_point(hp, Vec3(0, 1, 0), I));
+        const Ray down(Vec3(0.25f, 5.f, 0.25f), Vec3(0, -1, 0)), up(Vec3(0.5f, 5.f, 0.5f), Vec3(0, 1, 0));
+        TEST("polyhedron.rs:590 test_ray_discrete / :606 test_ray_discrete_transformed");
+        CHECK(ray_intersects_local(hp, down)); CHECK(!ray_intersects_local(hp, up));
+        CHECK(ray_intersects_transformed(hp, down, I)); CHECK(!ray_intersects_transformed(hp, up, I));
+        CHECK(ray_intersects_transformed(hp, down, transform_z(0, 1, 0, 0))); CHECK(ray_intersects_transformed(hp, down, transform_z(0, 0, 0, 0.3f)));
+        TEST("polyhedron.rs:629 test_ray_continuous");
+        CHECK(ray_intersection_local(hp, down, p));
+        CHECK(std::fabs(p.x - 0.25000018f) < F32_EPSILON); CHECK(std::fabs(p.y - 0.4999997f) < F32_EPSILON); CHECK(std::fabs(p.z - 0.25000018f) < F32_EPSILON);
+        CHECK(!ray_intersection_local(hp, up, p));
+        CHECK(ray_intersection_local(hp, Ray(Vec3(0, 5, 0), Vec3(0, -1, 0)), p)); CHECK_V3(0.f, 1.f, 0.f, p);
+        TEST("polyhedron.rs:651 test_ray_continuous_transformed");
+        CHECK(ray_intersection_transformed(hp, down, I, p));
+        CHECK(std::fabs(p.x - 0.25000018f) < F32_EPSILON); CHECK(std::fabs(p.y - 0.4999997f) < F32_EPSILON); CHECK(std::fabs(p.z - 0.25000018f) < F32_EPSILON);
+        CHECK(!ray_intersection_transformed(hp, up, I, p));
+        CHECK(ray_intersection_transformed(hp, down, transform_z(0, 1, 0, 0), p));
+        CHECK(std::fabs(p.x - 0.25000018f) < F32_EPSILON); CHECK(std::fabs(p.y - 1.4999998f) < F32_EPSILON); CHECK(std::fabs(p.z - 0.25000018f) < F32_EPSILON);
+        CHECK(ray_intersection_transformed(hp, down, transform_z(0, 0, 0, 0.3f), p));
+        CHECK(std::fabs(p.x - 0.2500002f) < F32_EPSILON); CHECK(std::fabs(p.y - 0.4987077f) < F32_EPSILON); CHECK(std::fabs(p.z - 0.25000012f) < F32_EPSILON);
+        TEST("polyhedron.rs:683 test_intersect_face (must not panic)");
+        ray_intersection_local(hp, Ray(Vec3(1, -1, 1), Vec3(0, 1, 0)), p); CHECK(true); }
     {   TEST("tests/point.rs:19 test_ray_intersect");
         Vec3 point(1.f, 2.f, 3.f);
         CHECK(point_ray_intersects(point, Ray(Vec3(1, 2, 0), Vec3(0, 0, 1))));

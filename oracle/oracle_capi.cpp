@@ -14,6 +14,10 @@ using namespace orc;
 
 namespace {
 
+// Half-edge structures of the mesh library's polyhedra that were built with faces (orc_set_mesh_faces); mesh m is in
+// HalfEdge mode iff g_half_edges[m] has faces. Process-wide, set by the tests before the batch calls that use it.
+std::vector<HalfEdgeMesh> g_half_edges;
+
 struct ShapeTable {
     const uint8_t* kind; const float* params; const float* xform; const uint32_t* mesh_id;
     const float* mesh_verts; const uint32_t* mesh_offsets;
@@ -23,6 +27,7 @@ struct ShapeTable {
             uint32_t m = mesh_id[i];
             s.verts = mesh_verts + 3 * (size_t)mesh_offsets[m];
             s.nverts = mesh_offsets[m + 1] - mesh_offsets[m];
+            if (m < g_half_edges.size() && !g_half_edges[m].faces.empty()) s.he = &g_half_edges[m];
         }
         return s;
     }
@@ -211,23 +216,42 @@ void orc_gjk_complex_batch(const uint8_t* kind, const float* params, const float
 }
 
 // ---- single-call helpers used by the parity / golden tests -------------------------------------------------
+// ConvexPolyhedron::new_with_faces for the meshes of a library: faces = (a, b, c) vertex indices local to the mesh,
+// face_offsets[m] .. face_offsets[m + 1] the faces of mesh m (none = VertexOnly). Returns 0, or 1 + the index of the first
+// mesh with a degenerate / out-of-range face (the reference panics there). n_meshes = 0 clears the registry.
+int32_t orc_set_mesh_faces(const float* mesh_verts, const uint32_t* mesh_offsets, uint32_t n_meshes, const uint32_t* faces,
+                           const uint32_t* face_offsets) {
+    g_half_edges.clear();
+    g_half_edges.resize(n_meshes);
+    for (uint32_t m = 0; m < n_meshes; ++m) {
+        const uint32_t nf = face_offsets[m + 1] - face_offsets[m];
+        if (nf == 0) continue;
+        if (!g_half_edges[m].build(mesh_verts + 3 * (size_t)mesh_offsets[m], mesh_offsets[m + 1] - mesh_offsets[m],
+                                   faces + 3 * (size_t)face_offsets[m], nf)) { g_half_edges.clear(); return 1 + (int32_t)m; }
+    }
+    return 0;
+}
+
 // Ray casts against primitives (ray_oracle.hpp). rays: n_rays x 6 f32 (origin, direction) — or, for query 2, segments
 // (start, end) of a swept Particle; casts: n x (ray index, shape index). query: 0 = intersects_transformed,
-// 1 = intersection_transformed, 2 = (Particle, Range<Vec3>). out_status: 0 hit, 1 miss, 6 unsupported (ConvexPolyhedron);
+// 1 = intersection_transformed, 2 = (Particle, Range<Vec3>). out_status: 0 hit, 1 miss, 6 unsupported (a ConvexPolyhedron
+// without faces);
 // out_points: n x 3 f32, the world-space hit point for queries 1 and 2 (zero otherwise).
-void orc_ray_cast_batch(const uint8_t* kind, const float* params, const float* xform, const float* rays, const uint32_t* casts,
-                        uint64_t n, int32_t query, float* out_points, uint8_t* out_status, int nthreads) {
-    ShapeTable T{kind, params, xform, nullptr, nullptr, nullptr};
+void orc_ray_cast_batch(const uint8_t* kind, const float* params, const float* xform, const uint32_t* mesh_id, const float* mesh_verts,
+                        const uint32_t* mesh_offsets, const float* rays, const uint32_t* casts, uint64_t n, int32_t query,
+                        float* out_points, uint8_t* out_status, int nthreads) {
+    ShapeTable T{kind, params, xform, mesh_id, mesh_verts, mesh_offsets};
     parallel_for(n, nthreads, [&](uint64_t b, uint64_t e, int) {
         for (uint64_t i = b; i < e; ++i) {
             const float* r = rays + 6 * (size_t)casts[2 * i];
             const uint32_t si = casts[2 * i + 1];
             Vec3 p = Vec3::zero();
             uint8_t st = 1;
-            if (kind[si] == POLYHEDRON) {
-                st = 6;
+            Shape s0 = (kind[si] == POLYHEDRON && !mesh_id) ? Shape() : T.shape(si);
+            if (kind[si] == POLYHEDRON && !s0.he) {
+                st = 6;  // VertexOnly polyhedron: no faces to walk
             } else {
-                Shape s = T.shape(si);
+                Shape s = s0;
                 Mat4 m = T.mat(si);
                 bool hit;
                 if (query == 0) hit = ray_intersects_transformed(s, Ray(Vec3(r[0], r[1], r[2]), Vec3(r[3], r[4], r[5])), m);

@@ -5,7 +5,9 @@
 //   (capsule.rs:69-178), Particle (particle.rs:53-69), cylinder_ray_quadratic_solve (primitive/util.rs:95-109);
 //   the blanket Discrete/ContinuousTransformed<Ray> (ray.rs:58-78); Primitive3's dispatch (primitive3.rs:133-166);
 //   the swept particle (Particle, Range<Vec3>) (particle.rs:39-128).
-// ConvexPolyhedron's ray walk (polyhedron.rs:373-522) needs the half-edge face lists and is not restated.
+// ConvexPolyhedron (polyhedron.rs:373-522): the face walk over the half-edge structure, for polyhedra built with
+// new_with_faces; a VertexOnly polyhedron has no faces, and the walk's `Some(0)` start then indexes an empty list (the
+// reference panics): reported as unsupported.
 #pragma once
 #include "bam3d_oracle.hpp"
 #include "broad_oracle.hpp"
@@ -30,6 +32,67 @@ inline bool cylinder_ray_quadratic_solve(const Ray& r, float radius, float& t1, 
     t1 = (-b + drsqrt) / (2.f * a);
     t2 = (-b - drsqrt) / (2.f * a);
     return true;
+}
+
+// primitive/util.rs:63-79 barycentric_point (same expressions as barycentric_vector)
+inline void barycentric_point(Vec3 p, Vec3 a, Vec3 b, Vec3 c, float& u, float& v, float& w) {
+    Vec3 v0 = b - a, v1 = c - a, v2 = p - a;
+    float d00 = dot(v0, v0), d01 = dot(v0, v1), d11 = dot(v1, v1), d20 = dot(v2, v0), d21 = dot(v2, v1);
+    float inv_denom = 1.f / (d00 * d11 - d01 * d01);
+    v = (d11 * d20 - d01 * d21) * inv_denom;
+    w = (d00 * d21 - d01 * d20) * inv_denom;
+    u = 1.f - v - w;
+}
+
+// find_intersecting_face (polyhedron.rs:401-425) with intersect_ray_face (:497-521) and next_face_classify (:433-494).
+// Returns the face index or -1; (u, v, w) are the hit's barycentric coordinates.
+inline int poly_find_intersecting_face(const Shape& s, const Ray& ray, float& u, float& v, float& w) {
+    const HalfEdgeMesh& m = *s.he;
+    const size_t nfaces = m.faces.size();
+    auto pos = [&](uint32_t i) { return Vec3(s.verts[3 * i], s.verts[3 * i + 1], s.verts[3 * i + 2]); };
+    std::vector<bool> checked(nfaces, false);
+    long face = 0;
+    while (face >= 0) {
+        const size_t fi = (size_t)face;
+        checked[fi] = true;
+        const HalfEdgeMesh::Face& f = m.faces[fi];
+        bool have = false;
+        if (dot(f.n, ray.direction) < 0.f) {           // intersect_ray_face
+            const float t = -(f.d + dot(ray.origin, f.n)) / dot(ray.direction, f.n);  // plane.rs:117-129
+            if (!(t < 0.f)) {
+                const Vec3 p = ray.origin + ray.direction * t;
+                barycentric_point(p, pos(f.v[0]), pos(f.v[1]), pos(f.v[2]), u, v, w);
+                have = true;
+                auto in_range = [](float x) { return x >= 0.f && x <= 1.f; };
+                if (in_range(u) && in_range(v) && in_range(w)) return (int)fi;
+            }
+        }
+        // next_face_classify
+        long next = -1;
+        if (nfaces < 10) {
+            next = (fi == nfaces - 1) ? -1 : (long)fi + 1;
+        } else if (!have) {
+            size_t nx = fi + 1;
+            while (nx < nfaces && checked[nx]) ++nx;
+            next = (nx == nfaces) ? -1 : (long)nx;
+        } else {
+            const uint32_t target = (u < 0.f) ? f.v[2] : ((v < 0.f) ? f.v[0] : f.v[1]);
+            const HalfEdgeMesh::Edge& fe = m.edges[f.edge];
+            uint32_t e3[3];
+            if (fe.target_vertex == target) { e3[0] = f.edge; e3[1] = fe.next_edge; e3[2] = fe.previous_edge; }
+            else if (m.edges[fe.previous_edge].target_vertex == target) { e3[0] = fe.previous_edge; e3[1] = f.edge; e3[2] = fe.next_edge; }
+            else { e3[0] = fe.next_edge; e3[1] = fe.previous_edge; e3[2] = f.edge; }
+            for (int k = 0; k < 3 && next < 0; ++k) {
+                const uint32_t lf = m.edges[m.edges[e3[k]].twin_edge].left_face;
+                if (!checked[lf]) next = (long)lf;
+            }
+            if (next < 0)
+                for (size_t i = 0; i < nfaces; ++i)
+                    if (!checked[i]) { next = (long)i; break; }
+        }
+        face = next;
+    }
+    return -1;
 }
 
 // Discrete<Ray> in the primitive's object space
@@ -92,6 +155,10 @@ inline bool ray_intersects_local(const Shape& s, const Ray& r) {
                 if (d2 <= radius * radius) return true;
             }
             return false;
+        }
+        case POLYHEDRON: {  // polyhedron.rs:373-378
+            float u, v, w;
+            return s.he && !s.he->faces.empty() && poly_find_intersecting_face(s, r, u, v, w) >= 0;
         }
         default: return false;
     }
@@ -177,6 +244,16 @@ inline bool ray_intersection_local(const Shape& s, const Ray& r, Vec3& out) {
             float full = hh + radius;
             if (pc.y > full || pc.y < -full) return false;
             out = pc;
+            return true;
+        }
+        case POLYHEDRON: {  // polyhedron.rs:380-394
+            if (!s.he || s.he->faces.empty()) return false;
+            float u, v, w;
+            const int fi = poly_find_intersecting_face(s, r, u, v, w);
+            if (fi < 0) return false;
+            const HalfEdgeMesh::Face& f = s.he->faces[(size_t)fi];
+            auto pos = [&](uint32_t i) { return Vec3(s.verts[3 * i], s.verts[3 * i + 1], s.verts[3 * i + 2]); };
+            out = (pos(f.v[0]) * u) + (pos(f.v[1]) * v) + (pos(f.v[2]) * w);
             return true;
         }
         default: return false;

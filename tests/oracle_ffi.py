@@ -128,9 +128,23 @@ class Oracle:
         n = len(casts)
         pts = np.zeros((n, 3), dtype=np.float32)
         st = np.zeros(n, dtype=np.uint8)
-        self.lib.orc_ray_cast_batch(_p(kind), _p(params), _p(xform), _p(rays), _p(casts), C.c_uint64(n), C.c_int32(int(query)), _p(pts),
-                                    _p(st), C.c_int(nthreads))
+        self.lib.orc_ray_cast_batch(_p(kind), _p(params), _p(xform), _p(mesh_id), _p(mv), _p(mo), _p(rays), _p(casts), C.c_uint64(n),
+                                    C.c_int32(int(query)), _p(pts), _p(st), C.c_int(nthreads))
         return pts, st
+
+    def set_mesh_faces(self, mesh_verts, mesh_offsets, faces, face_offsets):
+        """ConvexPolyhedron::new_with_faces for the meshes that have faces (HalfEdge mode in every later batch call of this
+        process); set_mesh_faces(None, ...) clears. Raises where the reference would panic (degenerate face)."""
+        if mesh_verts is None:
+            self.lib.orc_set_mesh_faces(None, None, C.c_uint32(0), None, None)
+            return
+        mv = np.ascontiguousarray(mesh_verts, dtype=np.float32)
+        mo = np.ascontiguousarray(mesh_offsets, dtype=np.uint32)
+        f = np.ascontiguousarray(faces, dtype=np.uint32).reshape(-1, 3)
+        fo = np.ascontiguousarray(face_offsets, dtype=np.uint32)
+        rc = self.lib.orc_set_mesh_faces(_p(mv), _p(mo), C.c_uint32(len(mo) - 1), _p(f), _p(fo))
+        if rc:
+            raise ValueError(f"mesh {rc - 1}: degenerate or out-of-range face")
 
     def support_point(self, kind, params4, direction, xform16, verts=None):
         params4 = np.ascontiguousarray(params4, dtype=np.float32)

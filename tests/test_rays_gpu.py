@@ -76,7 +76,7 @@ def test_ray_cast_parity_all_kinds(ctx, oracle, query):
     assert_f32_equal("hit point", pts, opts)
 
 
-def test_ray_cast_polyhedron_unsupported_and_empty(ctx):
+def test_ray_cast_vertex_only_polyhedron_unsupported_and_empty(ctx):
     lib = scenes.mesh_library(4)
     ps = scenes.polyhedron_pairs(8, library=lib)
     shapes = b3.ShapeSet(ctx, ps["kind"], ps["params"], ps["xform"], ps["mesh_id"], b3.MeshLibrary(ctx, *lib))
