@@ -213,7 +213,9 @@ B3_DEV void load_pair_shape(Shape& s, const ShapeSetDev& S, uint32_t idx) {
         uint32_t b = __ldg(S.mesh_offsets + mid), e = __ldg(S.mesh_offsets + mid + 1);
         s.verts = S.mesh_verts + b + MESH_HEADER_SLOTS;
         s.nverts = e - b - MESH_HEADER_SLOTS;
+#ifndef B3_NO_HALF_EDGE  // (development: measures what the HalfEdge-mode check costs the VertexOnly path)
         if (mesh_header(s.verts)->n_faces) s.nverts |= MESH_HALF_EDGE;
+#endif
     }
 }
 

@@ -127,7 +127,8 @@ B3_DEV const MeshHeader* mesh_header(const float4* verts) { return reinterpret_c
 // to the best of them, stop when a pass improves the dot product by less than f32::EPSILON. Serial by nature (in the warp
 // kernels every lane runs it on identical data). The caps only bound malformed input the reference would hang on (a ring
 // that does not close, NaN directions).
-B3_DEV V3 polyhedron_hill_climb(const float4* __restrict__ verts, uint32_t nverts, V3 d) {
+// (not inlined: the VertexOnly path, which C3 measures, should not carry this loop nest at every support call site)
+static __device__ __noinline__ V3 polyhedron_hill_climb(const float4* __restrict__ verts, uint32_t nverts, V3 d) {
     const MeshHeader* h = mesh_header(verts);
     const uint32_t* __restrict__ ve = h->vert_edge;
     const uint4* __restrict__ ed = h->edges;
@@ -194,8 +195,11 @@ B3_DEV V3 support_point(const Shape& s, V3 dir) {
             break;
         }
         default:  // K_POLYHEDRON, polyhedron.rs:342-355
+#ifndef B3_NO_HALF_EDGE
             if (s.nverts & MESH_HALF_EDGE) p = polyhedron_hill_climb(s.verts, s.nverts & ~MESH_HALF_EDGE, d);
-            else p = polyhedron_local_support<WARP>(s.verts, s.nverts, d);
+            else
+#endif
+                p = polyhedron_local_support<WARP>(s.verts, s.nverts, d);
             break;
     }
     return transform_point3(s, p);
