@@ -148,6 +148,7 @@ int32_t bam3d_ctx_create(int32_t device_ordinal, bam3d_ctx** out_ctx) {
     ctx->device = device_ordinal;
     if (const char* e = std::getenv("BAM3D_EPA_TIERS")) ctx->opt_epa_tiers = std::atoi(e) != 0;      // development A/B switches
     if (const char* e = std::getenv("BAM3D_EPA_OVERLAP")) ctx->opt_epa_overlap = std::atoi(e) != 0;
+    if (const char* e = std::getenv("BAM3D_EPA_GLOBAL")) ctx->opt_epa_global_polytopes = std::atoi(e) != 0;
     if (const char* e = std::getenv("BAM3D_INTERSECT_SPLIT")) ctx->opt_intersect_split = std::atoi(e) != 0;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return BAM3D_ERR_CUDA; }
     if (cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess ||
@@ -183,6 +184,7 @@ int32_t bam3d_ctx_set_option(bam3d_ctx* ctx, const char* name, int32_t value) {
     if (!std::strcmp(name, "timing")) { ctx->opt_timing = value != 0; return BAM3D_OK; }
     if (!std::strcmp(name, "epa_tiers")) { ctx->opt_epa_tiers = value != 0; return BAM3D_OK; }
     if (!std::strcmp(name, "epa_overlap")) { ctx->opt_epa_overlap = value != 0; return BAM3D_OK; }
+    if (!std::strcmp(name, "epa_global_polytopes")) { ctx->opt_epa_global_polytopes = value != 0; return BAM3D_OK; }
     if (!std::strcmp(name, "intersect_split")) { ctx->opt_intersect_split = value != 0; return BAM3D_OK; }
     if (!std::strcmp(name, "bvh_strategy")) { if (value < 0 || value > 2) return b3_fail(ctx, BAM3D_ERR_ARG, "bvh_strategy must be 0 (auto), 1 (traversal) or 2 (all pairs)", cudaSuccess); ctx->opt_bvh_strategy = value; return BAM3D_OK; }
     if (!std::strcmp(name, "sap_strategy")) { if (value < 0 || value > 2) return b3_fail(ctx, BAM3D_ERR_ARG, "sap_strategy must be 0 (auto), 1 (sweep) or 2 (bvh)", cudaSuccess); ctx->opt_sap_strategy = value; return BAM3D_OK; }
@@ -471,10 +473,15 @@ int32_t bam3d_gjk_contact_dev(bam3d_ctx* ctx, const bam3d_shapes* shapes, const 
     { KernelTimer kt(ctx);
       // without binning every thread-path pair has the same kind on both sides: tell the EPA which bin that is
       ContactSide side{ctx->stream2, ctx->ev_a, ctx->ev_b};
+      void* poly_slab = nullptr;
+      if (ctx->opt_epa_global_polytopes && plan.run_thread && strategy == BAM3D_FULL_RESOLUTION) {
+          if ((rc = ctx->epa_slab.reserve(ctx, contact_poly_slab_bytes()))) return rc;
+          poly_slab = ctx->epa_slab.ptr;
+      }
       uint32_t default_key = 0;
       for (uint32_t k = 0; k < 6; ++k) if (shapes->kind_hist[k]) default_key = k * 7 + k;
       ctx->launches += launch_contact(ctx->stream, S, (const uint2*)d_pairs, (uint32_t)n, pb, plan.run_thread, plan.run_warp, cfg, strategy,
-                                      default_key, ctx->opt_epa_tiers ? 1 : 0, ctx->opt_epa_overlap ? &side : nullptr, ctx->epa_overflow.ptr, ctx->epa_queue.ptr, (float4*)d_contacts,
+                                      default_key, ctx->opt_epa_tiers ? 1 : 0, ctx->opt_epa_overlap ? &side : nullptr, poly_slab, ctx->epa_overflow.ptr, ctx->epa_queue.ptr, (float4*)d_contacts,
                                       d_status); }
     return check_launch(ctx, "gjk_contact_kernel");
 }

@@ -25,6 +25,7 @@ struct bam3d_ctx {
     bool opt_binning = true;
     bool opt_epa_tiers = false;   // contact path: shared-memory EPA in size tiers (epa_tiers.cuh) instead of per-thread local-memory EPA
     bool opt_intersect_split = false;  // intersect, thread path: first-support test and the GJK loop as two launches (measured slower on C1: 0.176 vs 0.167 ms)
+    bool opt_epa_global_polytopes = true;   // thread-per-pair EPA: polytopes in a global slab (contiguous per thread) instead of local memory
     bool opt_epa_overlap = true;  // contact path: run the EPA overflow tier on the side stream next to the EPA kernel
     int opt_sap_strategy = 0;  // 0 auto, 1 tiled sweep, 2 BVH overlap query
     int opt_bvh_strategy = 0;  // variable-length queries: 0 auto, 1 tree traversal, 2 all (query, value) tests
@@ -34,11 +35,11 @@ struct bam3d_ctx {
     bool opt_timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_events;
     // scratch for the host-buffer entry points and the binning pass
-    DevBuf pairs, status, contacts, f0, f1, keys, order, small, epa_overflow, epa_queue;
+    DevBuf pairs, status, contacts, f0, f1, keys, order, small, epa_overflow, epa_queue, epa_slab;
     // broad-phase scratch
     DevBuf bp0, bp1, bp2, bp3, bp4, bp5, bp6, bp7, cub_tmp;
     void release_scratch() {
-        DevBuf* all[] = {&pairs, &status, &contacts, &f0, &f1, &keys, &order, &small, &epa_overflow, &epa_queue, &bp0, &bp1, &bp2, &bp3, &bp4, &bp5, &bp6, &bp7, &cub_tmp};
+        DevBuf* all[] = {&pairs, &status, &contacts, &f0, &f1, &keys, &order, &small, &epa_overflow, &epa_queue, &epa_slab, &bp0, &bp1, &bp2, &bp3, &bp4, &bp5, &bp6, &bp7, &cub_tmp};
         for (DevBuf* b : all) b->release();
     }
 };

@@ -454,9 +454,18 @@ __global__ void __launch_bounds__(TPB) gjk_phase_kernel(ShapeSetDev S, const uin
     }
 }
 
+// GLOBAL_POLY: the polytopes live in a global-memory slab, one contiguous EPA_SLAB_BYTES record per thread, instead of
+// per-thread local memory (which the hardware interleaves by lane at 4-byte granularity). Contiguous records mean every
+// 32-byte sector a lane fetches holds only its own data, whatever the other lanes of the warp are doing.
+constexpr size_t EPA_SLAB_VV = 1280, EPA_SLAB_FN = (size_t)EPA_FCAP * 16, EPA_SLAB_FI = (size_t)EPA_FCAP * 4;
+constexpr size_t EPA_SLAB_BYTES = 2 * EPA_SLAB_VV + EPA_SLAB_FN + EPA_SLAB_FI;  // 7680 = 60 x 128
+static_assert(EPA_SLAB_VV >= (size_t)EPA_VCAP * 12 && EPA_SLAB_BYTES % 128 == 0, "slab layout");
+
+template <bool GLOBAL_POLY>
 __global__ void __launch_bounds__(TPB, 4) epa_refill_kernel(ShapeSetDev S, const uint2* __restrict__ pairs, SettingsDev cfg,
                                                          const uint32_t* __restrict__ bin_start, BinOrder bo,
                                                          unsigned char* __restrict__ queue, unsigned char* __restrict__ ovf_scratch,
+                                                         unsigned char* __restrict__ slab,
                                                          float4* __restrict__ contacts, uint8_t* __restrict__ status) {
     // segment table in consumption order: s_pref[i] = records before segment i, s_base[i] = its first record
     __shared__ uint32_t s_pref[EPAQ_BINS + 1];
@@ -473,12 +482,20 @@ __global__ void __launch_bounds__(TPB, 4) epa_refill_kernel(ShapeSetDev S, const
         s_pref[EPAQ_BINS] = acc;
     }
     __syncthreads();
-    float lvv[EPA_VCAP * 3];
-    float lva[EPA_VCAP * 3];
-    float4 lfn[EPA_FCAP];
-    uint32_t lfi[EPA_FCAP];
+    float lvv[GLOBAL_POLY ? 1 : EPA_VCAP * 3];
+    float lva[GLOBAL_POLY ? 1 : EPA_VCAP * 3];
+    float4 lfn[GLOBAL_POLY ? 1 : EPA_FCAP];
+    uint32_t lfi[GLOBAL_POLY ? 1 : EPA_FCAP];
     PolytopeStore P;
-    P.vv = lvv; P.va = lva; P.fn = lfn; P.fi = lfi;
+    if (GLOBAL_POLY) {
+        unsigned char* mine = slab + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * EPA_SLAB_BYTES;
+        P.fn = reinterpret_cast<float4*>(mine);
+        P.fi = reinterpret_cast<uint32_t*>(mine + EPA_SLAB_FN);
+        P.vv = reinterpret_cast<float*>(mine + EPA_SLAB_FN + EPA_SLAB_FI);
+        P.va = reinterpret_cast<float*>(mine + EPA_SLAB_FN + EPA_SLAB_FI + EPA_SLAB_VV);
+    } else {
+        P.vv = lvv; P.va = lva; P.fn = lfn; P.fi = lfi;
+    }
     P.fcap = EPA_FCAP;
 #ifdef B3_EPA_LOCAL_EDGES
     uint16_t led[EPA_ECAP];
@@ -882,6 +899,7 @@ int launch_intersect(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs
     if (run_warp) { gjk_intersect_kernel<true><<<warp_grid(n), TPB, 0, st>>>(S, d_pairs, n, order, ranges, cfg, d_status); ++launched; }
     return launched;
 }
+size_t contact_poly_slab_bytes() { return (size_t)NUM_SMS * 4 * TPB * EPA_SLAB_BYTES; }
 size_t contact_overflow_scratch_bytes() { return OVF_HEADER_BYTES + (size_t)OVF_WARPS * EPA_BIG_SLAB_BYTES; }
 // header | n GJK->EPA records | 3 promotion lists of n record indices | sup_a scratch of the shared-memory EPA warps
 static size_t queue_lists_bytes(uint32_t n) { return ((size_t)n * 12 + 15) & ~(size_t)15; }
@@ -893,7 +911,8 @@ static int epa_refill_grid() {
     static int blocks = 0;
     if (!blocks) {
         int per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, epa_refill_kernel, TPB, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, epa_refill_kernel<false>, TPB, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
+        if (per_sm > 4) per_sm = 4;  // (the slab of the global-polytope variant is sized for 4 blocks per SM)
         if (const char* e = getenv("BAM3D_EPA_BLOCKS_PER_SM")) { int v = atoi(e); if (v >= 1 && v < per_sm) per_sm = v; }
         blocks = per_sm * NUM_SMS;
     }
@@ -952,7 +971,7 @@ static BinOrder epa_bin_order() {
 
 int launch_contact(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs, uint32_t n, const BinScratch* B, bool run_thread,
                    bool run_warp, const SettingsDev& cfg, int strategy, uint32_t default_key, int epa_mode, const ContactSide* side,
-                   void* d_overflow_scratch, void* d_queue, float4* d_contacts, uint8_t* d_status) {
+                   void* d_poly_slab, void* d_overflow_scratch, void* d_queue, float4* d_contacts, uint8_t* d_status) {
     unsigned char* ovf = reinterpret_cast<unsigned char*>(d_overflow_scratch);
     unsigned char* queue = reinterpret_cast<unsigned char*>(d_queue);
     if (n == 0) return 0;
@@ -1002,8 +1021,12 @@ int launch_contact(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs, 
             }
 #endif
         } else if (strategy == 0) {
-            epa_refill_kernel<<<epa_refill_grid(), TPB, 0, st>>>(S, d_pairs, cfg, bin_start, epa_bin_order(), queue, ovf, d_contacts,
-                                                                 d_status);
+            if (d_poly_slab)
+                epa_refill_kernel<true><<<epa_refill_grid(), TPB, 0, st>>>(S, d_pairs, cfg, bin_start, epa_bin_order(), queue, ovf,
+                                                                           reinterpret_cast<unsigned char*>(d_poly_slab), d_contacts, d_status);
+            else
+                epa_refill_kernel<false><<<epa_refill_grid(), TPB, 0, st>>>(S, d_pairs, cfg, bin_start, epa_bin_order(), queue, ovf, nullptr,
+                                                                            d_contacts, d_status);
             ++launched;
 #ifdef B3_TIER_TRACE
             {

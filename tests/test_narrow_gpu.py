@@ -153,10 +153,11 @@ def test_contact_parity_mixed(ctx, oracle):
     assert not contacts[~hit].any()
 
 
-@pytest.mark.parametrize("options", [{"epa_overlap": 0}, {"epa_tiers": 1}, {"binning": 0}])
+@pytest.mark.parametrize("options", [{"epa_overlap": 0}, {"epa_tiers": 1}, {"binning": 0}, {"epa_global_polytopes": 0}])
 def test_contact_parity_execution_options(ctx, oracle, options):
     """The contact path's execution switches change scheduling only: overflow tier in stream order instead of on the
-    side stream, shared-memory EPA tiers (promotion lists, restarts) instead of per-thread polytopes, no pair binning.
+    side stream, shared-memory EPA tiers (promotion lists, restarts) instead of per-thread polytopes, no pair binning,
+    polytopes in per-thread local memory instead of the global slab.
     Same bits out; the scene includes sphere-sphere pairs (tier 2 -> 3 promotions) and overflow-tier pairs."""
     scene = scenes.all_kinds_pairs(30_000, s=1.0)
     shapes = shapes_of(ctx, scene)
@@ -167,7 +168,7 @@ def test_contact_parity_execution_options(ctx, oracle, options):
         contacts, st = b3.GJK.new(ctx).intersection_batch(b3.CollisionStrategy.FullResolution, shapes, scene["pairs"])
     finally:
         for k in options:
-            ctx.set_option(k, {"epa_overlap": 1, "epa_tiers": 0, "binning": 1}[k])
+            ctx.set_option(k, {"epa_overlap": 1, "epa_tiers": 0, "binning": 1, "epa_global_polytopes": 1}[k])
     assert np.array_equal(st, ost), f"{int((st != ost).sum())} status mismatches"
     hit = st == 0
     assert_f32_equal("contact", contacts[:, 0:7], oc[:, 0:7], hit)
