@@ -40,9 +40,9 @@ ALGO_BYTES = {  # algorithmic HBM bytes per pair
     "c5": 0.4 * 148.0 + 0.2 * 129.0 + 0.2 * 124.0 + 0.2 * 264.0,  # the C5 mix of the four rows above (162.6 B/pair)
 }
 # DRAM traffic of the dominant kernel per launch (bytes), from the committed ncu captures (profiles/r1_*_ncu_full.txt);
-# for C2 it is far above the algorithmic bytes because the EPA polytopes live in per-thread local memory that
-# overflows L2 (DESIGN.md §11 records what was tried against it this round).
-NCU_DRAM_BYTES = {"c1": 223.0e6, "c2": 19.0e9, "c3": 258.0e6}  # c2 / c3: profiles/r1b_*_ncu_full.txt
+# for C2 it is far above the algorithmic bytes because the EPA polytopes (7.5 KB slab record per resident thread) do not
+# all stay in L2 (DESIGN.md §11 records what was tried against it this round: 24 GB -> 5.4 GB).
+NCU_DRAM_BYTES = {"c1": 223.0e6, "c2": 5.36e9, "c3": 258.0e6}  # c2: profiles/r1c_c2_ncu_full.txt, c3: r1b
 WORKLOAD_DESC = {
     "c1": "C1: GJK intersect, 2^20 random Cuboid-Cuboid pairs per GPU (f32, random transforms, offset U[-2,2]^3)",
     "c2": "C2: GJK+EPA Contact (FullResolution), 2^20 mixed Sphere/Cuboid/Cylinder pairs per GPU (offset U[-1.5,1.5]^3)",
