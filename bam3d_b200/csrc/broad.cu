@@ -428,23 +428,26 @@ __global__ void bvh_scene_init_kernel(uint32_t* scene) {
     else if (threadIdx.x < 6) scene[threadIdx.x] = 0u;
 }
 
+// scene bounds of the box centres (min / max per axis as order-preserving keys): grid-stride accumulation per thread, one
+// warp reduction (redux.sync) and six atomics per warp at the end
 __global__ void __launch_bounds__(BT) bvh_scene_kernel(const float* __restrict__ aabbs, uint32_t n, uint32_t* __restrict__ scene) {
-    uint32_t i = blockIdx.x * BT + threadIdx.x;
-    float c[3] = {0.f, 0.f, 0.f};
-    bool ok = i < n;
-    if (ok) {
+    uint32_t kmin[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, kmax[3] = {0u, 0u, 0u};
+    for (uint32_t i = blockIdx.x * BT + threadIdx.x; i < n; i += gridDim.x * BT) {
         const float* b = aabbs + 6 * (size_t)i;
-        c[0] = (b[0] + b[3]) * 0.5f; c[1] = (b[1] + b[4]) * 0.5f; c[2] = (b[2] + b[5]) * 0.5f;
+        const float c[3] = {(b[0] + b[3]) * 0.5f, (b[1] + b[4]) * 0.5f, (b[2] + b[5]) * 0.5f};
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            if (c[a] == c[a]) {
+                const uint32_t k = fkey(c[a]);
+                kmin[a] = min(kmin[a], k);
+                kmax[a] = max(kmax[a], k);
+            }
+        }
     }
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-        uint32_t kmin = ok && c[a] == c[a] ? fkey(c[a]) : 0xFFFFFFFFu, kmax = ok && c[a] == c[a] ? fkey(c[a]) : 0u;
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            kmin = min(kmin, __shfl_xor_sync(0xFFFFFFFFu, kmin, off));
-            kmax = max(kmax, __shfl_xor_sync(0xFFFFFFFFu, kmax, off));
-        }
-        if ((threadIdx.x & 31) == 0) { atomicMin(scene + a, kmin); atomicMax(scene + 3 + a, kmax); }
+        const uint32_t lo = __reduce_min_sync(0xFFFFFFFFu, kmin[a]), hi = __reduce_max_sync(0xFFFFFFFFu, kmax[a]);
+        if ((threadIdx.x & 31) == 0) { atomicMin(scene + a, lo); atomicMax(scene + 3 + a, hi); }
     }
 }
 
@@ -575,7 +578,7 @@ int launch_bvh_build(cudaStream_t st, const float* d_aabbs, uint32_t n, const Bv
     const int g = (n + BT - 1) / BT;
     uint32_t* scene = reinterpret_cast<uint32_t*>(W.scene);
     bvh_scene_init_kernel<<<1, 32, 0, st>>>(scene); ++launched;
-    bvh_scene_kernel<<<g, BT, 0, st>>>(d_aabbs, n, scene); ++launched;
+    bvh_scene_kernel<<<min(g, 148 * 16), BT, 0, st>>>(d_aabbs, n, scene); ++launched;
     bvh_morton_kernel<<<g, BT, 0, st>>>(d_aabbs, n, scene, W.morton_in, W.idx_in); ++launched;
     size_t tmp = W.cub_tmp_bytes;
     cub::DeviceRadixSort::SortPairs(W.cub_tmp, tmp, W.morton_in, W.morton_out, W.idx_in, leaf_value, (int)n, 0, 30, st); launched += 4;
