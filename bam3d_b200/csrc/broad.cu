@@ -514,15 +514,17 @@ __global__ void __launch_bounds__(BT) bvh_topology_kernel(const uint32_t* __rest
     if (i == 0) parent[0] = 0xFFFFFFFFu;
 }
 
+// Node record: two float4 side by side (one 32-byte sector): (min.xyz, left child) and (max.xyz, right child); the child
+// ids are stored as int bits, so a traversal reads one sector per node and no separate topology array.
 __global__ void __launch_bounds__(BT) bvh_refit_kernel(const float* __restrict__ aabbs, const uint32_t* __restrict__ leaf_value, uint32_t n,
                                                        const int2* __restrict__ children, const uint32_t* __restrict__ parent,
-                                                       uint32_t* __restrict__ flags, float4* __restrict__ lo, float4* __restrict__ hi) {
+                                                       uint32_t* __restrict__ flags, float4* __restrict__ nodes) {
     uint32_t k = blockIdx.x * BT + threadIdx.x;
     if (k >= n) return;
     const float* b = aabbs + 6 * (size_t)leaf_value[k];
     uint32_t node = (n - 1) + k;
-    lo[node] = make_float4(b[0], b[1], b[2], 0.f);
-    hi[node] = make_float4(b[3], b[4], b[5], 0.f);
+    nodes[2 * (size_t)node] = make_float4(b[0], b[1], b[2], 0.f);
+    nodes[2 * (size_t)node + 1] = make_float4(b[3], b[4], b[5], 0.f);
     if (n == 1) return;
     __threadfence();
     uint32_t p = parent[node];
@@ -530,10 +532,11 @@ __global__ void __launch_bounds__(BT) bvh_refit_kernel(const float* __restrict__
         if (atomicAdd(flags + p, 1u) == 0u) return;  // the second child to arrive computes the parent
         __threadfence();
         int2 ch = children[p];
-        float4 l0 = __ldcg(lo + ch.x), h0 = __ldcg(hi + ch.x), l1 = __ldcg(lo + ch.y), h1 = __ldcg(hi + ch.y);
+        float4 l0 = __ldcg(nodes + 2 * (size_t)ch.x), h0 = __ldcg(nodes + 2 * (size_t)ch.x + 1);
+        float4 l1 = __ldcg(nodes + 2 * (size_t)ch.y), h1 = __ldcg(nodes + 2 * (size_t)ch.y + 1);
         // union = grow(min).grow(max) with Rust's NaN-ignoring min/max (aabb3.rs:146-152)
-        lo[p] = make_float4(rmin(l0.x, l1.x), rmin(l0.y, l1.y), rmin(l0.z, l1.z), 0.f);
-        hi[p] = make_float4(rmax(h0.x, h1.x), rmax(h0.y, h1.y), rmax(h0.z, h1.z), 0.f);
+        nodes[2 * (size_t)p] = make_float4(rmin(l0.x, l1.x), rmin(l0.y, l1.y), rmin(l0.z, l1.z), __int_as_float(ch.x));
+        nodes[2 * (size_t)p + 1] = make_float4(rmax(h0.x, h1.x), rmax(h0.y, h1.y), rmax(h0.z, h1.z), __int_as_float(ch.y));
         __threadfence();
         p = parent[p];
     }
@@ -553,7 +556,7 @@ __global__ void __launch_bounds__(BT) bvh_parents_kernel(const int2* __restrict_
 }
 
 int launch_bvh_refit(cudaStream_t st, const float* d_aabbs, uint32_t n, const int2* children, const uint32_t* leaf_value, uint32_t* parent,
-                     uint32_t* flags, float4* lo, float4* hi) {
+                     uint32_t* flags, float4* nodes) {
     if (n == 0) return 0;
     int launched = 1;
     if (n > 1) {
@@ -561,7 +564,7 @@ int launch_bvh_refit(cudaStream_t st, const float* d_aabbs, uint32_t n, const in
         bvh_parents_kernel<<<(n + BT - 1) / BT, BT, 0, st>>>(children, n, parent);
         ++launched;
     }
-    bvh_refit_kernel<<<(n + BT - 1) / BT, BT, 0, st>>>(d_aabbs, leaf_value, n, children, parent, flags, lo, hi);
+    bvh_refit_kernel<<<(n + BT - 1) / BT, BT, 0, st>>>(d_aabbs, leaf_value, n, children, parent, flags, nodes);
     return launched;
 }
 
@@ -571,7 +574,7 @@ size_t bvh_cub_tmp_bytes(uint32_t n) {
     return a + 256;
 }
 
-int launch_bvh_build(cudaStream_t st, const float* d_aabbs, uint32_t n, const BvhBuildScratch& W, float4* lo, float4* hi, int2* children,
+int launch_bvh_build(cudaStream_t st, const float* d_aabbs, uint32_t n, const BvhBuildScratch& W, float4* nodes, int2* children,
                      uint32_t* leaf_value) {
     if (n == 0) return 0;
     int launched = 0;
@@ -586,7 +589,7 @@ int launch_bvh_build(cudaStream_t st, const float* d_aabbs, uint32_t n, const Bv
         cudaMemsetAsync(W.flags, 0, (size_t)(n - 1) * 4, st);
         bvh_topology_kernel<<<(n - 1 + BT - 1) / BT, BT, 0, st>>>(W.morton_out, n, children, W.parent); ++launched;
     }
-    bvh_refit_kernel<<<g, BT, 0, st>>>(d_aabbs, leaf_value, n, children, W.parent, W.flags, lo, hi); ++launched;
+    bvh_refit_kernel<<<g, BT, 0, st>>>(d_aabbs, leaf_value, n, children, W.parent, W.flags, nodes); ++launched;
     return launched;
 }
 
@@ -687,7 +690,7 @@ __global__ void __launch_bounds__(BT) bvh_query_kernel(BvhDev T, const float* __
         const uint32_t first_leaf = T.n - 1;
         while (sp > 0) {
             uint32_t node = stack[--sp];
-            float4 mn = __ldg(T.lo + node), mx = __ldg(T.hi + node);
+            float4 mn = __ldg(T.nodes + 2 * (size_t)node), mx = __ldg(T.nodes + 2 * (size_t)node + 1);
             V3 point; int rel = 0;
             if (!accept<KIND>(q, mn, mx, point, rel)) continue;
             if (node >= first_leaf) {
@@ -699,7 +702,7 @@ __global__ void __launch_bounds__(BT) bvh_query_kernel(BvhDev T, const float* __
                 }
                 ++cnt;
             } else if (sp <= 62) {
-                int2 ch = __ldg(T.children + node);
+                int2 ch = make_int2(__float_as_int(mn.w), __float_as_int(mx.w));
                 stack[sp++] = (uint32_t)ch.y;
                 stack[sp++] = (uint32_t)ch.x;
             }
@@ -804,7 +807,7 @@ __global__ void __launch_bounds__(BT) bvh_ray_closest_kernel(BvhDev T, const flo
         const uint32_t first_leaf = T.n - 1;
         while (sp > 0) {
             uint32_t node = stack[--sp];
-            float4 mn = __ldg(T.lo + node), mx = __ldg(T.hi + node);
+            float4 mn = __ldg(T.nodes + 2 * (size_t)node), mx = __ldg(T.nodes + 2 * (size_t)node + 1);
             V3 p;
             bool entered_from_outside;
             if (!ray_aabb(o, d, mn, mx, p, &entered_from_outside)) continue;
@@ -813,7 +816,7 @@ __global__ void __launch_bounds__(BT) bvh_ray_closest_kernel(BvhDev T, const flo
                 uint32_t v = __ldg(T.leaf_value + (node - first_leaf));
                 if (t < best_t || (t == best_t && v < best_v)) { best_t = t; best_v = v; best_p = p; }
             } else if (!(entered_from_outside && t > best_t) && sp <= 62) {
-                int2 ch = __ldg(T.children + node);
+                int2 ch = make_int2(__float_as_int(mn.w), __float_as_int(mx.w));
                 stack[sp++] = (uint32_t)ch.y;
                 stack[sp++] = (uint32_t)ch.x;
             }
@@ -856,7 +859,7 @@ __global__ void __launch_bounds__(BT) bvh_collider_pairs_kernel(BvhDev T, const 
         const uint32_t first_leaf = T.n - 1;
         while (sp > 0) {
             uint32_t node = stack[--sp];
-            float4 mn = __ldg(T.lo + node), mx = __ldg(T.hi + node);
+            float4 mn = __ldg(T.nodes + 2 * (size_t)node), mx = __ldg(T.nodes + 2 * (size_t)node + 1);
             V3 pt; int rel;
             if (!accept<BQ_AABB>(q, mn, mx, pt, rel)) continue;
             if (node >= first_leaf) {
@@ -867,7 +870,7 @@ __global__ void __launch_bounds__(BT) bvh_collider_pairs_kernel(BvhDev T, const 
                     ++cnt;
                 }
             } else if (sp <= 62) {
-                int2 ch = __ldg(T.children + node);
+                int2 ch = make_int2(__float_as_int(mn.w), __float_as_int(mx.w));
                 stack[sp++] = (uint32_t)ch.y;
                 stack[sp++] = (uint32_t)ch.x;
             }
@@ -899,7 +902,7 @@ __global__ void __launch_bounds__(BT) bvh_overlap_append_kernel(BvhDev T, const 
     const uint32_t first_leaf = T.n - 1;
     while (sp > 0) {
         const uint32_t node = stack[--sp];
-        const float4 mn = __ldg(T.lo + node), mx = __ldg(T.hi + node);
+        const float4 mn = __ldg(T.nodes + 2 * (size_t)node), mx = __ldg(T.nodes + 2 * (size_t)node + 1);
         V3 pt; int rel;
         if (!accept<BQ_AABB>(q, mn, mx, pt, rel)) continue;
         if (node >= first_leaf) {
@@ -914,7 +917,7 @@ __global__ void __launch_bounds__(BT) bvh_overlap_append_kernel(BvhDev T, const 
                 if (slot < capacity) keys[slot] = ((unsigned long long)v << key_shift) | h;
             }
         } else if (sp <= 62) {
-            const int2 ch = __ldg(T.children + node);
+            const int2 ch = make_int2(__float_as_int(mn.w), __float_as_int(mx.w));
             stack[sp++] = (uint32_t)ch.y;
             stack[sp++] = (uint32_t)ch.x;
         }

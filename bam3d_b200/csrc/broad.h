@@ -46,9 +46,7 @@ int launch_world_aabbs(cudaStream_t st, const ShapeSetDev& S, float* d_out6);
 struct BvhDev {
     // n leaves (values), n - 1 internal nodes. Node ids: internal 0..n-2 (root = 0), leaf k -> (n - 1) + k.
     uint32_t n;
-    const float4* lo;        // 2n - 1 node bounds (min xyz)
-    const float4* hi;        // 2n - 1 node bounds (max xyz)
-    const int2* children;    // n - 1 : (left, right) node ids
+    const float4* nodes;     // 2 x (2n - 1): (min.xyz, left child id as int bits), (max.xyz, right child id) — one 32-byte sector per node
     const uint32_t* leaf_value;  // n : value index of leaf k (Morton order)
 };
 struct BvhBuildScratch {
@@ -59,12 +57,12 @@ struct BvhBuildScratch {
     float* scene;       // 6 floats: scene bounds
 };
 size_t bvh_cub_tmp_bytes(uint32_t n);
-int launch_bvh_build(cudaStream_t st, const float* d_aabbs, uint32_t n, const BvhBuildScratch& W, float4* lo, float4* hi, int2* children,
+int launch_bvh_build(cudaStream_t st, const float* d_aabbs, uint32_t n, const BvhBuildScratch& W, float4* nodes, int2* children,
                      uint32_t* leaf_value);
 
 // bounds of an existing tree recomputed from new values (same topology); parent: 2n - 1 words, flags: n - 1 words of scratch
 int launch_bvh_refit(cudaStream_t st, const float* d_aabbs, uint32_t n, const int2* children, const uint32_t* leaf_value, uint32_t* parent,
-                     uint32_t* flags, float4* lo, float4* hi);
+                     uint32_t* flags, float4* nodes);
 
 enum BvhQueryKind { BQ_AABB = 0, BQ_RAY = 1, BQ_FRUSTUM = 2 };
 // pass 1 (d_offsets == nullptr): per-query hit counts into d_counts. pass 2: fill d_values / d_payload at d_offsets.

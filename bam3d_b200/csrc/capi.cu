@@ -645,14 +645,13 @@ int32_t bam3d_gjk_time_of_impact(bam3d_ctx* ctx, const bam3d_shapes* s0, const b
 struct bam3d_bvh {
     uint32_t n = 0;
     float* d_aabbs = nullptr;      // n x 6 (kept for DbvtBroadPhase queries)
-    float4* lo = nullptr;          // 2n - 1
-    float4* hi = nullptr;
-    int2* children = nullptr;      // n - 1
+    float4* nodes = nullptr;       // 2 x (2n - 1): node records (broad.h: BvhDev)
+    int2* children = nullptr;      // n - 1 (build / refit only)
     uint32_t* leaf_value = nullptr;
 };
 
 static BvhDev bvh_view(const bam3d_bvh* t) {
-    BvhDev v; v.n = t->n; v.lo = t->lo; v.hi = t->hi; v.children = t->children; v.leaf_value = t->leaf_value;
+    BvhDev v; v.n = t->n; v.nodes = t->nodes; v.leaf_value = t->leaf_value;
     return v;
 }
 
@@ -757,8 +756,7 @@ static int32_t sap_run(bam3d_ctx* ctx, const float* d_aabbs, uint64_t n64, int32
         char* q = slab;
         auto carve = [&](size_t bytes) { char* r = q; q += (bytes + 255) & ~(size_t)255; return r; };
         carve(nn * 24);  // d_sorted6
-        float4* nlo = (float4*)carve(2 * nn * 16);
-        float4* nhi = (float4*)carve(2 * nn * 16);
+        float4* nnodes = (float4*)carve(2 * 2 * nn * 16);
         int2* children = (int2*)carve(nn * 8);
         uint32_t* leaf_value = (uint32_t*)carve(nn * 4);
         BvhBuildScratch W;
@@ -770,10 +768,10 @@ static int32_t sap_run(bam3d_ctx* ctx, const float* d_aabbs, uint64_t n64, int32
         unsigned long long* d_offsets = (unsigned long long*)carve((nn + 1) * 8);
         W.cub_tmp = ctx->cub_tmp.ptr; W.cub_tmp_bytes = tmp_bytes;
         W.scene = (float*)((char*)ctx->small.ptr + 896);
-        BvhDev T; T.n = n; T.lo = nlo; T.hi = nhi; T.children = children; T.leaf_value = leaf_value;
+        BvhDev T; T.n = n; T.nodes = nnodes; T.leaf_value = leaf_value;
         const int shift = sap_bits_for(n);
         { KernelTimer kt(ctx);
-          ctx->launches += launch_bvh_build(ctx->stream, d_sorted6, n, W, nlo, nhi, children, leaf_value);
+          ctx->launches += launch_bvh_build(ctx->stream, d_sorted6, n, W, nnodes, children, leaf_value);
           ctx->launches += launch_bvh_overlap_append(ctx->stream, T, d_sorted6, j_begin, j_end, shift, S.pair_keys, capacity, d_count); }
         CU_TRY(cudaMemcpyAsync(&h_count, d_count, 8, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(count)");
         CU_TRY(cudaStreamSynchronize(ctx->stream), "sap bvh pair search");
@@ -885,8 +883,7 @@ void bam3d_bvh_free(bam3d_ctx* ctx, bam3d_bvh* t) {
     (void)ctx;
     if (!t) return;
     if (t->d_aabbs) cudaFree(t->d_aabbs);
-    if (t->lo) cudaFree(t->lo);
-    if (t->hi) cudaFree(t->hi);
+    if (t->nodes) cudaFree(t->nodes);
     if (t->children) cudaFree(t->children);
     if (t->leaf_value) cudaFree(t->leaf_value);
     delete t;
@@ -903,8 +900,8 @@ static int32_t bvh_build_impl(bam3d_ctx* ctx, const float* aabbs, bool on_device
     t->n = n;
     const size_t nn = n ? n : 1;
     cudaError_t e;
-    if ((e = cudaMalloc(&t->d_aabbs, nn * 24)) != cudaSuccess || (e = cudaMalloc(&t->lo, (2 * nn) * 16)) != cudaSuccess ||
-        (e = cudaMalloc(&t->hi, (2 * nn) * 16)) != cudaSuccess || (e = cudaMalloc(&t->children, nn * 8)) != cudaSuccess ||
+    if ((e = cudaMalloc(&t->d_aabbs, nn * 24)) != cudaSuccess || (e = cudaMalloc(&t->nodes, (2 * 2 * nn) * 16)) != cudaSuccess ||
+        (e = cudaMalloc(&t->children, nn * 8)) != cudaSuccess ||
         (e = cudaMalloc(&t->leaf_value, nn * 4)) != cudaSuccess) {
         bam3d_bvh_free(ctx, t);
         return b3_fail(ctx, BAM3D_ERR_OOM, "cudaMalloc(bvh)", e);
@@ -919,7 +916,7 @@ static int32_t bvh_build_impl(bam3d_ctx* ctx, const float* aabbs, bool on_device
     W.cub_tmp = ctx->cub_tmp.ptr; W.cub_tmp_bytes = tmp_bytes;
     W.scene = (float*)((char*)ctx->small.ptr + 896);
     { KernelTimer kt(ctx);
-      ctx->launches += launch_bvh_build(ctx->stream, t->d_aabbs, n, W, t->lo, t->hi, t->children, t->leaf_value); }
+      ctx->launches += launch_bvh_build(ctx->stream, t->d_aabbs, n, W, t->nodes, t->children, t->leaf_value); }
     e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) { bam3d_bvh_free(ctx, t); return b3_fail(ctx, BAM3D_ERR_CUDA, "bam3d_bvh_build", e); }
     *out = t;
@@ -938,7 +935,7 @@ static int32_t bvh_refit_impl(bam3d_ctx* ctx, bam3d_bvh* t, const float* aabbs, 
     uint32_t* flags = parent + 2 * nn;
     CU_TRY(cudaMemcpyAsync(t->d_aabbs, aabbs, nn * 24, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpyAsync(aabbs)");
     { KernelTimer kt(ctx);
-      ctx->launches += launch_bvh_refit(ctx->stream, t->d_aabbs, n, t->children, t->leaf_value, parent, flags, t->lo, t->hi); }
+      ctx->launches += launch_bvh_refit(ctx->stream, t->d_aabbs, n, t->children, t->leaf_value, parent, flags, t->nodes); }
     if ((rc = check_launch(ctx, "bvh_refit_kernel"))) return rc;
     if (!on_device) CU_TRY(cudaStreamSynchronize(ctx->stream), "bam3d_bvh_refit");
     return BAM3D_OK;
