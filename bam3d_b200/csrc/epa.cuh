@@ -69,9 +69,14 @@ struct ClosestFace {
 };
 
 // remove_or_add_edge (epa3d.rs:183-190): a reversed duplicate is removed (order preserving), else push.
-B3_DEV bool remove_or_add_edge(uint16_t* ed, int es, int& ne, int ecap, uint32_t a, uint32_t b) {
+// `seen` is a 64-bit Bloom filter over the directed edges pushed during this add(): a reversed duplicate can only be in the
+// list if its bit is set, so most pushes (two thirds of all calls on a well-formed polytope) skip the search loop
+// (C2: -3 %). (Tombstones instead of the order-preserving shift on removal were measured too: no gain.)
+B3_DEV uint32_t edge_bit(uint32_t a, uint32_t b) { return (a * 7u + b * 13u) & 63u; }
+B3_DEV bool remove_or_add_edge(uint16_t* ed, int es, int& ne, int ecap, uint32_t a, uint32_t b, unsigned long long& seen) {
     const uint16_t rev = (uint16_t)(b | (a << 8));
-    for (int i = 0; i < ne; ++i) {
+    const bool maybe = (seen >> edge_bit(b, a)) & 1ull;
+    for (int i = 0; maybe && i < ne; ++i) {
         if (ed[i * es] == rev) {
             for (int k = i; k + 1 < ne; ++k) ed[k * es] = ed[(k + 1) * es];
             --ne;
@@ -81,6 +86,7 @@ B3_DEV bool remove_or_add_edge(uint16_t* ed, int es, int& ne, int ecap, uint32_t
     if (ne >= ecap) return false;
     ed[ne * es] = (uint16_t)(a | (b << 8));
     ++ne;
+    seen |= 1ull << edge_bit(a, b);
     return true;
 }
 
@@ -216,6 +222,7 @@ B3_DEV uint8_t epa_iterate(const Shape& L, const Shape& R, float tolerance, uint
     }
     int ne = 0;
     bool ok = true;
+    unsigned long long seen = 0ull;
     for (int k = 0;;) {
         // next flagged slot >= k (bits at or beyond nf are always clear)
         int c = k >> 5;
@@ -237,9 +244,9 @@ B3_DEV uint8_t epa_iterate(const Shape& L, const Shape& R, float tolerance, uint
             if (!last_bit) cf.moved(lf.w, k);
         }
         uint32_t i0 = idx & 0xFF, i1 = (idx >> 8) & 0xFF, i2 = (idx >> 16) & 0xFF;
-        ok = ok && remove_or_add_edge(P.ed, P.estride, ne, P.ecap, i0, i1);
-        ok = ok && remove_or_add_edge(P.ed, P.estride, ne, P.ecap, i1, i2);
-        ok = ok && remove_or_add_edge(P.ed, P.estride, ne, P.ecap, i2, i0);
+        ok = ok && remove_or_add_edge(P.ed, P.estride, ne, P.ecap, i0, i1, seen);
+        ok = ok && remove_or_add_edge(P.ed, P.estride, ne, P.ecap, i1, i2, seen);
+        ok = ok && remove_or_add_edge(P.ed, P.estride, ne, P.ecap, i2, i0, seen);
         if (WARP) __syncwarp();
     }
     if (!ok || nv >= EPA_VCAP || nf + ne > P.fcap) return ST_CAPACITY;

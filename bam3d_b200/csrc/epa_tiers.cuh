@@ -277,6 +277,7 @@ B3_DEV bool tier_run(const TierSource& src, const TierShared& sh) {
         int ne = 0;
         if (scanning) {
             bool ok = true;
+            unsigned long long seen = 0ull;
             const int nchunks = (nf + 31) >> 5;
             for (int k = 0;;) {
                 int c = k >> 5;
@@ -298,9 +299,9 @@ B3_DEV bool tier_run(const TierSource& src, const TierShared& sh) {
                     if (!last_bit) cf.moved(lf.w, k);
                 }
                 const uint32_t i0 = idx & 0xFF, i1 = (idx >> 8) & 0xFF, i2 = (idx >> 16) & 0xFF;
-                ok = ok && remove_or_add_edge(P.ed, 1, ne, C::ECAP, i0, i1);
-                ok = ok && remove_or_add_edge(P.ed, 1, ne, C::ECAP, i1, i2);
-                ok = ok && remove_or_add_edge(P.ed, 1, ne, C::ECAP, i2, i0);
+                ok = ok && remove_or_add_edge(P.ed, 1, ne, C::ECAP, i0, i1, seen);
+                ok = ok && remove_or_add_edge(P.ed, 1, ne, C::ECAP, i1, i2, seen);
+                ok = ok && remove_or_add_edge(P.ed, 1, ne, C::ECAP, i2, i0, seen);
             }
             if (!ok || nf + ne > C::FCAP) {
                 scanning = false;
