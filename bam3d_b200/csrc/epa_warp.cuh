@@ -157,7 +157,8 @@ B3_DEV uint8_t epa_process_warp(const Shape& L, const Shape& R, const Simplex<tr
             }
             __syncwarp();
             const uint32_t vi[4] = {idx & 0xFF, (idx >> 8) & 0xFF, (idx >> 16) & 0xFF, idx & 0xFF};
-#pragma unroll
+            // not unrolled on purpose: the warp kernels are instruction-fetch bound (see support.cuh: support_point_outlined)
+#pragma unroll 1
             for (int e = 0; e < 3; ++e) {
                 const uint32_t a = vi[e], b = vi[e + 1];
                 if (!spilled) {

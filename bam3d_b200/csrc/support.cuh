@@ -207,8 +207,23 @@ B3_DEV V3 support_point(const Shape& s, V3 dir) {
 
 // SupportPoint::from_minkowski (minkowski/mod.rs:33-51): v = l - r, sup_a = l. sup_b is never read by the
 // reference and is not kept.
+// One out-of-line copy for the warp-per-pair kernels: with the support code inlined at every call site (two shapes x three
+// sites in the contact kernel, every primitive kind in each) those kernels stalled 43 % of the time on instruction fetch
+// (ncu: stall_no_inst) — 16 warps per SM at unrelated places of a code image far larger than the instruction cache.
+template <bool WARP>
+__device__ __noinline__ V3 support_point_outlined(const Shape& s, V3 dir) { return support_point<WARP>(s, dir); }
+
 template <bool WARP>
 B3_DEV void minkowski_support(const Shape& L, const Shape& R, V3 dir, V3& v, V3& sup_a) {
+#ifndef B3_INLINE_WARP_SUPPORT
+    if (WARP) {
+        V3 l = support_point_outlined<true>(L, dir);
+        V3 r = support_point_outlined<true>(R, -dir);
+        v = l - r;
+        sup_a = l;
+        return;
+    }
+#endif
     V3 l = support_point<WARP>(L, dir);
     V3 r = support_point<WARP>(R, -dir);
     v = l - r;
