@@ -213,12 +213,24 @@ B3_DEV V3 support_point(const Shape& s, V3 dir) {
 template <bool WARP>
 __device__ __noinline__ V3 support_point_outlined(const Shape& s, V3 dir) { return support_point<WARP>(s, dir); }
 
+// The polyhedron case of the warp kernels gets its own out-of-line function with BY-VALUE arguments (six registers): a
+// `const Shape&` parameter of a real call lives in local memory, and the callee's loads of the transform from it were a
+// quarter of the contact kernel's stall samples. The two small transforms stay inline at the call site.
+static __device__ __noinline__ V3 polyhedron_scan_outlined(const float4* __restrict__ verts, uint32_t nverts, V3 d) {
+    if (nverts & MESH_HALF_EDGE) return polyhedron_hill_climb(verts, nverts & ~MESH_HALF_EDGE, d);
+    return polyhedron_local_support<true>(verts, nverts, d);
+}
+B3_DEV V3 warp_support_point(const Shape& s, V3 dir) {
+    if (s.kind == K_POLYHEDRON) return transform_point3(s, polyhedron_scan_outlined(s.verts, s.nverts, inv_transform_vector3(s, dir)));
+    return support_point_outlined<true>(s, dir);
+}
+
 template <bool WARP>
 B3_DEV void minkowski_support(const Shape& L, const Shape& R, V3 dir, V3& v, V3& sup_a) {
 #ifndef B3_INLINE_WARP_SUPPORT
     if (WARP) {
-        V3 l = support_point_outlined<true>(L, dir);
-        V3 r = support_point_outlined<true>(R, -dir);
+        V3 l = warp_support_point(L, dir);
+        V3 r = warp_support_point(R, -dir);
         v = l - r;
         sup_a = l;
         return;
