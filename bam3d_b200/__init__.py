@@ -7,7 +7,8 @@ libbam3d_gpu.so.
 """
 from ._ffi import (Bam3dError, GjkSettings, KIND_CAPSULE, KIND_CUBOID, KIND_CYLINDER, KIND_PARTICLE, KIND_POLYHEDRON,  # noqa: F401
                    KIND_QUAD, KIND_SPHERE, STATUS_CAPACITY, STATUS_MAX_ITER, STATUS_MISS, STATUS_NAN, STATUS_OK,
-                   STATUS_REF_PANIC, STATUS_UNSUPPORTED, RAY_INTERSECTS, RAY_INTERSECTION, PARTICLE_SWEEP)
-from .api import (Capsule, CollisionStrategy, Contact, Context, ConvexPolyhedron, Cube, Cuboid, Cylinder, GJK,  # noqa: F401
+                   STATUS_REF_PANIC, STATUS_UNSUPPORTED, RAY_INTERSECTS, RAY_INTERSECTION, PARTICLE_SWEEP, FRAME_INTERSECT,
+                   FRAME_CONTACT, FRAME_TIME_OF_IMPACT)
+from .api import (Capsule, CollisionStrategy, Contact, Context, ConvexPolyhedron, Cube, Cuboid, Cylinder, FrameQueue, GJK,  # noqa: F401
                   MeshLibrary, Particle, Quad, Ray, ShapeSet, Sphere, default_context, intersection_transformed,
-                  intersects_transformed, particle_intersection_transformed, ray_cast_batch)
+                  intersects_transformed, particle_intersection_transformed, pinned_empty, ray_cast_batch)

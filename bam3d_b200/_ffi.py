@@ -17,6 +17,7 @@ KIND_PARTICLE, KIND_QUAD, KIND_SPHERE, KIND_CUBOID, KIND_CYLINDER, KIND_CAPSULE,
 STATUS_OK, STATUS_MISS, STATUS_MAX_ITER, STATUS_REF_PANIC, STATUS_NAN, STATUS_CAPACITY, STATUS_UNSUPPORTED = range(7)
 RAY_INTERSECTS, RAY_INTERSECTION, PARTICLE_SWEEP = 0, 1, 2
 FULL_RESOLUTION, COLLISION_ONLY = 0, 1
+FRAME_INTERSECT, FRAME_CONTACT, FRAME_TIME_OF_IMPACT = 0, 1, 2
 
 
 class GjkSettings(C.Structure):
@@ -83,6 +84,10 @@ SIGNATURES = {
     "bam3d_bvh_query_ray_closest": (_i32, [_vp, _vp, _vp, _u64, _vp, _vp]),
     "bam3d_bvh_find_collider_pairs": (_i32, [_vp, _vp, _vp, _vp, _u64, C.POINTER(_u64)]),
     "bam3d_frustum_from_mat4": (_i32, [_vp, _vp]),
+    "bam3d_frames_create": (_i32, [_vp, _vp, _vp, _vp, _vp, _u32, _vp, _u64, _u32, _i32, C.POINTER(_vp)]),
+    "bam3d_frames_submit": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _u64, _PS, _i32, _vp, _vp, C.POINTER(_u64)]),
+    "bam3d_frames_wait": (_i32, [_vp, _vp, _u64]),
+    "bam3d_frames_free": (None, [_vp, _vp]),
 }
 
 _lib = None

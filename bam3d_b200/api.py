@@ -263,6 +263,95 @@ class ShapeSet:
             self.handle = None
 
 
+def pinned_empty(ctx, shape, dtype):
+    """numpy array over page-locked host memory from bam3d_host_alloc (full-rate, asynchronous PCIe copies). The
+    memory is released when the array (and every view of it) is garbage-collected."""
+    import weakref
+    dtype = np.dtype(dtype)
+    count = int(np.prod(shape))
+    nbytes = max(1, count * dtype.itemsize)
+    ptr = C.c_void_p()
+    ctx.check(ctx._lib.bam3d_host_alloc(ctx.handle, nbytes, C.byref(ptr)))
+    buf = (C.c_char * nbytes).from_address(ptr.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
+    weakref.finalize(buf, ctx._lib.bam3d_host_free, ctx.handle, ptr)
+    return arr
+
+
+class FrameQueue:
+    """bam3d_frames: the per-frame sequence (new transforms -> narrow phase -> results in host memory) with `depth`
+    frames in flight, so that uploads and downloads run beside the kernels of the neighbouring frames.
+
+        q = FrameQueue(gjk, kind, params, xform0, max_pairs=n, depth=2)
+        f = q.submit_contact(strategy, xform, pairs, out_contacts, out_status)   # returns at once
+        ...
+        q.wait(f)                                                                # out_* now hold frame f's results
+
+    The arrays handed to submit_* must stay alive and untouched until wait(f) returns (use pinned_empty for them)."""
+
+    def __init__(self, gjk, kind, params, xform, mesh_id=None, meshes=None, max_pairs=0, depth=2, with_end=False):
+        self.gjk, self.ctx = gjk, gjk.ctx
+        kind = np.ascontiguousarray(kind, dtype=np.uint8)
+        self.n_shapes = len(kind)
+        params = np.ascontiguousarray(params, dtype=np.float32).reshape(self.n_shapes, 4)
+        xform = np.ascontiguousarray(xform, dtype=np.float32).reshape(self.n_shapes, 16)
+        mesh_id = None if mesh_id is None else np.ascontiguousarray(mesh_id, dtype=np.uint32)
+        self.meshes = meshes
+        self.max_pairs = int(max_pairs)
+        h = C.c_void_p()
+        self.ctx.check(self.ctx._lib.bam3d_frames_create(self.ctx.handle, _ptr(kind), _ptr(params), _ptr(xform), _ptr(mesh_id), self.n_shapes,
+                                                         meshes.handle if meshes is not None else None, self.max_pairs, int(depth),
+                                                         1 if with_end else 0, C.byref(h)))
+        self.handle = h
+        self._keep = {}  # frame -> arrays referenced by the copies in flight
+
+    def _submit(self, query, strategy, xform, xform_end, pairs, out_contacts, out_status):
+        def chk(a, dtype, shape):
+            if not (isinstance(a, np.ndarray) and a.dtype == dtype and a.flags.c_contiguous and a.size == int(np.prod(shape))):
+                raise ValueError(f"FrameQueue: expected a C-contiguous {np.dtype(dtype).name} array of {shape} elements")
+            return a
+        n = pairs.size // 2
+        chk(pairs, np.uint32, (n, 2)); chk(xform, np.float32, (self.n_shapes, 16)); chk(out_status, np.uint8, (n,))
+        if xform_end is not None:
+            chk(xform_end, np.float32, (self.n_shapes, 16))
+        if out_contacts is not None:
+            chk(out_contacts, np.float32, (n, 8))
+        frame = C.c_uint64(0)
+        self.ctx.check(self.ctx._lib.bam3d_frames_submit(self.ctx.handle, self.handle, query, _ptr(xform), _ptr(xform_end), _ptr(pairs), n,
+                                                         C.byref(self.gjk.settings), int(strategy), _ptr(out_contacts), _ptr(out_status),
+                                                         C.byref(frame)))
+        self._keep[frame.value] = (xform, xform_end, pairs, out_contacts, out_status)
+        return frame.value
+
+    def submit_intersect(self, xform, pairs, out_status):
+        return self._submit(_ffi.FRAME_INTERSECT, 0, xform, None, pairs, None, out_status)
+
+    def submit_contact(self, strategy, xform, pairs, out_contacts, out_status):
+        return self._submit(_ffi.FRAME_CONTACT, strategy, xform, None, pairs, out_contacts, out_status)
+
+    def submit_time_of_impact(self, xform_start, xform_end, pairs, out_contacts, out_status):
+        return self._submit(_ffi.FRAME_TIME_OF_IMPACT, 0, xform_start, xform_end, pairs, out_contacts, out_status)
+
+    def wait(self, frame):
+        try:
+            self.ctx.check(self.ctx._lib.bam3d_frames_wait(self.ctx.handle, self.handle, int(frame)))
+        finally:
+            for f in [f for f in self._keep if f <= frame]:
+                del self._keep[f]
+
+    def close(self):
+        if self.handle:
+            self.ctx._lib.bam3d_frames_free(self.ctx.handle, self.handle)
+            self.handle = None
+            self._keep.clear()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 # ---------------------------------------------------------------------------------------------------------
 # GJK
 # ---------------------------------------------------------------------------------------------------------

@@ -1083,4 +1083,170 @@ int32_t bam3d_bvh_find_collider_pairs(bam3d_ctx* ctx, const bam3d_bvh* t, const 
     return BAM3D_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// frame queue: set_transforms + narrow phase + results, `depth` frames in flight
+// ------------------------------------------------------------------------------------------------------------
+// Three streams: host->device copies and the pack kernel on `s_in`, the narrow-phase kernels on the ctx stream (they
+// share the ctx's scratch, so frames compute one after the other), device->host copies on `s_out`. Frame k+1's
+// upload and frame k-1's download therefore run beside frame k's kernels; a slot is reused once its download is done.
+struct bam3d_frames {
+    struct Slot {
+        bam3d_shapes* shapes = nullptr;
+        bam3d_shapes* shapes_end = nullptr;  // time of impact only
+        uint32_t* d_pairs = nullptr;
+        uint8_t* d_status = nullptr;
+        bam3d_contact* d_contacts = nullptr;
+        uint32_t* d_err = nullptr;   // pack_shapes_kernel's flags for this frame
+        uint32_t* h_err = nullptr;   // pinned copy, read by bam3d_frames_wait
+        cudaEvent_t uploaded = nullptr, computed = nullptr, downloaded = nullptr;
+        uint64_t frame = ~0ull;      // frame number in flight / last completed in this slot
+        bool in_flight = false;
+        int32_t launch_rc = BAM3D_OK;
+    };
+    std::vector<Slot> slots;
+    uint64_t max_pairs = 0, next_frame = 0;
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+};
+
+static int32_t frames_finish_slot(bam3d_ctx* ctx, bam3d_frames::Slot& sl) {
+    if (!sl.in_flight) return BAM3D_OK;
+    cudaError_t e = cudaEventSynchronize(sl.downloaded);
+    sl.in_flight = false;
+    if (e != cudaSuccess) return b3_fail(ctx, BAM3D_ERR_CUDA, "bam3d_frames_wait", e);
+    if (sl.launch_rc) return sl.launch_rc;
+    if (*sl.h_err & 1u) return b3_fail(ctx, BAM3D_ERR_NON_AFFINE, "a transform's 4th row is not (0,0,0,1)", cudaSuccess);
+    if (*sl.h_err) return b3_fail(ctx, BAM3D_ERR_ARG, "pack_shapes_kernel rejected the frame's shapes", cudaSuccess);
+    return BAM3D_OK;
+}
+
+void bam3d_frames_free(bam3d_ctx* ctx, bam3d_frames* F) {
+    if (!F) return;
+    if (ctx) cudaSetDevice(ctx->device);
+    for (auto& sl : F->slots) {
+        if (sl.in_flight && sl.downloaded) cudaEventSynchronize(sl.downloaded);
+        bam3d_shapes_free(ctx, sl.shapes);
+        bam3d_shapes_free(ctx, sl.shapes_end);
+        if (sl.d_pairs) cudaFree(sl.d_pairs);
+        if (sl.d_status) cudaFree(sl.d_status);
+        if (sl.d_contacts) cudaFree(sl.d_contacts);
+        if (sl.d_err) cudaFree(sl.d_err);
+        if (sl.h_err) cudaFreeHost(sl.h_err);
+        if (sl.uploaded) cudaEventDestroy(sl.uploaded);
+        if (sl.computed) cudaEventDestroy(sl.computed);
+        if (sl.downloaded) cudaEventDestroy(sl.downloaded);
+    }
+    if (F->s_in) { cudaStreamSynchronize(F->s_in); cudaStreamDestroy(F->s_in); }
+    if (F->s_out) { cudaStreamSynchronize(F->s_out); cudaStreamDestroy(F->s_out); }
+    delete F;
+}
+
+int32_t bam3d_frames_create(bam3d_ctx* ctx, const uint8_t* kind, const float* params, const float* xform, const uint32_t* mesh_id,
+                            uint32_t n_shapes, const bam3d_meshes* meshes, uint64_t max_pairs, uint32_t depth, int32_t with_end,
+                            bam3d_frames** out) {
+    if (!ctx || !out) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_frames_create: null argument", cudaSuccess);
+    *out = nullptr;
+    if (depth < 1 || depth > 8) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_frames_create: depth must be 1..8", cudaSuccess);
+    int32_t rc;
+    if ((rc = check_n(ctx, max_pairs))) return rc;
+    CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
+    bam3d_frames* F = new (std::nothrow) bam3d_frames();
+    if (!F) return BAM3D_ERR_OOM;
+    F->max_pairs = max_pairs;
+    F->slots.resize(depth);
+    cudaError_t e = cudaSuccess;
+    if ((e = cudaStreamCreateWithFlags(&F->s_in, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&F->s_out, cudaStreamNonBlocking)) != cudaSuccess) {
+        bam3d_frames_free(ctx, F);
+        return b3_fail(ctx, BAM3D_ERR_CUDA, "cudaStreamCreate(frames)", e);
+    }
+    const size_t np = max_pairs ? max_pairs : 1;
+    for (auto& sl : F->slots) {
+        // the synchronous upload validates kinds, mesh ids and the initial transforms once; a frame can then only fail on
+        // a non-affine transform, which is reported by bam3d_frames_wait for that frame
+        if ((rc = bam3d_shapes_upload(ctx, kind, params, xform, mesh_id, n_shapes, meshes, &sl.shapes)) ||
+            (with_end && (rc = bam3d_shapes_upload(ctx, kind, params, xform, mesh_id, n_shapes, meshes, &sl.shapes_end)))) {
+            bam3d_frames_free(ctx, F);
+            return rc;
+        }
+        if ((e = cudaMalloc(&sl.d_pairs, np * 8)) != cudaSuccess || (e = cudaMalloc(&sl.d_status, np)) != cudaSuccess ||
+            (e = cudaMalloc(&sl.d_contacts, np * 32)) != cudaSuccess || (e = cudaMalloc(&sl.d_err, 8)) != cudaSuccess ||
+            (e = cudaMallocHost(&sl.h_err, 8)) != cudaSuccess ||
+            (e = cudaEventCreateWithFlags(&sl.uploaded, cudaEventDisableTiming)) != cudaSuccess ||
+            (e = cudaEventCreateWithFlags(&sl.computed, cudaEventDisableTiming)) != cudaSuccess ||
+            (e = cudaEventCreateWithFlags(&sl.downloaded, cudaEventDisableTiming)) != cudaSuccess) {
+            bam3d_frames_free(ctx, F);
+            return b3_fail(ctx, BAM3D_ERR_OOM, "bam3d_frames_create: device / pinned allocation", e);
+        }
+        *sl.h_err = 0;
+    }
+    *out = F;
+    return BAM3D_OK;
+}
+
+int32_t bam3d_frames_submit(bam3d_ctx* ctx, bam3d_frames* F, int32_t query, const float* xform, const float* xform_end,
+                            const uint32_t* pairs, uint64_t n, const bam3d_gjk_settings* settings, int32_t strategy,
+                            bam3d_contact* out_contacts, uint8_t* out_status, uint64_t* out_frame) {
+    if (!ctx || !F || !xform || (n && (!pairs || !out_status))) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_frames_submit: null argument", cudaSuccess);
+    if (query < BAM3D_FRAME_INTERSECT || query > BAM3D_FRAME_TIME_OF_IMPACT) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_frames_submit: unknown query", cudaSuccess);
+    if (query != BAM3D_FRAME_INTERSECT && n && !out_contacts) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_frames_submit: out_contacts is null", cudaSuccess);
+    if (n > F->max_pairs) return b3_fail(ctx, BAM3D_ERR_CAPACITY, "bam3d_frames_submit: more pairs than max_pairs", cudaSuccess);
+    bam3d_frames::Slot& sl = F->slots[F->next_frame % F->slots.size()];
+    if (query == BAM3D_FRAME_TIME_OF_IMPACT && (!xform_end || !sl.shapes_end))
+        return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_frames_submit: time of impact needs xform_end and a queue created with with_end", cudaSuccess);
+    CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
+    // back-pressure: the frame `depth` submissions ago must have left this slot (its status is what bam3d_frames_wait on
+    // it returns; a caller that skipped the wait loses that frame's error code, not its data)
+    if (sl.in_flight) (void)frames_finish_slot(ctx, sl);
+    const uint32_t ns = sl.shapes->n;
+    const uint32_t n_meshes = sl.shapes->meshes ? sl.shapes->meshes->n_meshes : 0;
+    sl.frame = F->next_frame++;
+    sl.launch_rc = BAM3D_OK;
+    if (out_frame) *out_frame = sl.frame;
+    // upload + pack on the copy-in stream
+    CU_TRY(cudaMemsetAsync(sl.d_err, 0, 4, F->s_in), "cudaMemsetAsync(err)");
+    if (ns) {
+        CU_TRY(cudaMemcpyAsync(sl.shapes->d_xform, xform, (size_t)ns * 64, cudaMemcpyHostToDevice, F->s_in), "cudaMemcpyAsync(xform)");
+        ctx->launches += launch_pack_shapes(F->s_in, sl.shapes->d_kind, sl.shapes->d_params, sl.shapes->d_xform, sl.shapes->d_mesh_id, ns,
+                                            n_meshes, sl.shapes->recs, sl.shapes->meta, sl.d_err);
+        if (query == BAM3D_FRAME_TIME_OF_IMPACT) {
+            CU_TRY(cudaMemcpyAsync(sl.shapes_end->d_xform, xform_end, (size_t)ns * 64, cudaMemcpyHostToDevice, F->s_in), "cudaMemcpyAsync(xform_end)");
+            ctx->launches += launch_pack_shapes(F->s_in, sl.shapes_end->d_kind, sl.shapes_end->d_params, sl.shapes_end->d_xform,
+                                                sl.shapes_end->d_mesh_id, ns, n_meshes, sl.shapes_end->recs, sl.shapes_end->meta, sl.d_err);
+        }
+    }
+    if (n) CU_TRY(cudaMemcpyAsync(sl.d_pairs, pairs, n * 8, cudaMemcpyHostToDevice, F->s_in), "cudaMemcpyAsync(pairs)");
+    CU_TRY(cudaEventRecord(sl.uploaded, F->s_in), "cudaEventRecord");
+    // kernels on the ctx stream
+    CU_TRY(cudaStreamWaitEvent(ctx->stream, sl.uploaded, 0), "cudaStreamWaitEvent");
+    int32_t rc = BAM3D_OK;
+    if (n) {
+        if (query == BAM3D_FRAME_INTERSECT) rc = bam3d_gjk_intersect_dev(ctx, sl.shapes, sl.d_pairs, n, settings, sl.d_status);
+        else if (query == BAM3D_FRAME_CONTACT) rc = bam3d_gjk_contact_dev(ctx, sl.shapes, sl.d_pairs, n, settings, strategy, sl.d_contacts, sl.d_status);
+        else rc = bam3d_gjk_time_of_impact_dev(ctx, sl.shapes, sl.shapes_end, sl.d_pairs, n, settings, sl.d_contacts, sl.d_status);
+    }
+    CU_TRY(cudaEventRecord(sl.computed, ctx->stream), "cudaEventRecord");
+    if (rc) {  // nothing of this frame is copied back; the slot is free again once the upload has drained
+        cudaEventSynchronize(sl.computed);
+        return rc;
+    }
+    // results on the copy-out stream
+    CU_TRY(cudaStreamWaitEvent(F->s_out, sl.computed, 0), "cudaStreamWaitEvent");
+    if (n && query != BAM3D_FRAME_INTERSECT) CU_TRY(cudaMemcpyAsync(out_contacts, sl.d_contacts, n * 32, cudaMemcpyDeviceToHost, F->s_out), "cudaMemcpyAsync(contacts)");
+    if (n) CU_TRY(cudaMemcpyAsync(out_status, sl.d_status, n, cudaMemcpyDeviceToHost, F->s_out), "cudaMemcpyAsync(status)");
+    CU_TRY(cudaMemcpyAsync(sl.h_err, sl.d_err, 4, cudaMemcpyDeviceToHost, F->s_out), "cudaMemcpyAsync(err)");
+    CU_TRY(cudaEventRecord(sl.downloaded, F->s_out), "cudaEventRecord");
+    sl.in_flight = true;
+    return BAM3D_OK;
+}
+
+int32_t bam3d_frames_wait(bam3d_ctx* ctx, bam3d_frames* F, uint64_t frame) {
+    if (!ctx || !F) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_frames_wait: null argument", cudaSuccess);
+    if (frame >= F->next_frame) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_frames_wait: frame was never submitted", cudaSuccess);
+    bam3d_frames::Slot& sl = F->slots[frame % F->slots.size()];
+    if (sl.frame != frame) return BAM3D_OK;  // an older frame: its slot was reused, so it completed long ago
+    CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
+    return frames_finish_slot(ctx, sl);
+}
+
 }  // extern "C"

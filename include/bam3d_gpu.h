@@ -269,6 +269,34 @@ int32_t bam3d_bvh_find_collider_pairs(bam3d_ctx* ctx, const bam3d_bvh* bvh, cons
 /* Frustum::from_mat4 (frustum.rs:46-75) on the host; out_planes = 6 x (n.xyz, d). Returns BAM3D_ERR_ARG for None. */
 int32_t bam3d_frustum_from_mat4(const float* mat4_cols, float* out_planes);
 
+/* ---- frame queue: the per-frame sequence with `depth` frames in flight -------------------------------------- */
+/* A simulation loop calls, every frame: new Mat4 for every shape (bam3d_shapes_set_transforms), the narrow phase over the
+ * frame's candidate pairs (GJK::intersect / intersection / intersection_time_of_impact, gjk/mod.rs:74-113,:317-341,:130-217),
+ * results back in host memory. Done one call after the other, the PCIe copies (64 B per shape in, 33 B per pair out) and the
+ * kernels take turns. A frame queue keeps `depth` frames in flight instead: host->device copies + the pack kernel on one
+ * stream, the narrow-phase kernels on the ctx stream, device->host copies on a third, so that frame k+1's upload and frame
+ * k-1's download run beside frame k's kernels. Results are bit-identical to the one-call-after-the-other sequence.
+ * Host buffers should be page-locked (bam3d_host_alloc) — pageable memory still works but copies synchronously — and
+ * must stay untouched from submit until bam3d_frames_wait for that frame returns.
+ * create: kind / params / mesh_id / meshes as for bam3d_shapes_upload, `xform` = initial transforms (validated
+ * synchronously together with kinds and mesh ids); with_end != 0 also allocates the end-of-step sets time of impact needs. */
+typedef struct bam3d_frames bam3d_frames;
+#define BAM3D_FRAME_INTERSECT 0        /* bam3d_gjk_intersect: out_status only (out_contacts may be NULL) */
+#define BAM3D_FRAME_CONTACT 1          /* bam3d_gjk_contact with `strategy` */
+#define BAM3D_FRAME_TIME_OF_IMPACT 2   /* bam3d_gjk_time_of_impact between xform and xform_end */
+int32_t bam3d_frames_create(bam3d_ctx* ctx, const uint8_t* kind, const float* params, const float* xform, const uint32_t* mesh_id,
+                            uint32_t n_shapes, const bam3d_meshes* meshes, uint64_t max_pairs, uint32_t depth, int32_t with_end,
+                            bam3d_frames** out);
+/* Enqueue one frame and return at once; *out_frame (may be NULL) = its number (0, 1, 2, ... in submission order). Blocks only
+ * while the frame `depth` submissions ago is still in flight. xform_end is read for BAM3D_FRAME_TIME_OF_IMPACT only. */
+int32_t bam3d_frames_submit(bam3d_ctx* ctx, bam3d_frames* frames, int32_t query, const float* xform, const float* xform_end,
+                            const uint32_t* pairs, uint64_t n, const bam3d_gjk_settings* settings, int32_t strategy,
+                            bam3d_contact* out_contacts, uint8_t* out_status, uint64_t* out_frame);
+/* Block until that frame's results are in the host buffers given to its submit. Returns the frame's own status:
+ * BAM3D_ERR_NON_AFFINE if one of its transforms had a 4th row other than (0,0,0,1) (its results are then meaningless). */
+int32_t bam3d_frames_wait(bam3d_ctx* ctx, bam3d_frames* frames, uint64_t frame);
+void bam3d_frames_free(bam3d_ctx* ctx, bam3d_frames* frames);
+
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
 uint64_t bam3d_ctx_launch_count(const bam3d_ctx* ctx);
 

@@ -379,3 +379,92 @@ def test_compound_shapes_parity(ctx, oracle):
         assert hit.sum() > 20
         assert_f32_equal("complex toi", c[:, [0, 1, 2, 3, 7]], oc[:, [0, 1, 2, 3, 7]], hit)
         assert (np.isclose(c[hit][:, 4:7], oc[hit][:, 4:7], rtol=REL_TOL, atol=1e-4) | np.isnan(oc[hit][:, 4:7])).all()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# frame queue (bam3d_frames_*): several frames in flight == the same frames one call after the other
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("depth", [1, 2, 3])
+def test_frame_queue_matches_synchronous_calls(ctx, oracle, depth):
+    """Six frames of moving shapes through a FrameQueue (uploads, kernels and downloads of neighbouring frames overlap)
+    against set_transforms + the synchronous host-buffer calls, and frame 0 against the CPU oracle: bit-identical."""
+    scene = scenes.mixed_pairs(20_000, s=1.5, seed=0xB3D000F7)
+    n_shapes, n = len(scene["kind"]), len(scene["pairs"])
+    gjk = b3.GJK.new(ctx)
+    frames = [scene["xform"]] + [scenes.end_transforms(scene, span=0.4 * (k + 1)) for k in range(5)]
+    # synchronous sequence
+    shapes = shapes_of(ctx, scene)
+    want = []
+    for x in frames:
+        shapes.set_transforms(x)
+        c, st = gjk.intersection_batch(b3.CollisionStrategy.FullResolution, shapes, scene["pairs"])
+        want.append((c.copy(), st.copy(), gjk.intersect_batch(shapes, scene["pairs"]).copy()))
+    oc, _, ost = oracle.contact(scene, nthreads=8)
+    assert np.array_equal(want[0][1], ost)
+    assert_f32_equal("frame 0 contact vs oracle", want[0][0][:, 0:7], oc[:, 0:7], ost == 0)
+    # queued: a contact frame and an intersect frame per transform set, each with its own pinned buffers
+    q = b3.FrameQueue(gjk, scene["kind"], scene["params"], scene["xform"], max_pairs=n, depth=depth)
+    h_pairs = b3.pinned_empty(ctx, (n, 2), np.uint32)
+    h_pairs[:] = scene["pairs"]
+    tickets = []
+    for k, x in enumerate(frames):
+        hx = b3.pinned_empty(ctx, (n_shapes, 16), np.float32)
+        hx[:] = x.reshape(n_shapes, 16)
+        hc, hs, hs2 = b3.pinned_empty(ctx, (n, 8), np.float32), b3.pinned_empty(ctx, (n,), np.uint8), b3.pinned_empty(ctx, (n,), np.uint8)
+        hc[:] = np.nan
+        hs[:] = 0xEE
+        hs2[:] = 0xEE
+        f1 = q.submit_contact(b3.CollisionStrategy.FullResolution, hx, h_pairs, hc, hs)
+        f2 = q.submit_intersect(hx, h_pairs, hs2)
+        assert (f1, f2) == (2 * k, 2 * k + 1)
+        tickets.append((f1, f2, hc, hs, hs2))
+    for k in reversed(range(len(frames))):  # waiting out of order is allowed
+        f1, f2, hc, hs, hs2 = tickets[k]
+        q.wait(f2)
+        q.wait(f1)
+        assert np.array_equal(hs, want[k][1]), f"frame {k}: status"
+        assert np.array_equal(bits(hc), bits(want[k][0])), f"frame {k}: contacts"
+        assert np.array_equal(hs2, want[k][2]), f"frame {k}: intersect status"
+    q.close()
+
+
+def test_frame_queue_time_of_impact_errors_and_empty(ctx, oracle):
+    scene = scenes.mixed_pairs(4_000, s=1.5, seed=0xB3D000F8)
+    n_shapes, n = len(scene["kind"]), len(scene["pairs"])
+    gjk = b3.GJK.new(ctx)
+    x0 = np.ascontiguousarray(scene["xform"], dtype=np.float32).reshape(n_shapes, 16)
+    x1 = np.ascontiguousarray(scenes.end_transforms(scene, span=3.0), dtype=np.float32).reshape(n_shapes, 16)
+    s0, s1 = shapes_of(ctx, scene), shapes_of(ctx, scene, x1)
+    wc, wst = gjk.intersection_time_of_impact_batch(s0, s1, scene["pairs"])
+    q = b3.FrameQueue(gjk, scene["kind"], scene["params"], x0, max_pairs=n, depth=2, with_end=True)
+    pairs = np.ascontiguousarray(scene["pairs"], dtype=np.uint32)
+    hc, hs = np.full((n, 8), np.nan, dtype=np.float32), np.full(n, 0xEE, dtype=np.uint8)  # pageable memory also works
+    f = q.submit_time_of_impact(x0, x1, pairs, hc, hs)
+    # an empty frame and a frame with a non-affine transform behind it
+    e_st = np.zeros(0, dtype=np.uint8)
+    fe = q.submit_intersect(x0, np.zeros((0, 2), dtype=np.uint32), e_st)
+    bad = x0.copy()
+    bad[7, 3] = 0.5
+    hs_bad = np.zeros(n, dtype=np.uint8)
+    fb = q.submit_intersect(bad, pairs, hs_bad)
+    hs_ok = np.full(n, 0xEE, dtype=np.uint8)
+    fo = q.submit_intersect(x0, pairs, hs_ok)
+    q.wait(f)
+    assert np.array_equal(hs, wst)
+    assert np.array_equal(bits(hc), bits(wc))
+    q.wait(fe)
+    with pytest.raises(b3.Bam3dError) as ei:
+        q.wait(fb)
+    assert ei.value.code == -3  # BAM3D_ERR_NON_AFFINE, as bam3d_shapes_set_transforms reports it
+    q.wait(fo)  # the queue keeps working after a rejected frame
+    assert np.array_equal(hs_ok, gjk.intersect_batch(s0, pairs))
+    # argument checks
+    with pytest.raises(b3.Bam3dError):
+        q.submit_intersect(x0, np.zeros((n + 1, 2), dtype=np.uint32), np.zeros(n + 1, dtype=np.uint8))  # > max_pairs
+    q2 = b3.FrameQueue(gjk, scene["kind"], scene["params"], x0, max_pairs=n, depth=2)
+    with pytest.raises(b3.Bam3dError):
+        q2.submit_time_of_impact(x0, x1, pairs, hc, hs)  # created without with_end
+    with pytest.raises(b3.Bam3dError):
+        b3.FrameQueue(gjk, scene["kind"], scene["params"], x0, max_pairs=n, depth=0)
+    q.close()
+    q2.close()
