@@ -164,6 +164,8 @@ public:
         return intersection_time_of_impact_batch(s0, s1, {{0, 1}})[0];
     }
 
+    const bam3d_gjk_settings& settings() const { return s_; }
+
 private:
     static const uint32_t* flat(const std::vector<Pair>& p) { return reinterpret_cast<const uint32_t*>(p.data()); }
     static std::vector<std::optional<Contact>> to_optional(CollisionStrategy strategy, const std::vector<bam3d_contact>& c, const std::vector<uint8_t>& st) {
@@ -176,6 +178,58 @@ private:
     }
     const Context& ctx_;
     bam3d_gjk_settings s_;
+};
+
+// The per-frame sequence with several frames in flight (bam3d_frames_*): new Mat4 for every shape, the narrow phase over
+// the frame's pairs, results in host memory — uploads and downloads run beside the kernels of the neighbouring frames.
+// The buffers given to submit_* must stay alive and untouched until wait(frame) returns.
+class FrameQueue {
+public:
+    FrameQueue(const Context& ctx, const std::vector<Primitive3>& prims, const std::vector<Mat4>& xforms, uint64_t max_pairs,
+               uint32_t depth = 2, bool with_end = false) : ctx_(ctx) {
+        const uint32_t n = (uint32_t)prims.size();
+        std::vector<uint8_t> kind(n);
+        std::vector<float> params(4 * (size_t)n), verts;
+        std::vector<uint32_t> mesh_id(n, 0), offsets{0};
+        for (uint32_t i = 0; i < n; ++i) {
+            kind[i] = prims[i].kind;
+            for (int k = 0; k < 4; ++k) params[4 * i + k] = prims[i].params[k];
+            if (prims[i].kind == BAM3D_KIND_POLYHEDRON) {
+                mesh_id[i] = (uint32_t)offsets.size() - 1;
+                verts.insert(verts.end(), prims[i].vertices.begin(), prims[i].vertices.end());
+                offsets.push_back((uint32_t)(verts.size() / 3));
+            }
+        }
+        if (offsets.size() > 1) ctx_.check(bam3d_meshes_upload(ctx_.handle(), verts.data(), offsets.data(), (uint32_t)offsets.size() - 1, &meshes_));
+        ctx_.check(bam3d_frames_create(ctx_.handle(), kind.data(), params.data(), xforms.data()->data(), mesh_id.data(), n, meshes_, max_pairs,
+                                       depth, with_end ? 1 : 0, &h_));
+    }
+    ~FrameQueue() { bam3d_frames_free(ctx_.handle(), h_); bam3d_meshes_free(ctx_.handle(), meshes_); }
+    FrameQueue(const FrameQueue&) = delete;
+    FrameQueue& operator=(const FrameQueue&) = delete;
+    uint64_t submit_intersect(const GJK& gjk, const std::vector<Mat4>& xforms, const std::vector<Pair>& pairs, uint8_t* out_status) {
+        return submit(BAM3D_FRAME_INTERSECT, gjk, xforms.data()->data(), nullptr, pairs, CollisionStrategy::FullResolution, nullptr, out_status);
+    }
+    uint64_t submit_intersection(const GJK& gjk, CollisionStrategy strategy, const std::vector<Mat4>& xforms, const std::vector<Pair>& pairs,
+                                 bam3d_contact* out_contacts, uint8_t* out_status) {
+        return submit(BAM3D_FRAME_CONTACT, gjk, xforms.data()->data(), nullptr, pairs, strategy, out_contacts, out_status);
+    }
+    uint64_t submit_intersection_time_of_impact(const GJK& gjk, const std::vector<Mat4>& start, const std::vector<Mat4>& end,
+                                                const std::vector<Pair>& pairs, bam3d_contact* out_contacts, uint8_t* out_status) {
+        return submit(BAM3D_FRAME_TIME_OF_IMPACT, gjk, start.data()->data(), end.data()->data(), pairs, CollisionStrategy::FullResolution, out_contacts, out_status);
+    }
+    void wait(uint64_t frame) { ctx_.check(bam3d_frames_wait(ctx_.handle(), h_, frame)); }
+private:
+    uint64_t submit(int32_t query, const GJK& gjk, const float* x0, const float* x1, const std::vector<Pair>& pairs, CollisionStrategy strategy,
+                    bam3d_contact* out_contacts, uint8_t* out_status) {
+        uint64_t frame = 0;
+        ctx_.check(bam3d_frames_submit(ctx_.handle(), h_, query, x0, x1, reinterpret_cast<const uint32_t*>(pairs.data()), pairs.size(),
+                                       &gjk.settings(), (int32_t)strategy, out_contacts, out_status, &frame));
+        return frame;
+    }
+    const Context& ctx_;
+    bam3d_frames* h_ = nullptr;
+    bam3d_meshes* meshes_ = nullptr;
 };
 
 struct Aabb3 { Vec3 min, max; };  // volume/aabb/aabb3.rs:15-21 (6 contiguous f32)

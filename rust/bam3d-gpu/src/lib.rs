@@ -34,6 +34,14 @@ extern "C" {
                                   count: *mut u64, shard: u32, n_shards: u32) -> i32;
     fn bam3d_ray_cast(c: *mut ctx, s: *const c_void, rays: *const f32, n_rays: u64, casts: *const u32, n: u64, query: i32,
                       points: *mut f32, status: *mut u8) -> i32;
+    fn bam3d_host_alloc(c: *mut ctx, bytes: u64, out: *mut *mut c_void) -> i32;
+    fn bam3d_host_free(c: *mut ctx, p: *mut c_void);
+    fn bam3d_frames_create(c: *mut ctx, kind: *const u8, params: *const f32, xform: *const f32, mesh_id: *const u32, n_shapes: u32,
+                           meshes: *const c_void, max_pairs: u64, depth: u32, with_end: i32, out: *mut *mut c_void) -> i32;
+    fn bam3d_frames_submit(c: *mut ctx, f: *mut c_void, query: i32, xform: *const f32, xform_end: *const f32, pairs: *const u32, n: u64,
+                           cfg: *const GjkSettings, strategy: i32, out: *mut RawContact, status: *mut u8, frame: *mut u64) -> i32;
+    fn bam3d_frames_wait(c: *mut ctx, f: *mut c_void, frame: u64) -> i32;
+    fn bam3d_frames_free(c: *mut ctx, f: *mut c_void);
 }
 
 /// Batched `ContinuousTransformed<Ray> for Primitive3` (ray.rs:68-78): `casts[i] = (ray index, shape index)`.
@@ -95,6 +103,51 @@ pub fn intersection_batch(ctx: &Context, strategy: &CollisionStrategy, shapes: &
                                             Vec3::new(c.contact_point[0], c.contact_point[1], c.contact_point[2]));
         k.time_of_impact = c.time_of_impact; Some(k) } else { None }).collect())
 }
+
+/// Page-locked host buffer (`bam3d_host_alloc`): what a frame's transforms / pairs / results should live in so that the
+/// PCIe copies are asynchronous and run at full rate.
+pub struct Pinned<'a, T: Copy> { ctx: &'a Context, p: *mut T, len: usize }
+impl<'a, T: Copy> Pinned<'a, T> {
+    pub fn new(ctx: &'a Context, len: usize) -> Result<Self, i32> {
+        let mut p = std::ptr::null_mut();
+        let rc = unsafe { bam3d_host_alloc(ctx.0, (len.max(1) * std::mem::size_of::<T>()) as u64, &mut p) };
+        if rc == 0 { Ok(Pinned { ctx, p: p as *mut T, len }) } else { Err(rc) }
+    }
+    pub fn as_slice(&self) -> &[T] { unsafe { std::slice::from_raw_parts(self.p, self.len) } }
+    pub fn as_mut_slice(&mut self) -> &mut [T] { unsafe { std::slice::from_raw_parts_mut(self.p, self.len) } }
+}
+impl<'a, T: Copy> Drop for Pinned<'a, T> { fn drop(&mut self) { unsafe { bam3d_host_free(self.ctx.0, self.p as *mut c_void) } } }
+
+/// The per-frame sequence of a simulation loop — new `Mat4` for every shape, `GJK::intersection` over the frame's pairs,
+/// contacts back in host memory — with `depth` frames in flight (`bam3d_frames_*`): frame k+1's upload and frame k-1's
+/// download run beside frame k's kernels. `submit` borrows its buffers until `wait(frame)` returns, which is why they are
+/// `Pinned` values owned by the caller for the queue's lifetime.
+pub struct FrameQueue<'a> { ctx: &'a Context, h: *mut c_void, cfg: GjkSettings }
+impl<'a> FrameQueue<'a> {
+    pub fn new(ctx: &'a Context, shapes: &[(Primitive3, Mat4)], max_pairs: usize, depth: u32) -> Result<Self, i32> {
+        let n = shapes.len();
+        let (mut kind, mut params, mut xf) = (Vec::with_capacity(n), Vec::with_capacity(4 * n), Vec::with_capacity(16 * n));
+        for (p, t) in shapes { let (k, q) = pack(p); kind.push(k); params.extend_from_slice(&q); xf.extend_from_slice(&t.to_cols_array()); }
+        let mut cfg = GjkSettings { distance_tolerance: 0., continuous_tolerance: 0., epa_tolerance: 0., max_iterations: 0, toi_iteration_cap: 0 };
+        unsafe { bam3d_default_settings(&mut cfg) };
+        let mut h = std::ptr::null_mut();
+        let rc = unsafe { bam3d_frames_create(ctx.0, kind.as_ptr(), params.as_ptr(), xf.as_ptr(), std::ptr::null(), n as u32, std::ptr::null(),
+                                              max_pairs as u64, depth, 0, &mut h) };
+        if rc == 0 { Ok(FrameQueue { ctx, h, cfg }) } else { Err(rc) }
+    }
+    /// Enqueue `GJK::intersection(strategy, ..)` for every pair under this frame's transforms; returns the frame number.
+    pub fn submit_intersection(&mut self, strategy: &CollisionStrategy, xform: &Pinned<[f32; 16]>, pairs: &Pinned<(u32, u32)>,
+                               out: &mut Pinned<RawContact>, status: &mut Pinned<u8>) -> Result<u64, i32> {
+        let s = match strategy { CollisionStrategy::FullResolution => 0, CollisionStrategy::CollisionOnly => 1 };
+        let mut frame = 0u64;
+        let rc = unsafe { bam3d_frames_submit(self.ctx.0, self.h, 1, xform.p as *const f32, std::ptr::null(), pairs.p as *const u32, pairs.len as u64,
+                                              &self.cfg, s, out.p, status.p, &mut frame) };
+        if rc == 0 { Ok(frame) } else { Err(rc) }
+    }
+    /// Block until that frame's contacts and status are in the buffers given to its `submit_intersection`.
+    pub fn wait(&mut self, frame: u64) -> Result<(), i32> { let rc = unsafe { bam3d_frames_wait(self.ctx.0, self.h, frame) }; if rc == 0 { Ok(()) } else { Err(rc) } }
+}
+impl<'a> Drop for FrameQueue<'a> { fn drop(&mut self) { unsafe { bam3d_frames_free(self.ctx.0, self.h) } } }
 
 /// `SweepAndPrune3::find_collider_pairs` on the device: re-sorts `shapes` like the reference and returns indices into it.
 pub fn sap_find_collider_pairs(ctx: &Context, sweep_axis: &mut usize, shapes: &mut [Aabb3]) -> Result<Vec<(usize, usize)>, i32> {

@@ -64,6 +64,28 @@ int main() {
         CHECK(pairs.size() == 2);
         if (pairs.size() == 2) { CHECK(pairs[0].first == 0 && pairs[0].second == 1); CHECK(pairs[1].first == 1 && pairs[1].second == 2); }
     }
+    {   // FrameQueue: three frames of test_gjk_3d_hit's cuboids moving apart, two in flight, against the one-shot calls
+        std::vector<Primitive3> prims = {Primitive3::Cuboid(10, 10, 10), Primitive3::Cuboid(10, 10, 10)};
+        std::vector<std::vector<Mat4>> frames = {{transform_3d(15, 0, 0), transform_3d(7, 2, 0)}, {transform_3d(15, 0, 0), transform_3d(6, 2, 0)},
+                                                 {transform_3d(15, 0, 0), transform_3d(4, 2, 0)}};
+        std::vector<Pair> pairs = {{0, 1}};
+        FrameQueue q(ctx, prims, frames[0], 1, 2);
+        bam3d_contact c[3];
+        uint8_t st[3] = {0xEE, 0xEE, 0xEE};
+        uint64_t ticket[3];
+        for (int k = 0; k < 3; ++k) ticket[k] = q.submit_intersection(gjk, CollisionStrategy::FullResolution, frames[k], pairs, &c[k], &st[k]);
+        for (int k = 0; k < 3; ++k) {
+            q.wait(ticket[k]);
+            auto want = gjk.intersection(CollisionStrategy::FullResolution, prims[0], frames[k][0], prims[1], frames[k][1]);
+            CHECK((st[k] == BAM3D_STATUS_OK) == want.has_value());
+            if (want && st[k] == BAM3D_STATUS_OK) {
+                CHECK(c[k].penetration_depth == want->penetration_depth && c[k].normal[0] == want->normal[0]);
+                CHECK(c[k].contact_point[0] == want->contact_point[0] && c[k].contact_point[1] == want->contact_point[1] && c[k].contact_point[2] == want->contact_point[2]);
+            }
+        }
+        CHECK(st[0] == BAM3D_STATUS_OK && c[0].penetration_depth == 2.f);  // frame 0 is test_gjk_3d_hit
+        CHECK(st[2] != BAM3D_STATUS_OK);                                   // 15 - 4 = 11 > 10: separated
+    }
     std::printf("kat_gpu: %s\n", fails ? "FAILED" : "all passed");
     return fails ? 1 : 0;
 }
