@@ -321,6 +321,12 @@ __global__ void __launch_bounds__(TPB) gjk_intersect_survivors_kernel(ShapeSetDe
 #ifndef B3_WARP_MIN_BLOCKS
 #define B3_WARP_MIN_BLOCKS 1
 #endif
+#ifndef B3_WARP_SHAPES_SMEM
+#define B3_WARP_SHAPES_SMEM 0
+#endif
+// dynamic shared memory of the warp-per-pair contact kernel: the polytope slices, then (B3_WARP_SHAPES_SMEM) two Shape per warp
+__host__ __device__ constexpr size_t warp_shapes_offset() { return (WARPS_PER_BLOCK * sizeof(WarpPolytopeSmem) + 15) & ~(size_t)15; }
+constexpr size_t WARP_CONTACT_SMEM = B3_WARP_SHAPES_SMEM ? warp_shapes_offset() + WARPS_PER_BLOCK * 2 * sizeof(Shape) : WARPS_PER_BLOCK * sizeof(WarpPolytopeSmem);
 template <bool WARP>
 __global__ void __launch_bounds__(TPB, B3_WARP_MIN_BLOCKS) gjk_contact_kernel(ShapeSetDev S, const uint2* __restrict__ pairs, uint32_t n,
                                                           const uint32_t* __restrict__ order, const uint32_t* __restrict__ ranges,
@@ -346,9 +352,36 @@ __global__ void __launch_bounds__(TPB, B3_WARP_MIN_BLOCKS) gjk_contact_kernel(Sh
     for (uint32_t slot = first; slot < end; slot += stride) {
         uint32_t p = order ? __ldg(order + slot) : slot;
         uint2 pr = __ldg(pairs + p);
+#if B3_WARP_SHAPES_SMEM
+        // Warp-per-pair: every lane would hold the same two shape records (2 x 28 registers) for the whole pair. One copy
+        // per warp in shared memory instead (broadcast reads where the support function needs them) leaves the registers
+        // to the vertex scan and lets more warps be resident.
+        Shape Lreg, Rreg;
+        const Shape* Lp = &Lreg;
+        const Shape* Rp = &Rreg;
+        if constexpr (WARP) {
+            Shape* sh = reinterpret_cast<Shape*>(dyn_smem + warp_shapes_offset()) + 2 * (threadIdx.x / 32);
+            __syncwarp();
+            if ((threadIdx.x & 31) == 0) {
+                Shape t;
+                load_pair_shape(t, S, pr.x);
+                sh[0] = t;
+                load_pair_shape(t, S, pr.y);
+                sh[1] = t;
+            }
+            __syncwarp();
+            Lp = sh; Rp = sh + 1;
+        } else {
+            load_pair_shape(Lreg, S, pr.x);
+            load_pair_shape(Rreg, S, pr.y);
+        }
+        const Shape& L = *Lp;
+        const Shape& R = *Rp;
+#else
         Shape L, R;
         load_pair_shape(L, S, pr.x);
         load_pair_shape(R, S, pr.y);
+#endif
         Simplex<true> s;
         uint8_t st = gjk_intersect<WARP, true>(L, R, cfg.max_iterations, s);
         ContactOut c;
@@ -461,8 +494,14 @@ constexpr size_t EPA_SLAB_VV = 1280, EPA_SLAB_FN = (size_t)EPA_FCAP * 16, EPA_SL
 constexpr size_t EPA_SLAB_BYTES = 2 * EPA_SLAB_VV + EPA_SLAB_FN + EPA_SLAB_FI;  // 7680 = 60 x 128
 static_assert(EPA_SLAB_VV >= (size_t)EPA_VCAP * 12 && EPA_SLAB_BYTES % 128 == 0, "slab layout");
 
+#ifndef B3_EPA_BLOCKS
+#define B3_EPA_BLOCKS 4  // resident blocks per SM the EPA kernel is compiled for (register cap) and its slab is sized for
+#endif
+#ifndef B3_EPA_RELOAD_SHAPES
+#define B3_EPA_RELOAD_SHAPES 0
+#endif
 template <bool GLOBAL_POLY>
-__global__ void __launch_bounds__(TPB, 4) epa_refill_kernel(ShapeSetDev S, const uint2* __restrict__ pairs, SettingsDev cfg,
+__global__ void __launch_bounds__(TPB, B3_EPA_BLOCKS) epa_refill_kernel(ShapeSetDev S, const uint2* __restrict__ pairs, SettingsDev cfg,
                                                          const uint32_t* __restrict__ bin_start, BinOrder bo,
                                                          unsigned char* __restrict__ queue, unsigned char* __restrict__ ovf_scratch,
                                                          unsigned char* __restrict__ slab,
@@ -518,7 +557,14 @@ __global__ void __launch_bounds__(TPB, 4) epa_refill_kernel(ShapeSetDev S, const
     const uint32_t lane = threadIdx.x & 31u;
     bool active = false, exhausted = false;
     int seg = 0;  // the cursor only grows, so each lane walks the segment table forward
+#if B3_EPA_RELOAD_SHAPES
+    // The two shape records (2 x 28 registers) are only read by the support function at the top of a trip: keep the
+    // pair's shape indices instead and fetch the records again every trip (192 B, L1/L2 hits), so that the face scan
+    // and the horizon walk do not carry them.
+    uint2 pr_live = make_uint2(0u, 0u);
+#else
     Shape L, R;
+#endif
     int nv = 0, nf = 0;
     uint32_t it = 0, p = 0;
     V3 vmax = v3(0.f, 0.f, 0.f);
@@ -545,8 +591,12 @@ __global__ void __launch_bounds__(TPB, 4) epa_refill_kernel(ShapeSetDev S, const
                     s.v[3] = v3(e.z, e.w, f.x); s.a[3] = v3(f.y, f.z, f.w);
                     p = __float_as_uint(g.x);
                     uint2 pr = __ldg(pairs + p);
+#if B3_EPA_RELOAD_SHAPES
+                    pr_live = pr;
+#else
                     load_pair_shape(L, S, pr.x);
                     load_pair_shape(R, S, pr.y);
+#endif
                     epa_init<false>(s, P, nv, nf, it, vmax, best);
                     active = true;
                 } else {
@@ -560,6 +610,11 @@ __global__ void __launch_bounds__(TPB, 4) epa_refill_kernel(ShapeSetDev S, const
         if (!__any_sync(0xFFFFFFFFu, active)) break;
         if (active) {
             ContactOut c;
+#if B3_EPA_RELOAD_SHAPES
+            Shape L, R;
+            load_pair_shape(L, S, pr_live.x);
+            load_pair_shape(R, S, pr_live.y);
+#endif
             uint8_t st = epa_iterate<false>(L, R, cfg.epa_tolerance, cfg.max_iterations, P, nv, nf, it, vmax, best, c);
             if (st != EPA_CONTINUE) {
                 if (st != ST_OK) { c.normal = v3(0.f, 0.f, 0.f); c.depth = 0.f; c.point = v3(0.f, 0.f, 0.f); }
@@ -899,7 +954,7 @@ int launch_intersect(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs
     if (run_warp) { gjk_intersect_kernel<true><<<warp_grid(n), TPB, 0, st>>>(S, d_pairs, n, order, ranges, cfg, d_status); ++launched; }
     return launched;
 }
-size_t contact_poly_slab_bytes() { return (size_t)NUM_SMS * 4 * TPB * EPA_SLAB_BYTES; }
+size_t contact_poly_slab_bytes() { return (size_t)NUM_SMS * B3_EPA_BLOCKS * TPB * EPA_SLAB_BYTES; }
 size_t contact_overflow_scratch_bytes() { return OVF_HEADER_BYTES + (size_t)OVF_WARPS * EPA_BIG_SLAB_BYTES; }
 // header | n GJK->EPA records | 3 promotion lists of n record indices | sup_a scratch of the shared-memory EPA warps
 static size_t queue_lists_bytes(uint32_t n) { return ((size_t)n * 12 + 15) & ~(size_t)15; }
@@ -911,8 +966,8 @@ static int epa_refill_grid() {
     static int blocks = 0;
     if (!blocks) {
         int per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, epa_refill_kernel<false>, TPB, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
-        if (per_sm > 4) per_sm = 4;  // (the slab of the global-polytope variant is sized for 4 blocks per SM)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, epa_refill_kernel<true>, TPB, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
+        if (per_sm > B3_EPA_BLOCKS) per_sm = B3_EPA_BLOCKS;  // (the slab of the global-polytope variant is sized for this many blocks per SM)
         if (const char* e = getenv("BAM3D_EPA_BLOCKS_PER_SM")) { int v = atoi(e); if (v >= 1 && v < per_sm) per_sm = v; }
         blocks = per_sm * NUM_SMS;
     }
@@ -1040,7 +1095,7 @@ int launch_contact(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs, 
         }
     }
     if (run_warp) {
-        gjk_contact_kernel<true><<<warp_grid(n), TPB, WARPS_PER_BLOCK * sizeof(WarpPolytopeSmem), st>>>(S, d_pairs, n, order, ranges, cfg,
+        gjk_contact_kernel<true><<<warp_grid(n), TPB, WARP_CONTACT_SMEM, st>>>(S, d_pairs, n, order, ranges, cfg,
                                                                                                      strategy, ovf, d_contacts, d_status);
         ++launched;
     }
