@@ -113,9 +113,6 @@ B3_DEV void epa_init(const Simplex<true>& s, const PolytopeStore& P, int& nv, in
 
 constexpr uint8_t EPA_CONTINUE = 0xFF;
 
-#ifndef B3_EPA_PREFETCH_NEXT
-#define B3_EPA_PREFETCH_NEXT 0  // one-line-ahead prefetch inside pass A (see there)
-#endif
 #ifndef B3_EPA_PREFETCH
 #define B3_EPA_PREFETCH 0  // 0 = off (measured: L1/L2 prefetch of the face list costs 0.8 ms on C2 — the caches are over capacity), 1 = prefetch.L1, 2 = prefetch.L2
 #endif
@@ -194,17 +191,6 @@ B3_DEV uint8_t epa_iterate(const Shape& L, const Shape& R, float tolerance, uint
         const int k1 = min(nf, k0 + 32);
         for (int kb = k0; kb < k1; kb += 8) {
             float4 fb[8];
-#if B3_EPA_PREFETCH_NEXT
-            // thread-per-pair tier: a batch of 8 faces is exactly one 128-byte line of this lane's record; ask for the
-            // next line now so that its round trip overlaps this batch's arithmetic (1 = into L1, 2 = into L2)
-            if (!WARP && kb + 8 < nf) {
-#if B3_EPA_PREFETCH_NEXT == 2
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(P.fn + kb + 8));
-#else
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(P.fn + kb + 8));
-#endif
-            }
-#endif
 #pragma unroll
             for (int j = 0; j < 8; ++j) fb[j] = (kb + j < k1) ? P.fn[kb + j] : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll

@@ -497,9 +497,6 @@ static_assert(EPA_SLAB_VV >= (size_t)EPA_VCAP * 12 && EPA_SLAB_BYTES % 128 == 0,
 #ifndef B3_EPA_BLOCKS
 #define B3_EPA_BLOCKS 4  // resident blocks per SM the EPA kernel is compiled for (register cap) and its slab is sized for
 #endif
-#ifndef B3_EPA_RELOAD_SHAPES
-#define B3_EPA_RELOAD_SHAPES 0
-#endif
 template <bool GLOBAL_POLY>
 __global__ void __launch_bounds__(TPB, B3_EPA_BLOCKS) epa_refill_kernel(ShapeSetDev S, const uint2* __restrict__ pairs, SettingsDev cfg,
                                                          const uint32_t* __restrict__ bin_start, BinOrder bo,
@@ -557,14 +554,7 @@ __global__ void __launch_bounds__(TPB, B3_EPA_BLOCKS) epa_refill_kernel(ShapeSet
     const uint32_t lane = threadIdx.x & 31u;
     bool active = false, exhausted = false;
     int seg = 0;  // the cursor only grows, so each lane walks the segment table forward
-#if B3_EPA_RELOAD_SHAPES
-    // The two shape records (2 x 28 registers) are only read by the support function at the top of a trip: keep the
-    // pair's shape indices instead and fetch the records again every trip (192 B, L1/L2 hits), so that the face scan
-    // and the horizon walk do not carry them.
-    uint2 pr_live = make_uint2(0u, 0u);
-#else
     Shape L, R;
-#endif
     int nv = 0, nf = 0;
     uint32_t it = 0, p = 0;
     V3 vmax = v3(0.f, 0.f, 0.f);
@@ -591,12 +581,8 @@ __global__ void __launch_bounds__(TPB, B3_EPA_BLOCKS) epa_refill_kernel(ShapeSet
                     s.v[3] = v3(e.z, e.w, f.x); s.a[3] = v3(f.y, f.z, f.w);
                     p = __float_as_uint(g.x);
                     uint2 pr = __ldg(pairs + p);
-#if B3_EPA_RELOAD_SHAPES
-                    pr_live = pr;
-#else
                     load_pair_shape(L, S, pr.x);
                     load_pair_shape(R, S, pr.y);
-#endif
                     epa_init<false>(s, P, nv, nf, it, vmax, best);
                     active = true;
                 } else {
@@ -610,11 +596,6 @@ __global__ void __launch_bounds__(TPB, B3_EPA_BLOCKS) epa_refill_kernel(ShapeSet
         if (!__any_sync(0xFFFFFFFFu, active)) break;
         if (active) {
             ContactOut c;
-#if B3_EPA_RELOAD_SHAPES
-            Shape L, R;
-            load_pair_shape(L, S, pr_live.x);
-            load_pair_shape(R, S, pr_live.y);
-#endif
             uint8_t st = epa_iterate<false>(L, R, cfg.epa_tolerance, cfg.max_iterations, P, nv, nf, it, vmax, best, c);
             if (st != EPA_CONTINUE) {
                 if (st != ST_OK) { c.normal = v3(0.f, 0.f, 0.f); c.depth = 0.f; c.point = v3(0.f, 0.f, 0.f); }
