@@ -42,7 +42,7 @@ ALGO_BYTES = {  # algorithmic HBM bytes per pair
 # DRAM traffic of the dominant kernel per launch (bytes), from the committed ncu captures (profiles/r1_*_ncu_full.txt);
 # for C2 it is far above the algorithmic bytes because the EPA polytopes (7.5 KB slab record per resident thread) do not
 # all stay in L2 (DESIGN.md §11 records what was tried against it this round: 24 GB -> 5.4 GB).
-NCU_DRAM_BYTES = {"c1": 223.0e6, "c2": 5.36e9, "c3": 258.0e6}  # c2: profiles/r1c_c2_ncu_full.txt, c3: r1b
+NCU_DRAM_BYTES = {"c1": 223.0e6, "c2": 5.36e9, "c3": 261.8e6}  # c2: profiles/r1c_c2_ncu_full.txt, c3: profiles/r1f_c3_ncu_full.txt
 WORKLOAD_DESC = {
     "c1": "C1: GJK intersect, 2^20 random Cuboid-Cuboid pairs per GPU (f32, random transforms, offset U[-2,2]^3)",
     "c2": "C2: GJK+EPA Contact (FullResolution), 2^20 mixed Sphere/Cuboid/Cylinder pairs per GPU (offset U[-1.5,1.5]^3)",
@@ -531,15 +531,62 @@ def run_ours_c5(args):
     h2d = sum(len(v["kind"]) * 64 + len(v["pairs"]) * 8 for v in parts.values()) + len(parts["toi"]["kind"]) * 64
     d2h = n + n_dense * 32
     e2e_steps = max(3, min(args.steps, 5))
-    step_e2e(); sync_all()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        step_e2e()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * n * e2e_steps / float(t.item())
+
+    def timed(fn):
+        sync_all()
+        t0 = time.perf_counter()
+        fn()
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return world * n * e2e_steps / float(t.item())
+
+    step_e2e()
+    e2e_sync = timed(lambda: [step_e2e() for _ in range(e2e_steps)])
+    status_sync = {k: hst[k].clone() for k in sizes}
+
+    # The same frames through one frame queue per sub-batch (bam3d_frames_*), two steps in flight: step k+1's transforms and
+    # pairs are copied in, and step k-1's results copied out, while step k's kernels run.
+    DEPTH = 2
+    query = {"contact": 1, "intersect": 0, "poly": 1, "toi": 2}
+    queues = {}
+    for k, v in parts.items():
+        q = C.c_void_p()
+        kind, params = np.ascontiguousarray(v["kind"], dtype=np.uint8), np.ascontiguousarray(v["params"], dtype=np.float32)
+        mesh_id = None if v.get("mesh_id") is None else np.ascontiguousarray(v["mesh_id"], dtype=np.uint32)
+        ctx.check(lib.bam3d_frames_create(h, C.c_void_p(kind.ctypes.data), C.c_void_p(params.ctypes.data), hp(hx[k]),
+                                          C.c_void_p(mesh_id.ctypes.data) if mesh_id is not None else None, len(kind),
+                                          meshes.handle if k == "poly" else None, sizes[k], DEPTH, 1 if k == "toi" else 0, C.byref(q)))
+        queues[k] = q
+    qst = [{k: torch.empty(sizes[k], dtype=torch.uint8).pin_memory() for k in sizes} for _ in range(DEPTH)]
+    qct = [{k: torch.empty((sizes[k], 8), dtype=torch.float32).pin_memory() for k in order} for _ in range(DEPTH)]
+    submitted = {"n": 0}
+
+    def run_queues(steps):
+        ticket = C.c_uint64(0)
+        first = submitted["n"]
+        for s_ in range(steps):
+            f = first + s_
+            if s_ >= DEPTH:
+                for k in sizes:
+                    ctx.check(lib.bam3d_frames_wait(h, queues[k], f - DEPTH))
+            b = f % DEPTH
+            for k in sizes:
+                ctx.check(lib.bam3d_frames_submit(h, queues[k], query[k], hp(hx[k]), hp(hx_end) if k == "toi" else None, hp(hpairs[k]), sizes[k], S, 0,
+                                                  hp(qct[b][k]) if k in qct[b] else None, hp(qst[b][k]), C.byref(ticket)))
+        for f in range(first + max(0, steps - DEPTH), first + steps):
+            for k in sizes:
+                ctx.check(lib.bam3d_frames_wait(h, queues[k], f))
+        submitted["n"] = first + steps
+
+    run_queues(2)
+    e2e_value = timed(lambda: run_queues(e2e_steps))
+    for b in range(min(DEPTH, e2e_steps)):
+        for k in sizes:
+            if not torch.equal(qst[b][k], status_sync[k]):
+                raise SystemExit("bench.py: frame-queue results differ from the synchronous calls")
+    for q in queues.values():
+        lib.bam3d_frames_free(h, q)
 
     if rank == 0:
         peak, peak_src = load_peaks()
@@ -561,7 +608,10 @@ def run_ours_c5(args):
                        "l2": "inputs larger than L2 (shape records 96 B x 2 per pair); no flush",
                        "multi_gpu": "contiguous pair slices, per-rank compaction, NCCL all-gather of Contact40 records each step" if world > 1 else "single GPU"},
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                    "path": "bam3d_shapes_set_transforms + host-buffer bam3d_gjk_* calls per sub-batch, pinned host memory"},
+                    "path": f"one frame queue per sub-batch (bam3d_frames_submit / bam3d_frames_wait), {DEPTH} steps in flight: every step copies "
+                            "its transforms + pairs in from pinned host memory and its status (+ contacts) out to pinned host memory",
+                    "one_call_after_the_other": {"value": e2e_sync, "unit": "pairs/s",
+                                                 "path": "bam3d_shapes_set_transforms + host-buffer bam3d_gjk_* calls per sub-batch, synchronous"}},
             "gpu_launches": launches, "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                          "kernel": "epa_refill_kernel and gjk_contact_kernel<true> dominate (see the c2 / c3 lines and profiles/)",

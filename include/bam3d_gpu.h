@@ -96,9 +96,9 @@ void bam3d_default_settings(bam3d_gjk_settings* out); /* GJK::new() (gjk/mod.rs:
  * (default 0) brackets the main kernel(s) of every narrow-phase / broad-phase call with CUDA events; "sap_strategy"
  * picks how sweep-and-prune finds its pairs — 0 auto, 1 tiled forward sweep, 2 BVH overlap query (same output);
  * "bvh_strategy" picks how the variable-length BVH queries run — 0 auto, 1 tree traversal (thread per query), 2 every
- * (query, value) test (for few large queries; results then come back in value-index order); "epa_tiers" (default 1)
- * runs EPA with the polytopes in shared memory in size tiers, 0 = per-thread local-memory polytopes (same results);
- * "epa_overlap" (default 1) runs the EPA overflow tier on a side stream next to the EPA kernel;
+ * (query, value) test (for few large queries; results then come back in value-index order); "epa_tiers" (default 0)
+ * = 1 runs EPA with the polytopes in shared memory in size tiers instead of one polytope per thread (same results, measured
+ * slower: kept as an option); "epa_overlap" (default 1) runs the EPA overflow tier on a side stream next to the EPA kernel;
  * "epa_global_polytopes" (default 1) keeps the thread-per-pair EPA's polytopes in a global-memory slab, one contiguous
  * record per thread (582 MB of scratch), instead of per-thread local memory; "intersect_split"
  * (default 0) runs bam3d_gjk_intersect's thread path as two launches (first-support test, then GJK on the survivors) */
