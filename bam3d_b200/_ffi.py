@@ -72,6 +72,10 @@ SIGNATURES = {
     "bam3d_sap_variance": (_i32, [_vp, _vp, _u64, _vp, C.POINTER(_i32)]),
     "bam3d_shapes_world_aabbs": (_i32, [_vp, _vp, _vp]),
     "bam3d_shapes_world_aabbs_dev": (_i32, [_vp, _vp, _vp]),
+    "bam3d_shapes_world_spheres": (_i32, [_vp, _vp, _vp]),
+    "bam3d_shapes_world_spheres_dev": (_i32, [_vp, _vp, _vp]),
+    "bam3d_sap_find_pairs_spheres": (_i32, [_vp, _vp, _u64, C.POINTER(_i32), _vp, _vp, _u64, C.POINTER(_u64)]),
+    "bam3d_sap_find_pairs_spheres_dev": (_i32, [_vp, _vp, _u64, C.POINTER(_i32), _vp, _vp, _u64, C.POINTER(_u64)]),
     "bam3d_bvh_build": (_i32, [_vp, _vp, _u64, C.POINTER(_vp)]),
     "bam3d_bvh_build_dev": (_i32, [_vp, _vp, _u64, C.POINTER(_vp)]),
     "bam3d_bvh_refit": (_i32, [_vp, _vp, _vp]),

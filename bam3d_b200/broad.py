@@ -75,6 +75,38 @@ class SweepAndPrune3:
         return pairs[:cnt], perm
 
 
+class SweepAndPrune3Sphere(SweepAndPrune3):
+    """SweepAndPrune3<volume::Sphere> (sweep_prune.rs:27-128 with Bound for Sphere, volume/sphere.rs:17-48): bounds are rows
+    of 4 f32 (centre.xyz, radius); a pair is reported iff it is still active on the sweep axis and Sphere::intersects holds."""
+
+    def find_collider_pairs(self, spheres, capacity=None):
+        spheres = np.ascontiguousarray(spheres, dtype=np.float32).reshape(-1, 4)
+        n = len(spheres)
+        perm = np.empty(n, dtype=np.uint32)
+        ctx, lib = self.ctx, self.ctx._lib
+
+        def call(cap):
+            pairs = np.empty((cap, 2), dtype=np.uint32)
+            axis = C.c_int32(self.sweep_axis)
+            cnt = C.c_uint64(0)
+            rc = lib.bam3d_sap_find_pairs_spheres(ctx.handle, _ptr(spheres), n, C.byref(axis), _ptr(perm), _ptr(pairs), cap, C.byref(cnt))
+            return rc, cnt.value, (pairs, int(cnt.value), int(axis.value))
+
+        res = _retry_capacity(call, capacity if capacity is not None else 8 * n + 1024)
+        if isinstance(res, int):
+            ctx.check(res)
+        pairs, cnt, axis = res
+        self.sweep_axis = axis
+        return pairs[:cnt], perm
+
+
+def world_spheres(shapes):
+    """ComputeBound<volume::Sphere> + Bound::transform_volume for every shape of a ShapeSet -> [n, 4] (centre.xyz, radius)."""
+    out = np.empty((shapes.n, 4), dtype=np.float32)
+    shapes.ctx.check(shapes.ctx._lib.bam3d_shapes_world_spheres(shapes.ctx.handle, shapes.handle, _ptr(out)))
+    return out
+
+
 def variance3(ctx, aabbs):
     """Variance3 (sweep_prune.rs:166-216) over `aabbs` in the given order -> (sums[6] = csum.xyz, csumsq.xyz, next axis)."""
     aabbs = np.ascontiguousarray(aabbs, dtype=np.float32).reshape(-1, 6)

@@ -418,6 +418,124 @@ int launch_world_aabbs(cudaStream_t st, const ShapeSetDev& S, float* d_out6) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// world bounding spheres: ComputeBound<volume::Sphere> per primitive (primitive3.rs:98-114: particle r = 0, quad.rs:71-78,
+// sphere.rs:36-43, cuboid.rs:75-83 [the largest half extent, as written], cylinder.rs:73-80, capsule.rs:60-67,
+// polyhedron.rs:87-92,363-370 [largest vertex norm]), then Bound::transform_volume (volume/sphere.rs:34-39: the centre
+// moves, the radius stays). out = n x (centre.xyz, radius).
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BT) world_sphere_kernel(ShapeSetDev S, float4* __restrict__ out) {
+    uint32_t i = blockIdx.x * BT + threadIdx.x;
+    if (i >= S.n) return;
+    Shape s;
+    load_shape(s, S.recs, i);
+    uint32_t meta = S.meta[i];
+    float r = 0.f;
+    switch (meta & 0xFF) {
+        case K_PARTICLE: break;
+        case K_QUAD: r = rmax(s.p0, s.p1); break;
+        case K_SPHERE: r = s.p0; break;
+        case K_CUBOID: r = rmax(rmax(s.p0, s.p1), s.p2); break;
+        case K_CYLINDER: r = sqrtf((s.p1 * s.p1) + (s.p0 * s.p0)); break;   // p0 = half_height, p1 = radius
+        case K_CAPSULE: r = s.p0 + s.p1; break;
+        default: {
+            uint32_t mid = meta >> 8;
+            uint32_t b = S.mesh_offsets[mid] + MESH_HEADER_SLOTS, e = S.mesh_offsets[mid + 1];
+            bool any = false;
+            for (uint32_t k = b; k < e; ++k) {
+                float4 p = S.mesh_verts[k];
+                float len = sqrtf(dot(v3(p.x, p.y, p.z), v3(p.x, p.y, p.z)));
+                // Iterator::max_by keeps the later element unless the earlier one compares Greater (NaN compares Equal)
+                if (!any || !(r > len)) r = len;
+                any = true;
+            }
+        }
+    }
+    V3 c = transform_point3(s, v3(0.f, 0.f, 0.f));
+    out[i] = make_float4(c.x, c.y, c.z, r);
+}
+
+int launch_world_spheres(cudaStream_t st, const ShapeSetDev& S, float4* d_out) {
+    if (S.n == 0) return 0;
+    world_sphere_kernel<<<(S.n + BT - 1) / BT, BT, 0, st>>>(S, d_out);
+    return 1;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// SweepAndPrune3<volume::Sphere>: the same sort / Variance3 / pair search as for Aabb3, on the spheres' extents
+// (Bound for Sphere, volume/sphere.rs:19-25: centre + splat(-+ radius)); the pair test is Sphere::intersects
+// (volume/sphere.rs:82-91: |c1 - c2|^2 <= (r1 + r2)^2 — touching spheres are reported, unlike boxes).
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BT) spheres_to_extents_kernel(const float4* __restrict__ spheres, uint32_t n, float* __restrict__ boxes) {
+    uint32_t i = blockIdx.x * BT + threadIdx.x;
+    if (i >= n) return;
+    const float4 s = spheres[i];
+    float* o = boxes + 6 * (size_t)i;
+    o[0] = s.x + -s.w; o[1] = s.y + -s.w; o[2] = s.z + -s.w;
+    o[3] = s.x + s.w;  o[4] = s.y + s.w;  o[5] = s.z + s.w;
+}
+
+int launch_spheres_to_extents(cudaStream_t st, const float4* d_spheres, uint32_t n, float* d_boxes6) {
+    if (n == 0) return 0;
+    spheres_to_extents_kernel<<<(n + BT - 1) / BT, BT, 0, st>>>(d_spheres, n, d_boxes6);
+    return 1;
+}
+
+// The pair search works on strict box overlap. Sphere::intersects holds for touching spheres and is evaluated in f32, so
+// the search runs on boxes grown by a margin that covers both (relative 2^-16 of the radius and of the coordinate
+// magnitude — orders of magnitude above the rounding of the f32 test): a superset, filtered exactly afterwards.
+B3_DEV float grow_margin(float lo, float hi) { return (fabsf(lo) + fabsf(hi)) * 1.52587890625e-05f + 1e-30f; }
+__global__ void __launch_bounds__(BT) sap_inflate_kernel(float4* __restrict__ lo, float4* __restrict__ hi, float* __restrict__ sorted6, uint32_t n) {
+    uint32_t k = blockIdx.x * BT + threadIdx.x;
+    if (k >= n) return;
+    float4 a = lo[k], b = hi[k];
+    const float mx = grow_margin(a.x, b.x), my = grow_margin(a.y, b.y), mz = grow_margin(a.z, b.z);
+    a.x -= mx; a.y -= my; a.z -= mz; b.x += mx; b.y += my; b.z += mz;
+    lo[k] = a; hi[k] = b;
+    if (sorted6) { float* o = sorted6 + 6 * (size_t)k; o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = b.x; o[4] = b.y; o[5] = b.z; }
+}
+int launch_sap_inflate(cudaStream_t st, const SapScratch& S, float* d_sorted6, uint32_t n) {
+    if (n == 0) return 0;
+    sap_inflate_kernel<<<(n + BT - 1) / BT, BT, 0, st>>>(S.lo, S.hi, d_sorted6, n);
+    return 1;
+}
+
+__global__ void __launch_bounds__(BT) gather_spheres_kernel(const float4* __restrict__ spheres, const uint32_t* __restrict__ perm, uint32_t n,
+                                                            float4* __restrict__ sorted) {
+    uint32_t k = blockIdx.x * BT + threadIdx.x;
+    if (k < n) sorted[k] = spheres[perm[k]];
+}
+int launch_gather_spheres(cudaStream_t st, const float4* d_spheres, const uint32_t* d_perm, uint32_t n, float4* d_sorted) {
+    if (n == 0) return 0;
+    gather_spheres_kernel<<<(n + BT - 1) / BT, BT, 0, st>>>(d_spheres, d_perm, n, d_sorted);
+    return 1;
+}
+
+// Keeps (i, j), i < j in sorted order, iff the reference reports it: i is still active when j arrives
+// (max_extent_i[axis] >= min_extent_j[axis], sweep_prune.rs:102-105) and the spheres intersect. Order-preserving.
+struct SpherePairKeep {
+    const float4* s;
+    int axis;
+    __device__ bool operator()(const uint2& p) const {
+        const float4 a = s[p.x], b = s[p.y];
+        const float ca = axis == 0 ? a.x : (axis == 1 ? a.y : a.z), cb = axis == 0 ? b.x : (axis == 1 ? b.y : b.z);
+        if (!((ca + a.w) >= (cb + -b.w))) return false;
+        const V3 d = v3(a.x - b.x, a.y - b.y, a.z - b.z);
+        const float rr = a.w + b.w;
+        return dot(d, d) <= rr * rr;
+    }
+};
+size_t sphere_filter_tmp_bytes(uint64_t n_pairs) {
+    size_t bytes = 0;
+    cub::DeviceSelect::If((void*)nullptr, bytes, (const uint2*)nullptr, (uint2*)nullptr, (unsigned long long*)nullptr, (long long)n_pairs, SpherePairKeep{nullptr, 0});
+    return bytes;
+}
+int launch_sphere_pair_filter(cudaStream_t st, const float4* d_sorted_spheres, int axis, const uint2* d_in, uint64_t n_pairs, uint2* d_out,
+                              unsigned long long* d_count, void* d_tmp, size_t tmp_bytes) {
+    cub::DeviceSelect::If(d_tmp, tmp_bytes, d_in, d_out, d_count, (long long)n_pairs, SpherePairKeep{d_sorted_spheres, axis}, st);
+    return 2;
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // LBVH build (Karras 2012): Morton codes of box centres, radix sort, radix-tree topology, bottom-up bounds
 // ------------------------------------------------------------------------------------------------------------
 B3_DEV uint32_t fkey(float f) { uint32_t b = __float_as_uint(f); return (b & 0x80000000u) ? ~b : (b | 0x80000000u); }

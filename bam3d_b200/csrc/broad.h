@@ -41,6 +41,16 @@ int launch_sap_finish(cudaStream_t st, const SapScratch& S, uint64_t count, uint
 
 // ---- world AABBs of packed shapes (ComputeBound<Aabb3> + Aabb::transform) ---------------------------------------
 int launch_world_aabbs(cudaStream_t st, const ShapeSetDev& S, float* d_out6);
+// ComputeBound<volume::Sphere> + transform_volume per shape: n x (centre.xyz, radius)
+int launch_world_spheres(cudaStream_t st, const ShapeSetDev& S, float4* d_out);
+// SweepAndPrune3<volume::Sphere>: extents of the spheres as boxes (sort keys, Variance3), growth of the sorted boxes for the
+// candidate search, spheres in sorted order, and the exact order-preserving pair filter
+int launch_spheres_to_extents(cudaStream_t st, const float4* d_spheres, uint32_t n, float* d_boxes6);
+int launch_sap_inflate(cudaStream_t st, const SapScratch& S, float* d_sorted6, uint32_t n);
+int launch_gather_spheres(cudaStream_t st, const float4* d_spheres, const uint32_t* d_perm, uint32_t n, float4* d_sorted);
+size_t sphere_filter_tmp_bytes(uint64_t n_pairs);
+int launch_sphere_pair_filter(cudaStream_t st, const float4* d_sorted_spheres, int axis, const uint2* d_in, uint64_t n_pairs, uint2* d_out,
+                              unsigned long long* d_count, void* d_tmp, size_t tmp_bytes);
 
 // ---- static BVH answering the DBVT queries ---------------------------------------------------------------------
 struct BvhDev {

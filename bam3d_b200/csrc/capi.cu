@@ -688,8 +688,12 @@ int32_t bam3d_frustum_from_mat4(const float* m, float* out24) {
 // shard / n_shards: only the pairs whose higher sorted slot j lies in [n * shard / n_shards, n * (shard + 1) / n_shards)
 // are searched and returned (the sort is replicated on every GPU, the sweep is sharded by sorted-index range;
 // the shards' outputs, concatenated in shard order, are the unsharded output).
+// d_spheres != nullptr: SweepAndPrune3<volume::Sphere> — d_aabbs then holds the spheres' extents (sort keys and Variance3 are
+// exactly the Aabb3 path's on those), the candidate search runs on the grown boxes with the BVH strategy (the tiled sweep relies on
+// sorted mins, which growing does not keep), and the candidates are filtered by the reference's two tests (still-active on the sweep
+// axis, Sphere::intersects) in order; d_perm must then be given.
 static int32_t sap_run(bam3d_ctx* ctx, const float* d_aabbs, uint64_t n64, int32_t* inout_axis, uint32_t* d_perm, uint32_t* d_pairs,
-                       uint64_t capacity, uint64_t* out_count, uint32_t shard = 0, uint32_t n_shards = 1) {
+                       uint64_t capacity, uint64_t* out_count, uint32_t shard = 0, uint32_t n_shards = 1, const float4* d_spheres = nullptr) {
     const uint32_t n = (uint32_t)n64;
     if (n_shards == 0 || shard >= n_shards) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_sap_find_pairs: shard index out of range", cudaSuccess);
     const uint32_t j_begin = (uint32_t)(n64 * shard / n_shards), j_end = (uint32_t)(n64 * (shard + 1) / n_shards);
@@ -720,7 +724,7 @@ static int32_t sap_run(bam3d_ctx* ctx, const float* d_aabbs, uint64_t n64, int32
     int* d_axis = (int*)((char*)ctx->small.ptr + 840);
     unsigned long long* d_cand = (unsigned long long*)((char*)ctx->small.ptr + 848);
     float* d_sums = (float*)((char*)ctx->small.ptr + 864);
-    const int strategy = ctx->opt_sap_strategy;
+    const int strategy = d_spheres ? 2 : ctx->opt_sap_strategy;
     // BVH strategy scratch (one slab): sorted 6-float rows, node bounds, topology, per-slot counts / offsets
     float* d_sorted6 = nullptr;
     char* slab = nullptr;
@@ -738,6 +742,10 @@ static int32_t sap_run(bam3d_ctx* ctx, const float* d_aabbs, uint64_t n64, int32
     cudaStreamWaitEvent(ctx->stream2, ctx->ev_a, 0);
     ctx->launches += launch_sap_variance(ctx->stream2, S, n, ctx->bp7.ptr, d_sums, d_axis);
     cudaEventRecord(ctx->ev_b, ctx->stream2);
+    if (d_spheres) {  // Variance3 reads the exact extents: grow the sorted boxes only after it has
+        cudaStreamWaitEvent(ctx->stream, ctx->ev_b, 0);
+        ctx->launches += launch_sap_inflate(ctx->stream, S, d_sorted6, n);
+    }
     if ((rc = check_launch(ctx, "sap sort"))) return rc;
     bool use_bvh = strategy == 2;
     if (strategy == 0) {
@@ -785,14 +793,40 @@ static int32_t sap_run(bam3d_ctx* ctx, const float* d_aabbs, uint64_t n64, int32
         std::snprintf(msg, sizeof msg, "bam3d_sap_find_pairs: %llu pairs found, capacity %llu", h_count, (unsigned long long)capacity);
         return b3_fail(ctx, BAM3D_ERR_CAPACITY, msg, cudaSuccess);
     }
-    { KernelTimer kt(ctx);
-      ctx->launches += launch_sap_finish(ctx->stream, S, h_count, (uint2*)d_pairs, n); }
+    if (!d_spheres) {
+        KernelTimer kt(ctx);
+        ctx->launches += launch_sap_finish(ctx->stream, S, h_count, (uint2*)d_pairs, n);
+    } else {
+        const size_t filter_tmp = sphere_filter_tmp_bytes(h_count);
+        const size_t cand_bytes = (((size_t)(h_count ? h_count : 1) * 8) + 255) & ~(size_t)255;  // keeps the float4 array behind it aligned
+        if ((rc = ctx->sph1.reserve(ctx, cand_bytes + (size_t)n * 16)) || (rc = ctx->sph2.reserve(ctx, filter_tmp + 256))) return rc;
+        uint2* cand = (uint2*)ctx->sph1.ptr;
+        float4* sorted_spheres = (float4*)((char*)ctx->sph1.ptr + cand_bytes);
+        KernelTimer kt(ctx);
+        ctx->launches += launch_sap_finish(ctx->stream, S, h_count, cand, n);
+        ctx->launches += launch_gather_spheres(ctx->stream, d_spheres, d_perm, n, sorted_spheres);
+        ctx->launches += launch_sphere_pair_filter(ctx->stream, sorted_spheres, axis, cand, h_count, (uint2*)d_pairs, d_count, ctx->sph2.ptr, filter_tmp);
+        CU_TRY(cudaMemcpyAsync(&h_count, d_count, 8, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(count)");
+    }
     int h_axis = axis;
     cudaStreamWaitEvent(ctx->stream, ctx->ev_b, 0);
     CU_TRY(cudaMemcpyAsync(&h_axis, d_axis, 4, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(axis)");
     CU_TRY(cudaStreamSynchronize(ctx->stream), "sap finish");
     *inout_axis = h_axis;
+    if (d_spheres) *out_count = h_count;
     return check_launch(ctx, "sap finish");
+}
+
+// SweepAndPrune3<volume::Sphere>::find_collider_pairs; d_spheres = n x (centre.xyz, radius)
+static int32_t sap_run_spheres(bam3d_ctx* ctx, const float4* d_spheres, uint64_t n, int32_t* inout_axis, uint32_t* d_perm, uint32_t* d_pairs,
+                               uint64_t capacity, uint64_t* out_count) {
+    int32_t rc;
+    const size_t nn = n ? n : 1;
+    if ((rc = ctx->sph0.reserve(ctx, nn * 24 + nn * 4))) return rc;
+    float* d_extents = (float*)ctx->sph0.ptr;
+    if (!d_perm) d_perm = (uint32_t*)((char*)ctx->sph0.ptr + nn * 24);
+    ctx->launches += launch_spheres_to_extents(ctx->stream, d_spheres, (uint32_t)n, d_extents);
+    return sap_run(ctx, d_extents, n, inout_axis, d_perm, d_pairs, capacity, out_count, 0, 1, d_spheres);
 }
 
 int32_t bam3d_sap_find_pairs_shard_dev(bam3d_ctx* ctx, const float* d_aabbs, uint64_t n, int32_t* inout_sweep_axis, uint32_t* d_perm,
@@ -828,6 +862,34 @@ int32_t bam3d_sap_find_pairs_shard(bam3d_ctx* ctx, const float* aabbs, uint64_t 
     if (out_perm && n) CU_TRY(cudaMemcpyAsync(out_perm, d_perm, n * 4, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(perm)");
     if (*out_count) CU_TRY(cudaMemcpyAsync(out_pairs, d_pairs, *out_count * 8, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(pairs)");
     CU_TRY(cudaStreamSynchronize(ctx->stream), "bam3d_sap_find_pairs");
+    return BAM3D_OK;
+}
+
+int32_t bam3d_sap_find_pairs_spheres_dev(bam3d_ctx* ctx, const float* d_spheres, uint64_t n, int32_t* inout_sweep_axis, uint32_t* d_perm,
+                                         uint32_t* d_pairs, uint64_t capacity, uint64_t* out_count) {
+    if (!ctx || !inout_sweep_axis || !out_count || (n && !d_spheres) || (capacity && !d_pairs)) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_sap_find_pairs_spheres: null argument", cudaSuccess);
+    int32_t rc;
+    if ((rc = check_n(ctx, n)) || (rc = check_n(ctx, capacity))) return rc;
+    CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
+    return sap_run_spheres(ctx, (const float4*)d_spheres, n, inout_sweep_axis, d_perm, d_pairs, capacity, out_count);
+}
+int32_t bam3d_sap_find_pairs_spheres(bam3d_ctx* ctx, const float* spheres, uint64_t n, int32_t* inout_sweep_axis, uint32_t* out_perm,
+                                     uint32_t* out_pairs, uint64_t capacity, uint64_t* out_count) {
+    if (!ctx || !inout_sweep_axis || !out_count || (n && !spheres) || (capacity && !out_pairs)) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_sap_find_pairs_spheres: null argument", cudaSuccess);
+    int32_t rc;
+    if ((rc = check_n(ctx, n)) || (rc = check_n(ctx, capacity))) return rc;
+    CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
+    const size_t nn = n ? n : 1;
+    if ((rc = ctx->bp4.reserve(ctx, nn * 16 + nn * 4)) || (rc = ctx->bp5.reserve(ctx, (capacity ? capacity : 1) * 8))) return rc;
+    float4* d_spheres = (float4*)ctx->bp4.ptr;
+    uint32_t* d_perm = (uint32_t*)((char*)ctx->bp4.ptr + nn * 16);
+    uint32_t* d_pairs = (uint32_t*)ctx->bp5.ptr;
+    if (n) CU_TRY(cudaMemcpyAsync(d_spheres, spheres, n * 16, cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpyAsync(spheres)");
+    rc = sap_run_spheres(ctx, d_spheres, n, inout_sweep_axis, d_perm, d_pairs, capacity, out_count);
+    if (rc != BAM3D_OK) return rc;
+    if (out_perm && n) CU_TRY(cudaMemcpyAsync(out_perm, d_perm, n * 4, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(perm)");
+    if (*out_count) CU_TRY(cudaMemcpyAsync(out_pairs, d_pairs, *out_count * 8, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(pairs)");
+    CU_TRY(cudaStreamSynchronize(ctx->stream), "bam3d_sap_find_pairs_spheres");
     return BAM3D_OK;
 }
 
@@ -875,6 +937,22 @@ int32_t bam3d_shapes_world_aabbs(bam3d_ctx* ctx, const bam3d_shapes* shapes, flo
     if ((rc = bam3d_shapes_world_aabbs_dev(ctx, shapes, (float*)ctx->bp4.ptr))) return rc;
     if (shapes->n) CU_TRY(cudaMemcpyAsync(out6, ctx->bp4.ptr, (size_t)shapes->n * 24, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(aabbs)");
     CU_TRY(cudaStreamSynchronize(ctx->stream), "bam3d_shapes_world_aabbs");
+    return BAM3D_OK;
+}
+
+int32_t bam3d_shapes_world_spheres_dev(bam3d_ctx* ctx, const bam3d_shapes* shapes, float* d_out4) {
+    if (!ctx || !shapes || (shapes->n && !d_out4)) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_shapes_world_spheres: null argument", cudaSuccess);
+    CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
+    ctx->launches += launch_world_spheres(ctx->stream, view(shapes), (float4*)d_out4);
+    return check_launch(ctx, "world_sphere_kernel");
+}
+int32_t bam3d_shapes_world_spheres(bam3d_ctx* ctx, const bam3d_shapes* shapes, float* out4) {
+    if (!ctx || !shapes || (shapes->n && !out4)) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_shapes_world_spheres: null argument", cudaSuccess);
+    int32_t rc;
+    if ((rc = ctx->bp4.reserve(ctx, (size_t)(shapes->n ? shapes->n : 1) * 16))) return rc;
+    if ((rc = bam3d_shapes_world_spheres_dev(ctx, shapes, (float*)ctx->bp4.ptr))) return rc;
+    if (shapes->n) CU_TRY(cudaMemcpyAsync(out4, ctx->bp4.ptr, (size_t)shapes->n * 16, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(spheres)");
+    CU_TRY(cudaStreamSynchronize(ctx->stream), "bam3d_shapes_world_spheres");
     return BAM3D_OK;
 }
 

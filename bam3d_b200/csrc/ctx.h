@@ -37,9 +37,9 @@ struct bam3d_ctx {
     // scratch for the host-buffer entry points and the binning pass
     DevBuf pairs, status, contacts, f0, f1, keys, order, small, epa_overflow, epa_queue, epa_slab;
     // broad-phase scratch
-    DevBuf bp0, bp1, bp2, bp3, bp4, bp5, bp6, bp7, cub_tmp;
+    DevBuf bp0, bp1, bp2, bp3, bp4, bp5, bp6, bp7, cub_tmp, sph0, sph1, sph2;
     void release_scratch() {
-        DevBuf* all[] = {&pairs, &status, &contacts, &f0, &f1, &keys, &order, &small, &epa_overflow, &epa_queue, &epa_slab, &bp0, &bp1, &bp2, &bp3, &bp4, &bp5, &bp6, &bp7, &cub_tmp};
+        DevBuf* all[] = {&pairs, &status, &contacts, &f0, &f1, &keys, &order, &small, &epa_overflow, &epa_queue, &epa_slab, &bp0, &bp1, &bp2, &bp3, &bp4, &bp5, &bp6, &bp7, &cub_tmp, &sph0, &sph1, &sph2};
         for (DevBuf* b : all) b->release();
     }
 };

@@ -229,6 +229,23 @@ int32_t bam3d_sap_find_pairs_shard_dev(bam3d_ctx* ctx, const float* d_aabbs, uin
 int32_t bam3d_shapes_world_aabbs(bam3d_ctx* ctx, const bam3d_shapes* shapes, float* out_aabbs);
 int32_t bam3d_shapes_world_aabbs_dev(bam3d_ctx* ctx, const bam3d_shapes* shapes, float* d_out_aabbs);
 
+/* volume::Sphere as the bound type (volume/sphere.rs). A bounding sphere is 4 f32: centre.xyz, radius.
+ * ComputeBound<volume::Sphere> of every packed primitive (primitive3.rs:98-114 — particle: radius 0; quad.rs:71-78; sphere.rs:36-43;
+ * cuboid.rs:75-83: the largest half extent, as the reference writes it; cylinder.rs:73-80; capsule.rs:60-67; polyhedron.rs:87-92,
+ * 363-370: the largest vertex norm) moved to world space with Bound::transform_volume (volume/sphere.rs:34-39: the centre is
+ * transformed, the radius kept): n x 4 f32. */
+int32_t bam3d_shapes_world_spheres(bam3d_ctx* ctx, const bam3d_shapes* shapes, float* out_spheres);
+int32_t bam3d_shapes_world_spheres_dev(bam3d_ctx* ctx, const bam3d_shapes* shapes, float* d_out_spheres);
+/* SweepAndPrune3<volume::Sphere>::find_collider_pairs (sweep_prune.rs:69-128 with Bound for Sphere, volume/sphere.rs:17-48): sorted
+ * (stable) by (min_extent, max_extent) = centre -+ radius on the sweep axis; (i, j), i < j in sorted order, is reported iff i is
+ * still active when j arrives (max_extent_i >= min_extent_j on the sweep axis) and Sphere::intersects holds (|ci - cj|^2 <=
+ * (ri + rj)^2, volume/sphere.rs:82-91 — touching spheres count); Variance3 over the extents picks the next axis. Arguments as for
+ * bam3d_sap_find_pairs; `capacity` must also cover the candidate pairs of the box search (a few per cent more than the result). */
+int32_t bam3d_sap_find_pairs_spheres(bam3d_ctx* ctx, const float* spheres, uint64_t n, int32_t* inout_sweep_axis, uint32_t* out_perm,
+                                     uint32_t* out_pairs, uint64_t capacity, uint64_t* out_count);
+int32_t bam3d_sap_find_pairs_spheres_dev(bam3d_ctx* ctx, const float* d_spheres, uint64_t n, int32_t* inout_sweep_axis, uint32_t* d_perm,
+                                         uint32_t* d_pairs, uint64_t capacity, uint64_t* out_count);
+
 /* Static BVH over n values' bounds, answering DynamicBoundingVolumeTree::query_for_indices (dbvt/mod.rs:481-515).
  * Value index k = position in `aabbs` (the tree's `values` order). The reference's insert / remove / rotate
  * maintenance (dbvt/mod.rs:531-1235) is not reproduced: its tree shape is randomised (rand::thread_rng, :901) and

@@ -132,6 +132,8 @@ struct Aabb3 {
                o.max.z <= max.z;
     }
     Aabb3 union_(const Aabb3& o) const { return grow(o.min).grow(o.max); }  // aabb3.rs:146-152
+    Vec3 min_extent() const { return min; }  // Bound for Aabb3, aabb3.rs:50-57
+    Vec3 max_extent() const { return max; }
     // aabb3.rs:258-264
     float surface_area() const {
         Vec3 d = dim();
@@ -191,6 +193,109 @@ inline bool ray_aabb_intersects(const Ray& ray, const Aabb3& aabb) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// volume/sphere.rs — the bounding sphere (named BSphere here: the primitive Sphere lives in bam3d_oracle.hpp)
+// ---------------------------------------------------------------------------------------------------------
+struct BSphere {
+    Vec3 center;
+    float radius = 0.f;
+    BSphere() {}
+    BSphere(Vec3 c, float r) : center(c), radius(r) {}
+    // Bound for Sphere, sphere.rs:17-48
+    Vec3 min_extent() const { return center + Vec3(-radius, -radius, -radius); }
+    Vec3 max_extent() const { return center + Vec3(radius, radius, radius); }
+    BSphere with_margin(Vec3 add) const { return BSphere(center, radius + rmax(rmax(add.x, add.y), add.z)); }
+    BSphere transform_volume(const Mat4& t) const { return BSphere(t.transform_point3(center), radius); }
+    static BSphere empty() { return BSphere(Vec3::zero(), 0.f); }
+    // Continuous<Ray>, sphere.rs:50-67
+    bool intersection(const Ray& r, Vec3& out) const {
+        Vec3 l = center - r.origin;
+        float tca = dot(l, r.direction);
+        if (tca < 0.f) return false;
+        float d2 = dot(l, l) - tca * tca;
+        if (d2 > radius * radius) return false;
+        float thc = std::sqrt(radius * radius - d2);
+        out = r.origin + r.direction * (tca - thc);
+        return true;
+    }
+    // Discrete<Ray>, sphere.rs:69-80
+    bool intersects(const Ray& r) const {
+        Vec3 l = center - r.origin;
+        float tca = dot(l, r.direction);
+        if (tca < 0.f) return false;
+        float d2 = dot(l, l) - tca * tca;
+        return d2 <= radius * radius;
+    }
+    // Discrete<Sphere>, sphere.rs:82-91 — touching spheres intersect
+    bool intersects(const BSphere& s2) const {
+        Vec3 distance = center - s2.center;
+        float radiuses = radius + s2.radius;
+        return dot(distance, distance) <= radiuses * radiuses;
+    }
+    // PlaneBound, sphere.rs:93-104
+    Relation relate_plane(const Plane& plane) const {
+        float dist = dot(center, plane.n) - plane.d;
+        if (dist > radius) return In;
+        else if (dist < -radius) return Out;
+        else return Cross;
+    }
+    // Contains<Aabb3>, sphere.rs:106-119
+    bool contains(const Aabb3& aabb) const {
+        float radius_sq = radius * radius;
+        Vec3 c[8]; aabb.to_corners(c);
+        for (int i = 0; i < 8; ++i) {
+            Vec3 distance = c[i] - center;
+            if (dot(distance, distance) > radius_sq) return false;
+        }
+        return true;
+    }
+    // Contains<Vec3>, sphere.rs:121-127
+    bool contains(Vec3 p) const {
+        Vec3 distance = p - center;
+        return dot(distance, distance) <= radius * radius;
+    }
+    // Contains<Line>, sphere.rs:129-134
+    bool contains_line(Vec3 origin, Vec3 dest) const { return contains(origin) && contains(dest); }
+    // Contains<Sphere>, sphere.rs:136-143
+    bool contains(const BSphere& other) const {
+        Vec3 center_dist = other.center - center;
+        float distance_sq = dot(center_dist, center_dist);
+        return std::sqrt(distance_sq) + other.radius <= radius;
+    }
+    // Union, sphere.rs:145-163
+    BSphere union_(const BSphere& other) const {
+        if (contains(other)) return *this;
+        if (other.contains(*this)) return other;
+        Vec3 center_diff = other.center - center;
+        float center_diff_s = std::sqrt(dot(center_diff, center_diff));
+        float r = (radius + other.radius + center_diff_s) / 2.f;
+        return BSphere(center + center_diff * (r - radius) / center_diff_s, r);
+    }
+    // Union<Aabb3>, sphere.rs:165-190
+    BSphere union_(const Aabb3& aabb) const;
+    // SurfaceArea, sphere.rs:192-196
+    float surface_area() const { return 4.f * 3.14159265358979323846f * radius * radius; }
+};
+// Contains<Sphere> for Aabb3, aabb3.rs:125-136 (border hits count on both extents)
+inline bool aabb_contains_sphere(const Aabb3& a, const BSphere& s) {
+    return (s.center.x - s.radius) >= a.min.x && (s.center.y - s.radius) >= a.min.y && (s.center.z - s.radius) >= a.min.z &&
+           (s.center.x + s.radius) <= a.max.x && (s.center.y + s.radius) <= a.max.y && (s.center.z + s.radius) <= a.max.z;
+}
+// Union<Sphere> for Aabb3, aabb3.rs:153-163
+inline Aabb3 aabb_union_sphere(const Aabb3& a, const BSphere& s) {
+    return a.grow(Vec3(s.center.x - s.radius, s.center.y - s.radius, s.center.z - s.radius)).grow(s.center + Vec3(s.radius, s.radius, s.radius));
+}
+inline BSphere BSphere::union_(const Aabb3& aabb) const {
+    if (contains(aabb)) return *this;
+    Vec3 dist = aabb.max - aabb.center();
+    float aabb_radius = std::sqrt(dot(dist, dist));
+    if (aabb_contains_sphere(aabb, *this)) return BSphere(aabb.center(), aabb_radius);
+    Vec3 center_diff = aabb.center() - center;
+    float center_diff_s = std::sqrt(dot(center_diff, center_diff));
+    float r = (radius + aabb_radius + center_diff_s) / 2.f;
+    return BSphere(center + center_diff * (r - radius) / center_diff_s, r);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // frustum.rs
 // ---------------------------------------------------------------------------------------------------------
 struct Frustum {
@@ -207,7 +312,8 @@ struct Frustum {
         return true;
     }
     // frustum.rs:78-95: fold max over [left, right, top, bottom, near, far]
-    Relation contains(const Aabb3& b) const {
+    template <class B>  // any PlaneBound: Aabb3 or BSphere
+    Relation contains(const B& b) const {
         const Plane* ps[6] = {&left, &right, &top, &bottom, &near_, &far_};
         Relation cur = In;
         for (int i = 0; i < 6; ++i) {
@@ -224,8 +330,9 @@ struct Frustum {
 struct Variance3 {  // sweep_prune.rs:166-216
     Vec3 csum, csumsq;
     void clear() { csum = Vec3::zero(); csumsq = Vec3::zero(); }
-    void add_bound(const Aabb3& b) {  // :192-199
-        Vec3 sum = b.min + b.max;
+    template <class B>
+    void add_bound(const B& b) {  // :192-199
+        Vec3 sum = b.min_extent() + b.max_extent();
         Vec3 c = sum / 2.0f;
         csum = csum + c;
         csumsq = csumsq + c * c;
@@ -245,7 +352,9 @@ struct Variance3 {  // sweep_prune.rs:166-216
     }
 };
 
-struct SweepAndPrune3 {  // sweep_prune.rs:27-128
+template <class Bnd>
+struct SweepAndPruneT {  // sweep_prune.rs:27-128, generic over the bound type like the reference (A::Bound: Bound + Discrete<A::Bound>)
+    typedef Bnd Aabb3;  // (the body below was written for Aabb3; it only uses min_extent / max_extent / intersects)
     int sweep_axis = 0;
     Variance3 variance;
     // find_collider_pairs, :69-128. `bounds` is re-sorted in place (stable), `perm[k]` = original index of the
@@ -260,11 +369,11 @@ struct SweepAndPrune3 {  // sweep_prune.rs:27-128
         const int ax = sweep_axis;
         // slice::sort_by is a stable merge sort; comparator :80-90 (NaN compares Equal)
         auto cmp3 = [&](const Aabb3& a, const Aabb3& b) -> int {
-            float am = a.min[ax], bm = b.min[ax];
+            float am = a.min_extent()[ax], bm = b.min_extent()[ax];
             if (am < bm) return -1;
             if (am > bm) return 1;
             if (am == bm) {
-                float ax_ = a.max[ax], bx_ = b.max[ax];
+                float ax_ = a.max_extent()[ax], bx_ = b.max_extent()[ax];
                 if (ax_ < bx_) return -1;
                 if (ax_ > bx_) return 1;
                 return 0;  // Equal, or NaN -> unwrap_or(Equal)
@@ -287,7 +396,7 @@ struct SweepAndPrune3 {  // sweep_prune.rs:27-128
             // active.retain(...) :102-105
             size_t w = 0;
             for (size_t k = 0; k < active.size(); ++k)
-                if (bounds[active[k]].max[ax] >= shape.min[ax]) active[w++] = active[k];
+                if (bounds[active[k]].max_extent()[ax] >= shape.min_extent()[ax]) active[w++] = active[k];
             active.resize(w);
             for (size_t k = 0; k < active.size(); ++k)
                 if (bounds[active[k]].intersects(shape)) pairs.emplace_back(active[k], (uint32_t)shape_index);
@@ -298,6 +407,8 @@ struct SweepAndPrune3 {  // sweep_prune.rs:27-128
         return pairs;
     }
 };
+typedef SweepAndPruneT<Aabb3> SweepAndPrune3;          // SweepAndPrune3<Aabb3>
+typedef SweepAndPruneT<BSphere> SweepAndPrune3Sphere;  // SweepAndPrune3<volume::Sphere>
 
 // ---------------------------------------------------------------------------------------------------------
 // dbvt/mod.rs (insert + refit of bounds + query), dbvt/visitor.rs, dbvt/util.rs

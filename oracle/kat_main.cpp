@@ -423,7 +423,97 @@ static void ray_tests() {
         CHECK(!point_ray_intersects(point, Ray(Vec3(1, 0, 0), Vec3(0, 0, 1)))); }
 }
 
+// volume::Sphere (the bounding sphere): every test of tests/sphere.rs, the Sphere cases of tests/aabb.rs and tests/frustum.rs.
+static void bounding_sphere_tests() {
+    {   TEST("tests/sphere.rs:8 test_intersection");
+        BSphere sphere(Vec3(0, 0, 0), 1.f);
+        Vec3 dir = normalize(Vec3(0, 0, -5));
+        Ray r0(Vec3(0, 0, 5), dir), r1(Vec3(std::cos(1.f), 0, 5), dir), r2(Vec3(1, 0, 5), dir), r3(Vec3(2, 0, 5), dir);
+        Vec3 p;
+        CHECK(sphere.intersection(r0, p)); CHECK_V3(0.f, 0.f, 1.f, p); CHECK(sphere.intersects(r0));
+        CHECK(sphere.intersects(r1));
+        CHECK(sphere.intersection(r2, p)); CHECK_V3(1.f, 0.f, 0.f, p); CHECK(sphere.intersects(r2));
+        CHECK(!sphere.intersection(r3, p)); CHECK(!sphere.intersects(r3)); }
+    {   TEST("tests/sphere.rs:50 test_bound");
+        Vec3 point(1, 2, 3), normal(0, 0, 1);
+        BSphere sphere(point, 1.f);
+        CHECK(sphere.relate_plane(Plane::from_point_normal(point, normal)) == Cross);
+        CHECK(sphere.relate_plane(Plane::from_point_normal(point + normal * -3.f, normal)) == In);
+        CHECK(sphere.relate_plane(Plane::from_point_normal(point + normal * 3.f, normal)) == Out); }
+    {   TEST("tests/sphere.rs:73 test_sphere_contains_point");
+        BSphere sphere(Vec3(1, 2, 3), 1.f);
+        CHECK(sphere.contains(Vec3(1, 2.2f, 3))); CHECK(!sphere.contains(Vec3(11, 2.2f, 3))); }
+    {   TEST("tests/sphere.rs:87 test_sphere_contains_line");
+        BSphere sphere(Vec3(1, 2, 3), 1.f);
+        CHECK(sphere.contains_line(Vec3(1, 2, 3), Vec3(1, 2.2f, 3)));
+        CHECK(!sphere.contains_line(Vec3(11, 2, 3), Vec3(11, 2.2f, 3)));
+        CHECK(!sphere.contains_line(Vec3(1, 2, 3), Vec3(11, 2.2f, 3))); }
+    {   TEST("tests/sphere.rs:103 test_sphere_contains_sphere");
+        BSphere sphere(Vec3(1, 2, 3), 1.f);
+        CHECK(sphere.contains(BSphere(Vec3(1, 2, 3), 0.1f)));
+        CHECK(!sphere.contains(BSphere(Vec3(11, 2, 3), 0.1f)));
+        CHECK(!sphere.contains(BSphere(Vec3(1, 2, 3), 10.f))); }
+    {   TEST("tests/sphere.rs:128 test_sphere_contains_aabb");
+        BSphere sphere(Vec3(1, 2, 3), 1.f);
+        CHECK(sphere.contains(Aabb3(Vec3(1, 2, 3), Vec3(1, 2.2f, 3))));
+        CHECK(!sphere.contains(Aabb3(Vec3(11, 2, 3), Vec3(11, 2.2f, 3))));
+        CHECK(!sphere.contains(Aabb3(Vec3(1, 2, 3), Vec3(11, 2.2f, 3))));
+        CHECK(!sphere.contains(Aabb3(Vec3(1, 1.01f, 3), Vec3(1.99f, 2, 3.99f)))); }
+    {   TEST("tests/sphere.rs:146 test_sphere_union_sphere");
+        BSphere base(Vec3(0, 0, 0), 5.f);
+        BSphere u = base.union_(BSphere(Vec3(1, 1, 1), 1.f));
+        CHECK_V3(0.f, 0.f, 0.f, u.center); CHECK_EQF(5.f, u.radius);
+        u = base.union_(BSphere(Vec3(8, 8, 8), 1.f));
+        CHECK_V3(2.8452997f, 2.8452997f, 2.8452997f, u.center); CHECK_EQF(9.928204f, u.radius);
+        u = base.union_(BSphere(Vec3(4, 4, 4), 3.f));
+        CHECK_V3(1.4226499f, 1.4226499f, 1.4226499f, u.center); CHECK_EQF(7.464102f, u.radius); }
+    {   TEST("tests/sphere.rs:183 test_sphere_union_aabb3");
+        BSphere base(Vec3(0, 0, 0), 5.f);
+        BSphere u = base.union_(Aabb3(Vec3(0, 0, 0), Vec3(2, 2, 2)));
+        CHECK_V3(0.f, 0.f, 0.f, u.center); CHECK_EQF(5.f, u.radius);
+        u = base.union_(Aabb3(Vec3(6, 6, 6), Vec3(9, 9, 9)));
+        CHECK_V3(3.0566242f, 3.0566242f, 3.0566242f, u.center); CHECK_EQF(10.294229f, u.radius);
+        u = base.union_(Aabb3(Vec3(4, 4, 4), Vec3(7, 7, 7)));
+        CHECK_V3(2.0566242f, 2.0566242f, 2.0566242f, u.center); CHECK_EQF(8.562178f, u.radius); }
+    {   TEST("tests/sphere.rs:213 test_surface_area");
+        CHECK_EQF(4.f * 3.14159265358979323846f * 2.f * 2.f, BSphere(Vec3(2, 1, -4), 2.f).surface_area()); }
+    {   TEST("tests/aabb.rs:270 test_aabb3_contains_sphere");
+        Aabb3 aabb(Vec3(0, 0, 0), Vec3(10, 10, 10));
+        CHECK(aabb_contains_sphere(aabb, BSphere(Vec3(5, 5, 5), 1.f)));
+        CHECK(!aabb_contains_sphere(aabb, BSphere(Vec3(20, 20, 20), 1.f)));
+        CHECK(!aabb_contains_sphere(aabb, BSphere(Vec3(5, 5, 5), 10.f))); }
+    {   TEST("tests/aabb.rs:329 test_aabb3_union_sphere");
+        Aabb3 base(Vec3(0, 0, 0), Vec3(10, 10, 10));
+        Aabb3 u = aabb_union_sphere(base, BSphere(Vec3(5, 5, 5), 1.f));
+        CHECK_V3(0.f, 0.f, 0.f, u.min); CHECK_V3(10.f, 10.f, 10.f, u.max);
+        u = aabb_union_sphere(base, BSphere(Vec3(14, 14, 14), 1.f));
+        CHECK_V3(0.f, 0.f, 0.f, u.min); CHECK_V3(15.f, 15.f, 15.f, u.max);
+        u = aabb_union_sphere(base, BSphere(Vec3(8, 8, 8), 4.f));
+        CHECK_V3(0.f, 0.f, 0.f, u.min); CHECK_V3(12.f, 12.f, 12.f, u.max); }
+    {   TEST("tests/frustum.rs:8 test_contains");
+        // As written the test builds a 1-DEGREE frustum (`1_f32.to_radians()`), in which a unit sphere 5 units away cannot be `In`:
+        // the reference's code gives Cross / Out / Cross for the three spheres, so the test cannot pass as written (third documented
+        // discrepancy). With a field of view of 1 RADIAN the same code gives exactly the expected In / Cross / Out: pinned on that.
+        Frustum f; CHECK(Frustum::from_mat4(Mat4::perspective_rh_gl(to_radians(1.f), 1.f, 1.f, 10.f), f));
+        const char* names[3] = {"In", "Cross", "Out"};
+        std::printf("DISCREPANCY tests/frustum.rs:8 test_contains expects In, Cross, Out for a 1-degree frustum; the reference's code gives %s, %s, %s\n",
+                    names[f.contains(BSphere(Vec3(0, 0, -5), 1.f))], names[f.contains(BSphere(Vec3(0, 3, -5), 1.f))], names[f.contains(BSphere(Vec3(0, 0, 5), 1.f))]);
+        Frustum g; CHECK(Frustum::from_mat4(Mat4::perspective_rh_gl(1.f, 1.f, 1.f, 10.f), g));
+        CHECK(g.contains(BSphere(Vec3(0, 0, -5), 1.f)) == In);
+        CHECK(g.contains(BSphere(Vec3(0, 3, -5), 1.f)) == Cross);
+        CHECK(g.contains(BSphere(Vec3(0, 0, 5), 1.f)) == Out); }
+    {   TEST("SweepAndPrune3<volume::Sphere>: touching spheres are reported, separated ones are not (sphere.rs:82-91)");
+        std::vector<BSphere> b = {BSphere(Vec3(5, 0, 0), 0.5f), BSphere(Vec3(0, 0, 0), 1.f), BSphere(Vec3(2, 0, 0), 1.f), BSphere(Vec3(2, 2.1f, 0), 1.f)};
+        SweepAndPrune3Sphere sap;
+        std::vector<uint32_t> perm;
+        auto pairs = sap.find_collider_pairs(b, &perm);
+        // sorted by centre.x - r: (0,0,0) r1 [-1], (2,0,0) r1 [1], (2,2.1,0) r1 [1, same max], (5,0,0) r.5 [4.5]
+        CHECK(perm.size() == 4 && perm[0] == 1 && perm[1] == 2 && perm[2] == 3 && perm[3] == 0);
+        CHECK(pairs.size() == 1 && pairs[0].first == 0 && pairs[0].second == 1); }
+}
+
 int main() {
+    bounding_sphere_tests();
     simplex_tests();
     epa_tests();
     gjk_tests();

@@ -308,6 +308,42 @@ void orc_world_aabb_batch(const uint8_t* kind, const float* params, const float*
     }
 }
 
+// ComputeBound<volume::Sphere> for each primitive (primitive3.rs:98-114; quad.rs:71-78, sphere.rs:36-43, cuboid.rs:75-83,
+// cylinder.rs:73-80, capsule.rs:60-67, polyhedron.rs:87-92 + :363-370) followed by Bound::transform_volume (volume/sphere.rs:34-39).
+void orc_world_sphere_batch(const uint8_t* kind, const float* params, const float* xform, const uint32_t* mesh_id,
+                            const float* mesh_verts, const uint32_t* mesh_offsets, uint64_t n, float* out4) {
+    ShapeTable T{kind, params, xform, mesh_id, mesh_verts, mesh_offsets};
+    for (uint64_t i = 0; i < n; ++i) {
+        Shape s = T.shape((uint32_t)i);
+        BSphere b = BSphere::empty();
+        switch (s.kind) {
+            case PARTICLE: break;
+            case QUAD: b.radius = rmax(s.p0, s.p1); break;
+            case SPHERE: b.radius = s.p0; break;
+            case CUBOID: b.radius = rmax(rmax(s.p0, s.p1), s.p2); break;
+            case CYLINDER: b.radius = std::sqrt((s.p1 * s.p1) + (s.p0 * s.p0)); break;
+            case CAPSULE: b.radius = s.p0 + s.p1; break;
+            case POLYHEDRON: {
+                // .map(|p| p.dot(p).sqrt()).max_by(partial_cmp.unwrap_or(Equal)).unwrap_or(0.): max_by keeps the accumulated
+                // element only when it compares Greater than the next one
+                bool any = false;
+                float acc = 0.f;
+                for (uint32_t k = 0; k < s.nverts; ++k) {
+                    Vec3 p(s.verts[3 * k], s.verts[3 * k + 1], s.verts[3 * k + 2]);
+                    float len = std::sqrt(dot(p, p));
+                    if (!any || !(acc > len)) acc = len;
+                    any = true;
+                }
+                b.radius = acc;
+                break;
+            }
+        }
+        BSphere w = b.transform_volume(T.mat((uint32_t)i));
+        float* o = out4 + 4 * i;
+        o[0] = w.center.x; o[1] = w.center.y; o[2] = w.center.z; o[3] = w.radius;
+    }
+}
+
 // ---- broad phase ---------------------------------------------------------------------------------------------
 static Aabb3 box6(const float* a) { Aabb3 b; b.min = Vec3(a[0], a[1], a[2]); b.max = Vec3(a[3], a[4], a[5]); return b; }
 
@@ -319,6 +355,21 @@ uint64_t orc_sap_find_pairs(const float* aabbs, uint64_t n, int32_t* inout_axis,
     std::vector<Aabb3> b(n);
     for (uint64_t i = 0; i < n; ++i) b[i] = box6(aabbs + 6 * i);
     SweepAndPrune3 sap; sap.sweep_axis = *inout_axis;
+    std::vector<uint32_t> perm;
+    auto pairs = sap.find_collider_pairs(b, &perm);
+    *inout_axis = sap.sweep_axis;
+    if (out_perm) std::memcpy(out_perm, perm.data(), n * sizeof(uint32_t));
+    uint64_t w = std::min<uint64_t>(pairs.size(), pair_capacity);
+    for (uint64_t i = 0; i < w; ++i) { out_pairs[2 * i] = pairs[i].first; out_pairs[2 * i + 1] = pairs[i].second; }
+    return pairs.size();
+}
+
+// SweepAndPrune3<volume::Sphere>::find_collider_pairs; spheres: n x {centre xyz, radius}. Same conventions as orc_sap_find_pairs.
+uint64_t orc_sap_find_pairs_spheres(const float* spheres, uint64_t n, int32_t* inout_axis, uint32_t* out_perm, uint32_t* out_pairs,
+                                    uint64_t pair_capacity) {
+    std::vector<BSphere> b(n);
+    for (uint64_t i = 0; i < n; ++i) b[i] = BSphere(Vec3(spheres[4 * i], spheres[4 * i + 1], spheres[4 * i + 2]), spheres[4 * i + 3]);
+    SweepAndPrune3Sphere sap; sap.sweep_axis = *inout_axis;
     std::vector<uint32_t> perm;
     auto pairs = sap.find_collider_pairs(b, &perm);
     *inout_axis = sap.sweep_axis;

@@ -28,6 +28,7 @@ class Oracle:
     def __init__(self):
         self.lib = C.CDLL(LIB_PATH)
         self.lib.orc_sap_find_pairs.restype = C.c_uint64
+        self.lib.orc_sap_find_pairs_spheres.restype = C.c_uint64
         self.lib.orc_dbvt_build.restype = C.c_void_p
         for f in ("orc_dbvt_query_aabb", "orc_dbvt_query_ray", "orc_dbvt_query_frustum", "orc_dbvt_find_collider_pairs"):
             getattr(self.lib, f).restype = C.c_uint64
@@ -185,7 +186,27 @@ class Oracle:
         self.lib.orc_world_aabb_batch(_p(kind), _p(params), _p(xform), _p(mesh_id), _p(mv), _p(mo), C.c_uint64(len(kind)), _p(out))
         return out
 
+    def world_spheres(self, scene):
+        kind, params, mesh_id, mv, mo = self._scene_args(scene)
+        xform = np.ascontiguousarray(scene["xform"], dtype=np.float32)
+        out = np.empty((len(kind), 4), dtype=np.float32)
+        self.lib.orc_world_sphere_batch(_p(kind), _p(params), _p(xform), _p(mesh_id), _p(mv), _p(mo), C.c_uint64(len(kind)), _p(out))
+        return out
+
     # ---- broad phase -------------------------------------------------------------------------------------
+    def sap_find_pairs_spheres(self, spheres, axis=0):
+        spheres = np.ascontiguousarray(spheres, dtype=np.float32).reshape(-1, 4)
+        n = len(spheres)
+        perm = np.empty(n, dtype=np.uint32)
+        cap = max(1024, 16 * n)
+        while True:
+            pairs = np.empty((cap, 2), dtype=np.uint32)
+            ax = C.c_int32(axis)
+            cnt = self.lib.orc_sap_find_pairs_spheres(_p(spheres), C.c_uint64(n), C.byref(ax), _p(perm), _p(pairs), C.c_uint64(cap))
+            if cnt <= cap:
+                return pairs[:cnt].copy(), perm, int(ax.value)
+            cap = int(cnt)
+
     def sap_find_pairs(self, aabbs, axis=0):
         aabbs = np.ascontiguousarray(aabbs, dtype=np.float32).reshape(-1, 6)
         n = len(aabbs)

@@ -267,3 +267,87 @@ def test_bvh_refit_matches_a_tree_built_over_the_moved_boxes(ctx, oracle):
             assert np.array_equal(np.sort(vals[int(off[q]):int(off[q + 1])]), ot.query_aabb(qb[q]))
         dirty = (rng.random(len(moved)) < 0.2).astype(np.uint8)
         assert np.array_equal(bvh.find_collider_pairs(dirty), ot.find_collider_pairs(dirty))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# volume::Sphere as the bound type
+# ---------------------------------------------------------------------------------------------------------
+def test_world_spheres_parity(ctx, oracle):
+    """ComputeBound<volume::Sphere> + transform_volume for every primitive kind and for polyhedra: bit-exact."""
+    lib = scenes.mesh_library(32, seed=0xB3D0C402)
+    a = scenes.all_kinds_pairs(20_000, seed=0xB3D0C403)
+    p = scenes.polyhedron_pairs(20_000, library=lib, seed=0xB3D0C403)
+    rng = np.random.default_rng(1)
+    scene = dict(a)
+    scene["kind"] = np.where(rng.random(40_000) < 0.2, p["kind"], a["kind"]).astype(np.uint8)
+    scene["mesh_id"], (scene["mesh_verts"], scene["mesh_offsets"]) = p["mesh_id"], lib
+    meshes = b3.MeshLibrary(ctx, *lib)
+    shapes = b3.ShapeSet(ctx, scene["kind"], scene["params"], scene["xform"], scene["mesh_id"], meshes)
+    got = broad.world_spheres(shapes)
+    want = oracle.world_spheres(scene)
+    assert got.tobytes() == want.tobytes()
+    assert len(np.unique(scene["kind"])) == 7 and (got[:, 3] > 0).sum() > 30_000
+
+
+def _sphere_scene(n, seed, density=4.0):
+    L = (n / density) ** (1.0 / 3.0)
+    idx = np.arange(n, dtype=np.uint64)
+    c = np.stack([scenes.uniform(seed, 110 + k, idx, 0.0, L) for k in range(3)], axis=1)
+    r = scenes.uniform(seed, 113, idx, 0.1, 0.6)
+    return np.ascontiguousarray(np.concatenate([c, r[:, None]], axis=1), dtype=np.float32)
+
+
+def test_sap_spheres_parity_and_axis_sequence(ctx, oracle):
+    """SweepAndPrune3<volume::Sphere> on a random scene, three consecutive calls (axis hand-over): permutation, pair list in
+    the reference's order and next axis identical to the oracle; then the world spheres of a shape set, fed straight in."""
+    spheres = _sphere_scene(60_000, 0xB3D0C411)
+    sap = broad.SweepAndPrune3Sphere.new(ctx)
+    axis = 0
+    for _ in range(3):
+        pairs, perm = sap.find_collider_pairs(spheres)
+        opairs, operm, oaxis = oracle.sap_find_pairs_spheres(spheres, axis)
+        assert np.array_equal(perm, operm)
+        assert len(opairs) > 100_000 and np.array_equal(pairs, opairs)
+        assert sap.get_sweep_axis() == oaxis
+        axis = oaxis
+    scene = scenes.mixed_pairs(15_000, s=1.5, seed=0xB3D0C412)
+    scene["xform"][:, 12:15] *= np.float32(0.35)  # pack the shapes closer so that their bounds overlap
+    shapes = b3.ShapeSet(ctx, scene["kind"], scene["params"], scene["xform"])
+    ws = broad.world_spheres(shapes)
+    pairs, perm = broad.SweepAndPrune3Sphere.new(ctx).find_collider_pairs(ws)
+    opairs, operm, _ = oracle.sap_find_pairs_spheres(ws, 0)
+    assert np.array_equal(perm, operm) and len(opairs) > 10_000 and np.array_equal(pairs, opairs)
+
+
+def test_sap_spheres_edge_cases(ctx, oracle):
+    sap = broad.SweepAndPrune3Sphere.new(ctx)
+    p, perm = sap.find_collider_pairs(np.zeros((0, 4), dtype=np.float32))
+    assert len(p) == 0 and len(perm) == 0 and sap.get_sweep_axis() == 0
+    p, perm = sap.find_collider_pairs([[0, 0, 0, 1]])
+    assert len(p) == 0 and sap.get_sweep_axis() == 0
+    # touching spheres ARE pairs (volume/sphere.rs:82-91: <=), unlike touching boxes; coincident zero-radius spheres too
+    s = np.array([[5, 0, 0, 0.5], [0, 0, 0, 1], [2, 0, 0, 1], [2, 2.1, 0, 1], [7, 7, 7, 0], [7, 7, 7, 0], [-0.0, 3, 3, 0.25], [0.0, 3, 3, 0.25]],
+                 dtype=np.float32)
+    for axis in (0, 1, 2):
+        sap = broad.SweepAndPrune3Sphere.with_sweep_axis(axis, ctx)
+        pairs, perm = sap.find_collider_pairs(s)
+        opairs, operm, oaxis = oracle.sap_find_pairs_spheres(s, axis)
+        assert np.array_equal(perm, operm), (axis, perm, operm)
+        assert np.array_equal(pairs, opairs), (axis, pairs, opairs)
+        assert sap.get_sweep_axis() == oaxis
+    # a lattice of radius-0.5 spheres at integer points: every lattice neighbour touches exactly (distance^2 == 1 == (r + r)^2),
+    # many equal sort keys (stable sort), forced capacity retry
+    g = np.stack(np.meshgrid(np.arange(12), np.arange(12), np.arange(12), indexing="ij"), axis=-1).reshape(-1, 3).astype(np.float32)
+    rng = np.random.default_rng(9)
+    g = g[rng.permutation(len(g))]
+    lattice = np.concatenate([g, np.full((len(g), 1), 0.5, dtype=np.float32)], axis=1)
+    pairs, perm = broad.SweepAndPrune3Sphere.new(ctx).find_collider_pairs(lattice, capacity=16)
+    opairs, operm, _ = oracle.sap_find_pairs_spheres(lattice, 0)
+    assert len(opairs) == 3 * 12 * 12 * 11
+    assert np.array_equal(perm, operm) and np.array_equal(pairs, opairs)
+    # large coordinates and tiny radii (the candidate margin is relative to both)
+    far = _sphere_scene(20_000, 0xB3D0C413) * np.float32([1, 1, 1, 0.02]) + np.float32([1.0e4, -2.0e4, 3.0e3, 0.0])
+    far = np.concatenate([far, far[:2000] + np.float32([0.01, 0.0, 0.0, 0.0])]).astype(np.float32)
+    pairs, perm = broad.SweepAndPrune3Sphere.new(ctx).find_collider_pairs(far)
+    opairs, operm, _ = oracle.sap_find_pairs_spheres(far, 0)
+    assert len(opairs) >= 1000 and np.array_equal(perm, operm) and np.array_equal(pairs, opairs)
