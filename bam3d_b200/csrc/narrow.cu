@@ -235,6 +235,26 @@ B3_DEV void work_range(const uint32_t* ranges, uint32_t n, uint32_t& first, uint
     }
 }
 
+#ifndef B3_WARP_SHAPES_SMEM
+#define B3_WARP_SHAPES_SMEM 1  // warp-per-pair kernels: one copy of a pair's shape records per warp in shared memory (C3: 15.6 -> 13.4 ms)
+#endif
+// Warp-per-pair kernels: every lane would hold the same shape records (28 registers each) for the whole pair, and a call of an
+// out-of-line support function would copy them to local memory first. Lane 0 stages one copy per warp in shared memory instead;
+// the GJK / EPA code reads it with broadcast loads. `sh` = this warp's slots, idx[k] = shape index to load from sets[k].
+template <int N>
+B3_DEV void stage_warp_shapes(Shape* sh, const ShapeSetDev* const (&sets)[N], const uint32_t (&idx)[N]) {
+    __syncwarp();  // the previous pair's readers are done
+    if ((threadIdx.x & 31u) == 0) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            Shape t;
+            load_pair_shape(t, *sets[k], idx[k]);
+            sh[k] = t;
+        }
+    }
+    __syncwarp();
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // GJK::intersect
 // ------------------------------------------------------------------------------------------------------------
@@ -247,11 +267,21 @@ __global__ void __launch_bounds__(TPB) gjk_intersect_kernel(ShapeSetDev S, const
     for (uint32_t slot = first; slot < end; slot += stride) {
         uint32_t p = order ? __ldg(order + slot) : slot;
         uint2 pr = __ldg(pairs + p);
-        Shape L, R;
-        load_pair_shape(L, S, pr.x);
-        load_pair_shape(R, S, pr.y);
         Simplex<false> s;
-        uint8_t st = gjk_intersect<WARP, false>(L, R, cfg.max_iterations, s);
+        uint8_t st;
+        if constexpr (WARP && B3_WARP_SHAPES_SMEM) {
+            __shared__ Shape sh_all[WARPS_PER_BLOCK * 2];
+            Shape* sh = sh_all + 2 * (threadIdx.x / 32);
+            const ShapeSetDev* const sets[2] = {&S, &S};
+            const uint32_t idx[2] = {pr.x, pr.y};
+            stage_warp_shapes<2>(sh, sets, idx);
+            st = gjk_intersect<WARP, false>(sh[0], sh[1], cfg.max_iterations, s);
+        } else {
+            Shape L, R;
+            load_pair_shape(L, S, pr.x);
+            load_pair_shape(R, S, pr.y);
+            st = gjk_intersect<WARP, false>(L, R, cfg.max_iterations, s);
+        }
         if (!WARP || (threadIdx.x & 31) == 0) status[p] = st;
     }
 }
@@ -318,9 +348,6 @@ __global__ void __launch_bounds__(TPB) gjk_intersect_survivors_kernel(ShapeSetDe
 // ------------------------------------------------------------------------------------------------------------
 // GJK::intersection = intersect + EPA3::process (FullResolution) or Contact::new(CollisionOnly)
 // ------------------------------------------------------------------------------------------------------------
-#ifndef B3_WARP_SHAPES_SMEM
-#define B3_WARP_SHAPES_SMEM 1  // warp-per-pair contact kernel: one copy of the two shape records per warp in shared memory (C3: 15.6 -> 13.4 ms)
-#endif
 #ifndef B3_WARP_MIN_BLOCKS
 #define B3_WARP_MIN_BLOCKS (B3_WARP_SHAPES_SMEM ? 6 : 1)  // 6 x (4 polytope slices + shapes) = 205 KB of shared memory: the most that fits
 #endif
@@ -789,11 +816,21 @@ __global__ void __launch_bounds__(TPB) gjk_distance_kernel(ShapeSetDev S, const 
     for (uint32_t slot = first; slot < end; slot += stride) {
         uint32_t p = order ? __ldg(order + slot) : slot;
         uint2 pr = __ldg(pairs + p);
-        Shape L, R;
-        load_pair_shape(L, S, pr.x);
-        load_pair_shape(R, S, pr.y);
         float rv = 0.f, geo = 0.f;
-        uint8_t st = gjk_distance<WARP>(L, R, cfg.distance_tolerance, cfg.max_iterations, rv, geo);
+        uint8_t st;
+        if constexpr (WARP && B3_WARP_SHAPES_SMEM) {
+            __shared__ Shape sh_all[WARPS_PER_BLOCK * 2];
+            Shape* sh = sh_all + 2 * (threadIdx.x / 32);
+            const ShapeSetDev* const sets[2] = {&S, &S};
+            const uint32_t idx[2] = {pr.x, pr.y};
+            stage_warp_shapes<2>(sh, sets, idx);
+            st = gjk_distance<WARP>(sh[0], sh[1], cfg.distance_tolerance, cfg.max_iterations, rv, geo);
+        } else {
+            Shape L, R;
+            load_pair_shape(L, S, pr.x);
+            load_pair_shape(R, S, pr.y);
+            st = gjk_distance<WARP>(L, R, cfg.distance_tolerance, cfg.max_iterations, rv, geo);
+        }
         if (st != ST_OK) { rv = 0.f; geo = 0.f; }
         if (!WARP || (threadIdx.x & 31) == 0) { out_ref[p] = rv; out_geo[p] = geo; status[p] = st; }
     }
@@ -811,17 +848,27 @@ __global__ void __launch_bounds__(TPB) gjk_toi_kernel(ShapeSetDev S0, ShapeSetDe
     for (uint32_t slot = first; slot < end; slot += stride) {
         uint32_t p = order ? __ldg(order + slot) : slot;
         uint2 pr = __ldg(pairs + p);
-        Shape L0, R0, L1, R1;
-        load_pair_shape(L0, S0, pr.x);
-        load_pair_shape(R0, S0, pr.y);
-        // only the end transforms' affine columns are read (translation deltas; the right end transform's
-        // rotation/scale for the contact point)
-        load_shape(L1, S1.recs, pr.x);
-        load_shape(R1, S1.recs, pr.y);
         ContactOut c;
         c.normal = v3(0.f, 0.f, 0.f); c.depth = 0.f; c.point = v3(0.f, 0.f, 0.f);
         float toi = 0.f;
-        uint8_t st = gjk_time_of_impact<WARP>(L0, L1, R0, R1, cfg.continuous_tolerance, cfg.toi_iteration_cap, c, toi);
+        uint8_t st;
+        if constexpr (WARP && B3_WARP_SHAPES_SMEM) {
+            __shared__ Shape sh_all[WARPS_PER_BLOCK * 4];
+            Shape* sh = sh_all + 4 * (threadIdx.x / 32);
+            const ShapeSetDev* const sets[4] = {&S0, &S0, &S1, &S1};
+            const uint32_t idx[4] = {pr.x, pr.y, pr.x, pr.y};
+            stage_warp_shapes<4>(sh, sets, idx);
+            st = gjk_time_of_impact<WARP>(sh[0], sh[2], sh[1], sh[3], cfg.continuous_tolerance, cfg.toi_iteration_cap, c, toi);
+        } else {
+            Shape L0, R0, L1, R1;
+            load_pair_shape(L0, S0, pr.x);
+            load_pair_shape(R0, S0, pr.y);
+            // only the end transforms' affine columns are read (translation deltas; the right end transform's
+            // rotation/scale for the contact point)
+            load_shape(L1, S1.recs, pr.x);
+            load_shape(R1, S1.recs, pr.y);
+            st = gjk_time_of_impact<WARP>(L0, L1, R0, R1, cfg.continuous_tolerance, cfg.toi_iteration_cap, c, toi);
+        }
         if (st != ST_OK) { c.normal = v3(0.f, 0.f, 0.f); c.depth = 0.f; c.point = v3(0.f, 0.f, 0.f); toi = 0.f; }
         if (!WARP || (threadIdx.x & 31) == 0) {
             contacts[2 * (size_t)p] = make_float4(c.normal.x, c.normal.y, c.normal.z, c.depth);

@@ -23,7 +23,15 @@ def child(args):
     import bam3d_b200 as b3
     import bench
     wl, n = args.workload, args.pairs
-    scene = bench.make_scene(wl, n, 0)
+    # c3i / c3d / c3t: GJK intersect / distance / time of impact on the C3 polyhedron scene (the warp-per-pair kernels)
+    poly_mode = {"c3i": "intersect", "c3d": "distance", "c3t": "toi"}.get(wl)
+    if poly_mode:
+        from bam3d_b200 import scenes
+        scene = bench.make_scene("c3", n, 0)
+        scene["xform_end"] = scenes.end_transforms(scene)
+        wl = {"intersect": "c1", "distance": "dist", "toi": "toi"}[poly_mode]
+    else:
+        scene = bench.make_scene(wl, n, 0)
     ctx = b3.Context(0)
     gjk = b3.GJK.new(ctx)
     dev = torch.device("cuda:0")
@@ -39,6 +47,8 @@ def child(args):
     def step():
         if wl == "c1":
             gjk.intersect_dev(shapes, p(d_pairs), n, p(d_status))
+        elif wl == "dist":
+            gjk.distance_dev(shapes, p(d_pairs), n, p(d_contacts), C.c_void_p(d_contacts.data_ptr() + 4 * n), p(d_status))
         elif wl == "toi":
             gjk.intersection_time_of_impact_dev(shapes, shapes_end, p(d_pairs), n, p(d_contacts), p(d_status))
         else:
@@ -71,6 +81,10 @@ def child(args):
         orc = Oracle()
         if wl == "c1":
             ok = np.array_equal(orc.intersect(sub, nthreads=16)[1], st[:m])
+        elif wl == "dist":
+            oref, ogeo, _, ost = orc.distance(sub, nthreads=16)
+            flat = d_contacts.cpu().numpy()
+            ok = np.array_equal(ost, st[:m]) and np.array_equal(oref[ost == 0], flat[:m][ost == 0]) and np.array_equal(ogeo[ost == 0], flat[n:n + m][ost == 0])
         elif wl == "toi":
             oc, _, ost = orc.toi(sub, scene["xform_end"], nthreads=16)
             ok = np.array_equal(ost, st[:m]) and np.array_equal(oc[ost == 0][:, 7], ct[:m][ost == 0][:, 7])
