@@ -379,52 +379,37 @@ __global__ void __launch_bounds__(TPB, WARP ? B3_WARP_MIN_BLOCKS : 1) gjk_contac
     for (uint32_t slot = first; slot < end; slot += stride) {
         uint32_t p = order ? __ldg(order + slot) : slot;
         uint2 pr = __ldg(pairs + p);
-#if B3_WARP_SHAPES_SMEM
-        // Warp-per-pair: every lane would hold the same two shape records (2 x 28 registers) for the whole pair. One copy
-        // per warp in shared memory instead (broadcast reads where the support function needs them) leaves the registers
-        // to the vertex scan and lets more warps be resident.
-        Shape Lreg, Rreg;
-        const Shape* Lp = &Lreg;
-        const Shape* Rp = &Rreg;
-        if constexpr (WARP) {
+        auto run_pair = [&](const Shape& L, const Shape& R) {
+            Simplex<true> s;
+            uint8_t st = gjk_intersect<WARP, true>(L, R, cfg.max_iterations, s);
+            ContactOut c;
+            c.normal = v3(0.f, 0.f, 0.f); c.depth = 0.f; c.point = v3(0.f, 0.f, 0.f);
+            if (st == ST_OK && strategy == 0) {
+                if (WARP) st = epa_process_warp(L, R, s, cfg.epa_tolerance, cfg.max_iterations, reinterpret_cast<WarpPolytopeSmem*>(dyn_smem)[threadIdx.x / 32], c);
+                else st = epa_process<false>(L, R, s, cfg.epa_tolerance, cfg.max_iterations, P, c);
+                if (st != ST_OK) { c.normal = v3(0.f, 0.f, 0.f); c.depth = 0.f; c.point = v3(0.f, 0.f, 0.f); }
+            }
+            if (!WARP || (threadIdx.x & 31) == 0) {
+                contacts[2 * (size_t)p] = make_float4(c.normal.x, c.normal.y, c.normal.z, c.depth);
+                contacts[2 * (size_t)p + 1] = make_float4(c.point.x, c.point.y, c.point.z, 0.f);
+                status[p] = st;
+                if (st == ST_CAPACITY) {  // hand the pair to the overflow tier
+                    overflow_append(ovf_scratch, p);
+                }
+            }
+        };
+        if constexpr (WARP && B3_WARP_SHAPES_SMEM) {
+            // one copy of the pair's two shape records per warp, behind the polytope slices (stage_warp_shapes)
             Shape* sh = reinterpret_cast<Shape*>(dyn_smem + warp_shapes_offset()) + 2 * (threadIdx.x / 32);
-            __syncwarp();
-            if ((threadIdx.x & 31) == 0) {
-                Shape t;
-                load_pair_shape(t, S, pr.x);
-                sh[0] = t;
-                load_pair_shape(t, S, pr.y);
-                sh[1] = t;
-            }
-            __syncwarp();
-            Lp = sh; Rp = sh + 1;
+            const ShapeSetDev* const sets[2] = {&S, &S};
+            const uint32_t idx[2] = {pr.x, pr.y};
+            stage_warp_shapes<2>(sh, sets, idx);
+            run_pair(sh[0], sh[1]);
         } else {
-            load_pair_shape(Lreg, S, pr.x);
-            load_pair_shape(Rreg, S, pr.y);
-        }
-        const Shape& L = *Lp;
-        const Shape& R = *Rp;
-#else
-        Shape L, R;
-        load_pair_shape(L, S, pr.x);
-        load_pair_shape(R, S, pr.y);
-#endif
-        Simplex<true> s;
-        uint8_t st = gjk_intersect<WARP, true>(L, R, cfg.max_iterations, s);
-        ContactOut c;
-        c.normal = v3(0.f, 0.f, 0.f); c.depth = 0.f; c.point = v3(0.f, 0.f, 0.f);
-        if (st == ST_OK && strategy == 0) {
-            if (WARP) st = epa_process_warp(L, R, s, cfg.epa_tolerance, cfg.max_iterations, reinterpret_cast<WarpPolytopeSmem*>(dyn_smem)[threadIdx.x / 32], c);
-            else st = epa_process<false>(L, R, s, cfg.epa_tolerance, cfg.max_iterations, P, c);
-            if (st != ST_OK) { c.normal = v3(0.f, 0.f, 0.f); c.depth = 0.f; c.point = v3(0.f, 0.f, 0.f); }
-        }
-        if (!WARP || (threadIdx.x & 31) == 0) {
-            contacts[2 * (size_t)p] = make_float4(c.normal.x, c.normal.y, c.normal.z, c.depth);
-            contacts[2 * (size_t)p + 1] = make_float4(c.point.x, c.point.y, c.point.z, 0.f);
-            status[p] = st;
-            if (st == ST_CAPACITY) {  // hand the pair to the overflow tier
-                overflow_append(ovf_scratch, p);
-            }
+            Shape L, R;
+            load_pair_shape(L, S, pr.x);
+            load_pair_shape(R, S, pr.y);
+            run_pair(L, R);
         }
         if (WARP) __syncwarp();
     }
