@@ -264,4 +264,43 @@ private:
     int axis_;
 };
 
+struct Sphere { Vec3 center; float radius; };  // volume/sphere.rs:8-15 (the bounding sphere; 4 contiguous f32)
+
+// ComputeBound<volume::Sphere> + Bound::transform_volume for every shape of a set (primitive3.rs:98-114, volume/sphere.rs:34-39)
+inline std::vector<Sphere> world_spheres(const Context& ctx, const ShapeSet& shapes) {
+    std::vector<Sphere> out(bam3d_shapes_count(shapes.handle()));
+    ctx.check(bam3d_shapes_world_spheres(ctx.handle(), shapes.handle(), reinterpret_cast<float*>(out.data())));
+    return out;
+}
+
+// SweepAndPrune3<volume::Sphere>: same interface as SweepAndPrune3; touching spheres are reported (Sphere::intersects is <=).
+class SweepAndPrune3Sphere {
+public:
+    explicit SweepAndPrune3Sphere(const Context& ctx, int sweep_axis = 0) : ctx_(ctx), axis_(sweep_axis) {}
+    int get_sweep_axis() const { return axis_; }
+    std::vector<std::pair<size_t, size_t>> find_collider_pairs(std::vector<Sphere>& shapes) {
+        const uint64_t n = shapes.size();
+        std::vector<uint32_t> perm(n), pairs;
+        uint64_t cap = 8 * n + 1024, count = 0;
+        for (;;) {
+            pairs.resize(2 * cap);
+            int32_t axis = axis_;
+            int32_t rc = bam3d_sap_find_pairs_spheres(ctx_.handle(), reinterpret_cast<const float*>(shapes.data()), n, &axis, perm.data(), pairs.data(), cap, &count);
+            if (rc == BAM3D_ERR_CAPACITY && count > cap) { cap = count; continue; }
+            ctx_.check(rc);
+            axis_ = axis;
+            break;
+        }
+        std::vector<Sphere> sorted(n);
+        for (uint64_t k = 0; k < n; ++k) sorted[k] = shapes[perm[k]];
+        shapes.swap(sorted);
+        std::vector<std::pair<size_t, size_t>> out(count);
+        for (uint64_t k = 0; k < count; ++k) out[k] = {pairs[2 * k], pairs[2 * k + 1]};
+        return out;
+    }
+private:
+    const Context& ctx_;
+    int axis_;
+};
+
 }  // namespace bam3d

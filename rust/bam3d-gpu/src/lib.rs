@@ -2,7 +2,7 @@
 //! the ABI takes and exposes batched `GJK` / `SweepAndPrune3` calls with the crate's own types.
 //! SOURCE ONLY: this repository's build image has no cargo / rustc, so this file is not compiled or tested here; the
 //! compiled host layer with the same shape is include/bam3d.hpp (C++), exercised by tests/cpp/kat_gpu.cpp.
-use bam3d::{Aabb3, CollisionStrategy, Contact, Primitive3, Ray};
+use bam3d::{Aabb3, CollisionStrategy, Contact, Primitive3, Ray, Sphere};
 use glam::{Mat4, Vec3};
 use std::os::raw::{c_char, c_void};
 
@@ -34,6 +34,9 @@ extern "C" {
                                   count: *mut u64, shard: u32, n_shards: u32) -> i32;
     fn bam3d_ray_cast(c: *mut ctx, s: *const c_void, rays: *const f32, n_rays: u64, casts: *const u32, n: u64, query: i32,
                       points: *mut f32, status: *mut u8) -> i32;
+    fn bam3d_shapes_world_spheres(c: *mut ctx, s: *const c_void, out: *mut f32) -> i32;
+    fn bam3d_sap_find_pairs_spheres(c: *mut ctx, spheres: *const f32, n: u64, axis: *mut i32, perm: *mut u32, pairs: *mut u32, cap: u64,
+                                    count: *mut u64) -> i32;
     fn bam3d_host_alloc(c: *mut ctx, bytes: u64, out: *mut *mut c_void) -> i32;
     fn bam3d_host_free(c: *mut ctx, p: *mut c_void);
     fn bam3d_frames_create(c: *mut ctx, kind: *const u8, params: *const f32, xform: *const f32, mesh_id: *const u32, n_shapes: u32,
@@ -102,6 +105,33 @@ pub fn intersection_batch(ctx: &Context, strategy: &CollisionStrategy, shapes: &
         let mut k = Contact::new_with_point(strategy.clone(), Vec3::new(c.normal[0], c.normal[1], c.normal[2]), c.penetration_depth,
                                             Vec3::new(c.contact_point[0], c.contact_point[1], c.contact_point[2]));
         k.time_of_impact = c.time_of_impact; Some(k) } else { None }).collect())
+}
+
+/// `SweepAndPrune3<volume::Sphere>::find_collider_pairs` on the device (`bam3d::Sphere` = the bounding sphere of volume/sphere.rs):
+/// re-sorts `shapes` like the reference and returns indices into it; touching spheres are reported (`Sphere::intersects` is `<=`).
+pub fn sap_find_collider_pairs_spheres(ctx: &Context, sweep_axis: &mut usize, shapes: &mut [Sphere]) -> Result<Vec<(usize, usize)>, i32> {
+    let n = shapes.len();
+    let flat: Vec<f32> = shapes.iter().flat_map(|s| [s.center.x(), s.center.y(), s.center.z(), s.radius]).collect();
+    let (mut perm, mut cap, mut count) = (vec![0u32; n], 8 * n as u64 + 1024, 0u64);
+    loop {
+        let mut pairs = vec![0u32; 2 * cap as usize];
+        let mut axis = *sweep_axis as i32;
+        let rc = unsafe { bam3d_sap_find_pairs_spheres(ctx.0, flat.as_ptr(), n as u64, &mut axis, perm.as_mut_ptr(), pairs.as_mut_ptr(), cap, &mut count) };
+        if rc == -4 && count > cap { cap = count; continue; } // BAM3D_ERR_CAPACITY: call again with the reported size
+        if rc != 0 { return Err(rc); }
+        *sweep_axis = axis as usize;
+        let sorted: Vec<Sphere> = perm.iter().map(|&k| shapes[k as usize]).collect();
+        shapes.copy_from_slice(&sorted);
+        return Ok((0..count as usize).map(|k| (pairs[2 * k] as usize, pairs[2 * k + 1] as usize)).collect());
+    }
+}
+
+/// `ComputeBound<volume::Sphere>` + `Bound::transform_volume` for every shape of a set.
+pub fn world_spheres(ctx: &Context, shapes: &ShapeSet, n: usize) -> Result<Vec<Sphere>, i32> {
+    let mut out = vec![0f32; 4 * n];
+    let rc = unsafe { bam3d_shapes_world_spheres(ctx.0, shapes.h, out.as_mut_ptr()) };
+    if rc != 0 { return Err(rc); }
+    Ok(out.chunks(4).map(|c| Sphere { center: Vec3::new(c[0], c[1], c[2]), radius: c[3] }).collect())
 }
 
 /// Page-locked host buffer (`bam3d_host_alloc`): what a frame's transforms / pairs / results should live in so that the

@@ -64,6 +64,18 @@ int main() {
         CHECK(pairs.size() == 2);
         if (pairs.size() == 2) { CHECK(pairs[0].first == 0 && pairs[0].second == 1); CHECK(pairs[1].first == 1 && pairs[1].second == 2); }
     }
+    {   // SweepAndPrune3<volume::Sphere>: touching spheres are pairs (volume/sphere.rs:82-91), separated ones are not
+        std::vector<Sphere> shapes = {{{5, 0, 0}, 0.5f}, {{0, 0, 0}, 1.f}, {{2, 0, 0}, 1.f}, {{2, 2.1f, 0}, 1.f}};
+        SweepAndPrune3Sphere sap(ctx);
+        auto pairs = sap.find_collider_pairs(shapes);
+        CHECK(shapes[0].center[0] == 0.f && shapes[1].center[1] == 0.f && shapes[2].center[1] == 2.1f && shapes[3].center[0] == 5.f);
+        CHECK(pairs.size() == 1);
+        if (pairs.size() == 1) CHECK(pairs[0].first == 0 && pairs[0].second == 1);
+        ShapeSet set(ctx, {Primitive3::Cuboid(2, 4, 6), Primitive3::Capsule(1, 0.5f)}, {transform_3d(1, 2, 3), transform_3d(-1, 0, 0)});
+        auto ws = world_spheres(ctx, set);
+        CHECK(ws.size() == 2 && ws[0].radius == 3.f && ws[0].center[0] == 1.f && ws[0].center[2] == 3.f);  // cuboid.rs:75-83: largest half extent
+        CHECK(ws[1].radius == 1.5f && ws[1].center[0] == -1.f);                                            // capsule.rs:60-67
+    }
     {   // FrameQueue: three frames of test_gjk_3d_hit's cuboids moving apart, two in flight, against the one-shot calls
         std::vector<Primitive3> prims = {Primitive3::Cuboid(10, 10, 10), Primitive3::Cuboid(10, 10, 10)};
         std::vector<std::vector<Mat4>> frames = {{transform_3d(15, 0, 0), transform_3d(7, 2, 0)}, {transform_3d(15, 0, 0), transform_3d(6, 2, 0)},

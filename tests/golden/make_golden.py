@@ -62,6 +62,15 @@ def generate(oracle):
         pts, st = oracle.ray_cast(prim[0], r, casts, q)
         rg[name + "_points"], rg[name + "_status"] = pts, st
     out["rays_golden"] = rg
+    # volume::Sphere as the bound type: world bounding spheres of the narrow scene's shapes, and
+    # SweepAndPrune3<volume::Sphere> over them (translations scaled by 0.8 so that more bounds overlap) on every sweep axis
+    ws = oracle.world_spheres(narrow)
+    packed = ws * np.array([0.8, 0.8, 0.8, 1.0], dtype=np.float32)
+    sg = dict(world_spheres=ws, sap_spheres=packed.astype(np.float32))
+    for axis in (0, 1, 2):
+        spairs, sperm, snext = oracle.sap_find_pairs_spheres(sg["sap_spheres"], axis)
+        sg[f"pairs_axis{axis}"], sg[f"perm_axis{axis}"], sg[f"next_axis{axis}"] = spairs, sperm, np.array([snext], dtype=np.int32)
+    out["spheres_golden"] = sg
     return out
 
 

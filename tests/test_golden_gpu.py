@@ -62,3 +62,16 @@ def test_broad_against_golden(ctx):
         assert same(vals[a:b][o], g["frustum_values"][a:b]) and same(rel[a:b][o], g["frustum_relation"][a:b])
     dirty = (np.arange(len(boxes)) % 3 == 0).astype(np.uint8)
     assert same(bvh.find_collider_pairs(dirty), g["collider_pairs"])
+
+
+def test_sphere_bounds_against_golden(ctx):
+    narrow, _, _, _ = make_golden.scenes_for_golden()
+    g = np.load(os.path.join(HERE, "golden", "spheres_golden.npz"))
+    meshes = b3.MeshLibrary(ctx, narrow["mesh_verts"], narrow["mesh_offsets"])
+    s0 = b3.ShapeSet(ctx, narrow["kind"], narrow["params"], narrow["xform"], narrow["mesh_id"], meshes)
+    assert same(broad.world_spheres(s0), g["world_spheres"])
+    for axis in (0, 1, 2):
+        sap = broad.SweepAndPrune3Sphere.with_sweep_axis(axis, ctx)
+        pairs, perm = sap.find_collider_pairs(g["sap_spheres"])
+        assert len(g[f"pairs_axis{axis}"]) > 500
+        assert same(pairs, g[f"pairs_axis{axis}"]) and same(perm, g[f"perm_axis{axis}"]) and sap.get_sweep_axis() == int(g[f"next_axis{axis}"][0])

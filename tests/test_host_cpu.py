@@ -36,6 +36,28 @@ def test_oracle_reproduces_golden_fixtures(oracle):
                 assert a.tobytes() == b.tobytes(), (name, k)
 
 
+def test_oracle_sphere_sweep_matches_its_definition(oracle):
+    """SweepAndPrune3<volume::Sphere> in the oracle against the definition evaluated pair by pair in numpy f32: sorted by the
+    sphere's min extent, (i, j) reported iff i is still active (max_extent_i >= min_extent_j) and Sphere::intersects."""
+    rng = np.random.default_rng(0)
+    s = np.concatenate([rng.random((700, 3)) * 6, rng.random((700, 1)) * 0.5 + 0.1], axis=1).astype(np.float32)
+    s[50:60, 3] = 0.0                         # zero-radius spheres
+    s[100:110] = s[90:100]                    # duplicates (stable sort)
+    for axis in (0, 1, 2):
+        pairs, perm, _ = oracle.sap_find_pairs_spheres(s, axis)
+        ss = s[perm]
+        mn, mx = ss[:, axis] + (-ss[:, 3]), ss[:, axis] + ss[:, 3]
+        assert (np.diff(mn) >= 0).all() and np.array_equal(np.sort(perm), np.arange(len(s)))
+        d = ss[:, None, :3] - ss[None, :, :3]
+        d2 = (d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2]
+        rr = ss[:, None, 3] + ss[None, :, 3]
+        ok = (mx[:, None] >= mn[None, :]) & (d2 <= rr * rr)
+        i, j = np.nonzero(np.triu(ok, 1))
+        want = np.stack([i, j], axis=1)
+        want = want[np.lexsort((want[:, 0], want[:, 1]))].astype(np.uint32)
+        assert len(want) > 1000 and np.array_equal(pairs, want), axis
+
+
 def test_scene_generation_is_sliceable_and_matches_glam(oracle):
     from bam3d_b200 import scenes
     a = scenes.mixed_pairs(1000)
