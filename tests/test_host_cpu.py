@@ -201,3 +201,21 @@ def test_sap_shards_gather_over_gloo_world_size_2(oracle):
         assert p.exitcode == 0
     for rank, counts, same, total in res:
         assert same and sum(counts) == total > 1000 and min(counts) > 0
+
+
+def test_cpp_host_layer_compiles_and_links(gpu_lib, tmp_path):
+    """include/bam3d.hpp (the native host mirror of the crate's API) must compile as C++17 with warnings on and link against
+    libbam3d_gpu.so without a GPU; the program itself runs in the GPU suite (tests/test_cpp_host_gpu.py). The C header alone
+    must also be valid C (the cgo / bindgen / JNI side reads it as C)."""
+    libdir = os.path.join(ROOT, "bam3d_b200")
+    exe = str(tmp_path / "kat_gpu")
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-ffp-contract=off",
+                        os.path.join(ROOT, "tests", "cpp", "kat_gpu.cpp"), "-o", exe, "-L" + libdir, "-lbam3d_gpu",
+                        "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    csrc = tmp_path / "abi.c"
+    csrc.write_text('#include "bam3d_gpu.h"\nint main(void) { return (int)sizeof(bam3d_contact) - 32; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I" + os.path.join(ROOT, "include"), str(csrc),
+                        "-o", str(tmp_path / "abi")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert subprocess.run([str(tmp_path / "abi")]).returncode == 0  # bam3d_contact is 32 bytes in C as well
