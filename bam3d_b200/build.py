@@ -42,7 +42,7 @@ def build(force=False, verbose=False):
 
 def build_variant(name, extra_flags=(), csrc=CSRC):
     """Development: build the same sources with extra nvcc flags (e.g. -DB3_...) into build/variants/lib_<name>.so,
-    for A/B timing with tools/ab_time.py. The product library is untouched."""
+    for A/B timing with tests/tools/ab_time.py. The product library is untouched."""
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     out_dir = os.path.join(HERE, "..", "build", "variants")
     obj_dir = os.path.join(out_dir, "obj_" + name)

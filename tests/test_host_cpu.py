@@ -219,3 +219,92 @@ def test_cpp_host_layer_compiles_and_links(gpu_lib, tmp_path):
                         "-o", str(tmp_path / "abi")], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert subprocess.run([str(tmp_path / "abi")]).returncode == 0  # bam3d_contact is 32 bytes in C as well
+
+
+def test_oracle_aabb_sweep_matches_a_literal_python_replay(oracle):
+    """SweepAndPrune3<Aabb3> + Variance3 in the oracle against a second, literal restatement of sweep_prune.rs:69-128 and
+    :189-214 in Python (stable sort on (min, max) of the sweep axis, the `active` list with its retain, Aabb3 strict overlap
+    aabb3.rs:237-244, sequential f32 sums, variance = csumsq * (csum * csum / n), strict-> argmax from axis 0). The scene has
+    duplicates, exactly touching boxes (not pairs) and equal sort keys (stability)."""
+    f = np.float32
+    rng = np.random.default_rng(5)
+    c = (rng.random((500, 3)) * 8).astype(np.float32)
+    h = (rng.random((500, 3)) * 0.6 + 0.05).astype(np.float32)
+    boxes = np.concatenate([c - h, c + h], axis=1).astype(np.float32)
+    boxes[40:50] = boxes[30:40]                                   # duplicates
+    boxes[60:70, 0] = boxes[50:60, 3]                             # min.x == a neighbour's max.x: touching on x, never a pair
+    boxes[60:70, 3] = boxes[60:70, 0] + f(0.5)
+    boxes[80:120, 0] = np.round(boxes[80:120, 0])                 # many equal sweep keys on x
+    boxes[80:120, 3] = boxes[80:120, 0] + f(1.0)
+    for axis in (0, 1, 2):
+        pairs, perm, next_axis = oracle.sap_find_pairs(boxes, axis)
+        order = sorted(range(len(boxes)), key=lambda k: (boxes[k, axis], boxes[k, 3 + axis]))
+        assert np.array_equal(perm, np.array(order, dtype=np.uint32)), axis
+        s = boxes[order]
+        want, active = [], [0]
+        csum, csumsq = np.zeros(3, dtype=f), np.zeros(3, dtype=f)
+
+        def add_bound(b):
+            cc = (b[:3] + b[3:]) / f(2.0)
+            return csum + cc, csumsq + cc * cc
+        csum, csumsq = add_bound(s[0])
+        for j in range(1, len(s)):
+            active = [i for i in active if s[i, 3 + axis] >= s[j, axis]]
+            for i in active:
+                if all(s[i, k] < s[j, 3 + k] and s[i, 3 + k] > s[j, k] for k in range(3)):
+                    want.append((i, j))
+            active.append(j)
+            csum, csumsq = add_bound(s[j])
+        assert csum.dtype == f and csumsq.dtype == f
+        variance = csumsq * (csum * csum / f(len(s)))
+        want_axis = 0
+        for k in (1, 2):
+            if variance[k] > variance[want_axis]:
+                want_axis = k
+        assert len(want) > 300 and np.array_equal(pairs, np.array(want, dtype=np.uint32)), axis
+        assert next_axis == want_axis, axis
+        sums, vaxis = oracle.variance3(s)
+        assert sums.tobytes() == np.concatenate([csum, csumsq]).tobytes() and vaxis == want_axis, axis
+
+
+def test_oracle_dbvt_queries_match_brute_force(oracle):
+    """DBVT query result SETS in the oracle (dbvt/mod.rs:481-515 with the three visitors) against the leaf predicates applied
+    to every value by brute force in numpy f32: DiscreteVisitor = strict Aabb3 overlap (aabb3.rs:237-244), ray = slab test with
+    the reference's reject rule (aabb3.rs:165-195), DbvtBroadPhase with every value dirty = all strictly overlapping pairs,
+    sorted and unique (broad_phase/dbvt.rs:26-63)."""
+    f = np.float32
+    rng = np.random.default_rng(9)
+    c = (rng.random((800, 3)) * 10).astype(np.float32)
+    h = (rng.random((800, 3)) * 0.7 + 0.05).astype(np.float32)
+    boxes = np.concatenate([c - h, c + h], axis=1).astype(np.float32)
+    tree = oracle.dbvt_build(boxes)
+    assert not tree.stack_overflow()
+    lo, hi = boxes[:, :3], boxes[:, 3:]
+    for q in range(20):
+        qc = (rng.random(3) * 10).astype(np.float32)
+        qb = np.concatenate([qc - f(1.5), qc + f(1.5)]).astype(np.float32)
+        want = np.nonzero(((lo < qb[3:]) & (hi > qb[:3])).all(axis=1))[0]
+        assert np.array_equal(np.sort(tree.query_aabb(qb)), want.astype(np.uint32))
+    n_ray_hits = 0
+    with np.errstate(divide="ignore", invalid="ignore"):
+        for q in range(20):
+            o = (rng.random(3) * 10).astype(np.float32)
+            d = rng.normal(size=3).astype(np.float32)
+            if q % 4 == 0:
+                d[q % 3] = f(0.0)                                  # axis-parallel component: +-inf slabs
+            d = (d / np.sqrt((d * d).sum(dtype=f))).astype(np.float32)
+            inv = f(1.0) / d
+            t1, t2 = (lo - o) * inv, (hi - o) * inv
+            # Rust f32::min/max return the non-NaN operand: np.fmin / np.fmax have the same rule
+            tmin = np.fmax(np.fmax(np.fmin(t1[:, 0], t2[:, 0]), np.fmin(t1[:, 1], t2[:, 1])), np.fmin(t1[:, 2], t2[:, 2]))
+            tmax = np.fmin(np.fmin(np.fmax(t1[:, 0], t2[:, 0]), np.fmax(t1[:, 1], t2[:, 1])), np.fmax(t1[:, 2], t2[:, 2]))
+            hit = ~(((tmin < 0) & (tmax < 0)) | (tmax < tmin))
+            vals, _ = tree.query_ray(np.concatenate([o, d]))
+            assert np.array_equal(np.sort(vals), np.nonzero(hit)[0].astype(np.uint32)), q
+            n_ray_hits += int(hit.sum())
+    assert n_ray_hits > 50
+    ov = ((lo[:, None, :] < hi[None, :, :]) & (hi[:, None, :] > lo[None, :, :])).all(axis=2)
+    i, j = np.nonzero(np.triu(ov, 1))
+    want = np.stack([i, j], axis=1).astype(np.uint32)
+    got = tree.find_collider_pairs(np.ones(len(boxes), dtype=np.uint8))
+    assert len(want) > 200 and np.array_equal(got, want[np.lexsort((want[:, 1], want[:, 0]))])

@@ -1,6 +1,6 @@
 """Development tool: time one workload's resident step for several builds of libbam3d_gpu.so (A/B kernel variants).
 
-  python tools/ab_time.py c2 bam3d_b200/libbam3d_gpu.so gpurun_out/lib_x.so ...
+  python tests/tools/ab_time.py c2 bam3d_b200/libbam3d_gpu.so gpurun_out/lib_x.so ...
 
 Each library runs in its own process (BAM3D_LIB selects it). Prints ms per step (min / median over --steps), the
 event-timed main-kernel ms, and a CRC of (status, contacts) so that variants can be checked for identical output;
@@ -13,7 +13,7 @@ import subprocess
 import sys
 import zlib
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 
