@@ -150,6 +150,8 @@ int32_t bam3d_ctx_create(int32_t device_ordinal, bam3d_ctx** out_ctx) {
     if (const char* e = std::getenv("BAM3D_EPA_OVERLAP")) ctx->opt_epa_overlap = std::atoi(e) != 0;
     if (const char* e = std::getenv("BAM3D_EPA_GLOBAL")) ctx->opt_epa_global_polytopes = std::atoi(e) != 0;
     if (const char* e = std::getenv("BAM3D_INTERSECT_SPLIT")) ctx->opt_intersect_split = std::atoi(e) != 0;
+    if (const char* e = std::getenv("BAM3D_TOI_REFILL")) ctx->opt_toi_refill = std::atoi(e);
+    if (const char* e = std::getenv("BAM3D_INTERSECT_REFILL")) ctx->opt_intersect_refill = std::atoi(e);
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return BAM3D_ERR_CUDA; }
     if (cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_a, cudaEventDisableTiming) != cudaSuccess ||
@@ -186,6 +188,8 @@ int32_t bam3d_ctx_set_option(bam3d_ctx* ctx, const char* name, int32_t value) {
     if (!std::strcmp(name, "epa_overlap")) { ctx->opt_epa_overlap = value != 0; return BAM3D_OK; }
     if (!std::strcmp(name, "epa_global_polytopes")) { ctx->opt_epa_global_polytopes = value != 0; return BAM3D_OK; }
     if (!std::strcmp(name, "intersect_split")) { ctx->opt_intersect_split = value != 0; return BAM3D_OK; }
+    if (!std::strcmp(name, "intersect_refill")) { if (value < 0 || value > 32) return b3_fail(ctx, BAM3D_ERR_ARG, "intersect_refill must be 0 (off) or the number of idle lanes (1..32) that triggers a refill", cudaSuccess); ctx->opt_intersect_refill = value; return BAM3D_OK; }
+    if (!std::strcmp(name, "toi_refill")) { if (value < 0 || value > 32) return b3_fail(ctx, BAM3D_ERR_ARG, "toi_refill must be 0 (off) or the number of idle lanes (1..32) that triggers a refill", cudaSuccess); ctx->opt_toi_refill = value; return BAM3D_OK; }
     if (!std::strcmp(name, "bvh_strategy")) { if (value < 0 || value > 2) return b3_fail(ctx, BAM3D_ERR_ARG, "bvh_strategy must be 0 (auto), 1 (traversal) or 2 (all pairs)", cudaSuccess); ctx->opt_bvh_strategy = value; return BAM3D_OK; }
     if (!std::strcmp(name, "sap_strategy")) { if (value < 0 || value > 2) return b3_fail(ctx, BAM3D_ERR_ARG, "sap_strategy must be 0 (auto), 1 (sweep) or 2 (bvh)", cudaSuccess); ctx->opt_sap_strategy = value; return BAM3D_OK; }
     return b3_fail(ctx, BAM3D_ERR_ARG, "unknown option", cudaSuccess);
@@ -443,13 +447,14 @@ int32_t bam3d_gjk_intersect_dev(bam3d_ctx* ctx, const bam3d_shapes* shapes, cons
     BinScratch B; const BinScratch* pb;
     if ((rc = prepare_bins(ctx, plan, S, (const uint2*)d_pairs, (uint32_t)n, B, &pb))) return rc;
     void* split_scratch = nullptr;
-    if (plan.run_thread && ctx->opt_intersect_split) {
+    const int refill_min = ctx->opt_intersect_refill > 0 ? ctx->opt_intersect_refill : 0;
+    if (plan.run_thread && (ctx->opt_intersect_split || refill_min)) {
         if ((rc = ctx->epa_queue.reserve(ctx, intersect_scratch_bytes((uint32_t)n)))) return rc;
         split_scratch = ctx->epa_queue.ptr;
     }
     { KernelTimer kt(ctx);
       ctx->launches += launch_intersect(ctx->stream, S, (const uint2*)d_pairs, (uint32_t)n, pb, plan.run_thread, plan.run_warp, to_dev(settings),
-                                        split_scratch, d_status); }
+                                        split_scratch, refill_min, d_status); }
     return check_launch(ctx, "gjk_intersect_kernel");
 }
 
@@ -515,9 +520,14 @@ int32_t bam3d_gjk_time_of_impact_dev(bam3d_ctx* ctx, const bam3d_shapes* s0, con
     Plan plan = plan_for(ctx, s0);
     BinScratch B; const BinScratch* pb;
     if ((rc = prepare_bins(ctx, plan, S0, (const uint2*)d_pairs, (uint32_t)n, B, &pb))) return rc;
+    void* cursor = nullptr;
+    if (plan.run_thread && ctx->opt_toi_refill > 0) {
+        if ((rc = ctx->epa_queue.reserve(ctx, 256))) return rc;
+        cursor = ctx->epa_queue.ptr;
+    }
     { KernelTimer kt(ctx);
       ctx->launches += launch_toi(ctx->stream, S0, S1, (const uint2*)d_pairs, (uint32_t)n, pb, plan.run_thread, plan.run_warp, to_dev(settings),
-                                  (float4*)d_contacts, d_status); }
+                                  cursor, ctx->opt_toi_refill, (float4*)d_contacts, d_status); }
     return check_launch(ctx, "gjk_toi_kernel");
 }
 

@@ -25,6 +25,8 @@ struct bam3d_ctx {
     bool opt_binning = true;
     bool opt_epa_tiers = false;   // contact path: shared-memory EPA in size tiers (epa_tiers.cuh) instead of per-thread local-memory EPA
     bool opt_intersect_split = false;  // intersect, thread path: first-support test and the GJK loop as two launches (measured slower on C1: 0.176 vs 0.167 ms)
+    int opt_intersect_refill = 0;  // intersect, thread path: k >= 1 = persistent kernel whose lanes refill once k of a warp are idle (gjk_intersect_refill_kernel)
+    int opt_toi_refill = 8;  // time of impact, thread path: 0 = one pair per thread (1.16 ms per 2^20 mixed pairs); k >= 1 = persistent kernel whose lanes refill once k of a warp are idle (gjk_toi_refill_kernel: 0.56 ms at k = 8)
     bool opt_epa_global_polytopes = true;   // thread-per-pair EPA: polytopes in a global slab (contiguous per thread) instead of local memory
     bool opt_epa_overlap = true;  // contact path: run the EPA overflow tier on the side stream next to the EPA kernel
     int opt_sap_strategy = 0;  // 0 auto, 1 tiled sweep, 2 BVH overlap query

@@ -788,6 +788,81 @@ __global__ void __launch_bounds__(32) gjk_contact_overflow_kernel(ShapeSetDev S,
     }
 }
 
+// Thread-per-pair intersect with lane refill ("intersect_refill" = k): persistent grid, every lane owns one pair at a time, all
+// lanes advance by one iteration of the loop of gjk/mod.rs:96-111 per pass; lanes whose pair is decided wait until k lanes of the
+// warp are idle (or none is busy) and then fetch together, so the fetch path (two record loads + the first support test, which
+// alone decides about half of the pairs) runs with at least k lanes instead of once per finished pair. Same device functions in
+// the same order per pair as gjk_intersect<false, false>: bit-identical results.
+__global__ void __launch_bounds__(TPB) gjk_intersect_refill_kernel(ShapeSetDev S, const uint2* __restrict__ pairs, uint32_t n,
+                                                                   const uint32_t* __restrict__ order, const uint32_t* __restrict__ ranges,
+                                                                   SettingsDev cfg, uint32_t* __restrict__ cursor, int refill_min,
+                                                                   uint8_t* __restrict__ status) {
+    uint32_t begin = 0, end = n;
+    if (ranges) { begin = ranges[0]; end = ranges[1]; }
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t FULL = 0xFFFFFFFFu;
+    bool busy = false, drained = false;
+    uint32_t p = 0, it = 0;
+    Shape L, R;
+    V3 d = v3(0.f, 0.f, 0.f);
+    Simplex<false> s;
+    s.clear();
+    for (;;) {
+        const uint32_t need = __ballot_sync(FULL, !busy && !drained);
+        if (need && (__popc(need) >= refill_min || !__any_sync(FULL, busy))) {
+            const int leader = __ffs(need) - 1;
+            uint32_t base = 0;
+            if ((int)lane == leader) base = atomicAdd(cursor, (uint32_t)__popc(need));
+            base = __shfl_sync(FULL, base, leader);
+            if (!busy && !drained) {
+                const uint32_t off = base + (uint32_t)__popc(need & ((1u << lane) - 1u));
+                if (off >= end - begin) {
+                    drained = true;
+                } else {
+                    p = order ? __ldg(order + begin + off) : begin + off;
+                    const uint2 pr = __ldg(pairs + p);
+                    load_pair_shape(L, S, pr.x);
+                    load_pair_shape(R, S, pr.y);
+                    d = shape_origin(R) - shape_origin(L);
+                    if (is_zero(d)) d = v3(1.f, 1.f, 1.f);
+                    V3 pv, pa;
+                    minkowski_support<false>(L, R, d, pv, pa);
+                    if (dot(pv, d) <= 0.f) {
+                        status[p] = ST_MISS;
+                    } else {
+                        s.clear();
+                        s.push(pv, pa);
+                        d = -d;
+                        it = 0;
+                        busy = true;
+                    }
+                }
+            }
+        }
+        if (!__any_sync(FULL, busy)) {
+            if (!__any_sync(FULL, !drained)) break;
+            continue;  // every fetched pair was decided by its first support point: fetch again
+        }
+        if (busy) {
+            uint8_t st = 0xFF;  // 0xFF: the pair goes on
+            if (it >= cfg.max_iterations) {
+                st = ST_MAX_ITER;  // the reference returns None here too (gjk/mod.rs:112)
+            } else {
+                V3 pv, pa;
+                minkowski_support<false>(L, R, d, pv, pa);
+                if (dot(pv, d) <= 0.f) {
+                    st = ST_MISS;
+                } else {
+                    s.push(pv, pa);
+                    if (reduce_to_closest_feature(s, d)) st = ST_OK;
+                    ++it;
+                }
+            }
+            if (st != 0xFF) { status[p] = st; busy = false; }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // GJK::distance
 // ------------------------------------------------------------------------------------------------------------
@@ -859,6 +934,125 @@ __global__ void __launch_bounds__(TPB) gjk_toi_kernel(ShapeSetDev S0, ShapeSetDe
             contacts[2 * (size_t)p] = make_float4(c.normal.x, c.normal.y, c.normal.z, c.depth);
             contacts[2 * (size_t)p + 1] = make_float4(c.point.x, c.point.y, c.point.z, toi);
             status[p] = st;
+        }
+    }
+}
+
+// Thread-per-pair time of impact with lane refill ("toi_refill"). In gjk_toi_kernel<false> a warp lives as long as its
+// longest sweep: 90 % of the pairs of a mixed scene leave after at most two trips of the `while` loop (gjk/mod.rs:166) while
+// 4.6 % take ten or more (up to 82) and hold 82 % of all trips, so ncu sees 2.6 of 32 lanes active
+// (profiles/r1c_toi_ncu_full.txt). Here the grid is persistent, every LANE owns one pair at a time, all lanes advance by one
+// trip per pass, and a lane whose pair is finished takes the next slot of the analytic range from one cursor (one atomic per
+// warp and pass). The arithmetic of a pair is gjk_time_of_impact<false>'s, operation for operation (same device functions,
+// no contraction), so the results are bit-identical; only the interleaving across lanes changes. The end transforms are
+// read at the start (translation deltas) and the right one again for the contact point, instead of living in registers.
+__global__ void __launch_bounds__(TPB) gjk_toi_refill_kernel(ShapeSetDev S0, ShapeSetDev S1, const uint2* __restrict__ pairs, uint32_t n,
+                                                             const uint32_t* __restrict__ order, const uint32_t* __restrict__ ranges,
+                                                             SettingsDev cfg, uint32_t* __restrict__ cursor, int refill_min,
+                                                             float4* __restrict__ contacts, uint8_t* __restrict__ status) {
+    uint32_t begin = 0, end = n;
+    if (ranges) { begin = ranges[0]; end = ranges[1]; }
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t FULL = 0xFFFFFFFFu;
+    bool busy = false, drained = false;
+    uint32_t p = 0, right_idx = 0, iters = 0;
+    Shape L0, R0;
+    V3 ray = v3(0.f, 0.f, 0.f), v = ray, normal = ray, ray_origin = ray;
+    float lambda = 0.f;
+    Simplex<false> s;
+    s.clear();
+    for (;;) {
+        // lanes without a pair fetch together once `refill_min` of them are waiting (or nothing else is running): the fetch path
+        // (four record loads) then runs with that many lanes instead of once per finished pair
+        const uint32_t need = __ballot_sync(FULL, !busy && !drained);
+        if (need && (__popc(need) >= refill_min || !__any_sync(FULL, busy))) {
+            const int leader = __ffs(need) - 1;
+            uint32_t base = 0;
+            if ((int)lane == leader) base = atomicAdd(cursor, (uint32_t)__popc(need));
+            base = __shfl_sync(FULL, base, leader);
+            if (!busy && !drained) {
+                const uint32_t off = base + (uint32_t)__popc(need & ((1u << lane) - 1u));
+                if (off >= end - begin) {
+                    drained = true;
+                } else {
+                    p = order ? __ldg(order + begin + off) : begin + off;
+                    const uint2 pr = __ldg(pairs + p);
+                    right_idx = pr.y;
+                    load_pair_shape(L0, S0, pr.x);
+                    load_pair_shape(R0, S0, pr.y);
+                    Shape L1, R1;
+                    load_shape(L1, S1.recs, pr.x);
+                    load_shape(R1, S1.recs, pr.y);
+                    const V3 left_lin_vel = shape_origin(L1) - shape_origin(L0);
+                    const V3 right_lin_vel = shape_origin(R1) - shape_origin(R0);
+                    ray = right_lin_vel - left_lin_vel;
+                    lambda = 0.f;
+                    normal = v3(0.f, 0.f, 0.f);
+                    ray_origin = v3(0.f, 0.f, 0.f);
+                    s.clear();
+                    V3 pv, pa;
+                    minkowski_support<false>(L0, R0, -ray, pv, pa);
+                    v = pv;
+                    iters = 0;
+                    busy = true;
+                }
+            }
+        }
+        if (!__any_sync(FULL, busy)) break;
+        if (busy) {
+            uint8_t st = 0xFF;  // 0xFF: the pair goes on
+            if (dot(v, v) > cfg.continuous_tolerance) {
+                if (iters++ >= cfg.toi_iteration_cap) {
+                    st = ST_MAX_ITER;
+                } else {
+                    V3 pv, pa;
+                    minkowski_support<false>(L0, R0, -v, pv, pa);
+                    const float vp = dot(v, pv);
+                    const float vr = dot(v, ray);
+                    if (vp > lambda * vr) {
+                        if (vr > 0.f) {
+                            lambda = vp / vr;
+                            if (lambda > 1.f) {
+                                st = ST_MISS;
+                            } else {
+                                ray_origin = ray * lambda;
+                                s.clear();
+                                normal = -v;
+                            }
+                        } else {
+                            st = ST_MISS;
+                        }
+                    }
+                    if (st == 0xFF) {
+                        if (s.n >= 4) {
+                            st = ST_REF_PANIC;  // unreachable, see gjk_distance
+                        } else {
+                            s.push(pv - ray_origin, pa);
+                            uint8_t cst = ST_OK;
+                            v = closest_point_to_origin(s, cst);
+                            if (cst != ST_OK) st = cst;
+                        }
+                    }
+                }
+            } else {
+                st = (dot(v, v) <= cfg.continuous_tolerance) ? ST_OK : ST_NAN;  // NaN: the loop test and the <= test both fail -> None
+            }
+            if (st != 0xFF) {
+                float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;
+                if (st == ST_OK) {
+                    Shape R1;
+                    load_shape(R1, S1.recs, right_idx);
+                    const V3 nn = -normalize(normal);
+                    const float depth = sqrtf(dot(v, v));
+                    const V3 pt = toi_contact_point(R0, R1, lambda, ray_origin);
+                    c0 = make_float4(nn.x, nn.y, nn.z, depth);
+                    c1 = make_float4(pt.x, pt.y, pt.z, lambda);
+                }
+                contacts[2 * (size_t)p] = c0;
+                contacts[2 * (size_t)p + 1] = c1;
+                status[p] = st;
+                busy = false;
+            }
         }
     }
 }
@@ -945,14 +1139,26 @@ static inline int warp_grid(uint32_t n) { return grid_for(n, WARPS_PER_BLOCK, NU
 
 size_t intersect_scratch_bytes(uint32_t n) { return 256 + (size_t)n * 4; }
 
+static int persistent_grid(const void* kernel) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TPB, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
+    return per_sm * NUM_SMS;
+}
+
 int launch_intersect(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs, uint32_t n, const BinScratch* B, bool run_thread,
-                     bool run_warp, const SettingsDev& cfg, void* d_scratch, uint8_t* d_status) {
+                     bool run_warp, const SettingsDev& cfg, void* d_scratch, int refill_min, uint8_t* d_status) {
     if (n == 0) return 0;
     int launched = 0;
     const uint32_t* order = B ? B->order : nullptr;
     const uint32_t* ranges = B ? B->ranges : nullptr;
     if (run_thread) {
-        if (d_scratch) {
+        if (d_scratch && refill_min > 0) {
+            static const int grid = persistent_grid((const void*)gjk_intersect_refill_kernel);
+            cudaMemsetAsync(d_scratch, 0, 4, st);
+            gjk_intersect_refill_kernel<<<grid, TPB, 0, st>>>(S, d_pairs, n, order, ranges, cfg, reinterpret_cast<uint32_t*>(d_scratch),
+                                                              refill_min > 32 ? 32 : refill_min, d_status);
+            ++launched;
+        } else if (d_scratch) {
             uint32_t* n_survivors = reinterpret_cast<uint32_t*>(d_scratch);
             uint32_t* survivors = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(d_scratch) + 256);
             cudaMemsetAsync(n_survivors, 0, 4, st);
@@ -1132,8 +1338,28 @@ int launch_distance(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs,
                     bool run_warp, const SettingsDev& cfg, float* d_ref, float* d_geo, uint8_t* d_status) {
     B3_LAUNCH(gjk_distance_kernel, 0, S, d_pairs, n, order, ranges, cfg, d_ref, d_geo, d_status)
 }
+static int toi_refill_grid() {
+    static int blocks = 0;
+    if (!blocks) {
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gjk_toi_refill_kernel, TPB, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
+        blocks = per_sm * NUM_SMS;
+    }
+    return blocks;
+}
+// d_cursor: 4 bytes of device scratch for the lane-refill form of the thread path ("toi_refill"); null = one pair per thread.
 int launch_toi(cudaStream_t st, const ShapeSetDev& S0, const ShapeSetDev& S1, const uint2* d_pairs, uint32_t n, const BinScratch* B,
-               bool run_thread, bool run_warp, const SettingsDev& cfg, float4* d_contacts, uint8_t* d_status) {
+               bool run_thread, bool run_warp, const SettingsDev& cfg, void* d_cursor, int refill_min, float4* d_contacts, uint8_t* d_status) {
+    if (run_thread && d_cursor && n) {
+        const uint32_t* order = B ? B->order : nullptr;
+        const uint32_t* ranges = B ? B->ranges : nullptr;
+        int launched = 1;
+        cudaMemsetAsync(d_cursor, 0, 4, st);
+        gjk_toi_refill_kernel<<<toi_refill_grid(), TPB, 0, st>>>(S0, S1, d_pairs, n, order, ranges, cfg, reinterpret_cast<uint32_t*>(d_cursor),
+                                                                 refill_min < 1 ? 1 : (refill_min > 32 ? 32 : refill_min), d_contacts, d_status);
+        if (run_warp) { gjk_toi_kernel<true><<<warp_grid(n), TPB, 0, st>>>(S0, S1, d_pairs, n, order, ranges, cfg, d_contacts, d_status); ++launched; }
+        return launched;
+    }
     B3_LAUNCH(gjk_toi_kernel, 0, S0, S1, d_pairs, n, order, ranges, cfg, d_contacts, d_status)
 }
 

@@ -41,10 +41,11 @@ int launch_bin_pairs(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs
 
 // B may be null (no binning: the selected kernel covers every pair). run_thread / run_warp pick the execution shapes.
 // d_scratch: intersect_scratch_bytes(n) of device memory for the survivor list of the two-launch thread path, or null to
-// run the single-kernel thread path.
+// run the single-kernel thread path. refill_min > 0 (with d_scratch: 4 bytes suffice): the thread path runs as a persistent
+// kernel whose lanes take new pairs once `refill_min` lanes of a warp are idle ("intersect_refill").
 size_t intersect_scratch_bytes(uint32_t n);
 int launch_intersect(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs, uint32_t n, const BinScratch* B,
-                     bool run_thread, bool run_warp, const SettingsDev& cfg, void* d_scratch, uint8_t* d_status);
+                     bool run_thread, bool run_warp, const SettingsDev& cfg, void* d_scratch, int refill_min, uint8_t* d_status);
 // d_overflow_scratch: contact_overflow_scratch_bytes() of device memory for the EPA overflow tier (epa_big.cuh);
 // d_queue: contact_queue_bytes(n) for the GJK -> EPA hit queue of the thread-per-pair path.
 size_t contact_overflow_scratch_bytes();
@@ -62,8 +63,12 @@ int launch_contact(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs, 
 size_t contact_poly_slab_bytes();
 int launch_distance(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs, uint32_t n, const BinScratch* B,
                     bool run_thread, bool run_warp, const SettingsDev& cfg, float* d_ref, float* d_geo, uint8_t* d_status);
+// d_cursor (nullable): 4 bytes of device scratch; when given, the thread path runs as a persistent kernel whose lanes take a new
+// pair when theirs is finished ("toi_refill"; `refill_min` = how many lanes of a warp wait before they fetch together), instead of
+// one pair per thread.
 int launch_toi(cudaStream_t st, const ShapeSetDev& S0, const ShapeSetDev& S1, const uint2* d_pairs, uint32_t n,
-               const BinScratch* B, bool run_thread, bool run_warp, const SettingsDev& cfg, float4* d_contacts, uint8_t* d_status);
+               const BinScratch* B, bool run_thread, bool run_warp, const SettingsDev& cfg, void* d_cursor, int refill_min,
+               float4* d_contacts, uint8_t* d_status);
 // Ray casts against primitives: d_rays = n_rays x 6 f32 (origin, direction; query 2: segment start, end), d_casts = n x
 // (ray index, shape index); query 0 = intersects_transformed, 1 = intersection_transformed, 2 = swept particle.
 int launch_ray_cast(cudaStream_t st, const ShapeSetDev& S, const float* d_rays, const uint2* d_casts, uint64_t n, int query, float* d_points,

@@ -72,7 +72,8 @@ def child(args):
     st = d_status.cpu().numpy()
     ct = d_contacts.cpu().numpy().reshape(n, 8)
     crc = zlib.crc32(ct.tobytes(), zlib.crc32(st.tobytes()))
-    line = f"{os.path.basename(os.environ.get('BAM3D_LIB', 'default')):28s} {wl} n={n} min {min(times):8.3f} ms  med {sorted(times)[len(times) // 2]:8.3f} ms  kernels {kms / max(kcalls, 1):8.3f} ms  crc {crc:08x}"
+    tag = os.path.basename(os.environ.get('BAM3D_LIB', 'default')) + "".join(f" {k}={v}" for k, v in os.environ.items() if k.startswith("BAM3D_") and k != "BAM3D_LIB")
+    line = f"{tag:28s} {wl} n={n} min {min(times):8.3f} ms  med {sorted(times)[len(times) // 2]:8.3f} ms  kernels {kms / max(kcalls, 1):8.3f} ms  crc {crc:08x}"
     if args.check:
         from tests.oracle_ffi import Oracle
         m = args.check
@@ -107,7 +108,9 @@ def main():
     if args.child:
         return child(args)
     for i, lib in enumerate(args.libs or [os.path.join(ROOT, "bam3d_b200", "libbam3d_gpu.so")]):
+        lib, _, extra = lib.partition("@")  # path[@KEY=VALUE[,KEY=VALUE]]: environment switches for this run (e.g. BAM3D_TOI_REFILL=1)
         env = dict(os.environ, BAM3D_LIB=os.path.abspath(lib))
+        env.update(kv.split("=", 1) for kv in extra.split(",") if kv)
         cmd = [sys.executable, os.path.abspath(__file__), args.workload, "--child", "--pairs", str(args.pairs), "--steps", str(args.steps),
                "--check", str(args.check if i == 0 else 0)]
         subprocess.run(cmd, env=env, check=False)
