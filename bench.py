@@ -42,7 +42,7 @@ ALGO_BYTES = {  # algorithmic HBM bytes per pair
 # DRAM traffic of the dominant kernel per launch (bytes), from the committed ncu captures (profiles/r1_*_ncu_full.txt);
 # for C2 it is far above the algorithmic bytes because the EPA polytopes (7.5 KB slab record per resident thread) do not
 # all stay in L2 (DESIGN.md §11 records what was tried against it this round: 24 GB -> 5.4 GB).
-NCU_DRAM_BYTES = {"c1": 223.0e6, "c2": 5.36e9, "c3": 261.8e6}  # c2: profiles/r1c_c2_ncu_full.txt, c3: profiles/r1f_c3_ncu_full.txt
+NCU_DRAM_BYTES = {"c1": 223.0e6, "c2": 5.36e9, "c3": 261.8e6, "toi": 636.5e6}  # c2: profiles/r1c_c2_ncu_full.txt, c3: profiles/r1f_c3_ncu_full.txt, toi: profiles/r1h_toi_ncu_full.txt
 WORKLOAD_DESC = {
     "c1": "C1: GJK intersect, 2^20 random Cuboid-Cuboid pairs per GPU (f32, random transforms, offset U[-2,2]^3)",
     "c2": "C2: GJK+EPA Contact (FullResolution), 2^20 mixed Sphere/Cuboid/Cylinder pairs per GPU (offset U[-1.5,1.5]^3)",
@@ -842,7 +842,7 @@ def run_ours(args):
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture in profiles/"
                                            if NCU_DRAM_BYTES.get(wl) else None,
                          "kernel": {"c1": "gjk_intersect_kernel<false>", "c2": "epa_refill_kernel (+ gjk_phase_kernel, gjk_contact_overflow_kernel)",
-                                    "c3": "gjk_contact_kernel<true>", "toi": "gjk_toi_kernel<false>"}[wl],
+                                    "c3": "gjk_contact_kernel<true>", "toi": "gjk_toi_refill_kernel"}[wl],
                          "kernel_ms_per_launch": per_launch_ms, "algorithmic_bytes_per_pair": ALGO_BYTES[wl], "peak_source": peak_src,
                          "note": "plain-FP32 SIMT, compute/latency bound: see profiles/ for FP32-pipe and branch efficiency"},
             "cpu_baseline": {"value": n_sample / best, "unit": "pairs/s", "cores": cores, "kind": "port",
