@@ -225,6 +225,43 @@ def test_toi_parity(ctx, oracle):
     assert ok.all()
 
 
+def _refill_scene():
+    """Every analytic kind mixed with polyhedra (binned order: thread range + warp range in one call), ragged pair count."""
+    lib = scenes.mesh_library(16, seed=0xB3D000F4)
+    n = 20_011
+    a = scenes.all_kinds_pairs(n, s=3.0, seed=0xB3D000F5)
+    p = scenes.polyhedron_pairs(n, library=lib, s=3.0, seed=0xB3D000F5)
+    use_poly = np.random.default_rng(12).random(2 * n) < 0.05
+    scene = dict(a)
+    scene["kind"] = np.where(use_poly, p["kind"], a["kind"]).astype(np.uint8)
+    scene["mesh_id"] = p["mesh_id"]
+    scene["mesh_verts"], scene["mesh_offsets"] = lib
+    return scene, scenes.end_transforms(scene, span=3.0)
+
+
+@pytest.mark.parametrize("option,values,default", [("toi_refill", (0, 1, 32), 8), ("intersect_refill", (8, 32), 0)])
+def test_lane_refill_switches_change_scheduling_only(ctx, oracle, option, values, default):
+    """The persistent lane-refill kernels (time of impact: the default; intersect: opt-in) and the one-pair-per-thread kernels
+    run the same arithmetic per pair, so every setting returns the oracle's bits."""
+    scene, x1 = _refill_scene()
+    s0, s1 = shapes_of(ctx, scene), shapes_of(ctx, scene, x1)
+    gjk = b3.GJK.new(ctx)
+    oc, _, ost = oracle.toi(scene, x1, nthreads=8)
+    oist = oracle.intersect(scene, nthreads=8)[1]
+    assert (ost == 0).sum() > 300 and (oist == 0).sum() > 500
+    try:
+        for v in values:
+            ctx.set_option(option, v)
+            c, st = gjk.intersection_time_of_impact_batch(s0, s1, scene["pairs"])
+            assert np.array_equal(st, ost), (option, v)
+            assert_f32_equal(f"toi {option}={v}", c[:, [0, 1, 2, 3, 7]], oc[:, [0, 1, 2, 3, 7]], st == 0)
+            assert np.array_equal(gjk.intersect_batch(s0, scene["pairs"]), oist), (option, v)
+    finally:
+        ctx.set_option(option, default)
+    with pytest.raises(b3.Bam3dError):
+        ctx.set_option(option, 33)
+
+
 def test_polyhedron_parity(ctx, oracle):
     """C3 at reduced size: warp-cooperative support (64..256 vertices) vs the sequential scan of the oracle."""
     lib = scenes.mesh_library(256)
