@@ -101,7 +101,11 @@ void bam3d_default_settings(bam3d_gjk_settings* out); /* GJK::new() (gjk/mod.rs:
  * slower: kept as an option); "epa_overlap" (default 1) runs the EPA overflow tier on a side stream next to the EPA kernel;
  * "epa_global_polytopes" (default 1) keeps the thread-per-pair EPA's polytopes in a global-memory slab, one contiguous
  * record per thread (582 MB of scratch), instead of per-thread local memory; "intersect_split"
- * (default 0) runs bam3d_gjk_intersect's thread path as two launches (first-support test, then GJK on the survivors) */
+ * (default 0) runs bam3d_gjk_intersect's thread path as two launches (first-support test, then GJK on the survivors);
+ * "toi_refill" (default 8; 0..32) runs bam3d_gjk_time_of_impact's thread path as a persistent kernel in which every lane owns
+ * one pair and idle lanes fetch new pairs together once that many lanes of a warp are idle (0 = one pair per thread: same
+ * results, half the speed on mixed scenes); "intersect_refill" (default 0; 0..32) is the same scheme for bam3d_gjk_intersect
+ * (same results, measured slower: kept as an option). Every switch changes scheduling only, never a result bit. */
 int32_t bam3d_ctx_set_option(bam3d_ctx* ctx, const char* name, int32_t value);
 /* synchronise, then return and reset the summed device time (ms) and number of bracketed calls ("timing" = 1) */
 int32_t bam3d_ctx_read_timing(bam3d_ctx* ctx, double* out_total_ms, uint64_t* out_count);
