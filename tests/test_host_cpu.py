@@ -395,3 +395,43 @@ def test_oracle_distance_and_time_of_impact_agree_with_closed_forms_for_spheres(
     assert np.array_equal((stt == 0)[clear], want[clear]) and want[clear].sum() > 100
     h = clear & want
     assert np.abs(c[h][:, 7] - t0[h]).max() < 2e-3
+
+
+def test_oracle_ray_casts_agree_with_closed_forms_on_rotated_shapes(oracle):
+    """Ray casts against rotated / translated Spheres and Cuboids (the reference's tests use axis-aligned shapes, and the path
+    inverts the transform for every call): the oracle against the same formulas evaluated in f64 in the shape's frame —
+    sphere.rs:45-76 (miss when the centre is behind the origin, entry point tca - thc) and the slab test of aabb3.rs:165-195
+    through cuboid.rs:85-103. Hit / miss identical away from grazing rays (1e-4), hit points within 2e-4 absolute (coordinates
+    are of order 10)."""
+    from bam3d_b200 import _ffi, scenes
+    sc = scenes.mixed_pairs(4000, s=1.5, kinds=(_ffi.KIND_SPHERE, _ffi.KIND_CUBOID))
+    rays, _, casts = scenes.primitive_rays(sc, 8000)
+    pts, st = oracle.ray_cast(sc, rays, casts, 1, nthreads=4)
+    _, st_bool = oracle.ray_cast(sc, rays, casts, 0, nthreads=4)
+    assert np.array_equal(st_bool == 0, st == 0)                     # Discrete::intersects <=> Continuous::intersection is Some
+    o, d = rays[:, :3].astype(np.float64), rays[:, 3:].astype(np.float64)
+    unit = np.abs(np.linalg.norm(d, axis=1) - 1) < 1e-5              # the scene also holds rays that are not normalised
+    x = sc["xform"].astype(np.float64).reshape(-1, 4, 4)[casts[:, 1]]  # column-major: x[k, column, row]
+    c, axes = x[:, 3, :3], x[:, :3, :3]
+    kind, par = sc["kind"][casts[:, 1]], sc["params"][casts[:, 1]].astype(np.float64)
+
+    l = c - o
+    tca = (l * d).sum(1)
+    d2, r2 = (l * l).sum(1) - tca * tca, par[:, 0] ** 2
+    clear = (kind == _ffi.KIND_SPHERE) & unit & (np.abs(tca) > 1e-4) & (np.abs(d2 - r2) > 1e-4)
+    want = (tca >= 0) & (d2 <= r2)
+    assert clear.sum() > 3000 and want[clear].sum() > 800 and np.array_equal((st == 0)[clear], want[clear])
+    h = clear & want
+    assert np.abs(pts[h] - (o + d * (tca - np.sqrt(np.maximum(r2 - d2, 0)))[:, None])[h]).max() < 2e-4
+
+    lo, ld = np.einsum("kij,kj->ki", axes, o - c), np.einsum("kij,kj->ki", axes, d)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        t1, t2 = (-par[:, :3] - lo) / ld, (par[:, :3] - lo) / ld
+    tmin = np.fmax(np.fmax(np.fmin(t1[:, 0], t2[:, 0]), np.fmin(t1[:, 1], t2[:, 1])), np.fmin(t1[:, 2], t2[:, 2]))
+    tmax = np.fmin(np.fmin(np.fmax(t1[:, 0], t2[:, 0]), np.fmax(t1[:, 1], t2[:, 1])), np.fmax(t1[:, 2], t2[:, 2]))
+    want = ~(((tmin < 0) & (tmax < 0)) | (tmax < tmin))
+    clear = ((kind == _ffi.KIND_CUBOID) & unit & (np.abs(tmax - tmin) > 1e-4) & (np.abs(tmax) > 1e-4) & np.isfinite(tmin) & np.isfinite(tmax)
+             & (np.abs(ld) > 1e-6).all(1))
+    assert clear.sum() > 3000 and want[clear].sum() > 1000 and np.array_equal((st == 0)[clear], want[clear])
+    h = clear & want
+    assert np.abs(pts[h] - (o + d * np.where(tmin >= 0, tmin, tmax)[:, None])[h]).max() < 2e-4
