@@ -435,3 +435,32 @@ def test_oracle_ray_casts_agree_with_closed_forms_on_rotated_shapes(oracle):
     assert clear.sum() > 3000 and want[clear].sum() > 1000 and np.array_equal((st == 0)[clear], want[clear])
     h = clear & want
     assert np.abs(pts[h] - (o + d * np.where(tmin >= 0, tmin, tmax)[:, None])[h]).max() < 2e-4
+
+
+def test_oracle_polyhedron_path_equals_cuboid_path_on_boxes(oracle):
+    """Two code paths of the restatement that must agree bit for bit: a Cuboid and a VertexOnly ConvexPolyhedron holding the
+    cuboid's eight corners in `generate_corners` order (cuboid.rs:45-56) both reduce to the same strict-> fold over the same
+    vertices (util.rs:7-23, polyhedron.rs:135-150), so intersect / contact / distance / time of impact are identical."""
+    from bam3d_b200 import _ffi, scenes
+    n = 3000
+    box = scenes.cuboid_pairs(n, s=1.6)
+    h = box["params"][:, :3]
+    signs = np.array([[1, 1, 1], [-1, 1, 1], [-1, -1, 1], [1, -1, 1], [1, 1, -1], [-1, 1, -1], [-1, -1, -1], [1, -1, -1]], dtype=np.float32)
+    poly = dict(box)
+    poly["kind"] = np.full(2 * n, _ffi.KIND_POLYHEDRON, dtype=np.uint8)
+    poly["params"] = np.zeros((2 * n, 4), dtype=np.float32)
+    poly["mesh_id"] = np.arange(2 * n, dtype=np.uint32)
+    poly["mesh_verts"] = (h[:, None, :] * signs[None, :, :]).reshape(-1, 3).astype(np.float32)
+    poly["mesh_offsets"] = (8 * np.arange(2 * n + 1)).astype(np.uint32)
+    x1 = scenes.end_transforms(box, span=3.0)
+    for a, b in zip(oracle.intersect(box, nthreads=4), oracle.intersect(poly, nthreads=4)):
+        assert np.array_equal(a, b)
+    cb, _, sb = oracle.contact(box, strategy=0, nthreads=4)
+    cp, _, sp = oracle.contact(poly, strategy=0, nthreads=4)
+    assert np.array_equal(sb, sp) and (sb == 0).sum() > 1000 and cb[sb == 0].tobytes() == cp[sp == 0].tobytes()
+    rb, gb, _, db = oracle.distance(box, nthreads=4)
+    rp, gp, _, dp = oracle.distance(poly, nthreads=4)
+    assert np.array_equal(db, dp) and (db == 0).sum() > 1000 and gb[db == 0].tobytes() == gp[dp == 0].tobytes() and rb[db == 0].tobytes() == rp[dp == 0].tobytes()
+    tb, _, stb = oracle.toi(box, x1, nthreads=4)
+    tp, _, stp = oracle.toi(poly, x1, nthreads=4)
+    assert np.array_equal(stb, stp) and (stb == 0).sum() > 100 and tb[stb == 0].tobytes() == tp[stp == 0].tobytes()
