@@ -1139,6 +1139,7 @@ static inline int warp_grid(uint32_t n) { return grid_for(n, WARPS_PER_BLOCK, NU
 
 size_t intersect_scratch_bytes(uint32_t n) { return 256 + (size_t)n * 4; }
 
+// grid of a persistent kernel: as many blocks as are resident at once (occupancy x SMs)
 static int persistent_grid(const void* kernel) {
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TPB, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
@@ -1338,15 +1339,6 @@ int launch_distance(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs,
                     bool run_warp, const SettingsDev& cfg, float* d_ref, float* d_geo, uint8_t* d_status) {
     B3_LAUNCH(gjk_distance_kernel, 0, S, d_pairs, n, order, ranges, cfg, d_ref, d_geo, d_status)
 }
-static int toi_refill_grid() {
-    static int blocks = 0;
-    if (!blocks) {
-        int per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gjk_toi_refill_kernel, TPB, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
-        blocks = per_sm * NUM_SMS;
-    }
-    return blocks;
-}
 // d_cursor: 4 bytes of device scratch for the lane-refill form of the thread path ("toi_refill"); null = one pair per thread.
 int launch_toi(cudaStream_t st, const ShapeSetDev& S0, const ShapeSetDev& S1, const uint2* d_pairs, uint32_t n, const BinScratch* B,
                bool run_thread, bool run_warp, const SettingsDev& cfg, void* d_cursor, int refill_min, float4* d_contacts, uint8_t* d_status) {
@@ -1355,7 +1347,8 @@ int launch_toi(cudaStream_t st, const ShapeSetDev& S0, const ShapeSetDev& S1, co
         const uint32_t* ranges = B ? B->ranges : nullptr;
         int launched = 1;
         cudaMemsetAsync(d_cursor, 0, 4, st);
-        gjk_toi_refill_kernel<<<toi_refill_grid(), TPB, 0, st>>>(S0, S1, d_pairs, n, order, ranges, cfg, reinterpret_cast<uint32_t*>(d_cursor),
+        static const int grid = persistent_grid((const void*)gjk_toi_refill_kernel);
+        gjk_toi_refill_kernel<<<grid, TPB, 0, st>>>(S0, S1, d_pairs, n, order, ranges, cfg, reinterpret_cast<uint32_t*>(d_cursor),
                                                                  refill_min < 1 ? 1 : (refill_min > 32 ? 32 : refill_min), d_contacts, d_status);
         if (run_warp) { gjk_toi_kernel<true><<<warp_grid(n), TPB, 0, st>>>(S0, S1, d_pairs, n, order, ranges, cfg, d_contacts, d_status); ++launched; }
         return launched;
