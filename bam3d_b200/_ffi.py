@@ -11,7 +11,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BAM3D_LIB") or os.path.join(_HERE, "libbam3d_gpu.so")
 
 OK = 0
-ERR_CUDA, ERR_ARG, ERR_NON_AFFINE, ERR_CAPACITY, ERR_OOM = -1, -2, -3, -4, -5
+ERR_CUDA, ERR_ARG, ERR_NON_AFFINE, ERR_CAPACITY, ERR_OOM, ERR_COMM = -1, -2, -3, -4, -5, -6
+UNIQUE_ID_BYTES = 256
 
 KIND_PARTICLE, KIND_QUAD, KIND_SPHERE, KIND_CUBOID, KIND_CYLINDER, KIND_CAPSULE, KIND_POLYHEDRON = range(7)
 STATUS_OK, STATUS_MISS, STATUS_MAX_ITER, STATUS_REF_PANIC, STATUS_NAN, STATUS_CAPACITY, STATUS_UNSUPPORTED = range(7)
@@ -92,6 +93,21 @@ SIGNATURES = {
     "bam3d_frames_submit": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _u64, _PS, _i32, _vp, _vp, C.POINTER(_u64)]),
     "bam3d_frames_wait": (_i32, [_vp, _vp, _u64]),
     "bam3d_frames_free": (None, [_vp, _vp]),
+    "bam3d_frames_submit_gather": (_i32, [_vp, _vp, _vp, _i32, _vp, _vp, _vp, _u64, _PS, _i32, _u64, _vp, _u64, _vp, C.POINTER(_u64)]),
+    "bam3d_frames_gathered": (_i32, [_vp, _vp, _u64, _vp, C.POINTER(_u64)]),
+    "bam3d_comm_unique_id": (_i32, [_vp]),
+    "bam3d_comm_create": (_i32, [_i32, _vp, _i32, _i32, C.POINTER(_vp)]),
+    "bam3d_comm_destroy": (None, [_vp]),
+    "bam3d_comm_rank": (_i32, [_vp]),
+    "bam3d_comm_size": (_i32, [_vp]),
+    "bam3d_comm_stream": (_vp, [_vp]),
+    "bam3d_comm_unavailable_reason": (C.c_char_p, []),
+    "bam3d_gather_contacts_begin": (_i32, [_vp, _vp, _vp, C.POINTER(_u64)]),
+    "bam3d_gather_contacts_finish": (_i32, [_vp, _vp, _u64, _vp, _vp, _u64, _vp, C.POINTER(_u64)]),
+    "bam3d_comm_join": (_i32, [_vp, _vp]),
+    "bam3d_gather_contacts_wait": (_i32, [_vp, _vp, _u64]),
+    "bam3d_gather_contacts_dev": (_i32, [_vp, _vp, _vp, _vp, _vp, _u64, _vp, C.POINTER(_u64)]),
+    "bam3d_gather_contacts": (_i32, [_vp, _vp, _vp, _vp, _u64, _u64, _vp, _u64, _vp, C.POINTER(_u64)]),
 }
 
 _lib = None

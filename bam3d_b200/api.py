@@ -332,6 +332,25 @@ class FrameQueue:
     def submit_time_of_impact(self, xform_start, xform_end, pairs, out_contacts, out_status):
         return self._submit(_ffi.FRAME_TIME_OF_IMPACT, 0, xform_start, xform_end, pairs, out_contacts, out_status)
 
+    def submit_contact_gather(self, comm, strategy, xform, pairs, pair_index_base, out_gathered, out_status):
+        """bam3d_frames_submit_gather: like submit_contact, but wait() leaves the hits of ALL ranks (bam3d_contact40 rows as
+        uint32[capacity, 10]) in out_gathered instead of this rank's dense contacts; gathered(frame) gives the counts."""
+        n = pairs.size // 2
+        frame = C.c_uint64(0)
+        self.ctx.check(self.ctx._lib.bam3d_frames_submit_gather(self.ctx.handle, self.handle, comm.handle, _ffi.FRAME_CONTACT, _ptr(xform), None,
+                                                                _ptr(pairs), n, C.byref(self.gjk.settings), int(strategy), int(pair_index_base),
+                                                                _ptr(out_gathered), out_gathered.size // 10, _ptr(out_status), C.byref(frame)))
+        self._keep[frame.value] = (xform, pairs, out_gathered, out_status)
+        self._n_ranks = comm.n_ranks
+        return frame.value
+
+    def gathered(self, frame):
+        """-> (per-rank record counts, total) of a gather-mode frame, after wait(frame)."""
+        counts = np.zeros(self._n_ranks, dtype=np.uint64)
+        total = C.c_uint64(0)
+        self.ctx.check(self.ctx._lib.bam3d_frames_gathered(self.ctx.handle, self.handle, int(frame), _ptr(counts), C.byref(total)))
+        return counts, int(total.value)
+
     def wait(self, frame):
         try:
             self.ctx.check(self.ctx._lib.bam3d_frames_wait(self.ctx.handle, self.handle, int(frame)))

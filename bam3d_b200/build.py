@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libbam3d_gpu.so")
-SOURCES = ["narrow.cu", "broad.cu", "capi.cu"]
+SOURCES = ["narrow.cu", "broad.cu", "capi.cu", "comm.cu"]
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
@@ -30,12 +30,18 @@ def build(force=False, verbose=False):
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "bam3d_gpu.h"), __file__]
     if not force and _newer(LIB, deps):
         return LIB
-    objs = []
-    for src in SOURCES:
+    objs, procs = [], []
+    for src in SOURCES:  # the translation units compile side by side
         obj = os.path.join(CSRC, src.replace(".cu", ".o"))
         cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
-        subprocess.run(cmd, check=True)
+        procs.append((src, subprocess.Popen(cmd, stderr=subprocess.PIPE, text=True)))
         objs.append(obj)
+    for src, p in procs:
+        err = p.communicate()[1]
+        if p.returncode != 0 or verbose:
+            sys.stderr.write(err)
+        if p.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src}")
     subprocess.run([nvcc, "-shared", "-o", LIB] + objs + ["-lcudart_static", "-lpthread", "-ldl", "-lrt"], check=True)
     return LIB
 

@@ -152,6 +152,7 @@ int32_t bam3d_ctx_create(int32_t device_ordinal, bam3d_ctx** out_ctx) {
     if (const char* e = std::getenv("BAM3D_INTERSECT_SPLIT")) ctx->opt_intersect_split = std::atoi(e) != 0;
     if (const char* e = std::getenv("BAM3D_TOI_REFILL")) ctx->opt_toi_refill = std::atoi(e);
     if (const char* e = std::getenv("BAM3D_INTERSECT_REFILL")) ctx->opt_intersect_refill = std::atoi(e);
+    if (const char* e = std::getenv("BAM3D_DISTANCE_REFILL")) ctx->opt_distance_refill = std::atoi(e);
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return BAM3D_ERR_CUDA; }
     if (cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_a, cudaEventDisableTiming) != cudaSuccess ||
@@ -190,6 +191,7 @@ int32_t bam3d_ctx_set_option(bam3d_ctx* ctx, const char* name, int32_t value) {
     if (!std::strcmp(name, "intersect_split")) { ctx->opt_intersect_split = value != 0; return BAM3D_OK; }
     if (!std::strcmp(name, "intersect_refill")) { if (value < 0 || value > 32) return b3_fail(ctx, BAM3D_ERR_ARG, "intersect_refill must be 0 (off) or the number of idle lanes (1..32) that triggers a refill", cudaSuccess); ctx->opt_intersect_refill = value; return BAM3D_OK; }
     if (!std::strcmp(name, "toi_refill")) { if (value < 0 || value > 32) return b3_fail(ctx, BAM3D_ERR_ARG, "toi_refill must be 0 (off) or the number of idle lanes (1..32) that triggers a refill", cudaSuccess); ctx->opt_toi_refill = value; return BAM3D_OK; }
+    if (!std::strcmp(name, "distance_refill")) { if (value < 0 || value > 32) return b3_fail(ctx, BAM3D_ERR_ARG, "distance_refill must be 0 (off) or the number of idle lanes (1..32) that triggers a refill", cudaSuccess); ctx->opt_distance_refill = value; return BAM3D_OK; }
     if (!std::strcmp(name, "bvh_strategy")) { if (value < 0 || value > 2) return b3_fail(ctx, BAM3D_ERR_ARG, "bvh_strategy must be 0 (auto), 1 (traversal) or 2 (all pairs)", cudaSuccess); ctx->opt_bvh_strategy = value; return BAM3D_OK; }
     if (!std::strcmp(name, "sap_strategy")) { if (value < 0 || value > 2) return b3_fail(ctx, BAM3D_ERR_ARG, "sap_strategy must be 0 (auto), 1 (sweep) or 2 (bvh)", cudaSuccess); ctx->opt_sap_strategy = value; return BAM3D_OK; }
     return b3_fail(ctx, BAM3D_ERR_ARG, "unknown option", cudaSuccess);
@@ -502,9 +504,14 @@ int32_t bam3d_gjk_distance_dev(bam3d_ctx* ctx, const bam3d_shapes* shapes, const
     Plan plan = plan_for(ctx, shapes);
     BinScratch B; const BinScratch* pb;
     if ((rc = prepare_bins(ctx, plan, S, (const uint2*)d_pairs, (uint32_t)n, B, &pb))) return rc;
+    void* cursor = nullptr;
+    if (plan.run_thread && ctx->opt_distance_refill > 0) {
+        if ((rc = ctx->epa_queue.reserve(ctx, 256))) return rc;
+        cursor = ctx->epa_queue.ptr;
+    }
     { KernelTimer kt(ctx);
       ctx->launches += launch_distance(ctx->stream, S, (const uint2*)d_pairs, (uint32_t)n, pb, plan.run_thread, plan.run_warp, to_dev(settings),
-                                       d_ref_value, d_distance, d_status); }
+                                       cursor, ctx->opt_distance_refill, d_ref_value, d_distance, d_status); }
     return check_launch(ctx, "gjk_distance_kernel");
 }
 
@@ -1175,9 +1182,11 @@ int32_t bam3d_bvh_find_collider_pairs(bam3d_ctx* ctx, const bam3d_bvh* t, const 
 // ------------------------------------------------------------------------------------------------------------
 // frame queue: set_transforms + narrow phase + results, `depth` frames in flight
 // ------------------------------------------------------------------------------------------------------------
-// Three streams: host->device copies and the pack kernel on `s_in`, the narrow-phase kernels on the ctx stream (they
-// share the ctx's scratch, so frames compute one after the other), device->host copies on `s_out`. Frame k+1's
-// upload and frame k-1's download therefore run beside frame k's kernels; a slot is reused once its download is done.
+// Streams: host->device copies and the pack kernel on `s_in`, device->host copies on `s_out`, and the narrow-phase kernels
+// on TWO compute lanes (depth >= 2): lane = frame % 2, each lane a private sub-context with its own stream and its own
+// scratch (bins, GJK->EPA queue, polytope slab, overflow list). Frame k+1's upload and frame k-1's download run beside
+// frame k's kernels, and frame k+1's kernels start while frame k's persistent EPA kernel drains — its last ~20 % runs
+// with most lanes idle (no queued pairs left), which one frame alone cannot fill. A slot is reused once its download is done.
 struct bam3d_frames {
     struct Slot {
         bam3d_shapes* shapes = nullptr;
@@ -1191,14 +1200,54 @@ struct bam3d_frames {
         uint64_t frame = ~0ull;      // frame number in flight / last completed in this slot
         bool in_flight = false;
         int32_t launch_rc = BAM3D_OK;
+        // gather mode (bam3d_frames_submit_gather): hits compacted on the device, exchanged over NCCL, and the list of ALL
+        // ranks' hits copied to the host instead of this rank's dense contacts
+        bam3d_contact40* d_compact = nullptr;
+        bam3d_contact40* d_gathered = nullptr;
+        uint64_t* d_count = nullptr;
+        uint64_t gathered_capacity = 0;
+        bam3d_comm* comm = nullptr;   // non-null while a gather is pending for this slot
+        bam3d_ctx* lane = nullptr;
+        uint64_t ticket = 0, total = 0, out_capacity = 0;
+        bam3d_contact40* out_gathered = nullptr;
+        std::vector<uint64_t> counts;
+        cudaEvent_t exchanged = nullptr;
     };
     std::vector<Slot> slots;
     uint64_t max_pairs = 0, next_frame = 0;
     cudaStream_t s_in = nullptr, s_out = nullptr;
+    bam3d_ctx* lanes[2] = {nullptr, nullptr};  // compute lanes (null: the parent ctx computes)
 };
 
-static int32_t frames_finish_slot(bam3d_ctx* ctx, bam3d_frames::Slot& sl) {
+// the compute lane of a frame, with the parent's switches
+static bam3d_ctx* frames_lane(bam3d_ctx* ctx, bam3d_frames* F, uint64_t frame) {
+    bam3d_ctx* c = F->lanes[frame & 1];
+    if (!c) return ctx;
+    c->opt_binning = ctx->opt_binning; c->opt_epa_tiers = ctx->opt_epa_tiers; c->opt_intersect_split = ctx->opt_intersect_split;
+    c->opt_intersect_refill = ctx->opt_intersect_refill; c->opt_toi_refill = ctx->opt_toi_refill;
+    c->opt_epa_global_polytopes = ctx->opt_epa_global_polytopes; c->opt_epa_overlap = ctx->opt_epa_overlap;
+    c->opt_distance_refill = ctx->opt_distance_refill;
+    c->opt_timing = false;
+    return c;
+}
+
+static int32_t frames_finish_slot(bam3d_ctx* ctx, bam3d_frames* F, bam3d_frames::Slot& sl) {
     if (!sl.in_flight) return BAM3D_OK;
+    if (sl.comm) {
+        // second half of the exchange: the counts are on the host by now (the GPU is busy with the next frame); the payload
+        // goes over the comm stream, then to the host on the copy-out stream
+        bam3d_comm* comm = sl.comm;
+        sl.comm = nullptr;
+        int32_t rc = bam3d_gather_contacts_finish(sl.lane, comm, sl.ticket, sl.d_compact, sl.d_gathered,
+                                                  sl.out_capacity < sl.gathered_capacity ? sl.out_capacity : sl.gathered_capacity,
+                                                  sl.counts.data(), &sl.total);
+        if (rc) { if (sl.lane != ctx) ctx->err = sl.lane->err; cudaEventSynchronize(sl.downloaded); sl.in_flight = false; return rc; }
+        cudaStream_t cs = (cudaStream_t)bam3d_comm_stream(comm);
+        cudaEventRecord(sl.exchanged, cs);
+        cudaStreamWaitEvent(F->s_out, sl.exchanged, 0);
+        if (sl.total) cudaMemcpyAsync(sl.out_gathered, sl.d_gathered, sl.total * sizeof(bam3d_contact40), cudaMemcpyDeviceToHost, F->s_out);
+        cudaEventRecord(sl.downloaded, F->s_out);
+    }
     cudaError_t e = cudaEventSynchronize(sl.downloaded);
     sl.in_flight = false;
     if (e != cudaSuccess) return b3_fail(ctx, BAM3D_ERR_CUDA, "bam3d_frames_wait", e);
@@ -1219,6 +1268,10 @@ void bam3d_frames_free(bam3d_ctx* ctx, bam3d_frames* F) {
         if (sl.d_status) cudaFree(sl.d_status);
         if (sl.d_contacts) cudaFree(sl.d_contacts);
         if (sl.d_err) cudaFree(sl.d_err);
+        if (sl.d_compact) cudaFree(sl.d_compact);
+        if (sl.d_gathered) cudaFree(sl.d_gathered);
+        if (sl.d_count) cudaFree(sl.d_count);
+        if (sl.exchanged) cudaEventDestroy(sl.exchanged);
         if (sl.h_err) cudaFreeHost(sl.h_err);
         if (sl.uploaded) cudaEventDestroy(sl.uploaded);
         if (sl.computed) cudaEventDestroy(sl.computed);
@@ -1226,6 +1279,7 @@ void bam3d_frames_free(bam3d_ctx* ctx, bam3d_frames* F) {
     }
     if (F->s_in) { cudaStreamSynchronize(F->s_in); cudaStreamDestroy(F->s_in); }
     if (F->s_out) { cudaStreamSynchronize(F->s_out); cudaStreamDestroy(F->s_out); }
+    for (bam3d_ctx* c : F->lanes) if (c) bam3d_ctx_destroy(c);
     delete F;
 }
 
@@ -1247,6 +1301,13 @@ int32_t bam3d_frames_create(bam3d_ctx* ctx, const uint8_t* kind, const float* pa
         (e = cudaStreamCreateWithFlags(&F->s_out, cudaStreamNonBlocking)) != cudaSuccess) {
         bam3d_frames_free(ctx, F);
         return b3_fail(ctx, BAM3D_ERR_CUDA, "cudaStreamCreate(frames)", e);
+    }
+    if (depth >= 2 && !std::getenv("BAM3D_FRAMES_ONE_LANE")) {  // (development knob: the single-lane behaviour for A/B timing)
+        for (auto& lane : F->lanes)
+            if ((rc = bam3d_ctx_create(ctx->device, &lane))) {
+                bam3d_frames_free(ctx, F);
+                return b3_fail(ctx, rc, "bam3d_frames_create: compute lane", cudaSuccess);
+            }
     }
     const size_t np = max_pairs ? max_pairs : 1;
     for (auto& sl : F->slots) {
@@ -1272,12 +1333,18 @@ int32_t bam3d_frames_create(bam3d_ctx* ctx, const uint8_t* kind, const float* pa
     return BAM3D_OK;
 }
 
-int32_t bam3d_frames_submit(bam3d_ctx* ctx, bam3d_frames* F, int32_t query, const float* xform, const float* xform_end,
-                            const uint32_t* pairs, uint64_t n, const bam3d_gjk_settings* settings, int32_t strategy,
-                            bam3d_contact* out_contacts, uint8_t* out_status, uint64_t* out_frame) {
+}  // extern "C"
+
+struct FrameGather { bam3d_comm* comm; uint64_t base; bam3d_contact40* out; uint64_t capacity; };
+
+static int32_t frames_submit_impl(bam3d_ctx* ctx, bam3d_frames* F, int32_t query, const float* xform, const float* xform_end,
+                                  const uint32_t* pairs, uint64_t n, const bam3d_gjk_settings* settings, int32_t strategy,
+                                  bam3d_contact* out_contacts, uint8_t* out_status, uint64_t* out_frame, const FrameGather* G) {
     if (!ctx || !F || !xform || (n && (!pairs || !out_status))) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_frames_submit: null argument", cudaSuccess);
     if (query < BAM3D_FRAME_INTERSECT || query > BAM3D_FRAME_TIME_OF_IMPACT) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_frames_submit: unknown query", cudaSuccess);
-    if (query != BAM3D_FRAME_INTERSECT && n && !out_contacts) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_frames_submit: out_contacts is null", cudaSuccess);
+    if (!G && query != BAM3D_FRAME_INTERSECT && n && !out_contacts) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_frames_submit: out_contacts is null", cudaSuccess);
+    if (G && (query == BAM3D_FRAME_INTERSECT || !G->comm || (G->capacity && !G->out)))
+        return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_frames_submit_gather: needs a contact-producing query, a communicator and an output buffer", cudaSuccess);
     if (n > F->max_pairs) return b3_fail(ctx, BAM3D_ERR_CAPACITY, "bam3d_frames_submit: more pairs than max_pairs", cudaSuccess);
     bam3d_frames::Slot& sl = F->slots[F->next_frame % F->slots.size()];
     if (query == BAM3D_FRAME_TIME_OF_IMPACT && (!xform_end || !sl.shapes_end))
@@ -1285,7 +1352,17 @@ int32_t bam3d_frames_submit(bam3d_ctx* ctx, bam3d_frames* F, int32_t query, cons
     CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
     // back-pressure: the frame `depth` submissions ago must have left this slot (its status is what bam3d_frames_wait on
     // it returns; a caller that skipped the wait loses that frame's error code, not its data)
-    if (sl.in_flight) (void)frames_finish_slot(ctx, sl);
+    if (sl.in_flight) (void)frames_finish_slot(ctx, F, sl);
+    if (G && !sl.d_compact) {  // first gather through this slot: its exchange buffers
+        const size_t np = F->max_pairs ? F->max_pairs : 1;
+        const size_t cap = (size_t)np * (size_t)bam3d_comm_size(G->comm);
+        cudaError_t ea;
+        if ((ea = cudaMalloc(&sl.d_compact, np * sizeof(bam3d_contact40))) != cudaSuccess || (ea = cudaMalloc(&sl.d_gathered, cap * sizeof(bam3d_contact40))) != cudaSuccess ||
+            (ea = cudaMalloc(&sl.d_count, 8)) != cudaSuccess || (ea = cudaEventCreateWithFlags(&sl.exchanged, cudaEventDisableTiming)) != cudaSuccess)
+            return b3_fail(ctx, BAM3D_ERR_OOM, "bam3d_frames_submit_gather: exchange buffers", ea);
+        sl.gathered_capacity = cap;
+        sl.counts.assign((size_t)bam3d_comm_size(G->comm), 0);
+    }
     const uint32_t ns = sl.shapes->n;
     const uint32_t n_meshes = sl.shapes->meshes ? sl.shapes->meshes->n_meshes : 0;
     sl.frame = F->next_frame++;
@@ -1305,27 +1382,51 @@ int32_t bam3d_frames_submit(bam3d_ctx* ctx, bam3d_frames* F, int32_t query, cons
     }
     if (n) CU_TRY(cudaMemcpyAsync(sl.d_pairs, pairs, n * 8, cudaMemcpyHostToDevice, F->s_in), "cudaMemcpyAsync(pairs)");
     CU_TRY(cudaEventRecord(sl.uploaded, F->s_in), "cudaEventRecord");
-    // kernels on the ctx stream
-    CU_TRY(cudaStreamWaitEvent(ctx->stream, sl.uploaded, 0), "cudaStreamWaitEvent");
+    // kernels on the frame's compute lane
+    bam3d_ctx* cc = frames_lane(ctx, F, sl.frame);
+    CU_TRY(cudaStreamWaitEvent(cc->stream, sl.uploaded, 0), "cudaStreamWaitEvent");
     int32_t rc = BAM3D_OK;
+    const uint64_t launches0 = cc->launches;
     if (n) {
-        if (query == BAM3D_FRAME_INTERSECT) rc = bam3d_gjk_intersect_dev(ctx, sl.shapes, sl.d_pairs, n, settings, sl.d_status);
-        else if (query == BAM3D_FRAME_CONTACT) rc = bam3d_gjk_contact_dev(ctx, sl.shapes, sl.d_pairs, n, settings, strategy, sl.d_contacts, sl.d_status);
-        else rc = bam3d_gjk_time_of_impact_dev(ctx, sl.shapes, sl.shapes_end, sl.d_pairs, n, settings, sl.d_contacts, sl.d_status);
+        if (query == BAM3D_FRAME_INTERSECT) rc = bam3d_gjk_intersect_dev(cc, sl.shapes, sl.d_pairs, n, settings, sl.d_status);
+        else if (query == BAM3D_FRAME_CONTACT) rc = bam3d_gjk_contact_dev(cc, sl.shapes, sl.d_pairs, n, settings, strategy, sl.d_contacts, sl.d_status);
+        else rc = bam3d_gjk_time_of_impact_dev(cc, sl.shapes, sl.shapes_end, sl.d_pairs, n, settings, sl.d_contacts, sl.d_status);
     }
-    CU_TRY(cudaEventRecord(sl.computed, ctx->stream), "cudaEventRecord");
+    if (!rc && G) {  // hits only, tagged with the global pair index; then the first half of the exchange (record counts)
+        rc = bam3d_compact_contacts_dev(cc, sl.d_contacts, sl.d_status, n, G->base, sl.d_compact, n, sl.d_count);
+        if (!rc) rc = bam3d_gather_contacts_begin(cc, G->comm, sl.d_count, &sl.ticket);
+    }
+    if (cc != ctx) { ctx->launches += cc->launches - launches0; if (rc) ctx->err = cc->err; }
+    CU_TRY(cudaEventRecord(sl.computed, cc->stream), "cudaEventRecord");
     if (rc) {  // nothing of this frame is copied back; the slot is free again once the upload has drained
         cudaEventSynchronize(sl.computed);
         return rc;
     }
     // results on the copy-out stream
     CU_TRY(cudaStreamWaitEvent(F->s_out, sl.computed, 0), "cudaStreamWaitEvent");
-    if (n && query != BAM3D_FRAME_INTERSECT) CU_TRY(cudaMemcpyAsync(out_contacts, sl.d_contacts, n * 32, cudaMemcpyDeviceToHost, F->s_out), "cudaMemcpyAsync(contacts)");
+    if (G) { sl.comm = G->comm; sl.lane = cc; sl.out_gathered = G->out; sl.out_capacity = G->capacity; sl.total = 0; }
+    if (n && query != BAM3D_FRAME_INTERSECT && out_contacts) CU_TRY(cudaMemcpyAsync(out_contacts, sl.d_contacts, n * 32, cudaMemcpyDeviceToHost, F->s_out), "cudaMemcpyAsync(contacts)");
     if (n) CU_TRY(cudaMemcpyAsync(out_status, sl.d_status, n, cudaMemcpyDeviceToHost, F->s_out), "cudaMemcpyAsync(status)");
     CU_TRY(cudaMemcpyAsync(sl.h_err, sl.d_err, 4, cudaMemcpyDeviceToHost, F->s_out), "cudaMemcpyAsync(err)");
     CU_TRY(cudaEventRecord(sl.downloaded, F->s_out), "cudaEventRecord");
     sl.in_flight = true;
     return BAM3D_OK;
+}
+
+extern "C" {
+
+int32_t bam3d_frames_submit(bam3d_ctx* ctx, bam3d_frames* F, int32_t query, const float* xform, const float* xform_end,
+                            const uint32_t* pairs, uint64_t n, const bam3d_gjk_settings* settings, int32_t strategy,
+                            bam3d_contact* out_contacts, uint8_t* out_status, uint64_t* out_frame) {
+    return frames_submit_impl(ctx, F, query, xform, xform_end, pairs, n, settings, strategy, out_contacts, out_status, out_frame, nullptr);
+}
+
+int32_t bam3d_frames_submit_gather(bam3d_ctx* ctx, bam3d_frames* F, bam3d_comm* comm, int32_t query, const float* xform, const float* xform_end,
+                                   const uint32_t* pairs, uint64_t n, const bam3d_gjk_settings* settings, int32_t strategy,
+                                   uint64_t pair_index_base, bam3d_contact40* out_gathered, uint64_t capacity, uint8_t* out_status,
+                                   uint64_t* out_frame) {
+    FrameGather G{comm, pair_index_base, out_gathered, capacity};
+    return frames_submit_impl(ctx, F, query, xform, xform_end, pairs, n, settings, strategy, nullptr, out_status, out_frame, &G);
 }
 
 int32_t bam3d_frames_wait(bam3d_ctx* ctx, bam3d_frames* F, uint64_t frame) {
@@ -1334,7 +1435,17 @@ int32_t bam3d_frames_wait(bam3d_ctx* ctx, bam3d_frames* F, uint64_t frame) {
     bam3d_frames::Slot& sl = F->slots[frame % F->slots.size()];
     if (sl.frame != frame) return BAM3D_OK;  // an older frame: its slot was reused, so it completed long ago
     CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
-    return frames_finish_slot(ctx, sl);
+    return frames_finish_slot(ctx, F, sl);
+}
+
+int32_t bam3d_frames_gathered(bam3d_ctx* ctx, bam3d_frames* F, uint64_t frame, uint64_t* out_counts, uint64_t* out_total) {
+    if (!ctx || !F || !out_total) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_frames_gathered: null argument", cudaSuccess);
+    bam3d_frames::Slot& sl = F->slots[frame % F->slots.size()];
+    if (frame >= F->next_frame || sl.frame != frame || sl.in_flight || sl.counts.empty())
+        return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_frames_gathered: call it after bam3d_frames_wait for that frame, before its slot is reused", cudaSuccess);
+    if (out_counts) for (size_t r = 0; r < sl.counts.size(); ++r) out_counts[r] = sl.counts[r];
+    *out_total = sl.total;
+    return BAM3D_OK;
 }
 
 }  // extern "C"

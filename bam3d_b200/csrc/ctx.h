@@ -27,6 +27,7 @@ struct bam3d_ctx {
     bool opt_intersect_split = false;  // intersect, thread path: first-support test and the GJK loop as two launches (measured slower on C1: 0.176 vs 0.167 ms)
     int opt_intersect_refill = 0;  // intersect, thread path: k >= 1 = persistent kernel whose lanes refill once k of a warp are idle (gjk_intersect_refill_kernel)
     int opt_toi_refill = 8;  // time of impact, thread path: 0 = one pair per thread (1.16 ms per 2^20 mixed pairs); k >= 1 = persistent kernel whose lanes refill once k of a warp are idle (gjk_toi_refill_kernel: 0.56 ms at k = 8)
+    int opt_distance_refill = 8;  // distance, thread path: the same lane-refill scheme (gjk_distance_refill_kernel); 0 = one pair per thread
     bool opt_epa_global_polytopes = true;   // thread-per-pair EPA: polytopes in a global slab (contiguous per thread) instead of local memory
     bool opt_epa_overlap = true;  // contact path: run the EPA overflow tier on the side stream next to the EPA kernel
     int opt_sap_strategy = 0;  // 0 auto, 1 tiled sweep, 2 BVH overlap query

@@ -435,7 +435,9 @@ constexpr int EPAQ_BINS = 49;               // thread-path bins (kindL * 7 + kin
 // shape-kind combination (same support code, similar polytope sizes: their local-memory loads stay
 // sector-coalesced) except where one segment runs out. Without binning everything is bin 0 at base 0.
 // bin[i] = the i-th bin to consume; tier[i] = the shared-memory EPA tier its pairs start in (epa_tiers.cuh).
-struct BinOrder { uint8_t bin[64]; uint8_t tier[64]; };
+// refill[i] = idle lanes a warp waits for before it fetches from segment i (1 = every finished lane refills at once;
+// near 32 = "cohort" mode: the warp's lanes start their pairs together and stay at the same EPA iteration).
+struct BinOrder { uint8_t bin[64]; uint8_t tier[64]; uint8_t refill[64]; };
 // queue header words
 constexpr int QH_CURSOR = 1;        // epa_refill_kernel's cursor
 constexpr int QH_DONE = 4;          // pairs the EPA kernel has finished
@@ -518,6 +520,7 @@ __global__ void __launch_bounds__(TPB, B3_EPA_BLOCKS) epa_refill_kernel(ShapeSet
     // segment table in consumption order: s_pref[i] = records before segment i, s_base[i] = its first record
     __shared__ uint32_t s_pref[EPAQ_BINS + 1];
     __shared__ uint32_t s_base[EPAQ_BINS];
+    __shared__ uint8_t s_refill[EPAQ_BINS + 1];
     if (threadIdx.x == 0) {
         const uint32_t* q_count = reinterpret_cast<const uint32_t*>(queue) + QH_BIN_COUNT;
         uint32_t acc = 0;
@@ -525,9 +528,11 @@ __global__ void __launch_bounds__(TPB, B3_EPA_BLOCKS) epa_refill_kernel(ShapeSet
             const uint32_t b = bo.bin[i];
             s_pref[i] = acc;
             s_base[i] = bin_start ? bin_start[b] : 0u;
+            s_refill[i] = bo.refill[i];
             acc += q_count[b];
         }
         s_pref[EPAQ_BINS] = acc;
+        s_refill[EPAQ_BINS] = 1;
     }
     __syncthreads();
     float lvv[GLOBAL_POLY ? 1 : EPA_VCAP * 3];
@@ -571,10 +576,16 @@ __global__ void __launch_bounds__(TPB, B3_EPA_BLOCKS) epa_refill_kernel(ShapeSet
     uint32_t it = 0, p = 0;
     V3 vmax = v3(0.f, 0.f, 0.f);
     int best = 0;
+    // Idle lanes a warp waits for before it fetches (warp-uniform; follows the segment of the warp's last fetch). The
+    // segments of ball-like pairs (Sphere / Capsule on both sides) run as cohorts: their EPA iteration counts are nearly
+    // constant (5th..95th percentile 64..68 for Sphere-Sphere at the default tolerance), so lanes that start together
+    // keep the same face count and pass A's loop runs full — refilled one by one they sit at random phases of a
+    // 4 -> 136-face growth and the warp pays the largest polytope for every lane.
+    int refill_min = 1;
     for (;;) {
-        // refill idle lanes from the queue (one atomic per warp per trip)
+        // refill idle lanes from the queue (one atomic per warp per fetch)
         const uint32_t need = __ballot_sync(0xFFFFFFFFu, !active && !exhausted);
-        if (need) {
+        if (need && (__popc(need) >= refill_min || !__any_sync(0xFFFFFFFFu, active))) {
             uint32_t base = 0;
             const uint32_t leader = __ffs(need) - 1;
             if (lane == leader) base = atomicAdd(q_cursor, (uint32_t)__popc(need));
@@ -598,12 +609,15 @@ __global__ void __launch_bounds__(TPB, B3_EPA_BLOCKS) epa_refill_kernel(ShapeSet
                     epa_init<false>(s, P, nv, nf, it, vmax, best);
                     active = true;
                 } else {
+                    seg = EPAQ_BINS;
                     exhausted = true;
 #ifdef B3_TIER_TRACE
                     { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); atomicMin(reinterpret_cast<unsigned long long*>(queue) + 9, t_); atomicMax(reinterpret_cast<unsigned long long*>(queue) + 10, t_); }
 #endif
                 }
             }
+            // the threshold of the segment the first fetching lane landed in
+            refill_min = s_refill[__shfl_sync(0xFFFFFFFFu, seg, leader)];
         }
         if (!__any_sync(0xFFFFFFFFu, active)) break;
         if (active) {
@@ -893,6 +907,94 @@ __global__ void __launch_bounds__(TPB) gjk_distance_kernel(ShapeSetDev S, const 
         }
         if (st != ST_OK) { rv = 0.f; geo = 0.f; }
         if (!WARP || (threadIdx.x & 31) == 0) { out_ref[p] = rv; out_geo[p] = geo; status[p] = st; }
+    }
+}
+
+// Thread-per-pair distance with lane refill ("distance_refill"), the scheme of gjk_toi_refill_kernel: on a mixed scene a
+// fifth of the pairs run to the iteration cap (curved shapes do not reach the 1e-6 absolute tolerance in f32) and hold 80 % of
+// all trips of gjk/mod.rs:246-279's loop while the median pair takes 4, so a warp of gjk_distance_kernel<false> lives as
+// long as its slowest pair. Here the grid is persistent, every LANE owns one pair, all lanes advance one trip per pass, and
+// lanes whose pair is decided fetch together from one cursor once `refill_min` of a warp are idle. Per pair the arithmetic
+// is gjk_distance<false>'s, operation for operation (same device functions, no contraction): bit-identical results.
+__global__ void __launch_bounds__(TPB) gjk_distance_refill_kernel(ShapeSetDev S, const uint2* __restrict__ pairs, uint32_t n,
+                                                                  const uint32_t* __restrict__ order, const uint32_t* __restrict__ ranges,
+                                                                  SettingsDev cfg, uint32_t* __restrict__ cursor, int refill_min,
+                                                                  float* __restrict__ out_ref, float* __restrict__ out_geo,
+                                                                  uint8_t* __restrict__ status) {
+    uint32_t begin = 0, end = n;
+    if (ranges) { begin = ranges[0]; end = ranges[1]; }
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t FULL = 0xFFFFFFFFu;
+    bool busy = false, drained = false;
+    uint32_t p = 0, it = 0;
+    Shape L, R;
+    Simplex<false> s;
+    s.clear();
+    for (;;) {
+        const uint32_t need = __ballot_sync(FULL, !busy && !drained);
+        if (need && (__popc(need) >= refill_min || !__any_sync(FULL, busy))) {
+            const int leader = __ffs(need) - 1;
+            uint32_t base = 0;
+            if ((int)lane == leader) base = atomicAdd(cursor, (uint32_t)__popc(need));
+            base = __shfl_sync(FULL, base, leader);
+            if (!busy && !drained) {
+                const uint32_t off = base + (uint32_t)__popc(need & ((1u << lane) - 1u));
+                if (off >= end - begin) {
+                    drained = true;
+                } else {
+                    p = order ? __ldg(order + begin + off) : begin + off;
+                    const uint2 pr = __ldg(pairs + p);
+                    load_pair_shape(L, S, pr.x);
+                    load_pair_shape(R, S, pr.y);
+                    V3 d = shape_origin(R) - shape_origin(L);
+                    if (fabsf(d.x - 0.f) < F32_EPSILON && fabsf(d.y - 0.f) < F32_EPSILON && fabsf(d.z - 0.f) < F32_EPSILON) d = v3(1.f, 1.f, 1.f);
+                    s.clear();
+                    V3 pv, pa;
+                    minkowski_support<false>(L, R, d, pv, pa);
+                    s.push(pv, pa);
+                    minkowski_support<false>(L, R, -d, pv, pa);
+                    s.push(pv, pa);
+                    it = 0;
+                    busy = true;
+                }
+            }
+        }
+        if (!__any_sync(FULL, busy)) break;
+        if (busy) {
+            uint8_t st = 0xFF;  // 0xFF: the pair goes on
+            float rv = 0.f, geo = 0.f;
+            if (it >= cfg.max_iterations) {
+                st = ST_MAX_ITER;
+            } else {
+                uint8_t cst = ST_OK;
+                const V3 c = closest_point_to_origin(s, cst);
+                if (cst != ST_OK) {
+                    st = cst;
+                } else if (fabsf(c.x - 0.f) < F32_EPSILON && fabsf(c.y - 0.f) < F32_EPSILON && fabsf(c.z - 0.f) < F32_EPSILON) {
+                    st = ST_MISS;
+                } else {
+                    const V3 nd = -c;
+                    V3 pv, pa;
+                    minkowski_support<false>(L, R, nd, pv, pa);
+                    const float dp = dot(pv, nd);
+                    const float d0 = dot(s.v[0], nd);
+                    if (dp - d0 < cfg.distance_tolerance) {
+                        rv = dp - d0;
+                        geo = sqrtf(dot(nd, nd));
+                        st = ST_OK;
+                    } else if (s.n >= 4) {
+                        st = ST_REF_PANIC;  // unreachable, see gjk_distance
+                    } else {
+                        s.push(pv, pa);
+                        ++it;
+                    }
+                }
+            }
+            if (st != 0xFF) {
+                out_ref[p] = rv; out_geo[p] = geo; status[p] = st;
+                busy = false;
+            }
+        }
     }
 }
 
@@ -1239,6 +1341,9 @@ static BinOrder epa_bin_order() {
             }
         }
         for (int i = 0; i < EPAQ_BINS; ++i) bo.tier[i] = (uint8_t)tier[bo.bin[i]];
+        int cohort = 28;  // idle lanes that trigger a fetch in the ball-like segments (1 = refill at once)
+        if (const char* e = getenv("BAM3D_EPA_COHORT")) { int v = atoi(e); if (v >= 1 && v <= 32) cohort = v; }  // development knob
+        for (int i = 0; i < EPAQ_BINS; ++i) bo.refill[i] = (uint8_t)(bo.tier[i] == 2 ? cohort : 1);
         ready = true;
     }
     return bo;
@@ -1336,7 +1441,18 @@ int launch_contact(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs, 
     return launched;
 }
 int launch_distance(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs, uint32_t n, const BinScratch* B, bool run_thread,
-                    bool run_warp, const SettingsDev& cfg, float* d_ref, float* d_geo, uint8_t* d_status) {
+                    bool run_warp, const SettingsDev& cfg, void* d_cursor, int refill_min, float* d_ref, float* d_geo, uint8_t* d_status) {
+    if (run_thread && d_cursor && n) {
+        const uint32_t* order = B ? B->order : nullptr;
+        const uint32_t* ranges = B ? B->ranges : nullptr;
+        int launched = 1;
+        cudaMemsetAsync(d_cursor, 0, 4, st);
+        static const int grid = persistent_grid((const void*)gjk_distance_refill_kernel);
+        gjk_distance_refill_kernel<<<grid, TPB, 0, st>>>(S, d_pairs, n, order, ranges, cfg, reinterpret_cast<uint32_t*>(d_cursor),
+                                                         refill_min < 1 ? 1 : (refill_min > 32 ? 32 : refill_min), d_ref, d_geo, d_status);
+        if (run_warp) { gjk_distance_kernel<true><<<warp_grid(n), TPB, 0, st>>>(S, d_pairs, n, order, ranges, cfg, d_ref, d_geo, d_status); ++launched; }
+        return launched;
+    }
     B3_LAUNCH(gjk_distance_kernel, 0, S, d_pairs, n, order, ranges, cfg, d_ref, d_geo, d_status)
 }
 // d_cursor: 4 bytes of device scratch for the lane-refill form of the thread path ("toi_refill"); null = one pair per thread.

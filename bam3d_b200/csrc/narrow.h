@@ -61,8 +61,10 @@ int launch_contact(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs, 
 // d_poly_slab (nullable): contact_poly_slab_bytes() of device memory; when given, the thread-per-pair EPA keeps its polytopes
 // there (one contiguous record per thread) instead of in per-thread local memory.
 size_t contact_poly_slab_bytes();
+// d_cursor / refill_min: as launch_toi ("distance_refill").
 int launch_distance(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs, uint32_t n, const BinScratch* B,
-                    bool run_thread, bool run_warp, const SettingsDev& cfg, float* d_ref, float* d_geo, uint8_t* d_status);
+                    bool run_thread, bool run_warp, const SettingsDev& cfg, void* d_cursor, int refill_min, float* d_ref, float* d_geo,
+                    uint8_t* d_status);
 // d_cursor (nullable): 4 bytes of device scratch; when given, the thread path runs as a persistent kernel whose lanes take a new
 // pair when theirs is finished ("toi_refill"; `refill_min` = how many lanes of a warp wait before they fetch together), instead of
 // one pair per thread.

@@ -31,6 +31,7 @@ extern "C" {
 #define BAM3D_ERR_NON_AFFINE (-3)  /* a transform's 4th row is not (0,0,0,1) */
 #define BAM3D_ERR_CAPACITY (-4)    /* output capacity too small; the required count is reported */
 #define BAM3D_ERR_OOM (-5)
+#define BAM3D_ERR_COMM (-6)        /* multi-GPU exchange: libnccl could not be loaded, or an NCCL call failed */
 
 /* primitive kinds, in the order of `enum Primitive3` (primitive/primitive3.rs:16-33); Cube == Cuboid */
 #define BAM3D_KIND_PARTICLE 0   /* primitive/particle.rs   params: -                                  */
@@ -47,7 +48,9 @@ extern "C" {
 #define BAM3D_STATUS_MAX_ITER 2   /* None: max_iterations reached (TOI: the added iteration cap)        */
 #define BAM3D_STATUS_REF_PANIC 3  /* the reference would panic here (simplex3d.rs:134 unwrap, :138 assert!) */
 #define BAM3D_STATUS_NAN 4        /* None through a NaN comparison                                      */
-#define BAM3D_STATUS_CAPACITY 5   /* EPA polytope outgrew the device capacities (never seen on valid input) */
+#define BAM3D_STATUS_CAPACITY 5   /* EPA polytope outgrew 1024 faces: a pinched polytope on near-degenerate input (about 3 in 10^5
+                                   * mixed pairs, every one involving a Cylinder cap); the reference has no face limit and keeps
+                                   * growing such a polytope — tests/test_host_cpu.py records what it would have returned */
 #define BAM3D_STATUS_UNSUPPORTED 6 /* ray cast against a ConvexPolyhedron uploaded without faces (or > 4096 faces)   */
 
 /* CollisionStrategy (contact.rs:12-18) */
@@ -102,7 +105,7 @@ void bam3d_default_settings(bam3d_gjk_settings* out); /* GJK::new() (gjk/mod.rs:
  * "epa_global_polytopes" (default 1) keeps the thread-per-pair EPA's polytopes in a global-memory slab, one contiguous
  * record per thread (582 MB of scratch), instead of per-thread local memory; "intersect_split"
  * (default 0) runs bam3d_gjk_intersect's thread path as two launches (first-support test, then GJK on the survivors);
- * "toi_refill" (default 8; 0..32) runs bam3d_gjk_time_of_impact's thread path as a persistent kernel in which every lane owns
+ * "distance_refill" (default 8; 0..32) and "toi_refill" (default 8; 0..32) run bam3d_gjk_distance's / bam3d_gjk_time_of_impact's thread path as a persistent kernel in which every lane owns
  * one pair and idle lanes fetch new pairs together once that many lanes of a warp are idle (0 = one pair per thread: same
  * results, half the speed on mixed scenes); "intersect_refill" (default 0; 0..32) is the same scheme for bam3d_gjk_intersect
  * (same results, measured slower: kept as an option). Every switch changes scheduling only, never a result bit. */
@@ -317,6 +320,57 @@ int32_t bam3d_frames_submit(bam3d_ctx* ctx, bam3d_frames* frames, int32_t query,
  * BAM3D_ERR_NON_AFFINE if one of its transforms had a 4th row other than (0,0,0,1) (its results are then meaningless). */
 int32_t bam3d_frames_wait(bam3d_ctx* ctx, bam3d_frames* frames, uint64_t frame);
 void bam3d_frames_free(bam3d_ctx* ctx, bam3d_frames* frames);
+
+/* ---- multi-GPU: NCCL gather of the ranks' compacted contacts ------------------------------------------ */
+/* One process per GPU; pair lists shard across ranks with no data-path collective (each rank runs the narrow phase on its
+ * slice), and the one exchange step is the gather of the ranks' compacted contact lists so that every rank ends with the
+ * contacts of all pairs. The reference has no distributed layer; this is the `gpu` feature's addition (north_star). NCCL is
+ * bound at run time (dlopen of libnccl.so.2): every call returns BAM3D_ERR_COMM when it is not installed. */
+typedef struct bam3d_comm bam3d_comm;
+#define BAM3D_UNIQUE_ID_BYTES 256   /* two ncclUniqueId: counts and payloads travel on separate communicators */
+/* rank 0: a fresh rendezvous id (ncclGetUniqueId); hand the bytes to the other ranks by any host-side means */
+int32_t bam3d_comm_unique_id(uint8_t* out_id);
+/* every rank, collectively: join the communicator on `device` */
+int32_t bam3d_comm_create(int32_t device, const uint8_t* id, int32_t rank, int32_t n_ranks, bam3d_comm** out);
+void bam3d_comm_destroy(bam3d_comm* comm);
+int32_t bam3d_comm_rank(const bam3d_comm* comm);
+int32_t bam3d_comm_size(const bam3d_comm* comm);
+void* bam3d_comm_stream(bam3d_comm* comm);          /* the cudaStream_t the exchange runs on */
+const char* bam3d_comm_unavailable_reason(void);    /* "" when libnccl was loaded */
+/* The exchange, in two halves so that it overlaps the next step's kernels. `begin` (asynchronous): after everything
+ * enqueued on the ctx stream so far, all-gather the ranks' record counts (*d_count as written by
+ * bam3d_compact_contacts_dev) and copy them to the host. `finish`: waits on the host for that ticket's counts, then
+ * enqueues — on the comm stream — one broadcast per rank with the exact sizes, so that d_gathered holds the ranks' records
+ * concatenated in rank order (out_counts[n_ranks] on the host, may be NULL; *out_total = their sum; BAM3D_ERR_CAPACITY
+ * if it exceeds `capacity` records). bam3d_comm_join makes the ctx stream wait for the exchange before it reads
+ * d_gathered. Every rank must call begin / finish in the same order; at most 4 tickets may be open. Counts and payloads use
+ * separate communicators and streams, so a payload never queues behind the count exchange of a later step. */
+int32_t bam3d_gather_contacts_begin(bam3d_ctx* ctx, bam3d_comm* comm, const uint64_t* d_count, uint64_t* out_ticket);
+int32_t bam3d_gather_contacts_finish(bam3d_ctx* ctx, bam3d_comm* comm, uint64_t ticket, const bam3d_contact40* d_compact,
+                                     bam3d_contact40* d_gathered, uint64_t capacity, uint64_t* out_counts, uint64_t* out_total);
+int32_t bam3d_comm_join(bam3d_ctx* ctx, bam3d_comm* comm);
+/* finer than join: the ctx stream waits only for that ticket's payload (before it overwrites d_compact / reads d_gathered) */
+int32_t bam3d_gather_contacts_wait(bam3d_ctx* ctx, bam3d_comm* comm, uint64_t ticket);
+/* begin + finish + join in one call (no overlap) */
+int32_t bam3d_gather_contacts_dev(bam3d_ctx* ctx, bam3d_comm* comm, const bam3d_contact40* d_compact, const uint64_t* d_count,
+                                  bam3d_contact40* d_gathered, uint64_t capacity, uint64_t* out_counts, uint64_t* out_total);
+/* host buffers: this rank's dense results (as bam3d_gjk_contact / _time_of_impact returned them for its n pairs, whose global
+ * indices start at pair_index_base) in, the hits of ALL ranks out (rank order), synchronous on return */
+int32_t bam3d_gather_contacts(bam3d_ctx* ctx, bam3d_comm* comm, const bam3d_contact* contacts, const uint8_t* status, uint64_t n,
+                              uint64_t pair_index_base, bam3d_contact40* out, uint64_t capacity, uint64_t* out_counts,
+                              uint64_t* out_total);
+
+/* Frame queue with the exchange inside: like bam3d_frames_submit for a contact-producing query, but the frame's hits are
+ * compacted on the device (pair_index = index in `pairs` + pair_index_base), exchanged over `comm`, and bam3d_frames_wait
+ * leaves the hits of ALL ranks (rank order) in out_gathered (host, `capacity` records) instead of this rank's dense contacts;
+ * out_status still receives this rank's per-pair status. The record counts travel while the next frame computes; the
+ * payload is exchanged inside bam3d_frames_wait. Every rank must submit and wait in the same order.
+ * bam3d_frames_gathered (after the wait): per-rank record counts (n_ranks, may be NULL) and their sum. */
+int32_t bam3d_frames_submit_gather(bam3d_ctx* ctx, bam3d_frames* frames, bam3d_comm* comm, int32_t query, const float* xform,
+                                   const float* xform_end, const uint32_t* pairs, uint64_t n, const bam3d_gjk_settings* settings,
+                                   int32_t strategy, uint64_t pair_index_base, bam3d_contact40* out_gathered, uint64_t capacity,
+                                   uint8_t* out_status, uint64_t* out_frame);
+int32_t bam3d_frames_gathered(bam3d_ctx* ctx, bam3d_frames* frames, uint64_t frame, uint64_t* out_counts, uint64_t* out_total);
 
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
 uint64_t bam3d_ctx_launch_count(const bam3d_ctx* ctx);

@@ -262,6 +262,28 @@ def test_lane_refill_switches_change_scheduling_only(ctx, oracle, option, values
         ctx.set_option(option, 33)
 
 
+def test_distance_refill_switch_changes_scheduling_only(ctx, oracle):
+    """GJK::distance: the persistent lane-refill kernel (default, 8 idle lanes) and the one-pair-per-thread kernel return the
+    oracle's bits on a scene where a fifth of the pairs run to the iteration cap (the C2 scene) and on one with polyhedra."""
+    gjk = b3.GJK.new(ctx)
+    mixed, _ = _refill_scene()
+    for scene in (scenes.mixed_pairs(40_000, s=1.5), mixed):
+        shapes = shapes_of(ctx, scene)
+        oref, ogeo, _, ost = oracle.distance(scene, nthreads=8)
+        assert (ost == b3.STATUS_MAX_ITER).sum() > 100 and (ost == 0).sum() > 1000
+        try:
+            for v in (0, 1, 8, 32):
+                ctx.set_option("distance_refill", v)
+                ref, dist, st = gjk.distance_batch(shapes, scene["pairs"])
+                assert np.array_equal(st, ost), ("distance_refill", v, int((st != ost).sum()))
+                assert_f32_equal(f"ref_value distance_refill={v}", ref, oref, st == 0)
+                assert_f32_equal(f"distance distance_refill={v}", dist, ogeo, st == 0)
+        finally:
+            ctx.set_option("distance_refill", 8)
+    with pytest.raises(b3.Bam3dError):
+        ctx.set_option("distance_refill", 33)
+
+
 def test_polyhedron_parity(ctx, oracle):
     """C3 at reduced size: warp-cooperative support (64..256 vertices) vs the sequential scan of the oracle."""
     lib = scenes.mesh_library(256)
@@ -505,3 +527,47 @@ def test_frame_queue_time_of_impact_errors_and_empty(ctx, oracle):
         b3.FrameQueue(gjk, scene["kind"], scene["params"], x0, max_pairs=n, depth=0)
     q.close()
     q2.close()
+
+
+def test_native_gather_single_rank_and_frame_queue_gather(ctx, oracle):
+    """The library's own NCCL exchange (bam3d_comm_*, bam3d_gather_contacts*, bam3d_frames_submit_gather) with one rank: the
+    gathered list must be exactly this rank's hits in pair order, tagged with the global pair index, through all three forms
+    (device pointers, host buffers, frame queue). The world-size-2 form runs under torchrun in tests/tools/gather_2gpu.py."""
+    import ctypes as C
+    from bam3d_b200 import multi
+    lib = ctx._lib
+    comm = multi.Comm(0, 0, 1, exchange=lambda uid: uid)
+    scene = scenes.mixed_pairs(30_011, s=1.5, seed=0xB3D00A11)
+    shapes = shapes_of(ctx, scene)
+    gjk = b3.GJK.new(ctx)
+    FR = b3.CollisionStrategy.FullResolution
+    contacts, st = gjk.intersection_batch(FR, shapes, scene["pairs"])
+    oc, _, ost = oracle.contact(scene, strategy=0, nthreads=8)
+    assert np.array_equal(st, ost)
+    hits = np.nonzero(st == 0)[0]
+    base = 1_000_000
+    rec, counts = comm.gather(ctx, contacts, st, base, len(st))
+    assert counts.tolist() == [len(hits)] and len(rec) == len(hits)
+    order = np.argsort(rec[:, 0], kind="stable")
+    rec = rec[order]
+    assert np.array_equal(rec[:, 0], (hits + base).astype(np.uint32)) and (rec[:, 1] == 0).all()
+    assert rec[:, 2:10].tobytes() == contacts[hits].tobytes()
+    with pytest.raises(b3.Bam3dError):
+        comm.gather(ctx, contacts, st, base, len(hits) - 1)   # capacity too small -> BAM3D_ERR_CAPACITY
+    # frame queue, gather mode: two frames in flight
+    n_sh, n_pr = len(scene["kind"]), len(scene["pairs"])
+    fq = b3.FrameQueue(gjk, scene["kind"], scene["params"], scene["xform"], max_pairs=n_pr, depth=2)
+    hx = np.ascontiguousarray(scene["xform"], dtype=np.float32).reshape(n_sh, 16)
+    hpairs = np.ascontiguousarray(scene["pairs"], dtype=np.uint32)
+    frames = []
+    for _ in range(3):
+        g, hs = b3.pinned_empty(ctx, (n_pr, 10), np.uint32), b3.pinned_empty(ctx, (n_pr,), np.uint8)
+        frames.append((fq.submit_contact_gather(comm, FR, hx, hpairs, base, g, hs), g, hs))
+    for f, g, hs in frames:
+        fq.wait(f)
+        cnt, total = fq.gathered(f)
+        assert total == len(hits) and cnt.tolist() == [len(hits)] and np.array_equal(hs, st)
+        got = g[:total][np.argsort(g[:total, 0], kind="stable")]
+        assert got.tobytes() == rec.tobytes()
+    fq.close()
+    comm.close()
