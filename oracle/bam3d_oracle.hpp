@@ -110,6 +110,7 @@ struct Counters {
     uint64_t gjk_iterations = 0;  // simplex reductions
     uint64_t epa_iterations = 0;
     uint32_t max_faces = 0, max_verts = 0, max_edges = 0;
+    uint64_t removed_faces = 0;   // faces Polytope::add removed (the serial part of an EPA iteration)
 };
 
 // primitive/util.rs:7-23 get_max_point — inverse() recomputed on every call, fold from (zero, -inf), strict >.
@@ -408,7 +409,9 @@ struct Polytope {  // epa3d.rs:97-150
     std::vector<SupportPoint>& vertices;
     std::vector<Face> faces;
     uint32_t max_edges = 0;
+    uint64_t removed = 0;
     bool overflow = false;
+    size_t face_limit = EPA_FACE_LIMIT;  // the device's capacity by default; tests lift it to see what the reference itself returns
     explicit Polytope(std::vector<SupportPoint>& simplex) : vertices(simplex) {
         // Face::new, epa3d.rs:172-179
         faces.push_back(Face::new_impl(simplex, 3, 2, 1));
@@ -433,16 +436,17 @@ struct Polytope {  // epa3d.rs:97-150
                 Face face = faces[i];
                 faces[i] = faces.back();  // swap_remove
                 faces.pop_back();
+                ++removed;
                 for (int e = 0; e < 3; ++e) {
                     remove_or_add_edge(edges, {face.vertices[e], face.vertices[(e + 1) % 3]});
-                    if (edges.size() > EPA_EDGE_LIMIT) { overflow = true; return; }
+                    if (edges.size() > 3 * face_limit) { overflow = true; return; }
                 }
                 if (edges.size() > max_edges) max_edges = (uint32_t)edges.size();
             } else {
                 ++i;
             }
         }
-        if (faces.size() + edges.size() > EPA_FACE_LIMIT) { overflow = true; return; }
+        if (faces.size() + edges.size() > face_limit) { overflow = true; return; }
         uint32_t n = (uint32_t)vertices.size();
         vertices.push_back(sup);
         for (auto& e : edges) faces.push_back(Face::new_impl(vertices, n, e.first, e.second));
@@ -467,11 +471,13 @@ inline Contact epa_contact(const Polytope& polytope, const Face& face) {
 struct EPA3 {  // epa3d.rs:9-67; constants epa/mod.rs:12-13
     float tolerance = 0.00001f;
     uint32_t max_iterations = 100;
+    size_t face_limit = EPA_FACE_LIMIT;  // not in the reference (its Vec is unbounded): see the comment at EPA_FACE_LIMIT
     // epa3d.rs:16-52
     bool process(std::vector<SupportPoint>& simplex, const Shape& left, const Mat4& lt, const Shape& right,
                  const Mat4& rt, Contact& out, Counters* cnt = nullptr, Status* st = nullptr) const {
         if (simplex.size() < 4) return false;
         Polytope polytope(simplex);
+        polytope.face_limit = face_limit;
         uint32_t i = 1;
         for (;;) {
             const Face& face = polytope.closest_face_to_origin();
@@ -484,13 +490,14 @@ struct EPA3 {  // epa3d.rs:9-67; constants epa/mod.rs:12-13
                     if (polytope.faces.size() > cnt->max_faces) cnt->max_faces = (uint32_t)polytope.faces.size();
                     if (polytope.vertices.size() > cnt->max_verts) cnt->max_verts = (uint32_t)polytope.vertices.size();
                     if (polytope.max_edges > cnt->max_edges) cnt->max_edges = polytope.max_edges;
+                    cnt->removed_faces += polytope.removed;
                 }
                 return true;
             }
             polytope.add(p);
             if (polytope.overflow) {
                 if (st) *st = Status::Capacity;
-                if (cnt) cnt->max_faces = (uint32_t)EPA_FACE_LIMIT + 1;
+                if (cnt) cnt->max_faces = (uint32_t)face_limit + 1;
                 return false;
             }
             if (cnt && polytope.faces.size() > cnt->max_faces) cnt->max_faces = (uint32_t)polytope.faces.size();

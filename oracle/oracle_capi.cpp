@@ -139,6 +139,29 @@ void orc_gjk_contact_stats_batch(const uint8_t* kind, const float* params, const
     });
 }
 
+// The same with the oracle's EPA face limit replaced by `face_limit` (the reference's Vec is unbounded): what the reference
+// itself returns for the pairs the device reports as BAM3D_STATUS_CAPACITY. Single-threaded per pair; a pair whose polytope
+// passes face_limit still ends as Status::Capacity (the reference would keep growing it until the iteration cap or OOM).
+void orc_gjk_contact_face_limit(const uint8_t* kind, const float* params, const float* xform, const uint32_t* mesh_id,
+                                const float* mesh_verts, const uint32_t* mesh_offsets, const uint32_t* pairs, uint64_t n,
+                                uint64_t face_limit, float* out_contact, uint8_t* out_status, uint32_t* out_max_faces,
+                                uint32_t* out_epa_iterations, uint64_t* out_removed_faces, int nthreads) {
+    ShapeTable T{kind, params, xform, mesh_id, mesh_verts, mesh_offsets};
+    GJK gjk;
+    gjk.epa.face_limit = (size_t)face_limit;
+    parallel_for(n, nthreads, [&](uint64_t b, uint64_t e, int) {
+        for (uint64_t i = b; i < e; ++i) {
+            uint32_t l = pairs[2 * i], r = pairs[2 * i + 1];
+            Contact c; Status st; Counters cnt;
+            bool hit = gjk.intersection(CollisionStrategy::FullResolution, T.shape(l), T.mat(l), T.shape(r), T.mat(r), c, &st, &cnt);
+            out_status[i] = (uint8_t)st;
+            out_max_faces[i] = cnt.max_faces; out_epa_iterations[i] = (uint32_t)cnt.epa_iterations;
+            if (out_removed_faces) out_removed_faces[i] = cnt.removed_faces;
+            if (hit) put_contact(out_contact + 8 * i, c); else std::memset(out_contact + 8 * i, 0, 32);
+        }
+    });
+}
+
 // GJK::distance over a batch (gjk/mod.rs:232-280). out_some[i]=1 for Some; out_ref = dp-d0 (what the reference
 // returns), out_geo = sqrt(d.d).
 void orc_gjk_distance_batch(const uint8_t* kind, const float* params, const float* xform, const uint32_t* mesh_id,
@@ -445,6 +468,23 @@ int32_t orc_frustum_from_mat4(const float* m16, float* out24) {
 }
 void orc_perspective_rh_gl(float fov, float aspect, float zn, float zf, float* out16) { Mat4::perspective_rh_gl(fov, aspect, zn, zf).to_cols_array(out16); }
 // FrustumVisitor query (visitor.rs:99-134). planes24 in the order left,right,bottom,top,near,far.
+// Does any BRANCH bound on the path root -> leaf of `value` contain `origin` (min <= o <= max on every axis)? Then that
+// branch's visitor distance is the ray's EXIT distance (aabb3.rs:165-195 returns the far slab point when the origin is
+// inside), and RayClosestVisitor's `t < self.min` test (dbvt/util.rs:46-62) may prune it although it holds a closer leaf.
+int32_t orc_dbvt_origin_inside_ancestor(orc_dbvt* t, uint32_t value, const float* origin3) {
+    const Dbvt& T = t->tree;
+    uint32_t leaf = 0;
+    for (uint32_t i = 1; i < T.nodes.size(); ++i)
+        if (T.nodes[i].kind == Dbvt::Leaf && T.nodes[i].value == value) { leaf = i; break; }
+    if (!leaf) return -1;
+    for (uint32_t i = T.nodes[leaf].parent; i != 0; i = T.nodes[i].parent) {
+        const Aabb3& b = T.nodes[i].bound;
+        if (origin3[0] >= b.min.x && origin3[0] <= b.max.x && origin3[1] >= b.min.y && origin3[1] <= b.max.y &&
+            origin3[2] >= b.min.z && origin3[2] <= b.max.z) return 1;
+    }
+    return 0;
+}
+
 uint64_t orc_dbvt_query_frustum(orc_dbvt* t, const float* planes24, uint32_t* out_values, uint8_t* out_relation, uint64_t cap) {
     FrustumVisitor vis;
     Plane* ps[6] = {&vis.frustum.left, &vis.frustum.right, &vis.frustum.bottom, &vis.frustum.top, &vis.frustum.near_, &vis.frustum.far_};

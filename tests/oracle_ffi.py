@@ -284,6 +284,13 @@ class OracleDbvt:
         c = self.orc.lib.orc_dbvt_find_collider_pairs(self.h, _p(dirty), _p(out), C.c_uint64(cap))
         return out[:c].copy()
 
+    def origin_inside_ancestor(self, value, origin):
+        """True when a branch bound above `value`'s leaf contains `origin` (the reference's closest-ray prune can then miss it)."""
+        o = np.ascontiguousarray(origin, dtype=np.float32)
+        r = self.orc.lib.orc_dbvt_origin_inside_ancestor(self.h, C.c_uint32(int(value)), _p(o))
+        assert r >= 0
+        return bool(r)
+
     def stack_overflow(self):
         return bool(self.orc.lib.orc_dbvt_stack_overflow(self.h))
 

@@ -559,15 +559,20 @@ def test_native_gather_single_rank_and_frame_queue_gather(ctx, oracle):
     fq = b3.FrameQueue(gjk, scene["kind"], scene["params"], scene["xform"], max_pairs=n_pr, depth=2)
     hx = np.ascontiguousarray(scene["xform"], dtype=np.float32).reshape(n_sh, 16)
     hpairs = np.ascontiguousarray(scene["pairs"], dtype=np.uint32)
-    frames = []
-    for _ in range(3):
-        g, hs = b3.pinned_empty(ctx, (n_pr, 10), np.uint32), b3.pinned_empty(ctx, (n_pr,), np.uint8)
-        frames.append((fq.submit_contact_gather(comm, FR, hx, hpairs, base, g, hs), g, hs))
-    for f, g, hs in frames:
+    def check(f, g, hs):
         fq.wait(f)
         cnt, total = fq.gathered(f)
         assert total == len(hits) and cnt.tolist() == [len(hits)] and np.array_equal(hs, st)
         got = g[:total][np.argsort(g[:total, 0], kind="stable")]
         assert got.tobytes() == rec.tobytes()
+
+    frames = []
+    for k in range(4):
+        if k >= 2:
+            check(*frames[k - 2])   # depth 2: a frame's slot is reused two submissions later
+        g, hs = b3.pinned_empty(ctx, (n_pr, 10), np.uint32), b3.pinned_empty(ctx, (n_pr,), np.uint8)
+        frames.append((fq.submit_contact_gather(comm, FR, hx, hpairs, base, g, hs), g, hs))
+    check(*frames[2])
+    check(*frames[3])
     fq.close()
     comm.close()

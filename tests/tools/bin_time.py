@@ -10,7 +10,8 @@ import torch
 import bam3d_b200 as b3
 import bench
 
-n = 1 << 20
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
+only = sys.argv[2].split(",") if len(sys.argv) > 2 else None   # e.g. "sph-sph,all"
 scene = bench.make_scene("c2", n, 0)
 ctx = b3.Context(0)
 gjk = b3.GJK.new(ctx)
@@ -22,6 +23,8 @@ names = {2: "sph", 3: "cub", 4: "cyl"}
 p = lambda t: C.c_void_p(t.data_ptr())
 total = 0.0
 for sel_name, sel in [("all", np.ones(n, bool))] + [(f"{names[a]}-{names[b]}", (k[:, 0] == a) & (k[:, 1] == b)) for a in (2, 3, 4) for b in (2, 3, 4)]:
+    if only and sel_name not in only:
+        continue
     pairs = np.ascontiguousarray(scene["pairs"][sel])
     m = len(pairs)
     d_pairs = torch.from_numpy(pairs.astype(np.int32).reshape(-1)).to(dev)
@@ -40,5 +43,6 @@ for sel_name, sel in [("all", np.ones(n, bool))] + [(f"{names[a]}-{names[b]}", (
     t = min(times[1:])
     if sel_name != "all":
         total += t
-    print(f"{sel_name:8s} pairs {m:8d} hits {(st == 0).sum():7d} cap {(st == 5).sum():3d}  {t:8.3f} ms", flush=True)
+    tag = " ".join(f"{k_}={v_}" for k_, v_ in os.environ.items() if k_.startswith("BAM3D_"))
+    print(f"{tag} {sel_name:8s} pairs {m:8d} hits {(st == 0).sum():7d} cap {(st == 5).sum():3d}  {t:8.3f} ms", flush=True)
 print(f"sum of bins {total:.3f} ms")
