@@ -62,6 +62,11 @@ SIGNATURES = {
     "bam3d_gjk_contact_dev": (_i32, [_vp, _vp, _vp, _u64, _PS, _i32, _vp, _vp]),
     "bam3d_gjk_distance_dev": (_i32, [_vp, _vp, _vp, _u64, _PS, _vp, _vp, _vp]),
     "bam3d_gjk_time_of_impact_dev": (_i32, [_vp, _vp, _vp, _vp, _u64, _PS, _vp, _vp]),
+    "bam3d_compounds_upload": (_i32, [_vp, _vp, _vp, _vp, _vp, _u32, _vp, _u32, _vp, C.POINTER(_vp)]),
+    "bam3d_compounds_free": (None, [_vp, _vp]),
+    "bam3d_gjk_contact_complex": (_i32, [_vp, _vp, _vp, _vp, _u64, _PS, _i32, _vp, _vp]),
+    "bam3d_gjk_distance_complex": (_i32, [_vp, _vp, _vp, _vp, _u64, _PS, _vp, _vp]),
+    "bam3d_gjk_time_of_impact_complex": (_i32, [_vp, _vp, _vp, _vp, _vp, _u64, _PS, _i32, _vp, _vp]),
     "bam3d_ray_cast": (_i32, [_vp, _vp, _vp, _u64, _vp, _u64, _i32, _vp, _vp]),
     "bam3d_ray_cast_dev": (_i32, [_vp, _vp, _vp, _u64, _vp, _u64, _i32, _vp, _vp]),
     "bam3d_compact_contacts_dev": (_i32, [_vp, _vp, _vp, _u64, _u64, _vp, _u64, _vp]),
@@ -77,6 +82,8 @@ SIGNATURES = {
     "bam3d_shapes_world_spheres_dev": (_i32, [_vp, _vp, _vp]),
     "bam3d_sap_find_pairs_spheres": (_i32, [_vp, _vp, _u64, C.POINTER(_i32), _vp, _vp, _u64, C.POINTER(_u64)]),
     "bam3d_sap_find_pairs_spheres_dev": (_i32, [_vp, _vp, _u64, C.POINTER(_i32), _vp, _vp, _u64, C.POINTER(_u64)]),
+    "bam3d_pipeline_contacts": (_i32, [_vp, _vp, C.POINTER(_i32), _PS, _i32, _vp, _vp, _vp, _vp, _vp, _u64, C.POINTER(_u64)]),
+    "bam3d_pipeline_contacts_dev": (_i32, [_vp, _vp, C.POINTER(_i32), _PS, _i32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _u64, C.POINTER(_u64)]),
     "bam3d_bvh_build": (_i32, [_vp, _vp, _u64, C.POINTER(_vp)]),
     "bam3d_bvh_build_dev": (_i32, [_vp, _vp, _u64, C.POINTER(_vp)]),
     "bam3d_bvh_refit": (_i32, [_vp, _vp, _vp]),
@@ -88,6 +95,10 @@ SIGNATURES = {
     "bam3d_bvh_query_frustum": (_i32, [_vp, _vp, _vp, _u64, _vp, _vp, _vp, _u64, C.POINTER(_u64)]),
     "bam3d_bvh_query_ray_closest": (_i32, [_vp, _vp, _vp, _u64, _vp, _vp]),
     "bam3d_bvh_find_collider_pairs": (_i32, [_vp, _vp, _vp, _vp, _u64, C.POINTER(_u64)]),
+    "bam3d_bvh_query_aabb_dev": (_i32, [_vp, _vp, _vp, _u64, _vp, _vp, _u64, _vp]),
+    "bam3d_bvh_query_ray_dev": (_i32, [_vp, _vp, _vp, _u64, _vp, _vp, _vp, _u64, _vp]),
+    "bam3d_bvh_query_frustum_dev": (_i32, [_vp, _vp, _vp, _u64, _vp, _vp, _vp, _u64, _vp]),
+    "bam3d_bvh_query_ray_closest_dev": (_i32, [_vp, _vp, _vp, _u64, _vp, _vp]),
     "bam3d_frustum_from_mat4": (_i32, [_vp, _vp]),
     "bam3d_frames_create": (_i32, [_vp, _vp, _vp, _vp, _vp, _u32, _vp, _u64, _u32, _i32, C.POINTER(_vp)]),
     "bam3d_frames_submit": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _u64, _PS, _i32, _vp, _vp, C.POINTER(_u64)]),

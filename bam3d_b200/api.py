@@ -517,108 +517,65 @@ def mat4_mul(a, b):
 
 class CompoundSet:
     """Compound shapes: compound c owns primitives comp_offsets[c] .. comp_offsets[c+1] of (kind, params, local_xform);
-    the reference's `&[(Primitive, Mat4)]` slices (gjk/mod.rs:362-371)."""
+    the reference's `&[(Primitive, Mat4)]` slices (gjk/mod.rs:362-371), resident on the device (bam3d_compounds)."""
 
     def __init__(self, ctx, kind, params, local_xform, comp_offsets, mesh_id=None, meshes=None):
         self.ctx = ctx
         self.kind = np.ascontiguousarray(kind, dtype=np.uint8)
         self.params = np.ascontiguousarray(params, dtype=np.float32).reshape(-1, 4)
         self.local = np.ascontiguousarray(local_xform, dtype=np.float32).reshape(-1, 16)
-        self.offsets = np.ascontiguousarray(comp_offsets, dtype=np.int64)
-        self.mesh_id, self.meshes = mesh_id, meshes
+        self.offsets = np.ascontiguousarray(comp_offsets, dtype=np.uint32)
+        self.mesh_id = None if mesh_id is None else np.ascontiguousarray(mesh_id, dtype=np.uint32)
+        self.meshes = meshes
         if self.offsets[-1] != len(self.kind):
             raise ValueError("comp_offsets[-1] must equal the number of primitives")
-        self.owner = np.repeat(np.arange(len(self.offsets) - 1), np.diff(self.offsets))
+        self.n_compounds = len(self.offsets) - 1
+        h = C.c_void_p()
+        ctx.check(ctx._lib.bam3d_compounds_upload(ctx.handle, _ptr(self.kind), _ptr(self.params), _ptr(self.local), _ptr(self.mesh_id), len(self.kind),
+                                                  _ptr(self.offsets), self.n_compounds, meshes.handle if meshes is not None else None, C.byref(h)))
+        self.handle = h
 
-    def shapes(self, comp_xform):
-        """ShapeSet of all primitives with world transform = compound transform * local transform (gjk/mod.rs:377-379)."""
-        comp_xform = np.ascontiguousarray(comp_xform, dtype=np.float32).reshape(-1, 16)
-        return ShapeSet(self.ctx, self.kind, self.params, mat4_mul(comp_xform[self.owner], self.local), self.mesh_id, self.meshes)
+    def close(self):
+        if self.handle:
+            self.ctx._lib.bam3d_compounds_free(self.ctx.handle, self.handle)
+            self.handle = None
 
-    def expand(self, pairs):
-        """All primitive pairs of every compound pair in the reference's loop order (left outer, right inner)."""
-        pairs = np.ascontiguousarray(pairs, dtype=np.int64).reshape(-1, 2)
-        out, seg = [], [0]
-        for l, r in pairs:
-            li = np.arange(self.offsets[l], self.offsets[l + 1])
-            ri = np.arange(self.offsets[r], self.offsets[r + 1])
-            out.append(np.stack([np.repeat(li, len(ri)), np.tile(ri, len(li))], axis=1))
-            seg.append(seg[-1] + len(li) * len(ri))
-        flat = np.concatenate(out, axis=0).astype(np.uint32) if out else np.zeros((0, 2), dtype=np.uint32)
-        return flat, np.array(seg, dtype=np.int64)
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def _complex_methods():
+    def _xf(compounds, x):
+        return np.ascontiguousarray(x, dtype=np.float32).reshape(compounds.n_compounds, 16)
+
     def intersection_complex_batch(self, strategy, compounds, comp_xform, pairs):
         """GJK::intersection_complex per compound pair (gjk/mod.rs:362-407) -> (contacts[n, 8], status[n])."""
-        flat, seg = compounds.expand(pairs)
-        shapes = compounds.shapes(comp_xform)
-        try:
-            c, st = self.intersection_batch(strategy, shapes, flat)
-        finally:
-            shapes.close()
-        n = len(seg) - 1
-        out, ost = np.zeros((n, 8), dtype=np.float32), np.full(n, _ffi.STATUS_MISS, dtype=np.uint8)
-        for k in range(n):
-            hits = np.nonzero(st[seg[k]:seg[k + 1]] == _ffi.STATUS_OK)[0] + seg[k]
-            if len(hits) == 0:
-                continue
-            if int(strategy) == _ffi.COLLISION_ONLY:
-                best = hits[0]                     # first hit returns (:388-390)
-            else:
-                d = c[hits, 3]
-                if len(hits) > 1 and np.isnan(d).any():
-                    ost[k] = _ffi.STATUS_REF_PANIC  # partial_cmp(..).unwrap() on a NaN depth (:403-405)
-                    continue
-                best = hits[len(d) - 1 - int(np.argmax(d[::-1]))]  # Iterator::max_by keeps the LAST maximum
-            out[k], ost[k] = c[best], _ffi.STATUS_OK
-        return out, ost
+        pairs, n = self._pairs(pairs)
+        out, st = np.zeros((n, 8), dtype=np.float32), np.empty(n, dtype=np.uint8)
+        self.ctx.check(self.ctx._lib.bam3d_gjk_contact_complex(self.ctx.handle, compounds.handle, _ptr(_xf(compounds, comp_xform)), _ptr(pairs), n,
+                                                               C.byref(self.settings), int(strategy), _ptr(out), _ptr(st)))
+        return out, st
 
     def distance_complex_batch(self, compounds, comp_xform, pairs):
         """GJK::distance_complex per compound pair (gjk/mod.rs:422-456) -> (value[n], status[n]); value = the reference's
         return (min of the per-primitive residuals)."""
-        flat, seg = compounds.expand(pairs)
-        shapes = compounds.shapes(comp_xform)
-        try:
-            ref, _, st = self.distance_batch(shapes, flat)
-        finally:
-            shapes.close()
-        n = len(seg) - 1
-        out, ost = np.zeros(n, dtype=np.float32), np.full(n, _ffi.STATUS_MISS, dtype=np.uint8)
-        for k in range(n):
-            s, r = st[seg[k]:seg[k + 1]], ref[seg[k]:seg[k + 1]]
-            bad = np.nonzero(s != _ffi.STATUS_OK)[0]
-            if len(bad):                            # `None => return None` at the first primitive pair that fails (:444)
-                ost[k] = _ffi.STATUS_REF_PANIC if s[bad[0]] == _ffi.STATUS_REF_PANIC else _ffi.STATUS_MISS
-            elif len(s):
-                out[k], ost[k] = np.min(r), _ffi.STATUS_OK
-        return out, ost
+        pairs, n = self._pairs(pairs)
+        out, st = np.zeros(n, dtype=np.float32), np.empty(n, dtype=np.uint8)
+        self.ctx.check(self.ctx._lib.bam3d_gjk_distance_complex(self.ctx.handle, compounds.handle, _ptr(_xf(compounds, comp_xform)), _ptr(pairs), n,
+                                                                C.byref(self.settings), _ptr(out), _ptr(st)))
+        return out, st
 
     def intersection_complex_time_of_impact_batch(self, strategy, compounds, comp_xform_start, comp_xform_end, pairs):
         """GJK::intersection_complex_time_of_impact per compound pair (gjk/mod.rs:478-523)."""
-        flat, seg = compounds.expand(pairs)
-        s0, s1 = compounds.shapes(comp_xform_start), compounds.shapes(comp_xform_end)
-        try:
-            c, st = self.intersection_time_of_impact_batch(s0, s1, flat)
-        finally:
-            s0.close()
-            s1.close()
-        n = len(seg) - 1
-        out, ost = np.zeros((n, 8), dtype=np.float32), np.full(n, _ffi.STATUS_MISS, dtype=np.uint8)
-        for k in range(n):
-            s = st[seg[k]:seg[k + 1]]
-            hits = np.nonzero(s == _ffi.STATUS_OK)[0]
-            panics = np.nonzero(s == _ffi.STATUS_REF_PANIC)[0]
-            first_only = int(strategy) == _ffi.COLLISION_ONLY
-            if len(panics) and (len(hits) == 0 or not first_only or panics[0] < hits[0]):
-                ost[k] = _ffi.STATUS_REF_PANIC      # the reference would have panicked inside that primitive pair
-                continue
-            if len(hits) == 0:
-                continue
-            hits = hits + seg[k]
-            best = hits[0] if first_only else hits[int(np.argmin(c[hits, 7]))]  # min_by keeps the FIRST minimum
-            out[k], ost[k] = c[best], _ffi.STATUS_OK
-        return out, ost
+        pairs, n = self._pairs(pairs)
+        out, st = np.zeros((n, 8), dtype=np.float32), np.empty(n, dtype=np.uint8)
+        self.ctx.check(self.ctx._lib.bam3d_gjk_time_of_impact_complex(self.ctx.handle, compounds.handle, _ptr(_xf(compounds, comp_xform_start)),
+                                                                      _ptr(_xf(compounds, comp_xform_end)), _ptr(pairs), n, C.byref(self.settings),
+                                                                      int(strategy), _ptr(out), _ptr(st)))
+        return out, st
 
     GJK.intersection_complex_batch = intersection_complex_batch
     GJK.distance_complex_batch = distance_complex_batch

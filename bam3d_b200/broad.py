@@ -199,6 +199,21 @@ class Bvh:
         self.ctx.check(self.ctx._lib.bam3d_bvh_query_ray_closest(self.ctx.handle, self.handle, _ptr(r), len(r), _ptr(val), _ptr(pt)))
         return val, pt
 
+    # ---- device-resident one-pass forms (raw device pointers; asynchronous on ctx.stream; hits in arbitrary order) ----
+    def query_dev(self, kind, d_queries, nq, d_out_query, d_out_values, d_out_payload, capacity, d_count):
+        """kind: "aabb" | "ray" | "frustum". Appends (query, value[, point | relation]) per hit; *d_count = hits found."""
+        lib, h = self.ctx._lib, self.ctx.handle
+        if kind == "aabb":
+            rc = lib.bam3d_bvh_query_aabb_dev(h, self.handle, d_queries, nq, d_out_query, d_out_values, capacity, d_count)
+        elif kind == "ray":
+            rc = lib.bam3d_bvh_query_ray_dev(h, self.handle, d_queries, nq, d_out_query, d_out_values, d_out_payload, capacity, d_count)
+        else:
+            rc = lib.bam3d_bvh_query_frustum_dev(h, self.handle, d_queries, nq, d_out_query, d_out_values, d_out_payload, capacity, d_count)
+        self.ctx.check(rc)
+
+    def query_ray_closest_dev(self, d_rays, nq, d_out_value, d_out_point_t):
+        self.ctx.check(self.ctx._lib.bam3d_bvh_query_ray_closest_dev(self.ctx.handle, self.handle, d_rays, nq, d_out_value, d_out_point_t))
+
     def find_collider_pairs(self, dirty):
         """DbvtBroadPhase::find_collider_pairs -> sorted unique (low, high) pairs."""
         dirty = np.ascontiguousarray(dirty, dtype=np.uint8)
@@ -270,3 +285,129 @@ def world_aabbs(shapes):
     out = np.empty((shapes.n, 6), dtype=np.float32)
     shapes.ctx.check(shapes.ctx._lib.bam3d_shapes_world_aabbs(shapes.ctx.handle, shapes.handle, _ptr(out)))
     return out
+
+
+def pipeline_contacts(gjk, shapes, strategy, sweep_axis=0, capacity=None):
+    """bam3d_pipeline_contacts: world AABBs -> SweepAndPrune3 -> perm remap -> GJK::intersection per candidate pair, resident.
+    -> dict(pairs[m, 2] shape indices, sorted_pairs[m, 2] as the reference returns them, perm[n], contacts[m, 8], status[m],
+    next_axis)."""
+    ctx = shapes.ctx
+    n = shapes.n
+
+    def call(cap):
+        pairs = np.empty((cap, 2), dtype=np.uint32)
+        spairs = np.empty((cap, 2), dtype=np.uint32)
+        perm = np.empty(max(n, 1), dtype=np.uint32)
+        contacts = np.empty((cap, 8), dtype=np.float32)
+        status = np.empty(cap, dtype=np.uint8)
+        axis = C.c_int32(int(sweep_axis))
+        cnt = C.c_uint64(0)
+        rc = ctx._lib.bam3d_pipeline_contacts(ctx.handle, shapes.handle, C.byref(axis), C.byref(gjk.settings), int(strategy), _ptr(pairs), _ptr(spairs),
+                                              _ptr(perm), _ptr(contacts), _ptr(status), cap, C.byref(cnt))
+        m = int(cnt.value)
+        return rc, m, dict(pairs=pairs[:m], sorted_pairs=spairs[:m], perm=perm[:n], contacts=contacts[:m], status=status[:m], next_axis=int(axis.value))
+
+    res = _retry_capacity(call, capacity if capacity is not None else 8 * n + 1024)
+    if isinstance(res, int):
+        ctx.check(res)
+    return res
+
+
+# ---------------------------------------------------------------------------------------------------------
+# bench.py hooks (C4 extras): device-resident queries at the stated sizes, CUDA-event timed
+# ---------------------------------------------------------------------------------------------------------
+def bench_queries(env, bvh, rays, planes):
+    """2^20 ray queries, 2^20 closest-ray queries and 1024 frustum queries against `bvh`, device-resident, one pass each.
+    Every figure is events on the ctx stream around `reps` back-to-back calls (after one warm-up call)."""
+    torch = env.torch
+    ctx = bvh.ctx
+    ext = env.ext[0]
+    dev = env.dev
+    p = lambda t: C.c_void_p(t.data_ptr())
+    out = {}
+
+    def timed(fn, reps=3):
+        fn()
+        ctx.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ext)
+        for _ in range(reps):
+            fn()
+        e1.record(ext)
+        ctx.synchronize(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    d_count = torch.zeros(1, dtype=torch.int64, device=dev)
+    # rays: first a small batch to size the output (hits per ray), then the full batch
+    d_rays = torch.from_numpy(rays).to(dev)
+    nq = len(rays)
+    probe = min(nq, 4096)
+    bvh.query_dev("ray", p(d_rays), probe, None, None, None, 0, p(d_count))
+    ctx.synchronize()
+    cap = int(int(d_count.item()) / probe * nq * 1.15) + 65536
+    d_q = torch.empty(cap, dtype=torch.int32, device=dev)
+    d_v = torch.empty(cap, dtype=torch.int32, device=dev)
+    d_pt = torch.empty(cap * 3, dtype=torch.float32, device=dev)
+    ms = timed(lambda: bvh.query_dev("ray", p(d_rays), nq, p(d_q), p(d_v), p(d_pt), cap, p(d_count)))
+    hits = int(d_count.item())
+    out.update({"rays": nq, "ray_hits": hits, "ray_query_ms": ms, "ray_queries_per_s": nq / (ms * 1e-3), "ray_hits_per_s": hits / (ms * 1e-3),
+                "ray_capacity_ok": hits <= cap})
+    d_cv = torch.empty(nq, dtype=torch.int32, device=dev)
+    d_cp = torch.empty(nq * 4, dtype=torch.float32, device=dev)
+    ms = timed(lambda: bvh.query_ray_closest_dev(p(d_rays), nq, p(d_cv), p(d_cp)))
+    out.update({"ray_closest_ms": ms, "ray_closest_queries_per_s": nq / (ms * 1e-3)})
+    del d_q, d_v, d_pt
+    # frusta
+    d_pl = torch.from_numpy(np.ascontiguousarray(planes, dtype=np.float32)).to(dev)
+    nf = len(planes)
+    probe = min(nf, 16)
+    bvh.query_dev("frustum", p(d_pl), probe, None, None, None, 0, p(d_count))
+    ctx.synchronize()
+    cap = int(int(d_count.item()) / probe * nf * 1.25) + 65536
+    d_q = torch.empty(cap, dtype=torch.int32, device=dev)
+    d_v = torch.empty(cap, dtype=torch.int32, device=dev)
+    d_rel = torch.empty(cap, dtype=torch.uint8, device=dev)
+    ms = timed(lambda: bvh.query_dev("frustum", p(d_pl), nf, p(d_q), p(d_v), p(d_rel), cap, p(d_count)), reps=2)
+    hits = int(d_count.item())
+    out.update({"frusta": nf, "frustum_hits": hits, "frustum_query_ms": ms, "frustum_queries_per_s": nf / (ms * 1e-3),
+                "frustum_hits_per_s": hits / (ms * 1e-3), "frustum_capacity_ok": hits <= cap,
+                "path": "bam3d_bvh_query_{ray,ray_closest,frustum}_dev: device-resident, one pass (append), CUDA events on the ctx stream; "
+                        "rays: stackless traversal, one thread per ray; frusta: every (frustum, value) leaf test (few large queries)"})
+    return out
+
+
+def bench_pipeline(env, n=1 << 20, steps=5):
+    """g1 (BASELINE configs[3] "... then narrow phase"): 2^20 shapes of the C2 mix in one volume; one step = world AABBs ->
+    sweep and prune -> perm remap -> GJK+EPA on every candidate pair, through bam3d_pipeline_contacts_dev (N > 1: the sort is
+    replicated, every rank searches and resolves its own shard of the pair list). CUDA events on the ctx stream."""
+    from . import scenes
+    from .api import ShapeSet, CollisionStrategy
+    torch = env.torch
+    ctx, gjk = env.ctxs[0], env.gjks[0]
+    scene, L = scenes.world_scene(n)
+    shapes = ShapeSet(ctx, scene["kind"], scene["params"], scene["xform"])
+    cap = 6 * n
+    dev = env.dev
+    d_pairs = torch.empty(cap * 2, dtype=torch.int32, device=dev)
+    d_contacts = torch.empty(cap * 8, dtype=torch.float32, device=dev)
+    d_status = torch.empty(cap, dtype=torch.uint8, device=dev)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    cnt = C.c_uint64(0)
+
+    def step(k=0):
+        axis = C.c_int32(0)
+        ctx.check(ctx._lib.bam3d_pipeline_contacts_dev(ctx.handle, shapes.handle, C.byref(axis), C.byref(gjk.settings), int(CollisionStrategy.FullResolution),
+                                                       env.rank, env.world, p(d_pairs), None, None, p(d_contacts), p(d_status), cap, C.byref(cnt)))
+    step.finish = lambda: None
+    ms, launches = env.timed(step, steps, 3)
+    m = int(cnt.value)
+    hits = int((d_status[:m] == 0).sum().item())
+    m_total = int(env.sum_over_ranks(m))
+    hits_total = int(env.sum_over_ranks(hits))
+    shapes.close()
+    if env.rank != 0:
+        return None
+    return {"shapes": n, "candidate_pairs": m_total, "contacts": hits_total, "ms_per_step": ms / steps,
+            "shapes_per_s": n * steps / (ms * 1e-3), "candidate_pairs_per_s": m_total * steps / (ms * 1e-3),
+            "path": "bam3d_pipeline_contacts_dev: bam3d_shapes_world_aabbs_dev -> sweep and prune (shard of this rank) -> perm remap -> bam3d_gjk_contact_dev, "
+                    "resident; one host synchronisation (the pair count)", "gpu_launches": launches}

@@ -632,17 +632,37 @@ __global__ void __launch_bounds__(BT) bvh_topology_kernel(const uint32_t* __rest
     if (i == 0) parent[0] = 0xFFFFFFFFu;
 }
 
-// Node record: two float4 side by side (one 32-byte sector): (min.xyz, left child) and (max.xyz, right child); the child
-// ids are stored as int bits, so a traversal reads one sector per node and no separate topology array.
+// Ropes: rope[node] = the node a depth-first, left-first traversal continues with once it is done with `node`'s subtree —
+// the right sibling of the nearest ancestor-or-self that is a left child, BVH_END above the root. With them the traversal
+// needs no stack (dbvt/mod.rs:481-515 keeps a fixed 256-entry one and indexes past it on a deeper tree): hit an internal node
+// -> its left child; miss, or a leaf -> the rope.
+__global__ void __launch_bounds__(BT) bvh_ropes_kernel(const int2* __restrict__ children, const uint32_t* __restrict__ parent, uint32_t n,
+                                                       uint32_t* __restrict__ rope) {
+    const uint32_t node = blockIdx.x * BT + threadIdx.x;
+    if (node >= 2 * n - 1) return;
+    uint32_t cur = node, r = BVH_END;
+    for (;;) {
+        const uint32_t p = parent[cur];
+        if (p == 0xFFFFFFFFu) break;
+        const int2 ch = children[p];
+        if ((uint32_t)ch.x == cur) { r = (uint32_t)ch.y; break; }
+        cur = p;
+    }
+    rope[node] = r;
+}
+
+// Node record: two float4 side by side (one 32-byte sector): (min.xyz, A) and (max.xyz, rope) with A = the left child of an
+// internal node or the value index of a leaf, stored as int bits: a traversal step reads one sector and nothing else.
 __global__ void __launch_bounds__(BT) bvh_refit_kernel(const float* __restrict__ aabbs, const uint32_t* __restrict__ leaf_value, uint32_t n,
                                                        const int2* __restrict__ children, const uint32_t* __restrict__ parent,
-                                                       uint32_t* __restrict__ flags, float4* __restrict__ nodes) {
+                                                       const uint32_t* __restrict__ rope, uint32_t* __restrict__ flags, float4* __restrict__ nodes) {
     uint32_t k = blockIdx.x * BT + threadIdx.x;
     if (k >= n) return;
-    const float* b = aabbs + 6 * (size_t)leaf_value[k];
+    const uint32_t value = leaf_value[k];
+    const float* b = aabbs + 6 * (size_t)value;
     uint32_t node = (n - 1) + k;
-    nodes[2 * (size_t)node] = make_float4(b[0], b[1], b[2], 0.f);
-    nodes[2 * (size_t)node + 1] = make_float4(b[3], b[4], b[5], 0.f);
+    nodes[2 * (size_t)node] = make_float4(b[0], b[1], b[2], __int_as_float((int)value));
+    nodes[2 * (size_t)node + 1] = make_float4(b[3], b[4], b[5], __int_as_float((int)rope[node]));
     if (n == 1) return;
     __threadfence();
     uint32_t p = parent[node];
@@ -654,7 +674,7 @@ __global__ void __launch_bounds__(BT) bvh_refit_kernel(const float* __restrict__
         float4 l1 = __ldcg(nodes + 2 * (size_t)ch.y), h1 = __ldcg(nodes + 2 * (size_t)ch.y + 1);
         // union = grow(min).grow(max) with Rust's NaN-ignoring min/max (aabb3.rs:146-152)
         nodes[2 * (size_t)p] = make_float4(rmin(l0.x, l1.x), rmin(l0.y, l1.y), rmin(l0.z, l1.z), __int_as_float(ch.x));
-        nodes[2 * (size_t)p + 1] = make_float4(rmax(h0.x, h1.x), rmax(h0.y, h1.y), rmax(h0.z, h1.z), __int_as_float(ch.y));
+        nodes[2 * (size_t)p + 1] = make_float4(rmax(h0.x, h1.x), rmax(h0.y, h1.y), rmax(h0.z, h1.z), __int_as_float((int)rope[p]));
         __threadfence();
         p = parent[p];
     }
@@ -674,7 +694,7 @@ __global__ void __launch_bounds__(BT) bvh_parents_kernel(const int2* __restrict_
 }
 
 int launch_bvh_refit(cudaStream_t st, const float* d_aabbs, uint32_t n, const int2* children, const uint32_t* leaf_value, uint32_t* parent,
-                     uint32_t* flags, float4* nodes) {
+                     const uint32_t* rope, uint32_t* flags, float4* nodes) {
     if (n == 0) return 0;
     int launched = 1;
     if (n > 1) {
@@ -682,7 +702,7 @@ int launch_bvh_refit(cudaStream_t st, const float* d_aabbs, uint32_t n, const in
         bvh_parents_kernel<<<(n + BT - 1) / BT, BT, 0, st>>>(children, n, parent);
         ++launched;
     }
-    bvh_refit_kernel<<<(n + BT - 1) / BT, BT, 0, st>>>(d_aabbs, leaf_value, n, children, parent, flags, nodes);
+    bvh_refit_kernel<<<(n + BT - 1) / BT, BT, 0, st>>>(d_aabbs, leaf_value, n, children, parent, rope, flags, nodes);
     return launched;
 }
 
@@ -693,7 +713,7 @@ size_t bvh_cub_tmp_bytes(uint32_t n) {
 }
 
 int launch_bvh_build(cudaStream_t st, const float* d_aabbs, uint32_t n, const BvhBuildScratch& W, float4* nodes, int2* children,
-                     uint32_t* leaf_value) {
+                     uint32_t* leaf_value, uint32_t* rope) {
     if (n == 0) return 0;
     int launched = 0;
     const int g = (n + BT - 1) / BT;
@@ -706,8 +726,11 @@ int launch_bvh_build(cudaStream_t st, const float* d_aabbs, uint32_t n, const Bv
     if (n > 1) {
         cudaMemsetAsync(W.flags, 0, (size_t)(n - 1) * 4, st);
         bvh_topology_kernel<<<(n - 1 + BT - 1) / BT, BT, 0, st>>>(W.morton_out, n, children, W.parent); ++launched;
+        bvh_ropes_kernel<<<(2 * n - 1 + BT - 1) / BT, BT, 0, st>>>(children, W.parent, n, rope); ++launched;
+    } else {
+        cudaMemsetAsync(rope, 0xFF, 4, st);  // a single leaf: nothing follows it
     }
-    bvh_refit_kernel<<<g, BT, 0, st>>>(d_aabbs, leaf_value, n, children, W.parent, W.flags, nodes); ++launched;
+    bvh_refit_kernel<<<g, BT, 0, st>>>(d_aabbs, leaf_value, n, children, W.parent, rope, W.flags, nodes); ++launched;
     return launched;
 }
 
@@ -752,8 +775,27 @@ B3_DEV int relate_box(float4 mn, float4 mx, float4 pl) {
 B3_DEV int frustum_relation(float4 mn, float4 mx, const float4* pl) {
     int cur = 0;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) cur = max(cur, relate_box(mn, mx, pl[k]));
+    for (int k = 0; k < 6; ++k) {
+        cur = max(cur, relate_box(mn, mx, pl[k]));
+        if (cur == 2) break;  // Out stays Out whatever the other planes say (the fold is a max): same value, fewer planes
+    }
     return cur;
+}
+
+// Stackless depth-first traversal, left child first (the order the reference's explicit stack gives: it pushes left, right
+// and pops right first — result SETS are what is compared, see bam3d_gpu.h). `visit(leaf, A, mn, mx)` is called for every
+// node reached; for an internal node its return value says whether to descend; A = value index of a leaf.
+template <class F>
+B3_DEV void bvh_traverse(const BvhDev& T, F&& visit) {
+    if (T.n == 0) return;
+    const uint32_t first_leaf = T.n - 1;
+    uint32_t node = 0;  // the root (a single leaf has id 0 too)
+    while (node != BVH_END) {
+        const float4 mn = __ldg(T.nodes + 2 * (size_t)node), mx = __ldg(T.nodes + 2 * (size_t)node + 1);
+        const bool leaf = node >= first_leaf;
+        const bool down = visit(leaf, (uint32_t)__float_as_int(mn.w), mn, mx);
+        node = (down && !leaf) ? (uint32_t)__float_as_int(mn.w) : (uint32_t)__float_as_int(mx.w);
+    }
 }
 
 struct Query {
@@ -790,7 +832,7 @@ B3_DEV void load_query(Query& q, const float* __restrict__ queries, uint32_t qi)
     }
 }
 
-// One thread per query, explicit stack. FILL = false counts hits; FILL = true writes them at offsets[qi].
+// One thread per query, stackless. FILL = false counts hits; FILL = true writes them at offsets[qi].
 template <int KIND, bool FILL>
 __global__ void __launch_bounds__(BT) bvh_query_kernel(BvhDev T, const float* __restrict__ queries, uint32_t nq, uint32_t* __restrict__ counts,
                                                        const unsigned long long* __restrict__ offsets, uint32_t* __restrict__ values,
@@ -801,32 +843,148 @@ __global__ void __launch_bounds__(BT) bvh_query_kernel(BvhDev T, const float* __
     load_query<KIND>(q, queries, qi);
     unsigned long long w = FILL ? offsets[qi] : 0ull;
     uint32_t cnt = 0;
-    if (T.n > 0) {
-        uint32_t stack[64];
-        int sp = 0;
-        stack[sp++] = (T.n == 1) ? 0u + (T.n - 1) : 0u;
-        const uint32_t first_leaf = T.n - 1;
-        while (sp > 0) {
-            uint32_t node = stack[--sp];
-            float4 mn = __ldg(T.nodes + 2 * (size_t)node), mx = __ldg(T.nodes + 2 * (size_t)node + 1);
-            V3 point; int rel = 0;
-            if (!accept<KIND>(q, mn, mx, point, rel)) continue;
-            if (node >= first_leaf) {
-                if (FILL) {
-                    values[w] = __ldg(T.leaf_value + (node - first_leaf));
-                    if (KIND == BQ_RAY) { float* p = reinterpret_cast<float*>(payload) + 3 * w; p[0] = point.x; p[1] = point.y; p[2] = point.z; }
-                    if (KIND == BQ_FRUSTUM) reinterpret_cast<uint8_t*>(payload)[w] = (uint8_t)rel;
-                    ++w;
+    bvh_traverse(T, [&](bool leaf, uint32_t value, float4 mn, float4 mx) {
+        V3 point; int rel = 0;
+        if (!accept<KIND>(q, mn, mx, point, rel)) return false;
+        if (leaf) {
+            if (FILL) {
+                values[w] = value;
+                if (KIND == BQ_RAY) { float* p = reinterpret_cast<float*>(payload) + 3 * w; p[0] = point.x; p[1] = point.y; p[2] = point.z; }
+                if (KIND == BQ_FRUSTUM) reinterpret_cast<uint8_t*>(payload)[w] = (uint8_t)rel;
+                ++w;
+            }
+            ++cnt;
+        }
+        return true;
+    });
+    if (!FILL) counts[qi] = cnt;
+}
+
+// The same in ONE pass for device-resident callers: every hit is appended to (out_query, out_value, out_payload) through a
+// warp-aggregated atomic, in no particular order (sort by out_query for the per-query lists). *count keeps counting past
+// `capacity`; hits beyond it are dropped.
+template <int KIND>
+__global__ void __launch_bounds__(BT) bvh_query_append_kernel(BvhDev T, const float* __restrict__ queries, uint32_t nq, uint32_t* __restrict__ out_query,
+                                                              uint32_t* __restrict__ out_value, void* __restrict__ out_payload,
+                                                              unsigned long long capacity, unsigned long long* __restrict__ count) {
+    uint32_t qi = blockIdx.x * BT + threadIdx.x;
+    if (qi >= nq) return;
+    Query q;
+    load_query<KIND>(q, queries, qi);
+    const uint32_t lane = threadIdx.x & 31u;
+    bvh_traverse(T, [&](bool leaf, uint32_t value, float4 mn, float4 mx) {
+        V3 point; int rel = 0;
+        if (!accept<KIND>(q, mn, mx, point, rel)) return false;
+        if (leaf) {
+            const uint32_t act = __activemask();
+            const uint32_t leader = __ffs(act) - 1;
+            unsigned long long base = 0;
+            if (lane == leader) base = atomicAdd(count, (unsigned long long)__popc(act));
+            base = __shfl_sync(act, base, leader);
+            const unsigned long long w = base + __popc(act & ((1u << lane) - 1u));
+            if (w < capacity) {
+                out_query[w] = qi;
+                out_value[w] = value;
+                if (KIND == BQ_RAY) { float* p = reinterpret_cast<float*>(out_payload) + 3 * w; p[0] = point.x; p[1] = point.y; p[2] = point.z; }
+                if (KIND == BQ_FRUSTUM) reinterpret_cast<uint8_t*>(out_payload)[w] = (uint8_t)rel;
+            }
+        }
+        return true;
+    });
+}
+
+int launch_bvh_query_append(cudaStream_t st, const BvhDev& T, int kind, const float* d_queries, uint32_t nq, uint32_t* d_out_query,
+                            uint32_t* d_out_value, void* d_out_payload, uint64_t capacity, unsigned long long* d_count) {
+    cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), st);
+    if (nq == 0 || T.n == 0) return 0;
+    const int g = (nq + BT - 1) / BT;
+    if (kind == BQ_AABB) bvh_query_append_kernel<BQ_AABB><<<g, BT, 0, st>>>(T, d_queries, nq, d_out_query, d_out_value, d_out_payload, capacity, d_count);
+    else if (kind == BQ_RAY) bvh_query_append_kernel<BQ_RAY><<<g, BT, 0, st>>>(T, d_queries, nq, d_out_query, d_out_value, d_out_payload, capacity, d_count);
+    else bvh_query_append_kernel<BQ_FRUSTUM><<<g, BT, 0, st>>>(T, d_queries, nq, d_out_query, d_out_value, d_out_payload, capacity, d_count);
+    return 1;
+}
+
+// Few large queries, one pass: every (query, value) leaf test, a tile of 256 values per block against the queries of the grid's
+// y-slice staged in shared memory; a thread keeps its box in registers. Hits are collected per block (shared counter) and flushed
+// with one global atomic per block and query chunk, so the append counter is not hammered by 10^8 warp-level atomics.
+constexpr int BRUTE_Q = 16;  // queries per shared-memory chunk
+template <int KIND>
+__global__ void __launch_bounds__(256) bvh_brute_append_kernel(const float* __restrict__ aabbs, uint32_t n, const float* __restrict__ queries, uint32_t nq,
+                                                               uint32_t q_per_block, uint32_t* __restrict__ out_query, uint32_t* __restrict__ out_value,
+                                                               void* __restrict__ out_payload, unsigned long long capacity,
+                                                               unsigned long long* __restrict__ count) {
+    constexpr int QF = KIND == BQ_FRUSTUM ? 24 : 6;
+    __shared__ float sq[BRUTE_Q * QF];
+    __shared__ uint32_t s_n;
+    __shared__ unsigned long long s_base;
+    __shared__ uint32_t s_q[256 * 4], s_v[256 * 4];
+    __shared__ float s_p[KIND == BQ_RAY ? 256 * 4 * 3 : 1];
+    __shared__ uint8_t s_r[KIND == BQ_FRUSTUM ? 256 * 4 : 1];
+    const uint32_t v = blockIdx.x * 256 + threadIdx.x;
+    float4 mn = make_float4(0.f, 0.f, 0.f, 0.f), mx = mn;
+    if (v < n) { const float* b = aabbs + 6 * (size_t)v; mn = make_float4(b[0], b[1], b[2], 0.f); mx = make_float4(b[3], b[4], b[5], 0.f); }
+    const uint32_t q_begin = blockIdx.y * q_per_block, q_end = min(nq, q_begin + q_per_block);
+    for (uint32_t q0 = q_begin; q0 < q_end; q0 += BRUTE_Q) {
+        const uint32_t nqc = min((uint32_t)BRUTE_Q, q_end - q0);
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < nqc * QF; i += 256) sq[i] = queries[(size_t)q0 * QF + i];
+        if (threadIdx.x == 0) s_n = 0;
+        __syncthreads();
+        // at most 4 hits per thread are staged per flush; a chunk is processed in sub-chunks of 4 queries
+        for (uint32_t qs = 0; qs < nqc; qs += 4) {
+            for (uint32_t k = qs; k < min(nqc, qs + 4); ++k) {
+                Query q;
+                if (KIND == BQ_AABB) { const float* b = sq + k * 6; q.qlo = make_float4(b[0], b[1], b[2], 0.f); q.qhi = make_float4(b[3], b[4], b[5], 0.f); }
+                else if (KIND == BQ_RAY) { const float* b = sq + k * 6; q.o = v3(b[0], b[1], b[2]); q.d = v3(b[3], b[4], b[5]); }
+                else {
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) q.pl[j] = make_float4(sq[k * 24 + 4 * j], sq[k * 24 + 4 * j + 1], sq[k * 24 + 4 * j + 2], sq[k * 24 + 4 * j + 3]);
                 }
-                ++cnt;
-            } else if (sp <= 62) {
-                int2 ch = make_int2(__float_as_int(mn.w), __float_as_int(mx.w));
-                stack[sp++] = (uint32_t)ch.y;
-                stack[sp++] = (uint32_t)ch.x;
+                V3 point = v3(0.f, 0.f, 0.f); int rel = 0;
+                if (v < n && accept<KIND>(q, mn, mx, point, rel)) {
+                    const uint32_t at = atomicAdd(&s_n, 1u);
+                    s_q[at] = q0 + k; s_v[at] = v;
+                    if (KIND == BQ_RAY) { s_p[3 * at] = point.x; s_p[3 * at + 1] = point.y; s_p[3 * at + 2] = point.z; }
+                    if (KIND == BQ_FRUSTUM) s_r[at] = (uint8_t)rel;
+                }
+            }
+            __syncthreads();
+            const uint32_t cnt = s_n;
+            if (cnt) {
+                if (threadIdx.x == 0) s_base = atomicAdd(count, (unsigned long long)cnt);
+                __syncthreads();
+                const unsigned long long base = s_base;
+                for (uint32_t i = threadIdx.x; i < cnt; i += 256) {
+                    const unsigned long long w = base + i;
+                    if (w < capacity) {
+                        out_query[w] = s_q[i]; out_value[w] = s_v[i];
+                        if (KIND == BQ_RAY) { float* p = reinterpret_cast<float*>(out_payload) + 3 * w; p[0] = s_p[3 * i]; p[1] = s_p[3 * i + 1]; p[2] = s_p[3 * i + 2]; }
+                        if (KIND == BQ_FRUSTUM) reinterpret_cast<uint8_t*>(out_payload)[w] = s_r[i];
+                    }
+                }
+                __syncthreads();
+                if (threadIdx.x == 0) s_n = 0;
+                __syncthreads();
             }
         }
     }
-    if (!FILL) counts[qi] = cnt;
+}
+
+int launch_bvh_brute_append(cudaStream_t st, const float* d_aabbs, uint32_t n, int kind, const float* d_queries, uint32_t nq, uint32_t* d_out_query,
+                            uint32_t* d_out_value, void* d_out_payload, uint64_t capacity, unsigned long long* d_count) {
+    cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), st);
+    if (nq == 0 || n == 0) return 0;
+    const uint32_t ntiles = (n + 255) / 256;
+    // enough blocks to fill the machine a few times over, as few passes over the boxes as that allows
+    uint32_t ysplit = (148u * 32u + ntiles - 1) / ntiles;
+    if (ysplit < 1) ysplit = 1;
+    if (ysplit > nq) ysplit = nq;
+    const uint32_t q_per_block = (nq + ysplit - 1) / ysplit;
+    const dim3 grid(ntiles, (nq + q_per_block - 1) / q_per_block);
+    if (kind == BQ_AABB) bvh_brute_append_kernel<BQ_AABB><<<grid, 256, 0, st>>>(d_aabbs, n, d_queries, nq, q_per_block, d_out_query, d_out_value, d_out_payload, capacity, d_count);
+    else if (kind == BQ_RAY) bvh_brute_append_kernel<BQ_RAY><<<grid, 256, 0, st>>>(d_aabbs, n, d_queries, nq, q_per_block, d_out_query, d_out_value, d_out_payload, capacity, d_count);
+    else bvh_brute_append_kernel<BQ_FRUSTUM><<<grid, 256, 0, st>>>(d_aabbs, n, d_queries, nq, q_per_block, d_out_query, d_out_value, d_out_payload, capacity, d_count);
+    return 1;
 }
 
 int launch_bvh_query(cudaStream_t st, const BvhDev& T, int kind, const float* d_queries, uint32_t nq, uint32_t* d_counts,
@@ -918,28 +1076,17 @@ __global__ void __launch_bounds__(BT) bvh_ray_closest_kernel(BvhDev T, const flo
     float best_t = INFINITY;
     uint32_t best_v = 0xFFFFFFFFu;
     V3 best_p = v3(0.f, 0.f, 0.f);
-    if (T.n > 0) {
-        uint32_t stack[64];
-        int sp = 0;
-        stack[sp++] = (T.n == 1) ? (T.n - 1) : 0u;
-        const uint32_t first_leaf = T.n - 1;
-        while (sp > 0) {
-            uint32_t node = stack[--sp];
-            float4 mn = __ldg(T.nodes + 2 * (size_t)node), mx = __ldg(T.nodes + 2 * (size_t)node + 1);
-            V3 p;
-            bool entered_from_outside;
-            if (!ray_aabb(o, d, mn, mx, p, &entered_from_outside)) continue;
-            float t = dot(p - o, d);
-            if (node >= first_leaf) {
-                uint32_t v = __ldg(T.leaf_value + (node - first_leaf));
-                if (t < best_t || (t == best_t && v < best_v)) { best_t = t; best_v = v; best_p = p; }
-            } else if (!(entered_from_outside && t > best_t) && sp <= 62) {
-                int2 ch = make_int2(__float_as_int(mn.w), __float_as_int(mx.w));
-                stack[sp++] = (uint32_t)ch.y;
-                stack[sp++] = (uint32_t)ch.x;
-            }
+    bvh_traverse(T, [&](bool leaf, uint32_t v, float4 mn, float4 mx) {
+        V3 p;
+        bool entered_from_outside;
+        if (!ray_aabb(o, d, mn, mx, p, &entered_from_outside)) return false;
+        const float t = dot(p - o, d);
+        if (leaf) {
+            if (t < best_t || (t == best_t && v < best_v)) { best_t = t; best_v = v; best_p = p; }
+            return false;
         }
-    }
+        return !(entered_from_outside && t > best_t);
+    });
     out_value[qi] = best_v;
     float* op = out_point_t + 4 * (size_t)qi;
     op[0] = best_p.x; op[1] = best_p.y; op[2] = best_p.z; op[3] = best_t;
@@ -971,28 +1118,16 @@ __global__ void __launch_bounds__(BT) bvh_collider_pairs_kernel(BvhDev T, const 
         Query q;
         q.qlo = make_float4(b[0], b[1], b[2], 0.f); q.qhi = make_float4(b[3], b[4], b[5], 0.f);
         unsigned long long w = FILL ? offsets[v] : 0ull;
-        uint32_t stack[64];
-        int sp = 0;
-        stack[sp++] = (T.n == 1) ? (T.n - 1) : 0u;
-        const uint32_t first_leaf = T.n - 1;
-        while (sp > 0) {
-            uint32_t node = stack[--sp];
-            float4 mn = __ldg(T.nodes + 2 * (size_t)node), mx = __ldg(T.nodes + 2 * (size_t)node + 1);
+        bvh_traverse(T, [&](bool leaf, uint32_t h, float4 mn, float4 mx) {
             V3 pt; int rel;
-            if (!accept<BQ_AABB>(q, mn, mx, pt, rel)) continue;
-            if (node >= first_leaf) {
-                uint32_t h = __ldg(T.leaf_value + (node - first_leaf));
-                if (h != v && (dirty ? (!dirty[h] || v < h) : h < v)) {
-                    if (FILL) keys[w++] = key_shift ? (((unsigned long long)max(v, h) << key_shift) | min(v, h))
-                                                    : (((unsigned long long)min(v, h) << 32) | max(v, h));
-                    ++cnt;
-                }
-            } else if (sp <= 62) {
-                int2 ch = make_int2(__float_as_int(mn.w), __float_as_int(mx.w));
-                stack[sp++] = (uint32_t)ch.y;
-                stack[sp++] = (uint32_t)ch.x;
+            if (!accept<BQ_AABB>(q, mn, mx, pt, rel)) return false;
+            if (leaf && h != v && (dirty ? (!dirty[h] || v < h) : h < v)) {
+                if (FILL) keys[w++] = key_shift ? (((unsigned long long)max(v, h) << key_shift) | min(v, h))
+                                                : (((unsigned long long)min(v, h) << 32) | max(v, h));
+                ++cnt;
             }
-        }
+            return true;
+        });
     }
     if (!FILL) counts[v] = cnt;
 }
@@ -1014,32 +1149,20 @@ __global__ void __launch_bounds__(BT) bvh_overlap_append_kernel(BvhDev T, const 
     Query q;
     q.qlo = make_float4(b[0], b[1], b[2], 0.f); q.qhi = make_float4(b[3], b[4], b[5], 0.f);
     const uint32_t lane = threadIdx.x & 31u;
-    uint32_t stack[64];
-    int sp = 0;
-    stack[sp++] = (T.n == 1) ? (T.n - 1) : 0u;
-    const uint32_t first_leaf = T.n - 1;
-    while (sp > 0) {
-        const uint32_t node = stack[--sp];
-        const float4 mn = __ldg(T.nodes + 2 * (size_t)node), mx = __ldg(T.nodes + 2 * (size_t)node + 1);
+    bvh_traverse(T, [&](bool leaf, uint32_t h, float4 mn, float4 mx) {
         V3 pt; int rel;
-        if (!accept<BQ_AABB>(q, mn, mx, pt, rel)) continue;
-        if (node >= first_leaf) {
-            const uint32_t h = __ldg(T.leaf_value + (node - first_leaf));
-            if (h < v) {
-                const uint32_t act = __activemask();
-                const uint32_t leader = __ffs(act) - 1;
-                unsigned long long base = 0;
-                if (lane == leader) base = atomicAdd(count, (unsigned long long)__popc(act));
-                base = __shfl_sync(act, base, leader);
-                const unsigned long long slot = base + __popc(act & ((1u << lane) - 1u));
-                if (slot < capacity) keys[slot] = ((unsigned long long)v << key_shift) | h;
-            }
-        } else if (sp <= 62) {
-            const int2 ch = make_int2(__float_as_int(mn.w), __float_as_int(mx.w));
-            stack[sp++] = (uint32_t)ch.y;
-            stack[sp++] = (uint32_t)ch.x;
+        if (!accept<BQ_AABB>(q, mn, mx, pt, rel)) return false;
+        if (leaf && h < v) {
+            const uint32_t act = __activemask();
+            const uint32_t leader = __ffs(act) - 1;
+            unsigned long long base = 0;
+            if (lane == leader) base = atomicAdd(count, (unsigned long long)__popc(act));
+            base = __shfl_sync(act, base, leader);
+            const unsigned long long at = base + __popc(act & ((1u << lane) - 1u));
+            if (at < capacity) keys[at] = ((unsigned long long)v << key_shift) | h;
         }
-    }
+        return true;
+    });
 }
 
 int launch_bvh_overlap_append(cudaStream_t st, const BvhDev& T, const float* d_aabbs, uint32_t v_begin, uint32_t v_end, int key_shift,
@@ -1057,6 +1180,24 @@ int launch_bvh_collider_pairs(cudaStream_t st, const BvhDev& T, const float* d_a
     const int g = (T.n + BT - 1) / BT;
     if (d_offsets) bvh_collider_pairs_kernel<true><<<g, BT, 0, st>>>(T, d_aabbs, d_dirty, v_begin, v_end, d_counts, d_offsets, d_pair_keys, key_shift);
     else bvh_collider_pairs_kernel<false><<<g, BT, 0, st>>>(T, d_aabbs, d_dirty, v_begin, v_end, d_counts, d_offsets, d_pair_keys, key_shift);
+    return 1;
+}
+
+// SweepAndPrune3 returns indices into the slice it has just re-sorted (sweep_prune.rs:65-69,80): pair (i, j) means the shapes at
+// SORTED positions i and j. The narrow phase reads the caller's (unsorted) shape set, so the glue between the two is
+// out[k] = (perm[i], perm[j]) with perm[slot] = original index of the box at that sorted position.
+__global__ void __launch_bounds__(BT) remap_pairs_kernel(const uint2* __restrict__ sorted_pairs, const uint32_t* __restrict__ perm, uint64_t n,
+                                                         uint2* __restrict__ out) {
+    for (uint64_t k = (uint64_t)blockIdx.x * BT + threadIdx.x; k < n; k += (uint64_t)gridDim.x * BT) {
+        const uint2 p = sorted_pairs[k];
+        out[k] = make_uint2(__ldg(perm + p.x), __ldg(perm + p.y));
+    }
+}
+int launch_remap_pairs(cudaStream_t st, const uint2* d_sorted_pairs, const uint32_t* d_perm, uint64_t n, uint2* d_out) {
+    if (n == 0) return 0;
+    uint64_t g = (n + BT - 1) / BT;
+    if (g > 148ull * 32) g = 148ull * 32;
+    remap_pairs_kernel<<<(unsigned)g, BT, 0, st>>>(d_sorted_pairs, d_perm, n, d_out);
     return 1;
 }
 

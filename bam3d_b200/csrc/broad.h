@@ -53,10 +53,12 @@ int launch_sphere_pair_filter(cudaStream_t st, const float4* d_sorted_spheres, i
                               unsigned long long* d_count, void* d_tmp, size_t tmp_bytes);
 
 // ---- static BVH answering the DBVT queries ---------------------------------------------------------------------
+constexpr uint32_t BVH_END = 0xFFFFFFFFu;  // rope of the last node in traversal order
 struct BvhDev {
     // n leaves (values), n - 1 internal nodes. Node ids: internal 0..n-2 (root = 0), leaf k -> (n - 1) + k.
     uint32_t n;
-    const float4* nodes;     // 2 x (2n - 1): (min.xyz, left child id as int bits), (max.xyz, right child id) — one 32-byte sector per node
+    const float4* nodes;     // 2 x (2n - 1): (min.xyz, A), (max.xyz, rope) as int bits — one 32-byte sector per node; A = left child
+                             // (internal) or value index (leaf); rope = where a left-first depth-first traversal goes after this subtree
     const uint32_t* leaf_value;  // n : value index of leaf k (Morton order)
 };
 struct BvhBuildScratch {
@@ -67,12 +69,13 @@ struct BvhBuildScratch {
     float* scene;       // 6 floats: scene bounds
 };
 size_t bvh_cub_tmp_bytes(uint32_t n);
+// rope: 2n - 1 words, kept with the tree (the refit needs them again)
 int launch_bvh_build(cudaStream_t st, const float* d_aabbs, uint32_t n, const BvhBuildScratch& W, float4* nodes, int2* children,
-                     uint32_t* leaf_value);
+                     uint32_t* leaf_value, uint32_t* rope);
 
 // bounds of an existing tree recomputed from new values (same topology); parent: 2n - 1 words, flags: n - 1 words of scratch
 int launch_bvh_refit(cudaStream_t st, const float* d_aabbs, uint32_t n, const int2* children, const uint32_t* leaf_value, uint32_t* parent,
-                     uint32_t* flags, float4* nodes);
+                     const uint32_t* rope, uint32_t* flags, float4* nodes);
 
 enum BvhQueryKind { BQ_AABB = 0, BQ_RAY = 1, BQ_FRUSTUM = 2 };
 // pass 1 (d_offsets == nullptr): per-query hit counts into d_counts. pass 2: fill d_values / d_payload at d_offsets.
@@ -83,6 +86,12 @@ int launch_bvh_query(cudaStream_t st, const BvhDev& T, int kind, const float* d_
 // all (query, value) tests, for few large queries: d_counts / d_offsets are indexed [query * ntiles + tile], ntiles = ceil(n / 256)
 int launch_bvh_brute(cudaStream_t st, const float* d_aabbs, uint32_t n, int kind, const float* d_queries, uint32_t nq, uint32_t* d_counts,
                      const unsigned long long* d_offsets, uint32_t* d_values, void* d_payload);
+// one pass, device-resident: hits appended as (query, value, payload) in arbitrary order; *d_count (device u64) keeps counting
+// past `capacity`. _append: tree traversal, one thread per query; _brute_append: every (query, value) test, for few large queries.
+int launch_bvh_query_append(cudaStream_t st, const BvhDev& T, int kind, const float* d_queries, uint32_t nq, uint32_t* d_out_query,
+                            uint32_t* d_out_value, void* d_out_payload, uint64_t capacity, unsigned long long* d_count);
+int launch_bvh_brute_append(cudaStream_t st, const float* d_aabbs, uint32_t n, int kind, const float* d_queries, uint32_t nq, uint32_t* d_out_query,
+                            uint32_t* d_out_value, void* d_out_payload, uint64_t capacity, unsigned long long* d_count);
 int launch_bvh_ray_closest(cudaStream_t st, const BvhDev& T, const float* d_rays, uint32_t nq, uint32_t* d_value, float* d_point_t);
 // DbvtBroadPhase::find_collider_pairs: count / fill passes over the dirty values.
 // d_dirty == nullptr (sweep-and-prune over sorted slots): pairs are emitted from their higher slot, for the slots in
@@ -94,6 +103,8 @@ int launch_bvh_collider_pairs(cudaStream_t st, const BvhDev& T, const float* d_a
 // (v << key_shift | h) in arbitrary order; *d_count (device u64) = pairs found (may exceed capacity)
 int launch_bvh_overlap_append(cudaStream_t st, const BvhDev& T, const float* d_aabbs, uint32_t v_begin, uint32_t v_end, int key_shift,
                               unsigned long long* d_pair_keys, uint64_t capacity, unsigned long long* d_count);
+// sorted-position pairs -> shape-index pairs through perm (the glue between SweepAndPrune3's output and the narrow phase)
+int launch_remap_pairs(cudaStream_t st, const uint2* d_sorted_pairs, const uint32_t* d_perm, uint64_t n, uint2* d_out);
 int launch_exclusive_scan_u32_to_u64(cudaStream_t st, const uint32_t* d_in, unsigned long long* d_out, uint32_t n, void* tmp, size_t tmp_bytes);
 size_t scan_tmp_bytes(uint32_t n);
 int launch_sort_u64(cudaStream_t st, unsigned long long* d_keys, unsigned long long* d_alt, uint64_t n, void* tmp, size_t tmp_bytes, bool* in_alt);

@@ -146,12 +146,15 @@ int32_t bam3d_ctx_create(int32_t device_ordinal, bam3d_ctx** out_ctx) {
     bam3d_ctx* ctx = new (std::nothrow) bam3d_ctx();
     if (!ctx) return BAM3D_ERR_OOM;
     ctx->device = device_ordinal;
+#ifdef B3_EXPERIMENTS
     if (const char* e = std::getenv("BAM3D_EPA_TIERS")) ctx->opt_epa_tiers = std::atoi(e) != 0;      // development A/B switches
+    if (const char* e = std::getenv("BAM3D_EPA_PIPELINE")) ctx->opt_epa_pipeline = std::atoi(e) != 0;
+    if (const char* e = std::getenv("BAM3D_INTERSECT_SPLIT")) ctx->opt_intersect_split = std::atoi(e) != 0;
+    if (const char* e = std::getenv("BAM3D_INTERSECT_REFILL")) ctx->opt_intersect_refill = std::atoi(e);
+#endif
     if (const char* e = std::getenv("BAM3D_EPA_OVERLAP")) ctx->opt_epa_overlap = std::atoi(e) != 0;
     if (const char* e = std::getenv("BAM3D_EPA_GLOBAL")) ctx->opt_epa_global_polytopes = std::atoi(e) != 0;
-    if (const char* e = std::getenv("BAM3D_INTERSECT_SPLIT")) ctx->opt_intersect_split = std::atoi(e) != 0;
     if (const char* e = std::getenv("BAM3D_TOI_REFILL")) ctx->opt_toi_refill = std::atoi(e);
-    if (const char* e = std::getenv("BAM3D_INTERSECT_REFILL")) ctx->opt_intersect_refill = std::atoi(e);
     if (const char* e = std::getenv("BAM3D_DISTANCE_REFILL")) ctx->opt_distance_refill = std::atoi(e);
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return BAM3D_ERR_CUDA; }
     if (cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess ||
@@ -185,7 +188,12 @@ int32_t bam3d_ctx_set_option(bam3d_ctx* ctx, const char* name, int32_t value) {
     if (!ctx || !name) return BAM3D_ERR_ARG;
     if (!std::strcmp(name, "binning")) { ctx->opt_binning = value != 0; return BAM3D_OK; }
     if (!std::strcmp(name, "timing")) { ctx->opt_timing = value != 0; return BAM3D_OK; }
+#ifndef B3_EXPERIMENTS
+    if ((!std::strcmp(name, "epa_tiers") || !std::strcmp(name, "intersect_split") || !std::strcmp(name, "intersect_refill") || !std::strcmp(name, "epa_pipeline")) && value != 0)
+        return b3_fail(ctx, BAM3D_ERR_ARG, "this switch selects a measured-slower experiment kernel: build the library with -DB3_EXPERIMENTS to have it", cudaSuccess);
+#endif
     if (!std::strcmp(name, "epa_tiers")) { ctx->opt_epa_tiers = value != 0; return BAM3D_OK; }
+    if (!std::strcmp(name, "epa_pipeline")) { ctx->opt_epa_pipeline = value != 0; return BAM3D_OK; }
     if (!std::strcmp(name, "epa_overlap")) { ctx->opt_epa_overlap = value != 0; return BAM3D_OK; }
     if (!std::strcmp(name, "epa_global_polytopes")) { ctx->opt_epa_global_polytopes = value != 0; return BAM3D_OK; }
     if (!std::strcmp(name, "intersect_split")) { ctx->opt_intersect_split = value != 0; return BAM3D_OK; }
@@ -488,7 +496,7 @@ int32_t bam3d_gjk_contact_dev(bam3d_ctx* ctx, const bam3d_shapes* shapes, const 
       uint32_t default_key = 0;
       for (uint32_t k = 0; k < 6; ++k) if (shapes->kind_hist[k]) default_key = k * 7 + k;
       ctx->launches += launch_contact(ctx->stream, S, (const uint2*)d_pairs, (uint32_t)n, pb, plan.run_thread, plan.run_warp, cfg, strategy,
-                                      default_key, ctx->opt_epa_tiers ? 1 : 0, ctx->opt_epa_overlap ? &side : nullptr, poly_slab, ctx->epa_overflow.ptr, ctx->epa_queue.ptr, (float4*)d_contacts,
+                                      default_key, ctx->opt_epa_tiers ? 1 : 0, ctx->opt_epa_pipeline, ctx->opt_epa_overlap ? &side : nullptr, poly_slab, ctx->epa_overflow.ptr, ctx->epa_queue.ptr, (float4*)d_contacts,
                                       d_status); }
     return check_launch(ctx, "gjk_contact_kernel");
 }
@@ -654,6 +662,151 @@ int32_t bam3d_gjk_time_of_impact(bam3d_ctx* ctx, const bam3d_shapes* s0, const b
     return BAM3D_OK;
 }
 
+// ---- compound shapes (gjk/mod.rs:362-523) ----------------------------------------------------------------------
+}  // extern "C"
+
+struct bam3d_compounds {
+    bam3d_shapes* prims = nullptr;      // every primitive of every compound; d_xform is rewritten by each call (compose)
+    bam3d_shapes* prims_end = nullptr;  // time of impact: the same primitives at the end transforms (allocated on first use)
+    float* d_local = nullptr;           // n_prims x 16: local-to-model transforms
+    uint32_t* d_owner = nullptr;        // n_prims: compound of each primitive
+    uint32_t* d_offsets = nullptr;      // n_compounds + 1
+    std::vector<uint32_t> offsets;      // host copy (segment sizes)
+    std::vector<uint8_t> kind; std::vector<float> params; std::vector<uint32_t> mesh_id;  // for prims_end
+    const bam3d_meshes* meshes = nullptr;
+    uint32_t n_compounds = 0, n_prims = 0;
+};
+
+// world transforms of a compound set's primitives for the given compound transforms (host array), then the pack kernel
+static int32_t compounds_place(bam3d_ctx* ctx, bam3d_compounds* K, bam3d_shapes* target, const float* comp_xform) {
+    int32_t rc;
+    const size_t nc = K->n_compounds ? K->n_compounds : 1;
+    if ((rc = ctx->f1.reserve(ctx, nc * 64))) return rc;
+    if (K->n_compounds) CU_TRY(cudaMemcpyAsync(ctx->f1.ptr, comp_xform, (size_t)K->n_compounds * 64, cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpyAsync(comp_xform)");
+    ctx->launches += launch_compound_compose(ctx->stream, (const float*)ctx->f1.ptr, K->d_local, K->d_owner, K->n_prims, target->d_xform);
+    if ((rc = check_launch(ctx, "compound_compose_kernel"))) return rc;
+    return run_pack(ctx, target);
+}
+
+// mode 0 contact, 1 distance, 2 time of impact
+static int32_t compounds_run(bam3d_ctx* ctx, bam3d_compounds* K, int mode, const float* comp_xform, const float* comp_xform_end, const uint32_t* pairs,
+                             uint64_t n, const bam3d_gjk_settings* settings, int32_t strategy, bam3d_contact* out_contacts, float* out_value,
+                             uint8_t* out_status) {
+    if (!ctx || !K || (K->n_compounds && !comp_xform) || (n && (!pairs || !out_status)) || (n && mode != 1 && !out_contacts) || (n && mode == 1 && !out_value) ||
+        (mode == 2 && K->n_compounds && !comp_xform_end))
+        return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_gjk_*_complex: null argument", cudaSuccess);
+    if (mode != 1 && strategy != BAM3D_FULL_RESOLUTION && strategy != BAM3D_COLLISION_ONLY) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_gjk_*_complex: unknown strategy", cudaSuccess);
+    int32_t rc;
+    if ((rc = check_n(ctx, n))) return rc;
+    if (n == 0) return BAM3D_OK;
+    CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
+    // segments: compound pair k owns |left| x |right| primitive pairs
+    std::vector<unsigned long long> seg(n + 1, 0);
+    for (uint64_t k = 0; k < n; ++k) {
+        const uint32_t l = pairs[2 * k], r = pairs[2 * k + 1];
+        if (l >= K->n_compounds || r >= K->n_compounds) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_gjk_*_complex: compound index out of range", cudaSuccess);
+        seg[k + 1] = seg[k] + (unsigned long long)(K->offsets[l + 1] - K->offsets[l]) * (K->offsets[r + 1] - K->offsets[r]);
+    }
+    const uint64_t total = seg[n];
+    if ((rc = check_n(ctx, total))) return rc;
+    if ((rc = compounds_place(ctx, K, K->prims, comp_xform))) return rc;
+    if (mode == 2) {
+        if (!K->prims_end) {  // first use: an identically-typed set whose transforms the compose kernel fills
+            std::vector<float> ident((size_t)K->n_prims * 16, 0.f);
+            for (uint32_t i = 0; i < K->n_prims; ++i) ident[16 * (size_t)i] = ident[16 * (size_t)i + 5] = ident[16 * (size_t)i + 10] = ident[16 * (size_t)i + 15] = 1.f;
+            if ((rc = bam3d_shapes_upload(ctx, K->kind.data(), K->params.data(), ident.data(), K->mesh_id.empty() ? nullptr : K->mesh_id.data(), K->n_prims, K->meshes,
+                                          &K->prims_end))) return rc;
+        }
+        if ((rc = compounds_place(ctx, K, K->prims_end, comp_xform_end))) return rc;
+    }
+    const size_t tt = total ? total : 1;
+    if ((rc = ctx->pipe0.reserve(ctx, (n + 1) * 8)) || (rc = ctx->pipe1.reserve(ctx, n * 8)) || (rc = ctx->pairs.reserve(ctx, tt * 8)) ||
+        (rc = ctx->status.reserve(ctx, tt)) || (rc = ctx->contacts.reserve(ctx, tt * 32)) || (rc = ctx->f0.reserve(ctx, tt * 4)) || (rc = ctx->f1.reserve(ctx, tt * 4)) ||
+        (rc = ctx->pipe2.reserve(ctx, n * 32)) || (rc = ctx->pipe3.reserve(ctx, n + 16))) return rc;
+    CU_TRY(cudaMemcpyAsync(ctx->pipe0.ptr, seg.data(), (n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpyAsync(segments)");
+    CU_TRY(cudaMemcpyAsync(ctx->pipe1.ptr, pairs, n * 8, cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpyAsync(pairs)");
+    ctx->launches += launch_compound_expand(ctx->stream, (const uint2*)ctx->pipe1.ptr, (const unsigned long long*)ctx->pipe0.ptr, (uint32_t)n, total, K->d_offsets,
+                                            (uint2*)ctx->pairs.ptr);
+    if ((rc = check_launch(ctx, "compound_expand_kernel"))) return rc;
+    if (total) {
+        if (mode == 0) rc = bam3d_gjk_contact_dev(ctx, K->prims, (const uint32_t*)ctx->pairs.ptr, total, settings, strategy, (bam3d_contact*)ctx->contacts.ptr, (uint8_t*)ctx->status.ptr);
+        else if (mode == 1) rc = bam3d_gjk_distance_dev(ctx, K->prims, (const uint32_t*)ctx->pairs.ptr, total, settings, (float*)ctx->f0.ptr, (float*)ctx->f1.ptr, (uint8_t*)ctx->status.ptr);
+        else rc = bam3d_gjk_time_of_impact_dev(ctx, K->prims, K->prims_end, (const uint32_t*)ctx->pairs.ptr, total, settings, (bam3d_contact*)ctx->contacts.ptr, (uint8_t*)ctx->status.ptr);
+        if (rc) return rc;
+    }
+    ctx->launches += launch_compound_reduce(ctx->stream, mode, strategy, (const unsigned long long*)ctx->pipe0.ptr, (uint32_t)n, (const float4*)ctx->contacts.ptr,
+                                            (const float*)ctx->f0.ptr, (const uint8_t*)ctx->status.ptr, (float4*)ctx->pipe2.ptr, (float*)ctx->pipe2.ptr, (uint8_t*)ctx->pipe3.ptr);
+    if ((rc = check_launch(ctx, "compound_reduce_kernel"))) return rc;
+    if (mode == 1) CU_TRY(cudaMemcpyAsync(out_value, ctx->pipe2.ptr, n * 4, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(value)");
+    else CU_TRY(cudaMemcpyAsync(out_contacts, ctx->pipe2.ptr, n * 32, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(contacts)");
+    CU_TRY(cudaMemcpyAsync(out_status, ctx->pipe3.ptr, n, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(status)");
+    CU_TRY(cudaStreamSynchronize(ctx->stream), "bam3d_gjk_*_complex");
+    return BAM3D_OK;
+}
+
+extern "C" {
+
+void bam3d_compounds_free(bam3d_ctx* ctx, bam3d_compounds* K) {
+    if (!K) return;
+    bam3d_shapes_free(ctx, K->prims);
+    bam3d_shapes_free(ctx, K->prims_end);
+    if (K->d_local) cudaFree(K->d_local);
+    if (K->d_owner) cudaFree(K->d_owner);
+    if (K->d_offsets) cudaFree(K->d_offsets);
+    delete K;
+}
+
+int32_t bam3d_compounds_upload(bam3d_ctx* ctx, const uint8_t* kind, const float* params, const float* local_xform, const uint32_t* mesh_id,
+                               uint32_t n_prims, const uint32_t* comp_offsets, uint32_t n_compounds, const bam3d_meshes* meshes, bam3d_compounds** out) {
+    if (!ctx || !out || !comp_offsets || (n_prims && (!kind || !params || !local_xform))) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_compounds_upload: null argument", cudaSuccess);
+    *out = nullptr;
+    if (comp_offsets[0] != 0 || comp_offsets[n_compounds] != n_prims) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_compounds_upload: comp_offsets must run from 0 to n_prims", cudaSuccess);
+    for (uint32_t c = 0; c < n_compounds; ++c)
+        if (comp_offsets[c + 1] < comp_offsets[c]) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_compounds_upload: comp_offsets must be non-decreasing", cudaSuccess);
+    CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
+    bam3d_compounds* K = new (std::nothrow) bam3d_compounds();
+    if (!K) return BAM3D_ERR_OOM;
+    K->n_compounds = n_compounds; K->n_prims = n_prims; K->meshes = meshes;
+    K->offsets.assign(comp_offsets, comp_offsets + n_compounds + 1);
+    K->kind.assign(kind, kind + n_prims); K->params.assign(params, params + 4 * (size_t)n_prims);
+    if (mesh_id) K->mesh_id.assign(mesh_id, mesh_id + n_prims);
+    std::vector<uint32_t> owner(n_prims ? n_prims : 1, 0);
+    for (uint32_t c = 0; c < n_compounds; ++c) for (uint32_t i = comp_offsets[c]; i < comp_offsets[c + 1]; ++i) owner[i] = c;
+    // the local transforms double as the initial world transforms: validates kinds, mesh ids and affinity once
+    int32_t rc = bam3d_shapes_upload(ctx, kind, params, local_xform, mesh_id, n_prims, meshes, &K->prims);
+    if (rc) { bam3d_compounds_free(ctx, K); return rc; }
+    const size_t np = n_prims ? n_prims : 1;
+    cudaError_t e;
+    if ((e = cudaMalloc(&K->d_local, np * 64)) != cudaSuccess || (e = cudaMalloc(&K->d_owner, np * 4)) != cudaSuccess ||
+        (e = cudaMalloc(&K->d_offsets, ((size_t)n_compounds + 1) * 4)) != cudaSuccess) {
+        bam3d_compounds_free(ctx, K);
+        return b3_fail(ctx, BAM3D_ERR_OOM, "cudaMalloc(compounds)", e);
+    }
+    if (n_prims) {
+        cudaMemcpyAsync(K->d_local, local_xform, (size_t)n_prims * 64, cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(K->d_owner, owner.data(), (size_t)n_prims * 4, cudaMemcpyHostToDevice, ctx->stream);
+    }
+    cudaMemcpyAsync(K->d_offsets, comp_offsets, ((size_t)n_compounds + 1) * 4, cudaMemcpyHostToDevice, ctx->stream);
+    e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { bam3d_compounds_free(ctx, K); return b3_fail(ctx, BAM3D_ERR_CUDA, "bam3d_compounds_upload", e); }
+    *out = K;
+    return BAM3D_OK;
+}
+
+int32_t bam3d_gjk_contact_complex(bam3d_ctx* ctx, bam3d_compounds* K, const float* comp_xform, const uint32_t* pairs, uint64_t n,
+                                  const bam3d_gjk_settings* settings, int32_t strategy, bam3d_contact* out_contacts, uint8_t* out_status) {
+    return compounds_run(ctx, K, 0, comp_xform, nullptr, pairs, n, settings, strategy, out_contacts, nullptr, out_status);
+}
+int32_t bam3d_gjk_distance_complex(bam3d_ctx* ctx, bam3d_compounds* K, const float* comp_xform, const uint32_t* pairs, uint64_t n,
+                                   const bam3d_gjk_settings* settings, float* out_value, uint8_t* out_status) {
+    return compounds_run(ctx, K, 1, comp_xform, nullptr, pairs, n, settings, 0, nullptr, out_value, out_status);
+}
+int32_t bam3d_gjk_time_of_impact_complex(bam3d_ctx* ctx, bam3d_compounds* K, const float* comp_xform_start, const float* comp_xform_end,
+                                         const uint32_t* pairs, uint64_t n, const bam3d_gjk_settings* settings, int32_t strategy,
+                                         bam3d_contact* out_contacts, uint8_t* out_status) {
+    return compounds_run(ctx, K, 2, comp_xform_start, comp_xform_end, pairs, n, settings, strategy, out_contacts, nullptr, out_status);
+}
+
 }  // extern "C"
 
 // ============================================================================================================
@@ -665,6 +818,7 @@ struct bam3d_bvh {
     float4* nodes = nullptr;       // 2 x (2n - 1): node records (broad.h: BvhDev)
     int2* children = nullptr;      // n - 1 (build / refit only)
     uint32_t* leaf_value = nullptr;
+    uint32_t* rope = nullptr;      // 2n - 1 (written into the node records; kept for the refit)
 };
 
 static BvhDev bvh_view(const bam3d_bvh* t) {
@@ -747,7 +901,7 @@ static int32_t sap_run(bam3d_ctx* ctx, const float* d_aabbs, uint64_t n64, int32
     char* slab = nullptr;
     const size_t nn = n;
     if (strategy != 1) {
-        const size_t bytes = nn * 24 + 2 * nn * 16 * 2 + nn * 8 + nn * 4 + nn * 4 * 4 + 2 * nn * 4 + nn * 4 + (nn + 1) * 4 + (nn + 1) * 8 + 16 * 256;
+        const size_t bytes = nn * 24 + 2 * nn * 16 * 2 + nn * 8 + nn * 4 + 2 * nn * 4 + nn * 4 * 4 + 2 * nn * 4 + nn * 4 + (nn + 1) * 4 + (nn + 1) * 8 + 17 * 256;
         if ((rc = ctx->bp6.reserve(ctx, bytes))) return rc;
         slab = (char*)ctx->bp6.ptr;
         d_sorted6 = (float*)slab;
@@ -784,6 +938,7 @@ static int32_t sap_run(bam3d_ctx* ctx, const float* d_aabbs, uint64_t n64, int32
         float4* nnodes = (float4*)carve(2 * 2 * nn * 16);
         int2* children = (int2*)carve(nn * 8);
         uint32_t* leaf_value = (uint32_t*)carve(nn * 4);
+        uint32_t* rope = (uint32_t*)carve(2 * nn * 4);
         BvhBuildScratch W;
         W.morton_in = (uint32_t*)carve(nn * 4); W.morton_out = (uint32_t*)carve(nn * 4);
         W.idx_in = (uint32_t*)carve(nn * 4); W.idx_out = (uint32_t*)carve(nn * 4);
@@ -796,7 +951,7 @@ static int32_t sap_run(bam3d_ctx* ctx, const float* d_aabbs, uint64_t n64, int32
         BvhDev T; T.n = n; T.nodes = nnodes; T.leaf_value = leaf_value;
         const int shift = sap_bits_for(n);
         { KernelTimer kt(ctx);
-          ctx->launches += launch_bvh_build(ctx->stream, d_sorted6, n, W, nnodes, children, leaf_value);
+          ctx->launches += launch_bvh_build(ctx->stream, d_sorted6, n, W, nnodes, children, leaf_value, rope);
           ctx->launches += launch_bvh_overlap_append(ctx->stream, T, d_sorted6, j_begin, j_end, shift, S.pair_keys, capacity, d_count); }
         CU_TRY(cudaMemcpyAsync(&h_count, d_count, 8, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(count)");
         CU_TRY(cudaStreamSynchronize(ctx->stream), "sap bvh pair search");
@@ -973,6 +1128,59 @@ int32_t bam3d_shapes_world_spheres(bam3d_ctx* ctx, const bam3d_shapes* shapes, f
     return BAM3D_OK;
 }
 
+// ---- broad -> narrow pipeline (BASELINE configs[3]: "SweepAndPrune3 ... then narrow phase") ---------------------------------
+// world AABBs of the shape set (ComputeBound<Aabb3> + Aabb::transform) -> SweepAndPrune3::find_collider_pairs over them ->
+// sorted-position pairs mapped back to shape indices through perm -> GJK::intersection on every candidate pair. Everything
+// stays on the device; the one host synchronisation is sweep-and-prune's own (the pair count sizes its final sort and the
+// narrow-phase launch).
+int32_t bam3d_pipeline_contacts_dev(bam3d_ctx* ctx, const bam3d_shapes* shapes, int32_t* inout_sweep_axis, const bam3d_gjk_settings* settings,
+                                    int32_t strategy, uint32_t shard, uint32_t n_shards, uint32_t* d_pairs, uint32_t* d_sorted_pairs,
+                                    uint32_t* d_perm, bam3d_contact* d_contacts, uint8_t* d_status, uint64_t capacity, uint64_t* out_count) {
+    if (!ctx || !shapes || !inout_sweep_axis || !out_count || (capacity && (!d_pairs || !d_contacts || !d_status)))
+        return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_pipeline_contacts: null argument", cudaSuccess);
+    int32_t rc;
+    if ((rc = check_n(ctx, capacity))) return rc;
+    CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
+    const uint64_t n = shapes->n;
+    *out_count = 0;
+    if ((rc = ctx->pipe0.reserve(ctx, (size_t)(n ? n : 1) * 24))) return rc;
+    if (!d_perm) { if ((rc = ctx->pipe1.reserve(ctx, (size_t)(n ? n : 1) * 4))) return rc; d_perm = (uint32_t*)ctx->pipe1.ptr; }
+    if (!d_sorted_pairs) { if ((rc = ctx->pipe2.reserve(ctx, (size_t)(capacity ? capacity : 1) * 8))) return rc; d_sorted_pairs = (uint32_t*)ctx->pipe2.ptr; }
+    if ((rc = bam3d_shapes_world_aabbs_dev(ctx, shapes, (float*)ctx->pipe0.ptr))) return rc;
+    if ((rc = sap_run(ctx, (const float*)ctx->pipe0.ptr, n, inout_sweep_axis, d_perm, d_sorted_pairs, capacity, out_count, shard, n_shards))) return rc;
+    const uint64_t m = *out_count;
+    if (m == 0) return BAM3D_OK;
+    ctx->launches += launch_remap_pairs(ctx->stream, (const uint2*)d_sorted_pairs, d_perm, m, (uint2*)d_pairs);
+    if ((rc = check_launch(ctx, "remap_pairs_kernel"))) return rc;
+    return bam3d_gjk_contact_dev(ctx, shapes, d_pairs, m, settings, strategy, d_contacts, d_status);
+}
+
+int32_t bam3d_pipeline_contacts(bam3d_ctx* ctx, const bam3d_shapes* shapes, int32_t* inout_sweep_axis, const bam3d_gjk_settings* settings,
+                                int32_t strategy, uint32_t* out_pairs, uint32_t* out_sorted_pairs, uint32_t* out_perm, bam3d_contact* out_contacts,
+                                uint8_t* out_status, uint64_t capacity, uint64_t* out_count) {
+    if (!ctx || !shapes || !inout_sweep_axis || !out_count || (capacity && (!out_pairs || !out_contacts || !out_status)))
+        return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_pipeline_contacts: null argument", cudaSuccess);
+    int32_t rc;
+    if ((rc = check_n(ctx, capacity))) return rc;
+    CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
+    const size_t cap = capacity ? capacity : 1, nn = shapes->n ? shapes->n : 1;
+    if ((rc = ctx->pipe3.reserve(ctx, cap * 8 + 256)) || (rc = ctx->contacts.reserve(ctx, cap * 32)) || (rc = ctx->status.reserve(ctx, cap)) ||
+        (rc = ctx->pipe1.reserve(ctx, nn * 4)) || (rc = ctx->pipe2.reserve(ctx, cap * 8))) return rc;
+    rc = bam3d_pipeline_contacts_dev(ctx, shapes, inout_sweep_axis, settings, strategy, 0, 1, (uint32_t*)ctx->pipe3.ptr, (uint32_t*)ctx->pipe2.ptr,
+                                     (uint32_t*)ctx->pipe1.ptr, (bam3d_contact*)ctx->contacts.ptr, (uint8_t*)ctx->status.ptr, capacity, out_count);
+    if (rc) return rc;
+    const uint64_t m = *out_count;
+    if (out_perm && shapes->n) CU_TRY(cudaMemcpyAsync(out_perm, ctx->pipe1.ptr, (size_t)shapes->n * 4, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(perm)");
+    if (m) {
+        CU_TRY(cudaMemcpyAsync(out_pairs, ctx->pipe3.ptr, m * 8, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(pairs)");
+        if (out_sorted_pairs) CU_TRY(cudaMemcpyAsync(out_sorted_pairs, ctx->pipe2.ptr, m * 8, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(sorted pairs)");
+        CU_TRY(cudaMemcpyAsync(out_contacts, ctx->contacts.ptr, m * 32, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(contacts)");
+        CU_TRY(cudaMemcpyAsync(out_status, ctx->status.ptr, m, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(status)");
+    }
+    CU_TRY(cudaStreamSynchronize(ctx->stream), "bam3d_pipeline_contacts");
+    return BAM3D_OK;
+}
+
 // ---- BVH (DBVT queries) ----------------------------------------------------------------------------------------
 void bam3d_bvh_free(bam3d_ctx* ctx, bam3d_bvh* t) {
     (void)ctx;
@@ -981,6 +1189,7 @@ void bam3d_bvh_free(bam3d_ctx* ctx, bam3d_bvh* t) {
     if (t->nodes) cudaFree(t->nodes);
     if (t->children) cudaFree(t->children);
     if (t->leaf_value) cudaFree(t->leaf_value);
+    if (t->rope) cudaFree(t->rope);
     delete t;
 }
 
@@ -997,7 +1206,7 @@ static int32_t bvh_build_impl(bam3d_ctx* ctx, const float* aabbs, bool on_device
     cudaError_t e;
     if ((e = cudaMalloc(&t->d_aabbs, nn * 24)) != cudaSuccess || (e = cudaMalloc(&t->nodes, (2 * 2 * nn) * 16)) != cudaSuccess ||
         (e = cudaMalloc(&t->children, nn * 8)) != cudaSuccess ||
-        (e = cudaMalloc(&t->leaf_value, nn * 4)) != cudaSuccess) {
+        (e = cudaMalloc(&t->leaf_value, nn * 4)) != cudaSuccess || (e = cudaMalloc(&t->rope, 2 * nn * 4)) != cudaSuccess) {
         bam3d_bvh_free(ctx, t);
         return b3_fail(ctx, BAM3D_ERR_OOM, "cudaMalloc(bvh)", e);
     }
@@ -1011,7 +1220,7 @@ static int32_t bvh_build_impl(bam3d_ctx* ctx, const float* aabbs, bool on_device
     W.cub_tmp = ctx->cub_tmp.ptr; W.cub_tmp_bytes = tmp_bytes;
     W.scene = (float*)((char*)ctx->small.ptr + 896);
     { KernelTimer kt(ctx);
-      ctx->launches += launch_bvh_build(ctx->stream, t->d_aabbs, n, W, t->nodes, t->children, t->leaf_value); }
+      ctx->launches += launch_bvh_build(ctx->stream, t->d_aabbs, n, W, t->nodes, t->children, t->leaf_value, t->rope); }
     e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) { bam3d_bvh_free(ctx, t); return b3_fail(ctx, BAM3D_ERR_CUDA, "bam3d_bvh_build", e); }
     *out = t;
@@ -1030,7 +1239,7 @@ static int32_t bvh_refit_impl(bam3d_ctx* ctx, bam3d_bvh* t, const float* aabbs, 
     uint32_t* flags = parent + 2 * nn;
     CU_TRY(cudaMemcpyAsync(t->d_aabbs, aabbs, nn * 24, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpyAsync(aabbs)");
     { KernelTimer kt(ctx);
-      ctx->launches += launch_bvh_refit(ctx->stream, t->d_aabbs, n, t->children, t->leaf_value, parent, flags, t->nodes); }
+      ctx->launches += launch_bvh_refit(ctx->stream, t->d_aabbs, n, t->children, t->leaf_value, parent, t->rope, flags, t->nodes); }
     if ((rc = check_launch(ctx, "bvh_refit_kernel"))) return rc;
     if (!on_device) CU_TRY(cudaStreamSynchronize(ctx->stream), "bam3d_bvh_refit");
     return BAM3D_OK;
@@ -1138,6 +1347,49 @@ int32_t bam3d_bvh_query_ray_closest(bam3d_ctx* ctx, const bam3d_bvh* t, const fl
     return BAM3D_OK;
 }
 
+// ---- device-resident queries: one pass, hits appended as (query, value, payload) in arbitrary order, no synchronisation ----
+static int32_t bvh_query_dev_impl(bam3d_ctx* ctx, const bam3d_bvh* t, int kind, const float* d_queries, uint64_t nq64, uint32_t* d_out_query,
+                                  uint32_t* d_out_values, void* d_out_payload, uint64_t capacity, uint64_t* d_count, const char* what) {
+    if (!ctx || !t || !d_count || (nq64 && !d_queries) || (capacity && (!d_out_query || !d_out_values))) return b3_fail(ctx, BAM3D_ERR_ARG, what, cudaSuccess);
+    int32_t rc;
+    if ((rc = check_n(ctx, nq64))) return rc;
+    CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
+    const uint32_t nq = (uint32_t)nq64;
+    // few large queries -> every (query, value) test; many small ones -> tree traversal (as the host-buffer forms decide)
+    bool brute = ctx->opt_bvh_strategy == 2 || (ctx->opt_bvh_strategy == 0 && nq < 2048 && (uint64_t)nq * t->n <= (1ull << 35));
+    if (t->n == 0) brute = false;
+    { KernelTimer kt(ctx);
+      if (brute) ctx->launches += launch_bvh_brute_append(ctx->stream, t->d_aabbs, t->n, kind, d_queries, nq, d_out_query, d_out_values, d_out_payload, capacity,
+                                                          (unsigned long long*)d_count);
+      else ctx->launches += launch_bvh_query_append(ctx->stream, bvh_view(t), kind, d_queries, nq, d_out_query, d_out_values, d_out_payload, capacity,
+                                                    (unsigned long long*)d_count); }
+    return check_launch(ctx, "bvh query (append)");
+}
+int32_t bam3d_bvh_query_aabb_dev(bam3d_ctx* ctx, const bam3d_bvh* t, const float* d_queries, uint64_t nq, uint32_t* d_out_query, uint32_t* d_out_values,
+                                 uint64_t capacity, uint64_t* d_count) {
+    return bvh_query_dev_impl(ctx, t, BQ_AABB, d_queries, nq, d_out_query, d_out_values, nullptr, capacity, d_count, "bam3d_bvh_query_aabb_dev: null argument");
+}
+int32_t bam3d_bvh_query_ray_dev(bam3d_ctx* ctx, const bam3d_bvh* t, const float* d_rays, uint64_t nq, uint32_t* d_out_query, uint32_t* d_out_values,
+                                float* d_out_points, uint64_t capacity, uint64_t* d_count) {
+    if (capacity && !d_out_points) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_bvh_query_ray_dev: null argument", cudaSuccess);
+    return bvh_query_dev_impl(ctx, t, BQ_RAY, d_rays, nq, d_out_query, d_out_values, d_out_points, capacity, d_count, "bam3d_bvh_query_ray_dev: null argument");
+}
+int32_t bam3d_bvh_query_frustum_dev(bam3d_ctx* ctx, const bam3d_bvh* t, const float* d_planes, uint64_t nq, uint32_t* d_out_query, uint32_t* d_out_values,
+                                    uint8_t* d_out_relation, uint64_t capacity, uint64_t* d_count) {
+    if (capacity && !d_out_relation) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_bvh_query_frustum_dev: null argument", cudaSuccess);
+    return bvh_query_dev_impl(ctx, t, BQ_FRUSTUM, d_planes, nq, d_out_query, d_out_values, d_out_relation, capacity, d_count, "bam3d_bvh_query_frustum_dev: null argument");
+}
+int32_t bam3d_bvh_query_ray_closest_dev(bam3d_ctx* ctx, const bam3d_bvh* t, const float* d_rays, uint64_t nq64, uint32_t* d_out_value, float* d_out_point_t) {
+    if (!ctx || !t || (nq64 && (!d_rays || !d_out_value || !d_out_point_t))) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_bvh_query_ray_closest_dev: null argument", cudaSuccess);
+    int32_t rc;
+    if ((rc = check_n(ctx, nq64))) return rc;
+    if (nq64 == 0) return BAM3D_OK;
+    CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
+    { KernelTimer kt(ctx);
+      ctx->launches += launch_bvh_ray_closest(ctx->stream, bvh_view(t), d_rays, (uint32_t)nq64, d_out_value, d_out_point_t); }
+    return check_launch(ctx, "bvh_ray_closest_kernel");
+}
+
 int32_t bam3d_bvh_find_collider_pairs(bam3d_ctx* ctx, const bam3d_bvh* t, const uint8_t* dirty, uint32_t* out_pairs, uint64_t capacity, uint64_t* out_count) {
     if (!ctx || !t || !out_count || (t->n && !dirty) || (capacity && !out_pairs)) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_bvh_find_collider_pairs: null argument", cudaSuccess);
     CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
@@ -1226,7 +1478,7 @@ static bam3d_ctx* frames_lane(bam3d_ctx* ctx, bam3d_frames* F, uint64_t frame) {
     c->opt_binning = ctx->opt_binning; c->opt_epa_tiers = ctx->opt_epa_tiers; c->opt_intersect_split = ctx->opt_intersect_split;
     c->opt_intersect_refill = ctx->opt_intersect_refill; c->opt_toi_refill = ctx->opt_toi_refill;
     c->opt_epa_global_polytopes = ctx->opt_epa_global_polytopes; c->opt_epa_overlap = ctx->opt_epa_overlap;
-    c->opt_distance_refill = ctx->opt_distance_refill;
+    c->opt_distance_refill = ctx->opt_distance_refill; c->opt_epa_pipeline = ctx->opt_epa_pipeline;
     c->opt_timing = false;
     return c;
 }

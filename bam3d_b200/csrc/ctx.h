@@ -29,6 +29,7 @@ struct bam3d_ctx {
     int opt_toi_refill = 8;  // time of impact, thread path: 0 = one pair per thread (1.16 ms per 2^20 mixed pairs); k >= 1 = persistent kernel whose lanes refill once k of a warp are idle (gjk_toi_refill_kernel: 0.56 ms at k = 8)
     int opt_distance_refill = 8;  // distance, thread path: the same lane-refill scheme (gjk_distance_refill_kernel); 0 = one pair per thread
     bool opt_epa_global_polytopes = true;   // thread-per-pair EPA: polytopes in a global slab (contiguous per thread) instead of local memory
+    bool opt_epa_pipeline = false;  // thread-per-pair EPA: cp.async face ring + batched walk / moves / new faces (epa_pipe.cuh); 0 = epa.cuh's iteration
     bool opt_epa_overlap = true;  // contact path: run the EPA overflow tier on the side stream next to the EPA kernel
     int opt_sap_strategy = 0;  // 0 auto, 1 tiled sweep, 2 BVH overlap query
     int opt_bvh_strategy = 0;  // variable-length queries: 0 auto, 1 tree traversal, 2 all (query, value) tests
@@ -40,9 +41,9 @@ struct bam3d_ctx {
     // scratch for the host-buffer entry points and the binning pass
     DevBuf pairs, status, contacts, f0, f1, keys, order, small, epa_overflow, epa_queue, epa_slab;
     // broad-phase scratch
-    DevBuf bp0, bp1, bp2, bp3, bp4, bp5, bp6, bp7, cub_tmp, sph0, sph1, sph2;
+    DevBuf bp0, bp1, bp2, bp3, bp4, bp5, bp6, bp7, cub_tmp, sph0, sph1, sph2, pipe0, pipe1, pipe2, pipe3;
     void release_scratch() {
-        DevBuf* all[] = {&pairs, &status, &contacts, &f0, &f1, &keys, &order, &small, &epa_overflow, &epa_queue, &epa_slab, &bp0, &bp1, &bp2, &bp3, &bp4, &bp5, &bp6, &bp7, &cub_tmp, &sph0, &sph1, &sph2};
+        DevBuf* all[] = {&pairs, &status, &contacts, &f0, &f1, &keys, &order, &small, &epa_overflow, &epa_queue, &epa_slab, &bp0, &bp1, &bp2, &bp3, &bp4, &bp5, &bp6, &bp7, &cub_tmp, &sph0, &sph1, &sph2, &pipe0, &pipe1, &pipe2, &pipe3};
         for (DevBuf* b : all) b->release();
     }
 };

@@ -82,7 +82,6 @@ struct TierShared {
     unsigned char* pool;             // this warp's shared-memory pool
 };
 
-B3_DEV uint32_t ld_volatile_u32(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
 
 // Runs one stage with LPS lanes per slot until the source has nothing more to hand out and every slot of this warp
 // is finished. Returns true if the warp processed at least one pair. All 32 lanes call this convergently.

@@ -15,6 +15,9 @@
 #include "narrow.h"
 #include "gjk.cuh"
 #include "epa_big.cuh"
+#ifdef B3_EXPERIMENTS
+#include "epa_pipe.cuh"
+#endif
 #include "epa_warp.cuh"
 #include "raycast.cuh"
 
@@ -183,6 +186,8 @@ __global__ void __launch_bounds__(TPB) bin_scatter_kernel(const uint8_t* __restr
     }
 }
 
+B3_DEV uint32_t ld_volatile_u32(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
+
 __device__ __forceinline__ void overflow_append(unsigned char* ovf_scratch, uint32_t p) {
     __threadfence();  // the caller's ST_CAPACITY status / zero contact must land before the consumer can overwrite them
     const uint32_t slot = atomicAdd(reinterpret_cast<uint32_t*>(ovf_scratch) + OVF_COUNT, 1u);
@@ -286,6 +291,7 @@ __global__ void __launch_bounds__(TPB) gjk_intersect_kernel(ShapeSetDev S, const
     }
 }
 
+#ifdef B3_EXPERIMENTS  // measured slower than the single kernel: kept as the record of the experiment
 // Thread-per-pair intersect in two launches. Most misses are decided by the very first support point
 // (gjk/mod.rs:92: `a.v . d <= 0`), so a single kernel spends most of its issue slots with a third of the lanes alive
 // (ncu: 11 of 32). Launch 1 streams every pair through that first test with all lanes busy — misses get their status,
@@ -344,6 +350,8 @@ __global__ void __launch_bounds__(TPB) gjk_intersect_survivors_kernel(ShapeSetDe
         status[p] = gjk_intersect<false, false>(L, R, cfg.max_iterations, s);
     }
 }
+
+#endif  // B3_EXPERIMENTS
 
 // ------------------------------------------------------------------------------------------------------------
 // GJK::intersection = intersect + EPA3::process (FullResolution) or Contact::new(CollisionOnly)
@@ -511,7 +519,16 @@ static_assert(EPA_SLAB_VV >= (size_t)EPA_VCAP * 12 && EPA_SLAB_BYTES % 128 == 0,
 #ifndef B3_EPA_BLOCKS
 #define B3_EPA_BLOCKS 4  // resident blocks per SM the EPA kernel is compiled for (register cap) and its slab is sized for
 #endif
-template <bool GLOBAL_POLY>
+#ifndef B3_EXPERIMENTS
+struct PipeStore { float4 *vv4, *va4, *ring; uint32_t* proc; uint16_t* mov; float* stage; int stride; };  // (epa_pipe.cuh is an experiment)
+constexpr int EPA_RING = 0, EPA_PCAP = 0;
+constexpr size_t EPA_PIPE_SLAB_BYTES = 0;
+#define B3_PIPE_A 0
+#endif
+// dynamic shared memory of the PIPE form: face ring | horizon edges | moves | removed-face slots (epa_pipe.cuh)
+constexpr size_t EPA_PIPE_RING_BYTES = B3_PIPE_A ? (size_t)EPA_RING * 8 * TPB * 16 : 0;
+constexpr size_t EPA_PIPE_SMEM = EPA_PIPE_RING_BYTES + (size_t)EPA_ECAP_SMEM * TPB * 2 + (size_t)EPA_PCAP * TPB * 2 + (size_t)EPA_PCAP * TPB * 4 + (size_t)24 * TPB * 4;
+template <bool GLOBAL_POLY, bool PIPE>
 __global__ void __launch_bounds__(TPB, B3_EPA_BLOCKS) epa_refill_kernel(ShapeSetDev S, const uint2* __restrict__ pairs, SettingsDev cfg,
                                                          const uint32_t* __restrict__ bin_start, BinOrder bo,
                                                          unsigned char* __restrict__ queue, unsigned char* __restrict__ ovf_scratch,
@@ -540,12 +557,15 @@ __global__ void __launch_bounds__(TPB, B3_EPA_BLOCKS) epa_refill_kernel(ShapeSet
     float4 lfn[GLOBAL_POLY ? 1 : EPA_FCAP];
     uint32_t lfi[GLOBAL_POLY ? 1 : EPA_FCAP];
     PolytopeStore P;
+    PipeStore Q;
     if (GLOBAL_POLY) {
-        unsigned char* mine = slab + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * EPA_SLAB_BYTES;
+        unsigned char* mine = slab + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * (PIPE ? EPA_PIPE_SLAB_BYTES : EPA_SLAB_BYTES);
         P.fn = reinterpret_cast<float4*>(mine);
         P.fi = reinterpret_cast<uint32_t*>(mine + EPA_SLAB_FN);
         P.vv = reinterpret_cast<float*>(mine + EPA_SLAB_FN + EPA_SLAB_FI);
         P.va = reinterpret_cast<float*>(mine + EPA_SLAB_FN + EPA_SLAB_FI + EPA_SLAB_VV);
+        Q.vv4 = reinterpret_cast<float4*>(mine + EPA_SLAB_FN + EPA_SLAB_FI);
+        Q.va4 = Q.vv4 + EPA_VCAP;
     } else {
         P.vv = lvv; P.va = lva; P.fn = lfn; P.fi = lfi;
     }
@@ -559,8 +579,22 @@ __global__ void __launch_bounds__(TPB, B3_EPA_BLOCKS) epa_refill_kernel(ShapeSet
     // addresses. The horizon of a well-formed polytope is short (<= 12 edges for 99.7 % of mixed pairs, <= 16 for
     // all but ~1e-4); a pair that needs more than EPA_ECAP_SMEM goes to the overflow tier like one that outgrows
     // the face list.
-    __shared__ uint16_t s_ed[EPA_ECAP_SMEM * TPB];
-    P.ed = s_ed + threadIdx.x; P.ecap = EPA_ECAP_SMEM; P.estride = TPB;
+    extern __shared__ __align__(16) unsigned char epa_dyn[];
+    __shared__ uint16_t s_ed[PIPE ? 1 : EPA_ECAP_SMEM * TPB];
+    if (PIPE) {
+        Q.ring = reinterpret_cast<float4*>(epa_dyn) + threadIdx.x;
+        uint32_t* w32 = reinterpret_cast<uint32_t*>(epa_dyn + EPA_PIPE_RING_BYTES);
+        Q.proc = w32 + threadIdx.x;
+        Q.stage = reinterpret_cast<float*>(w32 + EPA_PCAP * TPB) + threadIdx.x;
+        uint16_t* w16 = reinterpret_cast<uint16_t*>(w32 + EPA_PCAP * TPB + 24 * TPB);
+        P.ed = w16 + threadIdx.x;
+        Q.mov = w16 + EPA_ECAP_SMEM * TPB + threadIdx.x;
+        Q.stride = TPB;
+    } else {
+        P.ed = s_ed + threadIdx.x;
+        Q.ring = nullptr; Q.proc = nullptr; Q.mov = nullptr; Q.stage = nullptr; Q.stride = TPB;
+    }
+    P.ecap = EPA_ECAP_SMEM; P.estride = TPB;
 #endif
     const uint32_t count = s_pref[EPAQ_BINS];
 #ifdef B3_TIER_TRACE
@@ -606,7 +640,11 @@ __global__ void __launch_bounds__(TPB, B3_EPA_BLOCKS) epa_refill_kernel(ShapeSet
                     uint2 pr = __ldg(pairs + p);
                     load_pair_shape(L, S, pr.x);
                     load_pair_shape(R, S, pr.y);
-                    epa_init<false>(s, P, nv, nf, it, vmax, best);
+#ifdef B3_EXPERIMENTS
+                    if constexpr (PIPE) epa_init_pipe(s, P, Q, nv, nf, it, vmax, best);
+                    else
+#endif
+                        epa_init<false>(s, P, nv, nf, it, vmax, best);
                     active = true;
                 } else {
                     seg = EPAQ_BINS;
@@ -622,7 +660,12 @@ __global__ void __launch_bounds__(TPB, B3_EPA_BLOCKS) epa_refill_kernel(ShapeSet
         if (!__any_sync(0xFFFFFFFFu, active)) break;
         if (active) {
             ContactOut c;
-            uint8_t st = epa_iterate<false>(L, R, cfg.epa_tolerance, cfg.max_iterations, P, nv, nf, it, vmax, best, c);
+            uint8_t st;
+#ifdef B3_EXPERIMENTS
+            if constexpr (PIPE) st = epa_iterate_pipe(L, R, cfg.epa_tolerance, cfg.max_iterations, P, Q, nv, nf, it, vmax, best, c);
+            else
+#endif
+                st = epa_iterate<false>(L, R, cfg.epa_tolerance, cfg.max_iterations, P, nv, nf, it, vmax, best, c);
             if (st != EPA_CONTINUE) {
                 if (st != ST_OK) { c.normal = v3(0.f, 0.f, 0.f); c.depth = 0.f; c.point = v3(0.f, 0.f, 0.f); }
                 contacts[2 * (size_t)p] = make_float4(c.normal.x, c.normal.y, c.normal.z, c.depth);
@@ -641,6 +684,7 @@ __global__ void __launch_bounds__(TPB, B3_EPA_BLOCKS) epa_refill_kernel(ShapeSet
     overflow_producer_exit(ovf_scratch);
 }
 
+#ifdef B3_EXPERIMENTS
 }  // namespace b3
 #include "epa_tiers.cuh"  // needs load_pair_shape
 namespace b3 {
@@ -738,6 +782,10 @@ __global__ void __launch_bounds__(32, TIER_WARPS_PER_SM) epa_tiers_kernel(ShapeS
     overflow_producer_exit(ovf_scratch);
 }
 
+#else
+constexpr size_t TIER_VA_BYTES = 0;
+#endif  // B3_EXPERIMENTS
+
 // Overflow tier of the contact kernels (epa_big.cuh): the fast-tier kernels append every pair they leave at
 // ST_CAPACITY to a device list; one warp per listed pair redoes GJK + EPA against a per-warp global-memory slab.
 // Rare (~6e-5 of mixed pairs), but those pairs are the long tail of the reference's cost.
@@ -802,6 +850,7 @@ __global__ void __launch_bounds__(32) gjk_contact_overflow_kernel(ShapeSetDev S,
     }
 }
 
+#ifdef B3_EXPERIMENTS
 // Thread-per-pair intersect with lane refill ("intersect_refill" = k): persistent grid, every lane owns one pair at a time, all
 // lanes advance by one iteration of the loop of gjk/mod.rs:96-111 per pass; lanes whose pair is decided wait until k lanes of the
 // warp are idle (or none is busy) and then fetch together, so the fetch path (two record loads + the first support test, which
@@ -876,6 +925,8 @@ __global__ void __launch_bounds__(TPB) gjk_intersect_refill_kernel(ShapeSetDev S
         }
     }
 }
+
+#endif  // B3_EXPERIMENTS
 
 // ------------------------------------------------------------------------------------------------------------
 // GJK::distance
@@ -1160,6 +1211,135 @@ __global__ void __launch_bounds__(TPB) gjk_toi_refill_kernel(ShapeSetDev S0, Sha
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// compound shapes: GJK::intersection_complex / distance_complex / intersection_complex_time_of_impact (gjk/mod.rs:362-523)
+// ------------------------------------------------------------------------------------------------------------
+// world transform of every primitive = compound transform * local transform, glam 0.8 Mat4::mul_mat4 (each result column is
+// self.mul_vec4(other column): x_axis * v.x, then y_axis * v.y + r, z_axis * v.z + r, w_axis * v.w + r — four components each)
+__global__ void __launch_bounds__(TPB) compound_compose_kernel(const float4* __restrict__ comp_xform, const float4* __restrict__ local,
+                                                               const uint32_t* __restrict__ owner, uint32_t n_prims, float4* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_prims) return;
+    const float4* a = comp_xform + 4 * (size_t)owner[i];
+    const float4 ax = a[0], ay = a[1], az = a[2], aw = a[3];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float4 v = local[4 * (size_t)i + j];
+        float4 r = make_float4(ax.x * v.x, ax.y * v.x, ax.z * v.x, ax.w * v.x);
+        r = make_float4(ay.x * v.y + r.x, ay.y * v.y + r.y, ay.z * v.y + r.z, ay.w * v.y + r.w);
+        r = make_float4(az.x * v.z + r.x, az.y * v.z + r.y, az.z * v.z + r.z, az.w * v.z + r.w);
+        r = make_float4(aw.x * v.w + r.x, aw.y * v.w + r.y, aw.z * v.w + r.z, aw.w * v.w + r.w);
+        out[4 * (size_t)i + j] = r;
+    }
+}
+
+// every primitive x primitive combination of every compound pair, in the reference's loop order (left outer, right inner);
+// seg[k] = first flat pair of compound pair k (seg[n] = total)
+__global__ void __launch_bounds__(TPB) compound_expand_kernel(const uint2* __restrict__ comp_pairs, const unsigned long long* __restrict__ seg,
+                                                              uint32_t n_pairs, const uint32_t* __restrict__ offsets, uint2* __restrict__ flat) {
+    const unsigned long long total = seg[n_pairs];
+    for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (unsigned long long)gridDim.x * blockDim.x) {
+        uint32_t lo = 0, hi = n_pairs;  // the last k with seg[k] <= t
+        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (seg[mid] <= t) lo = mid; else hi = mid; }
+        const uint2 cp = comp_pairs[lo];
+        const uint32_t nr = offsets[cp.y + 1] - offsets[cp.y];
+        const unsigned long long w = t - seg[lo];
+        flat[t] = make_uint2(offsets[cp.x] + (uint32_t)(w / nr), offsets[cp.y] + (uint32_t)(w % nr));
+    }
+}
+
+// The reference's reductions over one compound pair's primitive pairs, in order. mode 0: intersection_complex — CollisionOnly
+// returns the first hit; FullResolution keeps the LAST maximum penetration depth (Iterator::max_by) and panics on a NaN depth
+// among two or more hits (partial_cmp(..).unwrap(), :403-405) -> ST_REF_PANIC. mode 1: distance_complex — None at the first
+// primitive pair that is not Some (a would-be panic there stays ST_REF_PANIC), else f32::min over all. mode 2:
+// intersection_complex_time_of_impact — a would-be panic inside a primitive pair reached before the result is decided ->
+// ST_REF_PANIC; CollisionOnly returns the first hit; FullResolution keeps the FIRST minimum time of impact (min_by with
+// unwrap_or(Equal)). A primitive pair the device could not decide (ST_CAPACITY; the time-of-impact iteration cap ST_MAX_ITER,
+// which the reference does not have) makes the compound result undecided too: its status is reported instead of a contact
+// that might not be the reference's.
+__global__ void __launch_bounds__(TPB) compound_reduce_kernel(int mode, int strategy, const unsigned long long* __restrict__ seg, uint32_t n_pairs,
+                                                              const float4* __restrict__ contacts, const float* __restrict__ ref_value,
+                                                              const uint8_t* __restrict__ status, float4* __restrict__ out_contacts,
+                                                              float* __restrict__ out_value, uint8_t* __restrict__ out_status) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_pairs) return;
+    const unsigned long long b = seg[k], e = seg[k + 1];
+    uint8_t st = ST_MISS;
+    float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;
+    float value = 0.f;
+    if (mode == 1) {
+        bool have = false;
+        float mn = 0.f;
+        st = ST_OK;
+        for (unsigned long long t = b; t < e; ++t) {
+            const uint8_t s1 = status[t];
+            if (s1 != ST_OK) { st = (s1 == ST_REF_PANIC) ? ST_REF_PANIC : ST_MISS; break; }
+            const float rv = ref_value[t];
+            mn = have ? rmin(rv, mn) : rv;
+            have = true;
+        }
+        if (st == ST_OK && !have) st = ST_MISS;
+        if (st == ST_OK) value = mn;
+    } else {
+        long long best = -1;
+        int nhits = 0;
+        bool nan_depth = false;
+        uint8_t undecided = ST_OK;
+        for (unsigned long long t = b; t < e; ++t) {
+            const uint8_t s1 = status[t];
+            if (s1 == ST_OK) {
+                if (strategy == 1) { best = (long long)t; break; }  // CollisionOnly: the first hit returns
+                ++nhits;
+                if (mode == 0) {
+                    const float d = contacts[2 * t].w;
+                    if (best < 0) best = (long long)t;
+                    else {
+                        const float a = contacts[2 * (size_t)best].w;
+                        if (a != a || d != d) nan_depth = true;
+                        if (!(a > d)) best = (long long)t;  // max_by keeps the later element unless the earlier compares Greater
+                    }
+                } else {
+                    if (best < 0 || contacts[2 * t + 1].w < contacts[2 * (size_t)best + 1].w) best = (long long)t;  // min_by: first minimum
+                }
+            } else if (mode == 2 && s1 == ST_REF_PANIC) {
+                best = -2; break;  // the reference panics inside this primitive pair
+            } else if (s1 == ST_CAPACITY || (mode == 2 && s1 == ST_MAX_ITER)) {
+                if (undecided == ST_OK) undecided = s1;
+            }
+        }
+        if (best == -2) st = ST_REF_PANIC;
+        else if (undecided != ST_OK) st = undecided;
+        else if (mode == 0 && nan_depth) st = ST_REF_PANIC;
+        else if (best >= 0) { st = ST_OK; c0 = contacts[2 * (size_t)best]; c1 = contacts[2 * (size_t)best + 1]; }
+        (void)nhits;
+    }
+    out_status[k] = st;
+    if (mode == 1) out_value[k] = value;
+    else { out_contacts[2 * (size_t)k] = c0; out_contacts[2 * (size_t)k + 1] = c1; }
+}
+
+int launch_compound_compose(cudaStream_t st, const float* d_comp_xform, const float* d_local, const uint32_t* d_owner, uint32_t n_prims, float* d_out) {
+    if (n_prims == 0) return 0;
+    compound_compose_kernel<<<(n_prims + TPB - 1) / TPB, TPB, 0, st>>>(reinterpret_cast<const float4*>(d_comp_xform), reinterpret_cast<const float4*>(d_local),
+                                                                     d_owner, n_prims, reinterpret_cast<float4*>(d_out));
+    return 1;
+}
+int launch_compound_expand(cudaStream_t st, const uint2* d_comp_pairs, const unsigned long long* d_seg, uint32_t n_pairs, uint64_t total,
+                           const uint32_t* d_offsets, uint2* d_flat) {
+    if (total == 0) return 0;
+    uint64_t g = (total + TPB - 1) / TPB;
+    if (g > (uint64_t)NUM_SMS * 32) g = (uint64_t)NUM_SMS * 32;
+    compound_expand_kernel<<<(unsigned)g, TPB, 0, st>>>(d_comp_pairs, d_seg, n_pairs, d_offsets, d_flat);
+    return 1;
+}
+int launch_compound_reduce(cudaStream_t st, int mode, int strategy, const unsigned long long* d_seg, uint32_t n_pairs, const float4* d_contacts,
+                           const float* d_ref, const uint8_t* d_status, float4* d_out_contacts, float* d_out_value, uint8_t* d_out_status) {
+    if (n_pairs == 0) return 0;
+    compound_reduce_kernel<<<(n_pairs + TPB - 1) / TPB, TPB, 0, st>>>(mode, strategy, d_seg, n_pairs, d_contacts, d_ref, d_status, d_out_contacts, d_out_value,
+                                                                    d_out_status);
+    return 1;
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // contact compaction (hits only, tagged with the global pair index) — feeds the multi-GPU gather
 // ------------------------------------------------------------------------------------------------------------
 struct Contact40 { uint32_t pair_index, status; float4 a, b; };
@@ -1255,6 +1435,7 @@ int launch_intersect(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs
     const uint32_t* order = B ? B->order : nullptr;
     const uint32_t* ranges = B ? B->ranges : nullptr;
     if (run_thread) {
+#ifdef B3_EXPERIMENTS
         if (d_scratch && refill_min > 0) {
             static const int grid = persistent_grid((const void*)gjk_intersect_refill_kernel);
             cudaMemsetAsync(d_scratch, 0, 4, st);
@@ -1268,7 +1449,10 @@ int launch_intersect(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs
             gjk_first_test_kernel<<<thread_grid(n), TPB, 0, st>>>(S, d_pairs, n, order, ranges, survivors, n_survivors, d_status);
             gjk_intersect_survivors_kernel<<<thread_grid(n), TPB, 0, st>>>(S, d_pairs, survivors, n_survivors, cfg, d_status);
             launched += 2;
-        } else {
+        } else
+#endif
+        {
+            (void)d_scratch; (void)refill_min;
             gjk_intersect_kernel<false><<<thread_grid(n), TPB, 0, st>>>(S, d_pairs, n, order, ranges, cfg, d_status);
             ++launched;
         }
@@ -1276,7 +1460,7 @@ int launch_intersect(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs
     if (run_warp) { gjk_intersect_kernel<true><<<warp_grid(n), TPB, 0, st>>>(S, d_pairs, n, order, ranges, cfg, d_status); ++launched; }
     return launched;
 }
-size_t contact_poly_slab_bytes() { return (size_t)NUM_SMS * B3_EPA_BLOCKS * TPB * EPA_SLAB_BYTES; }
+size_t contact_poly_slab_bytes() { return (size_t)NUM_SMS * B3_EPA_BLOCKS * TPB * (EPA_PIPE_SLAB_BYTES > EPA_SLAB_BYTES ? EPA_PIPE_SLAB_BYTES : EPA_SLAB_BYTES); }
 size_t contact_overflow_scratch_bytes() { return OVF_HEADER_BYTES + (size_t)OVF_WARPS * EPA_BIG_SLAB_BYTES; }
 // header | n GJK->EPA records | 3 promotion lists of n record indices | sup_a scratch of the shared-memory EPA warps
 static size_t queue_lists_bytes(uint32_t n) { return ((size_t)n * 12 + 15) & ~(size_t)15; }
@@ -1288,7 +1472,7 @@ static int epa_refill_grid() {
     static int blocks = 0;
     if (!blocks) {
         int per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, epa_refill_kernel<true>, TPB, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, epa_refill_kernel<true, false>, TPB, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
         if (per_sm > B3_EPA_BLOCKS) per_sm = B3_EPA_BLOCKS;  // (the slab of the global-polytope variant is sized for this many blocks per SM)
         if (const char* e = getenv("BAM3D_EPA_BLOCKS_PER_SM")) { int v = atoi(e); if (v >= 1 && v < per_sm) per_sm = v; }
         blocks = per_sm * NUM_SMS;
@@ -1350,7 +1534,7 @@ static BinOrder epa_bin_order() {
 }
 
 int launch_contact(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs, uint32_t n, const BinScratch* B, bool run_thread,
-                   bool run_warp, const SettingsDev& cfg, int strategy, uint32_t default_key, int epa_mode, const ContactSide* side,
+                   bool run_warp, const SettingsDev& cfg, int strategy, uint32_t default_key, int epa_mode, bool epa_pipeline, const ContactSide* side,
                    void* d_poly_slab, void* d_overflow_scratch, void* d_queue, float4* d_contacts, uint8_t* d_status) {
     unsigned char* ovf = reinterpret_cast<unsigned char*>(d_overflow_scratch);
     unsigned char* queue = reinterpret_cast<unsigned char*>(d_queue);
@@ -1361,7 +1545,11 @@ int launch_contact(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs, 
     static bool smem_opt_in = false;
     if (!smem_opt_in) {
         cudaFuncSetAttribute(gjk_contact_overflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EPA_BIG_SMEM_BYTES);
+#ifdef B3_EXPERIMENTS
         cudaFuncSetAttribute(epa_tiers_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(epa_refill_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EPA_PIPE_SMEM);
+        if (B3_PIPE_A) cudaFuncSetAttribute(epa_refill_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+#endif
         cudaFuncSetAttribute(gjk_contact_overflow_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         smem_opt_in = true;
     }
@@ -1383,6 +1571,7 @@ int launch_contact(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs, 
                                                          d_contacts, d_status);
         ++launched;
         if (overlap) cudaEventRecord(side->fork, st);
+#ifdef B3_EXPERIMENTS
         if (strategy == 0 && epa_mode != 0) {
             cudaMemsetAsync(queue + EPAQ_HEADER_BYTES + (size_t)n * EPAQ_REC_F4 * 16, 0xFF, queue_lists_bytes(n), st);
             epa_tiers_kernel<<<NUM_SMS * TIER_WARPS_PER_SM, 32, TIER_POOL_BYTES, st>>>(S, d_pairs, cfg, bin_start, epa_bin_order(), queue, n, ovf,
@@ -1400,13 +1589,22 @@ int launch_contact(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs, 
                         w[QH_PROMO_COUNT + 2], w[QH_PROMO_COUNT + 3], w[QH_DONE]);
             }
 #endif
-        } else if (strategy == 0) {
-            if (d_poly_slab)
-                epa_refill_kernel<true><<<epa_refill_grid(), TPB, 0, st>>>(S, d_pairs, cfg, bin_start, epa_bin_order(), queue, ovf,
-                                                                           reinterpret_cast<unsigned char*>(d_poly_slab), d_contacts, d_status);
+        } else
+#endif
+        if (strategy == 0) {
+            (void)epa_mode; (void)epa_pipeline;
+#ifdef B3_EXPERIMENTS
+            if (d_poly_slab && epa_mode == 0 && epa_pipeline)
+                epa_refill_kernel<true, true><<<epa_refill_grid(), TPB, EPA_PIPE_SMEM, st>>>(S, d_pairs, cfg, bin_start, epa_bin_order(), queue, ovf,
+                                                                                             reinterpret_cast<unsigned char*>(d_poly_slab), d_contacts, d_status);
             else
-                epa_refill_kernel<false><<<epa_refill_grid(), TPB, 0, st>>>(S, d_pairs, cfg, bin_start, epa_bin_order(), queue, ovf, nullptr,
-                                                                            d_contacts, d_status);
+#endif
+            if (d_poly_slab)
+                epa_refill_kernel<true, false><<<epa_refill_grid(), TPB, 0, st>>>(S, d_pairs, cfg, bin_start, epa_bin_order(), queue, ovf,
+                                                                                  reinterpret_cast<unsigned char*>(d_poly_slab), d_contacts, d_status);
+            else
+                epa_refill_kernel<false, false><<<epa_refill_grid(), TPB, 0, st>>>(S, d_pairs, cfg, bin_start, epa_bin_order(), queue, ovf, nullptr,
+                                                                                   d_contacts, d_status);
             ++launched;
 #ifdef B3_TIER_TRACE
             {

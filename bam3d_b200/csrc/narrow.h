@@ -51,13 +51,14 @@ int launch_intersect(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs
 size_t contact_overflow_scratch_bytes();
 size_t contact_queue_bytes(uint32_t n);
 // default_key: the (kindL * 7 + kindR) bin of every pair when B is null (a single-kind shape set), else ignored.
-// epa_mode: 1 = shared-memory EPA in size tiers (epa_tiers.cuh), 0 = per-thread local-memory EPA (epa.cuh).
+// epa_mode: 1 = shared-memory EPA in size tiers (epa_tiers.cuh), 0 = per-thread EPA (epa.cuh).
+// epa_pipeline: the thread-per-pair EPA iteration with its memory round trips overlapped (epa_pipe.cuh; needs the slab).
 // side (nullable): a second stream and two events; when given, the EPA overflow tier runs on it concurrently with the
 // thread-per-pair EPA kernel and is joined back into `st` before the call returns.
 struct ContactSide { cudaStream_t stream; cudaEvent_t fork, join; };
 int launch_contact(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs, uint32_t n, const BinScratch* B,
                    bool run_thread, bool run_warp, const SettingsDev& cfg, int strategy, uint32_t default_key, int epa_mode,
-                   const ContactSide* side, void* d_poly_slab, void* d_overflow_scratch, void* d_queue, float4* d_contacts, uint8_t* d_status);
+                   bool epa_pipeline, const ContactSide* side, void* d_poly_slab, void* d_overflow_scratch, void* d_queue, float4* d_contacts, uint8_t* d_status);
 // d_poly_slab (nullable): contact_poly_slab_bytes() of device memory; when given, the thread-per-pair EPA keeps its polytopes
 // there (one contiguous record per thread) instead of in per-thread local memory.
 size_t contact_poly_slab_bytes();
@@ -75,6 +76,13 @@ int launch_toi(cudaStream_t st, const ShapeSetDev& S0, const ShapeSetDev& S1, co
 // (ray index, shape index); query 0 = intersects_transformed, 1 = intersection_transformed, 2 = swept particle.
 int launch_ray_cast(cudaStream_t st, const ShapeSetDev& S, const float* d_rays, const uint2* d_casts, uint64_t n, int query, float* d_points,
                     uint8_t* d_status);
+// compound shapes (gjk/mod.rs:362-523): world transforms of the primitives, the primitive-pair expansion, the reductions
+int launch_compound_compose(cudaStream_t st, const float* d_comp_xform, const float* d_local, const uint32_t* d_owner, uint32_t n_prims, float* d_out);
+int launch_compound_expand(cudaStream_t st, const uint2* d_comp_pairs, const unsigned long long* d_seg, uint32_t n_pairs, uint64_t total,
+                           const uint32_t* d_offsets, uint2* d_flat);
+// mode 0 intersection_complex, 1 distance_complex, 2 intersection_complex_time_of_impact
+int launch_compound_reduce(cudaStream_t st, int mode, int strategy, const unsigned long long* d_seg, uint32_t n_pairs, const float4* d_contacts,
+                           const float* d_ref, const uint8_t* d_status, float4* d_out_contacts, float* d_out_value, uint8_t* d_out_status);
 int launch_compact_contacts(cudaStream_t st, const float4* d_contacts, const uint8_t* d_status, uint64_t n,
                             uint64_t base, void* d_out, uint64_t capacity, unsigned long long* d_count);
 

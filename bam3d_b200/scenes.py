@@ -188,6 +188,19 @@ def aabb_scene(n, seed=SEED_C4, start=0, density=4.0, extent=None):
     return np.concatenate([(c - h).astype(np.float32), (c + h).astype(np.float32)], axis=1), L
 
 
+def world_scene(n, seed=SEED_C4, density=0.1, kinds=(_ffi.KIND_SPHERE, _ffi.KIND_CUBOID, _ffi.KIND_CYLINDER), extent=None):
+    """n shapes of the C2 mix scattered in one volume (positions U[0, L]^3, uniform rotations) — the input of the broad -> narrow
+    pipeline: no pair list, sweep and prune finds the candidates. density = shapes per unit volume (0.1: ~2.7 candidate pairs per
+    shape, about a quarter of them in contact)."""
+    L = float(extent) if extent is not None else (n / density) ** (1.0 / 3.0)
+    idx = np.arange(n, dtype=np.uint64)
+    kind, params = _analytic_side(seed, 140, idx, kinds)
+    t = np.stack([uniform(seed, 150 + k, idx, 0.0, L) for k in range(3)], axis=1)
+    q = random_quat(seed, 160, idx)
+    return dict(kind=kind, params=params, xform=mat4_from_rotation_translation(q, t), mesh_id=None, mesh_verts=None, mesh_offsets=None,
+                pairs=np.zeros((0, 2), dtype=np.uint32)), L
+
+
 def rays(nq, L, seed=SEED_C4, start=0):
     """Rays with origin U in the volume and direction uniform on the sphere: nq x (origin.xyz, direction.xyz)."""
     idx = np.arange(start, start + nq, dtype=np.uint64)

@@ -165,6 +165,33 @@ int32_t bam3d_gjk_time_of_impact(bam3d_ctx* ctx, const bam3d_shapes* shapes_star
                                  const uint32_t* pairs, uint64_t n, const bam3d_gjk_settings* settings,
                                  bam3d_contact* out_contacts, uint8_t* out_status);
 
+/* ---- compound shapes --------------------------------------------------------------------------------------- */
+/* The reference's `&[(Primitive, Mat4)]` slices (gjk/mod.rs:362-371): compound c owns the primitives comp_offsets[c] ..
+ * comp_offsets[c + 1] of (kind, params, local_xform = local-to-model Mat4, mesh_id); comp_offsets has n_compounds + 1 entries. */
+typedef struct bam3d_compounds bam3d_compounds;
+int32_t bam3d_compounds_upload(bam3d_ctx* ctx, const uint8_t* kind, const float* params, const float* local_xform, const uint32_t* mesh_id,
+                               uint32_t n_prims, const uint32_t* comp_offsets, uint32_t n_compounds, const bam3d_meshes* meshes,
+                               bam3d_compounds** out);
+void bam3d_compounds_free(bam3d_ctx* ctx, bam3d_compounds* compounds);
+/* pairs: n x (left compound, right compound); comp_xform: n_compounds x 16, the model-to-world Mat4 of every compound. On the
+ * device: world transform of every primitive = comp_xform.mul_mat4(local_xform) (gjk/mod.rs:377-379, glam's operation order),
+ * every primitive x primitive combination in the reference's loop order through the batched kernels, then the reference's
+ * reduction per compound pair:
+ *  - GJK::intersection_complex (gjk/mod.rs:362-407): CollisionOnly = the first hit; FullResolution = the LAST contact of maximum
+ *    penetration depth (Iterator::max_by); BAM3D_STATUS_REF_PANIC where partial_cmp(..).unwrap() would meet a NaN depth;
+ *  - GJK::distance_complex (:422-456): None (MISS) at the first primitive pair that is not Some, else f32::min over all;
+ *  - GJK::intersection_complex_time_of_impact (:478-523): CollisionOnly = the first hit; FullResolution = the FIRST contact of
+ *    minimum time of impact (min_by, unwrap_or(Equal)); REF_PANIC where a primitive pair the reference evaluates would panic.
+ * A primitive pair the device could not decide (BAM3D_STATUS_CAPACITY; the time-of-impact iteration cap BAM3D_STATUS_MAX_ITER,
+ * which the reference does not have) makes its compound pair undecided too: that status is returned instead of a contact. */
+int32_t bam3d_gjk_contact_complex(bam3d_ctx* ctx, bam3d_compounds* compounds, const float* comp_xform, const uint32_t* pairs, uint64_t n,
+                                  const bam3d_gjk_settings* settings, int32_t strategy, bam3d_contact* out_contacts, uint8_t* out_status);
+int32_t bam3d_gjk_distance_complex(bam3d_ctx* ctx, bam3d_compounds* compounds, const float* comp_xform, const uint32_t* pairs, uint64_t n,
+                                   const bam3d_gjk_settings* settings, float* out_value, uint8_t* out_status);
+int32_t bam3d_gjk_time_of_impact_complex(bam3d_ctx* ctx, bam3d_compounds* compounds, const float* comp_xform_start,
+                                         const float* comp_xform_end, const uint32_t* pairs, uint64_t n, const bam3d_gjk_settings* settings,
+                                         int32_t strategy, bam3d_contact* out_contacts, uint8_t* out_status);
+
 /* ---- narrow phase, device buffers (asynchronous on the ctx stream) -------------------------------------- */
 int32_t bam3d_gjk_intersect_dev(bam3d_ctx* ctx, const bam3d_shapes* shapes, const uint32_t* d_pairs, uint64_t n,
                                 const bam3d_gjk_settings* settings, uint8_t* d_status);
@@ -253,11 +280,28 @@ int32_t bam3d_sap_find_pairs_spheres(bam3d_ctx* ctx, const float* spheres, uint6
 int32_t bam3d_sap_find_pairs_spheres_dev(bam3d_ctx* ctx, const float* d_spheres, uint64_t n, int32_t* inout_sweep_axis, uint32_t* d_perm,
                                          uint32_t* d_pairs, uint64_t capacity, uint64_t* out_count);
 
+/* Broad phase -> narrow phase in one call, everything resident (BASELINE configs[3]): world Aabb3 of every shape
+ * (bam3d_shapes_world_aabbs) -> SweepAndPrune3::find_collider_pairs over them (bam3d_sap_find_pairs[_shard]) -> GJK::intersection
+ * (bam3d_gjk_contact) on every candidate pair. The reference leaves this glue to its caller, and find_collider_pairs returns
+ * indices into the slice it has just re-sorted (sweep_prune.rs:65-69,80): out_pairs[k] = (perm[i], perm[j]) are the SHAPE
+ * indices of candidate k, in the reference's emission order; out_sorted_pairs (may be NULL) the (i, j) sorted positions as the
+ * reference returns them, out_perm (may be NULL) the permutation. contacts / status are per candidate pair. If more than
+ * `capacity` candidates exist: BAM3D_ERR_CAPACITY with *out_count = the number required. The _dev form takes a shard
+ * (multi-GPU: the sort is replicated, each GPU searches and resolves its own slice of the pair list). */
+int32_t bam3d_pipeline_contacts(bam3d_ctx* ctx, const bam3d_shapes* shapes, int32_t* inout_sweep_axis, const bam3d_gjk_settings* settings,
+                                int32_t strategy, uint32_t* out_pairs, uint32_t* out_sorted_pairs, uint32_t* out_perm,
+                                bam3d_contact* out_contacts, uint8_t* out_status, uint64_t capacity, uint64_t* out_count);
+int32_t bam3d_pipeline_contacts_dev(bam3d_ctx* ctx, const bam3d_shapes* shapes, int32_t* inout_sweep_axis, const bam3d_gjk_settings* settings,
+                                    int32_t strategy, uint32_t shard, uint32_t n_shards, uint32_t* d_pairs, uint32_t* d_sorted_pairs,
+                                    uint32_t* d_perm, bam3d_contact* d_contacts, uint8_t* d_status, uint64_t capacity, uint64_t* out_count);
+
 /* Static BVH over n values' bounds, answering DynamicBoundingVolumeTree::query_for_indices (dbvt/mod.rs:481-515).
  * Value index k = position in `aabbs` (the tree's `values` order). The reference's insert / remove / rotate
  * maintenance (dbvt/mod.rs:531-1235) is not reproduced: its tree shape is randomised (rand::thread_rng, :901) and
  * query result SETS do not depend on the shape. Results of one query are returned in the device tree's traversal
- * order (deterministic for given boxes); compare with the reference as sets. */
+ * order (deterministic for given boxes); compare with the reference as sets. The traversal is stackless (every node
+ * record carries the node to continue with when its subtree is done), so no tree depth can overflow anything — the
+ * reference indexes past its fixed 256-entry stack on a deep enough tree. */
 int32_t bam3d_bvh_build(bam3d_ctx* ctx, const float* aabbs, uint64_t n, bam3d_bvh** out);
 int32_t bam3d_bvh_build_dev(bam3d_ctx* ctx, const float* d_aabbs, uint64_t n, bam3d_bvh** out);
 /* New bounds for the values of an existing tree, topology unchanged: the device form of update_node + do_refit
@@ -286,6 +330,18 @@ int32_t bam3d_bvh_query_frustum(bam3d_ctx* ctx, const bam3d_bvh* bvh, const floa
  * Exact ties in t resolve to the lowest value index (the reference keeps the first in its randomised traversal order). */
 int32_t bam3d_bvh_query_ray_closest(bam3d_ctx* ctx, const bam3d_bvh* bvh, const float* rays, uint64_t nq, uint32_t* out_value,
                                     float* out_point_t);
+/* The same queries for a resident frame loop (dbvt/mod.rs:481-515 is what such a loop calls every frame): device pointers, ONE
+ * traversal, no synchronisation. Hits are appended in arbitrary order as parallel arrays — d_out_query[i] = query index,
+ * d_out_values[i] = value index, plus the visitor's result (hit point / Relation) — up to `capacity`; *d_count (device u64)
+ * receives the number of hits found, which may exceed capacity (the excess is dropped). Sort by d_out_query for per-query lists. */
+int32_t bam3d_bvh_query_aabb_dev(bam3d_ctx* ctx, const bam3d_bvh* bvh, const float* d_queries, uint64_t nq, uint32_t* d_out_query,
+                                 uint32_t* d_out_values, uint64_t capacity, uint64_t* d_count);
+int32_t bam3d_bvh_query_ray_dev(bam3d_ctx* ctx, const bam3d_bvh* bvh, const float* d_rays, uint64_t nq, uint32_t* d_out_query,
+                                uint32_t* d_out_values, float* d_out_points, uint64_t capacity, uint64_t* d_count);
+int32_t bam3d_bvh_query_frustum_dev(bam3d_ctx* ctx, const bam3d_bvh* bvh, const float* d_planes, uint64_t nq, uint32_t* d_out_query,
+                                    uint32_t* d_out_values, uint8_t* d_out_relation, uint64_t capacity, uint64_t* d_count);
+int32_t bam3d_bvh_query_ray_closest_dev(bam3d_ctx* ctx, const bam3d_bvh* bvh, const float* d_rays, uint64_t nq, uint32_t* d_out_value,
+                                        float* d_out_point_t);
 /* DbvtBroadPhase::find_collider_pairs (algorithm/broad_phase/dbvt.rs:26-63): every value with dirty[k] != 0 is queried
  * against the tree; out_pairs = sorted unique (low, high) value-index pairs. */
 int32_t bam3d_bvh_find_collider_pairs(bam3d_ctx* ctx, const bam3d_bvh* bvh, const uint8_t* dirty, uint32_t* out_pairs,

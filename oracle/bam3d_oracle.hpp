@@ -583,6 +583,7 @@ struct GJK {
                               const std::vector<std::pair<Shape, Mat4>>& right, const Mat4& rt, Contact& out, Status& st) const {
         st = Status::Miss;
         std::vector<Contact> contacts;
+        bool undecided = false;  // a primitive pair stopped by the face limit (not in the reference): its contact is unknown, so is the maximum
         for (auto& l : left) {
             Mat4 ltf = lt.mul_mat4(l.second);
             for (auto& r : right) {
@@ -591,9 +592,10 @@ struct GJK {
                 if (intersection(strategy, l.first, ltf, r.first, rtf, c, &s1)) {
                     if (strategy == CollisionStrategy::CollisionOnly) { out = c; st = Status::Ok; return true; }
                     contacts.push_back(c);
-                }
+                } else if (s1 == Status::Capacity) undecided = true;
             }
         }
+        if (undecided) { st = Status::Capacity; return false; }
         if (contacts.empty()) return false;
         // Iterator::max_by: the LAST of several equal maxima is returned; unwrap() panics on NaN
         size_t best = 0;
@@ -633,17 +635,23 @@ struct GJK {
                                              Contact& out, Status& st) const {
         st = Status::Miss;
         std::vector<Contact> contacts;
+        bool undecided = false;  // a primitive pair stopped by the added iteration cap: the reference's loop has none, its outcome is unknown
         for (auto& l : left) {
             Mat4 l0 = lt0.mul_mat4(l.second), l1 = lt1.mul_mat4(l.second);
             for (auto& r : right) {
                 Mat4 r0 = rt0.mul_mat4(r.second), r1 = rt1.mul_mat4(r.second);
                 Contact c; Status s1;
                 if (intersection_time_of_impact(l.first, l0, l1, r.first, r0, r1, c, s1)) {
-                    if (strategy == CollisionStrategy::CollisionOnly) { c.strategy = CollisionStrategy::CollisionOnly; out = c; st = Status::Ok; return true; }
+                    if (strategy == CollisionStrategy::CollisionOnly) {
+                        if (undecided) { st = Status::MaxIter; return false; }
+                        c.strategy = CollisionStrategy::CollisionOnly; out = c; st = Status::Ok; return true;
+                    }
                     contacts.push_back(c);
                 } else if (s1 == Status::WouldPanic) { st = s1; return false; }
+                else if (s1 == Status::MaxIter) undecided = true;
             }
         }
+        if (undecided) { st = Status::MaxIter; return false; }
         if (contacts.empty()) return false;
         size_t best = 0;
         for (size_t i = 1; i < contacts.size(); ++i)

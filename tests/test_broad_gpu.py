@@ -381,3 +381,119 @@ def test_sap_spheres_edge_cases(ctx, oracle):
     pairs, perm = broad.SweepAndPrune3Sphere.new(ctx).find_collider_pairs(far)
     opairs, operm, _ = oracle.sap_find_pairs_spheres(far, 0)
     assert len(opairs) >= 1000 and np.array_equal(perm, operm) and np.array_equal(pairs, opairs)
+
+
+def test_bvh_device_resident_queries_match_the_host_buffer_forms(ctx, oracle, bvh_strategy):
+    """bam3d_bvh_query_{aabb,ray,frustum,ray_closest}_dev (one pass, append, device pointers) return exactly the (query, value,
+    payload) tuples of the count + scan + fill host-buffer forms — which the oracle checks above — in any order; a capacity
+    that is too small drops the excess but still reports the full count."""
+    import ctypes as C
+    import torch
+    boxes, L = scenes.aabb_scene(30_000, seed=0xB3D0C420)
+    bvh = broad.Bvh(ctx, boxes)
+    dev = torch.device("cuda:0")
+    p = lambda t: C.c_void_p(t.data_ptr())
+    d_count = torch.zeros(1, dtype=torch.int64, device=dev)
+
+    def run(kind, queries, width, pay_shape, pay_dtype):
+        q = np.ascontiguousarray(queries, dtype=np.float32).reshape(-1, width)
+        d_q = torch.from_numpy(q).to(dev)
+        bvh.query_dev(kind, p(d_q), len(q), None, None, None, 0, p(d_count))       # count only
+        ctx.synchronize()
+        total = int(d_count.item())
+        oq = torch.empty(total + 7, dtype=torch.int32, device=dev)
+        ov = torch.empty(total + 7, dtype=torch.int32, device=dev)
+        op = torch.empty((total + 7,) + pay_shape, dtype=pay_dtype, device=dev) if pay_dtype is not None else None
+        bvh.query_dev(kind, p(d_q), len(q), p(oq), p(ov), p(op) if op is not None else None, total + 7, p(d_count))
+        ctx.synchronize()
+        assert int(d_count.item()) == total
+        # too small: nothing written past the capacity, count unchanged
+        guard = torch.full((total + 7,), -1, dtype=torch.int32, device=dev)
+        bvh.query_dev(kind, p(d_q), len(q), p(guard), p(ov.clone()), p(op.clone()) if op is not None else None, total // 2, p(d_count))
+        ctx.synchronize()
+        assert int(d_count.item()) == total and bool((guard[total // 2:] == -1).all())
+        oq, ov = oq[:total].cpu().numpy().astype(np.uint32), ov[:total].cpu().numpy().astype(np.uint32)
+        pay = op[:total].cpu().numpy() if op is not None else None
+        order = np.lexsort((ov, oq))
+        return oq[order], ov[order], (pay[order] if pay is not None else None), total
+
+    qboxes, _ = scenes.aabb_scene(500, seed=0xB3D0C421, extent=L)
+    qboxes[:, 3:] += 1.0
+    rays = scenes.rays(500, L, seed=0xB3D0C422)
+    planes = np.stack([broad.frustum_from_mat4(m).reshape(24) for m in scenes.view_projections(12, L, seed=0xB3D0C423)])
+    for kind, queries, width, ps, pd, host in (("aabb", qboxes, 6, (), None, bvh.query_aabb), ("ray", rays, 6, (3,), torch.float32, bvh.query_ray),
+                                                ("frustum", planes, 24, (), torch.uint8, bvh.query_frustum)):
+        gq, gv, gp, total = run(kind, queries, width, ps, pd)
+        res = host(queries)
+        off, vals = res[0], res[1]
+        hq = np.repeat(np.arange(len(off) - 1, dtype=np.uint32), np.diff(off).astype(np.int64))
+        order = np.lexsort((vals, hq))
+        assert total == len(vals) and total > 500
+        assert np.array_equal(gq, hq[order]) and np.array_equal(gv, vals[order])
+        if gp is not None:
+            assert gp.tobytes() == res[2][order].tobytes()
+    # closest ray
+    d_r = torch.from_numpy(rays).to(dev)
+    cv = torch.empty(len(rays), dtype=torch.int32, device=dev)
+    cp = torch.empty((len(rays), 4), dtype=torch.float32, device=dev)
+    bvh.query_ray_closest_dev(p(d_r), len(rays), p(cv), p(cp))
+    ctx.synchronize()
+    hv, hp = bvh.query_ray_closest(rays)
+    assert np.array_equal(cv.cpu().numpy().astype(np.uint32), hv) and cp.cpu().numpy().tobytes() == hp.tobytes()
+
+
+def test_bvh_degenerate_scenes_lose_nothing(ctx, oracle):
+    """10^5 coincident boxes (every Morton code equal: the tree is split by index bits alone and is as deep as it gets) plus a
+    few others: every query must still return every hit. The traversal is stackless, so there is no depth at which children
+    could be dropped (the previous explicit 64-entry stack dropped them silently when full)."""
+    n = 100_000
+    boxes = np.tile(np.array([[1, 1, 1, 2, 2, 2]], dtype=np.float32), (n, 1))
+    boxes[-3:] = [[5, 5, 5, 6, 6, 6], [1.5, 1.5, 1.5, 7, 7, 7], [-3, -3, -3, -2, -2, -2]]
+    bvh = broad.Bvh(ctx, boxes)
+    off, vals = bvh.query_aabb([[0, 0, 0, 1.25, 1.25, 1.25], [5.5, 5.5, 5.5, 9, 9, 9], [10, 10, 10, 11, 11, 11]])
+    got = [np.sort(vals[int(off[k]):int(off[k + 1])]) for k in range(3)]
+    assert np.array_equal(got[0], np.arange(n - 3)) and got[1].tolist() == [n - 3, n - 2] and len(got[2]) == 0
+    off, vals, pts = bvh.query_ray([[0, 1.5, 1.5, 1, 0, 0], [0, 0, 0, -1, 0, 0]])
+    assert np.array_equal(np.sort(vals[int(off[0]):int(off[1])]), np.concatenate([np.arange(n - 3), [n - 2]])) and off[2] == off[1]
+    val, pt = bvh.query_ray_closest([[0, 1.5, 1.5, 1, 0, 0]])
+    assert val[0] == 0 and pt[0, 3] == np.float32(1.0)   # every coincident box ties at t = 1: lowest value index
+    # all-dirty DbvtBroadPhase on a smaller pile (n^2 / 2 pairs)
+    m = 600
+    pile = np.tile(np.array([[0, 0, 0, 1, 1, 1]], dtype=np.float32), (m, 1))
+    pairs = broad.Bvh(ctx, pile).find_collider_pairs(np.ones(m, dtype=np.uint8))
+    assert len(pairs) == m * (m - 1) // 2 and np.array_equal(pairs, oracle.dbvt_build(pile).find_collider_pairs(np.ones(m, dtype=np.uint8)))
+    # sweep and prune over the same pile: every pair, in the reference's order
+    sp, perm = broad.SweepAndPrune3.new(ctx).find_collider_pairs(pile)
+    op, operm, _ = oracle.sap_find_pairs(pile, 0)
+    assert np.array_equal(sp, op) and np.array_equal(perm, operm)
+
+
+def test_pipeline_broad_then_narrow_matches_the_oracle_chain(ctx, oracle):
+    """g1 (BASELINE configs[3]): world AABBs -> SweepAndPrune3 -> perm remap -> GJK::intersection, one resident call, against the
+    same chain run on the CPU: the oracle's world AABBs, the oracle's sweep over them (pairs index the SORTED order, as the
+    reference returns them: sweep_prune.rs:65-69,80), shapes[perm[i]], shapes[perm[j]] into the oracle's GJK+EPA. Pair list,
+    order, permutation, next axis, status and contacts are compared bit for bit; a second frame reuses the returned axis."""
+    import bam3d_b200 as b3
+    scene, L = scenes.world_scene(20_000, seed=0xB3D0C430)
+    shapes = b3.ShapeSet(ctx, scene["kind"], scene["params"], scene["xform"])
+    gjk = b3.GJK.new(ctx)
+    axis = 0
+    for frame in range(2):
+        got = broad.pipeline_contacts(gjk, shapes, b3.CollisionStrategy.FullResolution, sweep_axis=axis)
+        boxes = oracle.world_aabbs(scene)
+        opairs, operm, oaxis = oracle.sap_find_pairs(boxes, axis)
+        assert np.array_equal(got["sorted_pairs"], opairs) and np.array_equal(got["perm"], operm) and got["next_axis"] == oaxis
+        want_pairs = operm[opairs.astype(np.int64)].astype(np.uint32)
+        assert np.array_equal(got["pairs"], want_pairs) and len(want_pairs) > 20_000
+        sub = dict(scene)
+        sub["pairs"] = want_pairs
+        oc, _, ost = oracle.contact(sub, strategy=0, nthreads=8)
+        assert np.array_equal(got["status"], ost)
+        hit = ost == 0
+        assert hit.sum() > 3_000
+        assert got["contacts"][hit][:, :7].tobytes() == oc[hit][:, :7].tobytes()
+        axis = got["next_axis"]
+    # a capacity that is too small reports the size needed (the wrapper retries with it)
+    small = broad.pipeline_contacts(gjk, shapes, b3.CollisionStrategy.CollisionOnly, sweep_axis=0, capacity=16)
+    assert len(small["pairs"]) == len(opairs) or axis != 0
+    shapes.close()
