@@ -55,9 +55,10 @@ static SettingsDev to_dev(const bam3d_gjk_settings* s) {
     return r;
 }
 
-static ShapeSetDev view(const bam3d_shapes* s) {
+static ShapeSetDev view(const bam3d_ctx* ctx, const bam3d_shapes* s) {
     ShapeSetDev v;
     v.recs = s->recs; v.meta = s->meta; v.n = s->n;
+    v.err = s->err_flag ? s->err_flag : ctx->d_flags;
     v.mesh_verts = s->meshes ? s->meshes->verts : nullptr;
     v.mesh_offsets = s->meshes ? s->meshes->offsets : nullptr;
     return v;
@@ -118,8 +119,28 @@ struct KernelTimer {
     }
 };
 
+// the kernels walk batches with 32-bit grid-stride counters (strides up to 148 x 32 x 128): stay 2^24 below 2^32
 static int32_t check_n(bam3d_ctx* ctx, uint64_t n) {
-    if (n > 0xFFFFFF00ull) return b3_fail(ctx, BAM3D_ERR_ARG, "batch too large: n must be < 2^32 - 256 pairs per call", cudaSuccess);
+    if (n > 0xFF000000ull) return b3_fail(ctx, BAM3D_ERR_ARG, "batch too large: n must be <= 2^32 - 2^24 items per call", cudaSuccess);
+    return BAM3D_OK;
+}
+static int32_t check_pairs_over(bam3d_ctx* ctx, const bam3d_shapes* shapes, uint64_t n) {
+    if (n && shapes->n == 0) return b3_fail(ctx, BAM3D_ERR_ARG, "pairs over an empty shape set", cudaSuccess);
+    return BAM3D_OK;
+}
+
+// After a synchronisation point: has a kernel of this ctx met a pair whose shape index is out of range? (The index was clamped,
+// nothing was read out of bounds, but that pair's result is meaningless.) Reads and clears the flag.
+static int32_t take_index_flag(bam3d_ctx* ctx, const char* what) {
+    cudaError_t e = cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) return b3_fail(ctx, BAM3D_ERR_CUDA, what, e);
+    if (*ctx->h_flags & 1u) {
+        cudaMemsetAsync(ctx->d_flags, 0, 4, ctx->stream);
+        char msg[192];
+        std::snprintf(msg, sizeof msg, "%s: a pair names a shape index >= the shape set's size", what);
+        return b3_fail(ctx, BAM3D_ERR_ARG, msg, cudaSuccess);
+    }
     return BAM3D_OK;
 }
 
@@ -157,7 +178,9 @@ int32_t bam3d_ctx_create(int32_t device_ordinal, bam3d_ctx** out_ctx) {
     if (const char* e = std::getenv("BAM3D_TOI_REFILL")) ctx->opt_toi_refill = std::atoi(e);
     if (const char* e = std::getenv("BAM3D_DISTANCE_REFILL")) ctx->opt_distance_refill = std::atoi(e);
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return BAM3D_ERR_CUDA; }
-    if (cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+    if (cudaMalloc(&ctx->d_flags, 64) != cudaSuccess || cudaMemset(ctx->d_flags, 0, 64) != cudaSuccess ||
+        cudaHostAlloc(&ctx->h_flags, 64, cudaHostAllocDefault) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_a, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_b, cudaEventDisableTiming) != cudaSuccess) { bam3d_ctx_destroy(ctx); return BAM3D_ERR_CUDA; }
     *out_ctx = ctx;
@@ -168,6 +191,10 @@ void bam3d_ctx_destroy(bam3d_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    for (auto& ev : ctx->timing_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    ctx->timing_events.clear();
+    if (ctx->d_flags) cudaFree(ctx->d_flags);
+    if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
     ctx->release_scratch();
     if (ctx->stream2) { cudaStreamSynchronize(ctx->stream2); cudaStreamDestroy(ctx->stream2); }
     if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
@@ -179,8 +206,8 @@ void bam3d_ctx_destroy(bam3d_ctx* ctx) {
 const char* bam3d_last_error(const bam3d_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context (CUDA device unavailable?)"; }
 int32_t bam3d_ctx_synchronize(bam3d_ctx* ctx) {
     if (!ctx) return BAM3D_ERR_ARG;
-    CU_TRY(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize");
-    return BAM3D_OK;
+    // also the place where a device-pointer (_dev) call's out-of-range pair index comes to light
+    return take_index_flag(ctx, "bam3d_ctx_synchronize");
 }
 void* bam3d_ctx_stream(bam3d_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 uint64_t bam3d_ctx_launch_count(const bam3d_ctx* ctx) { return ctx ? ctx->launches : 0; }
@@ -449,10 +476,10 @@ int32_t bam3d_gjk_intersect_dev(bam3d_ctx* ctx, const bam3d_shapes* shapes, cons
                                 const bam3d_gjk_settings* settings, uint8_t* d_status) {
     if (!ctx || !shapes || (n && (!d_pairs || !d_status))) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_gjk_intersect: null argument", cudaSuccess);
     int32_t rc;
-    if ((rc = check_n(ctx, n))) return rc;
+    if ((rc = check_n(ctx, n)) || (rc = check_pairs_over(ctx, shapes, n))) return rc;
     if (n == 0) return BAM3D_OK;
     CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
-    ShapeSetDev S = view(shapes);
+    ShapeSetDev S = view(ctx, shapes);
     Plan plan = plan_for(ctx, shapes);
     BinScratch B; const BinScratch* pb;
     if ((rc = prepare_bins(ctx, plan, S, (const uint2*)d_pairs, (uint32_t)n, B, &pb))) return rc;
@@ -476,10 +503,10 @@ int32_t bam3d_gjk_contact_dev(bam3d_ctx* ctx, const bam3d_shapes* shapes, const 
     if (strategy == BAM3D_FULL_RESOLUTION && cfg.max_iterations > 100)
         return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_gjk_contact: max_iterations > 100 exceeds the device EPA polytope capacity", cudaSuccess);
     int32_t rc;
-    if ((rc = check_n(ctx, n))) return rc;
+    if ((rc = check_n(ctx, n)) || (rc = check_pairs_over(ctx, shapes, n))) return rc;
     if (n == 0) return BAM3D_OK;
     CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
-    ShapeSetDev S = view(shapes);
+    ShapeSetDev S = view(ctx, shapes);
     Plan plan = plan_for(ctx, shapes);
     BinScratch B; const BinScratch* pb;
     if ((rc = prepare_bins(ctx, plan, S, (const uint2*)d_pairs, (uint32_t)n, B, &pb))) return rc;
@@ -505,10 +532,10 @@ int32_t bam3d_gjk_distance_dev(bam3d_ctx* ctx, const bam3d_shapes* shapes, const
                                const bam3d_gjk_settings* settings, float* d_ref_value, float* d_distance, uint8_t* d_status) {
     if (!ctx || !shapes || (n && (!d_pairs || !d_status || !d_ref_value || !d_distance))) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_gjk_distance: null argument", cudaSuccess);
     int32_t rc;
-    if ((rc = check_n(ctx, n))) return rc;
+    if ((rc = check_n(ctx, n)) || (rc = check_pairs_over(ctx, shapes, n))) return rc;
     if (n == 0) return BAM3D_OK;
     CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
-    ShapeSetDev S = view(shapes);
+    ShapeSetDev S = view(ctx, shapes);
     Plan plan = plan_for(ctx, shapes);
     BinScratch B; const BinScratch* pb;
     if ((rc = prepare_bins(ctx, plan, S, (const uint2*)d_pairs, (uint32_t)n, B, &pb))) return rc;
@@ -527,11 +554,13 @@ int32_t bam3d_gjk_time_of_impact_dev(bam3d_ctx* ctx, const bam3d_shapes* s0, con
                                      const bam3d_gjk_settings* settings, bam3d_contact* d_contacts, uint8_t* d_status) {
     if (!ctx || !s0 || !s1 || (n && (!d_pairs || !d_status || !d_contacts))) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_gjk_time_of_impact: null argument", cudaSuccess);
     if (s0->n != s1->n) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_gjk_time_of_impact: start/end shape sets differ in size", cudaSuccess);
+    if (s0->meshes != s1->meshes || std::memcmp(s0->kind_hist, s1->kind_hist, sizeof s0->kind_hist) != 0)
+        return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_gjk_time_of_impact: the end shape set must hold the same primitives (kinds, mesh library) as the start set", cudaSuccess);
     int32_t rc;
-    if ((rc = check_n(ctx, n))) return rc;
+    if ((rc = check_n(ctx, n)) || (rc = check_pairs_over(ctx, s0, n))) return rc;
     if (n == 0) return BAM3D_OK;
     CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
-    ShapeSetDev S0 = view(s0), S1 = view(s1);
+    ShapeSetDev S0 = view(ctx, s0), S1 = view(ctx, s1);
     Plan plan = plan_for(ctx, s0);
     BinScratch B; const BinScratch* pb;
     if ((rc = prepare_bins(ctx, plan, S0, (const uint2*)d_pairs, (uint32_t)n, B, &pb))) return rc;
@@ -575,8 +604,7 @@ int32_t bam3d_gjk_intersect(bam3d_ctx* ctx, const bam3d_shapes* shapes, const ui
     if ((rc = stage_pairs(ctx, pairs, n)) || (rc = ctx->status.reserve(ctx, n))) return rc;
     if ((rc = bam3d_gjk_intersect_dev(ctx, shapes, (const uint32_t*)ctx->pairs.ptr, n, settings, (uint8_t*)ctx->status.ptr))) return rc;
     CU_TRY(cudaMemcpyAsync(out_status, ctx->status.ptr, n, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(status)");
-    CU_TRY(cudaStreamSynchronize(ctx->stream), "bam3d_gjk_intersect");
-    return BAM3D_OK;
+    return take_index_flag(ctx, "bam3d_gjk_intersect");
 }
 
 int32_t bam3d_gjk_contact(bam3d_ctx* ctx, const bam3d_shapes* shapes, const uint32_t* pairs, uint64_t n,
@@ -591,8 +619,7 @@ int32_t bam3d_gjk_contact(bam3d_ctx* ctx, const bam3d_shapes* shapes, const uint
                                     (uint8_t*)ctx->status.ptr))) return rc;
     CU_TRY(cudaMemcpyAsync(out_contacts, ctx->contacts.ptr, n * 32, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(contacts)");
     CU_TRY(cudaMemcpyAsync(out_status, ctx->status.ptr, n, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(status)");
-    CU_TRY(cudaStreamSynchronize(ctx->stream), "bam3d_gjk_contact");
-    return BAM3D_OK;
+    return take_index_flag(ctx, "bam3d_gjk_contact");
 }
 
 int32_t bam3d_gjk_distance(bam3d_ctx* ctx, const bam3d_shapes* shapes, const uint32_t* pairs, uint64_t n,
@@ -608,8 +635,7 @@ int32_t bam3d_gjk_distance(bam3d_ctx* ctx, const bam3d_shapes* shapes, const uin
     CU_TRY(cudaMemcpyAsync(out_ref_value, ctx->f0.ptr, n * 4, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(ref)");
     CU_TRY(cudaMemcpyAsync(out_distance, ctx->f1.ptr, n * 4, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(dist)");
     CU_TRY(cudaMemcpyAsync(out_status, ctx->status.ptr, n, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(status)");
-    CU_TRY(cudaStreamSynchronize(ctx->stream), "bam3d_gjk_distance");
-    return BAM3D_OK;
+    return take_index_flag(ctx, "bam3d_gjk_distance");
 }
 
 // ---- ray casts against primitives ---------------------------------------------------------------
@@ -623,7 +649,7 @@ int32_t bam3d_ray_cast_dev(bam3d_ctx* ctx, const bam3d_shapes* shapes, const flo
     if (n == 0) return BAM3D_OK;
     CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
     { KernelTimer kt(ctx);
-      ctx->launches += launch_ray_cast(ctx->stream, view(shapes), d_rays, (const uint2*)d_casts, n, query, d_points, d_status); }
+      ctx->launches += launch_ray_cast(ctx->stream, view(ctx, shapes), d_rays, (const uint2*)d_casts, n, query, d_points, d_status); }
     return check_launch(ctx, "ray_cast_kernel");
 }
 
@@ -658,8 +684,7 @@ int32_t bam3d_gjk_time_of_impact(bam3d_ctx* ctx, const bam3d_shapes* s0, const b
                                            (uint8_t*)ctx->status.ptr))) return rc;
     CU_TRY(cudaMemcpyAsync(out_contacts, ctx->contacts.ptr, n * 32, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(contacts)");
     CU_TRY(cudaMemcpyAsync(out_status, ctx->status.ptr, n, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(status)");
-    CU_TRY(cudaStreamSynchronize(ctx->stream), "bam3d_gjk_time_of_impact");
-    return BAM3D_OK;
+    return take_index_flag(ctx, "bam3d_gjk_time_of_impact");
 }
 
 // ---- compound shapes (gjk/mod.rs:362-523) ----------------------------------------------------------------------
@@ -1099,7 +1124,7 @@ int32_t bam3d_sap_variance(bam3d_ctx* ctx, const float* aabbs, uint64_t n64, flo
 int32_t bam3d_shapes_world_aabbs_dev(bam3d_ctx* ctx, const bam3d_shapes* shapes, float* d_out6) {
     if (!ctx || !shapes || (shapes->n && !d_out6)) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_shapes_world_aabbs: null argument", cudaSuccess);
     CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
-    ctx->launches += launch_world_aabbs(ctx->stream, view(shapes), d_out6);
+    ctx->launches += launch_world_aabbs(ctx->stream, view(ctx, shapes), d_out6);
     return check_launch(ctx, "world_aabb_kernel");
 }
 int32_t bam3d_shapes_world_aabbs(bam3d_ctx* ctx, const bam3d_shapes* shapes, float* out6) {
@@ -1115,7 +1140,7 @@ int32_t bam3d_shapes_world_aabbs(bam3d_ctx* ctx, const bam3d_shapes* shapes, flo
 int32_t bam3d_shapes_world_spheres_dev(bam3d_ctx* ctx, const bam3d_shapes* shapes, float* d_out4) {
     if (!ctx || !shapes || (shapes->n && !d_out4)) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_shapes_world_spheres: null argument", cudaSuccess);
     CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
-    ctx->launches += launch_world_spheres(ctx->stream, view(shapes), (float4*)d_out4);
+    ctx->launches += launch_world_spheres(ctx->stream, view(ctx, shapes), (float4*)d_out4);
     return check_launch(ctx, "world_sphere_kernel");
 }
 int32_t bam3d_shapes_world_spheres(bam3d_ctx* ctx, const bam3d_shapes* shapes, float* out4) {
@@ -1506,6 +1531,7 @@ static int32_t frames_finish_slot(bam3d_ctx* ctx, bam3d_frames* F, bam3d_frames:
     if (sl.launch_rc) return sl.launch_rc;
     if (*sl.h_err & 1u) return b3_fail(ctx, BAM3D_ERR_NON_AFFINE, "a transform's 4th row is not (0,0,0,1)", cudaSuccess);
     if (*sl.h_err) return b3_fail(ctx, BAM3D_ERR_ARG, "pack_shapes_kernel rejected the frame's shapes", cudaSuccess);
+    if (sl.h_err[1] & 1u) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_frames: a pair of this frame names a shape index >= the shape set's size", cudaSuccess);
     return BAM3D_OK;
 }
 
@@ -1579,7 +1605,7 @@ int32_t bam3d_frames_create(bam3d_ctx* ctx, const uint8_t* kind, const float* pa
             bam3d_frames_free(ctx, F);
             return b3_fail(ctx, BAM3D_ERR_OOM, "bam3d_frames_create: device / pinned allocation", e);
         }
-        *sl.h_err = 0;
+        sl.h_err[0] = sl.h_err[1] = 0;
     }
     *out = F;
     return BAM3D_OK;
@@ -1621,7 +1647,9 @@ static int32_t frames_submit_impl(bam3d_ctx* ctx, bam3d_frames* F, int32_t query
     sl.launch_rc = BAM3D_OK;
     if (out_frame) *out_frame = sl.frame;
     // upload + pack on the copy-in stream
-    CU_TRY(cudaMemsetAsync(sl.d_err, 0, 4, F->s_in), "cudaMemsetAsync(err)");
+    CU_TRY(cudaMemsetAsync(sl.d_err, 0, 8, F->s_in), "cudaMemsetAsync(err)");  // [0] pack_shapes_kernel's flags, [1] pair-index flag
+    sl.shapes->err_flag = sl.d_err + 1;
+    if (sl.shapes_end) sl.shapes_end->err_flag = sl.d_err + 1;
     if (ns) {
         CU_TRY(cudaMemcpyAsync(sl.shapes->d_xform, xform, (size_t)ns * 64, cudaMemcpyHostToDevice, F->s_in), "cudaMemcpyAsync(xform)");
         ctx->launches += launch_pack_shapes(F->s_in, sl.shapes->d_kind, sl.shapes->d_params, sl.shapes->d_xform, sl.shapes->d_mesh_id, ns,
@@ -1659,7 +1687,7 @@ static int32_t frames_submit_impl(bam3d_ctx* ctx, bam3d_frames* F, int32_t query
     if (G) { sl.comm = G->comm; sl.lane = cc; sl.out_gathered = G->out; sl.out_capacity = G->capacity; sl.total = 0; }
     if (n && query != BAM3D_FRAME_INTERSECT && out_contacts) CU_TRY(cudaMemcpyAsync(out_contacts, sl.d_contacts, n * 32, cudaMemcpyDeviceToHost, F->s_out), "cudaMemcpyAsync(contacts)");
     if (n) CU_TRY(cudaMemcpyAsync(out_status, sl.d_status, n, cudaMemcpyDeviceToHost, F->s_out), "cudaMemcpyAsync(status)");
-    CU_TRY(cudaMemcpyAsync(sl.h_err, sl.d_err, 4, cudaMemcpyDeviceToHost, F->s_out), "cudaMemcpyAsync(err)");
+    CU_TRY(cudaMemcpyAsync(sl.h_err, sl.d_err, 8, cudaMemcpyDeviceToHost, F->s_out), "cudaMemcpyAsync(err)");
     CU_TRY(cudaEventRecord(sl.downloaded, F->s_out), "cudaEventRecord");
     sl.in_flight = true;
     return BAM3D_OK;

@@ -35,6 +35,8 @@ struct bam3d_ctx {
     int opt_bvh_strategy = 0;  // variable-length queries: 0 auto, 1 tree traversal, 2 all (query, value) tests
     cudaStream_t stream2 = nullptr;  // side stream (Variance3 runs beside the pair search)
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    uint32_t* d_flags = nullptr;   // device flag word of this ctx (bit 0: a pair named a shape index out of range)
+    uint32_t* h_flags = nullptr;   // pinned copy
     // opt-in timing of the dominant kernel of each narrow-phase call (CUDA events on the ctx stream)
     bool opt_timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_events;
@@ -71,6 +73,7 @@ struct bam3d_shapes {
     uint32_t n = 0;
     const bam3d_meshes* meshes = nullptr;
     uint32_t kind_hist[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint32_t* err_flag = nullptr;  // where the kernels flag an out-of-range pair index (null: the calling ctx's own word); frame slots set their own
 };
 
 int32_t b3_fail(bam3d_ctx* ctx, int32_t code, const char* what, cudaError_t e);

@@ -131,14 +131,15 @@ B3_DEV uint32_t pair_key(uint32_t ml, uint32_t mr) {
     return (kl == K_POLYHEDRON || kr == K_POLYHEDRON) ? KEY_WARP : kl * 7 + kr;
 }
 
-__global__ void __launch_bounds__(TPB) bin_hist_kernel(const uint32_t* __restrict__ meta, const uint2* __restrict__ pairs, uint32_t n,
+__global__ void __launch_bounds__(TPB) bin_hist_kernel(const uint32_t* __restrict__ meta, uint32_t n_shapes, const uint2* __restrict__ pairs, uint32_t n,
                                                        uint8_t* __restrict__ keys, uint32_t* __restrict__ hist) {
     __shared__ uint32_t sh[64];
     if (threadIdx.x < 64) sh[threadIdx.x] = 0;
     __syncthreads();
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         uint2 pr = __ldg(pairs + i);
-        uint32_t key = pair_key(__ldg(meta + pr.x), __ldg(meta + pr.y));
+        // (an out-of-range index is reported by the kernel that loads the shapes; here it only must not be dereferenced)
+        uint32_t key = pair_key(__ldg(meta + min(pr.x, n_shapes - 1)), __ldg(meta + min(pr.y, n_shapes - 1)));
         keys[i] = (uint8_t)key;
         atomicAdd(&sh[key], 1u);
     }
@@ -206,7 +207,12 @@ __device__ __forceinline__ void overflow_producer_exit(unsigned char* ovf_scratc
 // ------------------------------------------------------------------------------------------------------------
 // pair loading
 // ------------------------------------------------------------------------------------------------------------
+B3_DEV uint32_t checked_index(const ShapeSetDev& S, uint32_t idx) {
+    if (idx >= S.n) { atomicOr(S.err, 1u); idx = S.n - 1; }  // (the entry points refuse pairs over an empty shape set)
+    return idx;
+}
 B3_DEV void load_pair_shape(Shape& s, const ShapeSetDev& S, uint32_t idx) {
+    idx = checked_index(S, idx);
     load_shape(s, S.recs, idx);
     uint32_t m = __ldg(S.meta + idx);
     s.kind = m & 0xFF;
@@ -1078,8 +1084,8 @@ __global__ void __launch_bounds__(TPB) gjk_toi_kernel(ShapeSetDev S0, ShapeSetDe
             load_pair_shape(R0, S0, pr.y);
             // only the end transforms' affine columns are read (translation deltas; the right end transform's
             // rotation/scale for the contact point)
-            load_shape(L1, S1.recs, pr.x);
-            load_shape(R1, S1.recs, pr.y);
+            load_shape(L1, S1.recs, checked_index(S0, pr.x));
+            load_shape(R1, S1.recs, checked_index(S0, pr.y));
             st = gjk_time_of_impact<WARP>(L0, L1, R0, R1, cfg.continuous_tolerance, cfg.toi_iteration_cap, c, toi);
         }
         if (st != ST_OK) { c.normal = v3(0.f, 0.f, 0.f); c.depth = 0.f; c.point = v3(0.f, 0.f, 0.f); toi = 0.f; }
@@ -1130,12 +1136,12 @@ __global__ void __launch_bounds__(TPB) gjk_toi_refill_kernel(ShapeSetDev S0, Sha
                 } else {
                     p = order ? __ldg(order + begin + off) : begin + off;
                     const uint2 pr = __ldg(pairs + p);
-                    right_idx = pr.y;
+                    right_idx = checked_index(S0, pr.y);
                     load_pair_shape(L0, S0, pr.x);
                     load_pair_shape(R0, S0, pr.y);
                     Shape L1, R1;
-                    load_shape(L1, S1.recs, pr.x);
-                    load_shape(R1, S1.recs, pr.y);
+                    load_shape(L1, S1.recs, checked_index(S0, pr.x));
+                    load_shape(R1, S1.recs, right_idx);
                     const V3 left_lin_vel = shape_origin(L1) - shape_origin(L0);
                     const V3 right_lin_vel = shape_origin(R1) - shape_origin(R0);
                     ray = right_lin_vel - left_lin_vel;
@@ -1396,7 +1402,7 @@ int launch_mesh_face_planes(cudaStream_t st, const float4* d_verts, uint4* d_fac
 int launch_bin_pairs(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs, uint32_t n, const BinScratch& B) {
     cudaMemsetAsync(B.hist, 0, 64 * sizeof(uint32_t), st);
     int g = grid_for(n, TPB, NUM_SMS * 8);
-    bin_hist_kernel<<<g, TPB, 0, st>>>(S.meta, d_pairs, n, B.keys, B.hist);
+    bin_hist_kernel<<<g, TPB, 0, st>>>(S.meta, S.n, d_pairs, n, B.keys, B.hist);
     bin_scan_kernel<<<1, 32, 0, st>>>(B.hist, B.start, B.cursor, B.ranges, n);
     bin_scatter_kernel<<<g, TPB, 0, st>>>(B.keys, n, B.cursor, B.order);
     return 3;
@@ -1427,6 +1433,15 @@ static int persistent_grid(const void* kernel) {
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TPB, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
     return per_sm * NUM_SMS;
 }
+// Function attributes and occupancy answers belong to a device: cache them per device ordinal (a process may drive several).
+constexpr int MAX_DEVICES = 64;
+static int current_device_slot() { int d = 0; cudaGetDevice(&d); return (d >= 0 && d < MAX_DEVICES) ? d : 0; }
+template <class K>
+static int persistent_grid_cached(K kernel, int (&cache)[MAX_DEVICES]) {
+    int& g = cache[current_device_slot()];
+    if (!g) g = persistent_grid((const void*)kernel);
+    return g;
+}
 
 int launch_intersect(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs, uint32_t n, const BinScratch* B, bool run_thread,
                      bool run_warp, const SettingsDev& cfg, void* d_scratch, int refill_min, uint8_t* d_status) {
@@ -1437,7 +1452,8 @@ int launch_intersect(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs
     if (run_thread) {
 #ifdef B3_EXPERIMENTS
         if (d_scratch && refill_min > 0) {
-            static const int grid = persistent_grid((const void*)gjk_intersect_refill_kernel);
+            static int grid_cache[MAX_DEVICES];
+            const int grid = persistent_grid_cached(gjk_intersect_refill_kernel, grid_cache);
             cudaMemsetAsync(d_scratch, 0, 4, st);
             gjk_intersect_refill_kernel<<<grid, TPB, 0, st>>>(S, d_pairs, n, order, ranges, cfg, reinterpret_cast<uint32_t*>(d_scratch),
                                                               refill_min > 32 ? 32 : refill_min, d_status);
@@ -1469,7 +1485,8 @@ size_t contact_queue_bytes(uint32_t n) {
 }
 
 static int epa_refill_grid() {
-    static int blocks = 0;
+    static int blocks_per_device[MAX_DEVICES];
+    int& blocks = blocks_per_device[current_device_slot()];
     if (!blocks) {
         int per_sm = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, epa_refill_kernel<true, false>, TPB, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
@@ -1542,7 +1559,8 @@ int launch_contact(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs, 
     int launched = 0;
     const uint32_t* order = B ? B->order : nullptr;
     const uint32_t* ranges = B ? B->ranges : nullptr;
-    static bool smem_opt_in = false;
+    static bool smem_opt_in_per_device[MAX_DEVICES];
+    bool& smem_opt_in = smem_opt_in_per_device[current_device_slot()];
     if (!smem_opt_in) {
         cudaFuncSetAttribute(gjk_contact_overflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EPA_BIG_SMEM_BYTES);
 #ifdef B3_EXPERIMENTS
@@ -1645,7 +1663,8 @@ int launch_distance(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs,
         const uint32_t* ranges = B ? B->ranges : nullptr;
         int launched = 1;
         cudaMemsetAsync(d_cursor, 0, 4, st);
-        static const int grid = persistent_grid((const void*)gjk_distance_refill_kernel);
+        static int grid_cache[MAX_DEVICES];
+        const int grid = persistent_grid_cached(gjk_distance_refill_kernel, grid_cache);
         gjk_distance_refill_kernel<<<grid, TPB, 0, st>>>(S, d_pairs, n, order, ranges, cfg, reinterpret_cast<uint32_t*>(d_cursor),
                                                          refill_min < 1 ? 1 : (refill_min > 32 ? 32 : refill_min), d_ref, d_geo, d_status);
         if (run_warp) { gjk_distance_kernel<true><<<warp_grid(n), TPB, 0, st>>>(S, d_pairs, n, order, ranges, cfg, d_ref, d_geo, d_status); ++launched; }
@@ -1661,7 +1680,8 @@ int launch_toi(cudaStream_t st, const ShapeSetDev& S0, const ShapeSetDev& S1, co
         const uint32_t* ranges = B ? B->ranges : nullptr;
         int launched = 1;
         cudaMemsetAsync(d_cursor, 0, 4, st);
-        static const int grid = persistent_grid((const void*)gjk_toi_refill_kernel);
+        static int grid_cache[MAX_DEVICES];
+        const int grid = persistent_grid_cached(gjk_toi_refill_kernel, grid_cache);
         gjk_toi_refill_kernel<<<grid, TPB, 0, st>>>(S0, S1, d_pairs, n, order, ranges, cfg, reinterpret_cast<uint32_t*>(d_cursor),
                                                                  refill_min < 1 ? 1 : (refill_min > 32 ? 32 : refill_min), d_contacts, d_status);
         if (run_warp) { gjk_toi_kernel<true><<<warp_grid(n), TPB, 0, st>>>(S0, S1, d_pairs, n, order, ranges, cfg, d_contacts, d_status); ++launched; }

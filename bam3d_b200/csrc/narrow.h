@@ -14,6 +14,8 @@ struct ShapeSetDev {
     const float4* mesh_verts;      // polyhedron vertices (xyz, w unused)
     const uint32_t* mesh_offsets;  // n_meshes + 1
     uint32_t n;
+    uint32_t* err;                 // device flag word: bit 0 is raised by a pair that names a shape index >= n (the index is clamped, so
+                                   // the kernels never read out of bounds; the entry points turn the flag into BAM3D_ERR_ARG)
 };
 
 struct SettingsDev {

@@ -409,6 +409,60 @@ def test_edge_cases(ctx, oracle):
         g3.intersection_batch(b3.CollisionStrategy.FullResolution, shapes, scene["pairs"])
 
 
+def test_out_of_range_pair_indices_are_an_error_not_a_fault(ctx, oracle):
+    """A pair that names a shape index >= the set's size must come back as BAM3D_ERR_ARG from every narrow-phase entry point —
+    host buffers, frame queue, and (at the next bam3d_ctx_synchronize) device pointers — and must leave the CUDA context alive:
+    the kernels clamp the index and raise a flag instead of reading out of bounds. The calls after it work as before."""
+    import ctypes as C
+    scene = scenes.mixed_pairs(2_000, s=1.5)
+    shapes = shapes_of(ctx, scene)
+    gjk = b3.GJK.new(ctx)
+    good_c, good_st = gjk.intersection_batch(b3.CollisionStrategy.FullResolution, shapes, scene["pairs"])
+    bad = scene["pairs"].copy()
+    bad[1234, 1] = len(scene["kind"]) + 5
+    x1 = scenes.end_transforms(scene)
+    shapes_end = shapes_of(ctx, scene, x1)
+    calls = (lambda: gjk.intersect_batch(shapes, bad), lambda: gjk.intersection_batch(b3.CollisionStrategy.FullResolution, shapes, bad),
+             lambda: gjk.distance_batch(shapes, bad), lambda: gjk.intersection_time_of_impact_batch(shapes, shapes_end, bad))
+    for call in calls:
+        with pytest.raises(b3.Bam3dError) as ei:
+            call()
+        assert ei.value.code == b3.ERR_ARG
+    c, st = gjk.intersection_batch(b3.CollisionStrategy.FullResolution, shapes, scene["pairs"])
+    assert np.array_equal(st, good_st) and c.tobytes() == good_c.tobytes()
+    # device pointers: the flag surfaces at the next synchronize, once
+    import torch
+    d_pairs = torch.from_numpy(np.ascontiguousarray(bad, dtype=np.uint32).view(np.int32).reshape(-1)).cuda()
+    d_status = torch.empty(len(bad), dtype=torch.uint8, device="cuda")
+    gjk.intersect_dev(shapes, C.c_void_p(d_pairs.data_ptr()), len(bad), C.c_void_p(d_status.data_ptr()))
+    with pytest.raises(b3.Bam3dError) as ei:
+        ctx.synchronize()
+    assert ei.value.code == b3.ERR_ARG
+    ctx.synchronize()   # reported once
+    # frame queue
+    n_sh, n_pr = len(scene["kind"]), len(bad)
+    fq = b3.FrameQueue(gjk, scene["kind"], scene["params"], scene["xform"], max_pairs=n_pr, depth=2)
+    hx = np.ascontiguousarray(scene["xform"], dtype=np.float32).reshape(n_sh, 16)
+    hc, hs = b3.pinned_empty(ctx, (n_pr, 8), np.float32), b3.pinned_empty(ctx, (n_pr,), np.uint8)
+    f_bad = fq.submit_contact(b3.CollisionStrategy.FullResolution, hx, np.ascontiguousarray(bad, dtype=np.uint32), hc, hs)
+    hc2, hs2 = b3.pinned_empty(ctx, (n_pr, 8), np.float32), b3.pinned_empty(ctx, (n_pr,), np.uint8)
+    f_ok = fq.submit_contact(b3.CollisionStrategy.FullResolution, hx, np.ascontiguousarray(scene["pairs"], dtype=np.uint32), hc2, hs2)
+    with pytest.raises(b3.Bam3dError) as ei:
+        fq.wait(f_bad)
+    assert ei.value.code == b3.ERR_ARG
+    fq.wait(f_ok)
+    assert np.array_equal(hs2, good_st) and hc2.tobytes() == good_c.tobytes()
+    fq.close()
+    # a time-of-impact end set that does not hold the same primitives is refused up front
+    other = scenes.all_kinds_pairs(2_000, s=1.5)
+    with pytest.raises(b3.Bam3dError):
+        gjk.intersection_time_of_impact_batch(shapes, shapes_of(ctx, other), scene["pairs"])
+    # pairs over an empty shape set
+    empty = b3.ShapeSet(ctx, np.zeros(0, np.uint8), np.zeros((0, 4), np.float32), np.zeros((0, 16), np.float32))
+    with pytest.raises(b3.Bam3dError):
+        gjk.intersect_batch(empty, [[0, 0]])
+
+
 def test_compound_shapes_parity(ctx, oracle):
     """a10: intersection_complex / distance_complex / intersection_complex_time_of_impact (gjk/mod.rs:362-523): all
     primitive x primitive combinations on the GPU, composed with Mat4::mul_mat4, then the reference's reductions
