@@ -174,6 +174,7 @@ int32_t bam3d_ctx_create(int32_t device_ordinal, bam3d_ctx** out_ctx) {
     if (const char* e = std::getenv("BAM3D_INTERSECT_REFILL")) ctx->opt_intersect_refill = std::atoi(e);
 #endif
     if (const char* e = std::getenv("BAM3D_EPA_OVERLAP")) ctx->opt_epa_overlap = std::atoi(e) != 0;
+    if (const char* e = std::getenv("BAM3D_EPA_HUGE")) ctx->opt_epa_huge = std::atoi(e) != 0;
     if (const char* e = std::getenv("BAM3D_EPA_GLOBAL")) ctx->opt_epa_global_polytopes = std::atoi(e) != 0;
     if (const char* e = std::getenv("BAM3D_TOI_REFILL")) ctx->opt_toi_refill = std::atoi(e);
     if (const char* e = std::getenv("BAM3D_DISTANCE_REFILL")) ctx->opt_distance_refill = std::atoi(e);
@@ -221,6 +222,7 @@ int32_t bam3d_ctx_set_option(bam3d_ctx* ctx, const char* name, int32_t value) {
 #endif
     if (!std::strcmp(name, "epa_tiers")) { ctx->opt_epa_tiers = value != 0; return BAM3D_OK; }
     if (!std::strcmp(name, "epa_pipeline")) { ctx->opt_epa_pipeline = value != 0; return BAM3D_OK; }
+    if (!std::strcmp(name, "epa_huge")) { ctx->opt_epa_huge = value != 0; return BAM3D_OK; }
     if (!std::strcmp(name, "epa_overlap")) { ctx->opt_epa_overlap = value != 0; return BAM3D_OK; }
     if (!std::strcmp(name, "epa_global_polytopes")) { ctx->opt_epa_global_polytopes = value != 0; return BAM3D_OK; }
     if (!std::strcmp(name, "intersect_split")) { ctx->opt_intersect_split = value != 0; return BAM3D_OK; }
@@ -520,10 +522,15 @@ int32_t bam3d_gjk_contact_dev(bam3d_ctx* ctx, const bam3d_shapes* shapes, const 
           if ((rc = ctx->epa_slab.reserve(ctx, contact_poly_slab_bytes()))) return rc;
           poly_slab = ctx->epa_slab.ptr;
       }
+      void* huge_slab = nullptr;
+      if (ctx->opt_epa_huge && strategy == BAM3D_FULL_RESOLUTION) {
+          if ((rc = ctx->epa_huge.reserve(ctx, contact_huge_slab_bytes()))) return rc;
+          huge_slab = ctx->epa_huge.ptr;
+      }
       uint32_t default_key = 0;
       for (uint32_t k = 0; k < 6; ++k) if (shapes->kind_hist[k]) default_key = k * 7 + k;
       ctx->launches += launch_contact(ctx->stream, S, (const uint2*)d_pairs, (uint32_t)n, pb, plan.run_thread, plan.run_warp, cfg, strategy,
-                                      default_key, ctx->opt_epa_tiers ? 1 : 0, ctx->opt_epa_pipeline, ctx->opt_epa_overlap ? &side : nullptr, poly_slab, ctx->epa_overflow.ptr, ctx->epa_queue.ptr, (float4*)d_contacts,
+                                      default_key, ctx->opt_epa_tiers ? 1 : 0, ctx->opt_epa_pipeline, ctx->opt_epa_overlap ? &side : nullptr, poly_slab, ctx->epa_overflow.ptr, huge_slab, ctx->epa_queue.ptr, (float4*)d_contacts,
                                       d_status); }
     return check_launch(ctx, "gjk_contact_kernel");
 }
@@ -1503,7 +1510,7 @@ static bam3d_ctx* frames_lane(bam3d_ctx* ctx, bam3d_frames* F, uint64_t frame) {
     c->opt_binning = ctx->opt_binning; c->opt_epa_tiers = ctx->opt_epa_tiers; c->opt_intersect_split = ctx->opt_intersect_split;
     c->opt_intersect_refill = ctx->opt_intersect_refill; c->opt_toi_refill = ctx->opt_toi_refill;
     c->opt_epa_global_polytopes = ctx->opt_epa_global_polytopes; c->opt_epa_overlap = ctx->opt_epa_overlap;
-    c->opt_distance_refill = ctx->opt_distance_refill; c->opt_epa_pipeline = ctx->opt_epa_pipeline;
+    c->opt_distance_refill = ctx->opt_distance_refill; c->opt_epa_pipeline = ctx->opt_epa_pipeline; c->opt_epa_huge = ctx->opt_epa_huge;
     c->opt_timing = false;
     return c;
 }

@@ -30,6 +30,7 @@ struct bam3d_ctx {
     int opt_distance_refill = 8;  // distance, thread path: the same lane-refill scheme (gjk_distance_refill_kernel); 0 = one pair per thread
     bool opt_epa_global_polytopes = true;   // thread-per-pair EPA: polytopes in a global slab (contiguous per thread) instead of local memory
     bool opt_epa_pipeline = false;  // thread-per-pair EPA: cp.async face ring + batched walk / moves / new faces (epa_pipe.cuh); 0 = epa.cuh's iteration
+    bool opt_epa_huge = true;  // contact path: pairs whose polytope outgrows the 1024-face overflow tier go to the block-per-pair tier (epa_huge.cuh, 2^18 faces) instead of ending as BAM3D_STATUS_CAPACITY
     bool opt_epa_overlap = true;  // contact path: run the EPA overflow tier on the side stream next to the EPA kernel
     int opt_sap_strategy = 0;  // 0 auto, 1 tiled sweep, 2 BVH overlap query
     int opt_bvh_strategy = 0;  // variable-length queries: 0 auto, 1 tree traversal, 2 all (query, value) tests
@@ -41,11 +42,11 @@ struct bam3d_ctx {
     bool opt_timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_events;
     // scratch for the host-buffer entry points and the binning pass
-    DevBuf pairs, status, contacts, f0, f1, keys, order, small, epa_overflow, epa_queue, epa_slab;
+    DevBuf pairs, status, contacts, f0, f1, keys, order, small, epa_overflow, epa_queue, epa_slab, epa_huge;
     // broad-phase scratch
     DevBuf bp0, bp1, bp2, bp3, bp4, bp5, bp6, bp7, cub_tmp, sph0, sph1, sph2, pipe0, pipe1, pipe2, pipe3;
     void release_scratch() {
-        DevBuf* all[] = {&pairs, &status, &contacts, &f0, &f1, &keys, &order, &small, &epa_overflow, &epa_queue, &epa_slab, &bp0, &bp1, &bp2, &bp3, &bp4, &bp5, &bp6, &bp7, &cub_tmp, &sph0, &sph1, &sph2, &pipe0, &pipe1, &pipe2, &pipe3};
+        DevBuf* all[] = {&pairs, &status, &contacts, &f0, &f1, &keys, &order, &small, &epa_overflow, &epa_queue, &epa_slab, &epa_huge, &bp0, &bp1, &bp2, &bp3, &bp4, &bp5, &bp6, &bp7, &cub_tmp, &sph0, &sph1, &sph2, &pipe0, &pipe1, &pipe2, &pipe3};
         for (DevBuf* b : all) b->release();
     }
 };

@@ -15,6 +15,7 @@
 #include "narrow.h"
 #include "gjk.cuh"
 #include "epa_big.cuh"
+#include "epa_huge.cuh"
 #ifdef B3_EXPERIMENTS
 #include "epa_pipe.cuh"
 #endif
@@ -33,6 +34,9 @@ constexpr uint32_t OVF_MAX = 65536;  // capacity of the EPA overflow list; pairs
 // [2] = "every producer kernel has finished", [3] = producer blocks that have exited; entries (pair indices) from
 // byte 256, preset to 0xFFFFFFFF so that a consumer that reserved a position can wait for its value to land.
 constexpr int OVF_COUNT = 0, OVF_CURSOR = 1, OVF_DONE = 2, OVF_EXITED = 3;
+// third tier (epa_huge.cuh): [4] = pairs the overflow tier could not finish either, [5] = consumer cursor; entries behind the overflow list
+constexpr int HUGE_COUNT = 4, HUGE_CURSOR = 5;
+constexpr uint32_t HUGE_MAX = 4096;
 
 // ------------------------------------------------------------------------------------------------------------
 // pack_shapes: Mat4 (16 f32, column-major) + params -> 96-byte ShapeRec with the inverse's linear part.
@@ -796,7 +800,7 @@ constexpr size_t TIER_VA_BYTES = 0;
 // ST_CAPACITY to a device list; one warp per listed pair redoes GJK + EPA against a per-warp global-memory slab.
 // Rare (~6e-5 of mixed pairs), but those pairs are the long tail of the reference's cost.
 constexpr int OVF_WARPS = NUM_SMS;        // one 32-thread block per SM
-constexpr size_t OVF_HEADER_BYTES = 256 + (size_t)OVF_MAX * 4;
+constexpr size_t OVF_HEADER_BYTES = 256 + (size_t)OVF_MAX * 4 + (size_t)HUGE_MAX * 4;
 
 __global__ void __launch_bounds__(32) gjk_contact_overflow_kernel(ShapeSetDev S, const uint2* __restrict__ pairs, SettingsDev cfg,
                                                                   unsigned char* __restrict__ scratch, int producers_running,
@@ -851,8 +855,57 @@ __global__ void __launch_bounds__(32) gjk_contact_overflow_kernel(ShapeSetDev S,
             contacts[2 * (size_t)p] = make_float4(c.normal.x, c.normal.y, c.normal.z, c.depth);
             contacts[2 * (size_t)p + 1] = make_float4(c.point.x, c.point.y, c.point.z, 0.f);
             status[p] = st;
+            if (st == ST_CAPACITY) {  // more than EPA_BIG_FCAP faces: the block-per-pair tier takes it (launched behind this kernel)
+                const uint32_t slot = atomicAdd(hdr + HUGE_COUNT, 1u);
+                if (slot < HUGE_MAX) reinterpret_cast<uint32_t*>(scratch + 256 + (size_t)OVF_MAX * 4)[slot] = p;
+            }
         }
         __syncwarp();
+    }
+}
+
+// Third tier (epa_huge.cuh): one block per listed pair, launched behind the overflow kernel (the list is final by then).
+__global__ void __launch_bounds__(HUGE_THREADS) gjk_contact_huge_kernel(ShapeSetDev S, const uint2* __restrict__ pairs, SettingsDev cfg,
+                                                                        unsigned char* __restrict__ scratch, unsigned char* __restrict__ slab,
+                                                                        float4* __restrict__ contacts, uint8_t* __restrict__ status) {
+    __shared__ HugeShared sh;
+    __shared__ uint32_t s_item;
+    __shared__ uint8_t s_st;
+    uint32_t* hdr = reinterpret_cast<uint32_t*>(scratch);
+    const uint32_t* list = reinterpret_cast<const uint32_t*>(scratch + 256 + (size_t)OVF_MAX * 4);
+    const uint32_t count = min(hdr[HUGE_COUNT], HUGE_MAX);
+    if (count == 0) return;
+    const HugeStore H = carve_huge_store(slab + (size_t)blockIdx.x * HUGE_SLAB_BYTES);
+    for (;;) {
+        if (threadIdx.x == 0) s_item = atomicAdd(hdr + HUGE_CURSOR, 1u);
+        __syncthreads();
+        const uint32_t i = s_item;
+        if (i >= count) break;
+        const uint32_t p = list[i];
+        const uint2 pr = __ldg(pairs + p);
+        Shape L, R;
+        load_pair_shape(L, S, pr.x);
+        load_pair_shape(R, S, pr.y);
+        Simplex<true> s;
+        s.n = 0;
+        if (threadIdx.x < 32) {
+            const uint8_t st0 = gjk_intersect<true, true>(L, R, cfg.max_iterations, s);
+            if (threadIdx.x == 0) s_st = st0;
+        }
+        __syncthreads();
+        uint8_t st = s_st;
+        ContactOut c;
+        c.normal = v3(0.f, 0.f, 0.f); c.depth = 0.f; c.point = v3(0.f, 0.f, 0.f);
+        if (st == ST_OK) {
+            st = epa_process_huge(L, R, s, cfg.epa_tolerance, cfg.max_iterations, H, sh, c);
+            if (st != ST_OK) { c.normal = v3(0.f, 0.f, 0.f); c.depth = 0.f; c.point = v3(0.f, 0.f, 0.f); }
+        }
+        if (threadIdx.x == 0) {
+            contacts[2 * (size_t)p] = make_float4(c.normal.x, c.normal.y, c.normal.z, c.depth);
+            contacts[2 * (size_t)p + 1] = make_float4(c.point.x, c.point.y, c.point.z, 0.f);
+            status[p] = st;
+        }
+        __syncthreads();
     }
 }
 
@@ -1478,6 +1531,7 @@ int launch_intersect(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs
 }
 size_t contact_poly_slab_bytes() { return (size_t)NUM_SMS * B3_EPA_BLOCKS * TPB * (EPA_PIPE_SLAB_BYTES > EPA_SLAB_BYTES ? EPA_PIPE_SLAB_BYTES : EPA_SLAB_BYTES); }
 size_t contact_overflow_scratch_bytes() { return OVF_HEADER_BYTES + (size_t)OVF_WARPS * EPA_BIG_SLAB_BYTES; }
+size_t contact_huge_slab_bytes() { return (size_t)HUGE_BLOCKS * HUGE_SLAB_BYTES; }
 // header | n GJK->EPA records | 3 promotion lists of n record indices | sup_a scratch of the shared-memory EPA warps
 static size_t queue_lists_bytes(uint32_t n) { return ((size_t)n * 12 + 15) & ~(size_t)15; }
 size_t contact_queue_bytes(uint32_t n) {
@@ -1552,7 +1606,7 @@ static BinOrder epa_bin_order() {
 
 int launch_contact(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs, uint32_t n, const BinScratch* B, bool run_thread,
                    bool run_warp, const SettingsDev& cfg, int strategy, uint32_t default_key, int epa_mode, bool epa_pipeline, const ContactSide* side,
-                   void* d_poly_slab, void* d_overflow_scratch, void* d_queue, float4* d_contacts, uint8_t* d_status) {
+                   void* d_poly_slab, void* d_overflow_scratch, void* d_huge_slab, void* d_queue, float4* d_contacts, uint8_t* d_status) {
     unsigned char* ovf = reinterpret_cast<unsigned char*>(d_overflow_scratch);
     unsigned char* queue = reinterpret_cast<unsigned char*>(d_queue);
     if (n == 0) return 0;
@@ -1647,10 +1701,12 @@ int launch_contact(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs, 
             // launched AFTER the producer (a tool that serialises kernels then still runs them in a terminating order)
             cudaStreamWaitEvent(side->stream, side->fork, 0);
             gjk_contact_overflow_kernel<<<OVF_WARPS, 32, EPA_BIG_SMEM_BYTES, side->stream>>>(S, d_pairs, cfg, ovf, 1, d_contacts, d_status);
+            if (d_huge_slab) { gjk_contact_huge_kernel<<<HUGE_BLOCKS, HUGE_THREADS, 0, side->stream>>>(S, d_pairs, cfg, ovf, reinterpret_cast<unsigned char*>(d_huge_slab), d_contacts, d_status); ++launched; }
             cudaEventRecord(side->join, side->stream);
             cudaStreamWaitEvent(st, side->join, 0);
         } else {
             gjk_contact_overflow_kernel<<<OVF_WARPS, 32, EPA_BIG_SMEM_BYTES, st>>>(S, d_pairs, cfg, ovf, 0, d_contacts, d_status);
+            if (d_huge_slab) { gjk_contact_huge_kernel<<<HUGE_BLOCKS, HUGE_THREADS, 0, st>>>(S, d_pairs, cfg, ovf, reinterpret_cast<unsigned char*>(d_huge_slab), d_contacts, d_status); ++launched; }
         }
         ++launched;
     }

@@ -60,7 +60,11 @@ size_t contact_queue_bytes(uint32_t n);
 struct ContactSide { cudaStream_t stream; cudaEvent_t fork, join; };
 int launch_contact(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs, uint32_t n, const BinScratch* B,
                    bool run_thread, bool run_warp, const SettingsDev& cfg, int strategy, uint32_t default_key, int epa_mode,
-                   bool epa_pipeline, const ContactSide* side, void* d_poly_slab, void* d_overflow_scratch, void* d_queue, float4* d_contacts, uint8_t* d_status);
+                   bool epa_pipeline, const ContactSide* side, void* d_poly_slab, void* d_overflow_scratch, void* d_huge_slab, void* d_queue, float4* d_contacts,
+                   uint8_t* d_status);
+// d_huge_slab (nullable): contact_huge_slab_bytes() for the third EPA tier (epa_huge.cuh: polytopes beyond 1024 faces, one block per pair);
+// without it such pairs keep BAM3D_STATUS_CAPACITY.
+size_t contact_huge_slab_bytes();
 // d_poly_slab (nullable): contact_poly_slab_bytes() of device memory; when given, the thread-per-pair EPA keeps its polytopes
 // there (one contiguous record per thread) instead of in per-thread local memory.
 size_t contact_poly_slab_bytes();

@@ -397,13 +397,12 @@ inline void remove_or_add_edge(std::vector<std::pair<uint32_t, uint32_t>>& edges
     edges.push_back(edge);
 }
 
-// The reference's Vecs are unbounded, and on near-degenerate input (e.g. a Particle inside a Cylinder: the cap's
-// rim supports are coplanar, visibility becomes rounding noise) its face list grows multiplicatively per
-// iteration — the reference itself then effectively hangs / exhausts memory. The oracle therefore stops a pair
-// whose polytope would exceed these capacities and reports Status::Capacity; the GPU path uses the same numbers
-// (EPA_BIG_FCAP in bam3d_b200/csrc/epa_big.cuh) for its overflow tier, so both report the same pairs.
-constexpr size_t EPA_FACE_LIMIT = 1024;                 // ~5x the 202 faces a valid 103-vertex polytope can have
-constexpr size_t EPA_EDGE_LIMIT = 3 * EPA_FACE_LIMIT;    // 3 edges per removed face: can never trigger first
+// The reference's Vecs are unbounded. On near-degenerate input (a Cylinder cap against a flat face: the cap's rim supports are
+// coplanar, visibility becomes rounding noise) its polytope pinches and the face list grows multiplicatively per iteration: 44 of
+// 2^20 mixed pairs pass 1024 faces, the largest reaches 121 962 — and the reference still returns a Contact after at most
+// max_iterations trips. The limit below is the capacity of the device's largest tier (HUGE_FCAP, bam3d_b200/csrc/epa_huge.cuh);
+// a pair that would pass it ends as Status::Capacity on both sides (none is known). EPA3::face_limit can be set per run.
+constexpr size_t EPA_FACE_LIMIT = (size_t)1 << 18;
 
 struct Polytope {  // epa3d.rs:97-150
     std::vector<SupportPoint>& vertices;
@@ -439,7 +438,6 @@ struct Polytope {  // epa3d.rs:97-150
                 ++removed;
                 for (int e = 0; e < 3; ++e) {
                     remove_or_add_edge(edges, {face.vertices[e], face.vertices[(e + 1) % 3]});
-                    if (edges.size() > 3 * face_limit) { overflow = true; return; }
                 }
                 if (edges.size() > max_edges) max_edges = (uint32_t)edges.size();
             } else {
@@ -447,6 +445,81 @@ struct Polytope {  // epa3d.rs:97-150
             }
         }
         if (faces.size() + edges.size() > face_limit) { overflow = true; return; }
+        uint32_t n = (uint32_t)vertices.size();
+        vertices.push_back(sup);
+        for (auto& e : edges) faces.push_back(Face::new_impl(vertices, n, e.first, e.second));
+    }
+
+    // The same Polytope::add written the way the device's large-polytope tier evaluates it (bam3d_b200/csrc/epa_huge.cuh): no
+    // sequential walk, only prefix sums, scatters and short per-key scans — each phase is data parallel. Executed sequentially
+    // here; tests/test_host_cpu.py checks that it builds the same face list, in the same order, as add() above.
+    //   visibility flags -> exclusive prefix counts -> S = survivors. The walk `while i < len { if visible(i) swap_remove(i) else
+    //   i++ }` is a two-pointer process: holes (visible positions below S, ascending: h_1 < h_2 < ...) are filled by the tail
+    //   survivors (non-visible positions >= S) taken from the back (t_1 > t_2 > ...), and the visible faces are REMOVED in the
+    //   order h_1, [visible positions in (t_1, F) descending], h_2, [visible in (t_2, t_1) descending], ..., and finally, if
+    //   positions remain between S and the last tail survivor taken, S itself followed by the rest of them descending.
+    //   The horizon list is the sequence of directed edges of the removed faces in that order under remove_or_add_edge; per
+    //   undirected edge that is a first-in-first-out matching of the two directions, so the survivors can be found per edge and
+    //   then compacted in sequence order.
+    void add_in_phases(const SupportPoint& sup) {
+        const size_t F = faces.size();
+        std::vector<uint8_t> vis(F);
+        for (size_t i = 0; i < F; ++i) vis[i] = dot(faces[i].normal, sup.v - vertices[faces[i].vertices[0]].v) > 0.f ? 1 : 0;
+        std::vector<uint32_t> before(F + 1, 0);  // visible positions < p
+        for (size_t i = 0; i < F; ++i) before[i + 1] = before[i] + vis[i];
+        const uint32_t V = before[F];
+        const size_t S = F - V;
+        auto vis_after = [&](size_t p) { return V - before[p] - vis[p]; };           // visible positions > p
+        auto surv_after = [&](size_t p) { return (uint32_t)(F - 1 - p) - vis_after(p); };  // survivors at positions > p
+        const uint32_t Hn = before[S];  // holes below S == tail survivors
+        std::vector<uint32_t> tsrc(Hn + 2, (uint32_t)F);  // tsrc[k] = position of the k-th tail survivor from the back; tsrc[0] = F
+        for (size_t p = S; p < F; ++p) if (!vis[p]) tsrc[surv_after(p) + 1] = (uint32_t)p;
+        const uint32_t t_last = Hn ? tsrc[Hn] : (uint32_t)F;
+        // removal order
+        std::vector<uint32_t> order(V);
+        for (size_t p = 0; p < F; ++p) {
+            if (!vis[p]) continue;
+            uint32_t idx;
+            if (p < S) {  // hole h_k
+                const uint32_t k = before[p] + 1;
+                idx = (k - 1) + (k >= 2 ? vis_after(tsrc[k - 1]) : 0u);
+            } else {
+                const uint32_t s = surv_after(p);
+                if (s < Hn) idx = (s + 1) + vis_after(p);                  // pulled in while hole h_(s+1) was being filled
+                else if (p == S) idx = Hn + vis_after(t_last == F ? F - 1 : t_last) + (t_last == F ? 0u : 0u);
+                else idx = Hn + 1 + vis_after(p);
+            }
+            order[idx] = (uint32_t)p;
+        }
+        // directed edge events in removal order, then the first-in-first-out matching per undirected edge
+        struct Ev { uint32_t a, b; };
+        std::vector<Ev> ev(3 * (size_t)V);
+        for (uint32_t i = 0; i < V; ++i) {
+            const Face& f = faces[order[i]];
+            for (int e = 0; e < 3; ++e) ev[3 * (size_t)i + e] = {f.vertices[e], f.vertices[(e + 1) % 3]};
+        }
+        std::vector<uint8_t> keep(ev.size(), 0);
+        std::map<std::pair<uint32_t, uint32_t>, std::vector<uint32_t>> by_edge;  // undirected key -> event indices, in sequence order
+        for (uint32_t i = 0; i < ev.size(); ++i) by_edge[{std::min(ev[i].a, ev[i].b), std::max(ev[i].a, ev[i].b)}].push_back(i);
+        for (auto& kv : by_edge) {
+            std::vector<uint32_t> live;  // events of one direction currently in the list, oldest first
+            size_t head = 0;
+            bool live_forward = true;
+            for (uint32_t i : kv.second) {
+                const bool forward = ev[i].a <= ev[i].b;
+                if (head < live.size() && forward != live_forward) { keep[live[head]] = 0; ++head; }  // removes the oldest reversed copy
+                else { if (head == live.size()) { live.clear(); head = 0; live_forward = forward; } live.push_back(i); keep[i] = 1; }
+            }
+        }
+        std::vector<std::pair<uint32_t, uint32_t>> edges;
+        for (uint32_t i = 0; i < ev.size(); ++i) if (keep[i]) edges.emplace_back(ev[i].a, ev[i].b);
+        if (edges.size() > max_edges) max_edges = (uint32_t)edges.size();
+        removed += V;
+        if (S + edges.size() > face_limit) { overflow = true; return; }
+        // survivors: positions below S stay, holes take the tail survivors from the back
+        std::vector<Face> next(S);
+        for (size_t p = 0; p < S; ++p) next[p] = vis[p] ? faces[tsrc[before[p] + 1]] : faces[p];
+        faces.swap(next);
         uint32_t n = (uint32_t)vertices.size();
         vertices.push_back(sup);
         for (auto& e : edges) faces.push_back(Face::new_impl(vertices, n, e.first, e.second));
@@ -472,6 +545,7 @@ struct EPA3 {  // epa3d.rs:9-67; constants epa/mod.rs:12-13
     float tolerance = 0.00001f;
     uint32_t max_iterations = 100;
     size_t face_limit = EPA_FACE_LIMIT;  // not in the reference (its Vec is unbounded): see the comment at EPA_FACE_LIMIT
+    bool in_phases = false;              // Polytope::add_in_phases instead of add (the device's data-parallel formulation)
     // epa3d.rs:16-52
     bool process(std::vector<SupportPoint>& simplex, const Shape& left, const Mat4& lt, const Shape& right,
                  const Mat4& rt, Contact& out, Counters* cnt = nullptr, Status* st = nullptr) const {
@@ -494,7 +568,7 @@ struct EPA3 {  // epa3d.rs:9-67; constants epa/mod.rs:12-13
                 }
                 return true;
             }
-            polytope.add(p);
+            if (in_phases) polytope.add_in_phases(p); else polytope.add(p);
             if (polytope.overflow) {
                 if (st) *st = Status::Capacity;
                 if (cnt) cnt->max_faces = (uint32_t)face_limit + 1;

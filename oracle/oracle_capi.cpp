@@ -145,10 +145,11 @@ void orc_gjk_contact_stats_batch(const uint8_t* kind, const float* params, const
 void orc_gjk_contact_face_limit(const uint8_t* kind, const float* params, const float* xform, const uint32_t* mesh_id,
                                 const float* mesh_verts, const uint32_t* mesh_offsets, const uint32_t* pairs, uint64_t n,
                                 uint64_t face_limit, float* out_contact, uint8_t* out_status, uint32_t* out_max_faces,
-                                uint32_t* out_epa_iterations, uint64_t* out_removed_faces, int nthreads) {
+                                uint32_t* out_epa_iterations, uint64_t* out_removed_faces, int nthreads, int in_phases) {
     ShapeTable T{kind, params, xform, mesh_id, mesh_verts, mesh_offsets};
     GJK gjk;
     gjk.epa.face_limit = (size_t)face_limit;
+    gjk.epa.in_phases = in_phases != 0;
     parallel_for(n, nthreads, [&](uint64_t b, uint64_t e, int) {
         for (uint64_t i = b; i < e; ++i) {
             uint32_t l = pairs[2 * i], r = pairs[2 * i + 1];

@@ -78,6 +78,20 @@ class Oracle:
                                        C.c_int(nthreads), C.byref(counters) if counters is not None else None)
         return contacts, hit, status
 
+    def contact_face_limit(self, scene, face_limit, in_phases=False, nthreads=1):
+        """GJK::intersection (FullResolution) with the oracle's EPA face limit set to `face_limit` (the reference has none) and,
+        optionally, Polytope::add evaluated in the device's data-parallel formulation (add_in_phases).
+        -> (contacts[n, 8], status[n], max_faces[n], epa_iterations[n], removed_faces[n])"""
+        kind, params, mesh_id, mv, mo = self._scene_args(scene)
+        xform = np.ascontiguousarray(scene["xform"], dtype=np.float32)
+        pairs = np.ascontiguousarray(scene["pairs"], dtype=np.uint32)
+        n = len(pairs)
+        ct, st = np.zeros((n, 8), dtype=np.float32), np.zeros(n, dtype=np.uint8)
+        mf, it, rem = np.zeros(n, dtype=np.uint32), np.zeros(n, dtype=np.uint32), np.zeros(n, dtype=np.uint64)
+        self.lib.orc_gjk_contact_face_limit(_p(kind), _p(params), _p(xform), _p(mesh_id), _p(mv), _p(mo), _p(pairs), C.c_uint64(n), C.c_uint64(int(face_limit)),
+                                            _p(ct), _p(st), _p(mf), _p(it), _p(rem), C.c_int(nthreads), C.c_int(1 if in_phases else 0))
+        return ct, st, mf, it, rem
+
     def distance(self, scene, settings=None, nthreads=1, counters=None):
         kind, params, mesh_id, mv, mo = self._scene_args(scene)
         xform = np.ascontiguousarray(scene["xform"], dtype=np.float32)

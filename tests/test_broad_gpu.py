@@ -453,9 +453,9 @@ def test_bvh_degenerate_scenes_lose_nothing(ctx, oracle):
     off, vals = bvh.query_aabb([[0, 0, 0, 1.25, 1.25, 1.25], [5.5, 5.5, 5.5, 9, 9, 9], [10, 10, 10, 11, 11, 11]])
     got = [np.sort(vals[int(off[k]):int(off[k + 1])]) for k in range(3)]
     assert np.array_equal(got[0], np.arange(n - 3)) and got[1].tolist() == [n - 3, n - 2] and len(got[2]) == 0
-    off, vals, pts = bvh.query_ray([[0, 1.5, 1.5, 1, 0, 0], [0, 0, 0, -1, 0, 0]])
+    off, vals, pts = bvh.query_ray([[0, 1.75, 1.75, 1, 0, 0], [0, 0, 0, -1, 0, 0]])
     assert np.array_equal(np.sort(vals[int(off[0]):int(off[1])]), np.concatenate([np.arange(n - 3), [n - 2]])) and off[2] == off[1]
-    val, pt = bvh.query_ray_closest([[0, 1.5, 1.5, 1, 0, 0]])
+    val, pt = bvh.query_ray_closest([[0, 1.75, 1.75, 1, 0, 0]])
     assert val[0] == 0 and pt[0, 3] == np.float32(1.0)   # every coincident box ties at t = 1: lowest value index
     # all-dirty DbvtBroadPhase on a smaller pile (n^2 / 2 pairs)
     m = 600

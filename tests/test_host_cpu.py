@@ -464,3 +464,45 @@ def test_oracle_polyhedron_path_equals_cuboid_path_on_boxes(oracle):
     tb, _, stb = oracle.toi(box, x1, nthreads=4)
     tp, _, stp = oracle.toi(poly, x1, nthreads=4)
     assert np.array_equal(stb, stp) and (stb == 0).sum() > 100 and tb[stb == 0].tobytes() == tp[stp == 0].tobytes()
+
+
+from tests.pinched import PINCHED_PAIRS, pinched_scene  # noqa: E402
+
+
+def test_reference_finishes_the_pinched_polytopes_the_device_used_to_cap(oracle):
+    """the oracle had been given the device's 1024-face limit, so both said STATUS_CAPACITY where the reference
+    returns a Contact. With the limit out of the way (epa3d.rs:121-149 has none) every such pair ends within max_iterations —
+    the reference's loop counter stops it at 100 — with polytopes of 10^3 .. 10^5 faces; every one involves a Cylinder cap
+    against a flat face. These are the results the device now has to reproduce (tests/test_narrow_gpu.py::test_pinched_*)."""
+    idx = [i for i, _ in PINCHED_PAIRS]
+    sc = pinched_scene(idx)
+    kinds = sc["kind"].reshape(-1, 2)
+    assert all(4 in k and (3 in k or 1 in k) for k in kinds.tolist())      # Cylinder vs Cuboid / Quad
+    _, st_capped, mf_capped, _, _ = oracle.contact_face_limit(sc, 1024, in_phases=True, nthreads=4)
+    assert (st_capped == 5).all()                                          # what round 1 reported
+    ct, st, mf, it, rem = oracle.contact_face_limit(sc, 1 << 18, in_phases=True, nthreads=4)
+    assert (st == 0).all() and (it == 100).all()                           # the iteration cap ends them, with a Contact
+    assert mf.tolist() == [f for _, f in PINCHED_PAIRS]
+    assert np.isfinite(ct[:, :7]).all()
+    # and the default oracle (sequential add(), the reference's literal walk) agrees on the ones it finishes quickly
+    small = pinched_scene(idx[:4])
+    oc, _, ost = oracle.contact(small, strategy=0, nthreads=4)
+    assert np.array_equal(ost, st[:4]) and oc[:, :7].tobytes() == ct[:4, :7].tobytes()
+
+
+def test_oracle_add_in_phases_equals_the_sequential_walk(oracle):
+    """Polytope::add_in_phases (prefix counts, two-pointer hole filling, removal order by formula, first-in-first-out edge
+    matching per undirected edge — the formulation bam3d_b200/csrc/epa_huge.cuh runs) builds the same polytope, list order
+    included, as the reference's sequential walk with swap_remove and remove_or_add_edge: identical contacts, statuses, face
+    high-water marks, iteration counts and removed-face totals on mixed pairs, on every primitive kind, on polyhedra, and on
+    pinched polytopes up to 10^4 faces (the sequential form is O(faces^2) per trip, so the largest ones are left to the test above)."""
+    from bam3d_b200 import scenes
+    lib = scenes.mesh_library(32)
+    cases = (scenes.mixed_pairs(40_000, s=1.5), scenes.all_kinds_pairs(30_000, s=1.0), scenes.polyhedron_pairs(4_000, library=lib),
+             pinched_scene([i for i, f in PINCHED_PAIRS if f < 11_000]))
+    for sc in cases:
+        a = oracle.contact_face_limit(sc, 1 << 18, in_phases=False, nthreads=8)
+        b = oracle.contact_face_limit(sc, 1 << 18, in_phases=True, nthreads=8)
+        for x, y, name in zip(a, b, ("contact", "status", "max_faces", "epa_iterations", "removed_faces")):
+            assert x.tobytes() == y.tobytes(), name
+        assert (a[1] == 0).sum() > 3

@@ -186,6 +186,40 @@ def test_contact_parity_execution_options(ctx, oracle, options):
     assert (st == b3.STATUS_CAPACITY).sum() == (ost == b3.STATUS_CAPACITY).sum()
 
 
+def test_pinched_polytopes_match_the_uncapped_reference(ctx, oracle):
+    """The 44 pairs per 2^20 of the C2 scene whose polytope passes 1024 faces (tests/pinched.py): the reference has no face limit
+    and returns a Contact for every one of them when its iteration cap ends the loop (tests/test_host_cpu.py). The device's
+    third EPA tier (epa_huge.cuh: block per pair, Polytope::add without a sequential walk) must return the same bits — not
+    BAM3D_STATUS_CAPACITY as in round 1 — whether the pairs arrive alone, mixed into a batch, or with the tier switched off
+    (then, and only then, CAPACITY)."""
+    from tests.pinched import ALL_PINCHED, pinched_scene
+    sc = pinched_scene(ALL_PINCHED)
+    want, wst, mf, it, _ = oracle.contact_face_limit(sc, 1 << 18, in_phases=True, nthreads=8)
+    assert (wst == 0).all() and mf.max() == 121962 and mf.min() > 1024
+    shapes = shapes_of(ctx, sc)
+    gjk = b3.GJK.new(ctx)
+    c, st = gjk.intersection_batch(b3.CollisionStrategy.FullResolution, shapes, sc["pairs"])
+    assert np.array_equal(st, wst), st.tolist()
+    assert_f32_equal("pinched contact", c[:, :7], want[:, :7])
+    # mixed into an ordinary batch (the thread-per-pair tier, the overflow tier and the third tier all run)
+    mixed = scenes.mixed_pairs(20_000, s=1.5, seed=0xB3D00B01)
+    both = dict(mixed)
+    for key in ("kind", "params", "xform"):
+        both[key] = np.concatenate([mixed[key], sc[key]])
+    both["pairs"] = np.concatenate([mixed["pairs"], sc["pairs"] + np.uint32(len(mixed["kind"]))])
+    cb, stb = gjk.intersection_batch(b3.CollisionStrategy.FullResolution, shapes_of(ctx, both), both["pairs"])
+    om, _, omst = oracle.contact(mixed, strategy=0, nthreads=8)
+    assert np.array_equal(stb[:20_000], omst) and np.array_equal(stb[20_000:], wst)
+    assert_f32_equal("mixed part", cb[:20_000, :7], om[:, :7], omst == 0)
+    assert_f32_equal("pinched part", cb[20_000:, :7], want[:, :7])
+    try:
+        ctx.set_option("epa_huge", 0)
+        _, st0 = gjk.intersection_batch(b3.CollisionStrategy.FullResolution, shapes, sc["pairs"])
+        assert (st0 == b3.STATUS_CAPACITY).all()
+    finally:
+        ctx.set_option("epa_huge", 1)
+
+
 def test_contact_parity_all_kinds_and_collision_only(ctx, oracle):
     scene = scenes.all_kinds_pairs(40_000, s=1.0)
     shapes = shapes_of(ctx, scene)
