@@ -871,11 +871,14 @@ __global__ void __launch_bounds__(HUGE_THREADS) gjk_contact_huge_kernel(ShapeSet
     __shared__ HugeShared sh;
     __shared__ uint32_t s_item;
     __shared__ uint8_t s_st;
+    extern __shared__ __align__(16) uint32_t huge_head[];  // 2 x HUGE_KEYS per-edge counters (epa_huge.cuh)
     uint32_t* hdr = reinterpret_cast<uint32_t*>(scratch);
     const uint32_t* list = reinterpret_cast<const uint32_t*>(scratch + 256 + (size_t)OVF_MAX * 4);
     const uint32_t count = min(hdr[HUGE_COUNT], HUGE_MAX);
     if (count == 0) return;
     const HugeStore H = carve_huge_store(slab + (size_t)blockIdx.x * HUGE_SLAB_BYTES);
+    for (uint32_t k = threadIdx.x; k < 2 * HUGE_KEYS; k += HUGE_THREADS) huge_head[k] = 0u;
+    __syncthreads();
     for (;;) {
         if (threadIdx.x == 0) s_item = atomicAdd(hdr + HUGE_CURSOR, 1u);
         __syncthreads();
@@ -897,7 +900,7 @@ __global__ void __launch_bounds__(HUGE_THREADS) gjk_contact_huge_kernel(ShapeSet
         ContactOut c;
         c.normal = v3(0.f, 0.f, 0.f); c.depth = 0.f; c.point = v3(0.f, 0.f, 0.f);
         if (st == ST_OK) {
-            st = epa_process_huge(L, R, s, cfg.epa_tolerance, cfg.max_iterations, H, sh, c);
+            st = epa_process_huge(L, R, s, cfg.epa_tolerance, cfg.max_iterations, H, sh, huge_head, c);
             if (st != ST_OK) { c.normal = v3(0.f, 0.f, 0.f); c.depth = 0.f; c.point = v3(0.f, 0.f, 0.f); }
         }
         if (threadIdx.x == 0) {
@@ -1617,6 +1620,7 @@ int launch_contact(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs, 
     bool& smem_opt_in = smem_opt_in_per_device[current_device_slot()];
     if (!smem_opt_in) {
         cudaFuncSetAttribute(gjk_contact_overflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EPA_BIG_SMEM_BYTES);
+        cudaFuncSetAttribute(gjk_contact_huge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HUGE_SMEM_BYTES);
 #ifdef B3_EXPERIMENTS
         cudaFuncSetAttribute(epa_tiers_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(epa_refill_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EPA_PIPE_SMEM);
@@ -1701,12 +1705,12 @@ int launch_contact(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs, 
             // launched AFTER the producer (a tool that serialises kernels then still runs them in a terminating order)
             cudaStreamWaitEvent(side->stream, side->fork, 0);
             gjk_contact_overflow_kernel<<<OVF_WARPS, 32, EPA_BIG_SMEM_BYTES, side->stream>>>(S, d_pairs, cfg, ovf, 1, d_contacts, d_status);
-            if (d_huge_slab) { gjk_contact_huge_kernel<<<HUGE_BLOCKS, HUGE_THREADS, 0, side->stream>>>(S, d_pairs, cfg, ovf, reinterpret_cast<unsigned char*>(d_huge_slab), d_contacts, d_status); ++launched; }
+            if (d_huge_slab) { gjk_contact_huge_kernel<<<HUGE_BLOCKS, HUGE_THREADS, HUGE_SMEM_BYTES, side->stream>>>(S, d_pairs, cfg, ovf, reinterpret_cast<unsigned char*>(d_huge_slab), d_contacts, d_status); ++launched; }
             cudaEventRecord(side->join, side->stream);
             cudaStreamWaitEvent(st, side->join, 0);
         } else {
             gjk_contact_overflow_kernel<<<OVF_WARPS, 32, EPA_BIG_SMEM_BYTES, st>>>(S, d_pairs, cfg, ovf, 0, d_contacts, d_status);
-            if (d_huge_slab) { gjk_contact_huge_kernel<<<HUGE_BLOCKS, HUGE_THREADS, 0, st>>>(S, d_pairs, cfg, ovf, reinterpret_cast<unsigned char*>(d_huge_slab), d_contacts, d_status); ++launched; }
+            if (d_huge_slab) { gjk_contact_huge_kernel<<<HUGE_BLOCKS, HUGE_THREADS, HUGE_SMEM_BYTES, st>>>(S, d_pairs, cfg, ovf, reinterpret_cast<unsigned char*>(d_huge_slab), d_contacts, d_status); ++launched; }
         }
         ++launched;
     }

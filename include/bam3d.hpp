@@ -303,4 +303,147 @@ private:
     int axis_;
 };
 
+// Compound shapes: the reference's `&[(Primitive, Mat4)]` slices (gjk/mod.rs:362-371), one per compound, resident on the device,
+// and GJK::intersection_complex / distance_complex / intersection_complex_time_of_impact (gjk/mod.rs:362-523) over pairs of them.
+class CompoundSet {
+public:
+    using Part = std::pair<Primitive3, Mat4>;  // (primitive, local-to-model transform)
+    CompoundSet(const Context& ctx, const std::vector<std::vector<Part>>& compounds) : ctx_(ctx), n_((uint32_t)compounds.size()) {
+        std::vector<uint8_t> kind;
+        std::vector<float> params, local, verts;
+        std::vector<uint32_t> mesh_id, voff{0}, offsets{0};
+        for (const auto& c : compounds) {
+            for (const auto& part : c) {
+                kind.push_back(part.first.kind);
+                params.insert(params.end(), part.first.params.begin(), part.first.params.end());
+                local.insert(local.end(), part.second.begin(), part.second.end());
+                mesh_id.push_back(0);
+                if (part.first.kind == BAM3D_KIND_POLYHEDRON) {
+                    mesh_id.back() = (uint32_t)voff.size() - 1;
+                    verts.insert(verts.end(), part.first.vertices.begin(), part.first.vertices.end());
+                    voff.push_back((uint32_t)(verts.size() / 3));
+                }
+            }
+            offsets.push_back((uint32_t)kind.size());
+        }
+        if (voff.size() > 1) ctx_.check(bam3d_meshes_upload(ctx_.handle(), verts.data(), voff.data(), (uint32_t)voff.size() - 1, &meshes_));
+        ctx_.check(bam3d_compounds_upload(ctx_.handle(), kind.data(), params.data(), local.data(), mesh_id.data(), (uint32_t)kind.size(), offsets.data(), n_, meshes_, &h_));
+    }
+    ~CompoundSet() { bam3d_compounds_free(ctx_.handle(), h_); bam3d_meshes_free(ctx_.handle(), meshes_); }
+    CompoundSet(const CompoundSet&) = delete;
+    CompoundSet& operator=(const CompoundSet&) = delete;
+    uint32_t size() const { return n_; }
+    // transforms[c] = model-to-world Mat4 of compound c
+    std::vector<std::optional<Contact>> intersection_complex_batch(const GJK& gjk, CollisionStrategy strategy, const std::vector<Mat4>& transforms,
+                                                                   const std::vector<Pair>& pairs) const {
+        std::vector<uint8_t> st(pairs.size());
+        std::vector<bam3d_contact> c(pairs.size());
+        ctx_.check(bam3d_gjk_contact_complex(ctx_.handle(), h_, transforms.data()->data(), reinterpret_cast<const uint32_t*>(pairs.data()), pairs.size(), &gjk.settings(),
+                                             (int32_t)strategy, c.data(), st.data()));
+        return opt(strategy, c, st);
+    }
+    std::vector<std::optional<float>> distance_complex_batch(const GJK& gjk, const std::vector<Mat4>& transforms, const std::vector<Pair>& pairs) const {
+        std::vector<uint8_t> st(pairs.size());
+        std::vector<float> v(pairs.size());
+        ctx_.check(bam3d_gjk_distance_complex(ctx_.handle(), h_, transforms.data()->data(), reinterpret_cast<const uint32_t*>(pairs.data()), pairs.size(), &gjk.settings(),
+                                              v.data(), st.data()));
+        std::vector<std::optional<float>> out(pairs.size());
+        for (size_t i = 0; i < pairs.size(); ++i) if (st[i] == BAM3D_STATUS_OK) out[i] = v[i];
+        return out;
+    }
+    std::vector<std::optional<Contact>> intersection_complex_time_of_impact_batch(const GJK& gjk, CollisionStrategy strategy, const std::vector<Mat4>& start,
+                                                                                  const std::vector<Mat4>& end, const std::vector<Pair>& pairs) const {
+        std::vector<uint8_t> st(pairs.size());
+        std::vector<bam3d_contact> c(pairs.size());
+        ctx_.check(bam3d_gjk_time_of_impact_complex(ctx_.handle(), h_, start.data()->data(), end.data()->data(), reinterpret_cast<const uint32_t*>(pairs.data()),
+                                                    pairs.size(), &gjk.settings(), (int32_t)strategy, c.data(), st.data()));
+        return opt(strategy, c, st);
+    }
+private:
+    static std::vector<std::optional<Contact>> opt(CollisionStrategy strategy, const std::vector<bam3d_contact>& c, const std::vector<uint8_t>& st) {
+        std::vector<std::optional<Contact>> out(c.size());
+        for (size_t i = 0; i < c.size(); ++i)
+            if (st[i] == BAM3D_STATUS_OK)
+                out[i] = Contact{strategy, {c[i].normal[0], c[i].normal[1], c[i].normal[2]}, c[i].penetration_depth,
+                                 {c[i].contact_point[0], c[i].contact_point[1], c[i].contact_point[2]}, c[i].time_of_impact};
+        return out;
+    }
+    const Context& ctx_;
+    bam3d_compounds* h_ = nullptr;
+    bam3d_meshes* meshes_ = nullptr;
+    uint32_t n_;
+};
+
+// The scalar forms of the reference (gjk/mod.rs:362, :422, :478), as batches of one compound pair.
+inline std::optional<Contact> intersection_complex(const Context& ctx, const GJK& gjk, CollisionStrategy strategy, const std::vector<CompoundSet::Part>& left,
+                                                   const Mat4& left_transform, const std::vector<CompoundSet::Part>& right, const Mat4& right_transform) {
+    CompoundSet c(ctx, {left, right});
+    return c.intersection_complex_batch(gjk, strategy, {left_transform, right_transform}, {{0, 1}})[0];
+}
+inline std::optional<float> distance_complex(const Context& ctx, const GJK& gjk, const std::vector<CompoundSet::Part>& left, const Mat4& left_transform,
+                                             const std::vector<CompoundSet::Part>& right, const Mat4& right_transform) {
+    CompoundSet c(ctx, {left, right});
+    return c.distance_complex_batch(gjk, {left_transform, right_transform}, {{0, 1}})[0];
+}
+
+// Broad phase -> narrow phase in one resident call (BASELINE configs[3]): world AABBs -> SweepAndPrune3 -> perm remap -> GJK::intersection.
+struct Candidate { uint32_t left, right; std::optional<Contact> contact; };  // SHAPE indices, not sorted positions
+inline std::vector<Candidate> collide_all(const Context& ctx, const GJK& gjk, CollisionStrategy strategy, const ShapeSet& shapes, int& sweep_axis, uint64_t capacity_guess = 0) {
+    uint64_t cap = capacity_guess ? capacity_guess : 4096, count = 0;
+    std::vector<uint32_t> pairs;
+    std::vector<bam3d_contact> c;
+    std::vector<uint8_t> st;
+    for (;;) {
+        pairs.resize(2 * cap); c.resize(cap); st.resize(cap);
+        int32_t axis = sweep_axis;
+        int32_t rc = bam3d_pipeline_contacts(ctx.handle(), shapes.handle(), &axis, &gjk.settings(), (int32_t)strategy, pairs.data(), nullptr, nullptr, c.data(), st.data(), cap, &count);
+        if (rc == BAM3D_ERR_CAPACITY && count > cap) { cap = count; continue; }
+        ctx.check(rc);
+        sweep_axis = axis;
+        break;
+    }
+    std::vector<Candidate> out(count);
+    for (uint64_t k = 0; k < count; ++k) {
+        out[k].left = pairs[2 * k]; out[k].right = pairs[2 * k + 1];
+        if (st[k] == BAM3D_STATUS_OK)
+            out[k].contact = Contact{strategy, {c[k].normal[0], c[k].normal[1], c[k].normal[2]}, c[k].penetration_depth,
+                                     {c[k].contact_point[0], c[k].contact_point[1], c[k].contact_point[2]}, c[k].time_of_impact};
+    }
+    return out;
+}
+
+// Multi-GPU (one process per GPU): the NCCL gather of the ranks' contacts (bam3d_comm_*). The 256-byte id is made by rank 0
+// (unique_id) and handed to the other ranks by the application's own channel.
+class Comm {
+public:
+    static std::array<uint8_t, BAM3D_UNIQUE_ID_BYTES> unique_id() {
+        std::array<uint8_t, BAM3D_UNIQUE_ID_BYTES> id{};
+        int32_t rc = bam3d_comm_unique_id(id.data());
+        if (rc != BAM3D_OK) throw Error(rc, std::string("bam3d_comm_unique_id: ") + bam3d_comm_unavailable_reason());
+        return id;
+    }
+    Comm(int device, const std::array<uint8_t, BAM3D_UNIQUE_ID_BYTES>& id, int rank, int n_ranks) : n_ranks_(n_ranks) {
+        int32_t rc = bam3d_comm_create(device, id.data(), rank, n_ranks, &h_);
+        if (rc != BAM3D_OK) throw Error(rc, std::string("bam3d_comm_create: ") + bam3d_comm_unavailable_reason());
+    }
+    ~Comm() { bam3d_comm_destroy(h_); }
+    Comm(const Comm&) = delete;
+    Comm& operator=(const Comm&) = delete;
+    bam3d_comm* handle() const { return h_; }
+    // this rank's dense results (for its slice of the pair list, global indices from pair_index_base) -> the hits of ALL ranks, rank order
+    std::vector<bam3d_contact40> gather_contacts(const Context& ctx, const std::vector<bam3d_contact>& contacts, const std::vector<uint8_t>& status,
+                                                 uint64_t pair_index_base, uint64_t capacity, std::vector<uint64_t>* counts = nullptr) const {
+        std::vector<bam3d_contact40> out(capacity ? capacity : 1);
+        std::vector<uint64_t> cnt((size_t)n_ranks_);
+        uint64_t total = 0;
+        ctx.check(bam3d_gather_contacts(ctx.handle(), h_, contacts.data(), status.data(), status.size(), pair_index_base, out.data(), capacity, cnt.data(), &total));
+        out.resize(total);
+        if (counts) *counts = cnt;
+        return out;
+    }
+private:
+    bam3d_comm* h_ = nullptr;
+    int n_ranks_;
+};
+
 }  // namespace bam3d

@@ -459,8 +459,8 @@ struct Polytope {  // epa3d.rs:97-150
     //   order h_1, [visible positions in (t_1, F) descending], h_2, [visible in (t_2, t_1) descending], ..., and finally, if
     //   positions remain between S and the last tail survivor taken, S itself followed by the rest of them descending.
     //   The horizon list is the sequence of directed edges of the removed faces in that order under remove_or_add_edge; per
-    //   undirected edge that is a first-in-first-out matching of the two directions, so the survivors can be found per edge and
-    //   then compacted in sequence order.
+    //   undirected edge that is a first-in-first-out matching of the two directions, whose survivors have a closed form (below),
+    //   compacted in sequence order.
     void add_in_phases(const SupportPoint& sup) {
         const size_t F = faces.size();
         std::vector<uint8_t> vis(F);
@@ -498,18 +498,17 @@ struct Polytope {  // epa3d.rs:97-150
             const Face& f = faces[order[i]];
             for (int e = 0; e < 3; ++e) ev[3 * (size_t)i + e] = {f.vertices[e], f.vertices[(e + 1) % 3]};
         }
+        // remove_or_add_edge over that sequence: per undirected edge the list only ever holds copies of one direction (an arriving
+        // edge removes the OLDEST copy of its reverse if there is one, else it is pushed), so what is left are the last
+        // |#forward - #backward| events of the majority direction: event i survives iff its rank among the events with the same
+        // directed edge, in sequence order, is >= the number of events of the reverse direction.
         std::vector<uint8_t> keep(ev.size(), 0);
-        std::map<std::pair<uint32_t, uint32_t>, std::vector<uint32_t>> by_edge;  // undirected key -> event indices, in sequence order
-        for (uint32_t i = 0; i < ev.size(); ++i) by_edge[{std::min(ev[i].a, ev[i].b), std::max(ev[i].a, ev[i].b)}].push_back(i);
-        for (auto& kv : by_edge) {
-            std::vector<uint32_t> live;  // events of one direction currently in the list, oldest first
-            size_t head = 0;
-            bool live_forward = true;
-            for (uint32_t i : kv.second) {
-                const bool forward = ev[i].a <= ev[i].b;
-                if (head < live.size() && forward != live_forward) { keep[live[head]] = 0; ++head; }  // removes the oldest reversed copy
-                else { if (head == live.size()) { live.clear(); head = 0; live_forward = forward; } live.push_back(i); keep[i] = 1; }
-            }
+        std::map<std::pair<uint32_t, uint32_t>, uint32_t> count, seen;
+        for (auto& e : ev) ++count[{e.a, e.b}];
+        for (uint32_t i = 0; i < ev.size(); ++i) {
+            const uint32_t n_rev = count.count({ev[i].b, ev[i].a}) ? count[{ev[i].b, ev[i].a}] : 0u;
+            const uint32_t rank = seen[{ev[i].a, ev[i].b}]++;
+            keep[i] = (count[{ev[i].a, ev[i].b}] > n_rev && rank >= n_rev) ? 1 : 0;
         }
         std::vector<std::pair<uint32_t, uint32_t>> edges;
         for (uint32_t i = 0; i < ev.size(); ++i) if (keep[i]) edges.emplace_back(ev[i].a, ev[i].b);

@@ -1,6 +1,6 @@
 // build.rs of the `gpu` feature of bam3d: compiles the CUDA sources for sm_100a with nvcc into a static library and
 // links it together with the CUDA runtime. SOURCE ONLY in this repository — no Rust toolchain exists in the build image
-// (see INTEGRATION.md); the same three translation units are what bam3d_b200/build.py compiles.
+// (see INTEGRATION.md); the same four translation units are what bam3d_b200/build.py compiles.
 use std::{env, path::PathBuf, process::Command};
 
 fn main() {
@@ -8,7 +8,7 @@ fn main() {
     let csrc = PathBuf::from(env::var("CARGO_MANIFEST_DIR").unwrap()).join("../../bam3d_b200/csrc");
     let nvcc = env::var("NVCC").unwrap_or_else(|_| "/usr/local/cuda/bin/nvcc".into());
     let mut objs = Vec::new();
-    for unit in ["narrow.cu", "broad.cu", "capi.cu"] {
+    for unit in ["narrow.cu", "broad.cu", "capi.cu", "comm.cu"] {
         let obj = out.join(unit.replace(".cu", ".o"));
         let ok = Command::new(&nvcc)
             .args(["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo"])

@@ -98,6 +98,27 @@ int main() {
         CHECK(st[0] == BAM3D_STATUS_OK && c[0].penetration_depth == 2.f);  // frame 0 is test_gjk_3d_hit
         CHECK(st[2] != BAM3D_STATUS_OK);                                   // 15 - 4 = 11 > 10: separated
     }
+    {   // compound shapes (gjk/mod.rs:362-456): two cuboids per side, local transforms composed with the model transforms
+        std::vector<CompoundSet::Part> left = {{Primitive3::Cuboid(10, 10, 10), transform_3d(0, 0, 0)}, {Primitive3::Cuboid(2, 2, 2), transform_3d(0, 20, 0)}};
+        std::vector<CompoundSet::Part> right = {{Primitive3::Cuboid(10, 10, 10), transform_3d(0, 0, 0)}, {Primitive3::Sphere(1), transform_3d(0, -20, 0)}};
+        auto c = intersection_complex(ctx, gjk, CollisionStrategy::FullResolution, left, transform_3d(15, 0, 0), right, transform_3d(7, 2, 0));
+        CHECK(c.has_value());
+        if (c) { CHECK(c->penetration_depth == 2.f && c->normal[0] == -1.f); CHECK(c->contact_point[0] == 10.f && c->contact_point[1] == 1.0000002f); }  // == test_gjk_3d_hit
+        CHECK(!intersection_complex(ctx, gjk, CollisionStrategy::FullResolution, left, transform_3d(15, 0, 0), right, transform_3d(-40, 2, 0)).has_value());
+        CHECK(!distance_complex(ctx, gjk, left, transform_3d(15, 0, 0), right, transform_3d(7, 2, 0)).has_value());  // colliding -> None
+        CHECK(distance_complex(ctx, gjk, left, transform_3d(15, 0, 0), right, transform_3d(-40, 2, 0)).has_value());
+    }
+    {   // broad -> narrow in one call: three cuboids in a row, the outer two do not touch; SHAPE indices come back
+        ShapeSet set(ctx, {Primitive3::Cuboid(10, 10, 10), Primitive3::Cuboid(10, 10, 10), Primitive3::Cuboid(10, 10, 10)},
+                     {transform_3d(30, 0, 0), transform_3d(7, 2, 0), transform_3d(15, 0, 0)});
+        int axis = 0;
+        auto cand = collide_all(ctx, gjk, CollisionStrategy::FullResolution, set, axis);
+        CHECK(cand.size() == 1);
+        if (cand.size() == 1) {
+            CHECK(cand[0].left == 1 && cand[0].right == 2);   // sorted by min x: shape 1 (x 2..12), shape 2 (10..20), shape 0 (25..35)
+            CHECK(cand[0].contact.has_value() && cand[0].contact->penetration_depth == 2.f);
+        }
+    }
     std::printf("kat_gpu: %s\n", fails ? "FAILED" : "all passed");
     return fails ? 1 : 0;
 }

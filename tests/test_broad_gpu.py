@@ -461,7 +461,13 @@ def test_bvh_degenerate_scenes_lose_nothing(ctx, oracle):
     m = 600
     pile = np.tile(np.array([[0, 0, 0, 1, 1, 1]], dtype=np.float32), (m, 1))
     pairs = broad.Bvh(ctx, pile).find_collider_pairs(np.ones(m, dtype=np.uint8))
-    assert len(pairs) == m * (m - 1) // 2 and np.array_equal(pairs, oracle.dbvt_build(pile).find_collider_pairs(np.ones(m, dtype=np.uint8)))
+    ii, jj = np.triu_indices(m, k=1)
+    assert np.array_equal(pairs, np.stack([ii, jj], axis=1).astype(np.uint32))
+    # (the oracle's tree over this pile is a chain 600 deep: its query overflows the reference's fixed 256-entry stack, where the
+    # reference itself panics with an index out of bounds — dbvt/mod.rs:486,507 — so there is no reference answer to compare with)
+    ot = oracle.dbvt_build(pile)
+    ot.find_collider_pairs(np.ones(m, dtype=np.uint8))
+    assert ot.stack_overflow()
     # sweep and prune over the same pile: every pair, in the reference's order
     sp, perm = broad.SweepAndPrune3.new(ctx).find_collider_pairs(pile)
     op, operm, _ = oracle.sap_find_pairs(pile, 0)
