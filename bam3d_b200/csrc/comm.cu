@@ -75,7 +75,7 @@ NcclApi& nccl() {
     return api;
 }
 
-constexpr int TICKETS = 4;  // count exchanges in flight
+constexpr int TICKETS = 16;  // count exchanges in flight
 
 }  // namespace
 
@@ -84,10 +84,10 @@ struct bam3d_comm {
     ncclComm_t comm_counts = nullptr, comm = nullptr;  // record counts | payload
     cudaStream_t s_counts = nullptr, stream = nullptr;
     cudaEvent_t ordered = nullptr, done = nullptr;  // ctx stream -> comm streams, comm streams -> ctx stream
-    cudaEvent_t exchanged[4] = {nullptr, nullptr, nullptr, nullptr};  // per ticket: its payload has arrived
+    cudaEvent_t exchanged[16] = {};  // per ticket: its payload has arrived
     uint64_t* d_counts = nullptr;                   // TICKETS x n_ranks
     uint64_t* h_counts = nullptr;                   // pinned, TICKETS x n_ranks
-    cudaEvent_t counted[TICKETS] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t counted[TICKETS] = {};
     uint64_t next_ticket = 0;
 };
 
@@ -187,7 +187,7 @@ int32_t bam3d_gather_contacts_finish(bam3d_ctx* ctx, bam3d_comm* c, uint64_t tic
                                      bam3d_contact40* d_gathered, uint64_t capacity, uint64_t* out_counts, uint64_t* out_total) {
     if (!ctx || !c || !out_total) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_gather_contacts_finish: null argument", cudaSuccess);
     if (ticket >= c->next_ticket || ticket + TICKETS < c->next_ticket)
-        return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_gather_contacts_finish: unknown ticket (at most 4 exchanges may be in flight)", cudaSuccess);
+        return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_gather_contacts_finish: unknown ticket (at most 16 exchanges may be in flight)", cudaSuccess);
     NcclApi& N = nccl();
     cudaError_t e;
     if ((e = cudaSetDevice(c->device)) != cudaSuccess) return b3_fail(ctx, BAM3D_ERR_CUDA, "cudaSetDevice", e);

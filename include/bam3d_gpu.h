@@ -399,7 +399,7 @@ const char* bam3d_comm_unavailable_reason(void);    /* "" when libnccl was loade
  * enqueues — on the comm stream — one broadcast per rank with the exact sizes, so that d_gathered holds the ranks' records
  * concatenated in rank order (out_counts[n_ranks] on the host, may be NULL; *out_total = their sum; BAM3D_ERR_CAPACITY
  * if it exceeds `capacity` records). bam3d_comm_join makes the ctx stream wait for the exchange before it reads
- * d_gathered. Every rank must call begin / finish in the same order; at most 4 tickets may be open. Counts and payloads use
+ * d_gathered. Every rank must call begin / finish in the same order; at most 16 tickets may be open. Counts and payloads use
  * separate communicators and streams, so a payload never queues behind the count exchange of a later step. */
 int32_t bam3d_gather_contacts_begin(bam3d_ctx* ctx, bam3d_comm* comm, const uint64_t* d_count, uint64_t* out_ticket);
 int32_t bam3d_gather_contacts_finish(bam3d_ctx* ctx, bam3d_comm* comm, uint64_t ticket, const bam3d_contact40* d_compact,

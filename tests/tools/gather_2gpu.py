@@ -69,16 +69,21 @@ def main():
     fq = b3.FrameQueue(gjk, mine["kind"], mine["params"], mine["xform"], max_pairs=n, depth=2)
     hx = np.ascontiguousarray(mine["xform"], dtype=np.float32).reshape(-1, 16)
     hp = np.ascontiguousarray(mine["pairs"], dtype=np.uint32)
-    frames = []
-    for _ in range(3):
-        g, hs = b3.pinned_empty(ctx, (len(fst), 10), np.uint32), b3.pinned_empty(ctx, (n,), np.uint8)
-        frames.append((fq.submit_contact_gather(comm, FR, hx, hp, starts[rank], g, hs), g, hs))
-    for f, g, hs in frames:
+    def check(f, g, hs):
         fq.wait(f)
         cnt, total = fq.gathered(f)
         assert cnt.tolist() == per_rank and total == len(fhits) and np.array_equal(hs, st)
         got = np.concatenate([g[off[r]:off[r + 1]][np.argsort(g[off[r]:off[r + 1], 0], kind="stable")] for r in range(world)])
         assert got.tobytes() == want.tobytes(), "frame-queue gather differs"
+
+    frames = []
+    for k in range(4):
+        if k >= 2:
+            check(*frames[k - 2])   # depth 2: a frame's slot is reused two submissions later
+        g, hs = b3.pinned_empty(ctx, (len(fst), 10), np.uint32), b3.pinned_empty(ctx, (n,), np.uint8)
+        frames.append((fq.submit_contact_gather(comm, FR, hx, hp, starts[rank], g, hs), g, hs))
+    check(*frames[2])
+    check(*frames[3])
     fq.close()
     dist.barrier()
     comm.close()
