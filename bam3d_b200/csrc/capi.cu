@@ -157,6 +157,17 @@ void bam3d_default_settings(bam3d_gjk_settings* out) {
     out->toi_iteration_cap = 100;
 }
 
+// The side stream carries the EPA overflow tiers: the longest jobs of a contact call, few blocks, each needing most of an SM.
+// At the highest priority their blocks are placed first whenever a multiprocessor drains, instead of queueing behind the
+// wide kernels of another compute lane. (BAM3D_SIDE_PRIORITY=0: default priority.)
+static cudaError_t create_side_stream(cudaStream_t* s) {
+    int least = 0, greatest = 0;
+    bool high = true;
+    if (const char* e = std::getenv("BAM3D_SIDE_PRIORITY")) high = std::atoi(e) != 0;
+    if (!high || cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess) return cudaStreamCreateWithFlags(s, cudaStreamNonBlocking);
+    return cudaStreamCreateWithPriority(s, cudaStreamNonBlocking, greatest);
+}
+
 int32_t bam3d_ctx_create(int32_t device_ordinal, bam3d_ctx** out_ctx) {
     if (!out_ctx) return BAM3D_ERR_ARG;
     *out_ctx = nullptr;
@@ -181,7 +192,7 @@ int32_t bam3d_ctx_create(int32_t device_ordinal, bam3d_ctx** out_ctx) {
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return BAM3D_ERR_CUDA; }
     if (cudaMalloc(&ctx->d_flags, 64) != cudaSuccess || cudaMemset(ctx->d_flags, 0, 64) != cudaSuccess ||
         cudaHostAlloc(&ctx->h_flags, 64, cudaHostAllocDefault) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+        create_side_stream(&ctx->stream2) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_a, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_b, cudaEventDisableTiming) != cudaSuccess) { bam3d_ctx_destroy(ctx); return BAM3D_ERR_CUDA; }
     *out_ctx = ctx;
@@ -561,7 +572,11 @@ int32_t bam3d_gjk_time_of_impact_dev(bam3d_ctx* ctx, const bam3d_shapes* s0, con
                                      const bam3d_gjk_settings* settings, bam3d_contact* d_contacts, uint8_t* d_status) {
     if (!ctx || !s0 || !s1 || (n && (!d_pairs || !d_status || !d_contacts))) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_gjk_time_of_impact: null argument", cudaSuccess);
     if (s0->n != s1->n) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_gjk_time_of_impact: start/end shape sets differ in size", cudaSuccess);
-    if (s0->meshes != s1->meshes || std::memcmp(s0->kind_hist, s1->kind_hist, sizeof s0->kind_hist) != 0)
+    // the end set contributes transforms only; its primitives must be the start set's (the same mesh library, or a second
+    // upload of the same one — only the sizes can be compared here)
+    const bool same_meshes = s0->meshes == s1->meshes ||
+                             (s0->meshes && s1->meshes && s0->meshes->n_meshes == s1->meshes->n_meshes && s0->meshes->nverts == s1->meshes->nverts);
+    if (!same_meshes || std::memcmp(s0->kind_hist, s1->kind_hist, sizeof s0->kind_hist) != 0)
         return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_gjk_time_of_impact: the end shape set must hold the same primitives (kinds, mesh library) as the start set", cudaSuccess);
     int32_t rc;
     if ((rc = check_n(ctx, n)) || (rc = check_pairs_over(ctx, s0, n))) return rc;

@@ -187,7 +187,7 @@ B3_DEV uint8_t epa_process_big(const Shape& L, const Shape& R, const Simplex<tru
         nlive = __shfl_sync(0xFFFFFFFFu, nlive, 0);
         ok = __shfl_sync(0xFFFFFFFFu, ok, 0);
         __syncwarp();
-        if (!ok || nv >= EPA_VCAP || nf + nlive > EPA_BIG_FCAP) return ST_CAPACITY;
+        if (!ok || nv >= EPA_VCAP || nf + nlive > EPA_BIG_FCAP) { out.depth = (float)nv; return ST_CAPACITY; }  // depth: how early it outgrew this tier (the next tier's schedule)
         const int n = nv;
         if (lane == 0) { st3(B.vv, n, pv); st3(B.va, n, pa); }
         ++nv;

@@ -37,6 +37,7 @@ constexpr int OVF_COUNT = 0, OVF_CURSOR = 1, OVF_DONE = 2, OVF_EXITED = 3;
 // third tier (epa_huge.cuh): [4] = pairs the overflow tier could not finish either, [5] = consumer cursor; entries behind the overflow list
 constexpr int HUGE_COUNT = 4, HUGE_CURSOR = 5;
 constexpr uint32_t HUGE_MAX = 4096;
+constexpr uint32_t HUGE_SORT_MAX = 1024;  // third-tier lists up to this long are taken longest-first
 
 // ------------------------------------------------------------------------------------------------------------
 // pack_shapes: Mat4 (16 f32, column-major) + params -> 96-byte ShapeRec with the inverse's linear part.
@@ -800,7 +801,7 @@ constexpr size_t TIER_VA_BYTES = 0;
 // ST_CAPACITY to a device list; one warp per listed pair redoes GJK + EPA against a per-warp global-memory slab.
 // Rare (~6e-5 of mixed pairs), but those pairs are the long tail of the reference's cost.
 constexpr int OVF_WARPS = NUM_SMS;        // one 32-thread block per SM
-constexpr size_t OVF_HEADER_BYTES = 256 + (size_t)OVF_MAX * 4 + (size_t)HUGE_MAX * 4;
+constexpr size_t OVF_HEADER_BYTES = 256 + (size_t)OVF_MAX * 4 + (size_t)HUGE_MAX * 8;  // header, overflow list, third-tier list + its keys
 
 __global__ void __launch_bounds__(32) gjk_contact_overflow_kernel(ShapeSetDev S, const uint2* __restrict__ pairs, SettingsDev cfg,
                                                                   unsigned char* __restrict__ scratch, int producers_running,
@@ -847,8 +848,10 @@ __global__ void __launch_bounds__(32) gjk_contact_overflow_kernel(ShapeSetDev S,
         uint8_t st = gjk_intersect<true, true>(L, R, cfg.max_iterations, s);
         ContactOut c;
         c.normal = v3(0.f, 0.f, 0.f); c.depth = 0.f; c.point = v3(0.f, 0.f, 0.f);
+        uint32_t grown_at = 0;  // vertices the polytope had when it outgrew this tier
         if (st == ST_OK) {
             st = epa_process_big(L, R, s, cfg.epa_tolerance, cfg.max_iterations, B, c);
+            if (st == ST_CAPACITY) grown_at = (uint32_t)c.depth;
             if (st != ST_OK) { c.normal = v3(0.f, 0.f, 0.f); c.depth = 0.f; c.point = v3(0.f, 0.f, 0.f); }
         }
         if (lane == 0) {
@@ -857,7 +860,11 @@ __global__ void __launch_bounds__(32) gjk_contact_overflow_kernel(ShapeSetDev S,
             status[p] = st;
             if (st == ST_CAPACITY) {  // more than EPA_BIG_FCAP faces: the block-per-pair tier takes it (launched behind this kernel)
                 const uint32_t slot = atomicAdd(hdr + HUGE_COUNT, 1u);
-                if (slot < HUGE_MAX) reinterpret_cast<uint32_t*>(scratch + 256 + (size_t)OVF_MAX * 4)[slot] = p;
+                if (slot < HUGE_MAX) {
+                    uint32_t* hl = reinterpret_cast<uint32_t*>(scratch + 256 + (size_t)OVF_MAX * 4);
+                    hl[slot] = p;
+                    hl[HUGE_MAX + slot] = grown_at;
+                }
             }
         }
         __syncwarp();
@@ -869,38 +876,54 @@ __global__ void __launch_bounds__(HUGE_THREADS) gjk_contact_huge_kernel(ShapeSet
                                                                         unsigned char* __restrict__ scratch, unsigned char* __restrict__ slab,
                                                                         float4* __restrict__ contacts, uint8_t* __restrict__ status) {
     __shared__ HugeShared sh;
-    __shared__ uint32_t s_item;
+    __shared__ uint32_t s_item, s_pair;
     __shared__ uint8_t s_st;
-    extern __shared__ __align__(16) uint32_t huge_head[];  // 2 x HUGE_KEYS per-edge counters (epa_huge.cuh)
+    extern __shared__ __align__(16) unsigned char huge_smem[];  // per-edge tables + the short lists of one add() (epa_huge.cuh)
     uint32_t* hdr = reinterpret_cast<uint32_t*>(scratch);
     const uint32_t* list = reinterpret_cast<const uint32_t*>(scratch + 256 + (size_t)OVF_MAX * 4);
     const uint32_t count = min(hdr[HUGE_COUNT], HUGE_MAX);
     if (count == 0) return;
     const HugeStore H = carve_huge_store(slab + (size_t)blockIdx.x * HUGE_SLAB_BYTES);
-    for (uint32_t k = threadIdx.x; k < 2 * HUGE_KEYS; k += HUGE_THREADS) huge_head[k] = 0u;
-    __syncthreads();
+    huge_zero_tables(huge_smem, sh);
     for (;;) {
-        if (threadIdx.x == 0) s_item = atomicAdd(hdr + HUGE_CURSOR, 1u);
+        if (threadIdx.x == 0) { s_item = atomicAdd(hdr + HUGE_CURSOR, 1u); s_pair = 0xFFFFFFFFu; }
         __syncthreads();
         const uint32_t i = s_item;
         if (i >= count) break;
-        const uint32_t p = list[i];
-        const uint2 pr = __ldg(pairs + p);
-        Shape L, R;
-        load_pair_shape(L, S, pr.x);
-        load_pair_shape(R, S, pr.y);
-        Simplex<true> s;
-        s.n = 0;
-        if (threadIdx.x < 32) {
-            const uint8_t st0 = gjk_intersect<true, true>(L, R, cfg.max_iterations, s);
-            if (threadIdx.x == 0) s_st = st0;
+        // Longest job first: a polytope that outgrew the overflow tier early keeps growing for more trips (final faces fall
+        // steeply with the trip it passed 1024 at: 121 962 faces for trip 48, 1 034 for trip 99), and the largest pair alone is
+        // as long as ten ordinary ones. The i-th pair in the order (grown_at, pair index): every block ranks the list itself.
+        if (count <= HUGE_SORT_MAX) {
+            for (uint32_t t = threadIdx.x; t < count; t += HUGE_THREADS) {
+                const unsigned long long kt = ((unsigned long long)list[HUGE_MAX + t] << 32) | list[t];
+                uint32_t rank = 0;
+                for (uint32_t u = 0; u < count; ++u) rank += (((unsigned long long)list[HUGE_MAX + u] << 32) | list[u]) < kt ? 1u : 0u;
+                if (rank == i) s_pair = list[t];
+            }
+            __syncthreads();
+        }
+        const uint32_t p = s_pair != 0xFFFFFFFFu ? s_pair : list[i];
+        if (threadIdx.x < 32) {  // warp 0: the pair's records into shared memory, GJK, the terminal simplex into the vertex lists
+            const uint2 pr = __ldg(pairs + p);
+            if (threadIdx.x == 0) { load_pair_shape(sh.L, S, pr.x); load_pair_shape(sh.R, S, pr.y); }
+            __syncwarp();
+            Simplex<true> s;
+            s.n = 0;
+            const uint8_t st0 = gjk_intersect<true, true>(sh.L, sh.R, cfg.max_iterations, s);
+            if (threadIdx.x == 0) {
+                s_st = st0;
+                if (st0 == ST_OK) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { st3(sh.vv, k, s.v[k]); st3(sh.va, k, s.a[k]); }
+                }
+            }
         }
         __syncthreads();
         uint8_t st = s_st;
         ContactOut c;
         c.normal = v3(0.f, 0.f, 0.f); c.depth = 0.f; c.point = v3(0.f, 0.f, 0.f);
         if (st == ST_OK) {
-            st = epa_process_huge(L, R, s, cfg.epa_tolerance, cfg.max_iterations, H, sh, huge_head, c);
+            st = epa_process_huge(cfg.epa_tolerance, cfg.max_iterations, H, sh, huge_smem, c);
             if (st != ST_OK) { c.normal = v3(0.f, 0.f, 0.f); c.depth = 0.f; c.point = v3(0.f, 0.f, 0.f); }
         }
         if (threadIdx.x == 0) {

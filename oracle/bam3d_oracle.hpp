@@ -510,6 +510,16 @@ struct Polytope {  // epa3d.rs:97-150
             const uint32_t rank = seen[{ev[i].a, ev[i].b}]++;
             keep[i] = (count[{ev[i].a, ev[i].b}] > n_rev && rank >= n_rev) ? 1 : 0;
         }
+#ifdef ORC_RANK_STATS
+        {   // directed edges whose events need a rank (both directions present, this one the majority), and the events they hold
+            uint32_t keys = 0, events = 0;
+            for (auto& kv : count) {
+                auto r = count.find({kv.first.second, kv.first.first});
+                if (r != count.end() && kv.second > r->second) { ++keys; events += kv.second; }
+            }
+            fprintf(stderr, "[rank] F=%zu V=%u keys=%u events=%u\n", F, V, keys, events);
+        }
+#endif
         std::vector<std::pair<uint32_t, uint32_t>> edges;
         for (uint32_t i = 0; i < ev.size(); ++i) if (keep[i]) edges.emplace_back(ev[i].a, ev[i].b);
         if (edges.size() > max_edges) max_edges = (uint32_t)edges.size();
