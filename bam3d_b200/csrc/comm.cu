@@ -20,7 +20,9 @@
 // ever waits for an NCCL kernel while resident, so the two communicators cannot deadlock each other.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -38,9 +40,21 @@ typedef int ncclDataType_t;  // ncclUint8 = 1, ncclUint64 = 5
 constexpr ncclDataType_t NCCL_UINT8 = 1, NCCL_UINT64 = 5;
 static_assert(2 * sizeof(ncclUniqueId) == BAM3D_UNIQUE_ID_BYTES, "unique id size: one NCCL id per communicator");
 
+// ncclConfig_t as NCCL 2.18 defined it (nccl.h: ncclConfig_v21700 with splitShare); later versions read it by its size / version fields
+struct NcclConfig217 {
+    size_t size;
+    unsigned int magic;
+    unsigned int version;
+    int blocking, cgaClusterSize, minCTAs, maxCTAs;
+    const char* netName;
+    int splitShare;
+};
+constexpr int NCCL_UNDEF_INT = (int)0x80000000;  // NCCL_CONFIG_UNDEF_INT (INT_MIN)
+
 struct NcclApi {
     ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitRankConfig)(ncclComm_t*, int, ncclUniqueId, int, NcclConfig217*) = nullptr;  // optional (NCCL >= 2.14)
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
@@ -72,7 +86,25 @@ NcclApi& nccl() {
     api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
     api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
     api.ok = all;
+    api.CommInitRankConfig = (decltype(api.CommInitRankConfig))dlsym(h, "ncclCommInitRankConfig");
     return api;
+}
+
+// A communicator limited to `max_ctas` thread blocks per collective. The exchange kernels mostly WAIT — for the slowest rank to
+// reach the same collective — and a waiting NCCL block holds a multiprocessor the compute lanes could use: measured on the C5
+// step (2 GPUs, payload kernels alive 9.4 ms per step for < 1 ms of transfer), 43.7 ms per step with NCCL's default block count,
+// 41.9 ms with 2 blocks; the volume (104 MB per rank and step) needs no more. Falls back to the default configuration when
+// the library has no ncclCommInitRankConfig.
+ncclResult_t comm_init(NcclApi& N, ncclComm_t* out, int n_ranks, const ncclUniqueId& id, int rank, int max_ctas) {
+    if (N.CommInitRankConfig && max_ctas > 0) {
+        NcclConfig217 cfg;
+        cfg.size = sizeof cfg; cfg.magic = 0xcafebeefu; cfg.version = 21800;
+        cfg.blocking = NCCL_UNDEF_INT; cfg.cgaClusterSize = NCCL_UNDEF_INT;
+        cfg.minCTAs = 1; cfg.maxCTAs = max_ctas;
+        cfg.netName = nullptr; cfg.splitShare = NCCL_UNDEF_INT;
+        return N.CommInitRankConfig(out, n_ranks, id, rank, &cfg);
+    }
+    return N.CommInitRank(out, n_ranks, id, rank);
 }
 
 constexpr int TICKETS = 16;  // count exchanges in flight
@@ -89,6 +121,22 @@ struct bam3d_comm {
     uint64_t* h_counts = nullptr;                   // pinned, TICKETS x n_ranks
     cudaEvent_t counted[TICKETS] = {};
     uint64_t next_ticket = 0;
+    // BAM3D_COMM_TRACE=1 (development): host time blocked on the counts and device time of the payload launches, printed at destroy
+    bool trace = false;
+    cudaEvent_t t0[TICKETS] = {}, t1[TICKETS] = {}, tc0[TICKETS] = {};
+    bool t_open[TICKETS] = {};
+    double host_wait_ms = 0, payload_ms = 0, payload_max_ms = 0, counts_ms = 0, counts_max_ms = 0;
+    uint64_t traced = 0;
+    void collect(int slot) {
+        if (!trace || !t_open[slot]) return;
+        float ms = 0, mc = 0;
+        if (cudaEventSynchronize(t1[slot]) == cudaSuccess && cudaEventElapsedTime(&ms, t0[slot], t1[slot]) == cudaSuccess) {
+            payload_ms += ms; if (ms > payload_max_ms) payload_max_ms = ms;
+        }
+        if (cudaEventElapsedTime(&mc, tc0[slot], counted[slot]) == cudaSuccess) { counts_ms += mc; if (mc > counts_max_ms) counts_max_ms = mc; }
+        ++traced;
+        t_open[slot] = false;
+    }
 };
 
 static int32_t nccl_fail(bam3d_ctx* ctx, const char* what, ncclResult_t r) {
@@ -116,6 +164,13 @@ void bam3d_comm_destroy(bam3d_comm* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->s_counts) cudaStreamSynchronize(c->s_counts);
+    if (c->trace) {
+        for (int t = 0; t < TICKETS; ++t) c->collect(t);
+        std::fprintf(stderr, "[bam3d comm rank %d] %llu exchanges: host blocked on counts %.3f ms avg; count exchange %.3f ms avg (max %.3f) on the device; payload %.3f ms avg (max %.3f)\n",
+                     c->rank, (unsigned long long)c->traced, c->traced ? c->host_wait_ms / c->traced : 0.0, c->traced ? c->counts_ms / c->traced : 0.0, c->counts_max_ms,
+                     c->traced ? c->payload_ms / c->traced : 0.0, c->payload_max_ms);
+        for (int t = 0; t < TICKETS; ++t) { if (c->t0[t]) cudaEventDestroy(c->t0[t]); if (c->t1[t]) cudaEventDestroy(c->t1[t]); if (c->tc0[t]) cudaEventDestroy(c->tc0[t]); }
+    }
     if (c->comm) nccl().CommDestroy(c->comm);
     if (c->comm_counts) nccl().CommDestroy(c->comm_counts);
     for (cudaEvent_t e : c->counted) if (e) cudaEventDestroy(e);
@@ -138,21 +193,33 @@ int32_t bam3d_comm_create(int32_t device, const uint8_t* id, int32_t rank, int32
     bam3d_comm* c = new (std::nothrow) bam3d_comm();
     if (!c) return BAM3D_ERR_OOM;
     c->device = device; c->rank = rank; c->n_ranks = n_ranks;
-    bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
-              cudaStreamCreateWithFlags(&c->s_counts, cudaStreamNonBlocking) == cudaSuccess &&
+    // Exchange streams at the default priority. (BAM3D_COMM_PRIORITY=1 puts them at the highest: measured on 2 GPUs it makes the
+    // C5 step SLOWER, 51.7 vs 44.9 ms — the NCCL kernels then displace blocks of the persistent compute kernels, whose
+    // remaining blocks carry the tail.)
+    int prio_least = 0, prio = 0;
+    bool high = false;
+    if (const char* e = std::getenv("BAM3D_COMM_PRIORITY")) high = std::atoi(e) != 0;
+    if (!high || cudaDeviceGetStreamPriorityRange(&prio_least, &prio) != cudaSuccess) prio = 0;
+    bool ok = cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio) == cudaSuccess &&
+              cudaStreamCreateWithPriority(&c->s_counts, cudaStreamNonBlocking, prio) == cudaSuccess &&
               cudaEventCreateWithFlags(&c->ordered, cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreateWithFlags(&c->done, cudaEventDisableTiming) == cudaSuccess &&
               cudaMalloc(&c->d_counts, sizeof(uint64_t) * TICKETS * n_ranks) == cudaSuccess &&
               cudaHostAlloc(&c->h_counts, sizeof(uint64_t) * TICKETS * n_ranks, cudaHostAllocDefault) == cudaSuccess;
+    if (const char* e = std::getenv("BAM3D_COMM_TRACE")) c->trace = std::atoi(e) != 0;
+    for (int t = 0; ok && c->trace && t < TICKETS; ++t)
+        ok = cudaEventCreate(&c->t0[t]) == cudaSuccess && cudaEventCreate(&c->t1[t]) == cudaSuccess && cudaEventCreate(&c->tc0[t]) == cudaSuccess;
     for (int t = 0; ok && t < TICKETS; ++t)
-        ok = cudaEventCreateWithFlags(&c->counted[t], cudaEventDisableTiming) == cudaSuccess &&
+        ok = cudaEventCreateWithFlags(&c->counted[t], c->trace ? cudaEventDefault : cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&c->exchanged[t], cudaEventDisableTiming) == cudaSuccess;
     if (!ok) { bam3d_comm_destroy(c); return BAM3D_ERR_CUDA; }
     ncclUniqueId uid;
+    int payload_ctas = 4;  // BAM3D_NCCL_MAX_CTAS: thread blocks per payload collective (0: NCCL's default)
+    if (const char* e = std::getenv("BAM3D_NCCL_MAX_CTAS")) payload_ctas = std::atoi(e);
     std::memcpy(uid.internal, id, sizeof uid);
-    if (N.CommInitRank(&c->comm_counts, n_ranks, uid, rank) != 0) { c->comm_counts = nullptr; bam3d_comm_destroy(c); return BAM3D_ERR_COMM; }
+    if (comm_init(N, &c->comm_counts, n_ranks, uid, rank, 1) != 0) { c->comm_counts = nullptr; bam3d_comm_destroy(c); return BAM3D_ERR_COMM; }
     std::memcpy(uid.internal, id + sizeof uid, sizeof uid);
-    if (N.CommInitRank(&c->comm, n_ranks, uid, rank) != 0) { c->comm = nullptr; bam3d_comm_destroy(c); return BAM3D_ERR_COMM; }
+    if (comm_init(N, &c->comm, n_ranks, uid, rank, payload_ctas) != 0) { c->comm = nullptr; bam3d_comm_destroy(c); return BAM3D_ERR_COMM; }
     *out = c;
     return BAM3D_OK;
 }
@@ -174,6 +241,7 @@ int32_t bam3d_gather_contacts_begin(bam3d_ctx* ctx, bam3d_comm* c, const uint64_
     // the count exchange continues after everything enqueued on the ctx stream so far (the compaction that wrote d_count)
     if ((e = cudaEventRecord(c->ordered, ctx->stream)) != cudaSuccess || (e = cudaStreamWaitEvent(c->s_counts, c->ordered, 0)) != cudaSuccess)
         return b3_fail(ctx, BAM3D_ERR_CUDA, "bam3d_gather_contacts_begin: stream ordering", e);
+    if (c->trace) { c->collect(slot); cudaEventRecord(c->tc0[slot], c->s_counts); }
     ncclResult_t r = N.AllGather(d_count, d, 1, NCCL_UINT64, c->comm_counts, c->s_counts);
     if (r != 0) return nccl_fail(ctx, "ncclAllGather(counts)", r);
     if ((e = cudaMemcpyAsync(h, d, sizeof(uint64_t) * c->n_ranks, cudaMemcpyDeviceToHost, c->s_counts)) != cudaSuccess ||
@@ -192,7 +260,9 @@ int32_t bam3d_gather_contacts_finish(bam3d_ctx* ctx, bam3d_comm* c, uint64_t tic
     cudaError_t e;
     if ((e = cudaSetDevice(c->device)) != cudaSuccess) return b3_fail(ctx, BAM3D_ERR_CUDA, "cudaSetDevice", e);
     const int slot = (int)(ticket % TICKETS);
+    const auto hw0 = std::chrono::steady_clock::now();
     if ((e = cudaEventSynchronize(c->counted[slot])) != cudaSuccess) return b3_fail(ctx, BAM3D_ERR_CUDA, "bam3d_gather_contacts_finish: counts", e);
+    if (c->trace) c->host_wait_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - hw0).count();
     const uint64_t* h = c->h_counts + (size_t)slot * c->n_ranks;
     uint64_t total = 0;
     for (int r = 0; r < c->n_ranks; ++r) { if (out_counts) out_counts[r] = h[r]; total += h[r]; }
@@ -205,6 +275,7 @@ int32_t bam3d_gather_contacts_finish(bam3d_ctx* ctx, bam3d_comm* c, uint64_t tic
     if (total == 0) { cudaEventRecord(c->exchanged[slot], c->stream); return BAM3D_OK; }
     if (!d_gathered || (h[c->rank] && !d_compact)) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_gather_contacts_finish: null buffer", cudaSuccess);
     // exact sizes: one broadcast per rank, grouped into a single NCCL launch; rank r's records land behind those of ranks < r
+    if (c->trace) { cudaEventRecord(c->t0[slot], c->stream); c->t_open[slot] = true; }
     ncclResult_t r0 = N.GroupStart();
     if (r0 != 0) return nccl_fail(ctx, "ncclGroupStart", r0);
     uint64_t off = 0;
@@ -220,6 +291,7 @@ int32_t bam3d_gather_contacts_finish(bam3d_ctx* ctx, bam3d_comm* c, uint64_t tic
     r0 = N.GroupEnd();
     if (bad != 0) return nccl_fail(ctx, "ncclBroadcast(contacts)", bad);
     if (r0 != 0) return nccl_fail(ctx, "ncclGroupEnd", r0);
+    if (c->trace) cudaEventRecord(c->t1[slot], c->stream);
     if ((e = cudaEventRecord(c->exchanged[slot], c->stream)) != cudaSuccess) return b3_fail(ctx, BAM3D_ERR_CUDA, "cudaEventRecord", e);
     return BAM3D_OK;
 }
