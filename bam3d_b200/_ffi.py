@@ -12,6 +12,7 @@ LIB_PATH = os.environ.get("BAM3D_LIB") or os.path.join(_HERE, "libbam3d_gpu.so")
 
 OK = 0
 ERR_CUDA, ERR_ARG, ERR_NON_AFFINE, ERR_CAPACITY, ERR_OOM, ERR_COMM = -1, -2, -3, -4, -5, -6
+XFORM_MAT4, XFORM_AFFINE3X4 = 0, 1   # transform layouts of bam3d_frames_set_transform_layout / *_set_transforms_affine
 UNIQUE_ID_BYTES = 256
 
 KIND_PARTICLE, KIND_QUAD, KIND_SPHERE, KIND_CUBOID, KIND_CYLINDER, KIND_CAPSULE, KIND_POLYHEDRON = range(7)
@@ -52,6 +53,8 @@ SIGNATURES = {
     "bam3d_meshes_free": (None, [_vp, _vp]),
     "bam3d_shapes_upload": (_i32, [_vp, _vp, _vp, _vp, _vp, _u32, _vp, C.POINTER(_vp)]),
     "bam3d_shapes_set_transforms": (_i32, [_vp, _vp, _vp]),
+    "bam3d_shapes_set_transforms_affine": (_i32, [_vp, _vp, _vp]),
+    "bam3d_frames_set_transform_layout": (_i32, [_vp, _vp, _i32]),
     "bam3d_shapes_free": (None, [_vp, _vp]),
     "bam3d_shapes_count": (_u32, [_vp]),
     "bam3d_gjk_intersect": (_i32, [_vp, _vp, _vp, _u64, _PS, _vp]),

@@ -257,10 +257,24 @@ class ShapeSet:
         xform = np.ascontiguousarray(xform, dtype=np.float32).reshape(self.n, 16)
         self.ctx.check(self.ctx._lib.bam3d_shapes_set_transforms(self.ctx.handle, self.handle, _ptr(xform)))
 
+    def set_transforms_affine(self, xform12):
+        """The same from affine3x4(xform): 12 floats per shape, a quarter less to upload."""
+        xform12 = np.ascontiguousarray(xform12, dtype=np.float32).reshape(self.n, 12)
+        self.ctx.check(self.ctx._lib.bam3d_shapes_set_transforms_affine(self.ctx.handle, self.handle, _ptr(xform12)))
+
     def close(self):
         if self.handle:
             self.ctx._lib.bam3d_shapes_free(self.ctx.handle, self.handle)
             self.handle = None
+
+
+def affine3x4(xform):
+    """Column-major Mat4 rows [n, 16] -> [n, 12]: the xyz of the four columns (BAM3D_XFORM_AFFINE3X4). The fourth row of a model
+    transform is (0, 0, 0, 1); anything else raises (the Mat4 upload would fail with ERR_NON_AFFINE)."""
+    x = np.ascontiguousarray(xform, dtype=np.float32).reshape(-1, 4, 4)
+    if not (np.all(x[:, :3, 3] == 0.0) and np.all(x[:, 3, 3] == 1.0)):
+        raise ValueError("affine3x4: a transform's fourth row is not (0, 0, 0, 1)")
+    return np.ascontiguousarray(x[:, :, :3]).reshape(-1, 12)
 
 
 def pinned_empty(ctx, shape, dtype):
@@ -303,7 +317,13 @@ class FrameQueue:
                                                          meshes.handle if meshes is not None else None, self.max_pairs, int(depth),
                                                          1 if with_end else 0, C.byref(h)))
         self.handle = h
+        self.xform_width = 16
         self._keep = {}  # frame -> arrays referenced by the copies in flight
+
+    def set_transform_layout(self, layout):
+        """_ffi.XFORM_MAT4 (16 floats per shape, the default) or _ffi.XFORM_AFFINE3X4 (12: see affine3x4) for later submits."""
+        self.ctx.check(self.ctx._lib.bam3d_frames_set_transform_layout(self.ctx.handle, self.handle, int(layout)))
+        self.xform_width = 12 if int(layout) == _ffi.XFORM_AFFINE3X4 else 16
 
     def _submit(self, query, strategy, xform, xform_end, pairs, out_contacts, out_status):
         def chk(a, dtype, shape):
@@ -311,9 +331,9 @@ class FrameQueue:
                 raise ValueError(f"FrameQueue: expected a C-contiguous {np.dtype(dtype).name} array of {shape} elements")
             return a
         n = pairs.size // 2
-        chk(pairs, np.uint32, (n, 2)); chk(xform, np.float32, (self.n_shapes, 16)); chk(out_status, np.uint8, (n,))
+        chk(pairs, np.uint32, (n, 2)); chk(xform, np.float32, (self.n_shapes, self.xform_width)); chk(out_status, np.uint8, (n,))
         if xform_end is not None:
-            chk(xform_end, np.float32, (self.n_shapes, 16))
+            chk(xform_end, np.float32, (self.n_shapes, self.xform_width))
         if out_contacts is not None:
             chk(out_contacts, np.float32, (n, 8))
         frame = C.c_uint64(0)

@@ -416,13 +416,13 @@ void bam3d_meshes_free(bam3d_ctx* ctx, bam3d_meshes* M) {
     delete M;
 }
 
-static int32_t run_pack(bam3d_ctx* ctx, bam3d_shapes* S) {
+static int32_t run_pack(bam3d_ctx* ctx, bam3d_shapes* S, bool affine48 = false) {
     int32_t rc = ctx->small.reserve(ctx, 1024);
     if (rc) return rc;
     uint32_t* d_err = (uint32_t*)ctx->small.ptr + 200;
     cudaMemsetAsync(d_err, 0, sizeof(uint32_t), ctx->stream);
     ctx->launches += launch_pack_shapes(ctx->stream, S->d_kind, S->d_params, S->d_xform, S->d_mesh_id, S->n,
-                                        S->meshes ? S->meshes->n_meshes : 0, S->recs, S->meta, d_err);
+                                        S->meshes ? S->meshes->n_meshes : 0, S->recs, S->meta, d_err, affine48);
     if ((rc = check_launch(ctx, "pack_shapes_kernel"))) return rc;
     uint32_t h_err = 0;
     CU_TRY(cudaMemcpyAsync(&h_err, d_err, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(err)");
@@ -467,6 +467,13 @@ int32_t bam3d_shapes_set_transforms(bam3d_ctx* ctx, bam3d_shapes* S, const float
     CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
     if (S->n) CU_TRY(cudaMemcpyAsync(S->d_xform, xform, (size_t)S->n * 64, cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpyAsync(xform)");
     return run_pack(ctx, S);
+}
+
+int32_t bam3d_shapes_set_transforms_affine(bam3d_ctx* ctx, bam3d_shapes* S, const float* xform12) {
+    if (!ctx || !S || !xform12) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_shapes_set_transforms_affine: null argument", cudaSuccess);
+    CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
+    if (S->n) CU_TRY(cudaMemcpyAsync(S->d_xform, xform12, (size_t)S->n * 48, cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpyAsync(xform)");
+    return run_pack(ctx, S, true);
 }
 
 void bam3d_shapes_free(bam3d_ctx* ctx, bam3d_shapes* S) {
@@ -1514,6 +1521,7 @@ struct bam3d_frames {
     };
     std::vector<Slot> slots;
     uint64_t max_pairs = 0, next_frame = 0;
+    int xform_layout = BAM3D_XFORM_MAT4;  // what submit's xform / xform_end hold
     cudaStream_t s_in = nullptr, s_out = nullptr;
     bam3d_ctx* lanes[2] = {nullptr, nullptr};  // compute lanes (null: the parent ctx computes)
 };
@@ -1673,13 +1681,15 @@ static int32_t frames_submit_impl(bam3d_ctx* ctx, bam3d_frames* F, int32_t query
     sl.shapes->err_flag = sl.d_err + 1;
     if (sl.shapes_end) sl.shapes_end->err_flag = sl.d_err + 1;
     if (ns) {
-        CU_TRY(cudaMemcpyAsync(sl.shapes->d_xform, xform, (size_t)ns * 64, cudaMemcpyHostToDevice, F->s_in), "cudaMemcpyAsync(xform)");
+        const bool affine48 = F->xform_layout == BAM3D_XFORM_AFFINE3X4;
+        const size_t xbytes = (size_t)ns * (affine48 ? 48 : 64);
+        CU_TRY(cudaMemcpyAsync(sl.shapes->d_xform, xform, xbytes, cudaMemcpyHostToDevice, F->s_in), "cudaMemcpyAsync(xform)");
         ctx->launches += launch_pack_shapes(F->s_in, sl.shapes->d_kind, sl.shapes->d_params, sl.shapes->d_xform, sl.shapes->d_mesh_id, ns,
-                                            n_meshes, sl.shapes->recs, sl.shapes->meta, sl.d_err);
+                                            n_meshes, sl.shapes->recs, sl.shapes->meta, sl.d_err, affine48);
         if (query == BAM3D_FRAME_TIME_OF_IMPACT) {
-            CU_TRY(cudaMemcpyAsync(sl.shapes_end->d_xform, xform_end, (size_t)ns * 64, cudaMemcpyHostToDevice, F->s_in), "cudaMemcpyAsync(xform_end)");
+            CU_TRY(cudaMemcpyAsync(sl.shapes_end->d_xform, xform_end, xbytes, cudaMemcpyHostToDevice, F->s_in), "cudaMemcpyAsync(xform_end)");
             ctx->launches += launch_pack_shapes(F->s_in, sl.shapes_end->d_kind, sl.shapes_end->d_params, sl.shapes_end->d_xform,
-                                                sl.shapes_end->d_mesh_id, ns, n_meshes, sl.shapes_end->recs, sl.shapes_end->meta, sl.d_err);
+                                                sl.shapes_end->d_mesh_id, ns, n_meshes, sl.shapes_end->recs, sl.shapes_end->meta, sl.d_err, affine48);
         }
     }
     if (n) CU_TRY(cudaMemcpyAsync(sl.d_pairs, pairs, n * 8, cudaMemcpyHostToDevice, F->s_in), "cudaMemcpyAsync(pairs)");
@@ -1716,6 +1726,13 @@ static int32_t frames_submit_impl(bam3d_ctx* ctx, bam3d_frames* F, int32_t query
 }
 
 extern "C" {
+
+int32_t bam3d_frames_set_transform_layout(bam3d_ctx* ctx, bam3d_frames* F, int32_t layout) {
+    if (!ctx || !F || (layout != BAM3D_XFORM_MAT4 && layout != BAM3D_XFORM_AFFINE3X4))
+        return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_frames_set_transform_layout: unknown layout", cudaSuccess);
+    F->xform_layout = layout;
+    return BAM3D_OK;
+}
 
 int32_t bam3d_frames_submit(bam3d_ctx* ctx, bam3d_frames* F, int32_t query, const float* xform, const float* xform_end,
                             const uint32_t* pairs, uint64_t n, const bam3d_gjk_settings* settings, int32_t strategy,

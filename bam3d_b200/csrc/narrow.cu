@@ -45,17 +45,30 @@ constexpr uint32_t HUGE_SORT_MAX = 1024;  // third-tier lists up to this long ar
 // order; only its upper-left 3x3 is kept because the reference only ever applies the inverse through
 // transform_vector3 (primitive/util.rs:11, sphere.rs:22, cylinder.rs:39, capsule.rs:43, polyhedron.rs:346-350).
 // ------------------------------------------------------------------------------------------------------------
+// AFFINE48: the transforms arrive as 12 floats per shape — the xyz of the four columns, i.e. the Mat4 without its fourth row,
+// which a model transform has as (0, 0, 0, 1) (anything else is rejected below) — a quarter less to move over PCIe per frame.
+// The same expressions are then evaluated on the same 16 values: bit-identical records.
+template <bool AFFINE48>
 __global__ void __launch_bounds__(TPB) pack_shapes_kernel(const uint8_t* __restrict__ kind, const float4* __restrict__ params,
                                                           const float4* __restrict__ xform, const uint32_t* __restrict__ mesh_id,
                                                           uint32_t n, uint32_t n_meshes, ShapeRec* __restrict__ recs,
                                                           uint32_t* __restrict__ meta, uint32_t* __restrict__ err) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    float4 cx = xform[4 * (size_t)i + 0], cy = xform[4 * (size_t)i + 1], cz = xform[4 * (size_t)i + 2], cw = xform[4 * (size_t)i + 3];
-    float m00 = cx.x, m01 = cx.y, m02 = cx.z, m03 = cx.w;
-    float m10 = cy.x, m11 = cy.y, m12 = cy.z, m13 = cy.w;
-    float m20 = cz.x, m21 = cz.y, m22 = cz.z, m23 = cz.w;
-    float m30 = cw.x, m31 = cw.y, m32 = cw.z, m33 = cw.w;
+    float m00, m01, m02, m03, m10, m11, m12, m13, m20, m21, m22, m23, m30, m31, m32, m33;
+    if (AFFINE48) {
+        const float4 a = xform[3 * (size_t)i + 0], b = xform[3 * (size_t)i + 1], c = xform[3 * (size_t)i + 2];
+        m00 = a.x; m01 = a.y; m02 = a.z; m03 = 0.f;
+        m10 = a.w; m11 = b.x; m12 = b.y; m13 = 0.f;
+        m20 = b.z; m21 = b.w; m22 = c.x; m23 = 0.f;
+        m30 = c.y; m31 = c.z; m32 = c.w; m33 = 1.f;
+    } else {
+        const float4 cx = xform[4 * (size_t)i + 0], cy = xform[4 * (size_t)i + 1], cz = xform[4 * (size_t)i + 2], cw = xform[4 * (size_t)i + 3];
+        m00 = cx.x; m01 = cx.y; m02 = cx.z; m03 = cx.w;
+        m10 = cy.x; m11 = cy.y; m12 = cy.z; m13 = cy.w;
+        m20 = cz.x; m21 = cz.y; m22 = cz.z; m23 = cz.w;
+        m30 = cw.x; m31 = cw.y; m32 = cw.z; m33 = cw.w;
+    }
     uint32_t e = 0;
     if (!(m03 == 0.f && m13 == 0.f && m23 == 0.f && m33 == 1.f)) e |= ERR_NON_AFFINE;
 
@@ -1465,10 +1478,14 @@ static inline int grid_for(uint64_t items, int per_block, int max_blocks) {
 }
 
 int launch_pack_shapes(cudaStream_t st, const uint8_t* d_kind, const float* d_params, const float* d_xform,
-                       const uint32_t* d_mesh_id, uint32_t n, uint32_t n_meshes, ShapeRec* recs, uint32_t* meta, uint32_t* d_err) {
+                       const uint32_t* d_mesh_id, uint32_t n, uint32_t n_meshes, ShapeRec* recs, uint32_t* meta, uint32_t* d_err, bool affine48) {
     if (n == 0) return 0;
-    pack_shapes_kernel<<<(n + TPB - 1) / TPB, TPB, 0, st>>>(d_kind, reinterpret_cast<const float4*>(d_params),
-                                                            reinterpret_cast<const float4*>(d_xform), d_mesh_id, n, n_meshes, recs, meta, d_err);
+    if (affine48)
+        pack_shapes_kernel<true><<<(n + TPB - 1) / TPB, TPB, 0, st>>>(d_kind, reinterpret_cast<const float4*>(d_params),
+                                                                      reinterpret_cast<const float4*>(d_xform), d_mesh_id, n, n_meshes, recs, meta, d_err);
+    else
+        pack_shapes_kernel<false><<<(n + TPB - 1) / TPB, TPB, 0, st>>>(d_kind, reinterpret_cast<const float4*>(d_params),
+                                                                       reinterpret_cast<const float4*>(d_xform), d_mesh_id, n, n_meshes, recs, meta, d_err);
     return 1;
 }
 

@@ -36,7 +36,7 @@ struct BinScratch {
 // Each launcher returns the number of kernels it enqueued (for the launch counter); errors via cudaGetLastError.
 int launch_pack_shapes(cudaStream_t st, const uint8_t* d_kind, const float* d_params, const float* d_xform,
                        const uint32_t* d_mesh_id, uint32_t n, uint32_t n_meshes, ShapeRec* recs, uint32_t* meta,
-                       uint32_t* d_err);
+                       uint32_t* d_err, bool affine48 = false);
 // planes of the half-edge meshes' faces (2 x uint4 per face: indices, then vertex-slot base -> plane); *d_err != 0: degenerate face
 int launch_mesh_face_planes(cudaStream_t st, const float4* d_verts, uint4* d_faces, uint64_t nfaces, uint32_t* d_err);
 int launch_bin_pairs(cudaStream_t st, const ShapeSetDev& S, const uint2* d_pairs, uint32_t n, const BinScratch& B);

@@ -518,15 +518,24 @@ def make_queue(env, scene, meshes, n, query, base, gather_cap):
     torch, lib, ctx = env.torch, env.lib, env.ctxs[0]
     kind, params = np.ascontiguousarray(scene["kind"], dtype=np.uint8), np.ascontiguousarray(scene["params"], dtype=np.float32)
     mesh_id = None if scene.get("mesh_id") is None else np.ascontiguousarray(scene["mesh_id"], dtype=np.uint32)
-    hx = torch.from_numpy(scene["xform"]).pin_memory()
+    # per-frame transforms in the 48-byte layout (the four columns' xyz: a model transform's fourth row is (0,0,0,1), and the
+    # 64-byte form is rejected when it is not); BAM3D_BENCH_MAT4=1 uploads whole Mat4s instead
+    from bam3d_b200 import api as b3api, _ffi
+    affine = not os.environ.get("BAM3D_BENCH_MAT4")
+    conv = (lambda x: b3api.affine3x4(x)) if affine else (lambda x: x)
+    x0 = np.ascontiguousarray(scene["xform"], dtype=np.float32)
+    hx = torch.from_numpy(conv(x0)).pin_memory()
     q = {"query": query, "n": n, "base": base, "hx": hx, "hpairs": torch.from_numpy(scene["pairs"].astype(np.int32)).pin_memory()}
     if query == 2:
-        q["hx_end"] = torch.from_numpy(scene["xform_end"]).pin_memory()
+        q["hx_end"] = torch.from_numpy(conv(scene["xform_end"])).pin_memory()
     handle = C.c_void_p()
-    ctx.check(lib.bam3d_frames_create(ctx.handle, C.c_void_p(kind.ctypes.data), C.c_void_p(params.ctypes.data), C.c_void_p(hx.data_ptr()),
+    ctx.check(lib.bam3d_frames_create(ctx.handle, C.c_void_p(kind.ctypes.data), C.c_void_p(params.ctypes.data), C.c_void_p(x0.ctypes.data),
                                       C.c_void_p(mesh_id.ctypes.data) if mesh_id is not None else None, len(kind),
                                       meshes.handle if meshes is not None else None, n, 2, 1 if query == 2 else 0, C.byref(handle)))
+    if affine:
+        ctx.check(lib.bam3d_frames_set_transform_layout(ctx.handle, handle, _ffi.XFORM_AFFINE3X4))
     q["handle"] = handle
+    q["xform_bytes"] = 48 if affine else 64
     bufs = []
     for _ in range(2):
         b = {"status": torch.empty(n, dtype=torch.uint8).pin_memory()}
@@ -537,7 +546,7 @@ def make_queue(env, scene, meshes, n, query, base, gather_cap):
                 b["contacts"] = torch.empty((n, 8), dtype=torch.float32).pin_memory()
         bufs.append(b)
     q["bufs"] = bufs
-    q["h2d"] = len(kind) * 64 * (2 if query == 2 else 1) + n * 8
+    q["h2d"] = len(kind) * q["xform_bytes"] * (2 if query == 2 else 1) + n * 8
     return q
 
 
@@ -585,14 +594,14 @@ def bench_narrow(env, wl, n, steps, warmup, cpu_pairs, cpu_budget):
     gather = has_contacts and env.world > 1
     gcap = int(1.1 * hit_rate * n * env.world) + 65536 if gather else None  # every rank's slice has the same hit rate up to sampling noise
     q = make_queue(env, scene, meshes, n, {"c1": 0, "toi": 2}.get(wl, 1), env.rank * n, gcap) if wl != "dist" else None
-    e2e_steps = max(3, min(steps, 10))
+    e2e_steps = max(3, steps)  # the same K steps, pipeline fill and drain inside the timed region
     if q is not None:
         dt = e2e_frames(env, [q], e2e_steps, gather)
         e2e_value = env.world * n * e2e_steps / dt
         d2h = n + (0 if wl == "c1" else (int(hit_rate * n * env.world) * 40 if gather else n * 32))
         e2e = {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": q["h2d"], "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                "path": "bam3d_frames_submit" + ("_gather" if gather else "") + " / bam3d_frames_wait, 2 frames in flight on two compute lanes: every frame copies its "
-                       "transforms + pairs in from pinned host memory and its status + " + ("the gathered hits of all ranks" if gather else "contacts") +
+                       "transforms (48 B each: the Mat4 without its constant fourth row) + pairs in from pinned host memory and its status + " + ("the gathered hits of all ranks" if gather else "contacts") +
                        " out to pinned host memory"}
         # the queue's results are the resident path's (bit for bit)
         st_q = q["bufs"][0]["status"]
@@ -707,7 +716,7 @@ def bench_c5(env, n, steps, warmup, cpu_pairs, cpu_budget):
     part_hits = {k: int((status_mixed[off[k]: off[k] + sizes[k]] == 0).sum().item()) for k in order}
     queues = [make_queue(env, parts[k], meshes if k == "poly" else None, sizes[k], query[k], base[k],
                          int(1.1 * part_hits[k] * env.world) + 65536 if gather else None) for k in ("contact", "intersect", "poly", "toi")]
-    e2e_steps = max(3, min(steps, 5))
+    e2e_steps = max(3, steps)  # the same K steps, pipeline fill and drain inside the timed region
     dt = e2e_frames(env, queues, e2e_steps, gather)
     e2e_value = env.world * n * e2e_steps / dt
     for q, k in zip(queues, ("contact", "intersect", "poly", "toi")):
@@ -733,7 +742,7 @@ def bench_c5(env, n, steps, warmup, cpu_pairs, cpu_budget):
                                 "what": "GJK+EPA Contact (FullResolution) over ALL pairs of the C5 slice, compaction + NCCL gather inside"},
                 "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                         "path": "one frame queue per sub-batch (bam3d_frames_submit" + ("_gather" if gather else "") + " / bam3d_frames_wait), 2 frames in flight on two compute "
-                                "lanes: every step copies its transforms + pairs in from pinned host memory and its status + " +
+                                "lanes: every step copies its transforms (48 B each: the Mat4 without its constant fourth row) + pairs in from pinned host memory and its status + " +
                                 ("the gathered hits of all ranks" if gather else "contacts") + " out to pinned host memory"},
                 "gpu_launches": launches + launches_i + launches_c, "clocks": env.clocks(),
                 "roofline": roofline_for("c5", ALGO_BYTES["c5"] * n, kernel_ms, f"{ALGO_BYTES['c5']:.1f} B/pair (the mix of the four rows of DESIGN.md §5) x {n} pairs per step"),
@@ -781,7 +790,7 @@ def bench_c4(env, n, steps, warmup, cpu_boxes):
     def step_e2e():
         axis = C.c_int32(0)
         ctx.check(lib.bam3d_sap_find_pairs_shard(h, hp(h_boxes), n, C.byref(axis), hp(h_perm), hp(h_pairs), cap, C.byref(cnt), rank, world))
-    e2e_steps = max(3, min(steps, 5))
+    e2e_steps = max(3, steps)  # the same K steps, pipeline fill and drain inside the timed region
     step_e2e(); env.sync_all()
     w0 = time.time(); t0 = time.perf_counter()
     for _ in range(e2e_steps):

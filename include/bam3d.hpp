@@ -97,6 +97,8 @@ public:
     ShapeSet& operator=(const ShapeSet&) = delete;
     bam3d_shapes* handle() const { return h_; }
     void set_transforms(const std::vector<Mat4>& xforms) { ctx_.check(bam3d_shapes_set_transforms(ctx_.handle(), h_, xforms.data()->data())); }
+    /// The same from the 48-byte layout (the four columns' xyz; see affine3x4): a quarter less to upload per frame.
+    void set_transforms(const std::vector<std::array<float, 12>>& xforms) { ctx_.check(bam3d_shapes_set_transforms_affine(ctx_.handle(), h_, xforms.data()->data())); }
 private:
     const Context& ctx_;
     bam3d_shapes* h_ = nullptr;

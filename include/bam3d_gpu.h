@@ -139,6 +139,12 @@ int32_t bam3d_shapes_upload(bam3d_ctx* ctx, const uint8_t* kind, const float* pa
                             const uint32_t* mesh_id, uint32_t n, const bam3d_meshes* meshes, bam3d_shapes** out);
 /* replace every transform (next frame) without re-sending kinds / params */
 int32_t bam3d_shapes_set_transforms(bam3d_ctx* ctx, bam3d_shapes* shapes, const float* xform);
+/* The same from 12 floats per shape: the xyz of the x, y, z and w columns — the column-major Mat4 without its fourth row. A
+ * model transform has (0, 0, 0, 1) there (the Mat4 form fails with BAM3D_ERR_NON_AFFINE otherwise), so nothing is lost and a
+ * quarter less crosses PCIe per frame; the records built on the device are bit-identical. */
+int32_t bam3d_shapes_set_transforms_affine(bam3d_ctx* ctx, bam3d_shapes* shapes, const float* xform12);
+#define BAM3D_XFORM_MAT4 0       /* 16 floats per shape, column-major (glam Mat4) */
+#define BAM3D_XFORM_AFFINE3X4 1  /* 12 floats per shape: the four columns' xyz */
 void bam3d_shapes_free(bam3d_ctx* ctx, bam3d_shapes* shapes);
 uint32_t bam3d_shapes_count(const bam3d_shapes* shapes);
 
@@ -369,6 +375,8 @@ int32_t bam3d_frames_create(bam3d_ctx* ctx, const uint8_t* kind, const float* pa
                             bam3d_frames** out);
 /* Enqueue one frame and return at once; *out_frame (may be NULL) = its number (0, 1, 2, ... in submission order). Blocks only
  * while the frame `depth` submissions ago is still in flight. xform_end is read for BAM3D_FRAME_TIME_OF_IMPACT only. */
+/* Layout of the xform / xform_end arrays later submits pass (BAM3D_XFORM_*; default BAM3D_XFORM_MAT4). */
+int32_t bam3d_frames_set_transform_layout(bam3d_ctx* ctx, bam3d_frames* frames, int32_t layout);
 int32_t bam3d_frames_submit(bam3d_ctx* ctx, bam3d_frames* frames, int32_t query, const float* xform, const float* xform_end,
                             const uint32_t* pairs, uint64_t n, const bam3d_gjk_settings* settings, int32_t strategy,
                             bam3d_contact* out_contacts, uint8_t* out_status, uint64_t* out_frame);

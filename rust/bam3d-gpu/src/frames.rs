@@ -21,6 +21,19 @@ impl<'a> FrameQueue<'a> {
                                                     max_pairs as u64, depth, with_end as i32, &mut h) })?;
         Ok(FrameQueue { ctx, h, cfg: *gjk.settings(), _meshes: meshes })
     }
+    /// Later submits pass 12 floats per shape (the four columns' xyz; `ShapeSet::set_transforms_affine` describes the layout)
+    /// through the `*_affine` methods: a quarter less to upload per frame.
+    pub fn use_affine_layout(&mut self) -> Result<()> {
+        self.ctx.check(unsafe { ffi::bam3d_frames_set_transform_layout(self.ctx.0, self.h, ffi::XFORM_AFFINE3X4) })
+    }
+    /// `submit_intersection` in the 48-byte layout (after `use_affine_layout`).
+    pub fn submit_intersection_affine(&mut self, strategy: &CollisionStrategy, xform: &Pinned<[f32; 12]>, pairs: &Pinned<(u32, u32)>,
+                                      out: &mut Pinned<ffi::RawContact>, status: &mut Pinned<u8>) -> Result<u64> {
+        let mut f = 0u64;
+        self.ctx.check(unsafe { ffi::bam3d_frames_submit(self.ctx.0, self.h, ffi::FRAME_CONTACT, xform.p as *const f32, std::ptr::null(), pairs.p as *const u32,
+                                                         pairs.len as u64, &self.cfg, code(strategy), out.p, status.p, &mut f) })?;
+        Ok(f)
+    }
     /// `GJK::intersect` for every pair under this frame's transforms; returns the frame number.
     pub fn submit_intersect(&mut self, xform: &Pinned<[f32; 16]>, pairs: &Pinned<(u32, u32)>, status: &mut Pinned<u8>) -> Result<u64> {
         let mut f = 0u64;

@@ -122,6 +122,13 @@ impl<'a> ShapeSet<'a> {
         let flat: Vec<f32> = transforms.iter().flat_map(|t| t.to_cols_array().to_vec()).collect();
         self.ctx.check(unsafe { ffi::bam3d_shapes_set_transforms(self.ctx.0, self.h, flat.as_ptr()) })
     }
+    /// The same in the 48-byte layout (the four columns' xyz — a model transform's fourth row is (0, 0, 0, 1)): a quarter
+    /// less to upload per frame, bit-identical records on the device.
+    pub fn set_transforms_affine(&mut self, transforms: &[Mat4]) -> Result<()> {
+        assert_eq!(transforms.len(), self.n);
+        let flat: Vec<f32> = transforms.iter().flat_map(|t| { let c = t.to_cols_array(); [c[0], c[1], c[2], c[4], c[5], c[6], c[8], c[9], c[10], c[12], c[13], c[14]] }).collect();
+        self.ctx.check(unsafe { ffi::bam3d_shapes_set_transforms_affine(self.ctx.0, self.h, flat.as_ptr()) })
+    }
 }
 impl<'a> Drop for ShapeSet<'a> { fn drop(&mut self) { unsafe { ffi::bam3d_shapes_free(self.ctx.0, self.h) } } }
 

@@ -624,6 +624,58 @@ def test_frame_queue_matches_synchronous_calls(ctx, oracle, depth):
     q.close()
 
 
+def test_affine_transform_layout_is_bit_identical(ctx, oracle):
+    """BAM3D_XFORM_AFFINE3X4 (12 floats per shape: the Mat4 without its constant fourth row) through set_transforms_affine and
+    through a frame queue (contact + time of impact) returns exactly what the Mat4 upload returns, which is the oracle's."""
+    from bam3d_b200 import _ffi
+    from bam3d_b200.api import affine3x4
+    scene = scenes.mixed_pairs(20_000, s=1.5, seed=0xB3D000FA)
+    n_shapes, n = len(scene["kind"]), len(scene["pairs"])
+    gjk = b3.GJK.new(ctx)
+    x0 = np.ascontiguousarray(scene["xform"], dtype=np.float32).reshape(n_shapes, 16)
+    x1 = np.ascontiguousarray(scenes.end_transforms(scene, span=2.0), dtype=np.float32).reshape(n_shapes, 16)
+    a0, a1 = affine3x4(x0), affine3x4(x1)
+    assert a0.shape == (n_shapes, 12) and np.array_equal(a0[:, 9:12], x0[:, 12:15])
+    FR = b3.CollisionStrategy.FullResolution
+    shapes = shapes_of(ctx, scene)
+    want_c, want_st = gjk.intersection_batch(FR, shapes, scene["pairs"])
+    oc, _, ost = oracle.contact(scene, nthreads=8)
+    assert np.array_equal(want_st, ost)
+    assert_f32_equal("contact vs oracle", want_c[:, 0:7], oc[:, 0:7], ost == 0)
+    # set_transforms_affine: move away and back
+    shapes.set_transforms_affine(a1)
+    moved_c, moved_st = gjk.intersection_batch(FR, shapes, scene["pairs"])
+    shapes.set_transforms(x1)
+    c1, st1 = gjk.intersection_batch(FR, shapes, scene["pairs"])
+    assert np.array_equal(moved_st, st1) and np.array_equal(bits(moved_c), bits(c1))
+    shapes.set_transforms_affine(a0)
+    c0, st0 = gjk.intersection_batch(FR, shapes, scene["pairs"])
+    assert np.array_equal(st0, want_st) and np.array_equal(bits(c0), bits(want_c))
+    # frame queue in the 48-byte layout
+    s_end = shapes_of(ctx, scene, x1)
+    toi_c, toi_st = gjk.intersection_time_of_impact_batch(shapes, s_end, scene["pairs"])
+    q = b3.FrameQueue(gjk, scene["kind"], scene["params"], x0, max_pairs=n, depth=2, with_end=True)
+    q.set_transform_layout(_ffi.XFORM_AFFINE3X4)
+    pairs = np.ascontiguousarray(scene["pairs"], dtype=np.uint32)
+    hc, hs = np.full((n, 8), np.nan, dtype=np.float32), np.full(n, 0xEE, dtype=np.uint8)
+    hc2, hs2 = np.full((n, 8), np.nan, dtype=np.float32), np.full(n, 0xEE, dtype=np.uint8)
+    f1 = q.submit_contact(FR, a0, pairs, hc, hs)
+    f2 = q.submit_time_of_impact(a0, a1, pairs, hc2, hs2)
+    q.wait(f1)
+    q.wait(f2)
+    assert np.array_equal(hs, want_st) and np.array_equal(bits(hc), bits(want_c))
+    assert np.array_equal(hs2, toi_st) and np.array_equal(bits(hc2), bits(toi_c))
+    with pytest.raises(ValueError):
+        q.submit_contact(FR, x0, pairs, hc, hs)       # a Mat4 array while the queue expects 12 floats per shape
+    with pytest.raises(b3.Bam3dError):
+        q.set_transform_layout(7)
+    bad = x0.copy()
+    bad[3, 15] = 2.0
+    with pytest.raises(ValueError):
+        affine3x4(bad)
+    q.close()
+
+
 def test_frame_queue_time_of_impact_errors_and_empty(ctx, oracle):
     scene = scenes.mixed_pairs(4_000, s=1.5, seed=0xB3D000F8)
     n_shapes, n = len(scene["kind"]), len(scene["pairs"])
