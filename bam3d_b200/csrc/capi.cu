@@ -158,11 +158,12 @@ void bam3d_default_settings(bam3d_gjk_settings* out) {
 }
 
 // The side stream carries the EPA overflow tiers: the longest jobs of a contact call, few blocks, each needing most of an SM.
-// At the highest priority their blocks are placed first whenever a multiprocessor drains, instead of queueing behind the
-// wide kernels of another compute lane. (BAM3D_SIDE_PRIORITY=0: default priority.)
+// Default priority. (BAM3D_SIDE_PRIORITY=1 creates it at the highest priority so that its blocks are placed first whenever a
+// multiprocessor drains: measured, no gain on C2 / C5 with two compute lanes — and the overflow consumer SPINS until its
+// producers have exited, so favouring it over the producers of other lanes is the wrong way round.)
 static cudaError_t create_side_stream(cudaStream_t* s) {
     int least = 0, greatest = 0;
-    bool high = true;
+    bool high = false;
     if (const char* e = std::getenv("BAM3D_SIDE_PRIORITY")) high = std::atoi(e) != 0;
     if (!high || cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess) return cudaStreamCreateWithFlags(s, cudaStreamNonBlocking);
     return cudaStreamCreateWithPriority(s, cudaStreamNonBlocking, greatest);

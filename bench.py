@@ -349,7 +349,10 @@ class Env:
         from bam3d_b200 import build, multi
         build.build()
         self.b3 = b3
-        self.ctxs = [b3.Context(self.local_rank), b3.Context(self.local_rank)]
+        # compute lanes: library contexts with their own stream and scratch; step k runs on lane k % lanes, so the steps in
+        # flight overlap each other's serial tails (EPA drain, overflow tiers) — BAM3D_BENCH_LANES (default 2)
+        self.lanes = max(1, int(os.environ.get("BAM3D_BENCH_LANES", "2")))
+        self.ctxs = [b3.Context(self.local_rank) for _ in range(self.lanes)]
         self.gjks = [b3.GJK.new(c) for c in self.ctxs]
         self.lib = self.ctxs[0]._lib
         self.ext = [torch.cuda.ExternalStream(c.stream, device=self.dev) for c in self.ctxs]
@@ -386,7 +389,7 @@ class Env:
     def timed(self, enqueue, steps, warmup):
         """`warmup` untimed steps, then exactly `steps` steps bracketed by barrier + synchronize on both sides, timed with
         CUDA events on lane 0's stream (the end event waits for lane 1 and the exchange). enqueue(k) enqueues step k on lane
-        k % 2 and returns nothing; enqueue.finish() completes whatever is still pending (exchange). -> (ms max over ranks, launches)"""
+        k % lanes and returns nothing; enqueue.finish() completes whatever is still pending (exchange). -> (ms max over ranks, launches)"""
         torch = self.torch
         for k in range(warmup):
             enqueue(k)
@@ -399,8 +402,9 @@ class Env:
         for k in range(steps):
             enqueue(warmup + k)
         enqueue.finish()
-        evl.record(self.ext[1])
-        self.ext[0].wait_event(evl)
+        for x in self.ext[1:]:
+            evl.record(x)
+            self.ext[0].wait_event(evl)
         if self.comm is not None:
             self.comm.join(self.ctxs[0])
         ev1.record(self.ext[0])
@@ -433,9 +437,9 @@ def dptr(t, off=0):
 
 
 class Exchange:
-    """Per-lane buffers and bookkeeping of the contact exchange for a resident loop. Step k (lane k % 2) is: its kernels; then the
-    payload of step k - 2 (the step that last used this lane: by now its counts are on the host, so the call rarely blocks);
-    then compaction and the count exchange of step k. The host blocks only when it is two steps ahead of the device, so every
+    """Per-lane buffers and bookkeeping of the contact exchange for a resident loop. Step k (lane k % L) is: its kernels; then the
+    payload of step k - L (the step that last used this lane: by now its counts are on the host, so the call rarely blocks);
+    then compaction and the count exchange of step k. The host blocks only when it is L steps ahead of the device, so every
     lane always has its next step queued behind the running one — finishing step k - 1 here instead (one step less latency for
     the payload) leaves the lane idle from the moment its step ends until the host has seen the counts, relaunched and the peers
     have caught up: 44.5 instead of 41.4 ms per C5 step on 2 GPUs."""
@@ -443,10 +447,11 @@ class Exchange:
     def __init__(self, env, n_dense):
         torch = env.torch
         self.env, self.n = env, n_dense
-        self.compact = [torch.empty(n_dense * 10, dtype=torch.int32, device=env.dev) for _ in range(2)]
-        self.count = [torch.zeros(1, dtype=torch.int64, device=env.dev) for _ in range(2)]
-        self.gathered = [torch.empty(env.world * n_dense * 10, dtype=torch.int32, device=env.dev) for _ in range(2)] if env.comm is not None else None
-        self.ticket = [None, None]   # per lane: the exchange whose payload has not been enqueued yet
+        L = env.lanes
+        self.compact = [torch.empty(n_dense * 10, dtype=torch.int32, device=env.dev) for _ in range(L)]
+        self.count = [torch.zeros(1, dtype=torch.int64, device=env.dev) for _ in range(L)]
+        self.gathered = [torch.empty(env.world * n_dense * 10, dtype=torch.int32, device=env.dev) for _ in range(L)] if env.comm is not None else None
+        self.ticket = [None] * L   # per lane: the exchange whose payload has not been enqueued yet
         self.total = 0
 
     def after_step(self, lane, d_contacts, d_status):
@@ -469,7 +474,7 @@ class Exchange:
         """The payloads still owed, oldest first (every rank issues its collectives in the same order)."""
         if self.env.comm is None:
             return
-        for lane in sorted((l for l in (0, 1) if self.ticket[l] is not None), key=lambda l: self.ticket[l]):
+        for lane in sorted((l for l in range(self.env.lanes) if self.ticket[l] is not None), key=lambda l: self.ticket[l]):
             self.finish_lane(lane)
 
 
@@ -560,10 +565,10 @@ def bench_narrow(env, wl, n, steps, warmup, cpu_pairs, cpu_budget):
     shapes_end = b3.ShapeSet(ctx0, scene["kind"], scene["params"], scene["xform_end"], scene.get("mesh_id"), meshes) if wl == "toi" else None
     n_shapes = len(scene["kind"])
     d_pairs = torch.from_numpy(scene["pairs"].astype(np.int32).reshape(-1)).to(env.dev)
-    d_status = [torch.empty(n, dtype=torch.uint8, device=env.dev) for _ in range(2)]
+    d_status = [torch.empty(n, dtype=torch.uint8, device=env.dev) for _ in range(env.lanes)]
     has_contacts = wl in ("c2", "c3", "toi")
-    d_contacts = [torch.empty(n * 8, dtype=torch.float32, device=env.dev) for _ in range(2)] if has_contacts else None
-    d_f = [torch.empty(2 * n, dtype=torch.float32, device=env.dev) for _ in range(2)] if wl == "dist" else None
+    d_contacts = [torch.empty(n * 8, dtype=torch.float32, device=env.dev) for _ in range(env.lanes)] if has_contacts else None
+    d_f = [torch.empty(2 * n, dtype=torch.float32, device=env.dev) for _ in range(env.lanes)] if wl == "dist" else None
     xch = Exchange(env, n) if (has_contacts and env.world > 1) else None
     FR = b3.CollisionStrategy.FullResolution
 
@@ -579,7 +584,7 @@ def bench_narrow(env, wl, n, steps, warmup, cpu_pairs, cpu_budget):
             gjk.intersection_dev(FR, shapes, dptr(d_pairs), n, dptr(d_contacts[lane]), dptr(d_status[lane]))
 
     def enqueue(k):
-        lane = k & 1
+        lane = k % env.lanes
         compute(lane)
         if xch is not None:
             xch.after_step(lane, d_contacts[lane], d_status[lane])
@@ -666,8 +671,8 @@ def bench_c5(env, n, steps, warmup, cpu_pairs, cpu_budget):
         off[k] = acc
         acc += sizes[k]
     n_dense = acc - sizes["intersect"]  # the three contact-producing sub-batches come first
-    d_status = [torch.empty(n, dtype=torch.uint8, device=env.dev) for _ in range(2)]
-    d_contacts = [torch.empty(n * 8, dtype=torch.float32, device=env.dev) for _ in range(2)]
+    d_status = [torch.empty(n, dtype=torch.uint8, device=env.dev) for _ in range(env.lanes)]
+    d_contacts = [torch.empty(n * 8, dtype=torch.float32, device=env.dev) for _ in range(env.lanes)]
     FR = b3.CollisionStrategy.FullResolution
 
     def mixed(lane):
@@ -692,7 +697,7 @@ def bench_c5(env, n, steps, warmup, cpu_pairs, cpu_budget):
         xch = Exchange(env, n_x) if with_exchange else None
 
         def enqueue(k):
-            lane = k & 1
+            lane = k % env.lanes
             fn(lane)
             if xch is not None:
                 xch.after_step(lane, d_contacts[lane], d_status[lane])
