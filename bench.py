@@ -168,7 +168,7 @@ def cpu_time(workload, scene, n_sample, budget_s, repeats=3):
         t0 = time.perf_counter(); once(); best = min(best, time.perf_counter() - t0)
     return {"value": n_done / best, "unit": "pairs/s", "cores": cores, "kind": "port",
             "sample": f"first {n_done} pairs of rank 0's batch" + (" (same 40/20/20/20 mix)" if workload == "c5" else "") +
-                      f", best of {repeats}, std::thread static partition over {cores} threads"}
+                      f", best of {repeats}, std::thread, 256-pair chunks from a shared counter, {cores} threads"}
 
 
 def run_reference(args):
@@ -202,7 +202,7 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": cfg, "note": REF_NOTE,
         "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port",
-                         "sample": f"{n_done} pairs of the workload per step, std::thread static partition over {cores} threads"},
+                         "sample": f"{n_done} pairs of the workload per step, std::thread, 256-pair chunks from a shared counter, {cores} threads"},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     if wl == "c5" and not args.no_extra:

@@ -1,7 +1,7 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY (see glam_mini.hpp header). C ABI over the CPU restatement so that tests/
 // (ctypes), __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs can call it. Batched
-// entry points take the same SoA layout the GPU C-ABI (include/bam3d_gpu.h) takes and split the batch
-// statically over `nthreads` std::threads (the reference itself is single-threaded; threads only replicate it).
+// entry points take the same SoA layout the GPU C-ABI (include/bam3d_gpu.h) takes and hand the batch out in chunks
+// to `nthreads` std::threads (the reference itself is single-threaded; threads only replicate it).
 #include <atomic>
 #include <cstring>
 #include <thread>
@@ -34,15 +34,22 @@ struct ShapeTable {
     Mat4 mat(uint32_t i) const { return Mat4::from_cols_array(xform + 16 * (size_t)i); }
 };
 
+// f(begin, end, thread) over [0, n) in chunks of 256 handed out by an atomic counter: a few pairs cost 10^4 times the median
+// (pinched EPA polytopes, time-of-impact sweeps that run to the cap), so a static split leaves most threads idle behind one.
 template <class F>
 void parallel_for(uint64_t n, int nthreads, F f) {
     if (nthreads <= 1 || n < 64) { f(0, n, 0); return; }
+    const uint64_t chunk = 256;
+    std::atomic<uint64_t> next{0};
     std::vector<std::thread> th;
-    uint64_t chunk = (n + nthreads - 1) / nthreads;
     for (int t = 0; t < nthreads; ++t) {
-        uint64_t b = t * chunk, e = std::min<uint64_t>(n, b + chunk);
-        if (b >= e) break;
-        th.emplace_back([=] { f(b, e, t); });
+        th.emplace_back([&, t] {
+            for (;;) {
+                const uint64_t b = next.fetch_add(chunk);
+                if (b >= n) break;
+                f(b, std::min<uint64_t>(n, b + chunk), t);
+            }
+        });
     }
     for (auto& x : th) x.join();
 }
