@@ -322,6 +322,11 @@ def roofline_for(wl, algo_bytes, kernel_ms, units_note):
          "note": "plain-FP32 SIMT, compute/latency bound: the ncu object holds FP32-pipe, branch and lane efficiency"}
     if ncu:
         r["ncu"] = ncu  # fp32_pipe_pct, branch_uniform_pct, lanes_active, dram_gbs, source file under profiles/
+        if ncu.get("duration_ms_under_ncu"):
+            # the live bracket covers every main kernel of the call (for C2: GJK phase + EPA + both overflow tiers, serialised on one
+            # context); the dominant kernel alone, from the committed capture of this build — not measured by this run:
+            r["dominant_kernel_alone"] = {"kernel": ncu.get("kernel"), "ms_under_ncu": ncu["duration_ms_under_ncu"],
+                                          "frac": algo_bytes / (ncu["duration_ms_under_ncu"] * 1e-3) / 1e9 / peak, "source": ncu.get("source")}
     return r
 
 
