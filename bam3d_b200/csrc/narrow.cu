@@ -1,7 +1,9 @@
 // Narrow-phase kernels for sm_100a: shape packing, pair binning, and batched GJK intersect / contact (GJK+EPA) /
 // distance / time of impact. Two execution shapes per query:
 //   * thread-per-pair  — analytic supports (sphere, cuboid, cylinder, capsule, quad, particle); simplex in
-//     registers; EPA polytope in per-thread local memory;
+//     registers; EPA polytope in a global-memory slab, one contiguous record per resident thread (persistent kernels in which
+//     every lane owns one pair and idle lanes refill: contact, time of impact, distance), with a warp-per-pair and a
+//     block-per-pair overflow tier behind it for polytopes beyond 256 / 1024 faces;
 //   * warp-per-pair    — any pair that involves a ConvexPolyhedron: the 32 lanes stride the vertex list and
 //     arg-max by shuffle (support.cuh); everything else runs redundantly on identical data in all lanes, with the
 //     EPA polytope in a per-warp shared-memory slice.

@@ -48,9 +48,10 @@ extern "C" {
 #define BAM3D_STATUS_MAX_ITER 2   /* None: max_iterations reached (TOI: the added iteration cap)        */
 #define BAM3D_STATUS_REF_PANIC 3  /* the reference would panic here (simplex3d.rs:134 unwrap, :138 assert!) */
 #define BAM3D_STATUS_NAN 4        /* None through a NaN comparison                                      */
-#define BAM3D_STATUS_CAPACITY 5   /* EPA polytope outgrew 1024 faces: a pinched polytope on near-degenerate input (about 3 in 10^5
-                                   * mixed pairs, every one involving a Cylinder cap); the reference has no face limit and keeps
-                                   * growing such a polytope — tests/test_host_cpu.py records what it would have returned */
+#define BAM3D_STATUS_CAPACITY 5   /* EPA polytope outgrew 2^18 faces (never seen). The reference has no face limit: on near-degenerate
+                                   * input (a Cylinder cap against a flat face) its polytope pinches and grows multiplicatively — 44 of 2^20
+                                   * mixed pairs pass 1024 faces, the largest reaches 121 962 — and it still returns a Contact when its
+                                   * iteration cap ends the loop; three EPA tiers (thread / warp / block per pair) return that Contact */
 #define BAM3D_STATUS_UNSUPPORTED 6 /* ray cast against a ConvexPolyhedron uploaded without faces (or > 4096 faces)   */
 
 /* CollisionStrategy (contact.rs:12-18) */
@@ -99,16 +100,16 @@ void bam3d_default_settings(bam3d_gjk_settings* out); /* GJK::new() (gjk/mod.rs:
  * (default 0) brackets the main kernel(s) of every narrow-phase / broad-phase call with CUDA events; "sap_strategy"
  * picks how sweep-and-prune finds its pairs — 0 auto, 1 tiled forward sweep, 2 BVH overlap query (same output);
  * "bvh_strategy" picks how the variable-length BVH queries run — 0 auto, 1 tree traversal (thread per query), 2 every
- * (query, value) test (for few large queries; results then come back in value-index order); "epa_tiers" (default 0)
- * = 1 runs EPA with the polytopes in shared memory in size tiers instead of one polytope per thread (same results, measured
- * slower: kept as an option); "epa_overlap" (default 1) runs the EPA overflow tier on a side stream next to the EPA kernel;
- * "epa_global_polytopes" (default 1) keeps the thread-per-pair EPA's polytopes in a global-memory slab, one contiguous
- * record per thread (582 MB of scratch), instead of per-thread local memory; "intersect_split"
- * (default 0) runs bam3d_gjk_intersect's thread path as two launches (first-support test, then GJK on the survivors);
- * "distance_refill" (default 8; 0..32) and "toi_refill" (default 8; 0..32) run bam3d_gjk_distance's / bam3d_gjk_time_of_impact's thread path as a persistent kernel in which every lane owns
- * one pair and idle lanes fetch new pairs together once that many lanes of a warp are idle (0 = one pair per thread: same
- * results, half the speed on mixed scenes); "intersect_refill" (default 0; 0..32) is the same scheme for bam3d_gjk_intersect
- * (same results, measured slower: kept as an option). Every switch changes scheduling only, never a result bit. */
+ * (query, value) test (for few large queries); "epa_overlap" (default 1) runs the EPA overflow tiers on a side stream next
+ * to the EPA kernel; "epa_huge" (default 1) enables the third EPA tier (0: pairs beyond 1024 faces keep
+ * BAM3D_STATUS_CAPACITY, as in the first release); "epa_global_polytopes" (default 1) keeps the thread-per-pair EPA's
+ * polytopes in a global-memory slab, one contiguous record per thread (582 MB of scratch), instead of per-thread local
+ * memory; "distance_refill" (default 8; 0..32) and "toi_refill" (default 8; 0..32) run bam3d_gjk_distance's /
+ * bam3d_gjk_time_of_impact's thread path as a persistent kernel in which every lane owns one pair and idle lanes fetch new
+ * pairs together once that many lanes of a warp are idle (0 = one pair per thread: same results, less than half the speed on
+ * mixed scenes). Every switch changes scheduling only, never a result bit. "epa_tiers", "epa_pipeline", "intersect_split" and
+ * "intersect_refill" select kernels that were measured slower than the defaults; they exist only in a library built with
+ * -DB3_EXPERIMENTS and are refused (BAM3D_ERR_ARG) otherwise. */
 int32_t bam3d_ctx_set_option(bam3d_ctx* ctx, const char* name, int32_t value);
 /* synchronise, then return and reset the summed device time (ms) and number of bracketed calls ("timing" = 1) */
 int32_t bam3d_ctx_read_timing(bam3d_ctx* ctx, double* out_total_ms, uint64_t* out_count);
