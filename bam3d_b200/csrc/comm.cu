@@ -121,6 +121,12 @@ struct bam3d_comm {
     uint64_t* h_counts = nullptr;                   // pinned, TICKETS x n_ranks
     cudaEvent_t counted[TICKETS] = {};
     uint64_t next_ticket = 0;
+    // payload as ONE all-gather of max-count records per rank into a staging buffer + exact-size local copies (default from 3
+    // ranks up; BAM3D_COMM_ALLGATHER=0/1 forces it): NCCL's all-gather moves 7 x 104 MB per rank over NVSwitch far better than
+    // eight grouped broadcasts through four thread blocks
+    bool allgather = false;
+    unsigned char* stage = nullptr;  // one buffer for all tickets: the payloads run one after the other on `stream`
+    size_t stage_bytes = 0;
     // BAM3D_COMM_TRACE=1 (development): host time blocked on the counts and device time of the payload launches, printed at destroy
     bool trace = false;
     cudaEvent_t t0[TICKETS] = {}, t1[TICKETS] = {}, tc0[TICKETS] = {};
@@ -179,6 +185,7 @@ void bam3d_comm_destroy(bam3d_comm* c) {
     if (c->ordered) cudaEventDestroy(c->ordered);
     if (c->done) cudaEventDestroy(c->done);
     if (c->d_counts) cudaFree(c->d_counts);
+    if (c->stage) cudaFree(c->stage);
     if (c->h_counts) cudaFreeHost(c->h_counts);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -207,6 +214,8 @@ int32_t bam3d_comm_create(int32_t device, const uint8_t* id, int32_t rank, int32
               cudaMalloc(&c->d_counts, sizeof(uint64_t) * TICKETS * n_ranks) == cudaSuccess &&
               cudaHostAlloc(&c->h_counts, sizeof(uint64_t) * TICKETS * n_ranks, cudaHostAllocDefault) == cudaSuccess;
     if (const char* e = std::getenv("BAM3D_COMM_TRACE")) c->trace = std::atoi(e) != 0;
+    c->allgather = n_ranks >= 3;
+    if (const char* e = std::getenv("BAM3D_COMM_ALLGATHER")) c->allgather = std::atoi(e) != 0;
     for (int t = 0; ok && c->trace && t < TICKETS; ++t)
         ok = cudaEventCreate(&c->t0[t]) == cudaSuccess && cudaEventCreate(&c->t1[t]) == cudaSuccess && cudaEventCreate(&c->tc0[t]) == cudaSuccess;
     for (int t = 0; ok && t < TICKETS; ++t)
@@ -274,8 +283,36 @@ int32_t bam3d_gather_contacts_finish(bam3d_ctx* ctx, bam3d_comm* c, uint64_t tic
     }
     if (total == 0) { cudaEventRecord(c->exchanged[slot], c->stream); return BAM3D_OK; }
     if (!d_gathered || (h[c->rank] && !d_compact)) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_gather_contacts_finish: null buffer", cudaSuccess);
-    // exact sizes: one broadcast per rank, grouped into a single NCCL launch; rank r's records land behind those of ranks < r
     if (c->trace) { cudaEventRecord(c->t0[slot], c->stream); c->t_open[slot] = true; }
+    if (c->allgather) {
+        uint64_t maxc = 0;
+        for (int r = 0; r < c->n_ranks; ++r) maxc = h[r] > maxc ? h[r] : maxc;
+        const size_t per_rank = (size_t)maxc * sizeof(bam3d_contact40);
+        const size_t need = per_rank * (size_t)c->n_ranks;
+        if (c->stage_bytes < need) {  // grows during the first steps only (12 % headroom)
+            if (c->stage) { cudaStreamSynchronize(c->stream); cudaFree(c->stage); c->stage = nullptr; c->stage_bytes = 0; }
+            const size_t want = need + need / 8;
+            if ((e = cudaMalloc(&c->stage, want)) != cudaSuccess) return b3_fail(ctx, BAM3D_ERR_OOM, "bam3d_gather_contacts_finish: staging buffer", e);
+            c->stage_bytes = want;
+        }
+        unsigned char* st = c->stage;
+        unsigned char* mine = st + per_rank * (size_t)c->rank;
+        if (h[c->rank] && (e = cudaMemcpyAsync(mine, d_compact, h[c->rank] * sizeof(bam3d_contact40), cudaMemcpyDeviceToDevice, c->stream)) != cudaSuccess)
+            return b3_fail(ctx, BAM3D_ERR_CUDA, "bam3d_gather_contacts_finish: stage copy", e);
+        ncclResult_t ra = N.AllGather(mine, st, per_rank, NCCL_UINT8, c->comm, c->stream);  // in place: every rank's slot is maxc records wide
+        if (ra != 0) return nccl_fail(ctx, "ncclAllGather(contacts)", ra);
+        uint64_t off2 = 0;
+        for (int r = 0; r < c->n_ranks; ++r) {  // exact sizes, rank order: the same contiguous list the broadcast form produces
+            if (h[r] && (e = cudaMemcpyAsync(reinterpret_cast<unsigned char*>(d_gathered) + off2 * sizeof(bam3d_contact40), st + per_rank * (size_t)r,
+                                             h[r] * sizeof(bam3d_contact40), cudaMemcpyDeviceToDevice, c->stream)) != cudaSuccess)
+                return b3_fail(ctx, BAM3D_ERR_CUDA, "bam3d_gather_contacts_finish: unstage copy", e);
+            off2 += h[r];
+        }
+        if (c->trace) cudaEventRecord(c->t1[slot], c->stream);
+        if ((e = cudaEventRecord(c->exchanged[slot], c->stream)) != cudaSuccess) return b3_fail(ctx, BAM3D_ERR_CUDA, "cudaEventRecord", e);
+        return BAM3D_OK;
+    }
+    // exact sizes: one broadcast per rank, grouped into a single NCCL launch; rank r's records land behind those of ranks < r
     ncclResult_t r0 = N.GroupStart();
     if (r0 != 0) return nccl_fail(ctx, "ncclGroupStart", r0);
     uint64_t off = 0;
