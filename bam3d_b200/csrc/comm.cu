@@ -122,8 +122,8 @@ struct bam3d_comm {
     cudaEvent_t counted[TICKETS] = {};
     uint64_t next_ticket = 0;
     // payload as ONE all-gather of max-count records per rank into a staging buffer + exact-size local copies (default from 3
-    // ranks up; BAM3D_COMM_ALLGATHER=0/1 forces it): NCCL's all-gather moves 7 x 104 MB per rank over NVSwitch far better than
-    // eight grouped broadcasts through four thread blocks
+    // ranks up; BAM3D_COMM_ALLGATHER=0/1 forces it): measured on 8 GPUs, 7 x 104 MB received per rank and step, 44.6 ms per C5 step
+    // against 46.1 ms with eight grouped broadcasts (same block count)
     bool allgather = false;
     unsigned char* stage = nullptr;  // one buffer for all tickets: the payloads run one after the other on `stream`
     size_t stage_bytes = 0;
@@ -223,7 +223,9 @@ int32_t bam3d_comm_create(int32_t device, const uint8_t* id, int32_t rank, int32
              cudaEventCreateWithFlags(&c->exchanged[t], cudaEventDisableTiming) == cudaSuccess;
     if (!ok) { bam3d_comm_destroy(c); return BAM3D_ERR_CUDA; }
     ncclUniqueId uid;
-    int payload_ctas = 4;  // BAM3D_NCCL_MAX_CTAS: thread blocks per payload collective (0: NCCL's default)
+    // thread blocks per payload collective (BAM3D_NCCL_MAX_CTAS; 0: NCCL's default). Measured on the C5 step: 2 ranks 41.9 ms with 4
+    // (44.5 with NCCL's default); 8 ranks 44.6 ms with 4, 43.1 ms with 8 (41.8 ms with the exchange switched off).
+    int payload_ctas = n_ranks <= 2 ? 4 : 8;
     if (const char* e = std::getenv("BAM3D_NCCL_MAX_CTAS")) payload_ctas = std::atoi(e);
     std::memcpy(uid.internal, id, sizeof uid);
     if (comm_init(N, &c->comm_counts, n_ranks, uid, rank, 1) != 0) { c->comm_counts = nullptr; bam3d_comm_destroy(c); return BAM3D_ERR_COMM; }
