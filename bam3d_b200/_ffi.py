@@ -94,6 +94,10 @@ SIGNATURES = {
     "bam3d_bvh_free": (None, [_vp, _vp]),
     "bam3d_bvh_count": (_u32, [_vp]),
     "bam3d_bvh_query_aabb": (_i32, [_vp, _vp, _vp, _u64, _vp, _vp, _u64, C.POINTER(_u64)]),
+    "bam3d_bvh_build_spheres": (_i32, [_vp, _vp, _u64, C.POINTER(_vp)]),
+    "bam3d_bvh_build_spheres_dev": (_i32, [_vp, _vp, _u64, C.POINTER(_vp)]),
+    "bam3d_bvh_query_sphere": (_i32, [_vp, _vp, _vp, _u64, _vp, _vp, _u64, C.POINTER(_u64)]),
+    "bam3d_bvh_query_sphere_dev": (_i32, [_vp, _vp, _vp, _u64, _vp, _vp, _u64, _vp]),
     "bam3d_bvh_query_ray": (_i32, [_vp, _vp, _vp, _u64, _vp, _vp, _vp, _u64, C.POINTER(_u64)]),
     "bam3d_bvh_query_frustum": (_i32, [_vp, _vp, _vp, _u64, _vp, _vp, _vp, _u64, C.POINTER(_u64)]),
     "bam3d_bvh_query_ray_closest": (_i32, [_vp, _vp, _vp, _u64, _vp, _vp]),

@@ -205,11 +205,18 @@ class Bvh:
         lib, h = self.ctx._lib, self.ctx.handle
         if kind == "aabb":
             rc = lib.bam3d_bvh_query_aabb_dev(h, self.handle, d_queries, nq, d_out_query, d_out_values, capacity, d_count)
+        elif kind == "sphere":
+            rc = lib.bam3d_bvh_query_sphere_dev(h, self.handle, d_queries, nq, d_out_query, d_out_values, capacity, d_count)
         elif kind == "ray":
             rc = lib.bam3d_bvh_query_ray_dev(h, self.handle, d_queries, nq, d_out_query, d_out_values, d_out_payload, capacity, d_count)
         else:
             rc = lib.bam3d_bvh_query_frustum_dev(h, self.handle, d_queries, nq, d_out_query, d_out_values, d_out_payload, capacity, d_count)
         self.ctx.check(rc)
+
+    def query_sphere(self, spheres):
+        """DiscreteVisitor per query sphere (centre.xyz, radius) on a tree over sphere bounds -> (offsets[nq+1], values)."""
+        off, vals, _ = self._var_query(self.ctx._lib.bam3d_bvh_query_sphere, spheres, 4, None)
+        return off, vals
 
     def query_ray_closest_dev(self, d_rays, nq, d_out_value, d_out_point_t):
         self.ctx.check(self.ctx._lib.bam3d_bvh_query_ray_closest_dev(self.ctx.handle, self.handle, d_rays, nq, d_out_value, d_out_point_t))
@@ -231,6 +238,20 @@ class Bvh:
             ctx.check(res)
         pairs, cnt = res
         return pairs[:cnt]
+
+
+class SphereBvh(Bvh):
+    """The same tree over values whose bound is volume::Sphere (bam3d_bvh_build_spheres): spheres[n, 4] = (centre.xyz, radius).
+    query_sphere / query_ray / query_frustum apply the sphere's own predicates (volume/sphere.rs); query_aabb, query_ray_closest,
+    refit and find_collider_pairs are not available on it (the library reports BAM3D_ERR_ARG)."""
+
+    def __init__(self, ctx, spheres):
+        self.ctx = ctx
+        self.spheres = np.ascontiguousarray(spheres, dtype=np.float32).reshape(-1, 4)
+        h = C.c_void_p()
+        ctx.check(ctx._lib.bam3d_bvh_build_spheres(ctx.handle, _ptr(self.spheres), len(self.spheres), C.byref(h)))
+        self.handle = h
+        self.n = len(self.spheres)
 
 
 class DynamicBoundingVolumeTree:

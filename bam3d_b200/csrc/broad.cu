@@ -499,6 +499,26 @@ int launch_sap_inflate(cudaStream_t st, const SapScratch& S, float* d_sorted6, u
     return 1;
 }
 
+// Boxes that cover the spheres with the same margin: the node bounds of a BVH over volume::Sphere values. A query that the
+// sphere's own f32 predicate accepts (touching counts, rounding either way) must reach the leaf, so the cover is a superset.
+__global__ void __launch_bounds__(BT) sphere_cover_boxes_kernel(const float4* __restrict__ spheres, uint32_t n, float* __restrict__ boxes6) {
+    uint32_t k = blockIdx.x * BT + threadIdx.x;
+    if (k >= n) return;
+    const float4 s = spheres[k];
+    float lo[3] = {s.x - s.w, s.y - s.w, s.z - s.w}, hi[3] = {s.x + s.w, s.y + s.w, s.z + s.w};
+    float* o = boxes6 + 6 * (size_t)k;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float m = grow_margin(lo[a], hi[a]);
+        o[a] = lo[a] - m; o[3 + a] = hi[a] + m;
+    }
+}
+int launch_sphere_cover_boxes(cudaStream_t st, const float4* d_spheres, uint32_t n, float* d_boxes6) {
+    if (n == 0) return 0;
+    sphere_cover_boxes_kernel<<<(n + BT - 1) / BT, BT, 0, st>>>(d_spheres, n, d_boxes6);
+    return 1;
+}
+
 __global__ void __launch_bounds__(BT) gather_spheres_kernel(const float4* __restrict__ spheres, const uint32_t* __restrict__ perm, uint32_t n,
                                                             float4* __restrict__ sorted) {
     uint32_t k = blockIdx.x * BT + threadIdx.x;
@@ -802,6 +822,7 @@ struct Query {
     float4 qlo, qhi;     // BQ_AABB
     V3 o, d;             // BQ_RAY
     float4 pl[6];        // BQ_FRUSTUM
+    float4 sph;          // BQ_SPHERE: centre, radius
 };
 
 template <int KIND>
@@ -811,9 +832,50 @@ B3_DEV bool accept(const Query& q, float4 mn, float4 mx, V3& point, int& rel) {
         return mx.x > q.qlo.x && mn.x < q.qhi.x && mx.y > q.qlo.y && mn.y < q.qhi.y && mx.z > q.qlo.z && mn.z < q.qhi.z;
     } else if (KIND == BQ_RAY) {
         return ray_aabb(q.o, q.d, mn, mx, point);
+    } else if (KIND == BQ_SPHERE) {
+        // node test only (the leaf is decided by sphere_leaf): the node box against the query sphere's grown extent, touching included
+        const float4 c = q.sph;
+        const float mx_ = grow_margin(c.x - c.w, c.x + c.w), my_ = grow_margin(c.y - c.w, c.y + c.w), mz_ = grow_margin(c.z - c.w, c.z + c.w);
+        return mx.x >= c.x - c.w - mx_ && mn.x <= c.x + c.w + mx_ && mx.y >= c.y - c.w - my_ && mn.y <= c.y + c.w + my_ &&
+               mx.z >= c.z - c.w - mz_ && mn.z <= c.z + c.w + mz_;
     } else {
         rel = frustum_relation(mn, mx, q.pl);
         return rel != 2;
+    }
+}
+
+// The leaf predicate of a tree over volume::Sphere bounds (volume/sphere.rs), `s` = the value's bound:
+//   BQ_SPHERE  DiscreteVisitor: Discrete<Sphere> (:82-91), touching spheres intersect;
+//   BQ_RAY     ContinuousVisitor: Continuous<Ray> (:50-67), the first point on the sphere (None when the centre is behind the origin);
+//   BQ_FRUSTUM FrustumVisitor: Frustum::contains over PlaneBound for Sphere (:93-104), fold max over the six planes.
+template <int KIND>
+B3_DEV bool sphere_leaf(const Query& q, float4 s, V3& point, int& rel) {
+    const V3 c = v3(s.x, s.y, s.z);
+    if (KIND == BQ_SPHERE) {
+        const V3 distance = c - v3(q.sph.x, q.sph.y, q.sph.z);
+        const float radiuses = s.w + q.sph.w;
+        return dot(distance, distance) <= radiuses * radiuses;
+    } else if (KIND == BQ_RAY) {
+        const V3 l = c - q.o;
+        const float tca = dot(l, q.d);
+        if (tca < 0.f) return false;
+        const float d2 = dot(l, l) - tca * tca;
+        if (d2 > s.w * s.w) return false;
+        const float thc = sqrtf(s.w * s.w - d2);
+        point = q.o + q.d * (tca - thc);
+        return true;
+    } else if (KIND == BQ_FRUSTUM) {
+        int cur = 0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const float dist = dot(c, v3(q.pl[k].x, q.pl[k].y, q.pl[k].z)) - q.pl[k].w;
+            const int r = dist > s.w ? 0 : (dist < -s.w ? 2 : 1);
+            cur = max(cur, r);
+        }
+        rel = cur;
+        return cur != 2;
+    } else {
+        return false;  // an Aabb3 query against sphere bounds is not a reference operation
     }
 }
 
@@ -825,6 +887,8 @@ B3_DEV void load_query(Query& q, const float* __restrict__ queries, uint32_t qi)
     } else if (KIND == BQ_RAY) {
         const float* b = queries + 6 * (size_t)qi;
         q.o = v3(b[0], b[1], b[2]); q.d = v3(b[3], b[4], b[5]);
+    } else if (KIND == BQ_SPHERE) {
+        q.sph = reinterpret_cast<const float4*>(queries)[qi];
     } else {
         const float4* b = reinterpret_cast<const float4*>(queries) + 6 * (size_t)qi;
 #pragma unroll
@@ -846,6 +910,7 @@ __global__ void __launch_bounds__(BT) bvh_query_kernel(BvhDev T, const float* __
     bvh_traverse(T, [&](bool leaf, uint32_t value, float4 mn, float4 mx) {
         V3 point; int rel = 0;
         if (!accept<KIND>(q, mn, mx, point, rel)) return false;
+        if (leaf && T.spheres && !sphere_leaf<KIND>(q, __ldg(T.spheres + value), point, rel)) return false;
         if (leaf) {
             if (FILL) {
                 values[w] = value;
@@ -875,6 +940,7 @@ __global__ void __launch_bounds__(BT) bvh_query_append_kernel(BvhDev T, const fl
     bvh_traverse(T, [&](bool leaf, uint32_t value, float4 mn, float4 mx) {
         V3 point; int rel = 0;
         if (!accept<KIND>(q, mn, mx, point, rel)) return false;
+        if (leaf && T.spheres && !sphere_leaf<KIND>(q, __ldg(T.spheres + value), point, rel)) return false;
         if (leaf) {
             const uint32_t act = __activemask();
             const uint32_t leader = __ffs(act) - 1;
@@ -899,6 +965,7 @@ int launch_bvh_query_append(cudaStream_t st, const BvhDev& T, int kind, const fl
     if (nq == 0 || T.n == 0) return 0;
     const int g = (nq + BT - 1) / BT;
     if (kind == BQ_AABB) bvh_query_append_kernel<BQ_AABB><<<g, BT, 0, st>>>(T, d_queries, nq, d_out_query, d_out_value, d_out_payload, capacity, d_count);
+    else if (kind == BQ_SPHERE) bvh_query_append_kernel<BQ_SPHERE><<<g, BT, 0, st>>>(T, d_queries, nq, d_out_query, d_out_value, d_out_payload, capacity, d_count);
     else if (kind == BQ_RAY) bvh_query_append_kernel<BQ_RAY><<<g, BT, 0, st>>>(T, d_queries, nq, d_out_query, d_out_value, d_out_payload, capacity, d_count);
     else bvh_query_append_kernel<BQ_FRUSTUM><<<g, BT, 0, st>>>(T, d_queries, nq, d_out_query, d_out_value, d_out_payload, capacity, d_count);
     return 1;
@@ -996,6 +1063,7 @@ int launch_bvh_query(cudaStream_t st, const BvhDev& T, int kind, const float* d_
     if (fill) bvh_query_kernel<KIND, true><<<g, BT, 0, st>>>(T, d_queries, nq, d_counts, d_offsets, d_values, d_payload); \
     else bvh_query_kernel<KIND, false><<<g, BT, 0, st>>>(T, d_queries, nq, d_counts, d_offsets, d_values, d_payload);
     if (kind == BQ_AABB) { B3_Q(BQ_AABB) }
+    else if (kind == BQ_SPHERE) { B3_Q(BQ_SPHERE) }
     else if (kind == BQ_RAY) { B3_Q(BQ_RAY) }
     else { B3_Q(BQ_FRUSTUM) }
 #undef B3_Q

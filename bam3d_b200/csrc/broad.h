@@ -46,6 +46,8 @@ int launch_world_spheres(cudaStream_t st, const ShapeSetDev& S, float4* d_out);
 // SweepAndPrune3<volume::Sphere>: extents of the spheres as boxes (sort keys, Variance3), growth of the sorted boxes for the
 // candidate search, spheres in sorted order, and the exact order-preserving pair filter
 int launch_spheres_to_extents(cudaStream_t st, const float4* d_spheres, uint32_t n, float* d_boxes6);
+// the same grown by grow_margin: the node boxes of a BVH over sphere bounds
+int launch_sphere_cover_boxes(cudaStream_t st, const float4* d_spheres, uint32_t n, float* d_boxes6);
 int launch_sap_inflate(cudaStream_t st, const SapScratch& S, float* d_sorted6, uint32_t n);
 int launch_gather_spheres(cudaStream_t st, const float4* d_spheres, const uint32_t* d_perm, uint32_t n, float4* d_sorted);
 size_t sphere_filter_tmp_bytes(uint64_t n_pairs);
@@ -60,6 +62,8 @@ struct BvhDev {
     const float4* nodes;     // 2 x (2n - 1): (min.xyz, A), (max.xyz, rope) as int bits — one 32-byte sector per node; A = left child
                              // (internal) or value index (leaf); rope = where a left-first depth-first traversal goes after this subtree
     const uint32_t* leaf_value;  // n : value index of leaf k (Morton order)
+    const float4* spheres = nullptr;  // n x (centre.xyz, radius) when the values' bounds are volume::Sphere: the node boxes are then a
+                                      // conservative cover (grown sphere extents) and every leaf is decided by the sphere's own predicate
 };
 struct BvhBuildScratch {
     uint32_t* morton_in; uint32_t* morton_out; uint32_t* idx_in; uint32_t* idx_out;
@@ -77,7 +81,7 @@ int launch_bvh_build(cudaStream_t st, const float* d_aabbs, uint32_t n, const Bv
 int launch_bvh_refit(cudaStream_t st, const float* d_aabbs, uint32_t n, const int2* children, const uint32_t* leaf_value, uint32_t* parent,
                      const uint32_t* rope, uint32_t* flags, float4* nodes);
 
-enum BvhQueryKind { BQ_AABB = 0, BQ_RAY = 1, BQ_FRUSTUM = 2 };
+enum BvhQueryKind { BQ_AABB = 0, BQ_RAY = 1, BQ_FRUSTUM = 2, BQ_SPHERE = 3 };  // BQ_SPHERE: nq x 4 f32 (centre, radius), sphere trees only
 // pass 1 (d_offsets == nullptr): per-query hit counts into d_counts. pass 2: fill d_values / d_payload at d_offsets.
 //   BQ_AABB: queries nq x 6 f32, no payload;  BQ_RAY: nq x 6 f32 (origin, direction), payload 3 f32 (hit point) per hit;
 //   BQ_FRUSTUM: nq x 24 f32 (6 planes n.xyz,d in the order left,right,bottom,top,near,far), payload 1 byte (Relation).

@@ -874,10 +874,11 @@ struct bam3d_bvh {
     int2* children = nullptr;      // n - 1 (build / refit only)
     uint32_t* leaf_value = nullptr;
     uint32_t* rope = nullptr;      // 2n - 1 (written into the node records; kept for the refit)
+    float4* d_spheres = nullptr;   // n x (centre, radius) for a tree over volume::Sphere bounds (d_aabbs then holds the cover boxes)
 };
 
 static BvhDev bvh_view(const bam3d_bvh* t) {
-    BvhDev v; v.n = t->n; v.nodes = t->nodes; v.leaf_value = t->leaf_value;
+    BvhDev v; v.n = t->n; v.nodes = t->nodes; v.leaf_value = t->leaf_value; v.spheres = t->d_spheres;
     return v;
 }
 
@@ -1245,10 +1246,12 @@ void bam3d_bvh_free(bam3d_ctx* ctx, bam3d_bvh* t) {
     if (t->children) cudaFree(t->children);
     if (t->leaf_value) cudaFree(t->leaf_value);
     if (t->rope) cudaFree(t->rope);
+    if (t->d_spheres) cudaFree(t->d_spheres);
     delete t;
 }
 
-static int32_t bvh_build_impl(bam3d_ctx* ctx, const float* aabbs, bool on_device, uint64_t n64, bam3d_bvh** out) {
+// `spheres`: the values' bounds are volume::Sphere (n x 4 floats in `aabbs`' place); the tree is then built over their cover boxes
+static int32_t bvh_build_impl(bam3d_ctx* ctx, const float* aabbs, bool on_device, uint64_t n64, bam3d_bvh** out, bool spheres = false) {
     *out = nullptr;
     int32_t rc;
     if ((rc = check_n(ctx, n64))) return rc;
@@ -1265,7 +1268,15 @@ static int32_t bvh_build_impl(bam3d_ctx* ctx, const float* aabbs, bool on_device
         bam3d_bvh_free(ctx, t);
         return b3_fail(ctx, BAM3D_ERR_OOM, "cudaMalloc(bvh)", e);
     }
-    if (n) cudaMemcpyAsync(t->d_aabbs, aabbs, (size_t)n * 24, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream);
+    if (spheres) {
+        if ((e = cudaMalloc(&t->d_spheres, nn * 16)) != cudaSuccess) { bam3d_bvh_free(ctx, t); return b3_fail(ctx, BAM3D_ERR_OOM, "cudaMalloc(bvh spheres)", e); }
+        if (n) {
+            cudaMemcpyAsync(t->d_spheres, aabbs, (size_t)n * 16, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream);
+            ctx->launches += launch_sphere_cover_boxes(ctx->stream, t->d_spheres, n, t->d_aabbs);
+        }
+    } else if (n) {
+        cudaMemcpyAsync(t->d_aabbs, aabbs, (size_t)n * 24, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream);
+    }
     BvhBuildScratch W;
     const size_t tmp_bytes = bvh_cub_tmp_bytes(n ? n : 1);
     if ((rc = ctx->bp0.reserve(ctx, nn * 4 * 4)) || (rc = ctx->bp1.reserve(ctx, (2 * nn) * 4 + nn * 4)) || (rc = ctx->cub_tmp.reserve(ctx, tmp_bytes)) ||
@@ -1284,6 +1295,7 @@ static int32_t bvh_build_impl(bam3d_ctx* ctx, const float* aabbs, bool on_device
 
 static int32_t bvh_refit_impl(bam3d_ctx* ctx, bam3d_bvh* t, const float* aabbs, bool on_device) {
     if (!ctx || !t || (t->n && !aabbs)) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_bvh_refit: null argument", cudaSuccess);
+    if (t->d_spheres) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_bvh_refit: a tree over sphere bounds is rebuilt, not refitted", cudaSuccess);
     CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
     const uint32_t n = t->n;
     if (n == 0) return BAM3D_OK;
@@ -1310,22 +1322,37 @@ int32_t bam3d_bvh_build_dev(bam3d_ctx* ctx, const float* d_aabbs, uint64_t n, ba
     if (!ctx || !out || (n && !d_aabbs)) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_bvh_build: null argument", cudaSuccess);
     return bvh_build_impl(ctx, d_aabbs, true, n, out);
 }
+int32_t bam3d_bvh_build_spheres(bam3d_ctx* ctx, const float* spheres, uint64_t n, bam3d_bvh** out) {
+    if (!ctx || !out || (n && !spheres)) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_bvh_build_spheres: null argument", cudaSuccess);
+    return bvh_build_impl(ctx, spheres, false, n, out, true);
+}
+int32_t bam3d_bvh_build_spheres_dev(bam3d_ctx* ctx, const float* d_spheres, uint64_t n, bam3d_bvh** out) {
+    if (!ctx || !out || (n && !d_spheres)) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_bvh_build_spheres: null argument", cudaSuccess);
+    return bvh_build_impl(ctx, d_spheres, true, n, out, true);
+}
 uint32_t bam3d_bvh_count(const bam3d_bvh* t) { return t ? t->n : 0; }
+
+// which queries a tree answers: Aabb3 queries need box bounds, Sphere queries sphere bounds; rays and frusta work on both
+static int32_t bvh_kind_check(bam3d_ctx* ctx, const bam3d_bvh* t, int kind) {
+    if (kind == BQ_AABB && t->d_spheres) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_bvh_query_aabb: the tree's bounds are spheres (use bam3d_bvh_query_sphere)", cudaSuccess);
+    if (kind == BQ_SPHERE && !t->d_spheres) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_bvh_query_sphere: the tree's bounds are boxes (use bam3d_bvh_query_aabb)", cudaSuccess);
+    return BAM3D_OK;
+}
 
 // Shared implementation of the variable-length queries: count pass, exclusive scan, fill pass.
 static int32_t bvh_query_impl(bam3d_ctx* ctx, const bam3d_bvh* t, int kind, const float* queries, uint64_t nq64, uint64_t* out_offsets,
                               uint32_t* out_values, void* out_payload, size_t payload_stride, uint64_t capacity, uint64_t* out_total) {
     int32_t rc;
-    if ((rc = check_n(ctx, nq64))) return rc;
+    if ((rc = check_n(ctx, nq64)) || (rc = bvh_kind_check(ctx, t, kind))) return rc;
     CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
     const uint32_t nq = (uint32_t)nq64;
     *out_total = 0;
     if (nq == 0) { if (out_offsets) out_offsets[0] = 0; return BAM3D_OK; }
-    const size_t qfloats = kind == BQ_FRUSTUM ? 24 : 6;
+    const size_t qfloats = kind == BQ_FRUSTUM ? 24 : (kind == BQ_SPHERE ? 4 : 6);
     // few large queries -> evaluate the leaf predicate for every (query, value); many small ones -> tree traversal
     const uint32_t ntiles = (t->n + 255) / 256;
     bool brute = ctx->opt_bvh_strategy == 2 || (ctx->opt_bvh_strategy == 0 && nq < 2048 && (uint64_t)nq * t->n <= (1ull << 35));
-    if (nq > 65535 || t->n == 0) brute = false;
+    if (nq > 65535 || t->n == 0 || t->d_spheres) brute = false;  // (the flat scan tests boxes only)
     const size_t ncount = brute ? (size_t)nq * ntiles : (size_t)nq;
     const size_t scan_bytes = scan_tmp_bytes((uint32_t)ncount);
     if (ncount > 0xFFFFFF00ull) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_bvh_query: too many (query, tile) cells", cudaSuccess);
@@ -1373,6 +1400,11 @@ int32_t bam3d_bvh_query_aabb(bam3d_ctx* ctx, const bam3d_bvh* t, const float* qu
     if (!ctx || !t || !out_total || (nq && !queries) || (capacity && !out_values)) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_bvh_query_aabb: null argument", cudaSuccess);
     return bvh_query_impl(ctx, t, BQ_AABB, queries, nq, out_offsets, out_values, nullptr, 0, capacity, out_total);
 }
+int32_t bam3d_bvh_query_sphere(bam3d_ctx* ctx, const bam3d_bvh* t, const float* spheres, uint64_t nq, uint64_t* out_offsets, uint32_t* out_values,
+                               uint64_t capacity, uint64_t* out_total) {
+    if (!ctx || !t || !out_total || (nq && !spheres) || (capacity && !out_values)) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_bvh_query_sphere: null argument", cudaSuccess);
+    return bvh_query_impl(ctx, t, BQ_SPHERE, spheres, nq, out_offsets, out_values, nullptr, 0, capacity, out_total);
+}
 int32_t bam3d_bvh_query_ray(bam3d_ctx* ctx, const bam3d_bvh* t, const float* rays, uint64_t nq, uint64_t* out_offsets, uint32_t* out_values,
                             float* out_points, uint64_t capacity, uint64_t* out_total) {
     if (!ctx || !t || !out_total || (nq && !rays) || (capacity && (!out_values || !out_points))) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_bvh_query_ray: null argument", cudaSuccess);
@@ -1386,6 +1418,7 @@ int32_t bam3d_bvh_query_frustum(bam3d_ctx* ctx, const bam3d_bvh* t, const float*
 
 int32_t bam3d_bvh_query_ray_closest(bam3d_ctx* ctx, const bam3d_bvh* t, const float* rays, uint64_t nq64, uint32_t* out_value, float* out_point_t) {
     if (!ctx || !t || (nq64 && (!rays || !out_value || !out_point_t))) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_bvh_query_ray_closest: null argument", cudaSuccess);
+    if (t->d_spheres) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_bvh_query_ray_closest: not available over sphere bounds (use bam3d_bvh_query_ray)", cudaSuccess);
     int32_t rc;
     if ((rc = check_n(ctx, nq64))) return rc;
     if (nq64 == 0) return BAM3D_OK;
@@ -1407,12 +1440,12 @@ static int32_t bvh_query_dev_impl(bam3d_ctx* ctx, const bam3d_bvh* t, int kind, 
                                   uint32_t* d_out_values, void* d_out_payload, uint64_t capacity, uint64_t* d_count, const char* what) {
     if (!ctx || !t || !d_count || (nq64 && !d_queries) || (capacity && (!d_out_query || !d_out_values))) return b3_fail(ctx, BAM3D_ERR_ARG, what, cudaSuccess);
     int32_t rc;
-    if ((rc = check_n(ctx, nq64))) return rc;
+    if ((rc = check_n(ctx, nq64)) || (rc = bvh_kind_check(ctx, t, kind))) return rc;
     CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
     const uint32_t nq = (uint32_t)nq64;
     // few large queries -> every (query, value) test; many small ones -> tree traversal (as the host-buffer forms decide)
     bool brute = ctx->opt_bvh_strategy == 2 || (ctx->opt_bvh_strategy == 0 && nq < 2048 && (uint64_t)nq * t->n <= (1ull << 35));
-    if (t->n == 0) brute = false;
+    if (t->n == 0 || t->d_spheres) brute = false;
     { KernelTimer kt(ctx);
       if (brute) ctx->launches += launch_bvh_brute_append(ctx->stream, t->d_aabbs, t->n, kind, d_queries, nq, d_out_query, d_out_values, d_out_payload, capacity,
                                                           (unsigned long long*)d_count);
@@ -1423,6 +1456,10 @@ static int32_t bvh_query_dev_impl(bam3d_ctx* ctx, const bam3d_bvh* t, int kind, 
 int32_t bam3d_bvh_query_aabb_dev(bam3d_ctx* ctx, const bam3d_bvh* t, const float* d_queries, uint64_t nq, uint32_t* d_out_query, uint32_t* d_out_values,
                                  uint64_t capacity, uint64_t* d_count) {
     return bvh_query_dev_impl(ctx, t, BQ_AABB, d_queries, nq, d_out_query, d_out_values, nullptr, capacity, d_count, "bam3d_bvh_query_aabb_dev: null argument");
+}
+int32_t bam3d_bvh_query_sphere_dev(bam3d_ctx* ctx, const bam3d_bvh* t, const float* d_spheres, uint64_t nq, uint32_t* d_out_query, uint32_t* d_out_values,
+                                   uint64_t capacity, uint64_t* d_count) {
+    return bvh_query_dev_impl(ctx, t, BQ_SPHERE, d_spheres, nq, d_out_query, d_out_values, nullptr, capacity, d_count, "bam3d_bvh_query_sphere_dev: null argument");
 }
 int32_t bam3d_bvh_query_ray_dev(bam3d_ctx* ctx, const bam3d_bvh* t, const float* d_rays, uint64_t nq, uint32_t* d_out_query, uint32_t* d_out_values,
                                 float* d_out_points, uint64_t capacity, uint64_t* d_count) {
@@ -1436,6 +1473,7 @@ int32_t bam3d_bvh_query_frustum_dev(bam3d_ctx* ctx, const bam3d_bvh* t, const fl
 }
 int32_t bam3d_bvh_query_ray_closest_dev(bam3d_ctx* ctx, const bam3d_bvh* t, const float* d_rays, uint64_t nq64, uint32_t* d_out_value, float* d_out_point_t) {
     if (!ctx || !t || (nq64 && (!d_rays || !d_out_value || !d_out_point_t))) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_bvh_query_ray_closest_dev: null argument", cudaSuccess);
+    if (t->d_spheres) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_bvh_query_ray_closest: not available over sphere bounds (use bam3d_bvh_query_ray)", cudaSuccess);
     int32_t rc;
     if ((rc = check_n(ctx, nq64))) return rc;
     if (nq64 == 0) return BAM3D_OK;
@@ -1447,6 +1485,7 @@ int32_t bam3d_bvh_query_ray_closest_dev(bam3d_ctx* ctx, const bam3d_bvh* t, cons
 
 int32_t bam3d_bvh_find_collider_pairs(bam3d_ctx* ctx, const bam3d_bvh* t, const uint8_t* dirty, uint32_t* out_pairs, uint64_t capacity, uint64_t* out_count) {
     if (!ctx || !t || !out_count || (t->n && !dirty) || (capacity && !out_pairs)) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_bvh_find_collider_pairs: null argument", cudaSuccess);
+    if (t->d_spheres) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_bvh_find_collider_pairs: not available over sphere bounds (bam3d_sap_find_pairs_spheres is the sphere broad phase)", cudaSuccess);
     CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
     *out_count = 0;
     const uint32_t n = t->n;

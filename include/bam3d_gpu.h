@@ -349,6 +349,21 @@ int32_t bam3d_bvh_query_frustum_dev(bam3d_ctx* ctx, const bam3d_bvh* bvh, const 
                                     uint32_t* d_out_values, uint8_t* d_out_relation, uint64_t capacity, uint64_t* d_count);
 int32_t bam3d_bvh_query_ray_closest_dev(bam3d_ctx* ctx, const bam3d_bvh* bvh, const float* d_rays, uint64_t nq, uint32_t* d_out_value,
                                         float* d_out_point_t);
+/* The same tree over values whose bound is volume::Sphere (volume/sphere.rs:17-196; DynamicBoundingVolumeTree is generic over the
+ * bound): spheres = n x (centre.xyz, radius). The node boxes are a conservative cover of the spheres; every leaf is decided by the
+ * sphere's own predicate, so result sets are those of the leaf predicate over all values (as for boxes, independent of tree shape):
+ *   bam3d_bvh_query_sphere[_dev]   DiscreteVisitor with a Sphere: Discrete<Sphere> for Sphere (:82-91; touching spheres intersect)
+ *   bam3d_bvh_query_ray[_dev]      ContinuousVisitor: Continuous<Ray> for Sphere (:50-67) — the first point on the sphere, no hit when
+ *                                  the centre is behind the origin; directions are unit vectors, as Ray::new's callers provide
+ *   bam3d_bvh_query_frustum[_dev]  FrustumVisitor: Frustum::contains over PlaneBound for Sphere (:93-104)
+ * bam3d_bvh_query_aabb, _ray_closest, _refit and _find_collider_pairs return BAM3D_ERR_ARG on such a tree (rebuild instead of
+ * refit; bam3d_sap_find_pairs_spheres is the sphere broad phase), bam3d_bvh_query_sphere on a tree over boxes likewise. */
+int32_t bam3d_bvh_build_spheres(bam3d_ctx* ctx, const float* spheres, uint64_t n, bam3d_bvh** out);
+int32_t bam3d_bvh_build_spheres_dev(bam3d_ctx* ctx, const float* d_spheres, uint64_t n, bam3d_bvh** out);
+int32_t bam3d_bvh_query_sphere(bam3d_ctx* ctx, const bam3d_bvh* bvh, const float* spheres, uint64_t nq, uint64_t* out_offsets, uint32_t* out_values,
+                               uint64_t capacity, uint64_t* out_total);
+int32_t bam3d_bvh_query_sphere_dev(bam3d_ctx* ctx, const bam3d_bvh* bvh, const float* d_spheres, uint64_t nq, uint32_t* d_out_query,
+                                   uint32_t* d_out_values, uint64_t capacity, uint64_t* d_count);
 /* DbvtBroadPhase::find_collider_pairs (algorithm/broad_phase/dbvt.rs:26-63): every value with dirty[k] != 0 is queried
  * against the tree; out_pairs = sorted unique (low, high) value-index pairs. */
 int32_t bam3d_bvh_find_collider_pairs(bam3d_ctx* ctx, const bam3d_bvh* bvh, const uint8_t* dirty, uint32_t* out_pairs,

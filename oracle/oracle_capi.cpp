@@ -509,6 +509,42 @@ uint64_t orc_dbvt_find_collider_pairs(orc_dbvt* t, const uint8_t* dirty, uint32_
     for (uint64_t i = 0; i < pr.size() && i < cap; ++i) { out_pairs[2 * i] = pr[i].first; out_pairs[2 * i + 1] = pr[i].second; }
     return pr.size();
 }
+// A DynamicBoundingVolumeTree whose values are bounded by volume::Sphere (the tree is generic over the bound): the leaf predicate of
+// the matching visitor applied to every value — the result set of query_for_indices, which does not depend on the tree's shape
+// (branch bounds contain their leaves, the visitors are monotone). kind 0: DiscreteVisitor with a Sphere (query = centre, radius;
+// sphere.rs:82-91), 1: ContinuousVisitor (query = ray origin, direction; :50-67; out_points), 2: FrustumVisitor (query = 6 planes
+// n.xyz, d in the order left, right, bottom, top, near, far; :93-104 under frustum.rs:78-95; out_relation). Values ascending.
+uint64_t orc_sphere_values_query(const float* spheres, uint64_t n, int32_t kind, const float* query, uint32_t* out_values, float* out_points,
+                                 uint8_t* out_relation, uint64_t cap) {
+    uint64_t hits = 0;
+    Frustum fr;
+    if (kind == 2) {
+        Plane* ps[6] = {&fr.left, &fr.right, &fr.bottom, &fr.top, &fr.near_, &fr.far_};
+        for (int i = 0; i < 6; ++i) *ps[i] = Plane(Vec3(query[4 * i], query[4 * i + 1], query[4 * i + 2]), query[4 * i + 3]);
+    }
+    for (uint64_t v = 0; v < n; ++v) {
+        const BSphere s(Vec3(spheres[4 * v], spheres[4 * v + 1], spheres[4 * v + 2]), spheres[4 * v + 3]);
+        bool hit = false;
+        Vec3 p = Vec3::zero();
+        Relation rel = In;
+        if (kind == 0) {
+            hit = s.intersects(BSphere(Vec3(query[0], query[1], query[2]), query[3]));
+        } else if (kind == 1) {
+            hit = s.intersection(Ray(Vec3(query[0], query[1], query[2]), Vec3(query[3], query[4], query[5])), p);
+        } else {
+            rel = fr.contains(s);
+            hit = rel != Out;
+        }
+        if (!hit) continue;
+        if (hits < cap) {
+            out_values[hits] = (uint32_t)v;
+            if (kind == 1 && out_points) { out_points[3 * hits] = p.x; out_points[3 * hits + 1] = p.y; out_points[3 * hits + 2] = p.z; }
+            if (kind == 2 && out_relation) out_relation[hits] = (uint8_t)rel;
+        }
+        ++hits;
+    }
+    return hits;
+}
 // Ray / frustum vs one Aabb3 (aabb3.rs:165-257, frustum.rs:78-95) for direct leaf-level parity checks.
 int32_t orc_ray_aabb(const float* ray6, const float* box, float* out_point3) {
     Vec3 p; bool ok = ray_aabb_intersection(Ray(Vec3(ray6[0], ray6[1], ray6[2]), Vec3(ray6[3], ray6[4], ray6[5])), box6(box), p);

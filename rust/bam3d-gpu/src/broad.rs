@@ -116,6 +116,26 @@ impl<'a> DynamicBoundingVolumeTree<'a> {
         ctx.check(unsafe { ffi::bam3d_bvh_build(ctx.0, flat.as_ptr(), bounds.len() as u64, &mut h) })?;
         Ok(DynamicBoundingVolumeTree { ctx, h, n: bounds.len() })
     }
+    /// The same tree over values bounded by `volume::Sphere` (`DynamicBoundingVolumeTree` is generic over the bound): `query_ray`
+    /// and `query_frustum` then apply `Continuous<Ray>` / `PlaneBound for Sphere`, `query_discrete_sphere` `Discrete<Sphere>`;
+    /// `query_discrete`, `query_ray_closest` and `refit` report an error on such a tree.
+    pub fn new_with_spheres(ctx: &'a Context, bounds: &[Sphere]) -> Result<Self> {
+        let flat: Vec<f32> = bounds.iter().flat_map(|s| vec![s.center.x(), s.center.y(), s.center.z(), s.radius]).collect();
+        let mut h = std::ptr::null_mut();
+        ctx.check(unsafe { ffi::bam3d_bvh_build_spheres(ctx.0, flat.as_ptr(), bounds.len() as u64, &mut h) })?;
+        Ok(DynamicBoundingVolumeTree { ctx, h, n: bounds.len() })
+    }
+    /// `query(&mut DiscreteVisitor::new(&sphere))` on a tree over sphere bounds (sphere.rs:82-91; touching spheres intersect).
+    pub fn query_discrete_sphere(&self, queries: &[Sphere]) -> Result<Vec<Vec<usize>>> {
+        let flat: Vec<f32> = queries.iter().flat_map(|s| vec![s.center.x(), s.center.y(), s.center.z(), s.radius]).collect();
+        let mut off = vec![0u64; queries.len() + 1];
+        let (vals, _) = with_capacity(self.ctx, 16 * queries.len() as u64 + 1024, |cap, total| {
+            let mut vals = vec![0u32; cap as usize];
+            let rc = unsafe { ffi::bam3d_bvh_query_sphere(self.ctx.0, self.h, flat.as_ptr(), queries.len() as u64, off.as_mut_ptr(), vals.as_mut_ptr(), cap, total) };
+            (rc, vals)
+        })?;
+        Ok((0..queries.len()).map(|q| vals[off[q] as usize..off[q + 1] as usize].iter().map(|&v| v as usize).collect()).collect())
+    }
     /// `update_node` + `do_refit` for every value at once (dbvt/mod.rs:561-589): new bounds, same topology.
     pub fn refit(&mut self, bounds: &[Aabb3]) -> Result<()> {
         assert_eq!(bounds.len(), self.n);

@@ -92,6 +92,17 @@ class Oracle:
                                             _p(ct), _p(st), _p(mf), _p(it), _p(rem), C.c_int(nthreads), C.c_int(1 if in_phases else 0))
         return ct, st, mf, it, rem
 
+    def sphere_values_query(self, spheres, kind, query):
+        """The leaf predicate of a DBVT over volume::Sphere bounds applied to every value: kind 0 sphere (4 floats), 1 ray (6 floats,
+        -> points), 2 frustum (24 floats, -> relations). -> (values ascending, points[k, 3] | None, relation[k] | None)"""
+        spheres = np.ascontiguousarray(spheres, dtype=np.float32).reshape(-1, 4)
+        query = np.ascontiguousarray(query, dtype=np.float32).reshape(-1)
+        n = len(spheres)
+        vals, pts, rel = np.empty(n, dtype=np.uint32), np.empty((n, 3), dtype=np.float32), np.empty(n, dtype=np.uint8)
+        self.lib.orc_sphere_values_query.restype = C.c_uint64
+        k = self.lib.orc_sphere_values_query(_p(spheres), C.c_uint64(n), C.c_int32(kind), _p(query), _p(vals), _p(pts), _p(rel), C.c_uint64(n))
+        return vals[:k], (pts[:k] if kind == 1 else None), (rel[:k] if kind == 2 else None)
+
     def distance(self, scene, settings=None, nthreads=1, counters=None):
         kind, params, mesh_id, mv, mo = self._scene_args(scene)
         xform = np.ascontiguousarray(scene["xform"], dtype=np.float32)

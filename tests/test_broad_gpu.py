@@ -503,3 +503,82 @@ def test_pipeline_broad_then_narrow_matches_the_oracle_chain(ctx, oracle):
     small = broad.pipeline_contacts(gjk, shapes, b3.CollisionStrategy.CollisionOnly, sweep_axis=0, capacity=16)
     assert len(small["pairs"]) == len(opairs) or axis != 0
     shapes.close()
+
+
+def test_bvh_over_sphere_bounds_applies_the_sphere_predicates(ctx, oracle):
+    """DynamicBoundingVolumeTree is generic over the bound: with volume::Sphere (volume/sphere.rs:17-196) the visitors call
+    Discrete<Sphere>, Continuous<Ray> and PlaneBound for Sphere. The device tree's nodes are boxes that cover the spheres and its
+    leaves apply those predicates; the result sets (and hit points / relations, bit for bit) are compared with the predicates
+    applied to every value by the oracle (whose BSphere is pinned by all of tests/sphere.rs and the sphere cases of
+    tests/aabb.rs / tests/frustum.rs). Includes touching spheres, rays that start inside a sphere (a hit only while the centre
+    is ahead), axis-parallel rays, a degenerate pile of coincident spheres, and the host-buffer and device-resident forms."""
+    import torch
+    import ctypes as C
+    scene, L = scenes.world_scene(30_000, seed=0xB3D0C440)
+    shapes = b3.ShapeSet(ctx, scene["kind"], scene["params"], scene["xform"])
+    spheres = broad.world_spheres(shapes)                       # ComputeBound<volume::Sphere> of every shape
+    assert spheres.tobytes() == oracle.world_spheres(scene).tobytes()
+    spheres = spheres.copy()
+    spheres[-200:] = spheres[-1]                                  # a pile of 200 coincident spheres
+    spheres[100] = [1.0, 1.0, 1.0, 0.5]
+    spheres[101] = [2.5, 1.0, 1.0, 1.0]                           # touches sphere 100 exactly: (1.5)^2 <= (1.5)^2
+    tree = broad.SphereBvh(ctx, spheres)
+    # Discrete<Sphere>
+    q = spheres[::97].copy()
+    q[:, 3] *= 1.5
+    q[0] = spheres[100]
+    off, vals = tree.query_sphere(q)
+    total = 0
+    for k in range(len(q)):
+        want, _, _ = oracle.sphere_values_query(spheres, 0, q[k])
+        got = np.sort(vals[int(off[k]):int(off[k + 1])])
+        assert np.array_equal(got, want), f"sphere query {k}"
+        total += len(want)
+    assert total >= len(q) and {100, 101} <= set(vals[int(off[0]):int(off[1])].tolist())
+    # Continuous<Ray>: random unit directions, some origins at sphere centres (inside), some axis-parallel
+    rays = scenes.rays(400, L, seed=0xB3D0C441)
+    rays[:50, :3] = spheres[:50, :3]
+    rays[50:60, 3:] = [1.0, 0.0, 0.0]
+    off, vals, pts = tree.query_ray(rays)
+    hits = 0
+    for k in range(len(rays)):
+        want, wpts, _ = oracle.sphere_values_query(spheres, 1, rays[k])
+        sl = slice(int(off[k]), int(off[k + 1]))
+        order = np.argsort(vals[sl], kind="stable")
+        assert np.array_equal(vals[sl][order], want), f"ray {k}"
+        assert pts[sl][order].tobytes() == wpts.tobytes(), f"ray {k}: points"
+        hits += len(want)
+    assert hits > 100
+    # FrustumVisitor
+    planes = np.stack([broad.frustum_from_mat4(m).reshape(24) for m in scenes.view_projections(8, L, seed=0xB3D0C442)])
+    off, vals, rel = tree.query_frustum(planes)
+    seen = set()
+    for k in range(len(planes)):
+        want, _, wrel = oracle.sphere_values_query(spheres, 2, planes[k])
+        sl = slice(int(off[k]), int(off[k + 1]))
+        order = np.argsort(vals[sl], kind="stable")
+        assert np.array_equal(vals[sl][order], want) and np.array_equal(rel[sl][order], wrel), f"frustum {k}"
+        seen |= set(wrel.tolist())
+    assert 1 in seen and seen <= {0, 1}                           # In / Cross only (Out is not reported)
+    # device-resident one-pass form: the same hits in arbitrary order
+    dev = torch.device("cuda", 0)
+    d_q = torch.from_numpy(q).to(dev)
+    cap = int(total) + 16
+    d_oq, d_ov = torch.empty(cap, dtype=torch.int32, device=dev), torch.empty(cap, dtype=torch.int32, device=dev)
+    d_cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    tree.query_dev("sphere", p(d_q), len(q), p(d_oq), p(d_ov), None, cap, p(d_cnt))
+    ctx.synchronize()
+    assert int(d_cnt.item()) == total
+    got = np.stack([d_oq.cpu().numpy()[:total], d_ov.cpu().numpy()[:total]], axis=1).astype(np.uint32)
+    off, vals = tree.query_sphere(q)
+    want = np.stack([np.repeat(np.arange(len(q), dtype=np.uint32), np.diff(off).astype(np.int64)), vals], axis=1)
+    assert np.array_equal(got[np.lexsort((got[:, 1], got[:, 0]))], want[np.lexsort((want[:, 1], want[:, 0]))])
+    # what a sphere tree does not answer
+    for bad in (lambda: tree.query_aabb([[0, 0, 0, 1, 1, 1]]), lambda: tree.query_ray_closest(rays[:1]),
+                lambda: tree.find_collider_pairs(np.ones(tree.n, dtype=np.uint8)), lambda: broad.Bvh(ctx, [[0, 0, 0, 1, 1, 1]]).query_sphere(q[:1])):
+        with pytest.raises(b3.Bam3dError):
+            bad()
+    empty = broad.SphereBvh(ctx, np.zeros((0, 4), dtype=np.float32))
+    off, vals = empty.query_sphere(q[:3])
+    assert off.tolist() == [0, 0, 0, 0] and len(vals) == 0

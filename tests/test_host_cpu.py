@@ -508,6 +508,40 @@ def test_oracle_add_in_phases_equals_the_sequential_walk(oracle):
         assert (a[1] == 0).sum() > 3
 
 
+def test_oracle_sphere_bound_queries_agree_with_closed_forms(oracle):
+    """The oracle's leaf predicates of a DBVT over volume::Sphere bounds (used as the expected result of the device tree) against the
+    geometry in f64: sphere-sphere by centre distance, ray-sphere by the quadratic's smaller root (only when the centre is ahead of
+    the origin, as the reference decides it), frustum relation by signed plane distances — identical away from the boundaries."""
+    rng = np.random.default_rng(7)
+    sp = np.concatenate([rng.uniform(-10, 10, (4000, 3)), rng.uniform(0.1, 1.5, (4000, 1))], axis=1).astype(np.float32)
+    c, r = sp[:, :3].astype(np.float64), sp[:, 3].astype(np.float64)
+    q = np.array([0.5, -1.0, 2.0, 2.5], dtype=np.float32)
+    vals, _, _ = oracle.sphere_values_query(sp, 0, q)
+    gap = np.linalg.norm(c - q[:3].astype(np.float64), axis=1) - (r + float(q[3]))
+    sure = np.abs(gap) > 1e-4
+    assert np.array_equal(np.isin(np.arange(len(sp)), vals)[sure], (gap <= 0)[sure]) and len(vals) > 20
+    d = np.array([1.0, 2.0, -0.5]); d /= np.linalg.norm(d)
+    ray = np.concatenate([[-12.0, -9.0, 4.0], d]).astype(np.float32)
+    o, dd = ray[:3].astype(np.float64), ray[3:].astype(np.float64)
+    vals, pts, _ = oracle.sphere_values_query(sp, 1, ray)
+    l = c - o
+    tca = l @ dd
+    d2 = (l * l).sum(axis=1) - tca * tca
+    hit = (tca >= 0) & (d2 <= r * r)
+    sure = (np.abs(d2 - r * r) > 1e-3) & (np.abs(tca) > 1e-4)
+    assert np.array_equal(np.isin(np.arange(len(sp)), vals)[sure], hit[sure]) and len(vals) > 5
+    t = tca[vals] - np.sqrt(np.maximum(r[vals] ** 2 - d2[vals], 0.0))
+    assert np.abs(pts.astype(np.float64) - (o + t[:, None] * dd)).max() < 2e-3
+    planes = np.array([[1, 0, 0, -6], [-1, 0, 0, -6], [0, 1, 0, -6], [0, -1, 0, -6], [0, 0, 1, -6], [0, 0, -1, -6]], dtype=np.float32)  # the cube |x| < 6
+    vals, _, rel = oracle.sphere_values_query(sp, 2, planes.reshape(-1))
+    dist = c @ planes[:, :3].astype(np.float64).T - planes[:, 3].astype(np.float64)      # signed distances to the six planes
+    want = np.where((dist < -r[:, None]).any(axis=1), 2, np.where((dist > r[:, None]).all(axis=1), 0, 1))
+    sure = (np.abs(np.abs(dist) - r[:, None]) > 1e-4).all(axis=1)
+    got = np.full(len(sp), 2)
+    got[vals] = rel
+    assert np.array_equal(got[sure], want[sure]) and {0, 1} <= set(rel.tolist())
+
+
 def test_rust_ffi_covers_the_whole_abi():
     """rust/bam3d-gpu/src/ffi.rs is generated from include/bam3d_gpu.h (tools/gen_rust_ffi.py): the committed file must be what
     the generator writes today, and must declare every entry point the library exports (the hand-written shim
