@@ -305,6 +305,114 @@ private:
     int axis_;
 };
 
+// ---- DBVT queries (dbvt/mod.rs:451-515, visitor.rs, util.rs) ---------------------------------------------------------------------
+struct Ray { Vec3 origin, direction; };            // ray.rs (6 contiguous f32)
+struct Plane { Vec3 n; float d; };                 // plane.rs:17-22: n . x = d (4 contiguous f32)
+enum class Relation : uint8_t { In = 0, Cross = 1, Out = 2 };  // bound.rs:9-17
+struct Frustum {                                   // frustum.rs:17-24 (24 contiguous f32 in this order)
+    Plane left, right, bottom, top, near, far;
+    /// Frustum::from_mat4 (frustum.rs:46-75, including its near / far = left / right rows); nullopt where the reference returns None.
+    static std::optional<Frustum> from_mat4(const Mat4& m) {
+        Frustum f;
+        if (bam3d_frustum_from_mat4(m.data(), reinterpret_cast<float*>(&f)) != BAM3D_OK) return std::nullopt;
+        return f;
+    }
+};
+static_assert(sizeof(Frustum) == 96 && sizeof(Ray) == 24, "query layouts are the C ABI's");
+
+/// The query side of DynamicBoundingVolumeTree over a static set of values (value index = position in `bounds`), bounds being
+/// Aabb3 or volume::Sphere. Result sets equal the reference's (they do not depend on its randomised tree shape).
+class DynamicBoundingVolumeTree {
+public:
+    DynamicBoundingVolumeTree(const Context& ctx, const std::vector<Aabb3>& bounds) : ctx_(ctx), n_(bounds.size()) {
+        ctx_.check(bam3d_bvh_build(ctx_.handle(), reinterpret_cast<const float*>(bounds.data()), n_, &h_));
+    }
+    DynamicBoundingVolumeTree(const Context& ctx, const std::vector<Sphere>& bounds) : ctx_(ctx), n_(bounds.size()), spheres_(true) {
+        ctx_.check(bam3d_bvh_build_spheres(ctx_.handle(), reinterpret_cast<const float*>(bounds.data()), n_, &h_));
+    }
+    ~DynamicBoundingVolumeTree() { bam3d_bvh_free(ctx_.handle(), h_); }
+    DynamicBoundingVolumeTree(const DynamicBoundingVolumeTree&) = delete;
+    DynamicBoundingVolumeTree& operator=(const DynamicBoundingVolumeTree&) = delete;
+    /// update_node + do_refit for every value at once (dbvt/mod.rs:561-589): new bounds, same topology (box trees).
+    void refit(const std::vector<Aabb3>& bounds) { ctx_.check(bam3d_bvh_refit(ctx_.handle(), h_, reinterpret_cast<const float*>(bounds.data()))); }
+    /// query(&mut DiscreteVisitor::new(&bound)) (visitor.rs:57-90): the values whose bound intersects `bound`.
+    std::vector<uint32_t> query_discrete(const Aabb3& bound) const {
+        return var([&](uint64_t* off, uint32_t* v, uint64_t cap, uint64_t* total) {
+            return bam3d_bvh_query_aabb(ctx_.handle(), h_, reinterpret_cast<const float*>(&bound), 1, off, v, cap, total); });
+    }
+    std::vector<uint32_t> query_discrete(const Sphere& bound) const {
+        return var([&](uint64_t* off, uint32_t* v, uint64_t cap, uint64_t* total) {
+            return bam3d_bvh_query_sphere(ctx_.handle(), h_, reinterpret_cast<const float*>(&bound), 1, off, v, cap, total); });
+    }
+    /// query_ray (util.rs:114-129): (value, hit point) of every value the ray meets.
+    std::vector<std::pair<uint32_t, Vec3>> query_ray(const Ray& ray) const {
+        std::vector<Vec3> pts;
+        auto vals = var([&](uint64_t* off, uint32_t* v, uint64_t cap, uint64_t* total) {
+            pts.resize(cap);
+            return bam3d_bvh_query_ray(ctx_.handle(), h_, reinterpret_cast<const float*>(&ray), 1, off, v, reinterpret_cast<float*>(pts.data()), cap, total); });
+        std::vector<std::pair<uint32_t, Vec3>> out(vals.size());
+        for (size_t k = 0; k < vals.size(); ++k) out[k] = {vals[k], pts[k]};
+        return out;
+    }
+    /// query_ray_closest (util.rs:77-103): the hit of smallest t over all values the ray meets (box trees).
+    std::optional<std::pair<uint32_t, Vec3>> query_ray_closest(const Ray& ray) const {
+        uint32_t v = 0; float pt[4];
+        ctx_.check(bam3d_bvh_query_ray_closest(ctx_.handle(), h_, reinterpret_cast<const float*>(&ray), 1, &v, pt));
+        if (v == 0xFFFFFFFFu) return std::nullopt;
+        return std::make_pair(v, Vec3{pt[0], pt[1], pt[2]});
+    }
+    /// query(&mut FrustumVisitor::new(&frustum)) (visitor.rs:99-134): (value, Relation) — Out is never reported.
+    std::vector<std::pair<uint32_t, Relation>> query_frustum(const Frustum& f) const {
+        std::vector<uint8_t> rel;
+        auto vals = var([&](uint64_t* off, uint32_t* v, uint64_t cap, uint64_t* total) {
+            rel.resize(cap);
+            return bam3d_bvh_query_frustum(ctx_.handle(), h_, reinterpret_cast<const float*>(&f), 1, off, v, rel.data(), cap, total); });
+        std::vector<std::pair<uint32_t, Relation>> out(vals.size());
+        for (size_t k = 0; k < vals.size(); ++k) out[k] = {vals[k], static_cast<Relation>(rel[k])};
+        return out;
+    }
+    /// DbvtBroadPhase::find_collider_pairs (algorithm/broad_phase/dbvt.rs:26-63): sorted unique (low, high) value pairs.
+    std::vector<std::pair<uint32_t, uint32_t>> find_collider_pairs(const std::vector<uint8_t>& dirty) const {
+        uint64_t cap = 8 * n_ + 1024, count = 0;
+        std::vector<uint32_t> pairs;
+        for (;;) {
+            pairs.resize(2 * cap);
+            int32_t rc = bam3d_bvh_find_collider_pairs(ctx_.handle(), h_, dirty.data(), pairs.data(), cap, &count);
+            if (rc == BAM3D_ERR_CAPACITY && count > cap) { cap = count; continue; }
+            ctx_.check(rc);
+            break;
+        }
+        std::vector<std::pair<uint32_t, uint32_t>> out(count);
+        for (uint64_t k = 0; k < count; ++k) out[k] = {pairs[2 * k], pairs[2 * k + 1]};
+        return out;
+    }
+private:
+    template <class F> std::vector<uint32_t> var(F call) const {  // one query, retried with the reported size
+        uint64_t cap = 1024, total = 0, off[2] = {0, 0};
+        std::vector<uint32_t> vals;
+        for (;;) {
+            vals.resize(cap);
+            int32_t rc = call(off, vals.data(), cap, &total);
+            if (rc == BAM3D_ERR_CAPACITY && total > cap) { cap = total; continue; }
+            ctx_.check(rc);
+            break;
+        }
+        vals.resize(total);
+        return vals;
+    }
+    const Context& ctx_;
+    uint64_t n_;
+    bool spheres_ = false;
+    bam3d_bvh* h_ = nullptr;
+};
+
+/// ComputeBound<Aabb3> + Aabb::transform of every shape of the set (primitive3.rs:77-96, aabb3.rs:89-96).
+inline std::vector<Aabb3> world_aabbs(const Context& ctx, const ShapeSet& shapes) {
+    std::vector<Aabb3> out(bam3d_shapes_count(shapes.handle()));
+    ctx.check(bam3d_shapes_world_aabbs(ctx.handle(), shapes.handle(), reinterpret_cast<float*>(out.data())));
+    return out;
+}
+
 // Compound shapes: the reference's `&[(Primitive, Mat4)]` slices (gjk/mod.rs:362-371), one per compound, resident on the device,
 // and GJK::intersection_complex / distance_complex / intersection_complex_time_of_impact (gjk/mod.rs:362-523) over pairs of them.
 class CompoundSet {

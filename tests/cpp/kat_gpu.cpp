@@ -123,6 +123,57 @@ int main() {
             CHECK(cand[0].contact.has_value() && cand[0].contact->penetration_depth == 2.f);
         }
     }
+    {   // DBVT queries through the host layer: tests/dbvt.rs:39-53 test_frustum, ray-vs-Aabb3 KATs of tests/aabb.rs:62-157, DbvtBroadPhase
+        auto perspective_rh_gl = [](float fov_y, float aspect, float z_near, float z_far) {   // glam Mat4::perspective_rh_gl
+            const float inv_length = 1.0f / (z_near - z_far), f = 1.0f / std::tan(0.5f * fov_y), a = f / aspect;
+            return Mat4{a, 0, 0, 0, 0, f, 0, 0, 0, 0, (z_near + z_far) * inv_length, -1, 0, 0, (2.0f * z_near * z_far) * inv_length, 0};
+        };
+        DynamicBoundingVolumeTree tree(ctx, std::vector<Aabb3>{{{0.2f, 0.2f, 0.2f}, {10, 10, 10}}, {{0.2f, 0.2f, -10}, {10, 10, -0.2f}}});
+        auto fr = Frustum::from_mat4(perspective_rh_gl(60.0f * (3.14159265358979323846f / 180.0f), 16.f / 9.f, 0.1f, 4.0f));
+        CHECK(fr.has_value());
+        if (fr) {
+            auto hits = tree.query_frustum(*fr);
+            CHECK(hits.size() == 1);
+            if (hits.size() == 1) CHECK(hits[0].first == 1 && hits[0].second == Relation::Cross);
+        }
+        DynamicBoundingVolumeTree one(ctx, std::vector<Aabb3>{{{1, 1, 1}, {5, 5, 5}}});
+        CHECK(one.query_ray(Ray{{0, 0, 0}, {1, 0, 0}}).empty());
+        CHECK(one.query_ray(Ray{{6, 2, 2}, {1, 0, 0}}).empty());
+        auto h = one.query_ray(Ray{{0, 6, 0}, {1, -1, 1}});
+        CHECK(h.size() == 1);
+        if (h.size() == 1) CHECK(h[0].first == 0 && h[0].second[0] == 1.f && h[0].second[1] == 5.f && h[0].second[2] == 1.f);
+        auto c = one.query_ray_closest(Ray{{6, 2, 2}, {-1, 0, 0}});
+        CHECK(c.has_value());
+        if (c) CHECK(c->first == 0 && c->second[0] == 5.f && c->second[1] == 2.f && c->second[2] == 2.f);
+        CHECK(!one.query_ray_closest(Ray{{6, 2, 2}, {1, 0, 0}}).has_value());
+        CHECK(one.query_discrete(Aabb3{{4, 4, 4}, {6, 6, 6}}).size() == 1 && one.query_discrete(Aabb3{{5, 5, 5}, {6, 6, 6}}).empty());  // strict overlap
+        DynamicBoundingVolumeTree three(ctx, std::vector<Aabb3>{{{0, 0, 0}, {2, 2, 2}}, {{1, 1, 1}, {3, 3, 3}}, {{5, 5, 5}, {6, 6, 6}}});
+        auto pairs = three.find_collider_pairs({1, 1, 1});
+        CHECK(pairs.size() == 1);
+        if (pairs.size() == 1) CHECK(pairs[0].first == 0 && pairs[0].second == 1);
+        // the same tree type over volume::Sphere bounds: tests/sphere.rs:7-47 test_intersection, tests/frustum.rs test_contains (with the
+        // 1-radian field of view for which its expectations hold: DESIGN.md, documented discrepancies)
+        DynamicBoundingVolumeTree ball(ctx, std::vector<Sphere>{{{0, 0, 0}, 1.f}});
+        auto b0 = ball.query_ray(Ray{{0, 0, 5}, {0, 0, -1}});
+        CHECK(b0.size() == 1);
+        if (b0.size() == 1) CHECK(b0[0].second[0] == 0.f && b0[0].second[1] == 0.f && b0[0].second[2] == 1.f);
+        auto b2 = ball.query_ray(Ray{{1, 0, 5}, {0, 0, -1}});
+        CHECK(b2.size() == 1);
+        if (b2.size() == 1) CHECK(b2[0].second[0] == 1.f && b2[0].second[1] == 0.f && b2[0].second[2] == 0.f);
+        CHECK(ball.query_ray(Ray{{2, 0, 5}, {0, 0, -1}}).empty());
+        CHECK(ball.query_discrete(Sphere{{2, 0, 0}, 1.f}).size() == 1 && ball.query_discrete(Sphere{{2.5f, 0, 0}, 1.f}).empty());   // touching spheres intersect
+        DynamicBoundingVolumeTree balls(ctx, std::vector<Sphere>{{{0, 0, -5}, 1.f}, {{0, 3, -5}, 1.f}, {{0, 0, 5}, 1.f}});
+        auto fr2 = Frustum::from_mat4(perspective_rh_gl(1.0f, 1.f, 1.f, 10.f));
+        CHECK(fr2.has_value());
+        if (fr2) {
+            auto hits = balls.query_frustum(*fr2);
+            CHECK(hits.size() == 2);
+            for (auto& kv : hits) CHECK((kv.first == 0 && kv.second == Relation::In) || (kv.first == 1 && kv.second == Relation::Cross));
+        }
+        bool threw = false;
+        try { ball.query_discrete(Aabb3{{0, 0, 0}, {1, 1, 1}}); } catch (const Error&) { threw = true; }
+        CHECK(threw);   // an Aabb3 query against sphere bounds is not a reference operation
+    }
     std::printf("kat_gpu: %s\n", fails ? "FAILED" : "all passed");
     return fails ? 1 : 0;
 }
