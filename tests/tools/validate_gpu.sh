@@ -1,9 +1,10 @@
 #!/bin/bash
+# Final check of a build on one GPU: pytest -m gpu, smoke(), the default bench line and the reference arm. Run with gpurun.
 mkdir -p gpurun_out
-timeout -s KILL 900 python -m pytest tests -m gpu -q 2>&1 | tail -4 | tee gpurun_out/c27_pytest.log
+timeout -s KILL 900 python -m pytest tests -m gpu -q 2>&1 | tail -4 | tee gpurun_out/val_pytest.log
 timeout -s KILL 200 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
-timeout -s KILL 600 python bench.py > gpurun_out/bench_c5_r2_final.json 2> gpurun_out/c27_bench.err; echo "bench rc=$?"
-timeout -s KILL 600 python bench.py --impl reference > gpurun_out/bench_c5_reference_r2_final.json 2> gpurun_out/c27_ref.err; echo "ref rc=$?"
+timeout -s KILL 600 python bench.py > gpurun_out/bench_c5_r2_final.json 2> gpurun_out/val_bench.err; echo "bench rc=$?"
+timeout -s KILL 600 python bench.py --impl reference > gpurun_out/bench_c5_reference_r2_final.json 2> gpurun_out/val_ref.err; echo "ref rc=$?"
 python - <<'PY'
 import json
 d = json.loads(open('gpurun_out/bench_c5_r2_final.json').read().strip().splitlines()[-1])
