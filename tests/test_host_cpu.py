@@ -570,3 +570,50 @@ def test_rust_ffi_covers_the_whole_abi():
     for impl in ("Discrete<Ray> for DeviceShape", "Continuous<Ray> for DeviceShape", "Discrete<DeviceShape", "Continuous<DeviceShape"):
         assert impl in traits, impl
     assert len(used) >= 45
+
+
+def test_affine_layout_helper_and_cpu_rate_bookkeeping():
+    """Host-side pieces with no GPU in them: the 48-byte transform layout (api.affine3x4) and the CPU arm's two rates."""
+    from bam3d_b200 import scenes
+    from bam3d_b200.api import affine3x4
+    import bench
+    sc = scenes.mixed_pairs(64, s=1.5)
+    x = np.ascontiguousarray(sc["xform"], dtype=np.float32).reshape(-1, 16)
+    a = affine3x4(x)
+    assert a.shape == (len(x), 12) and a.dtype == np.float32
+    back = np.zeros_like(x)
+    back.reshape(-1, 4, 4)[:, :, :3] = a.reshape(-1, 4, 3)
+    back[:, 15] = 1.0
+    assert back.tobytes() == x.tobytes()                      # nothing but the constant row is dropped
+    bad = x.copy()
+    bad[5, 7] = 1e-3                                          # y column's w
+    with pytest.raises(ValueError):
+        affine3x4(bad)
+    o = bench.cpu_baseline_object(1000, wall=2.0, cpu_s=4.0, cores=8, what="sample")
+    assert o["value"] == 1000 / 0.5 and o["wall_value"] == 500.0 and o["cores"] == 8 and "balanced" in o["value_is"]
+    assert bench.cpu_baseline_object(10, wall=1.0, cpu_s=0.0, cores=4, what="x")["value"] == 10.0
+
+
+def test_profile_summaries_from_ncu_csv(tmp_path):
+    """profiles/summarize.py: the launch-list table, the step cut and the counters file bench.py's roofline object reads."""
+    import importlib.util
+    import json
+    spec = importlib.util.spec_from_file_location("summarize", os.path.join(ROOT, "profiles", "summarize.py"))
+    sm = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sm)
+    hdr = '"ID","Process ID","Process Name","Host Name","Kernel Name","Context","Stream","Block Size","Grid Size","Device","CC","Section Name","Metric Name","Metric Unit","Metric Value"\n'
+    def rows(i, k, ns, rd, wr):
+        base = f'"{i}","1","python","h","{k}","1","7","(128, 1, 1)","(1, 1, 1)","0","10.0","s",'
+        return base + f'"dram__bytes_read.sum","byte","{rd}"\n' + base + f'"dram__bytes_write.sum","byte","{wr}"\n' + base + f'"gpu__time_duration.sum","ns","{ns}"\n'
+    csv_text = "==PROF== log line\n" + hdr + rows(0, "void b3::pack_shapes_kernel<0>(int)", 1000, 10, 10) + rows(1, "void b3::gjk_phase_kernel(int)", 2_000_000, 100, 50) + \
+        rows(2, "void b3::epa_refill_kernel<1, 0>(int)", 6_000_000, 3000, 1000) + rows(3, "void b3::compact_contacts_kernel(int)", 1_000_000, 20, 20) + \
+        rows(4, "void b3::gjk_phase_kernel(int)", 2_000_000, 100, 50)
+    src = tmp_path / "l.csv"
+    src.write_text(csv_text)
+    ls = sm.read_launches(str(src))
+    assert [d["k"] for d in ls][:3] == ["pack_shapes_kernel<0>", "gjk_phase_kernel", "epa_refill_kernel<1, 0>"] and ls[2]["ms"] == 6.0 and ls[2]["dram"] == 4000.0
+    sm.launches(str(src), str(tmp_path / "l.txt"))
+    assert "epa_refill_kernel<1, 0>" in (tmp_path / "l.txt").read_text()
+    sm.step(str(src), str(tmp_path / "s.txt"), "compact_contacts", str(tmp_path / "c.json"), "c5")
+    c = json.load(open(tmp_path / "c.json"))["c5"]
+    assert c["launches_per_step"] == 3 and c["dram_bytes"] == 150 + 4000 + 40 and abs(c["step_ms_under_ncu"] - 9.0) < 1e-9 and c["top_kernel"].startswith("epa_refill")
