@@ -327,7 +327,7 @@ public:
     DynamicBoundingVolumeTree(const Context& ctx, const std::vector<Aabb3>& bounds) : ctx_(ctx), n_(bounds.size()) {
         ctx_.check(bam3d_bvh_build(ctx_.handle(), reinterpret_cast<const float*>(bounds.data()), n_, &h_));
     }
-    DynamicBoundingVolumeTree(const Context& ctx, const std::vector<Sphere>& bounds) : ctx_(ctx), n_(bounds.size()), spheres_(true) {
+    DynamicBoundingVolumeTree(const Context& ctx, const std::vector<Sphere>& bounds) : ctx_(ctx), n_(bounds.size()) {
         ctx_.check(bam3d_bvh_build_spheres(ctx_.handle(), reinterpret_cast<const float*>(bounds.data()), n_, &h_));
     }
     ~DynamicBoundingVolumeTree() { bam3d_bvh_free(ctx_.handle(), h_); }
@@ -402,7 +402,6 @@ private:
     }
     const Context& ctx_;
     uint64_t n_;
-    bool spheres_ = false;
     bam3d_bvh* h_ = nullptr;
 };
 
