@@ -617,3 +617,25 @@ def test_profile_summaries_from_ncu_csv(tmp_path):
     sm.step(str(src), str(tmp_path / "s.txt"), "compact_contacts", str(tmp_path / "c.json"), "c5")
     c = json.load(open(tmp_path / "c.json"))["c5"]
     assert c["launches_per_step"] == 3 and c["dram_bytes"] == 150 + 4000 + 40 and abs(c["step_ms_under_ncu"] - 9.0) < 1e-9 and c["top_kernel"].startswith("epa_refill")
+
+
+def test_bench_reference_arm_contract_and_no_gpu_fallback():
+    """bench.py on a box without a GPU: `--impl reference` prints one JSON line with the contract's keys (the CPU arm is the oracle
+    port: no GPU needed), and the GPU arm refuses to run instead of falling back to anything."""
+    import json
+    import subprocess
+    import sys
+    import torch
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "c2", "--pairs", "8192", "--cpu-pairs", "8192",
+                        "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["steps"] == 2 and line["value"] > 0 and line["higher_is_better"] is True
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["wall_value"] > 0
+    assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0 and line["config"]["pairs_per_gpu"] == 8192
+    if not torch.cuda.is_available():
+        g = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", "c2", "--pairs", "8192", "--steps", "1", "--warmup", "1"],
+                           capture_output=True, text=True, timeout=300, cwd=ROOT)
+        assert g.returncode != 0 and "no CUDA device" in (g.stderr + g.stdout) and not g.stdout.strip().startswith("{")
