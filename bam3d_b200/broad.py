@@ -242,8 +242,8 @@ class Bvh:
 
 class SphereBvh(Bvh):
     """The same tree over values whose bound is volume::Sphere (bam3d_bvh_build_spheres): spheres[n, 4] = (centre.xyz, radius).
-    query_sphere / query_ray / query_frustum apply the sphere's own predicates (volume/sphere.rs); query_aabb, query_ray_closest,
-    refit and find_collider_pairs are not available on it (the library reports BAM3D_ERR_ARG)."""
+    query_sphere / query_ray / query_ray_closest / query_frustum / find_collider_pairs apply the sphere's own predicates
+    (volume/sphere.rs); query_aabb and refit are not available on it (the library reports BAM3D_ERR_ARG)."""
 
     def __init__(self, ctx, spheres):
         self.ctx = ctx

@@ -1148,11 +1148,19 @@ __global__ void __launch_bounds__(BT) bvh_ray_closest_kernel(BvhDev T, const flo
         V3 p;
         bool entered_from_outside;
         if (!ray_aabb(o, d, mn, mx, p, &entered_from_outside)) return false;
-        const float t = dot(p - o, d);
+        float t = dot(p - o, d);
         if (leaf) {
+            if (T.spheres) {  // sphere bounds: the leaf's own Continuous<Ray> point (t < 0 when the origin is inside the sphere, as in the reference)
+                Query q;
+                q.o = o; q.d = d;
+                int rel = 0;
+                if (!sphere_leaf<BQ_RAY>(q, __ldg(T.spheres + v), p, rel)) return false;
+                t = dot(p - o, d);
+            }
             if (t < best_t || (t == best_t && v < best_v)) { best_t = t; best_v = v; best_p = p; }
             return false;
         }
+        // (a node of a sphere tree is a box that covers its spheres: its entry t bounds theirs from below when the origin is outside it)
         return !(entered_from_outside && t > best_t);
     });
     out_value[qi] = best_v;
@@ -1189,6 +1197,12 @@ __global__ void __launch_bounds__(BT) bvh_collider_pairs_kernel(BvhDev T, const 
         bvh_traverse(T, [&](bool leaf, uint32_t h, float4 mn, float4 mx) {
             V3 pt; int rel;
             if (!accept<BQ_AABB>(q, mn, mx, pt, rel)) return false;
+            if (leaf && T.spheres) {  // sphere bounds: Discrete<Sphere> decides (the cover boxes only route the traversal)
+                const float4 a = __ldg(T.spheres + v), c = __ldg(T.spheres + h);
+                const V3 dist = v3(c.x, c.y, c.z) - v3(a.x, a.y, a.z);   // bound(h).intersects(bound(v)): self = the tree value
+                const float radiuses = c.w + a.w;
+                if (!(dot(dist, dist) <= radiuses * radiuses)) return true;
+            }
             if (leaf && h != v && (dirty ? (!dirty[h] || v < h) : h < v)) {
                 if (FILL) keys[w++] = key_shift ? (((unsigned long long)max(v, h) << key_shift) | min(v, h))
                                                 : (((unsigned long long)min(v, h) << 32) | max(v, h));

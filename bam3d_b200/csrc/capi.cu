@@ -1418,7 +1418,6 @@ int32_t bam3d_bvh_query_frustum(bam3d_ctx* ctx, const bam3d_bvh* t, const float*
 
 int32_t bam3d_bvh_query_ray_closest(bam3d_ctx* ctx, const bam3d_bvh* t, const float* rays, uint64_t nq64, uint32_t* out_value, float* out_point_t) {
     if (!ctx || !t || (nq64 && (!rays || !out_value || !out_point_t))) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_bvh_query_ray_closest: null argument", cudaSuccess);
-    if (t->d_spheres) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_bvh_query_ray_closest: not available over sphere bounds (use bam3d_bvh_query_ray)", cudaSuccess);
     int32_t rc;
     if ((rc = check_n(ctx, nq64))) return rc;
     if (nq64 == 0) return BAM3D_OK;
@@ -1473,7 +1472,6 @@ int32_t bam3d_bvh_query_frustum_dev(bam3d_ctx* ctx, const bam3d_bvh* t, const fl
 }
 int32_t bam3d_bvh_query_ray_closest_dev(bam3d_ctx* ctx, const bam3d_bvh* t, const float* d_rays, uint64_t nq64, uint32_t* d_out_value, float* d_out_point_t) {
     if (!ctx || !t || (nq64 && (!d_rays || !d_out_value || !d_out_point_t))) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_bvh_query_ray_closest_dev: null argument", cudaSuccess);
-    if (t->d_spheres) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_bvh_query_ray_closest: not available over sphere bounds (use bam3d_bvh_query_ray)", cudaSuccess);
     int32_t rc;
     if ((rc = check_n(ctx, nq64))) return rc;
     if (nq64 == 0) return BAM3D_OK;
@@ -1485,7 +1483,6 @@ int32_t bam3d_bvh_query_ray_closest_dev(bam3d_ctx* ctx, const bam3d_bvh* t, cons
 
 int32_t bam3d_bvh_find_collider_pairs(bam3d_ctx* ctx, const bam3d_bvh* t, const uint8_t* dirty, uint32_t* out_pairs, uint64_t capacity, uint64_t* out_count) {
     if (!ctx || !t || !out_count || (t->n && !dirty) || (capacity && !out_pairs)) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_bvh_find_collider_pairs: null argument", cudaSuccess);
-    if (t->d_spheres) return b3_fail(ctx, BAM3D_ERR_ARG, "bam3d_bvh_find_collider_pairs: not available over sphere bounds (bam3d_sap_find_pairs_spheres is the sphere broad phase)", cudaSuccess);
     CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
     *out_count = 0;
     const uint32_t n = t->n;

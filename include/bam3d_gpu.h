@@ -356,8 +356,11 @@ int32_t bam3d_bvh_query_ray_closest_dev(bam3d_ctx* ctx, const bam3d_bvh* bvh, co
  *   bam3d_bvh_query_ray[_dev]      ContinuousVisitor: Continuous<Ray> for Sphere (:50-67) — the first point on the sphere, no hit when
  *                                  the centre is behind the origin; directions are unit vectors, as Ray::new's callers provide
  *   bam3d_bvh_query_frustum[_dev]  FrustumVisitor: Frustum::contains over PlaneBound for Sphere (:93-104)
- * bam3d_bvh_query_aabb, _ray_closest, _refit and _find_collider_pairs return BAM3D_ERR_ARG on such a tree (rebuild instead of
- * refit; bam3d_sap_find_pairs_spheres is the sphere broad phase), bam3d_bvh_query_sphere on a tree over boxes likewise. */
+ *   bam3d_bvh_query_ray_closest[_dev]  the smallest t = (point - origin) . direction over the spheres the ray meets (negative when the
+ *                                  origin is inside that sphere: Continuous<Ray> returns the point behind it), ties to the lowest value
+ *   bam3d_bvh_find_collider_pairs  DbvtBroadPhase with Discrete<Sphere> as the leaf test
+ * bam3d_bvh_query_aabb and bam3d_bvh_refit return BAM3D_ERR_ARG on such a tree (rebuild instead of refit), bam3d_bvh_query_sphere on
+ * a tree over boxes likewise. */
 int32_t bam3d_bvh_build_spheres(bam3d_ctx* ctx, const float* spheres, uint64_t n, bam3d_bvh** out);
 int32_t bam3d_bvh_build_spheres_dev(bam3d_ctx* ctx, const float* d_spheres, uint64_t n, bam3d_bvh** out);
 int32_t bam3d_bvh_query_sphere(bam3d_ctx* ctx, const bam3d_bvh* bvh, const float* spheres, uint64_t nq, uint64_t* out_offsets, uint32_t* out_values,

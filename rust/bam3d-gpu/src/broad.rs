@@ -117,8 +117,8 @@ impl<'a> DynamicBoundingVolumeTree<'a> {
         Ok(DynamicBoundingVolumeTree { ctx, h, n: bounds.len() })
     }
     /// The same tree over values bounded by `volume::Sphere` (`DynamicBoundingVolumeTree` is generic over the bound): `query_ray`
-    /// and `query_frustum` then apply `Continuous<Ray>` / `PlaneBound for Sphere`, `query_discrete_sphere` `Discrete<Sphere>`;
-    /// `query_discrete`, `query_ray_closest` and `refit` report an error on such a tree.
+    /// `query_ray_closest` and `query_frustum` then apply `Continuous<Ray>` / `PlaneBound for Sphere`, `query_discrete_sphere` and
+    /// `DbvtBroadPhase` `Discrete<Sphere>`; `query_discrete` (an Aabb3 query) and `refit` report an error on such a tree.
     pub fn new_with_spheres(ctx: &'a Context, bounds: &[Sphere]) -> Result<Self> {
         let flat: Vec<f32> = bounds.iter().flat_map(|s| vec![s.center.x(), s.center.y(), s.center.z(), s.radius]).collect();
         let mut h = std::ptr::null_mut();

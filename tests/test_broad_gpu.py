@@ -574,9 +574,31 @@ def test_bvh_over_sphere_bounds_applies_the_sphere_predicates(ctx, oracle):
     off, vals = tree.query_sphere(q)
     want = np.stack([np.repeat(np.arange(len(q), dtype=np.uint32), np.diff(off).astype(np.int64)), vals], axis=1)
     assert np.array_equal(got[np.lexsort((got[:, 1], got[:, 0]))], want[np.lexsort((want[:, 1], want[:, 0]))])
+    # closest hit: the smallest t = (point - origin) . direction over the spheres a ray meets, ties to the lowest value
+    val, pt = tree.query_ray_closest(rays)
+    f32 = np.float32
+    for k in range(len(rays)):
+        want, wpts, _ = oracle.sphere_values_query(spheres, 1, rays[k])
+        if len(want) == 0:
+            assert val[k] == 0xFFFFFFFF
+            continue
+        dlt = wpts - rays[k, :3]
+        t = (dlt[:, 0] * rays[k, 3] + dlt[:, 1] * rays[k, 4]).astype(f32) + (dlt[:, 2] * rays[k, 5]).astype(f32)
+        best = int(np.flatnonzero(t == t.min())[0])           # `want` ascends: the first minimum is the lowest value
+        assert val[k] == want[best] and pt[k, :3].tobytes() == wpts[best].tobytes() and pt[k, 3] == t[best], f"closest ray {k}"
+    assert (pt[:50, 3][val[:50] != 0xFFFFFFFF] < 0).any()        # origins at sphere centres: the reference's point lies behind them
+    # DbvtBroadPhase over sphere bounds, all values dirty on a sub-tree
+    sub = spheres[:3000].copy()
+    sub_tree = broad.SphereBvh(ctx, sub)
+    pairs = sub_tree.find_collider_pairs(np.ones(len(sub), dtype=np.uint8))
+    want_pairs = []
+    for i in range(len(sub)):
+        v, _, _ = oracle.sphere_values_query(sub, 0, sub[i])
+        want_pairs += [(i, int(j)) for j in v if j > i]
+    assert np.array_equal(pairs, np.array(want_pairs, dtype=np.uint32).reshape(-1, 2)) and len(want_pairs) > 100
     # what a sphere tree does not answer
-    for bad in (lambda: tree.query_aabb([[0, 0, 0, 1, 1, 1]]), lambda: tree.query_ray_closest(rays[:1]),
-                lambda: tree.find_collider_pairs(np.ones(tree.n, dtype=np.uint8)), lambda: broad.Bvh(ctx, [[0, 0, 0, 1, 1, 1]]).query_sphere(q[:1])):
+    for bad in (lambda: tree.query_aabb([[0, 0, 0, 1, 1, 1]]), lambda: tree.refit(np.zeros((tree.n, 6), dtype=np.float32)),
+                lambda: broad.Bvh(ctx, [[0, 0, 0, 1, 1, 1]]).query_sphere(q[:1])):
         with pytest.raises(b3.Bam3dError):
             bad()
     empty = broad.SphereBvh(ctx, np.zeros((0, 4), dtype=np.float32))
