@@ -639,3 +639,96 @@ def test_bench_reference_arm_contract_and_no_gpu_fallback():
         g = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", "c2", "--pairs", "8192", "--steps", "1", "--warmup", "1"],
                            capture_output=True, text=True, timeout=300, cwd=ROOT)
         assert g.returncode != 0 and "no CUDA device" in (g.stderr + g.stdout) and not g.stdout.strip().startswith("{")
+
+
+def test_oracle_gjk_epa_equals_a_literal_python_replay_of_the_reference(oracle):
+    """The C++ oracle's GJK::intersection against tests/replay_gjk_epa.py — the reference's control flow (simplex processor, EPA's
+    ordered lists, first-minimum closest face, swap_remove walk, remove_or_add_edge) transcribed a second time, from the Rust source
+    into Python, one f32 operation at a time — on Sphere / Cuboid pairs under translations: hit / miss, normal, depth and contact
+    point bit for bit. Axis-aligned Cuboid pairs are the tie-heavy cases (coplanar faces, equal distances), Sphere pairs the long
+    ones (EPA runs ~70 trips and ~140 faces). The replay reproduces the reference's own test_gjk_3d_hit value first."""
+    from tests import replay_gjk_epa as R
+    import bam3d_b200._ffi as F
+    c = R.Cuboid(5, 5, 5)
+    normal, depth, point, _, _ = R.intersection(c, R.v3(15, 0, 0), c, R.v3(7, 2, 0))     # gjk/mod.rs:585-596
+    assert [float(x) for x in normal] == [-1.0, 0.0, 0.0] and float(depth) == 2.0
+    assert [np.float32(x) for x in point] == [np.float32(10.0), np.float32(1.0000002), np.float32(4.999999)]
+    rng = np.random.default_rng(20240611)
+    n = 1600
+    kind = np.empty(2 * n, dtype=np.uint8)
+    params = np.zeros((2 * n, 4), dtype=np.float32)
+    pos = np.zeros((2 * n, 3), dtype=np.float32)
+    prims = []
+    for i in range(2 * n):
+        combo = (i // 2) % 4                              # SS, SC, CS, CC
+        is_sphere = (combo in (0, 1)) if i % 2 == 0 else (combo in (0, 2))
+        if is_sphere:
+            r = np.float32(rng.uniform(0.5, 1.5))
+            kind[i], params[i, 0] = F.KIND_SPHERE, r
+            prims.append(R.Sphere(r))
+        else:
+            h = rng.uniform(0.4, 1.4, 3).astype(np.float32)
+            if (i // 8) % 3 == 0:
+                h = np.round(h * 4) / np.float32(4)       # quarter-unit boxes: exact ties between corners and faces
+            kind[i], params[i, :3] = F.KIND_CUBOID, h
+            prims.append(R.Cuboid(*h))
+        pos[i] = rng.uniform(-1.0, 1.0, 3) if i % 2 else 0.0
+        if (i // 8) % 3 == 0 and i % 2:
+            pos[i] = np.round(pos[i] * 4) / 4             # ... at quarter-unit offsets
+    pos[1::2] *= np.float32(2.0)
+    xform = np.tile(np.eye(4, dtype=np.float32).reshape(16), (2 * n, 1))
+    xform[:, 12:15] = pos
+    scene = dict(kind=kind, params=params, xform=xform, mesh_id=None, mesh_verts=None, mesh_offsets=None,
+                 pairs=np.arange(2 * n, dtype=np.uint32).reshape(n, 2))
+    oc, ohit, ost = oracle.contact(scene, strategy=0, nthreads=4)
+    hits = 0
+    for k in range(n):
+        r = R.intersection(prims[2 * k], tuple(pos[2 * k]), prims[2 * k + 1], tuple(pos[2 * k + 1]))
+        assert (r is not None) == (ost[k] == 0), f"pair {k}: hit/miss"
+        if r is None:
+            continue
+        hits += 1
+        got = np.array(list(r[0]) + [r[1]] + list(r[2]), dtype=np.float32)
+        assert got.tobytes() == oc[k, :7].tobytes(), f"pair {k} ({['SS', 'SC', 'CS', 'CC'][k % 4]}): {got} vs {oc[k, :7]}"
+    assert n // 3 < hits < n - n // 8
+
+
+def test_oracle_distance_equals_a_literal_python_replay_of_the_reference(oracle):
+    """GJK::distance the same way: tests/replay_gjk_epa.py transcribes gjk/mod.rs:231-280 with get_closest_point_to_origin,
+    get_closest_point_on_face (its unwrap() and assert! become ReferencePanic), get_closest_point_on_edge, Plane::from_points and
+    the plane x ray intersection from the Rust source. Outcome class (Some / None: colliding / None: iteration cap / panic) and the
+    returned value (dp - d0) must equal the C++ oracle's on Sphere / Cuboid pairs under translations, bit for bit."""
+    from tests import replay_gjk_epa as R
+    import bam3d_b200._ffi as F
+    rng = np.random.default_rng(5)
+    n = 1200
+    kind = np.empty(2 * n, dtype=np.uint8)
+    params = np.zeros((2 * n, 4), dtype=np.float32)
+    pos = np.zeros((2 * n, 3), dtype=np.float32)
+    prims = []
+    for i in range(2 * n):
+        combo = (i // 2) % 4
+        is_sphere = (combo in (0, 1)) if i % 2 == 0 else (combo in (0, 2))
+        if is_sphere:
+            r = np.float32(rng.uniform(0.5, 1.5))
+            kind[i], params[i, 0] = F.KIND_SPHERE, r
+            prims.append(R.Sphere(r))
+        else:
+            h = rng.uniform(0.4, 1.4, 3).astype(np.float32)
+            kind[i], params[i, :3] = F.KIND_CUBOID, h
+            prims.append(R.Cuboid(*h))
+        pos[i] = rng.uniform(-3, 3, 3) if i % 2 else 0.0
+    xform = np.tile(np.eye(4, dtype=np.float32).reshape(16), (2 * n, 1))
+    xform[:, 12:15] = pos
+    scene = dict(kind=kind, params=params, xform=xform, mesh_id=None, mesh_verts=None, mesh_offsets=None,
+                 pairs=np.arange(2 * n, dtype=np.uint32).reshape(n, 2))
+    ref, _, _, st = oracle.distance(scene, nthreads=4)
+    status_of = {"some": F.STATUS_OK, "none": F.STATUS_MISS, "max_iterations": F.STATUS_MAX_ITER, "panic": F.STATUS_REF_PANIC}
+    seen = set()
+    for k in range(n):
+        r = R.distance(prims[2 * k], tuple(pos[2 * k]), prims[2 * k + 1], tuple(pos[2 * k + 1]))
+        assert status_of[r[0]] == st[k], f"pair {k}: replay {r[0]}, oracle status {st[k]}"
+        if r[0] == "some":
+            assert np.float32(r[1]).tobytes() == ref[k].tobytes(), f"pair {k}: {r[1]} vs {ref[k]}"
+        seen.add(r[0])
+    assert seen == {"some", "none", "max_iterations", "panic"}
