@@ -2,16 +2,21 @@
 GJK::intersect (algorithm/minkowski/gjk/mod.rs:74-113), SimplexProcessor3::reduce_to_closest_feature + check_side
 (gjk/simplex/simplex3d.rs:16-89,160-205), EPA3::process with Polytope / Face / remove_or_add_edge (epa/epa3d.rs:16-190),
 contact() / point() (:69-94), barycentric_vector (primitive/util.rs:44-60), SupportPoint::from_minkowski (minkowski/mod.rs:33-51)
-and the Sphere / Cuboid support functions (primitive/sphere.rs:21-24, cuboid.rs:46-63, util.rs:7-23) — written from the Rust
+and the Sphere / Cuboid / Cylinder / Capsule support functions (primitive/sphere.rs:21-24, cuboid.rs:46-63, util.rs:7-23,
+cylinder.rs:38-61, capsule.rs:41-48) — written from the Rust
 source with Python lists for the SmallVec / Vec containers (remove, swap, swap_remove, position + remove), one f32 operation at a
 time (numpy.float32 scalars: every product and sum is rounded separately, as glam's scalar-math does without FMA).
-Only TRANSLATION transforms are supported: Mat4::inverse().transform_vector3 is then the identity and transform_point3 is
-`w_axis + p` (glam 0.8: the x, y, z axis products are exact), so nothing of glam's matrix code is restated here.
+Transforms are full Mat4s: glam 0.8's scalar Mat4::inverse (cofactor expansion with its sign vectors), transform_vector3 and
+transform_point3 are restated below as well — they have to be, even for translations: the inverse of a translation has -0.0 in
+some off-diagonal entries, so a direction component of exactly +-0 can change its sign on the way through, and Cylinder / Capsule
+supports branch on that sign (an axis-aligned EPA face normal is enough to get there). The control flow is what this replay
+restates independently; the glam formulas are the same assumption the oracle makes (glam is not vendored in the reference).
 tests/test_host_cpu.py compares the C++ oracle with this replay bit for bit. TEST INFRASTRUCTURE ONLY."""
 import numpy as np
 
 f32 = np.float32
 ZERO = (f32(0), f32(0), f32(0))
+F32_EPS = f32(1.1920929e-07)  # f32::EPSILON
 
 
 def v3(x, y, z):
@@ -50,13 +55,67 @@ def is_zero(a):
     return a[0] == 0 and a[1] == 0 and a[2] == 0
 
 
+class Mat4:
+    """glam 0.8 Mat4, column-major: cols[c] = (x, y, z, w) of column c."""
+
+    def __init__(self, cols16):
+        m = [f32(x) for x in cols16]
+        self.c = [tuple(m[4 * k:4 * k + 4]) for k in range(4)]
+        self._inv = None
+
+    @staticmethod
+    def from_translation(t):
+        return Mat4([1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, t[0], t[1], t[2], 1])
+
+    def transform_point3(self, p):   # r = x_axis * p.x; r = y_axis * p.y + r; r = z_axis * p.z + r; r = w_axis + r
+        x, y, z, w = (c[:3] for c in self.c)
+        r = scale(x, p[0])
+        r = add(scale(y, p[1]), r)
+        r = add(scale(z, p[2]), r)
+        return add(w, r)
+
+    def transform_vector3(self, v):
+        x, y, z = (c[:3] for c in self.c[:3])
+        r = scale(x, v[0])
+        r = add(scale(y, v[1]), r)
+        return add(scale(z, v[2]), r)
+
+    def inverse(self):
+        if self._inv is not None:
+            return self._inv
+        (m00, m01, m02, m03), (m10, m11, m12, m13), (m20, m21, m22, m23), (m30, m31, m32, m33) = self.c
+        coef00 = m22 * m33 - m32 * m23; coef02 = m12 * m33 - m32 * m13; coef03 = m12 * m23 - m22 * m13
+        coef04 = m21 * m33 - m31 * m23; coef06 = m11 * m33 - m31 * m13; coef07 = m11 * m23 - m21 * m13
+        coef08 = m21 * m32 - m31 * m22; coef10 = m11 * m32 - m31 * m12; coef11 = m11 * m22 - m21 * m12
+        coef12 = m20 * m33 - m30 * m23; coef14 = m10 * m33 - m30 * m13; coef15 = m10 * m23 - m20 * m13
+        coef16 = m20 * m32 - m30 * m22; coef18 = m10 * m32 - m30 * m12; coef19 = m10 * m22 - m20 * m12
+        coef20 = m20 * m31 - m30 * m21; coef22 = m10 * m31 - m30 * m11; coef23 = m10 * m21 - m20 * m11
+        fac = [(coef00, coef00, coef02, coef03), (coef04, coef04, coef06, coef07), (coef08, coef08, coef10, coef11),
+               (coef12, coef12, coef14, coef15), (coef16, coef16, coef18, coef19), (coef20, coef20, coef22, coef23)]
+        vec = [(m10, m00, m00, m00), (m11, m01, m01, m01), (m12, m02, m02, m02), (m13, m03, m03, m03)]
+        comb = lambda a, fa, b, fb, c, fc: tuple(a[k] * fa[k] - b[k] * fb[k] + c[k] * fc[k] for k in range(4))
+        inv0 = comb(vec[1], fac[0], vec[2], fac[1], vec[3], fac[2])
+        inv1 = comb(vec[0], fac[0], vec[2], fac[3], vec[3], fac[4])
+        inv2 = comb(vec[0], fac[1], vec[1], fac[3], vec[3], fac[5])
+        inv3 = comb(vec[0], fac[2], vec[1], fac[4], vec[2], fac[5])
+        sa, sb = (f32(1), f32(-1), f32(1), f32(-1)), (f32(-1), f32(1), f32(-1), f32(1))
+        cols = [tuple(inv0[k] * sa[k] for k in range(4)), tuple(inv1[k] * sb[k] for k in range(4)),
+                tuple(inv2[k] * sa[k] for k in range(4)), tuple(inv3[k] * sb[k] for k in range(4))]
+        d = [self.c[0][k] * cols[k][0] for k in range(4)]
+        rcp_det = f32(1.0) / (((d[0] + d[1]) + d[2]) + d[3])
+        out = Mat4([0] * 16)
+        out.c = [tuple(x * rcp_det for x in col) for col in cols]
+        self._inv = out
+        return out
+
+
 class Sphere:
     def __init__(self, radius):
         self.radius = f32(radius)
 
-    def support_point(self, direction, pos):  # sphere.rs:21-24
-        d = direction  # transform.inverse().transform_vector3(direction) for a translation
-        return add(pos, scale(d, self.radius / np.sqrt(dot(d, d))))
+    def support_point(self, direction, transform):  # sphere.rs:21-24
+        d = transform.inverse().transform_vector3(direction)
+        return transform.transform_point3(scale(d, self.radius / np.sqrt(dot(d, d))))
 
 
 class Cuboid:
@@ -64,13 +123,46 @@ class Cuboid:
         hx, hy, hz = f32(hx), f32(hy), f32(hz)
         self.corners = [(hx, hy, hz), (-hx, hy, hz), (-hx, -hy, hz), (hx, -hy, hz), (hx, hy, -hz), (-hx, hy, -hz), (-hx, -hy, -hz), (hx, -hy, -hz)]  # cuboid.rs:46-57
 
-    def support_point(self, direction, pos):  # util.rs:7-23 get_max_point: the FIRST maximum wins (strict >)
+    def support_point(self, direction, transform):  # util.rs:7-23 get_max_point: the FIRST maximum wins (strict >)
+        direction = transform.inverse().transform_vector3(direction)
         max_p, max_dot = ZERO, f32(-np.inf)
         for v in self.corners:
             d = dot(v, direction)
             if d > max_dot:
                 max_p, max_dot = v, d
-        return add(pos, max_p)
+        return transform.transform_point3(max_p)
+
+
+class Cylinder:
+    def __init__(self, half_height, radius):
+        self.half_height, self.radius = f32(half_height), f32(radius)
+
+    def support_point(self, direction, transform):  # cylinder.rs:38-61 (Y-axis aligned)
+        result = transform.inverse().transform_vector3(direction)
+        negative = bool(np.signbit(result[1]))               # f32::is_sign_negative (true for -0.0 and negative NaN)
+        result = (result[0], f32(0), result[2])
+        if abs(dot(result, result) - 0) < F32_EPS:
+            result = ZERO
+        else:
+            result = normalize(result)
+            if abs(result[1] - 0) < F32_EPS and abs(result[0] - 0) < F32_EPS and abs(result[2] - 0) < F32_EPS:
+                result = ZERO
+            else:
+                result = scale(result, self.radius)
+        result = (result[0], -self.half_height if negative else self.half_height, result[2])
+        return transform.transform_point3(result)
+
+
+class Capsule:
+    def __init__(self, half_height, radius):
+        self.half_height, self.radius = f32(half_height), f32(radius)
+
+    def support_point(self, direction, transform):  # capsule.rs:41-48
+        direction = transform.inverse().transform_vector3(direction)
+        sy = direction[1]
+        sign = f32(np.nan) if sy != sy else (f32(-1.0) if np.signbit(sy) else f32(1.0))   # f32::signum: +-1 by sign bit, NaN for NaN
+        result = (f32(0), sign * self.half_height, f32(0))
+        return transform.transform_point3(add(result, scale(direction, self.radius / np.sqrt(dot(direction, direction)))))
 
 
 class SupportPoint:
@@ -139,7 +231,9 @@ def reduce_to_closest_feature(simplex, v):  # simplex3d.rs:16-89 -> (origin insi
 
 
 def gjk_intersect(left, lpos, right, rpos, max_iterations=100):  # gjk/mod.rs:74-113 -> simplex or None
-    d = sub(rpos, lpos)  # transform_point3(zero) of a translation is its w axis
+    left_pos = lpos.transform_point3(ZERO)
+    right_pos = rpos.transform_point3(ZERO)
+    d = sub(right_pos, left_pos)
     if is_zero(d):
         d = v3(1, 1, 1)
     a = from_minkowski(left, lpos, right, rpos, d)
@@ -286,7 +380,9 @@ def get_closest_point_to_origin(simplex):
 def distance(left, lpos, right, rpos, max_iterations=100, distance_tolerance=f32(0.000001)):
     """-> ("some", dp - d0) | ("none",) colliding | ("max_iterations",) | ("panic",)"""
     near_zero = lambda d: abs(d[0] - 0) < F32_EPSILON and abs(d[1] - 0) < F32_EPSILON and abs(d[2] - 0) < F32_EPSILON
-    d = sub(rpos, lpos)
+    right_pos = rpos.transform_point3(ZERO)
+    left_pos = lpos.transform_point3(ZERO)
+    d = sub(right_pos, left_pos)
     if near_zero(d):
         d = v3(1, 1, 1)
     simplex = [from_minkowski(left, lpos, right, rpos, d), from_minkowski(left, lpos, right, rpos, neg(d))]

@@ -650,7 +650,7 @@ def test_oracle_gjk_epa_equals_a_literal_python_replay_of_the_reference(oracle):
     from tests import replay_gjk_epa as R
     import bam3d_b200._ffi as F
     c = R.Cuboid(5, 5, 5)
-    normal, depth, point, _, _ = R.intersection(c, R.v3(15, 0, 0), c, R.v3(7, 2, 0))     # gjk/mod.rs:585-596
+    normal, depth, point, _, _ = R.intersection(c, R.Mat4.from_translation((15, 0, 0)), c, R.Mat4.from_translation((7, 2, 0)))     # gjk/mod.rs:585-596
     assert [float(x) for x in normal] == [-1.0, 0.0, 0.0] and float(depth) == 2.0
     assert [np.float32(x) for x in point] == [np.float32(10.0), np.float32(1.0000002), np.float32(4.999999)]
     rng = np.random.default_rng(20240611)
@@ -683,7 +683,7 @@ def test_oracle_gjk_epa_equals_a_literal_python_replay_of_the_reference(oracle):
     oc, ohit, ost = oracle.contact(scene, strategy=0, nthreads=4)
     hits = 0
     for k in range(n):
-        r = R.intersection(prims[2 * k], tuple(pos[2 * k]), prims[2 * k + 1], tuple(pos[2 * k + 1]))
+        r = R.intersection(prims[2 * k], R.Mat4(xform[2 * k]), prims[2 * k + 1], R.Mat4(xform[2 * k + 1]))
         assert (r is not None) == (ost[k] == 0), f"pair {k}: hit/miss"
         if r is None:
             continue
@@ -726,9 +726,53 @@ def test_oracle_distance_equals_a_literal_python_replay_of_the_reference(oracle)
     status_of = {"some": F.STATUS_OK, "none": F.STATUS_MISS, "max_iterations": F.STATUS_MAX_ITER, "panic": F.STATUS_REF_PANIC}
     seen = set()
     for k in range(n):
-        r = R.distance(prims[2 * k], tuple(pos[2 * k]), prims[2 * k + 1], tuple(pos[2 * k + 1]))
+        r = R.distance(prims[2 * k], R.Mat4(xform[2 * k]), prims[2 * k + 1], R.Mat4(xform[2 * k + 1]))
         assert status_of[r[0]] == st[k], f"pair {k}: replay {r[0]}, oracle status {st[k]}"
         if r[0] == "some":
             assert np.float32(r[1]).tobytes() == ref[k].tobytes(), f"pair {k}: {r[1]} vs {ref[k]}"
         seen.add(r[0])
     assert seen == {"some", "none", "max_iterations", "panic"}
+
+
+def _replay_prim(kind, p):
+    from tests import replay_gjk_epa as R
+    import bam3d_b200._ffi as F
+    return {F.KIND_SPHERE: lambda: R.Sphere(p[0]), F.KIND_CUBOID: lambda: R.Cuboid(p[0], p[1], p[2]),
+            F.KIND_CYLINDER: lambda: R.Cylinder(p[0], p[1]), F.KIND_CAPSULE: lambda: R.Capsule(p[0], p[1])}[int(kind)]()
+
+
+def test_python_replay_on_rotated_mixed_pairs_and_pinched_polytopes(oracle):
+    """The literal Python replay (tests/replay_gjk_epa.py, with glam's Mat4 inverse / transforms restated) against the C++ oracle on
+    (1) 2000 pairs of the C2 scene — rotated Spheres, Cuboids, Cylinders — and (2) pinched polytopes of that scene (tests/pinched.py):
+    the replay, too, runs them to the 100-trip cap and ends with 1034 / 1060 / 1924 / 6892 / 10382 faces and the oracle's contact
+    bit for bit. (Run by hand once more on the two largest: 35 530 faces in 15 s and 121 962 faces in 159 s of Python, both equal.)
+    So two restatements of epa3d.rs:121-149 written at different times in different languages agree that the reference's face list
+    grows like this, which is what the device's third EPA tier reproduces."""
+    from bam3d_b200 import scenes
+    from tests import replay_gjk_epa as R
+    import warnings
+    sc = scenes.mixed_pairs(2000, s=1.5)
+    oc, _, ost = oracle.contact(sc, strategy=0, nthreads=4)
+    hits = 0
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")                       # f32 overflow / invalid on degenerate faces: the reference computes them too
+        for k, (a, b) in enumerate(sc["pairs"]):
+            r = R.intersection(_replay_prim(sc["kind"][a], sc["params"][a]), R.Mat4(sc["xform"][a]),
+                               _replay_prim(sc["kind"][b], sc["params"][b]), R.Mat4(sc["xform"][b]))
+            assert (r is not None) == (ost[k] == 0), f"pair {k}: hit/miss"
+            if r is not None:
+                hits += 1
+                got = np.array(list(r[0]) + [r[1]] + list(r[2]), dtype=np.float32)
+                assert got.tobytes() == oc[k, :7].tobytes(), f"pair {k}: {got} vs {oc[k, :7]}"
+        assert hits > 800
+        idx = (127779, 69343, 75000, 62559, 87554)
+        faces = (1034, 1060, 1924, 6892, 10382)
+        pin = pinched_scene(idx)
+        want, wst, mf, it, _ = oracle.contact_face_limit(pin, 1 << 18, nthreads=4)
+        assert (wst == 0).all() and tuple(int(x) for x in mf) == faces
+        for k, (a, b) in enumerate(pin["pairs"]):
+            r = R.intersection(_replay_prim(pin["kind"][a], pin["params"][a]), R.Mat4(pin["xform"][a]),
+                               _replay_prim(pin["kind"][b], pin["params"][b]), R.Mat4(pin["xform"][b]))
+            assert r is not None and r[3] == 100 and r[4] == faces[k], (idx[k], r[3], r[4])
+            got = np.array(list(r[0]) + [r[1]] + list(r[2]), dtype=np.float32)
+            assert got.tobytes() == want[k, :7].tobytes(), f"pinched pair {idx[k]}"
