@@ -6,7 +6,9 @@
 // Pinning: the reference cannot be compiled here (no cargo/rustc), so this restatement is pinned by the
 // reference's own known-answer tests, ported bit-exactly in oracle/kat_main.cpp. Paths with NO reference test
 // (rotated / mixed-shape GJK+EPA pairs, Particle/Primitive3 dispatch, intersection_complex*) are
-// "parity unpinned": only this restatement stands behind them.
+// "parity unpinned": no reference value stands behind them. For GJK::intersection / GJK::distance on Sphere, Cuboid, Cylinder and
+// Capsule pairs (rotated ones and the pinched EPA polytopes included) this restatement is additionally checked bit for bit against a
+// second one written independently from the Rust source (tests/replay_gjk_epa.py, tests/test_host_cpu.py).
 //
 // Rust panics on this path (simplex3d.rs:134 unwrap, :138-142 assert!) are mapped to Status::WouldPanic; the
 // uncapped TOI loop (gjk/mod.rs:166) is capped at `toi_iteration_cap` and reported as Status::MaxIter.
