@@ -401,3 +401,43 @@ def distance(left, lpos, right, rpos, max_iterations=100, distance_tolerance=f32
     except ReferencePanic:
         return ("panic",)
     return ("max_iterations",)
+
+
+# ---- GJK::intersection_time_of_impact (gjk/mod.rs:130-217), without the contact point (that goes through glam's quaternion
+# decomposition in translation_interpolate, traits.rs:180-190, which is not restated here) ----
+def time_of_impact(left, l0, l1, right, r0, r1, continuous_tolerance=f32(0.000001), cap=100):
+    """-> ("some", lambda, normal, depth) | ("none",) | ("panic",) | ("cap",): the reference's while loop has no bound (the device and
+    the oracle stop after `cap` trips and report STATUS_MAX_ITER)"""
+    left_lin_vel = sub(l1.transform_point3(ZERO), l0.transform_point3(ZERO))
+    right_lin_vel = sub(r1.transform_point3(ZERO), r0.transform_point3(ZERO))
+    ray = sub(right_lin_vel, left_lin_vel)
+    lam = f32(0)
+    normal, ray_origin = ZERO, ZERO
+    simplex = []
+    p = from_minkowski(left, l0, right, r0, neg(ray))
+    v = p.v
+    trips = 0
+    try:
+        while dot(v, v) > continuous_tolerance:
+            if trips >= cap:
+                return ("cap",)
+            trips += 1
+            p = from_minkowski(left, l0, right, r0, neg(v))
+            vp, vr = dot(v, p.v), dot(v, ray)
+            if vp > lam * vr:
+                if vr > 0:
+                    lam = vp / vr
+                    if lam > 1:
+                        return ("none",)
+                    ray_origin = scale(ray, lam)
+                    simplex.clear()
+                    normal = neg(v)
+                else:
+                    return ("none",)
+            simplex.append(SupportPoint(sub(p.v, ray_origin), p.sup_a))
+            v = get_closest_point_to_origin(simplex)
+    except ReferencePanic:
+        return ("panic",)
+    if dot(v, v) <= continuous_tolerance:
+        return ("some", lam, neg(normalize(normal)), np.sqrt(dot(v, v)))
+    return ("none",)

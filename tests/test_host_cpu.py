@@ -776,3 +776,30 @@ def test_python_replay_on_rotated_mixed_pairs_and_pinched_polytopes(oracle):
             assert r is not None and r[3] == 100 and r[4] == faces[k], (idx[k], r[3], r[4])
             got = np.array(list(r[0]) + [r[1]] + list(r[2]), dtype=np.float32)
             assert got.tobytes() == want[k, :7].tobytes(), f"pinched pair {idx[k]}"
+
+
+def test_python_replay_of_time_of_impact(oracle):
+    """GJK::intersection_time_of_impact (gjk/mod.rs:130-217) replayed in Python against the C++ oracle on 3000 rotated pairs of the
+    time-of-impact scene moving between two transform sets: outcome class, time of impact, normal (-normalize(normal): NaN when the
+    shapes already overlap at t = 0, reproduced) and depth, bit for bit. (The contact point passes through glam's quaternion
+    decomposition in translation_interpolate, which the replay does not restate.)"""
+    from bam3d_b200 import scenes
+    from tests import replay_gjk_epa as R
+    import bam3d_b200._ffi as F
+    import warnings
+    sc = scenes.mixed_pairs(3000, s=4.0)
+    x1 = scenes.end_transforms(sc)
+    oc, _, ost = oracle.toi(sc, x1, nthreads=4)
+    status_of = {"some": F.STATUS_OK, "none": F.STATUS_MISS, "cap": F.STATUS_MAX_ITER, "panic": F.STATUS_REF_PANIC}
+    hits = 0
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for k, (a, b) in enumerate(sc["pairs"]):
+            r = R.time_of_impact(_replay_prim(sc["kind"][a], sc["params"][a]), R.Mat4(sc["xform"][a]), R.Mat4(x1[a]),
+                                 _replay_prim(sc["kind"][b], sc["params"][b]), R.Mat4(sc["xform"][b]), R.Mat4(x1[b]))
+            assert status_of[r[0]] == ost[k], f"pair {k}: replay {r[0]}, oracle status {ost[k]}"
+            if r[0] == "some":
+                hits += 1
+                got = np.array(list(r[2]) + [r[3]], dtype=np.float32)
+                assert got.tobytes() == oc[k, :4].tobytes() and np.float32(r[1]).tobytes() == oc[k, 7].tobytes(), f"pair {k}"
+    assert hits > 150
