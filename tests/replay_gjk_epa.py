@@ -441,3 +441,59 @@ def time_of_impact(left, l0, l1, right, r0, r1, continuous_tolerance=f32(0.00000
     if dot(v, v) <= continuous_tolerance:
         return ("some", lam, neg(normalize(normal)), np.sqrt(dot(v, v)))
     return ("none",)
+
+
+# ---- compound shapes (gjk/mod.rs:362-456, 478-523): every primitive x primitive pair under mul_mat4-composed transforms, then Rust's
+# Iterator::max_by (the LAST maximum) with partial_cmp().unwrap() / min_by (the FIRST minimum) with unwrap_or(Equal) ----
+def mul_mat4(a, b):
+    """glam 0.8 Mat4::mul_mat4 (a * b): column j = a.x_axis * b[j].x; a.y_axis * b[j].y + r; a.z_axis * b[j].z + r; a.w_axis * b[j].w + r"""
+    cols = []
+    for v in b.c:
+        r = tuple(a.c[0][k] * v[0] for k in range(4))
+        for ax in (1, 2, 3):
+            r = tuple(a.c[ax][k] * v[ax] + r[k] for k in range(4))
+        cols.extend(r)
+    return Mat4(cols)
+
+
+def intersection_complex(left, lt, right, rt, collision_only=False):
+    """left / right: lists of (primitive, local Mat4). -> None | "hit" (CollisionOnly) | (normal, depth, point) | raises ReferencePanic"""
+    contacts = []
+    for lp, ll in left:
+        ltc = mul_mat4(lt, ll)
+        for rp, rl in right:
+            rtc = mul_mat4(rt, rl)
+            if collision_only:
+                if gjk_intersect(lp, ltc, rp, rtc) is not None:
+                    return "hit"
+                continue
+            c = intersection(lp, ltc, rp, rtc)
+            if c is not None:
+                contacts.append(c[:3])
+    best = None
+    for c in contacts:                                   # max_by: a later element that compares Equal or Greater replaces the current one
+        if best is not None and (c[1] != c[1] or best[1] != best[1]):
+            raise ReferencePanic("partial_cmp(NaN).unwrap()")
+        if best is None or not (c[1] < best[1]):
+            best = c
+    return best
+
+
+def distance_complex(left, lt, right, rt):
+    """-> None as soon as one primitive pair returns None, else the f32::min of all (NaN-ignoring, as f32::min is)"""
+    best = None
+    for lp, ll in left:
+        ltc = mul_mat4(lt, ll)
+        for rp, rl in right:
+            rtc = mul_mat4(rt, rl)
+            r = distance(lp, ltc, rp, rtc)
+            if r[0] == "panic":
+                raise ReferencePanic("distance")
+            if r[0] != "some":
+                return None
+            d = r[1]
+            if best is None:
+                best = d
+            else:                                           # distance.min(min_distance): Rust f32::min returns the other operand for a NaN
+                best = best if d != d else (d if best != best else (d if d < best else best))
+    return best
