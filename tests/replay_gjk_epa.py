@@ -2,8 +2,8 @@
 GJK::intersect (algorithm/minkowski/gjk/mod.rs:74-113), SimplexProcessor3::reduce_to_closest_feature + check_side
 (gjk/simplex/simplex3d.rs:16-89,160-205), EPA3::process with Polytope / Face / remove_or_add_edge (epa/epa3d.rs:16-190),
 contact() / point() (:69-94), barycentric_vector (primitive/util.rs:44-60), SupportPoint::from_minkowski (minkowski/mod.rs:33-51)
-and the Sphere / Cuboid / Cylinder / Capsule support functions (primitive/sphere.rs:21-24, cuboid.rs:46-63, util.rs:7-23,
-cylinder.rs:38-61, capsule.rs:41-48) — written from the Rust
+and the Particle / Quad / Sphere / Cuboid / Cylinder / Capsule support functions (primitive3.rs:116-131, quad.rs:45-59,
+sphere.rs:21-24, cuboid.rs:46-63, util.rs:7-23, cylinder.rs:38-61, capsule.rs:41-48) — written from the Rust
 source with Python lists for the SmallVec / Vec containers (remove, swap, swap_remove, position + remove), one f32 operation at a
 time (numpy.float32 scalars: every product and sum is rounded separately, as glam's scalar-math does without FMA).
 Transforms are full Mat4s: glam 0.8's scalar Mat4::inverse (cofactor expansion with its sign vectors), transform_vector3 and
@@ -131,6 +131,19 @@ class Cuboid:
             if d > max_dot:
                 max_p, max_dot = v, d
         return transform.transform_point3(max_p)
+
+
+class Quad:
+    def __init__(self, hx, hy):  # half dimensions
+        hx, hy = f32(hx), f32(hy)
+        self.corners = [(hx, hy, f32(0)), (-hx, hy, f32(0)), (-hx, -hy, f32(0)), (hx, -hy, f32(0))]  # quad.rs:45-52
+
+    support_point = Cuboid.support_point  # quad.rs:55-59: get_max_point over its corners
+
+
+class Particle:
+    def support_point(self, direction, transform):  # primitive3.rs:119 / particle.rs: the transformed origin
+        return transform.transform_point3(ZERO)
 
 
 class Cylinder:
