@@ -141,6 +141,13 @@ class Quad:
     support_point = Cuboid.support_point  # quad.rs:55-59: get_max_point over its corners
 
 
+class ConvexPolyhedron:
+    def __init__(self, vertices):  # ConvexPolyhedron::new (VertexOnly mode): brute-force support, polyhedron.rs:135-150, 342-355
+        self.corners = [v3(*v) for v in vertices]
+
+    support_point = Cuboid.support_point  # the same fold: first maximum over the vertices in their stored order
+
+
 class Particle:
     def support_point(self, direction, transform):  # primitive3.rs:119 / particle.rs: the transformed origin
         return transform.transform_point3(ZERO)

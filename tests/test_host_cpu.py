@@ -859,3 +859,27 @@ def test_python_replay_of_compound_shapes(oracle):
                 assert np.float32(d).tobytes() == od[k, 3].tobytes(), f"pair {k}: distance"
             seen.add((int(ost[k]), int(odst[k])))
     assert {s for s, _ in seen} >= {0, 1} and {s for _, s in seen} >= {0, 1, 3}
+
+
+def test_python_replay_on_polyhedron_pairs(oracle):
+    """ConvexPolyhedron::new (VertexOnly: the brute-force first-maximum vertex, polyhedron.rs:135-150) through the Python replay's GJK +
+    EPA against the C++ oracle on 800 rotated pairs of 64-256-vertex meshes (the C3 scene's library generator): bit for bit."""
+    from bam3d_b200 import scenes
+    from tests import replay_gjk_epa as R
+    import warnings
+    lib = scenes.mesh_library(32)
+    ps = scenes.polyhedron_pairs(800, library=lib)
+    verts, offs = np.asarray(lib[0]).reshape(-1, 3), np.asarray(lib[1])
+    meshes = [R.ConvexPolyhedron(verts[offs[m]:offs[m + 1]]) for m in range(len(offs) - 1)]
+    oc, _, ost = oracle.contact(ps, strategy=0, nthreads=4)
+    hits = 0
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for k, (a, b) in enumerate(ps["pairs"]):
+            r = R.intersection(meshes[ps["mesh_id"][a]], R.Mat4(ps["xform"][a]), meshes[ps["mesh_id"][b]], R.Mat4(ps["xform"][b]))
+            assert (r is not None) == (ost[k] == 0), f"pair {k}: hit/miss"
+            if r is not None:
+                hits += 1
+                got = np.array(list(r[0]) + [r[1]] + list(r[2]), dtype=np.float32)
+                assert got.tobytes() == oc[k, :7].tobytes(), f"pair {k}"
+    assert hits > 200
