@@ -148,6 +148,61 @@ class ConvexPolyhedron:
     support_point = Cuboid.support_point  # the same fold: first maximum over the vertices in their stored order
 
 
+class ConvexPolyhedronWithFaces:
+    """ConvexPolyhedron::new_with_faces (HalfEdge mode): build_half_edges (polyhedron.rs:246-340) and hill_climb_support_point
+    (:153-183). Only the links the climb follows are kept: per vertex its first outgoing edge, per edge target / twin / next."""
+
+    def __init__(self, vertices, faces):
+        self.pos = [v3(*v) for v in vertices]
+        n = len(self.pos)
+        self.vertex_edge, vertex_ready = [0] * n, [False] * n
+        self.target, self.twin, self.next_edge = [], [], []
+        edge_map = {}
+        for a, b, c in faces:
+            fv = (int(a), int(b), int(c))
+            face_edges = [0, 0, 0]
+            for j in range(3):
+                i = 2 if j == 0 else j - 1
+                v0, v1 = fv[i], fv[j]
+                if (v0, v1) in edge_map:
+                    e01 = edge_map[(v0, v1)]
+                    e10 = self.twin[e01]
+                else:
+                    e01, e10 = len(self.target), len(self.target) + 1
+                    self.target += [v1, v0]
+                    self.twin += [e10, e01]
+                    self.next_edge += [0, 0]
+                edge_map[(v0, v1)] = e01
+                edge_map[(v1, v0)] = e10
+                if not vertex_ready[v0]:
+                    self.vertex_edge[v0] = e01
+                    vertex_ready[v0] = True
+                face_edges[i] = e01
+            for j in range(3):
+                i = 2 if j == 0 else j - 1
+                self.next_edge[face_edges[i]] = face_edges[j]
+
+    def support_point(self, direction, transform):
+        d = transform.inverse().transform_vector3(direction)
+        best_index = 0
+        best_dot = dot(self.pos[best_index], d)
+        while True:
+            previous_best_dot = best_dot
+            edge_index = self.vertex_edge[best_index]
+            start_edge_index = edge_index
+            while True:
+                vertex_index = self.target[edge_index]
+                dt = dot(self.pos[vertex_index], d)
+                if dt > best_dot:
+                    best_index, best_dot = vertex_index, dt
+                edge_index = self.next_edge[self.twin[edge_index]]
+                if start_edge_index == edge_index:
+                    break
+            if abs(best_dot - previous_best_dot) < F32_EPS:
+                break
+        return transform.transform_point3(self.pos[best_index])
+
+
 class Particle:
     def support_point(self, direction, transform):  # primitive3.rs:119 / particle.rs: the transformed origin
         return transform.transform_point3(ZERO)
